@@ -1,0 +1,97 @@
+"""ctypes binding of libmtrl_b200.so (the C-ABI declared in include/mtrl_b200.h).
+
+There is no CPU fallback: if the library is missing or a call fails, the error is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+_LIB_PATH = _PKG / "libmtrl_b200.so"
+_lib = None
+
+
+class MtrlError(RuntimeError):
+    pass
+
+
+class GemmProblem(C.Structure):
+    _fields_ = [
+        ("A", C.c_void_p), ("lda", C.c_longlong), ("a_major", C.c_int),
+        ("B", C.c_void_p), ("ldb", C.c_longlong), ("b_major", C.c_int),
+        ("D", C.c_void_p), ("ldd", C.c_longlong),
+        ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
+        ("block_n", C.c_int), ("k_splits", C.c_int), ("epilogue", C.c_int),
+        ("bias", C.c_void_p), ("mask", C.c_void_p), ("ldmask", C.c_longlong),
+    ]
+
+
+EPI_STORE, EPI_BIAS_RELU, EPI_RELU_MASK, EPI_ATOMIC_ADD, EPI_STORE_TF32 = range(5)
+
+
+def lib() -> C.CDLL:
+    """Load (building first if the .so is absent and nvcc is present) and return the library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists() or os.environ.get("MTRL_B200_REBUILD"):
+        from . import build as _build
+
+        _build.build_library()
+    if not _LIB_PATH.exists():
+        raise MtrlError(f"{_LIB_PATH} is missing: the CUDA extension was not built; there is no CPU fallback")
+    l = C.CDLL(str(_LIB_PATH), mode=C.RTLD_GLOBAL)
+    l.mtrl_last_error.restype = C.c_char_p
+    l.mtrl_abi_version.restype = C.c_int
+    _declare(l)
+    _lib = l
+    return l
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise MtrlError(f"mtrl_b200 error {rc}: {lib().mtrl_last_error().decode()}")
+
+
+def _declare(l: C.CDLL) -> None:
+    vp, i, ll = C.c_void_p, C.c_int, C.c_longlong
+    l.mtrl_gemm_plan_create.argtypes = [C.POINTER(vp), C.POINTER(GemmProblem), i]
+    l.mtrl_gemm_plan_run.argtypes = [vp, vp]
+    l.mtrl_gemm_plan_units.argtypes = [vp]
+    l.mtrl_gemm_plan_destroy.argtypes = [vp]
+    l.mtrl_gemm_plan_destroy.restype = None
+    for name, spec in _EXTRA_DECLS.items():
+        fn = getattr(l, name)
+        fn.argtypes = spec[0]
+        fn.restype = spec[1] if len(spec) > 1 else C.c_int
+
+
+# Filled in by the modules that own the corresponding C entry points (keeps this file small).
+_EXTRA_DECLS: dict = {}
+
+
+def current_stream_ptr() -> int:
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream
+
+
+class GemmPlan:
+    """One persistent grouped launch; holds the encoded TMA descriptors."""
+
+    def __init__(self, problems: list[GemmProblem]):
+        arr = (GemmProblem * len(problems))(*problems)
+        h = C.c_void_p()
+        check(lib().mtrl_gemm_plan_create(C.byref(h), arr, len(problems)))
+        self._h = h
+        self.units = lib().mtrl_gemm_plan_units(h)
+
+    def run(self, stream: int | None = None) -> None:
+        check(lib().mtrl_gemm_plan_run(self._h, C.c_void_p(stream if stream is not None else current_stream_ptr())))
+
+    def __del__(self):
+        if getattr(self, "_h", None) is not None and _lib is not None:
+            _lib.mtrl_gemm_plan_destroy(self._h)
+            self._h = None
