@@ -1,0 +1,112 @@
+"""CPU checks of the update oracle: known parameter count, head-selection equivalence, fp32 vs
+fp64 agreement, closed-form VJPs of SURVEY Appendix A, optimiser algebra, ordering facts."""
+import math
+
+import pytest
+import torch
+
+from oracle import mtsac_oracle as O
+
+
+def small_cfg(**kw):
+    base = dict(num_tasks=3, obs_dim=7 + 3, action_dim=2, width=16, depth=3)
+    base.update(kw)
+    return O.OracleConfig(**base)
+
+
+def test_param_count_kat():
+    """plots/get_data.py:51-53 hard-codes 370_000 for mt10_mtmhsac; the exact architecture count is
+    372 880 = 49*400+400 + 2*(400^2+400) + 10*(400*8+8)."""
+    cfg = O.OracleConfig(num_tasks=10, obs_dim=49, action_dim=4, width=400)
+    st = O.init_state(cfg)
+    assert O.num_params(st.actor) == 372_880
+    assert O.num_params(st.critic) == 692_820  # SURVEY 8d table, two members
+
+
+def test_all_heads_equals_selected_head():
+    cfg = small_cfg()
+    st = O.init_state(cfg, dtype=torch.float64)
+    batch, ec, ea = O.synthetic_batch(cfg, per_task=5, dtype=torch.float64)
+    s1, l1 = O.mtsac_update(st.clone(), batch, ec, ea, cfg, all_heads=False)
+    s2, l2 = O.mtsac_update(st.clone(), batch, ec, ea, cfg, all_heads=True)
+    for k in O.LOG_KEYS:
+        assert torch.allclose(l1[k], l2[k], rtol=1e-12, atol=1e-14), k
+    for a, b in zip(O.tree_leaves(s1.critic), O.tree_leaves(s2.critic)):
+        assert torch.allclose(a, b, rtol=1e-12, atol=1e-14)
+
+
+def test_fp32_tracks_fp64():
+    cfg = small_cfg(width=32)
+    st64 = O.init_state(cfg, dtype=torch.float64)
+    # make the fp64 state exactly the fp32 one
+    st32 = O.init_state(cfg, dtype=torch.float32)
+    st64 = st32.to(torch.float64)
+    b32, ec32, ea32 = O.synthetic_batch(cfg, per_task=8, dtype=torch.float32)
+    b64 = tuple(t.double() for t in b32)
+    n32, l32 = O.mtsac_update(st32, b32, ec32, ea32, cfg)
+    n64, l64 = O.mtsac_update(st64, b64, ec32.double(), ea32.double(), cfg)
+    for k in O.LOG_KEYS:
+        assert abs(float(l32[k]) - float(l64[k])) <= 1e-4 * max(1e-6, abs(float(l64[k]))), k
+    for a, b in zip(O.tree_leaves(n32.actor), O.tree_leaves(n64.actor)):
+        assert (a.double() - b).norm() <= 1e-4 * b.norm()
+
+
+def test_tanh_gaussian_vjp_closed_form():
+    """dlogp/dx = 2 tanh(x), dx/dmu = 1, dx/dl = sigma*eps, dlogp/dl|direct = -1,
+    da/dx = 1 - a^2.  These are the formulas the CUDA loss kernel implements."""
+    torch.manual_seed(0)
+    mu = torch.randn(6, 4, dtype=torch.float64, requires_grad=True)
+    ls = (torch.randn(6, 4, dtype=torch.float64) * 0.5).requires_grad_(True)
+    eps = torch.randn(6, 4, dtype=torch.float64)
+    std = torch.exp(ls)
+    x = mu + std * eps
+    a = torch.tanh(x)
+    logp = (-0.5 * eps**2 - 0.5 * math.log(2 * math.pi) - ls).sum(-1) - (2 * (math.log(2) - x - torch.nn.functional.softplus(-2 * x))).sum(-1)
+    ga = torch.randn(6, 4, dtype=torch.float64)
+    gl = torch.randn(6, dtype=torch.float64)
+    (a * ga).sum().add((logp * gl).sum()).backward()
+    gx = ga * (1 - a.detach() ** 2) + gl[:, None] * 2 * a.detach()
+    assert torch.allclose(mu.grad, gx, rtol=1e-10, atol=1e-12)
+    assert torch.allclose(ls.grad, gx * std.detach() * eps - gl[:, None], rtol=1e-10, atol=1e-12)
+
+
+def test_adam_first_step_and_clip():
+    p = {"w": torch.tensor([1.0, -2.0, 3.0], dtype=torch.float64)}
+    g = {"w": torch.tensor([3.0, 4.0, 0.0], dtype=torch.float64)}  # norm 5 -> clipped to 1
+    opt = {"m": {"w": torch.zeros(3, dtype=torch.float64)}, "v": {"w": torch.zeros(3, dtype=torch.float64)}, "count": 0}
+    newp, o2 = O.adam_step(p, g, opt, lr=3e-4, eps=1e-5, b1=0.9, b2=0.999, max_norm=1.0)
+    gc = torch.tensor([0.6, 0.8, 0.0], dtype=torch.float64)
+    exp = p["w"] - 3e-4 * gc / (gc.abs() + 1e-5)
+    assert torch.allclose(newp["w"], exp, rtol=1e-12)
+    assert o2["count"] == 1
+    # below the threshold the gradient is untouched
+    newp2, _ = O.adam_step(p, {"w": gc * 0.5}, opt, 3e-4, 1e-5, 0.9, 0.999, 1.0)
+    assert torch.allclose(newp2["w"], p["w"] - 3e-4 * (gc * 0.5) / ((gc * 0.5).abs() + 1e-5), rtol=1e-12)
+
+
+def test_update_ordering_facts():
+    """mtsac.py: target uses the NEW critic (:607-613); alpha step uses log-probs of the OLD actor."""
+    cfg = small_cfg()
+    st = O.init_state(cfg, dtype=torch.float64)
+    batch, ec, ea = O.synthetic_batch(cfg, per_task=4, dtype=torch.float64)
+    new, logs, grads, aux = O.mtsac_update(st.clone(), batch, ec, ea, cfg, return_grads=True)
+    for n, t_old, t_new in zip(O.tree_leaves(new.critic), O.tree_leaves(st.critic_target), O.tree_leaves(new.critic_target)):
+        assert torch.allclose(t_new, cfg.tau * n + (1 - cfg.tau) * t_old, rtol=1e-12)
+    obs = batch[0]
+    task = obs[:, -cfg.num_tasks:].argmax(1)
+    _, logp_old = O.actor_sample_and_log_prob(st.actor, obs, ea, cfg)
+    g = torch.zeros(cfg.num_tasks, dtype=torch.float64)
+    g.index_add_(0, task, -(logp_old + cfg.target_entropy) / obs.shape[0])
+    assert torch.allclose(grads["alpha"], g, rtol=1e-10)
+    assert set(logs) == set(O.LOG_KEYS)
+
+
+def test_input_state_not_mutated():
+    cfg = small_cfg()
+    st = O.init_state(cfg, dtype=torch.float64)
+    ref = st.clone()
+    batch, ec, ea = O.synthetic_batch(cfg, per_task=4, dtype=torch.float64)
+    O.mtsac_update(st, batch, ec, ea, cfg)
+    assert st.opt["critic"]["count"] == 0
+    for a, b in zip(O.tree_leaves(st.critic), O.tree_leaves(ref.critic)):
+        assert torch.equal(a, b)
