@@ -63,6 +63,38 @@ int mtrl_gemm_plan_run(mtrl_gemm_plan_t* plan, void* stream);
 int mtrl_gemm_plan_units(const mtrl_gemm_plan_t* plan);
 void mtrl_gemm_plan_destroy(mtrl_gemm_plan_t* plan);
 
+/* ------------------------------------------------------------------------------------------
+ * Replay sampler.  Replaces MultiTaskReplayBuffer.add / .sample
+ * (mtrl/rl/buffers.py:426-474, 494-549) and the np.random.Generator(PCG64) it draws from
+ * (buffers.py:260, 523-527).  Storage arrays are device fp32 (capacity, T, dim), reference layout
+ * (buffers.py:293-306), owned by the caller.  Array order everywhere: observations, actions,
+ * next_observations, dones, rewards (= ReplayBufferSamples, mtrl/types.py:30-35).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct mtrl_sampler mtrl_sampler_t;
+
+int mtrl_sampler_create(mtrl_sampler_t** out, int capacity, int num_tasks, int obs_dim, int act_dim,
+                        float* obs, float* actions, float* next_obs, float* dones, float* rewards);
+void mtrl_sampler_destroy(mtrl_sampler_t* s);
+/* state4 = {state_hi, state_lo, inc_hi, inc_lo}: numpy's PCG64 `bit_generator.state` dict split in
+ * 64-bit words; has_uint32/uinteger are the buffered 32-bit half.  Both calls synchronise `stream`. */
+int mtrl_sampler_set_state(mtrl_sampler_t* s, const uint64_t* state4, uint32_t has_uint32, uint32_t uinteger,
+                           void* stream);
+int mtrl_sampler_get_state(mtrl_sampler_t* s, uint64_t* state4, uint32_t* has_uint32, uint32_t* uinteger,
+                           void* stream);
+/* buffers.py:453-457.  Sources are (T, dim) fp32, host or device. */
+int mtrl_sampler_add(mtrl_sampler_t* s, int pos, const float* obs, const float* actions, const float* next_obs,
+                     const float* dones, const float* rewards, void* stream);
+/* buffers.py:520-549: one shared index vector of n_per_task draws in [0, max(fill, n_per_task)); outputs
+ * are device (n_per_task*T, dim), row i <-> (sample i / T, task i % T).  norm_mode 1 applies
+ * rewards' = (double(r) - shift[t]) / den[t] (buffers.py:531-538); shift/den are device double[T]. */
+int mtrl_sampler_sample(mtrl_sampler_t* s, int fill, int n_per_task, long long* idx_out, float* obs_out,
+                        float* actions_out, float* next_obs_out, float* dones_out, float* rewards_out,
+                        int norm_mode, const double* shift, const double* den, void* stream);
+/* buffers.py:496-519: counts is a host int[T]; independent draws per task, rows concatenated by task. */
+int mtrl_sampler_sample_per_task(mtrl_sampler_t* s, int fill, const int* counts, float* obs_out,
+                                 float* actions_out, float* next_obs_out, float* dones_out, float* rewards_out,
+                                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif
