@@ -95,6 +95,120 @@ int mtrl_sampler_sample_per_task(mtrl_sampler_t* s, int fill, const int* counts,
                                  float* actions_out, float* next_obs_out, float* dones_out, float* rewards_out,
                                  void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * MT-SAC update.  Replaces MTSAC.update / _update_inner (mtrl/rl/algorithms/mtsac.py:1173-1251):
+ * update_critic (MSE branch, :513-621), update_actor (:623-711), update_alpha (:713-731) on
+ * MultiHeadNetwork actor / critic ensemble (mtrl/nn/multi_head.py:21-68, mtrl/rl/networks.py:21-67,
+ * 208-222), optax clip_by_global_norm + adam (mtrl/config/optim.py:26-43) and the Polyak target
+ * update (mtsac.py:607-613).
+ * ------------------------------------------------------------------------------------------ */
+#define MTRL_MAX_DEPTH 4
+
+typedef struct mtrl_sac_config {
+  int num_tasks;        /* T: width of the one-hot block that ends every observation             */
+  int task_begin;       /* first task owned by this handle (0 on one GPU)                         */
+  int num_local_tasks;  /* tasks owned by this handle (T on one GPU)                              */
+  int obs_dim;          /* observation length including the one-hot (39 + T for Meta-World)       */
+  int action_dim;       /* 1..8                                                                   */
+  int width;            /* hidden width, multiple of 4                                            */
+  int depth;            /* trunk layers, 1..MTRL_MAX_DEPTH (reference default 3)                  */
+  int num_critics;      /* ensemble size, 1..4 (reference default 2)                              */
+  int max_rows;         /* packed-row capacity: >= sum_t roundup(rows of task t, 128); mult of 128 */
+  int max_batch;        /* largest batch (rows) one update call may pass                          */
+  float gamma, tau;
+  float actor_lr, critic_lr, alpha_lr;
+  float adam_b1, adam_b2, adam_eps;
+  float actor_max_grad_norm, critic_max_grad_norm, alpha_max_grad_norm; /* <= 0: no clipping      */
+  float log_std_min, log_std_max;
+  float target_entropy;
+  int clip_q;           /* AlgorithmConfig.clip: clamp target and prediction to +-5000            */
+  int use_task_weights; /* MTSACConfig.use_task_weights                                           */
+  unsigned long long noise_seed; /* Philox seed used when eps_c / eps_a are NULL                  */
+} mtrl_sac_config_t;
+
+/* Flat fp32 layout of one network (all ensemble members).  [member trunks | 32 reduction slots |
+ * member heads]; the trunk prefix (plus the slots) is what ranks all-reduce.  Flax names:
+ * layer_i/kernel (in, W) at trunk(e) + kernel_off[i], layer_i/bias (W) at trunk(e) + bias_off[i],
+ * VmapDense_0/kernel (T_local, W, head) at heads(e) + head_kernel_off, bias (T_local, head). */
+typedef struct mtrl_net_layout {
+  long long total;
+  long long trunk_total;        /* members * member_trunk_stride                                  */
+  long long slots_off;          /* == trunk_total; 32 floats                                      */
+  long long heads_base;
+  long long member_trunk_stride;
+  long long member_head_stride;
+  long long kernel_off[MTRL_MAX_DEPTH];
+  long long bias_off[MTRL_MAX_DEPTH];
+  long long head_kernel_off;
+  long long head_bias_off;
+  int in_dim, head_dim, members, num_local_tasks, width, depth;
+} mtrl_net_layout_t;
+
+typedef struct mtrl_sac_layout {
+  mtrl_net_layout_t actor;
+  mtrl_net_layout_t critic;
+  long long workspace_bytes;
+  int k_actor;   /* padded input pitch of the actor  (floats) */
+  int k_critic;  /* padded input pitch of the critic (floats) */
+} mtrl_sac_layout_t;
+
+int mtrl_sac_query_layout(const mtrl_sac_config_t* cfg, mtrl_sac_layout_t* out);
+
+/* All device memory, allocated by the caller with the sizes mtrl_sac_query_layout reports
+ * (net arrays: layout.total floats, 128-byte aligned; zero-initialise grads/m/v/steps). */
+typedef struct mtrl_sac_buffers {
+  float *actor_params, *actor_grads, *actor_m, *actor_v, *actor_shadow;
+  float *critic_params, *critic_grads, *critic_m, *critic_v, *critic_shadow;
+  float *critic_target, *critic_target_shadow;
+  float *log_alpha, *alpha_m, *alpha_v; /* [num_local_tasks]                                       */
+  int* steps;                           /* int[4]: actor, critic, alpha Adam counts; noise counter */
+  float* logs;                          /* float[16], see MTRL_LOG_*                               */
+  void* workspace;
+} mtrl_sac_buffers_t;
+
+/* Indices into logs[] in the order the reference merges its log dicts
+ * (mtsac.py:616-621, 704-709, 728-731). */
+enum {
+  MTRL_LOG_QF_VALUES = 0,
+  MTRL_LOG_QF_LOSS = 1,
+  MTRL_LOG_CRITIC_GRAD_MAGNITUDE = 2,
+  MTRL_LOG_CRITIC_PARAMS_NORM = 3,
+  MTRL_LOG_ACTOR_LOSS = 4,
+  MTRL_LOG_ACTOR_GRAD_MAGNITUDE = 5,
+  MTRL_LOG_ACTOR_PARAMS_NORM = 6,
+  MTRL_LOG_EXPLORE_LOSS = 7,
+  MTRL_LOG_ALPHA_LOSS = 8,
+  MTRL_LOG_ALPHA = 9,
+  MTRL_LOG_COUNT = 16
+};
+
+typedef struct mtrl_sac mtrl_sac_t;
+
+int mtrl_sac_create(mtrl_sac_t** out, const mtrl_sac_config_t* cfg, const mtrl_sac_buffers_t* buffers);
+void mtrl_sac_destroy(mtrl_sac_t* h);
+/* Recompute the tf32 operand copies after the caller wrote params / target directly. */
+int mtrl_sac_refresh_shadows(mtrl_sac_t* h, void* stream);
+
+/* One MTSAC.update on `batch` rows (device fp32, ReplayBufferSamples field order, any row order;
+ * the task of a row is argmax of its trailing one-hot).  global_batch is the B every loss mean
+ * divides by (== batch on one GPU).  eps_c / eps_a: device (batch, action_dim) standard normal
+ * draws for the critic-target and actor samples, or NULL for in-kernel Philox. */
+int mtrl_sac_update(mtrl_sac_t* h, const float* obs, const float* actions, const float* next_obs,
+                    const float* dones, const float* rewards, int batch, int global_batch, const float* eps_c,
+                    const float* eps_a, void* stream);
+/* The same update cut at the two points where ranks exchange trunk gradients (all-reduce sum over
+ * grads[0 .. trunk_total + 32) of the critic after phase 1 and of the actor after phase 2). */
+int mtrl_sac_phase1_critic_grads(mtrl_sac_t* h, const float* obs, const float* actions, const float* next_obs,
+                                 const float* dones, const float* rewards, int batch, int global_batch,
+                                 const float* eps_c, const float* eps_a, void* stream);
+int mtrl_sac_phase2_critic_step_actor_grads(mtrl_sac_t* h, void* stream);
+int mtrl_sac_phase3_actor_step_alpha(mtrl_sac_t* h, void* stream);
+/* Number of kernels one mtrl_sac_update launches (for bench.py's gpu_launches). */
+int mtrl_sac_launches_per_update(const mtrl_sac_t* h);
+/* Asynchronous copy of the packing status of the last update into 4 pinned host ints:
+ * [0] == 0 ok, 1: a row's task is outside this handle's task range, 2: rows do not fit max_rows. */
+int mtrl_sac_read_status_async(const mtrl_sac_t* h, int* host_pinned4, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,66 @@
+"""Mirror of mtrl/config/optim.py:14-43.  `spawn()` returns the description of
+optax.chain(clip_by_global_norm(max_grad_norm), adam(lr, eps)) that the fused CUDA optimiser
+(csrc/sac_kernels.cuh adam_kernel) executes; the gradient-surgery configs (optim.py:46-118) keep
+their names but are outside this hot path."""
+from dataclasses import dataclass
+
+from .utils import Optimizer
+
+
+@dataclass(frozen=True)
+class AdamChainSpec:
+    """What OptimizerConfig.spawn() would build with optax, as data."""
+
+    lr: float
+    eps: float
+    b1: float = 0.9
+    b2: float = 0.999
+    max_grad_norm: float | None = None
+
+
+@dataclass(frozen=True, kw_only=True)
+class OptimizerConfig:
+    lr: float = 3e-4
+    optimizer: Optimizer = Optimizer.Adam
+    max_grad_norm: float | None = None
+    eps: float | None = None
+    weight_decay: float | None = None
+
+    @property
+    def requires_split_task_losses(self) -> bool:
+        return False
+
+    def spawn(self) -> AdamChainSpec:
+        if self.optimizer != Optimizer.Adam:
+            raise NotImplementedError(
+                f"{self.optimizer}: only Adam (+ global-norm clip) is on the accelerated path; no experiment of the "
+                "reference's MT-SAC grid uses another optimiser")
+        eps = self.eps if self.eps is not None else 1e-5  # optim.py:29-32
+        return AdamChainSpec(lr=self.lr, eps=eps, max_grad_norm=self.max_grad_norm)
+
+
+def _unsupported(name):
+    def spawn(self):
+        raise NotImplementedError(f"{name} needs per-task gradients (split losses); not on the accelerated path yet")
+    return spawn
+
+
+@dataclass(frozen=True, kw_only=True)
+class DummyMultiTaskConfig(OptimizerConfig):
+    @property
+    def requires_split_task_losses(self) -> bool:
+        return True
+
+    spawn = _unsupported("DummyMultiTaskConfig")
+
+
+@dataclass(frozen=True, kw_only=True)
+class PCGradConfig(OptimizerConfig):
+    num_tasks: int
+    cosine_sim_logs: bool = False
+
+    @property
+    def requires_split_task_losses(self) -> bool:
+        return True
+
+    spawn = _unsupported("PCGradConfig")

@@ -1,0 +1,688 @@
+// MT-SAC update on one device: handle, buffer carve-up, GEMM plans and the launch sequence.
+//
+// Sequence = MTSAC._update_inner (/root/reference/mtrl/rl/algorithms/mtsac.py:1173-1247), non-split branch:
+//   critic step (:513-621)  uses OLD actor and OLD alpha; target update uses the NEW critic (:607-613)
+//   actor  step (:623-711)  uses the NEW critic and OLD alpha
+//   alpha  step (:713-731)  uses log-probs of the OLD actor (the ones the actor loss sampled)
+// Networks: MultiHeadNetwork (mtrl/nn/multi_head.py:21-68) trunk Dense+ReLU layers as tcgen05 GEMMs,
+// own-task heads as CUDA-core row dots; critic input is (action, state) (mtrl/rl/networks.py:61).
+#include <vector>
+
+#include "common.cuh"
+#include "mtrl_b200.h"
+#include "sac_kernels.cuh"
+
+using namespace sac;
+
+namespace {
+
+inline long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
+
+void fill_net_layout(mtrl_net_layout_t* L, int in_dim, int head_dim, int members, int t_local, int width, int depth) {
+  memset(L, 0, sizeof(*L));
+  L->in_dim = in_dim;
+  L->head_dim = head_dim;
+  L->members = members;
+  L->num_local_tasks = t_local;
+  L->width = width;
+  L->depth = depth;
+  long long off = 0;
+  int d = in_dim;
+  for (int i = 0; i < depth; ++i) {
+    L->kernel_off[i] = off;
+    off = round_up(off + static_cast<long long>(d) * width, 32);
+    L->bias_off[i] = off;
+    off = round_up(off + width, 32);
+    d = width;
+  }
+  L->member_trunk_stride = off;
+  L->trunk_total = off * members;
+  L->slots_off = L->trunk_total;
+  L->heads_base = L->trunk_total + 32;
+  long long h = 0;
+  L->head_kernel_off = h;
+  h = round_up(h + static_cast<long long>(t_local) * width * head_dim, 32);
+  L->head_bias_off = h;
+  h = round_up(h + static_cast<long long>(t_local) * head_dim, 32);
+  L->member_head_stride = h;
+  L->total = L->heads_base + h * members;
+}
+
+struct Workspace {
+  float *Xa_next, *Xa, *Xc_next, *Xc;
+  float *An[MTRL_MAX_DEPTH], *Ao[MTRL_MAX_DEPTH];
+  float *C[kMaxE][MTRL_MAX_DEPTH], *Tg[kMaxE][MTRL_MAX_DEPTH];
+  float* G[kMaxE][2];
+  float* dXin;
+  float *rew, *done, *eps_c, *eps_a, *logp_next, *logp, *act, *logstd, *dq, *dout, *colsum_part, *alpha_val, *task_w;
+  unsigned* inrange;
+  int *row_slot, *slot_src, *tile_task, *seg_start, *status;
+  double* acc;
+};
+
+// Bump allocation; with base == nullptr only the size is computed.
+long long carve(const mtrl_sac_config_t& c, int Ka, int Kc, uint8_t* base, Workspace* ws) {
+  long long off = 0;
+  auto take = [&](long long bytes) -> uint8_t* {
+    uint8_t* p = base ? base + off : nullptr;
+    off = round_up(off + bytes, 256);
+    return p;
+  };
+  const long long M = c.max_rows, W = c.width, A = c.action_dim, E = c.num_critics;
+  auto f = [&](long long n) { return reinterpret_cast<float*>(take(n * 4 + 256)); };  // +256: slack for vector tails
+  Workspace w;
+  memset(&w, 0, sizeof(w));
+  w.Xa_next = f(M * Ka);
+  w.Xa = f(M * Ka);
+  w.Xc_next = f(M * Kc);
+  w.Xc = f(M * Kc);
+  for (int l = 0; l < c.depth; ++l) {
+    w.An[l] = f(M * W);
+    w.Ao[l] = f(M * W);
+    for (int e = 0; e < E; ++e) {
+      w.C[e][l] = f(M * W);
+      w.Tg[e][l] = f(M * W);
+    }
+  }
+  for (int e = 0; e < E; ++e) {
+    w.G[e][0] = f(M * W);
+    w.G[e][1] = f(M * W);
+  }
+  w.dXin = f(E * M * 16);
+  w.rew = f(M);
+  w.done = f(M);
+  w.eps_c = f(M * A);
+  w.eps_a = f(M * A);
+  w.logp_next = f(M);
+  w.logp = f(M);
+  w.act = f(M * A);
+  w.logstd = f(M * A);
+  w.dq = f(E * M);
+  w.dout = f(M * 2 * A);
+  w.colsum_part = f(static_cast<long long>(kColsumSplits) * kMaxE * W);
+  w.alpha_val = f(c.num_local_tasks);
+  w.task_w = f(c.num_local_tasks);
+  w.inrange = reinterpret_cast<unsigned*>(take(M * 4));
+  w.row_slot = reinterpret_cast<int*>(take(static_cast<long long>(c.max_batch) * 4));
+  w.slot_src = reinterpret_cast<int*>(take(M * 4));
+  w.tile_task = reinterpret_cast<int*>(take(M / kTileRows * 4));
+  w.seg_start = reinterpret_cast<int*>(take((c.num_local_tasks + 1) * 4));
+  w.status = reinterpret_cast<int*>(take(16));
+  w.acc = reinterpret_cast<double*>(take(ACC_COUNT * 8));
+  if (ws) *ws = w;
+  return off;
+}
+
+int validate(const mtrl_sac_config_t& c) {
+  MTRL_REQUIRE(c.num_tasks >= 1 && c.num_local_tasks >= 1 && c.task_begin >= 0 &&
+                   c.task_begin + c.num_local_tasks <= c.num_tasks,
+               "sac config: bad task range [%d, %d) of %d", c.task_begin, c.task_begin + c.num_local_tasks, c.num_tasks);
+  MTRL_REQUIRE(c.obs_dim > c.num_tasks, "sac config: obs_dim %d must exceed num_tasks %d (one-hot suffix)", c.obs_dim,
+               c.num_tasks);
+  MTRL_REQUIRE(c.action_dim >= 1 && c.action_dim <= kMaxA, "sac config: action_dim %d outside [1, %d]", c.action_dim, kMaxA);
+  MTRL_REQUIRE(c.obs_dim + c.action_dim >= 16, "sac config: critic input narrower than 16 is not supported");
+  MTRL_REQUIRE(c.width >= 16 && c.width % 4 == 0, "sac config: width %d must be a multiple of 4 and >= 16", c.width);
+  MTRL_REQUIRE(c.depth >= 1 && c.depth <= MTRL_MAX_DEPTH, "sac config: depth %d outside [1, %d]", c.depth, MTRL_MAX_DEPTH);
+  MTRL_REQUIRE(c.num_critics >= 1 && c.num_critics <= kMaxE, "sac config: num_critics %d outside [1, %d]", c.num_critics,
+               kMaxE);
+  MTRL_REQUIRE(c.max_rows >= kTileRows && c.max_rows % kTileRows == 0, "sac config: max_rows %d must be a multiple of %d",
+               c.max_rows, kTileRows);
+  MTRL_REQUIRE(c.max_batch >= 1 && c.max_batch <= c.max_rows, "sac config: max_batch %d outside [1, max_rows]", c.max_batch);
+  MTRL_REQUIRE(!(c.use_task_weights && c.num_local_tasks != c.num_tasks),
+               "sac config: use_task_weights needs all tasks on one handle (softmax over every log_alpha)");
+  return MTRL_OK;
+}
+
+int block_n_for(int n) {
+  const int tiles = (n + 255) / 256;
+  const int bn = static_cast<int>(round_up((n + tiles - 1) / tiles, 16));
+  return bn > 256 ? 256 : bn;
+}
+
+}  // namespace
+
+struct mtrl_sac {
+  mtrl_sac_config_t cfg;
+  mtrl_sac_buffers_t buf;
+  mtrl_sac_layout_t lay;
+  Workspace ws;
+  int sms = 148;
+  // GEMM plans
+  std::vector<mtrl_gemm_plan_t*> fwd;          // [depth] actor(next), actor(obs), critic members
+  std::vector<mtrl_gemm_plan_t*> fwd_target;   // [depth]
+  std::vector<mtrl_gemm_plan_t*> bwd_critic;   // [depth] (index l: dW_l of every member + dZ_{l-1})
+  std::vector<mtrl_gemm_plan_t*> fwd_pi;       // [depth] critic (new params) on (pi(s), s)
+  std::vector<mtrl_gemm_plan_t*> bwd_pi;       // [depth] dX only
+  std::vector<mtrl_gemm_plan_t*> bwd_actor;    // [depth]
+  int launches = 0;
+  int batch = 0, global_batch = 0;
+};
+
+namespace {
+
+float* tk(float* base, const mtrl_net_layout_t& L, int e, int l) { return base + e * L.member_trunk_stride + L.kernel_off[l]; }
+float* tb(float* base, const mtrl_net_layout_t& L, int e, int l) { return base + e * L.member_trunk_stride + L.bias_off[l]; }
+float* hk(float* base, const mtrl_net_layout_t& L, int e) { return base + L.heads_base + e * L.member_head_stride + L.head_kernel_off; }
+float* hb(float* base, const mtrl_net_layout_t& L, int e) { return base + L.heads_base + e * L.member_head_stride + L.head_bias_off; }
+
+mtrl_gemm_problem_t fwd_problem(const float* X, int ldx, int K, const float* Wsh, const float* bias, float* out, int M, int W) {
+  mtrl_gemm_problem_t p;
+  memset(&p, 0, sizeof(p));
+  p.A = X; p.lda = ldx; p.a_major = 0;
+  p.B = Wsh; p.ldb = W; p.b_major = 1;     // Flax kernel (in, out): N contiguous
+  p.D = out; p.ldd = W;
+  p.M = M; p.N = W; p.K = K;
+  p.block_n = block_n_for(W); p.k_splits = 1; p.epilogue = MTRL_EPI_BIAS_RELU; p.bias = bias;
+  return p;
+}
+// dZ_prev = (dZ W^T) * (H_prev > 0): A = dZ [M][W] K-major, B = W [in=N][W=K] K-major
+mtrl_gemm_problem_t dx_problem(const float* dZ, const float* Wsh, int n_in, const float* mask, float* out, int M, int W) {
+  mtrl_gemm_problem_t p;
+  memset(&p, 0, sizeof(p));
+  p.A = dZ; p.lda = W; p.a_major = 0;
+  p.B = Wsh; p.ldb = W; p.b_major = 0;
+  p.D = out; p.ldd = n_in;
+  p.M = M; p.N = n_in; p.K = W;
+  p.block_n = block_n_for(n_in); p.k_splits = 1; p.epilogue = MTRL_EPI_RELU_MASK; p.mask = mask; p.ldmask = n_in;
+  return p;
+}
+// dW = X^T dZ: A = X [rows][in] MN-major, B = dZ [rows][W] MN-major, K = rows
+mtrl_gemm_problem_t dw_problem(const float* X, int ldx, int n_in, const float* dZ, float* dW, int M, int W, int sms,
+                               int units_hint) {
+  mtrl_gemm_problem_t p;
+  memset(&p, 0, sizeof(p));
+  p.A = X; p.lda = ldx; p.a_major = 1;
+  p.B = dZ; p.ldb = W; p.b_major = 1;
+  p.D = dW; p.ldd = W;
+  p.M = n_in; p.N = W; p.K = M;
+  p.block_n = block_n_for(W);
+  const int kb = (M + 31) / 32;
+  const int tiles = ((n_in + 127) / 128) * ((W + p.block_n - 1) / p.block_n);
+  int splits;
+  if (n_in >= 128) {
+    // match the K depth of the dX units that share the launch (W/32 k-blocks) so units are uniform
+    splits = (kb + (W / 32) - 1) / (W / 32 > 0 ? W / 32 : 1);
+  } else {
+    splits = sms / (tiles > 0 ? tiles : 1);
+  }
+  const int max_splits = kb / 4 > 0 ? kb / 4 : 1;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  (void)units_hint;
+  p.k_splits = splits;
+  p.epilogue = splits > 1 ? MTRL_EPI_ATOMIC_ADD : MTRL_EPI_STORE;
+  return p;
+}
+
+int make_plan(std::vector<mtrl_gemm_plan_t*>& dst, const std::vector<mtrl_gemm_problem_t>& probs) {
+  mtrl_gemm_plan_t* plan = nullptr;
+  MTRL_PROPAGATE(mtrl_gemm_plan_create(&plan, probs.data(), static_cast<int>(probs.size())));
+  dst.push_back(plan);
+  return MTRL_OK;
+}
+
+int build_plans(mtrl_sac* h) {
+  const mtrl_sac_config_t& c = h->cfg;
+  const mtrl_net_layout_t& LA = h->lay.actor;
+  const mtrl_net_layout_t& LC = h->lay.critic;
+  const Workspace& w = h->ws;
+  const int M = c.max_rows, W = c.width, D = c.depth, E = c.num_critics;
+  const int Ka = h->lay.k_actor, Kc = h->lay.k_critic;
+  float* ash = h->buf.actor_shadow;
+  float* csh = h->buf.critic_shadow;
+  float* tsh = h->buf.critic_target_shadow;
+  for (int l = 0; l < D; ++l) {
+    std::vector<mtrl_gemm_problem_t> p;
+    const int K = l == 0 ? Ka : W;
+    p.push_back(fwd_problem(l == 0 ? w.Xa_next : w.An[l - 1], K, l == 0 ? LA.in_dim : W, tk(ash, LA, 0, l),
+                            tb(h->buf.actor_params, LA, 0, l), w.An[l], M, W));
+    p.push_back(fwd_problem(l == 0 ? w.Xa : w.Ao[l - 1], K, l == 0 ? LA.in_dim : W, tk(ash, LA, 0, l),
+                            tb(h->buf.actor_params, LA, 0, l), w.Ao[l], M, W));
+    for (int e = 0; e < E; ++e)
+      p.push_back(fwd_problem(l == 0 ? w.Xc : w.C[e][l - 1], l == 0 ? Kc : W, l == 0 ? LC.in_dim : W, tk(csh, LC, e, l),
+                              tb(h->buf.critic_params, LC, e, l), w.C[e][l], M, W));
+    MTRL_PROPAGATE(make_plan(h->fwd, p));
+  }
+  for (int l = 0; l < D; ++l) {
+    std::vector<mtrl_gemm_problem_t> p, q;
+    for (int e = 0; e < E; ++e) {
+      p.push_back(fwd_problem(l == 0 ? w.Xc_next : w.Tg[e][l - 1], l == 0 ? Kc : W, l == 0 ? LC.in_dim : W,
+                              tk(tsh, LC, e, l), tb(h->buf.critic_target, LC, e, l), w.Tg[e][l], M, W));
+      q.push_back(fwd_problem(l == 0 ? w.Xc : w.C[e][l - 1], l == 0 ? Kc : W, l == 0 ? LC.in_dim : W, tk(csh, LC, e, l),
+                              tb(h->buf.critic_params, LC, e, l), w.C[e][l], M, W));
+    }
+    MTRL_PROPAGATE(make_plan(h->fwd_target, p));
+    MTRL_PROPAGATE(make_plan(h->fwd_pi, q));
+  }
+  // Backward: dZ_{D-1} (masked head VJP) sits in G[e][0]; layer l reads G[e][(D-1-l)&1], writes G[e][(D-l)&1].
+  for (int l = D - 1; l >= 0; --l) {
+    const int src = (D - 1 - l) & 1, dst = src ^ 1;
+    std::vector<mtrl_gemm_problem_t> pc, ppi, pa;
+    for (int e = 0; e < E; ++e) {
+      const float* X = l == 0 ? w.Xc : w.C[e][l - 1];
+      pc.push_back(dw_problem(X, l == 0 ? Kc : W, l == 0 ? LC.in_dim : W, w.G[e][src], tk(h->buf.critic_grads, LC, e, l), M, W,
+                              h->sms, 0));
+    }
+    for (int e = 0; e < E; ++e) {
+      if (l > 0) {
+        pc.push_back(dx_problem(w.G[e][src], tk(csh, LC, e, l), W, w.C[e][l - 1], w.G[e][dst], M, W));
+        ppi.push_back(dx_problem(w.G[e][src], tk(csh, LC, e, l), W, w.C[e][l - 1], w.G[e][dst], M, W));
+      } else {
+        // actor step: only dL/da = first action_dim input columns of dZ_0 W_0^T (N = 16 rows of W_0)
+        mtrl_gemm_problem_t p;
+        memset(&p, 0, sizeof(p));
+        p.A = w.G[e][src]; p.lda = W; p.a_major = 0;
+        p.B = tk(csh, LC, e, 0); p.ldb = W; p.b_major = 0;
+        p.D = w.dXin + static_cast<long long>(e) * M * 16; p.ldd = 16;
+        p.M = M; p.N = 16; p.K = W; p.block_n = 16; p.k_splits = 1; p.epilogue = MTRL_EPI_STORE;
+        ppi.push_back(p);
+      }
+    }
+    pa.push_back(dw_problem(l == 0 ? w.Xa : w.Ao[l - 1], l == 0 ? Ka : W, l == 0 ? LA.in_dim : W, w.G[0][src],
+                            tk(h->buf.actor_grads, LA, 0, l), M, W, h->sms, 0));
+    if (l > 0) pa.push_back(dx_problem(w.G[0][src], tk(ash, LA, 0, l), W, w.Ao[l - 1], w.G[0][dst], M, W));
+    MTRL_PROPAGATE(make_plan(h->bwd_critic, pc));
+    MTRL_PROPAGATE(make_plan(h->bwd_pi, ppi));
+    MTRL_PROPAGATE(make_plan(h->bwd_actor, pa));
+  }
+  return MTRL_OK;
+}
+
+#define LAUNCHED(h) ((h)->launches++)
+
+int run_plan(mtrl_sac* h, mtrl_gemm_plan_t* plan, cudaStream_t st) {
+  MTRL_PROPAGATE(mtrl_gemm_plan_run(plan, st));
+  LAUNCHED(h);
+  return MTRL_OK;
+}
+
+int launch_actor_head(mtrl_sac* h, const float* H, const float* eps, float* Xdst, float* logp, bool save, cudaStream_t st) {
+  const mtrl_sac_config_t& c = h->cfg;
+  ActorHeadArgs a;
+  a.H = H;
+  a.Wh = hk(h->buf.actor_params, h->lay.actor, 0);
+  a.bh = hb(h->buf.actor_params, h->lay.actor, 0);
+  a.tile_task = h->ws.tile_task;
+  a.slot_src = h->ws.slot_src;
+  a.eps = eps;
+  a.Xdst = Xdst;
+  a.ldx = h->lay.k_critic;
+  a.act = save ? h->ws.act : nullptr;
+  a.logp = logp;
+  a.logstd = save ? h->ws.logstd : nullptr;
+  a.inrange = save ? h->ws.inrange : nullptr;
+  a.M = c.max_rows;
+  a.W = c.width;
+  a.ls_min = c.log_std_min;
+  a.ls_max = c.log_std_max;
+  const int wpb = 8;
+  dim3 grid((c.max_rows + wpb - 1) / wpb), block(wpb * 32);
+  switch (c.action_dim) {
+    case 1: actor_head_kernel<1><<<grid, block, 0, st>>>(a); break;
+    case 2: actor_head_kernel<2><<<grid, block, 0, st>>>(a); break;
+    case 3: actor_head_kernel<3><<<grid, block, 0, st>>>(a); break;
+    case 4: actor_head_kernel<4><<<grid, block, 0, st>>>(a); break;
+    case 5: actor_head_kernel<5><<<grid, block, 0, st>>>(a); break;
+    case 6: actor_head_kernel<6><<<grid, block, 0, st>>>(a); break;
+    case 7: actor_head_kernel<7><<<grid, block, 0, st>>>(a); break;
+    default: actor_head_kernel<8><<<grid, block, 0, st>>>(a); break;
+  }
+  MTRL_CUDA_CHECK(cudaGetLastError());
+  LAUNCHED(h);
+  return MTRL_OK;
+}
+
+template <int HD>
+void launch_head_bwd_t(const HeadBwdArgs& a, int T_local, int E, cudaStream_t st) {
+  dim3 grid((a.W + 127) / 128, T_local, E);
+  head_bwd_kernel<HD><<<grid, 128, 0, st>>>(a);
+}
+
+int launch_head_bwd(mtrl_sac* h, const HeadBwdArgs& a, int hd, int E, cudaStream_t st) {
+  const int T = h->cfg.num_local_tasks;
+  switch (hd) {
+    case 1: launch_head_bwd_t<1>(a, T, E, st); break;
+    case 2: launch_head_bwd_t<2>(a, T, E, st); break;
+    case 4: launch_head_bwd_t<4>(a, T, E, st); break;
+    case 6: launch_head_bwd_t<6>(a, T, E, st); break;
+    case 8: launch_head_bwd_t<8>(a, T, E, st); break;
+    case 10: launch_head_bwd_t<10>(a, T, E, st); break;
+    case 12: launch_head_bwd_t<12>(a, T, E, st); break;
+    case 14: launch_head_bwd_t<14>(a, T, E, st); break;
+    case 16: launch_head_bwd_t<16>(a, T, E, st); break;
+    default: mtrl_set_error("head_bwd: unsupported head_dim %d", hd); return MTRL_ERR_UNSUPPORTED;
+  }
+  MTRL_CUDA_CHECK(cudaGetLastError());
+  LAUNCHED(h);
+  return MTRL_OK;
+}
+
+int launch_colsum(mtrl_sac* h, const ColsumJobs& jobs, cudaStream_t st) {
+  const int M = h->cfg.max_rows, W = h->cfg.width;
+  dim3 g1((W + 127) / 128, kColsumSplits, jobs.njobs);
+  colsum_partial_kernel<<<g1, 128, 0, st>>>(jobs, M, W, h->ws.colsum_part);
+  dim3 g2((W + 127) / 128, jobs.njobs);
+  colsum_final_kernel<<<g2, 128, 0, st>>>(jobs, kColsumSplits, W, h->ws.colsum_part);
+  MTRL_CUDA_CHECK(cudaGetLastError());
+  h->launches += 2;
+  return MTRL_OK;
+}
+
+// Trunk backward of one network: bias gradients (column sums of dZ_l) + the dW / dX GEMM plan per layer.
+int run_trunk_backward(mtrl_sac* h, std::vector<mtrl_gemm_plan_t*>& plans, float* grads, const mtrl_net_layout_t& L, int E,
+                       bool want_wgrad, cudaStream_t st) {
+  const int D = h->cfg.depth;
+  for (int l = D - 1, i = 0; l >= 0; --l, ++i) {
+    const int src = (D - 1 - l) & 1;
+    if (want_wgrad) {
+      ColsumJobs jobs;
+      jobs.njobs = E;
+      for (int e = 0; e < E; ++e) {
+        jobs.src[e] = h->ws.G[e][src];
+        jobs.dst[e] = tb(grads, L, e, l);
+      }
+      MTRL_PROPAGATE(launch_colsum(h, jobs, st));
+    }
+    MTRL_PROPAGATE(run_plan(h, plans[i], st));
+  }
+  return MTRL_OK;
+}
+
+int head_sumsq_to_slot(mtrl_sac* h, float* grads, const mtrl_net_layout_t& L, int acc_idx, cudaStream_t st) {
+  const long long n = L.total - L.heads_base;
+  sumsq_kernel<<<64, 256, 0, st>>>(grads + L.heads_base, n, h->ws.acc + acc_idx);
+  write_slot_kernel<<<1, 1, 0, st>>>(grads + L.slots_off, h->ws.acc + acc_idx);
+  MTRL_CUDA_CHECK(cudaGetLastError());
+  h->launches += 2;
+  return MTRL_OK;
+}
+
+}  // namespace
+
+extern "C" int mtrl_sac_query_layout(const mtrl_sac_config_t* cfg, mtrl_sac_layout_t* out) {
+  MTRL_REQUIRE(cfg && out, "mtrl_sac_query_layout: null argument");
+  MTRL_PROPAGATE(validate(*cfg));
+  memset(out, 0, sizeof(*out));
+  fill_net_layout(&out->actor, cfg->obs_dim, 2 * cfg->action_dim, 1, cfg->num_local_tasks, cfg->width, cfg->depth);
+  fill_net_layout(&out->critic, cfg->action_dim + cfg->obs_dim, 1, cfg->num_critics, cfg->num_local_tasks, cfg->width,
+                  cfg->depth);
+  out->k_actor = static_cast<int>(round_up(cfg->obs_dim, 32));
+  out->k_critic = static_cast<int>(round_up(cfg->action_dim + cfg->obs_dim, 32));
+  out->workspace_bytes = carve(*cfg, out->k_actor, out->k_critic, nullptr, nullptr);
+  return MTRL_OK;
+}
+
+extern "C" int mtrl_sac_create(mtrl_sac_t** out, const mtrl_sac_config_t* cfg, const mtrl_sac_buffers_t* b) {
+  MTRL_REQUIRE(out && cfg && b, "mtrl_sac_create: null argument");
+  mtrl_sac* h = new mtrl_sac();
+  h->cfg = *cfg;
+  h->buf = *b;
+  int rc = mtrl_sac_query_layout(cfg, &h->lay);
+  if (rc != MTRL_OK) { delete h; return rc; }
+  const void* need[] = {b->actor_params, b->actor_grads, b->actor_m, b->actor_v, b->actor_shadow, b->critic_params,
+                        b->critic_grads, b->critic_m, b->critic_v, b->critic_shadow, b->critic_target,
+                        b->critic_target_shadow, b->log_alpha, b->alpha_m, b->alpha_v, b->steps, b->logs, b->workspace};
+  for (const void* p : need) {
+    if (!p || (reinterpret_cast<uintptr_t>(p) & 15u)) {
+      delete h;
+      mtrl_set_error("mtrl_sac_create: every buffer must be non-null and 16-byte aligned");
+      return MTRL_ERR_INVALID;
+    }
+  }
+  carve(*cfg, h->lay.k_actor, h->lay.k_critic, static_cast<uint8_t*>(b->workspace), &h->ws);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaMemset(b->workspace, 0, h->lay.workspace_bytes);
+  cudaFuncSetAttribute(pack_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  rc = build_plans(h);
+  if (rc != MTRL_OK) { mtrl_sac_destroy(h); return rc; }
+  rc = mtrl_sac_refresh_shadows(h, nullptr);
+  if (rc != MTRL_OK) { mtrl_sac_destroy(h); return rc; }
+  cudaDeviceSynchronize();
+  *out = h;
+  return MTRL_OK;
+}
+
+extern "C" void mtrl_sac_destroy(mtrl_sac_t* h) {
+  if (!h) return;
+  for (auto* v : {&h->fwd, &h->fwd_target, &h->bwd_critic, &h->fwd_pi, &h->bwd_pi, &h->bwd_actor})
+    for (auto* p : *v) mtrl_gemm_plan_destroy(p);
+  delete h;
+}
+
+extern "C" int mtrl_sac_refresh_shadows(mtrl_sac_t* h, void* stream) {
+  MTRL_REQUIRE(h, "mtrl_sac_refresh_shadows: null handle");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  shadow_kernel<<<h->sms * 4, 256, 0, st>>>(h->buf.actor_params, h->buf.actor_shadow, h->lay.actor.total);
+  shadow_kernel<<<h->sms * 4, 256, 0, st>>>(h->buf.critic_params, h->buf.critic_shadow, h->lay.critic.total);
+  shadow_kernel<<<h->sms * 4, 256, 0, st>>>(h->buf.critic_target, h->buf.critic_target_shadow, h->lay.critic.total);
+  MTRL_CUDA_CHECK(cudaGetLastError());
+  return MTRL_OK;
+}
+
+extern "C" int mtrl_sac_phase1_critic_grads(mtrl_sac_t* h, const float* obs, const float* actions, const float* next_obs,
+                                            const float* dones, const float* rewards, int batch, int global_batch,
+                                            const float* eps_c, const float* eps_a, void* stream) {
+  MTRL_REQUIRE(h && obs && actions && next_obs && dones && rewards, "mtrl_sac_update: null batch pointer");
+  const mtrl_sac_config_t& c = h->cfg;
+  MTRL_REQUIRE(batch >= 1 && batch <= c.max_batch, "mtrl_sac_update: batch %d outside [1, %d]", batch, c.max_batch);
+  MTRL_REQUIRE(global_batch >= batch, "mtrl_sac_update: global_batch %d < batch %d", global_batch, batch);
+  MTRL_REQUIRE((eps_c == nullptr) == (eps_a == nullptr), "mtrl_sac_update: pass both eps_c and eps_a or neither");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Workspace& w = h->ws;
+  const mtrl_net_layout_t& LA = h->lay.actor;
+  const mtrl_net_layout_t& LC = h->lay.critic;
+  const int M = c.max_rows, W = c.width, D = c.depth, E = c.num_critics, T = c.num_local_tasks;
+  h->launches = 0;
+  h->batch = batch;
+  h->global_batch = global_batch;
+
+  MTRL_CUDA_CHECK(cudaMemsetAsync(w.acc, 0, ACC_COUNT * sizeof(double), st));
+  MTRL_CUDA_CHECK(cudaMemsetAsync(w.status, 0, 16, st));
+  MTRL_CUDA_CHECK(cudaMemsetAsync(h->buf.critic_grads, 0, LC.total * sizeof(float), st));
+  MTRL_CUDA_CHECK(cudaMemsetAsync(h->buf.actor_grads, 0, LA.total * sizeof(float), st));
+  h->launches += 4;
+
+  alpha_prep_kernel<<<1, 256, 0, st>>>(h->buf.log_alpha, T, c.use_task_weights, w.alpha_val, w.task_w);
+  LAUNCHED(h);
+  {
+    const int nchunks = (batch + 31) / 32;
+    const size_t smem = (static_cast<size_t>(nchunks) * T + T + 1) * sizeof(int);
+    MTRL_REQUIRE(smem <= 200 * 1024, "mtrl_sac_update: batch %d x %d tasks exceeds the packing kernel's shared memory", batch, T);
+    pack_plan_kernel<<<1, 1024, smem, st>>>(obs, batch, c.obs_dim, c.num_tasks, c.task_begin, T, M, w.row_slot, w.slot_src,
+                                            w.tile_task, w.seg_start, w.status);
+    LAUNCHED(h);
+    PackArgs a;
+    a.obs = obs; a.actions = actions; a.next_obs = next_obs; a.dones = dones; a.rewards = rewards;
+    a.eps_c = eps_c; a.eps_a = eps_a;
+    a.Xa_next = w.Xa_next; a.Xa = w.Xa; a.Xc_next = w.Xc_next; a.Xc = w.Xc;
+    a.rew = w.rew; a.done = w.done; a.peps_c = w.eps_c; a.peps_a = w.eps_a;
+    a.slot_src = w.slot_src;
+    a.noise_counter = h->buf.steps + 3;
+    a.seed = c.noise_seed;
+    a.obs_dim = c.obs_dim; a.act_dim = c.action_dim; a.Ka = h->lay.k_actor; a.Kc = h->lay.k_critic;
+    pack_rows_kernel<<<M, 128, 0, st>>>(a);
+    LAUNCHED(h);
+    MTRL_CUDA_CHECK(cudaGetLastError());
+  }
+  // forward: actor on s' and s (old actor), critics on (a, s)
+  for (int l = 0; l < D; ++l) MTRL_PROPAGATE(run_plan(h, h->fwd[l], st));
+  // a' ~ pi(s'), log pi(a'|s')   (mtsac.py:526-528); a' lands in the action columns of the target critics' input
+  MTRL_PROPAGATE(launch_actor_head(h, w.An[D - 1], w.eps_c, w.Xc_next, w.logp_next, false, st));
+  for (int l = 0; l < D; ++l) MTRL_PROPAGATE(run_plan(h, h->fwd_target[l], st));
+  {
+    CriticLossArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int e = 0; e < E; ++e) {
+      a.target.H[e] = w.Tg[e][D - 1];
+      a.target.w[e] = hk(h->buf.critic_target, LC, e);
+      a.target.b[e] = hb(h->buf.critic_target, LC, e);
+      a.online.H[e] = w.C[e][D - 1];
+      a.online.w[e] = hk(h->buf.critic_params, LC, e);
+      a.online.b[e] = hb(h->buf.critic_params, LC, e);
+    }
+    a.tile_task = w.tile_task; a.slot_src = w.slot_src;
+    a.rew = w.rew; a.done = w.done; a.logp_next = w.logp_next; a.alpha_val = w.alpha_val; a.task_w = w.task_w;
+    a.dq = w.dq; a.acc = w.acc;
+    a.M = M; a.W = W; a.E = E;
+    a.gamma = c.gamma;
+    a.inv_eb = 1.f / (static_cast<float>(E) * static_cast<float>(global_batch));
+    a.clip = c.clip_q;
+    critic_loss_kernel<<<(M + 7) / 8, 256, 0, st>>>(a);
+    MTRL_CUDA_CHECK(cudaGetLastError());
+    LAUNCHED(h);
+  }
+  {
+    HeadBwdArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int e = 0; e < E; ++e) {
+      a.H[e] = w.C[e][D - 1];
+      a.dout[e] = w.dq + static_cast<long long>(e) * M;
+      a.Wh[e] = hk(h->buf.critic_params, LC, e);
+      a.dZ[e] = w.G[e][0];
+      a.dWh[e] = hk(h->buf.critic_grads, LC, e);
+      a.dbh[e] = hb(h->buf.critic_grads, LC, e);
+    }
+    a.seg_start = w.seg_start; a.M = M; a.W = W;
+    MTRL_PROPAGATE(launch_head_bwd(h, a, 1, E, st));
+  }
+  MTRL_PROPAGATE(run_trunk_backward(h, h->bwd_critic, h->buf.critic_grads, LC, E, true, st));
+  MTRL_PROPAGATE(head_sumsq_to_slot(h, h->buf.critic_grads, LC, ACC_CRITIC_HEAD_G2, st));
+  return MTRL_OK;
+}
+
+extern "C" int mtrl_sac_phase2_critic_step_actor_grads(mtrl_sac_t* h, void* stream) {
+  MTRL_REQUIRE(h && h->batch > 0, "mtrl_sac_phase2: phase 1 has not run");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const mtrl_sac_config_t& c = h->cfg;
+  Workspace& w = h->ws;
+  const mtrl_net_layout_t& LA = h->lay.actor;
+  const mtrl_net_layout_t& LC = h->lay.critic;
+  const int M = c.max_rows, W = c.width, D = c.depth, E = c.num_critics;
+  const float inv_b = 1.f / static_cast<float>(h->global_batch);
+  // ---- critic optimiser step + Polyak (mtsac.py:599-613) ----
+  sumsq_kernel<<<h->sms * 2, 256, 0, st>>>(h->buf.critic_grads, LC.trunk_total, w.acc + ACC_CRITIC_G2);
+  LAUNCHED(h);
+  {
+    AdamArgs a;
+    a.p = h->buf.critic_params; a.m = h->buf.critic_m; a.v = h->buf.critic_v; a.shadow = h->buf.critic_shadow;
+    a.g = h->buf.critic_grads; a.target = h->buf.critic_target; a.target_shadow = h->buf.critic_target_shadow;
+    a.n = LC.total; a.trunk_n = LC.trunk_total;
+    a.g2_trunk = w.acc + ACC_CRITIC_G2; a.g2_heads = h->buf.critic_grads + LC.slots_off;
+    a.step = h->buf.steps + 1;
+    a.p2_trunk = w.acc + ACC_CRITIC_P2_TRUNK; a.p2_head = w.acc + ACC_CRITIC_P2_HEAD;
+    a.lr = c.critic_lr; a.b1 = c.adam_b1; a.b2 = c.adam_b2; a.eps = c.adam_eps; a.max_norm = c.critic_max_grad_norm;
+    a.tau = c.tau;
+    adam_kernel<<<h->sms * 4, 256, 0, st>>>(a);
+    LAUNCHED(h);
+    finalize_critic_kernel<<<1, 1, 0, st>>>(w.acc, h->buf.critic_grads + LC.slots_off, h->buf.steps, h->buf.logs,
+                                            1.f / (static_cast<float>(E) * static_cast<float>(h->global_batch)));
+    LAUNCHED(h);
+    MTRL_CUDA_CHECK(cudaGetLastError());
+  }
+  // ---- actor loss (mtsac.py:631-675): a ~ pi(s) with the old actor, Q from the NEW critic ----
+  MTRL_PROPAGATE(launch_actor_head(h, w.Ao[D - 1], w.eps_a, w.Xc, w.logp, true, st));
+  for (int l = 0; l < D; ++l) MTRL_PROPAGATE(run_plan(h, h->fwd_pi[l], st));
+  {
+    ActorLossArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int e = 0; e < E; ++e) {
+      a.online.H[e] = w.C[e][D - 1];
+      a.online.w[e] = hk(h->buf.critic_params, LC, e);
+      a.online.b[e] = hb(h->buf.critic_params, LC, e);
+    }
+    a.tile_task = w.tile_task; a.slot_src = w.slot_src; a.logp = w.logp; a.alpha_val = w.alpha_val; a.task_w = w.task_w;
+    a.dq = w.dq; a.acc = w.acc; a.M = M; a.W = W; a.E = E; a.inv_b = inv_b;
+    actor_loss_kernel<<<(M + 7) / 8, 256, 0, st>>>(a);
+    MTRL_CUDA_CHECK(cudaGetLastError());
+    LAUNCHED(h);
+  }
+  {
+    HeadBwdArgs a;  // critic heads, input gradients only
+    memset(&a, 0, sizeof(a));
+    for (int e = 0; e < E; ++e) {
+      a.H[e] = w.C[e][D - 1];
+      a.dout[e] = w.dq + static_cast<long long>(e) * M;
+      a.Wh[e] = hk(h->buf.critic_params, LC, e);
+      a.dZ[e] = w.G[e][0];
+    }
+    a.seg_start = w.seg_start; a.M = M; a.W = W;
+    MTRL_PROPAGATE(launch_head_bwd(h, a, 1, E, st));
+  }
+  MTRL_PROPAGATE(run_trunk_backward(h, h->bwd_pi, nullptr, LC, E, false, st));
+  {
+    ActorDoutArgs a;
+    a.dXin = w.dXin; a.act = w.act; a.logstd = w.logstd; a.eps = w.eps_a; a.alpha_val = w.alpha_val; a.task_w = w.task_w;
+    a.inrange = w.inrange; a.tile_task = w.tile_task; a.slot_src = w.slot_src; a.dout = w.dout;
+    a.M = M; a.E = E; a.A = c.action_dim; a.inv_b = inv_b;
+    actor_dout_kernel<<<(M + 127) / 128, 128, 0, st>>>(a);
+    MTRL_CUDA_CHECK(cudaGetLastError());
+    LAUNCHED(h);
+  }
+  {
+    HeadBwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.H[0] = w.Ao[D - 1];
+    a.dout[0] = w.dout;
+    a.Wh[0] = hk(h->buf.actor_params, LA, 0);
+    a.dZ[0] = w.G[0][0];
+    a.dWh[0] = hk(h->buf.actor_grads, LA, 0);
+    a.dbh[0] = hb(h->buf.actor_grads, LA, 0);
+    a.seg_start = w.seg_start; a.M = M; a.W = W;
+    MTRL_PROPAGATE(launch_head_bwd(h, a, 2 * c.action_dim, 1, st));
+  }
+  MTRL_PROPAGATE(run_trunk_backward(h, h->bwd_actor, h->buf.actor_grads, LA, 1, true, st));
+  MTRL_PROPAGATE(head_sumsq_to_slot(h, h->buf.actor_grads, LA, ACC_ACTOR_HEAD_G2, st));
+  return MTRL_OK;
+}
+
+extern "C" int mtrl_sac_phase3_actor_step_alpha(mtrl_sac_t* h, void* stream) {
+  MTRL_REQUIRE(h && h->batch > 0, "mtrl_sac_phase3: phase 1 has not run");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const mtrl_sac_config_t& c = h->cfg;
+  Workspace& w = h->ws;
+  const mtrl_net_layout_t& LA = h->lay.actor;
+  const float inv_b = 1.f / static_cast<float>(h->global_batch);
+  sumsq_kernel<<<h->sms * 2, 256, 0, st>>>(h->buf.actor_grads, LA.trunk_total, w.acc + ACC_ACTOR_G2);
+  LAUNCHED(h);
+  AdamArgs a;
+  a.p = h->buf.actor_params; a.m = h->buf.actor_m; a.v = h->buf.actor_v; a.shadow = h->buf.actor_shadow;
+  a.g = h->buf.actor_grads; a.target = nullptr; a.target_shadow = nullptr;
+  a.n = LA.total; a.trunk_n = LA.trunk_total;
+  a.g2_trunk = w.acc + ACC_ACTOR_G2; a.g2_heads = h->buf.actor_grads + LA.slots_off;
+  a.step = h->buf.steps + 0;
+  a.p2_trunk = w.acc + ACC_ACTOR_P2_TRUNK; a.p2_head = w.acc + ACC_ACTOR_P2_HEAD;
+  a.lr = c.actor_lr; a.b1 = c.adam_b1; a.b2 = c.adam_b2; a.eps = c.adam_eps; a.max_norm = c.actor_max_grad_norm; a.tau = 0.f;
+  adam_kernel<<<h->sms * 4, 256, 0, st>>>(a);
+  LAUNCHED(h);
+  finalize_actor_kernel<<<1, 1, 0, st>>>(w.acc, h->buf.actor_grads + LA.slots_off, h->buf.steps, h->buf.logs, inv_b);
+  LAUNCHED(h);
+  AlphaArgs al;
+  al.log_alpha = h->buf.log_alpha; al.m = h->buf.alpha_m; al.v = h->buf.alpha_v;
+  al.logp = w.logp; al.seg_start = w.seg_start; al.slot_src = w.slot_src; al.steps = h->buf.steps; al.logs = h->buf.logs;
+  al.T_local = c.num_local_tasks; al.target_entropy = c.target_entropy; al.inv_b = inv_b;
+  al.lr = c.alpha_lr; al.b1 = c.adam_b1; al.b2 = c.adam_b2; al.eps = c.adam_eps; al.max_norm = c.alpha_max_grad_norm;
+  alpha_step_kernel<<<1, 1024, c.num_local_tasks * sizeof(float), st>>>(al);
+  LAUNCHED(h);
+  MTRL_CUDA_CHECK(cudaGetLastError());
+  return MTRL_OK;
+}
+
+extern "C" int mtrl_sac_update(mtrl_sac_t* h, const float* obs, const float* actions, const float* next_obs,
+                               const float* dones, const float* rewards, int batch, int global_batch, const float* eps_c,
+                               const float* eps_a, void* stream) {
+  MTRL_PROPAGATE(mtrl_sac_phase1_critic_grads(h, obs, actions, next_obs, dones, rewards, batch, global_batch, eps_c, eps_a, stream));
+  MTRL_PROPAGATE(mtrl_sac_phase2_critic_step_actor_grads(h, stream));
+  MTRL_PROPAGATE(mtrl_sac_phase3_actor_step_alpha(h, stream));
+  return MTRL_OK;
+}
+
+extern "C" int mtrl_sac_launches_per_update(const mtrl_sac_t* h) { return h ? h->launches : 0; }
+// Device int[4] written by the packing kernel: [0] != 0 means the last batch was rejected
+// (1: a row's task is outside this handle's range, 2: rows do not fit max_rows).
+extern "C" int mtrl_sac_read_status_async(const mtrl_sac_t* h, int* host_pinned4, void* stream) {
+  MTRL_REQUIRE(h && host_pinned4, "mtrl_sac_read_status_async: null argument");
+  MTRL_CUDA_CHECK(cudaMemcpyAsync(host_pinned4, h->ws.status, 16, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+  return MTRL_OK;
+}

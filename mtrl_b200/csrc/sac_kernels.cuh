@@ -1,0 +1,745 @@
+// Non-GEMM kernels of the MT-SAC update (HBM-bound elementwise / reduction work):
+// batch packing, per-task heads, the fused SAC losses, bias gradients, the multi-tensor
+// Adam + global-norm clip + Polyak step and the temperature step.
+// Reference semantics: mtrl/rl/algorithms/mtsac.py:513-731, 1173-1247 (see sac.cu for the sequence).
+#pragma once
+
+#include <curand_kernel.h>
+
+#include "common.cuh"
+#include "mtrl_b200.h"
+
+namespace sac {
+
+constexpr int kTileRows = 128;   // rows of one task are padded to a multiple of the GEMM M tile
+constexpr int kMaxE = 4;
+constexpr int kMaxA = 8;
+constexpr int kColsumSplits = 32;
+
+// accumulators (double, zeroed at the start of every update)
+enum {
+  ACC_QLOSS = 0, ACC_QSUM, ACC_CRITIC_G2, ACC_CRITIC_P2_TRUNK, ACC_CRITIC_P2_HEAD, ACC_CRITIC_HEAD_G2,
+  ACC_ACTOR_LOSS, ACC_ACTOR_G2, ACC_ACTOR_P2_TRUNK, ACC_ACTOR_P2_HEAD, ACC_ACTOR_HEAD_G2,
+  ACC_COUNT = 16
+};
+
+// extra (non reference) log slots used to combine ranks: squared norms that are per-rank partial
+enum { LOG_X_CRITIC_P2_TRUNK = 10, LOG_X_CRITIC_P2_HEAD = 11, LOG_X_ACTOR_P2_TRUNK = 12, LOG_X_ACTOR_P2_HEAD = 13 };
+
+__device__ __forceinline__ float block_sum(float v, float* smem) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) smem[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    v = lane < (blockDim.x + 31) / 32 ? smem[lane] : 0.f;
+    v = warp_sum(v);
+  }
+  return v;  // valid in warp 0
+}
+__device__ __forceinline__ double block_sum(double v, double* smem) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) smem[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    v = lane < (blockDim.x + 31) / 32 ? smem[lane] : 0.0;
+    v = warp_sum(v);
+  }
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Packing: rows arrive in any order (the reference batch is (sample, task) interleaved,
+// buffers.py:547-548); internally rows are task-major with each task padded to 128-row tiles so a
+// GEMM M tile belongs to one task (own-task head only).
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_plan_kernel(const float* __restrict__ obs, int B, int obs_dim, int T, int task_begin, int T_local,
+                                 int max_rows, int* __restrict__ row_slot, int* __restrict__ slot_src,
+                                 int* __restrict__ tile_task, int* __restrict__ seg_start, int* __restrict__ status) {
+  extern __shared__ int sm[];
+  const int nchunks = (B + 31) / 32;
+  int* counts = sm;                       // [nchunks][T_local]
+  int* seg = sm + nchunks * T_local;      // [T_local + 1]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  for (int i = tid; i < nchunks * T_local; i += blockDim.x) counts[i] = 0;
+  for (int i = tid; i < max_rows; i += blockDim.x) slot_src[i] = -1;
+  __syncthreads();
+  // pass 1: task of every row (first arg-max of the one-hot, like jnp.argmax), per-chunk histograms
+  for (int c = warp; c < nchunks; c += nwarps) {
+    const int row = c * 32 + lane;
+    int task = -1;
+    if (row < B) {
+      const float* oh = obs + static_cast<long long>(row) * obs_dim + (obs_dim - T);
+      float best = oh[0];
+      int bi = 0;
+      for (int t = 1; t < T; ++t) {
+        const float v = oh[t];
+        if (v > best) { best = v; bi = t; }
+      }
+      task = bi - task_begin;
+      if (task < 0 || task >= T_local) { atomicExch(status, 1); task = -1; }
+      row_slot[row] = task;  // stash
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, task);
+    if (task >= 0 && lane == __ffs(peers) - 1) counts[c * T_local + task] = __popc(peers);
+  }
+  __syncthreads();
+  // pass 2: exclusive scan over chunks per task
+  for (int t = tid; t < T_local; t += blockDim.x) {
+    int run = 0;
+    for (int c = 0; c < nchunks; ++c) {
+      const int v = counts[c * T_local + t];
+      counts[c * T_local + t] = run;
+      run += v;
+    }
+    seg[t] = run;  // rows of task t
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int off = 0;
+    for (int t = 0; t < T_local; ++t) {
+      const int n = seg[t];
+      const int padded = (n + kTileRows - 1) / kTileRows * kTileRows;
+      seg[t] = off;
+      seg_start[t] = off;
+      if (off + padded > max_rows) { atomicExch(status, 2); break; }
+      for (int tile = off / kTileRows; tile < (off + padded) / kTileRows; ++tile) tile_task[tile] = t;
+      off += padded;
+    }
+    seg[T_local] = off;
+    seg_start[T_local] = off;
+    for (int tile = off / kTileRows; tile < max_rows / kTileRows; ++tile) tile_task[tile] = 0;
+  }
+  __syncthreads();
+  if (*status) return;
+  // pass 3: slot of every row (stable within a task)
+  for (int c = warp; c < nchunks; c += nwarps) {
+    const int row = c * 32 + lane;
+    const int task = row < B ? row_slot[row] : -1;
+    const unsigned peers = __match_any_sync(0xffffffffu, task);
+    if (task >= 0) {
+      const int rank = __popc(peers & ((1u << lane) - 1u));
+      const int slot = seg[task] + counts[c * T_local + task] + rank;
+      row_slot[row] = slot;
+      slot_src[slot] = row;
+    }
+  }
+}
+
+struct PackArgs {
+  const float *obs, *actions, *next_obs, *dones, *rewards, *eps_c, *eps_a;
+  float *Xa_next, *Xa, *Xc_next, *Xc, *rew, *done, *peps_c, *peps_a;
+  const int* slot_src;
+  const int* noise_counter;
+  unsigned long long seed;
+  int obs_dim, act_dim, Ka, Kc;
+};
+
+// One block per packed row.  Inputs are rounded to tf32 here (they are GEMM A operands).
+__global__ void pack_rows_kernel(const PackArgs a) {
+  const int slot = blockIdx.x;
+  const int src = a.slot_src[slot];
+  const int A = a.act_dim, od = a.obs_dim;
+  float* xa = a.Xa + static_cast<long long>(slot) * a.Ka;
+  float* xan = a.Xa_next + static_cast<long long>(slot) * a.Ka;
+  float* xc = a.Xc + static_cast<long long>(slot) * a.Kc;
+  float* xcn = a.Xc_next + static_cast<long long>(slot) * a.Kc;
+  if (src < 0) {
+    for (int j = threadIdx.x; j < a.Ka; j += blockDim.x) { xa[j] = 0.f; xan[j] = 0.f; }
+    for (int j = threadIdx.x; j < a.Kc; j += blockDim.x) { xc[j] = 0.f; xcn[j] = 0.f; }
+    if (threadIdx.x < A) { a.peps_c[slot * A + threadIdx.x] = 0.f; a.peps_a[slot * A + threadIdx.x] = 0.f; }
+    if (threadIdx.x == 0) { a.rew[slot] = 0.f; a.done[slot] = 0.f; }
+    return;
+  }
+  const float* o = a.obs + static_cast<long long>(src) * od;
+  const float* on = a.next_obs + static_cast<long long>(src) * od;
+  for (int j = threadIdx.x; j < a.Ka; j += blockDim.x) {
+    const float v = j < od ? tf32_rna(o[j]) : 0.f;
+    const float vn = j < od ? tf32_rna(on[j]) : 0.f;
+    xa[j] = v;
+    xan[j] = vn;
+  }
+  for (int j = threadIdx.x; j < a.Kc; j += blockDim.x) {
+    float v = 0.f, vn = 0.f;
+    if (j < A) v = tf32_rna(a.actions[static_cast<long long>(src) * A + j]);   // (action, state) order, networks.py:61
+    else if (j < A + od) { v = tf32_rna(o[j - A]); vn = tf32_rna(on[j - A]); }
+    xc[j] = v;
+    xcn[j] = vn;  // action columns of the next-state input are filled by the actor sample
+  }
+  if (threadIdx.x == 0) {
+    a.rew[slot] = a.rewards[src];
+    a.done[slot] = a.dones[src];
+    if (a.eps_c && a.eps_a) {
+      for (int d = 0; d < A; ++d) {
+        a.peps_c[slot * A + d] = a.eps_c[static_cast<long long>(src) * A + d];
+        a.peps_a[slot * A + d] = a.eps_a[static_cast<long long>(src) * A + d];
+      }
+    } else {
+      curandStatePhilox4_32_10_t st;
+      curand_init(a.seed, static_cast<unsigned long long>(src), static_cast<unsigned long long>(*a.noise_counter) * 32ull, &st);
+      for (int d = 0; d < A; d += 4) {
+        const float4 n = curand_normal4(&st);
+        const float nn[4] = {n.x, n.y, n.z, n.w};
+        for (int q = 0; q < 4 && d + q < A; ++q) a.peps_c[slot * A + d + q] = nn[q];
+      }
+      for (int d = 0; d < A; d += 4) {
+        const float4 n = curand_normal4(&st);
+        const float nn[4] = {n.x, n.y, n.z, n.w};
+        for (int q = 0; q < 4 && d + q < A; ++q) a.peps_a[slot * A + d + q] = nn[q];
+      }
+    }
+  }
+}
+
+// alpha_t = exp(log_alpha_t) (MultiTaskTemperature, mtsac.py:60-63); w_t = T * softmax(-log_alpha)_t
+// (extract_task_weights, mtsac.py:103-113) or 1.
+__global__ void alpha_prep_kernel(const float* __restrict__ log_alpha, int T_local, int use_w, float* __restrict__ alpha_val,
+                                  float* __restrict__ task_w) {
+  if (blockIdx.x != 0) return;
+  __shared__ float red[32];
+  float mx = -INFINITY;
+  for (int t = threadIdx.x; t < T_local; t += blockDim.x) mx = fmaxf(mx, -log_alpha[t]);
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int w = 1; w < (blockDim.x + 31) / 32; ++w) mx = fmaxf(mx, red[w]);
+  __syncthreads();
+  float s = 0.f;
+  for (int t = threadIdx.x; t < T_local; t += blockDim.x) s += expf(-log_alpha[t] - mx);
+  s = block_sum(s, red);
+  __shared__ float denom;
+  if (threadIdx.x == 0) denom = s;
+  __syncthreads();
+  for (int t = threadIdx.x; t < T_local; t += blockDim.x) {
+    alpha_val[t] = expf(log_alpha[t]);
+    task_w[t] = use_w ? expf(-log_alpha[t] - mx) / denom * static_cast<float>(T_local) : 1.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Actor head + tanh-Gaussian sample and log-prob (networks.py:29-45, nn/distributions.py:6-16).
+// One warp per packed row.
+// ---------------------------------------------------------------------------------------------
+struct ActorHeadArgs {
+  const float* H;        // [M][W] last trunk activation
+  const float* Wh;       // (T_local, W, 2A)
+  const float* bh;       // (T_local, 2A)
+  const int* tile_task;
+  const int* slot_src;
+  const float* eps;      // [M][A] packed
+  float* Xdst;           // critic input buffer whose columns [0, A) receive tf32(a)
+  int ldx;
+  float* act;            // [M][A] (may be null)
+  float* logp;           // [M]
+  float* logstd;         // [M][A] clipped (may be null)
+  unsigned* inrange;     // [M] (may be null)
+  int M, W;
+  float ls_min, ls_max;
+};
+
+template <int A>
+__global__ void actor_head_kernel(const ActorHeadArgs p) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= p.M) return;
+  const bool valid = p.slot_src[row] >= 0;
+  const int t = p.tile_task[row / kTileRows];
+  float acc[2 * A];
+#pragma unroll
+  for (int j = 0; j < 2 * A; ++j) acc[j] = 0.f;
+  if (valid) {
+    const float* h = p.H + static_cast<long long>(row) * p.W;
+    const float* w = p.Wh + static_cast<long long>(t) * p.W * (2 * A);
+    for (int k = lane; k < p.W; k += 32) {
+      const float hv = h[k];
+      const float* wk = w + static_cast<long long>(k) * (2 * A);
+#pragma unroll
+      for (int j = 0; j < 2 * A; ++j) acc[j] = fmaf(hv, __ldg(wk + j), acc[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 2 * A; ++j) acc[j] = warp_sum(acc[j]);
+  float lp = 0.f;
+  unsigned mask = 0;
+  if (lane < A) {
+    const int d = lane;
+    float mean = 0.f, ls_raw = 0.f;
+#pragma unroll
+    for (int j = 0; j < A; ++j) {
+      if (j == d) { mean = acc[j]; ls_raw = acc[A + j]; }
+    }
+    float a = 0.f, ls = 0.f;
+    if (valid) {
+      mean += p.bh[t * 2 * A + d];
+      ls_raw += p.bh[t * 2 * A + A + d];
+      ls = fminf(fmaxf(ls_raw, p.ls_min), p.ls_max);
+      const float sd = expf(ls);
+      const float e = p.eps[row * A + d];
+      const float x = fmaf(sd, e, mean);
+      a = tanhf(x);
+      const float z = -2.f * x;
+      const float softplus = z > 0.f ? z + log1pf(expf(-z)) : log1pf(expf(z));
+      const float fldj = 2.f * (0.69314718055994531f - x - softplus);
+      lp = -0.5f * e * e - 0.91893853320467274f - ls - fldj;
+      if (ls_raw > p.ls_min && ls_raw < p.ls_max) mask = 1u << d;
+    }
+    p.Xdst[static_cast<long long>(row) * p.ldx + d] = tf32_rna(a);
+    if (p.act) p.act[row * A + d] = a;
+    if (p.logstd) p.logstd[row * A + d] = ls;
+  }
+  lp = warp_sum(lp);
+  for (int o = 16; o > 0; o >>= 1) mask |= __shfl_xor_sync(0xffffffffu, mask, o);
+  if (lane == 0) {
+    p.logp[row] = lp;
+    if (p.inrange) p.inrange[row] = mask;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Critic heads + losses.  One warp per packed row; E members.
+// ---------------------------------------------------------------------------------------------
+struct QHeads {
+  const float* H[kMaxE];   // [M][W] last trunk activation of member e
+  const float* w[kMaxE];   // (T_local, W, 1)
+  const float* b[kMaxE];   // (T_local, 1)
+};
+
+__device__ __forceinline__ float row_dot(const float* __restrict__ h, const float* __restrict__ w, int W, int lane) {
+  float s = 0.f;
+  const float4* h4 = reinterpret_cast<const float4*>(h);
+  const float4* w4 = reinterpret_cast<const float4*>(w);
+  for (int k = lane; k < W / 4; k += 32) {
+    const float4 a = h4[k];
+    const float4 c = __ldg(w4 + k);
+    s = fmaf(a.x, c.x, s);
+    s = fmaf(a.y, c.y, s);
+    s = fmaf(a.z, c.z, s);
+    s = fmaf(a.w, c.w, s);
+  }
+  return warp_sum(s);
+}
+
+struct CriticLossArgs {
+  QHeads target, online;
+  const int* tile_task;
+  const int* slot_src;
+  const float *rew, *done, *logp_next, *alpha_val, *task_w;
+  float* dq;       // [E][M]
+  double* acc;
+  int M, W, E;
+  float gamma, inv_eb;  // 1 / (E * B_global)
+  int clip;
+};
+
+// y = r + (1-d) gamma (min_e Qbar_e - alpha logp')   (mtsac.py:547-553)
+// L = mean_{e,b} w (Q_e - y)^2                        (mtsac.py:562-565);  dq_e = dL/dQ_e
+__global__ void critic_loss_kernel(const CriticLossArgs p) {
+  __shared__ double red[32];
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  double loss = 0.0, qsum = 0.0;
+  if (row < p.M) {
+    const bool valid = p.slot_src[row] >= 0;
+    const int t = p.tile_task[row / kTileRows];
+    float qt_min = INFINITY;
+    float q[kMaxE];
+#pragma unroll
+    for (int e = 0; e < kMaxE; ++e) {
+      q[e] = 0.f;
+      if (e < p.E && valid) {
+        const long long ro = static_cast<long long>(row) * p.W, wo = static_cast<long long>(t) * p.W;
+        const float qt = row_dot(p.target.H[e] + ro, p.target.w[e] + wo, p.W, lane) + p.target.b[e][t];
+        qt_min = fminf(qt_min, qt);
+        q[e] = row_dot(p.online.H[e] + ro, p.online.w[e] + wo, p.W, lane) + p.online.b[e][t];
+      }
+    }
+    if (lane == 0) {
+      if (valid) {
+        const float w = p.task_w[t];
+        float y = p.rew[row] + (1.f - p.done[row]) * p.gamma * (qt_min - p.alpha_val[t] * p.logp_next[row]);
+        if (p.clip) y = fminf(fmaxf(y, -5000.f), 5000.f);
+#pragma unroll
+        for (int e = 0; e < kMaxE; ++e) {
+          if (e < p.E) {
+            float qc = q[e];
+            float pass = 1.f;
+            if (p.clip) {
+              qc = fminf(fmaxf(qc, -5000.f), 5000.f);
+              pass = (q[e] > -5000.f && q[e] < 5000.f) ? 1.f : 0.f;
+            }
+            const float diff = qc - y;
+            loss += static_cast<double>(w * diff * diff);
+            qsum += static_cast<double>(qc);
+            p.dq[static_cast<long long>(e) * p.M + row] = 2.f * w * diff * p.inv_eb * pass;
+          }
+        }
+      } else {
+        for (int e = 0; e < p.E; ++e) p.dq[static_cast<long long>(e) * p.M + row] = 0.f;
+      }
+    }
+  }
+  loss = block_sum(loss, red);
+  qsum = block_sum(qsum, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(p.acc + ACC_QLOSS, loss);
+    atomicAdd(p.acc + ACC_QSUM, qsum);
+  }
+}
+
+struct ActorLossArgs {
+  QHeads online;
+  const int* tile_task;
+  const int* slot_src;
+  const float *logp, *alpha_val, *task_w;
+  float* dq;  // [E][M] seeds dL/dQ_e
+  double* acc;
+  int M, W, E;
+  float inv_b;  // 1 / B_global
+};
+
+// L = mean_b w (alpha logp - min_e Q_e(s, a))   (mtsac.py:659-666); min routes the gradient to the arg-min.
+__global__ void actor_loss_kernel(const ActorLossArgs p) {
+  __shared__ double red[32];
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  double loss = 0.0;
+  if (row < p.M) {
+    const bool valid = p.slot_src[row] >= 0;
+    const int t = p.tile_task[row / kTileRows];
+    float q[kMaxE];
+    float qmin = INFINITY;
+#pragma unroll
+    for (int e = 0; e < kMaxE; ++e) {
+      q[e] = INFINITY;
+      if (e < p.E && valid) {
+        q[e] = row_dot(p.online.H[e] + static_cast<long long>(row) * p.W, p.online.w[e] + static_cast<long long>(t) * p.W,
+                       p.W, lane) + p.online.b[e][t];
+        qmin = fminf(qmin, q[e]);
+      }
+    }
+    if (lane == 0) {
+      if (valid) {
+        const float w = p.task_w[t];
+        loss = static_cast<double>(w * (p.alpha_val[t] * p.logp[row] - qmin));
+        int ties = 0;
+#pragma unroll
+        for (int e = 0; e < kMaxE; ++e) ties += (e < p.E && q[e] == qmin) ? 1 : 0;
+        const float seed = -w * p.inv_b / static_cast<float>(ties);
+#pragma unroll
+        for (int e = 0; e < kMaxE; ++e)
+          if (e < p.E) p.dq[static_cast<long long>(e) * p.M + row] = (q[e] == qmin) ? seed : 0.f;
+      } else {
+        for (int e = 0; e < p.E; ++e) p.dq[static_cast<long long>(e) * p.M + row] = 0.f;
+      }
+    }
+  }
+  loss = block_sum(loss, red);
+  if (threadIdx.x == 0) atomicAdd(p.acc + ACC_ACTOR_LOSS, loss);
+}
+
+// dL/d(head output) of the actor from dL/da (through the critics) and dL/dlogp = alpha w / B
+// (SURVEY Appendix A): gx = da (1 - a^2) + gl 2a; dmu = gx; dl = (gx sigma eps - gl) [l strictly inside the clip].
+struct ActorDoutArgs {
+  const float* dXin;   // [E][M][16], columns [0, A) = dL/da through member e
+  const float *act, *logstd, *eps, *alpha_val, *task_w;
+  const unsigned* inrange;
+  const int* tile_task;
+  const int* slot_src;
+  float* dout;         // [M][2A]
+  int M, E, A;
+  float inv_b;
+};
+
+__global__ void actor_dout_kernel(const ActorDoutArgs p) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= p.M) return;
+  const int A = p.A;
+  if (p.slot_src[row] < 0) {
+    for (int j = 0; j < 2 * A; ++j) p.dout[row * 2 * A + j] = 0.f;
+    return;
+  }
+  const int t = p.tile_task[row / kTileRows];
+  const float gl = p.alpha_val[t] * p.task_w[t] * p.inv_b;
+  const unsigned m = p.inrange[row];
+  for (int d = 0; d < A; ++d) {
+    float da = 0.f;
+    for (int e = 0; e < p.E; ++e) da += p.dXin[(static_cast<long long>(e) * p.M + row) * 16 + d];
+    const float a = p.act[row * A + d];
+    const float gx = da * (1.f - a * a) + gl * 2.f * a;
+    const float sd = expf(p.logstd[row * A + d]);
+    p.dout[row * 2 * A + d] = gx;
+    p.dout[row * 2 * A + A + d] = ((m >> d) & 1u) ? (gx * sd * p.eps[row * A + d] - gl) : 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Head VJP (nn.vmap(Dense) heads, multi_head.py:50-66, own-task rows only):
+//   dZ[row,k]   = (sum_j dout[row,j] Wh[t,k,j]) * (H[row,k] > 0)      (masked by the trunk's last ReLU)
+//   dWh[t,k,j]  = sum_{rows of t} H[row,k] dout[row,j];   dbh[t,j] = sum_{rows of t} dout[row,j]
+// grid (W/128, T_local, E); a thread owns one hidden unit k and walks the task's rows.
+// ---------------------------------------------------------------------------------------------
+struct HeadBwdArgs {
+  const float* H[kMaxE];
+  const float* dout[kMaxE];   // [M][HD]
+  const float* Wh[kMaxE];     // (T_local, W, HD)
+  float* dZ[kMaxE];           // [M][W]
+  float* dWh[kMaxE];          // may be null (no weight gradients)
+  float* dbh[kMaxE];
+  const int* seg_start;
+  int M, W;
+};
+
+template <int HD>
+__global__ void head_bwd_kernel(const HeadBwdArgs p) {
+  __shared__ float sd[kTileRows * HD];
+  const int e = blockIdx.z, t = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool kok = k < p.W;
+  const int r0 = p.seg_start[t], r1 = p.seg_start[t + 1];
+  const float* H = p.H[e];
+  const float* dout = p.dout[e];
+  float* dZ = p.dZ[e];
+  float w[HD], acc[HD];
+#pragma unroll
+  for (int j = 0; j < HD; ++j) {
+    acc[j] = 0.f;
+    w[j] = kok ? p.Wh[e][(static_cast<long long>(t) * p.W + k) * HD + j] : 0.f;
+  }
+  float bsum = 0.f;  // threads j < HD of block x == 0 accumulate the bias gradient
+  for (int base = r0; base < r1; base += kTileRows) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kTileRows * HD; i += blockDim.x) sd[i] = dout[static_cast<long long>(base) * HD + i];
+    __syncthreads();
+    if (kok) {
+#pragma unroll 4
+      for (int r = 0; r < kTileRows; ++r) {
+        const float h = H[static_cast<long long>(base + r) * p.W + k];
+        float dz = 0.f;
+#pragma unroll
+        for (int j = 0; j < HD; ++j) {
+          const float d = sd[r * HD + j];
+          acc[j] = fmaf(h, d, acc[j]);
+          dz = fmaf(d, w[j], dz);
+        }
+        dZ[static_cast<long long>(base + r) * p.W + k] = h > 0.f ? tf32_rna(dz) : 0.f;
+      }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < HD)
+      for (int r = 0; r < kTileRows; ++r) bsum += sd[r * HD + threadIdx.x];
+  }
+  if (p.dWh[e]) {
+    if (kok) {
+#pragma unroll
+      for (int j = 0; j < HD; ++j) p.dWh[e][(static_cast<long long>(t) * p.W + k) * HD + j] = acc[j];
+    }
+    if (blockIdx.x == 0 && threadIdx.x < HD) p.dbh[e][t * HD + threadIdx.x] = bsum;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bias gradients: column sums of dZ.  Two stages keep the sum order fixed (no float atomics).
+// ---------------------------------------------------------------------------------------------
+struct ColsumJobs {
+  const float* src[kMaxE];
+  float* dst[kMaxE];
+  int njobs;
+};
+
+__global__ void colsum_partial_kernel(const ColsumJobs jobs, int M, int W, float* __restrict__ part) {
+  const int job = blockIdx.z;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= W) return;
+  const int rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
+  const float* s = jobs.src[job];
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int r = r0;
+  for (; r + 4 <= r1; r += 4) {
+    a0 += s[static_cast<long long>(r) * W + k];
+    a1 += s[static_cast<long long>(r + 1) * W + k];
+    a2 += s[static_cast<long long>(r + 2) * W + k];
+    a3 += s[static_cast<long long>(r + 3) * W + k];
+  }
+  for (; r < r1; ++r) a0 += s[static_cast<long long>(r) * W + k];
+  part[(static_cast<long long>(job) * gridDim.y + blockIdx.y) * W + k] = (a0 + a1) + (a2 + a3);
+}
+
+__global__ void colsum_final_kernel(const ColsumJobs jobs, int splits, int W, const float* __restrict__ part) {
+  const int job = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= W) return;
+  float a = 0.f;
+  for (int s = 0; s < splits; ++s) a += part[(static_cast<long long>(job) * splits + s) * W + k];
+  jobs.dst[job][k] = a;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Optimiser: optax.chain(clip_by_global_norm, adam) + apply_updates (config/optim.py:26-43,
+// algorithms/utils.py:11-46) over the flat parameter buffer of a network, fused with the Polyak
+// target update (mtsac.py:607-613) and the tf32 operand copies the GEMMs read.
+// ---------------------------------------------------------------------------------------------
+__global__ void sumsq_kernel(const float* __restrict__ x, long long n, double* __restrict__ acc) {
+  __shared__ double red[32];
+  double s = 0.0;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long n4 = n / 4;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = x4[i];
+    s += static_cast<double>(v.x * v.x + v.y * v.y) + static_cast<double>(v.z * v.z + v.w * v.w);
+  }
+  for (long long i = n4 * 4 + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    s += static_cast<double>(x[i] * x[i]);
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) atomicAdd(acc, s);
+}
+
+// grads[slot] = local head-gradient squared norm, so one all-reduce of [trunk | slots] carries it.
+__global__ void write_slot_kernel(float* __restrict__ slot, const double* __restrict__ acc) { *slot = static_cast<float>(*acc); }
+
+struct AdamArgs {
+  float *p, *m, *v, *shadow;
+  const float* g;
+  float *target, *target_shadow;     // null for networks without a target
+  long long n;
+  long long trunk_n;                 // elements [0, trunk_n) count into the trunk param norm, the rest into the head norm;
+                                     // [trunk_n, trunk_n + 32) are the reduction slots, not parameters
+  const double* g2_trunk;            // squared norm of the (all-reduced) trunk gradients
+  const float* g2_heads;             // all-reduced slot: squared norm of every rank's head gradients
+  const int* step;                   // Adam count before this step
+  double* p2_trunk;
+  double* p2_head;
+  float lr, b1, b2, eps, max_norm, tau;
+};
+
+__global__ void adam_kernel(const AdamArgs a) {
+  __shared__ double red[32];
+  const double g2 = *a.g2_trunk + static_cast<double>(*a.g2_heads);
+  const float gn = static_cast<float>(sqrt(g2));
+  // optax.clip_by_global_norm: g if norm < max else g / norm * max
+  const float scale = (a.max_norm > 0.f && !(gn < a.max_norm)) ? a.max_norm / gn : 1.f;
+  const int t = *a.step + 1;
+  const float bc1 = static_cast<float>(1.0 - pow(static_cast<double>(a.b1), static_cast<double>(t)));
+  const float bc2 = static_cast<float>(1.0 - pow(static_cast<double>(a.b2), static_cast<double>(t)));
+  double s_trunk = 0.0, s_head = 0.0;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+    if (i >= a.trunk_n && i < a.trunk_n + 32) continue;
+    const float g = a.g[i] * scale;
+    const float m = a.b1 * a.m[i] + (1.f - a.b1) * g;
+    const float v = a.b2 * a.v[i] + (1.f - a.b2) * g * g;
+    const float p = a.p[i] - a.lr * (m / bc1) / (sqrtf(v / bc2) + a.eps);
+    a.m[i] = m;
+    a.v[i] = v;
+    a.p[i] = p;
+    a.shadow[i] = tf32_rna(p);
+    if (a.target) {
+      const float tg = a.tau * p + (1.f - a.tau) * a.target[i];
+      a.target[i] = tg;
+      a.target_shadow[i] = tf32_rna(tg);
+    }
+    if (i < a.trunk_n) s_trunk += static_cast<double>(p) * p;
+    else s_head += static_cast<double>(p) * p;
+  }
+  s_trunk = block_sum(s_trunk, red);
+  s_head = block_sum(s_head, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(a.p2_trunk, s_trunk);
+    atomicAdd(a.p2_head, s_head);
+  }
+}
+
+__global__ void shadow_kernel(const float* __restrict__ p, float* __restrict__ s, long long n) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) s[i] = tf32_rna(p[i]);
+}
+
+// Single thread: turn accumulators into the reference's log scalars and advance the Adam count.
+__global__ void finalize_critic_kernel(const double* acc, const float* g2_heads, int* steps, float* logs, float inv_eb) {
+  logs[MTRL_LOG_QF_VALUES] = static_cast<float>(acc[ACC_QSUM] * inv_eb);
+  logs[MTRL_LOG_QF_LOSS] = static_cast<float>(acc[ACC_QLOSS] * inv_eb);
+  logs[MTRL_LOG_CRITIC_GRAD_MAGNITUDE] = static_cast<float>(sqrt(acc[ACC_CRITIC_G2] + static_cast<double>(*g2_heads)));
+  logs[MTRL_LOG_CRITIC_PARAMS_NORM] = static_cast<float>(sqrt(acc[ACC_CRITIC_P2_TRUNK] + acc[ACC_CRITIC_P2_HEAD]));
+  logs[LOG_X_CRITIC_P2_TRUNK] = static_cast<float>(acc[ACC_CRITIC_P2_TRUNK]);
+  logs[LOG_X_CRITIC_P2_HEAD] = static_cast<float>(acc[ACC_CRITIC_P2_HEAD]);
+  steps[1] += 1;
+}
+__global__ void finalize_actor_kernel(const double* acc, const float* g2_heads, int* steps, float* logs, float inv_b) {
+  logs[MTRL_LOG_ACTOR_LOSS] = static_cast<float>(acc[ACC_ACTOR_LOSS] * inv_b);
+  logs[MTRL_LOG_ACTOR_GRAD_MAGNITUDE] = static_cast<float>(sqrt(acc[ACC_ACTOR_G2] + static_cast<double>(*g2_heads)));
+  logs[MTRL_LOG_ACTOR_PARAMS_NORM] = static_cast<float>(sqrt(acc[ACC_ACTOR_P2_TRUNK] + acc[ACC_ACTOR_P2_HEAD]));
+  logs[LOG_X_ACTOR_P2_TRUNK] = static_cast<float>(acc[ACC_ACTOR_P2_TRUNK]);
+  logs[LOG_X_ACTOR_P2_HEAD] = static_cast<float>(acc[ACC_ACTOR_P2_HEAD]);
+  logs[MTRL_LOG_EXPLORE_LOSS] = 0.f;  // explore=False (mtsac.py:277, 671)
+  steps[0] += 1;
+  steps[3] += 1;  // noise counter
+}
+
+// Temperature step (mtsac.py:713-731): L = mean_b -log_alpha[task_b] (logp_b + target_entropy); Adam on log_alpha.
+// One block; warp per task over that task's packed rows.
+struct AlphaArgs {
+  float *log_alpha, *m, *v;
+  const float* logp;
+  const int* seg_start;
+  const int* slot_src;
+  int* steps;
+  float* logs;
+  int T_local;
+  float target_entropy, inv_b, lr, b1, b2, eps, max_norm;
+};
+
+__global__ void alpha_step_kernel(const AlphaArgs a) {
+  extern __shared__ float sg[];  // [T_local] gradients
+  __shared__ float red[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float loss = 0.f;
+  for (int t = warp; t < a.T_local; t += nw) {
+    float s = 0.f;
+    for (int r = a.seg_start[t] + lane; r < a.seg_start[t + 1]; r += 32)
+      if (a.slot_src[r] >= 0) s += a.logp[r] + a.target_entropy;
+    s = warp_sum(s);
+    if (lane == 0) {
+      sg[t] = -s * a.inv_b;
+      loss += -a.log_alpha[t] * s * a.inv_b;
+    }
+  }
+  loss = block_sum(loss, red);
+  __shared__ float sh_loss, sh_scale;
+  if (threadIdx.x == 0) sh_loss = loss;
+  __syncthreads();
+  float g2 = 0.f;
+  for (int t = threadIdx.x; t < a.T_local; t += blockDim.x) g2 += sg[t] * sg[t];
+  g2 = block_sum(g2, red);
+  if (threadIdx.x == 0) {
+    const float gn = sqrtf(g2);
+    sh_scale = (a.max_norm > 0.f && !(gn < a.max_norm)) ? a.max_norm / gn : 1.f;
+  }
+  __syncthreads();
+  const int tstep = a.steps[2] + 1;
+  const float bc1 = static_cast<float>(1.0 - pow(static_cast<double>(a.b1), static_cast<double>(tstep)));
+  const float bc2 = static_cast<float>(1.0 - pow(static_cast<double>(a.b2), static_cast<double>(tstep)));
+  float asum = 0.f;
+  for (int t = threadIdx.x; t < a.T_local; t += blockDim.x) {
+    const float g = sg[t] * sh_scale;
+    const float m = a.b1 * a.m[t] + (1.f - a.b1) * g;
+    const float v = a.b2 * a.v[t] + (1.f - a.b2) * g * g;
+    const float la = a.log_alpha[t] - a.lr * (m / bc1) / (sqrtf(v / bc2) + a.eps);
+    a.m[t] = m;
+    a.v[t] = v;
+    a.log_alpha[t] = la;
+    asum += expf(la);
+  }
+  asum = block_sum(asum, red);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    a.logs[MTRL_LOG_ALPHA_LOSS] = sh_loss;
+    a.logs[MTRL_LOG_ALPHA] = asum;
+    a.steps[2] = tstep;
+  }
+}
+
+}  // namespace sac

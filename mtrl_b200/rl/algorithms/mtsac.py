@@ -1,0 +1,378 @@
+"""Mirror of `mtrl.rl.algorithms.mtsac.MTSAC` (/root/reference/mtrl/rl/algorithms/mtsac.py:116-311,
+1173-1251) on top of the fused CUDA update (csrc/sac.cu, C-ABI `mtrl_sac_*`).
+
+Same surface: `MTSACConfig`, `MTSAC.initialize(config, env_config, seed)`, `update(data) -> (self,
+logs)`, `get_num_params()`, state fields `actor`, `critic` (with `.target_params`), `alpha`, each a
+TrainState-like object with `step`, `params`, `opt_state`.  Parameter trees carry the Flax names
+(`layer_i/kernel (in, W)`, `VmapDense_0/kernel (T, W, head)`, critic under `VmapQValueFunction_0`
+with a leading ensemble axis) as zero-copy views of the flat device buffers the kernels use.
+
+Deliberate differences: the update is in place and returns `self` (the
+reference returns a new immutable pytree); noise comes from in-kernel Philox unless `eps_c/eps_a`
+are passed (jax.random streams cannot be reproduced without JAX).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+import math
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from ... import _lib as L
+from ...config.networks import ContinuousActionPolicyConfig, QValueFunctionConfig
+from ...config.nn import MultiHeadConfig
+from ...config.optim import OptimizerConfig
+from ...config.rl import AlgorithmConfig
+from ...nn import get_nn_arch_for_config
+from ...nn.multi_head import uniform
+from ...types import ReplayBufferSamples
+
+MAX_DEPTH = 4
+LOG_KEYS = (
+    "losses/qf_values", "losses/qf_loss", "metrics/critic_grad_magnitude", "metrics/critic_params_norm",
+    "losses/actor_loss", "metrics/actor_grad_magnitude", "metrics/actor_params_norm", "metrics/explore_loss",
+    "losses/alpha_loss", "alpha",
+)  # mtsac.py:616-621, 704-709, 728-731 -- also the order of MTRL_LOG_* in include/mtrl_b200.h
+
+
+class SacConfigC(C.Structure):
+    _fields_ = [
+        ("num_tasks", C.c_int), ("task_begin", C.c_int), ("num_local_tasks", C.c_int), ("obs_dim", C.c_int),
+        ("action_dim", C.c_int), ("width", C.c_int), ("depth", C.c_int), ("num_critics", C.c_int),
+        ("max_rows", C.c_int), ("max_batch", C.c_int),
+        ("gamma", C.c_float), ("tau", C.c_float),
+        ("actor_lr", C.c_float), ("critic_lr", C.c_float), ("alpha_lr", C.c_float),
+        ("adam_b1", C.c_float), ("adam_b2", C.c_float), ("adam_eps", C.c_float),
+        ("actor_max_grad_norm", C.c_float), ("critic_max_grad_norm", C.c_float), ("alpha_max_grad_norm", C.c_float),
+        ("log_std_min", C.c_float), ("log_std_max", C.c_float), ("target_entropy", C.c_float),
+        ("clip_q", C.c_int), ("use_task_weights", C.c_int), ("noise_seed", C.c_ulonglong),
+    ]
+
+
+class NetLayoutC(C.Structure):
+    _fields_ = [
+        ("total", C.c_longlong), ("trunk_total", C.c_longlong), ("slots_off", C.c_longlong), ("heads_base", C.c_longlong),
+        ("member_trunk_stride", C.c_longlong), ("member_head_stride", C.c_longlong),
+        ("kernel_off", C.c_longlong * MAX_DEPTH), ("bias_off", C.c_longlong * MAX_DEPTH),
+        ("head_kernel_off", C.c_longlong), ("head_bias_off", C.c_longlong),
+        ("in_dim", C.c_int), ("head_dim", C.c_int), ("members", C.c_int), ("num_local_tasks", C.c_int),
+        ("width", C.c_int), ("depth", C.c_int),
+    ]
+
+
+class SacLayoutC(C.Structure):
+    _fields_ = [("actor", NetLayoutC), ("critic", NetLayoutC), ("workspace_bytes", C.c_longlong),
+                ("k_actor", C.c_int), ("k_critic", C.c_int)]
+
+
+class SacBuffersC(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "actor_params", "actor_grads", "actor_m", "actor_v", "actor_shadow",
+        "critic_params", "critic_grads", "critic_m", "critic_v", "critic_shadow", "critic_target", "critic_target_shadow",
+        "log_alpha", "alpha_m", "alpha_v", "steps", "logs", "workspace")]
+
+
+_vp, _i = C.c_void_p, C.c_int
+L._EXTRA_DECLS.update({
+    "mtrl_sac_query_layout": ([C.POINTER(SacConfigC), C.POINTER(SacLayoutC)],),
+    "mtrl_sac_create": ([C.POINTER(_vp), C.POINTER(SacConfigC), C.POINTER(SacBuffersC)],),
+    "mtrl_sac_destroy": ([_vp], None),
+    "mtrl_sac_refresh_shadows": ([_vp, _vp],),
+    "mtrl_sac_update": ([_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp],),
+    "mtrl_sac_phase1_critic_grads": ([_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp],),
+    "mtrl_sac_phase2_critic_step_actor_grads": ([_vp, _vp],),
+    "mtrl_sac_phase3_actor_step_alpha": ([_vp, _vp],),
+    "mtrl_sac_launches_per_update": ([_vp],),
+    "mtrl_sac_read_status_async": ([_vp, _vp, _vp],),
+})
+
+
+@dataclasses.dataclass(frozen=True)
+class MTSACConfig(AlgorithmConfig):  # mtsac.py:116-127
+    actor_config: ContinuousActionPolicyConfig = ContinuousActionPolicyConfig()
+    critic_config: QValueFunctionConfig = QValueFunctionConfig()
+    temperature_optimizer_config: OptimizerConfig = OptimizerConfig(max_grad_norm=None)
+    initial_temperature: float = 1.0
+    num_critics: int = 2
+    tau: float = 0.005
+    use_task_weights: bool = False
+    v_min: float = -10.0
+    v_max: float = 10.0
+    n_atoms: int = 51
+
+
+@dataclass
+class TrainState:
+    """Shape of flax.training.train_state.TrainState as the reference uses it (algorithms/utils.py:11-46):
+    `step`, `params`, `opt_state` = (clip state, (ScaleByAdamState(count, mu, nu), ...)) flattened to a dict."""
+    step: torch.Tensor
+    params: dict
+    opt_state: dict
+    tx: object = None
+    apply_fn: object = None
+    target_params: dict | None = None
+    grads: dict | None = None   # not in the reference: the raw (pre-clip) gradients of the last update
+
+
+def task_partition(num_tasks: int, world_size: int) -> list[tuple[int, int]]:
+    """Contiguous task blocks, sizes ceil/floor(T/G): MT50 over 8 -> 7,7,6,6,6,6,6,6."""
+    base, extra = divmod(num_tasks, world_size)
+    out, start = [], 0
+    for r in range(world_size):
+        n = base + (1 if r < extra else 0)
+        out.append((start, start + n))
+        start += n
+    return out
+
+
+def _views(flat: torch.Tensor, lay: NetLayoutC, in_dim: int, ensemble: bool) -> dict:
+    """Flax-named zero-copy views of one network's flat buffer."""
+    W, D, T, E, hd = lay.width, lay.depth, lay.num_local_tasks, lay.members, lay.head_dim
+    tree = {}
+    d = in_dim
+    for i in range(D):
+        k = flat.as_strided((E, d, W), (lay.member_trunk_stride, W, 1), lay.kernel_off[i])
+        b = flat.as_strided((E, W), (lay.member_trunk_stride, 1), lay.bias_off[i])
+        tree[f"layer_{i}"] = {"kernel": k if ensemble else k[0], "bias": b if ensemble else b[0]}
+        d = W
+    hk = flat.as_strided((E, T, W, hd), (lay.member_head_stride, W * hd, hd, 1), lay.heads_base + lay.head_kernel_off)
+    hb = flat.as_strided((E, T, hd), (lay.member_head_stride, hd, 1), lay.heads_base + lay.head_bias_off)
+    tree["VmapDense_0"] = {"kernel": hk if ensemble else hk[0], "bias": hb if ensemble else hb[0]}
+    return tree
+
+
+def _wrap(tree: dict, ensemble: bool) -> dict:
+    inner = {"MultiHeadNetwork_0": tree}
+    return {"params": {"VmapQValueFunction_0": inner} if ensemble else inner}
+
+
+def _tree_copy_(dst: dict, src: dict) -> None:
+    for k, v in src.items():
+        if isinstance(v, dict):
+            _tree_copy_(dst[k], v)
+        else:
+            dst[k].copy_(torch.as_tensor(np.asarray(v) if not isinstance(v, torch.Tensor) else v).to(dst[k].dtype))
+
+
+class MTSAC:
+    """See module docstring."""
+
+    LOG_KEYS = LOG_KEYS
+
+    def __init__(self):
+        raise TypeError("use MTSAC.initialize(config, env_config, seed)")
+
+    # ------------------------------------------------------------------ construction
+    @staticmethod
+    def initialize(config: MTSACConfig, env_config, seed: int = 1, *, max_batch: int | None = None,
+                   max_rows: int | None = None, rank: int = 0, world_size: int = 1, process_group=None,
+                   device: str | torch.device | None = None) -> "MTSAC":
+        """mtsac.py:152-284.  `env_config` needs `.observation_space.shape` and `.action_space.shape`
+        (the observation includes the one-hot task id).  `max_batch` bounds the rows one update may
+        pass (default 128 per local task, the reference's batch).  rank/world_size shard the tasks."""
+        if not torch.cuda.is_available():
+            raise L.MtrlError("MTSAC needs a CUDA device; there is no CPU fallback")
+        self = object.__new__(MTSAC)
+        dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.device = dev
+        self.config = config
+        self.num_tasks = config.num_tasks
+        self.rank, self.world_size, self.process_group = rank, world_size, process_group
+        self.task_begin, self.task_end = task_partition(config.num_tasks, world_size)[rank]
+        t_local = self.task_end - self.task_begin
+        obs_dim = int(np.prod(env_config.observation_space.shape))
+        act_dim = int(np.prod(env_config.action_space.shape))
+        for nc in (config.actor_config.network_config, config.critic_config.network_config):
+            if type(nc) is not MultiHeadConfig:
+                get_nn_arch_for_config(nc)  # raises like the reference for the bare base config
+                raise NotImplementedError(f"{type(nc).__name__}: the accelerated MT-SAC path covers MultiHeadConfig")
+            assert nc.num_tasks == config.num_tasks
+        anc, cnc = config.actor_config.network_config, config.critic_config.network_config
+        if (anc.width, anc.depth) != (cnc.width, cnc.depth):
+            raise NotImplementedError("actor and critic must share width and depth (true for every reference experiment)")
+        if config.critic_config.use_classification or not config.actor_config.squash_tanh:
+            raise NotImplementedError("c51 critic / unsquashed policy are outside the accelerated path")
+        a_opt, c_opt = anc.optimizer.spawn(), cnc.optimizer.spawn()
+        t_opt = config.temperature_optimizer_config.spawn()
+        if (a_opt.eps, a_opt.b1, a_opt.b2) != (c_opt.eps, c_opt.b1, c_opt.b2) or a_opt.eps != t_opt.eps:
+            raise NotImplementedError("one Adam eps / betas for actor, critic and temperature")
+        if max_batch is None:
+            max_batch = 128 * t_local
+        if max_rows is None:
+            max_rows = -(-max_batch // 128) * 128 + 128 * (t_local - 1) if max_batch != 128 * t_local else 128 * t_local
+        self.gamma, self.tau = config.gamma, config.tau
+        self.target_entropy = -float(act_dim)  # mtsac.py:258
+        self.use_task_weights, self.clip, self.num_critics = config.use_task_weights, config.clip, config.num_critics
+        self.split_actor_losses = self.split_critic_losses = False
+        self.explore = False
+        self.actor_network_type, self.critic_network_type = "vanilla", "mse"
+        nm = lambda v: -1.0 if v is None else float(v)  # noqa: E731
+        self._cfg = SacConfigC(
+            num_tasks=config.num_tasks, task_begin=self.task_begin, num_local_tasks=t_local, obs_dim=obs_dim,
+            action_dim=act_dim, width=anc.width, depth=anc.depth, num_critics=config.num_critics, max_rows=max_rows,
+            max_batch=max_batch, gamma=config.gamma, tau=config.tau, actor_lr=a_opt.lr, critic_lr=c_opt.lr,
+            alpha_lr=t_opt.lr, adam_b1=a_opt.b1, adam_b2=a_opt.b2, adam_eps=a_opt.eps,
+            actor_max_grad_norm=nm(a_opt.max_grad_norm), critic_max_grad_norm=nm(c_opt.max_grad_norm),
+            alpha_max_grad_norm=nm(t_opt.max_grad_norm), log_std_min=config.actor_config.log_std_min,
+            log_std_max=config.actor_config.log_std_max, target_entropy=self.target_entropy,
+            clip_q=int(config.clip), use_task_weights=int(config.use_task_weights), noise_seed=int(seed) & (2**63 - 1))
+        lay = SacLayoutC()
+        L.check(L.lib().mtrl_sac_query_layout(C.byref(self._cfg), C.byref(lay)))
+        self._lay = lay
+        z = lambda n, dt=torch.float32: torch.zeros(int(n), dtype=dt, device=dev)  # noqa: E731
+        self._flat = {f"actor_{k}": z(lay.actor.total) for k in ("params", "grads", "m", "v", "shadow")}
+        self._flat.update({f"critic_{k}": z(lay.critic.total)
+                           for k in ("params", "grads", "m", "v", "shadow", "target", "target_shadow")})
+        self._flat.update({"log_alpha": z(max(t_local, 4)), "alpha_m": z(max(t_local, 4)), "alpha_v": z(max(t_local, 4))})
+        self._steps = z(4, torch.int32)
+        self._logs = z(16)
+        self._workspace = z((lay.workspace_bytes + 3) // 4 + 64)
+        self._status_host = torch.zeros(4, dtype=torch.int32).pin_memory()
+
+        # parameter views with the Flax names (mtsac.py:203-246 prints these trees)
+        def ts(prefix, l, in_dim, ens, tx, step_idx):
+            v = lambda name: _wrap(_views(self._flat[f"{prefix}_{name}"], l, in_dim, ens), ens)  # noqa: E731
+            return TrainState(step=self._steps[step_idx], params=v("params"),
+                              opt_state={"count": self._steps[step_idx], "mu": v("m"), "nu": v("v")}, tx=tx,
+                              target_params=v("target") if ens else None, grads=v("grads"))
+        self.actor = ts("actor", lay.actor, obs_dim, False, a_opt, 0)
+        self.critic = ts("critic", lay.critic, act_dim + obs_dim, True, c_opt, 1)
+        la = self._flat["log_alpha"][:t_local]
+        self.alpha = TrainState(step=self._steps[2], params={"params": {"log_alpha": la}},
+                                opt_state={"count": self._steps[2], "mu": {"params": {"log_alpha": self._flat["alpha_m"][:t_local]}},
+                                           "nu": {"params": {"log_alpha": self._flat["alpha_v"][:t_local]}}}, tx=t_opt)
+
+        # initial weights: same distributions as the reference (he_uniform trunk, zero bias, heads U(+-1e-3) / U(+-3e-3),
+        # networks.py:33-34, 65-66; log_alpha = log(initial_temperature), mtsac.py:52-58).  Every rank draws the full
+        # T-head tensors from the same seed and keeps its slice, so all ranks agree on the replicated trunk.
+        gen = torch.Generator().manual_seed(int(seed))
+        a_net = get_nn_arch_for_config(anc)(config=anc, head_dim=2 * act_dim, head_kernel_init=uniform(1e-3),
+                                            head_bias_init=uniform(1e-3))
+        c_net = get_nn_arch_for_config(cnc)(config=cnc, head_dim=1, head_kernel_init=uniform(3e-3),
+                                            head_bias_init=uniform(3e-3))
+        a_init = a_net.init(gen, obs_dim)
+        c_init = c_net.init(gen, act_dim + obs_dim, ensemble=config.num_critics)
+        sl = slice(self.task_begin, self.task_end)
+        a_init["VmapDense_0"] = {k: v[sl] for k, v in a_init["VmapDense_0"].items()}
+        c_init["VmapDense_0"] = {k: v[:, sl] for k, v in c_init["VmapDense_0"].items()}
+        _tree_copy_(self.actor.params["params"]["MultiHeadNetwork_0"], a_init)
+        _tree_copy_(self.critic.params["params"]["VmapQValueFunction_0"]["MultiHeadNetwork_0"], c_init)
+        self._flat["critic_target"].copy_(self._flat["critic_params"])  # target_params=critic_init_params, mtsac.py:238-242
+        la.fill_(math.log(config.initial_temperature))
+
+        bufs = SacBuffersC(**{k: v.data_ptr() for k, v in self._flat.items()}, steps=self._steps.data_ptr(),
+                           logs=self._logs.data_ptr(), workspace=self._workspace.data_ptr())
+        h = _vp()
+        L.check(L.lib().mtrl_sac_create(C.byref(h), C.byref(self._cfg), C.byref(bufs)))
+        self._h = h
+        self._status_event = torch.cuda.Event()
+        self._pending_status = False
+        return self
+
+    def __del__(self):
+        if getattr(self, "_h", None) is not None and L._lib is not None:
+            L._lib.mtrl_sac_destroy(self._h)
+            self._h = None
+
+    # ------------------------------------------------------------------ reference surface
+    def get_num_params(self) -> dict[str, int]:
+        """mtsac.py:289-296 (counts the logical parameters, not the alignment padding)."""
+        c, T = self._cfg, self.num_tasks
+
+        def count(in_dim, head):
+            n, d = 0, in_dim
+            for _ in range(c.depth):
+                n += d * c.width + c.width
+                d = c.width
+            return n + T * (c.width * head + head)
+        return {"actor_num_params": count(c.obs_dim, 2 * c.action_dim),
+                "critic_num_params": c.num_critics * count(c.action_dim + c.obs_dim, 1)}
+
+    def refresh(self) -> None:
+        """Call after writing into `.params` / `.target_params` views directly (e.g. loading a checkpoint)."""
+        L.check(L.lib().mtrl_sac_refresh_shadows(self._h, _vp(L.current_stream_ptr())))
+
+    def _dev(self, x) -> torch.Tensor:
+        if isinstance(x, torch.Tensor):
+            t = x.to(device=self.device, dtype=torch.float32, non_blocking=True)
+        else:
+            t = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float32)).to(self.device, non_blocking=True)
+        return t.contiguous()
+
+    def _check_status(self) -> None:
+        if self._pending_status:
+            self._status_event.synchronize()
+            self._pending_status = False
+            code = int(self._status_host[0])
+            if code == 1:
+                raise ValueError("update: a batch row belongs to a task outside this rank's range "
+                                 f"[{self.task_begin}, {self.task_end})")
+            if code == 2:
+                raise ValueError("update: the batch does not fit max_rows (rows per task are padded to 128)")
+
+    def update(self, data: ReplayBufferSamples, eps_c=None, eps_a=None, *, global_batch: int | None = None,
+               check: bool = False):
+        """`MTSAC.update` (mtsac.py:1249-1251).  Returns (self, logs) with logs as 0-dim device tensors in
+        the reference's keys; nothing here synchronises the host unless `check=True`."""
+        self._check_status()
+        obs, act, nxt, done, rew = (self._dev(x) for x in data)
+        B = obs.shape[0]
+        assert obs.shape[1] == self._cfg.obs_dim and act.shape == (B, self._cfg.action_dim)
+        ec = self._dev(eps_c) if eps_c is not None else None
+        ea = self._dev(eps_a) if eps_a is not None else None
+        stream = _vp(L.current_stream_ptr())
+        args = (self._h, _vp(obs.data_ptr()), _vp(act.data_ptr()), _vp(nxt.data_ptr()), _vp(done.data_ptr()),
+                _vp(rew.data_ptr()), B)
+        p = lambda t: _vp(t.data_ptr() if t is not None else None)  # noqa: E731
+        if self.world_size == 1:
+            L.check(L.lib().mtrl_sac_update(*args, global_batch or B, p(ec), p(ea), stream))
+        else:
+            import torch.distributed as dist
+
+            gb = global_batch
+            if gb is None:
+                raise ValueError("multi-GPU update needs global_batch (the B every loss mean divides by)")
+            L.check(L.lib().mtrl_sac_phase1_critic_grads(*args, gb, p(ec), p(ea), stream))
+            lc, la = self._lay.critic, self._lay.actor
+            dist.all_reduce(self._flat["critic_grads"][: lc.trunk_total + 32], group=self.process_group)
+            L.check(L.lib().mtrl_sac_phase2_critic_step_actor_grads(self._h, stream))
+            dist.all_reduce(self._flat["actor_grads"][: la.trunk_total + 32], group=self.process_group)
+            L.check(L.lib().mtrl_sac_phase3_actor_step_alpha(self._h, stream))
+        # asynchronous status read-back (checked at the next call, or now if check=True)
+        L.check(L.lib().mtrl_sac_read_status_async(self._h, _vp(self._status_host.data_ptr()), stream))
+        self._status_event.record()
+        self._pending_status = True
+        if check:
+            self._check_status()
+        logs = self.logs()
+        return self, logs
+
+    def logs(self) -> dict:
+        """The ten log scalars of the last update as 0-dim device tensors (keys of mtsac.py:616-621, 704-709, 728-731).
+        With world_size > 1 the per-rank partial sums are combined here (one 16-float all-reduce)."""
+        v = self._logs
+        if self.world_size > 1:
+            import torch.distributed as dist
+
+            s = v.clone()
+            dist.all_reduce(s, group=self.process_group)
+            out = {}
+            summable = {0, 1, 4, 8, 9}
+            for i, k in enumerate(LOG_KEYS):
+                out[k] = s[i] if i in summable else v[i]
+            out["metrics/critic_params_norm"] = torch.sqrt(v[10] + s[11])
+            out["metrics/actor_params_norm"] = torch.sqrt(v[12] + s[13])
+            return out
+        return {k: v[i] for i, k in enumerate(LOG_KEYS)}
+
+    def launches_per_update(self) -> int:
+        return int(L.lib().mtrl_sac_launches_per_update(self._h))
+
+    def sample_action(self, observation):
+        raise NotImplementedError("action sampling (mtsac.py:299-304) is env-side; SURVEY 8(f) row 2")
+
+    def eval_action(self, observations):
+        raise NotImplementedError("eval_action (mtsac.py:306-311) is env-side; SURVEY 8(f) row 2")

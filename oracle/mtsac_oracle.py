@@ -52,6 +52,11 @@ class OracleConfig:
     clip: bool = False          # AlgorithmConfig.clip, config/rl.py:21; mtsac.py:558-560
     use_task_weights: bool = False  # mtsac.py:124
     initial_temperature: float = 1.0
+    # "exact": plain fp32/fp64 matmuls (the reference's CPU numerics).
+    # "tf32": round trunk-matmul operands (inputs, kernels, stored activations) to tf32 at the points the
+    #         sm_100a kernels do, which is also what XLA's default f32 dot precision does on NVIDIA GPUs.
+    #         Used by tests to separate kernel correctness from the tf32 ReLU-gate effect.
+    matmul_operands: str = "exact"
 
     @property
     def target_entropy(self) -> float:  # mtsac.py:258
@@ -140,15 +145,29 @@ def init_state(cfg: OracleConfig, seed: int = 1, dtype=torch.float32) -> OracleS
 # --------------------------------------------------------------------------------------------
 # Networks
 # --------------------------------------------------------------------------------------------
-def multihead_forward(p: dict, x: torch.Tensor, num_tasks: int, depth: int, all_heads: bool = False) -> torch.Tensor:
+def tf32_round(x: torch.Tensor) -> torch.Tensor:
+    """cvt.rna.tf32.f32: round to 10 mantissa bits, ties away from zero (value semantics only)."""
+    i = x.detach().to(torch.float32).contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32).to(x.dtype)
+
+
+def _rt(x: torch.Tensor, mode: str) -> torch.Tensor:
+    """Operand rounding with a straight-through gradient."""
+    if mode == "exact":
+        return x
+    return x + (tf32_round(x) - x).detach()
+
+
+def multihead_forward(p: dict, x: torch.Tensor, num_tasks: int, depth: int, all_heads: bool = False,
+                      operands: str = "exact") -> torch.Tensor:
     """MultiHeadNetwork.__call__ (mtrl/nn/multi_head.py:21-68): `depth` Dense+ReLU layers on the full
     input (one-hot included), T heads, then pick the head of argmax(one-hot).  `all_heads=True`
     evaluates every head for every row and gathers, exactly as the reference does (:50-66); the
     default computes only the selected head (same numbers, less work)."""
     task = x[..., -num_tasks:].argmax(dim=-1)  # :26, :65
-    h = x
+    h = _rt(x, operands)
     for i in range(depth):
-        h = torch.relu(h @ p[f"layer_{i}"]["kernel"] + p[f"layer_{i}"]["bias"])  # :34-44
+        h = _rt(torch.relu(h @ _rt(p[f"layer_{i}"]["kernel"], operands) + p[f"layer_{i}"]["bias"]), operands)  # :34-44
     hk, hb = p["heads"]["kernel"], p["heads"]["bias"]
     if all_heads:
         out = torch.einsum("bw,twh->bth", h, hk) + hb[None]       # :50-62
@@ -156,26 +175,27 @@ def multihead_forward(p: dict, x: torch.Tensor, num_tasks: int, depth: int, all_
     return torch.einsum("bw,bwh->bh", h, hk[task]) + hb[task]
 
 
-def ensemble_forward(p: dict, x: torch.Tensor, num_tasks: int, depth: int, all_heads: bool = False) -> torch.Tensor:
+def ensemble_forward(p: dict, x: torch.Tensor, num_tasks: int, depth: int, all_heads: bool = False,
+                     operands: str = "exact") -> torch.Tensor:
     """Ensemble (mtrl/rl/networks.py:208-222): params stacked on axis 0, shared input -> (E, B, 1)."""
     E = p["layer_0"]["kernel"].shape[0]
     outs = []
     for e in range(E):
         pe = tree_map(lambda t: t[e], p)
-        outs.append(multihead_forward(pe, x, num_tasks, depth, all_heads))
+        outs.append(multihead_forward(pe, x, num_tasks, depth, all_heads, operands))
     return torch.stack(outs, 0)
 
 
 def critic_forward(p: dict, obs: torch.Tensor, act: torch.Tensor, cfg: OracleConfig, all_heads=False) -> torch.Tensor:
     """QValueFunction (networks.py:55-67): input is concatenate((action, state)) (:61)."""
-    return ensemble_forward(p, torch.cat((act, obs), dim=-1), cfg.num_tasks, cfg.depth, all_heads)
+    return ensemble_forward(p, torch.cat((act, obs), dim=-1), cfg.num_tasks, cfg.depth, all_heads, cfg.matmul_operands)
 
 
 def actor_sample_and_log_prob(p: dict, obs: torch.Tensor, eps: torch.Tensor, cfg: OracleConfig, all_heads=False):
     """ContinuousActionPolicy (networks.py:29-45) + TanhMultivariateNormalDiag.sample_and_log_prob
     (mtrl/nn/distributions.py:6-16; distrax Transformed: log_prob(y) = base.log_prob(x) - fldj(x),
     Tanh.forward_log_det_jacobian(x) = 2 (log 2 - x - softplus(-2x)), summed by Block(.,1))."""
-    out = multihead_forward(p, obs, cfg.num_tasks, cfg.depth, all_heads)
+    out = multihead_forward(p, obs, cfg.num_tasks, cfg.depth, all_heads, cfg.matmul_operands)
     mean, log_std = out[..., : cfg.action_dim], out[..., cfg.action_dim:]          # :37
     log_std = torch.clamp(log_std, cfg.log_std_min, cfg.log_std_max)               # :38-40
     std = torch.exp(log_std)                                                       # :41
