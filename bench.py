@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""MT-SAC gradient updates/sec on synthetic Meta-World-shaped transitions (BASELINE.json metric).
+
+A "step" is one pass of the hot path: `replay_buffer.sample(B)` (CUDA sampler) followed by
+`MTSAC.update(data)` (fused CUDA update) -- /root/reference/mtrl/rl/algorithms/base.py:220-221.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload mt50_w2048]
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   (N > 1)
+  python bench.py --impl reference ...      the reference's CPU update path (oracle port) on host cores
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (num_tasks, width, per_task_batch)   obs = 39 + T, action = 4 (mtrl/envs/metaworld.py:26-100)
+    "mt10_w400": (10, 400, 128),
+    "mt10_w1024": (10, 1024, 128),
+    "mt50_w400": (50, 400, 128),
+    "mt50_w1024": (50, 1024, 128),
+    "mt50_w2048": (50, 2048, 128),
+    "mt50_w4096": (50, 4096, 128),
+}
+METRIC = "MT-SAC gradient updates/sec"
+UNIT = "updates/s"
+
+
+def algorithmic_flops(T: int, W: int, B: int, trunk_only: bool = False) -> float:
+    """F(d,h) = 2B(dW + 2W^2 + Wh); FLOPs_update = 4 F(39, 8) + 12 F(43, 1)."""
+    def F(d, h):
+        return 2.0 * B * (d * W + 2.0 * W * W + (0 if trunk_only else W * h))
+    return 4 * F(39, 8) + 12 * F(43, 1)
+
+
+def measured_peaks() -> dict:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        d["_source"] = "measured"
+        return d
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "_source": "fallback"}
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                       "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+                power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.f.name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+def synthetic_fill(buf, T_local: int, task_begin: int, T: int, seed: int) -> None:
+    """SURVEY 8(d) synthetic transitions written straight into the device ring (full=True)."""
+    import torch
+
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    cap = buf.capacity
+    feat = buf._obs_shape - T
+    chunk = max(1, min(cap, (256 << 20) // (T_local * buf._obs_shape * 4)))
+    for s in range(0, cap, chunk):
+        e = min(cap, s + chunk)
+        o = torch.randn(e - s, T_local, feat, generator=g, device="cuda")
+        buf.obs[s:e, :, :feat] = o
+        buf.next_obs[s:e, :, :feat] = o + 0.01 * torch.randn(e - s, T_local, feat, generator=g, device="cuda")
+        buf.actions[s:e] = torch.rand(e - s, T_local, buf._action_shape, generator=g, device="cuda") * 2 - 1
+        buf.rewards[s:e] = torch.rand(e - s, T_local, 1, generator=g, device="cuda") * 10
+        buf.dones[s:e] = (torch.rand(e - s, T_local, 1, generator=g, device="cuda") < 0.002).float()
+    buf.obs[:, :, feat:] = 0
+    buf.next_obs[:, :, feat:] = 0
+    for t in range(T_local):
+        buf.obs[:, t, feat + task_begin + t] = 1.0
+        buf.next_obs[:, t, feat + task_begin + t] = 1.0
+    buf.full = True
+    buf.pos = 0
+
+
+def cpu_update_rate(T: int, W: int, per_task: int, budget_s: float, threads: int | None = None) -> dict:
+    """The reference's CPU update path (fp32 PyTorch-CPU restatement, heads evaluated for all T tasks
+    and gathered exactly like mtrl/nn/multi_head.py:50-66, plus the NumPy sampler) on the host cores."""
+    import numpy as np
+    import torch
+
+    from oracle import mtsac_oracle as O
+    from oracle.sampler_oracle import MultiTaskReplayBufferOracle
+
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    cfg = O.OracleConfig(num_tasks=T, obs_dim=39 + T, action_dim=4, width=W)
+    st = O.init_state(cfg, seed=1)
+    cap = 2048
+    buf = MultiTaskReplayBufferOracle(cap * T, T, cfg.obs_dim, 4, seed=1)
+    rng = np.random.default_rng(0)
+    buf.obs[:] = rng.standard_normal(buf.obs.shape, dtype=np.float32)
+    buf.next_obs[:] = buf.obs
+    for t in range(T):
+        buf.obs[:, t, 39:] = 0
+        buf.obs[:, t, 39 + t] = 1
+    buf.next_obs[:, :, 39:] = buf.obs[:, :, 39:]
+    buf.actions[:] = rng.uniform(-1, 1, buf.actions.shape).astype(np.float32)
+    buf.rewards[:] = rng.uniform(0, 10, buf.rewards.shape).astype(np.float32)
+    buf.full = True
+    g = torch.Generator().manual_seed(0)
+    B = per_task * T
+
+    def one(state):
+        s = buf.sample(B)
+        batch = tuple(torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)) for x in s)
+        ec = torch.randn(B, 4, generator=g)
+        ea = torch.randn(B, 4, generator=g)
+        new, logs = O.mtsac_update(state, batch, ec, ea, cfg, all_heads=True)
+        float(logs["losses/qf_loss"])
+        return new
+
+    t0 = time.perf_counter()
+    st = one(st)  # warm-up (allocator, thread pool)
+    t_first = time.perf_counter() - t0
+    n_timed = max(1, min(20, int(budget_s / max(t_first, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(n_timed):
+        st = one(st)
+    dt = (time.perf_counter() - t0) / n_timed
+    return {"value": 1.0 / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"1 warm-up + {n_timed} full updates (B={B}, incl. NumPy sample) of the fp32 torch-CPU oracle, "
+                      f"{dt*1e3:.0f} ms each, torch threads={torch.get_num_threads()}",
+            "_sec_per_update": dt, "_n_timed": n_timed}
+
+
+# ---------------------------------------------------------------------------------------------
+def run_reference_arm(args) -> None:
+    """--impl reference: the reference's own update cannot be imported here or on the GPU box (no jax/flax/
+    optax/distrax, no network), so the arm times its CPU restatement (oracle/) with all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    T, W, per_task = WORKLOADS[args.workload]
+    budget = float(os.environ.get("MTRL_REF_BUDGET_S", "150"))
+    # every step is a full update; the number of timed steps is bounded by the budget
+    r = cpu_update_rate(T, W, per_task, budget_s=budget)
+    dt = r.pop("_sec_per_update")
+    n_timed = r.pop("_n_timed")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": n_timed, "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "num_tasks": T, "width": W, "global_batch": per_task * T,
+                   "note": "CPU restatement of MTSAC.update + NumPy sampler; steps bounded by a time budget: " + r["sample"]},
+        "cpu_baseline": r,
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("MTRL_WORKLOAD", "mt50_w2048"), choices=sorted(WORKLOADS))
+    ap.add_argument("--capacity", type=int, default=int(os.environ.get("MTRL_BENCH_CAPACITY", "100000")),
+                    help="ring capacity per task (reference: 100 000)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from mtrl_b200.presets import EnvSpec, _Space, metaworld_mtmhsac
+    from mtrl_b200.rl.algorithms.mtsac import MTSAC, task_partition
+    from mtrl_b200.rl.buffers import MultiTaskReplayBuffer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks")
+    torch.cuda.set_device(local_rank)
+    pg = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        pg = dist.group.WORLD
+
+    T, W, per_task = WORKLOADS[args.workload]
+    B = per_task * T
+    t0, t1 = task_partition(T, world)[rank]
+    T_local = t1 - t0
+    B_local = per_task * T_local
+    mcfg, env = metaworld_mtmhsac(T, W)
+    agent = MTSAC.initialize(mcfg, env, seed=1, max_batch=B_local, rank=rank, world_size=world, process_group=pg)
+    buf = MultiTaskReplayBuffer(args.capacity * T_local, T_local, _Space((39 + T,)), _Space((4,)), seed=1)
+    synthetic_fill(buf, T_local, t0, T, seed=1234 + rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        data = buf.sample(B_local)
+        agent.update(data, global_batch=B)
+
+    # ---------------- warm-up ----------------
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    launches_per_step = agent.launches_per_update() + 2  # + index draw and gather kernels of the sampler
+
+    # ---------------- timed region 1: inputs resident in HBM ----------------
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    agent.profile_gemms(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    gemm_ms, gemm_launches = agent.profile_read()
+    agent.profile_gemms(False)
+
+    # ---------------- timed region 2: end to end through the public API with host buffers ----------------
+    n_host = min(args.steps, 8)
+    host_batches = []
+    for _ in range(n_host):
+        s = buf.sample(B_local)
+        host_batches.append(tuple(x.cpu().pin_memory() for x in s))
+    barrier()
+    log_host = torch.empty(16, dtype=torch.float32).pin_memory()
+    for i in range(3):
+        agent.update(tuple(x.cuda(non_blocking=True) for x in host_batches[i % n_host]), global_batch=B)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(args.steps):
+        hb = host_batches[i % n_host]
+        _, logs = agent.update(tuple(x.cuda(non_blocking=True) for x in hb), global_batch=B)
+        log_host.copy_(agent._logs, non_blocking=False)  # the reference's jax.device_get(logs) (base.py:223)
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    clk = clocks.stop() if rank == 0 else None
+    h2d = sum(x.numel() * 4 for x in host_batches[0])
+    d2h = 16 * 4
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e, gemm_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e, gemm_ms = (float(x) for x in t)
+        hb = torch.tensor([h2d], device="cuda", dtype=torch.float64)
+        dist.all_reduce(hb)
+        h2d = int(hb.item())
+        d2h *= world
+
+    if rank == 0:
+        peaks = measured_peaks()
+        value = args.steps / (ms / 1e3)
+        e2e_value = args.steps / (ms_e2e / 1e3)
+        # dominant kernel: gemm_tf32_grouped_kernel (tensor bound).  Algorithmic trunk FLOPs of this rank's rows.
+        flops_rank = algorithmic_flops(T, W, B_local if world > 1 else B, trunk_only=True)
+        n_l = max(gemm_launches, 1)
+        achieved = flops_rank * args.steps / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
+        tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
+        traffic = None
+        prof_json = os.path.join(ROOT, "profiles", "gemm_ncu_summary.json")
+        if os.path.exists(prof_json):
+            try:
+                traffic = json.load(open(prof_json)).get("dram_bytes_per_launch")
+            except Exception:  # noqa: BLE001
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "tf32", "data": "synthetic",
+            "config": {"workload": args.workload, "num_tasks": T, "width": W, "depth": 3, "num_critics": 2,
+                       "global_batch": B, "per_task_batch": per_task, "obs_dim": 39 + T, "action_dim": 4,
+                       "ring_capacity_per_task": args.capacity,
+                       "parallelism": f"tasks sharded over {world} GPU(s), trunk gradients all-reduced (NCCL)" if world > 1 else "single GPU",
+                       "l2": "per-step working set (activations + parameters, ~%.1f GB) exceeds the 126 MB L2; no explicit flush"
+                             % ((22 * B_local * W * 4 + 12 * 3 * W * W * 4) / 1e9),
+                       "precision": "fp32 storage, tf32 tensor-core operands (round-to-nearest), fp32 accumulate"},
+            "gpu_launches": launches_per_step * args.steps,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "roofline": {"bound": "tensor", "kernel": "gemm_tf32_grouped_kernel", "achieved": achieved, "peak": tf32_peak,
+                         "unit": "TFLOP/s", "frac": (achieved / tf32_peak) if achieved else None, "traffic": traffic,
+                         "launches_per_step": n_l / args.steps, "avg_launch_ms": gemm_ms / n_l,
+                         "gemm_share_of_step": gemm_ms / ms,
+                         "peak_source": f"{peaks['_source']}: bf16_tflops_sustained / 2 (tcgen05 kind::tf32 runs at half the bf16 rate)",
+                         "algorithmic_flops_per_step": flops_rank},
+            "clocks": clk,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            r = cpu_update_rate(T, W, per_task, budget_s=float(os.environ.get("MTRL_CPU_BUDGET_S", "20")))
+            r.pop("_sec_per_update", None)
+            r.pop("_n_timed", None)
+            line["cpu_baseline"] = r
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

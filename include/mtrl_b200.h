@@ -205,6 +205,10 @@ int mtrl_sac_phase2_critic_step_actor_grads(mtrl_sac_t* h, void* stream);
 int mtrl_sac_phase3_actor_step_alpha(mtrl_sac_t* h, void* stream);
 /* Number of kernels one mtrl_sac_update launches (for bench.py's gpu_launches). */
 int mtrl_sac_launches_per_update(const mtrl_sac_t* h);
+/* Bracket every GEMM launch of the following updates with CUDA events on the launch stream
+ * (enable = 1) and read back their summed duration and count (synchronises on those events). */
+int mtrl_sac_profile_gemms(mtrl_sac_t* h, int enable);
+int mtrl_sac_profile_read(mtrl_sac_t* h, double* total_ms, int* launches);
 /* Asynchronous copy of the packing status of the last update into 4 pinned host ints:
  * [0] == 0 ok, 1: a row's task is outside this handle's task range, 2: rows do not fit max_rows. */
 int mtrl_sac_read_status_async(const mtrl_sac_t* h, int* host_pinned4, void* stream);

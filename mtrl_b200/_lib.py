@@ -63,13 +63,28 @@ def _declare(l: C.CDLL) -> None:
     l.mtrl_gemm_plan_destroy.argtypes = [vp]
     l.mtrl_gemm_plan_destroy.restype = None
     for name, spec in _EXTRA_DECLS.items():
-        fn = getattr(l, name)
-        fn.argtypes = spec[0]
-        fn.restype = spec[1] if len(spec) > 1 else C.c_int
+        _apply(l, name, spec)
 
 
-# Filled in by the modules that own the corresponding C entry points (keeps this file small).
-_EXTRA_DECLS: dict = {}
+def _apply(l: C.CDLL, name: str, spec) -> None:
+    fn = getattr(l, name)
+    fn.argtypes = spec[0]
+    fn.restype = spec[1] if len(spec) > 1 else C.c_int
+
+
+class _Decls(dict):
+    """name -> (argtypes[, restype]).  Modules that own a group of C entry points register them here;
+    a registration made after the library is already loaded is applied immediately (without argtypes
+    ctypes would truncate 64-bit device pointers to int)."""
+
+    def update(self, other=(), **kw):  # noqa: A003
+        super().update(other, **kw)
+        if _lib is not None:
+            for name, spec in dict(other, **kw).items():
+                _apply(_lib, name, spec)
+
+
+_EXTRA_DECLS = _Decls()
 
 
 def current_stream_ptr() -> int:

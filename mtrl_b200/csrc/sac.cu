@@ -156,6 +156,10 @@ struct mtrl_sac {
   std::vector<mtrl_gemm_plan_t*> bwd_actor;    // [depth]
   int launches = 0;
   int batch = 0, global_batch = 0;
+  // optional CUDA-event bracketing of every GEMM launch (bench.py's live roofline measurement)
+  bool prof = false;
+  std::vector<cudaEvent_t> ev;
+  size_t ev_used = 0;
 };
 
 namespace {
@@ -291,7 +295,19 @@ int build_plans(mtrl_sac* h) {
 #define LAUNCHED(h) ((h)->launches++)
 
 int run_plan(mtrl_sac* h, mtrl_gemm_plan_t* plan, cudaStream_t st) {
+  if (h->prof) {
+    while (h->ev.size() < h->ev_used + 2) {
+      cudaEvent_t e;
+      MTRL_CUDA_CHECK(cudaEventCreate(&e));
+      h->ev.push_back(e);
+    }
+    MTRL_CUDA_CHECK(cudaEventRecord(h->ev[h->ev_used], st));
+  }
   MTRL_PROPAGATE(mtrl_gemm_plan_run(plan, st));
+  if (h->prof) {
+    MTRL_CUDA_CHECK(cudaEventRecord(h->ev[h->ev_used + 1], st));
+    h->ev_used += 2;
+  }
   LAUNCHED(h);
   return MTRL_OK;
 }
@@ -448,6 +464,7 @@ extern "C" void mtrl_sac_destroy(mtrl_sac_t* h) {
   if (!h) return;
   for (auto* v : {&h->fwd, &h->fwd_target, &h->bwd_critic, &h->fwd_pi, &h->bwd_pi, &h->bwd_actor})
     for (auto* p : *v) mtrl_gemm_plan_destroy(p);
+  for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   delete h;
 }
 
@@ -679,6 +696,29 @@ extern "C" int mtrl_sac_update(mtrl_sac_t* h, const float* obs, const float* act
 }
 
 extern "C" int mtrl_sac_launches_per_update(const mtrl_sac_t* h) { return h ? h->launches : 0; }
+
+extern "C" int mtrl_sac_profile_gemms(mtrl_sac_t* h, int enable) {
+  MTRL_REQUIRE(h, "mtrl_sac_profile_gemms: null handle");
+  h->prof = enable != 0;
+  h->ev_used = 0;
+  return MTRL_OK;
+}
+
+// Sum of the event-bracketed GEMM launch durations since profiling was enabled (synchronises on the events).
+extern "C" int mtrl_sac_profile_read(mtrl_sac_t* h, double* total_ms, int* launches) {
+  MTRL_REQUIRE(h && total_ms && launches, "mtrl_sac_profile_read: null argument");
+  double sum = 0.0;
+  for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
+    MTRL_CUDA_CHECK(cudaEventSynchronize(h->ev[i + 1]));
+    float ms = 0.f;
+    MTRL_CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]));
+    sum += ms;
+  }
+  *total_ms = sum;
+  *launches = static_cast<int>(h->ev_used / 2);
+  h->ev_used = 0;
+  return MTRL_OK;
+}
 // Device int[4] written by the packing kernel: [0] != 0 means the last batch was rejected
 // (1: a row's task is outside this handle's range, 2: rows do not fit max_rows).
 extern "C" int mtrl_sac_read_status_async(const mtrl_sac_t* h, int* host_pinned4, void* stream) {

@@ -87,6 +87,8 @@ L._EXTRA_DECLS.update({
     "mtrl_sac_phase3_actor_step_alpha": ([_vp, _vp],),
     "mtrl_sac_launches_per_update": ([_vp],),
     "mtrl_sac_read_status_async": ([_vp, _vp, _vp],),
+    "mtrl_sac_profile_gemms": ([_vp, _i],),
+    "mtrl_sac_profile_read": ([_vp, C.POINTER(C.c_double), C.POINTER(_i)],),
 })
 
 
@@ -370,6 +372,15 @@ class MTSAC:
 
     def launches_per_update(self) -> int:
         return int(L.lib().mtrl_sac_launches_per_update(self._h))
+
+    def profile_gemms(self, enable: bool) -> None:
+        L.check(L.lib().mtrl_sac_profile_gemms(self._h, int(enable)))
+
+    def profile_read(self) -> tuple[float, int]:
+        """(sum of GEMM-launch durations in ms, number of GEMM launches) since profile_gemms(True)."""
+        ms, n = C.c_double(), _i()
+        L.check(L.lib().mtrl_sac_profile_read(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     def sample_action(self, observation):
         raise NotImplementedError("action sampling (mtsac.py:299-304) is env-side; SURVEY 8(f) row 2")
