@@ -61,6 +61,10 @@ typedef struct mtrl_gemm_plan mtrl_gemm_plan_t;
 int mtrl_gemm_plan_create(mtrl_gemm_plan_t** out, const mtrl_gemm_problem_t* problems, int n);
 int mtrl_gemm_plan_run(mtrl_gemm_plan_t* plan, void* stream);
 int mtrl_gemm_plan_units(const mtrl_gemm_plan_t* plan);
+/* 2 when the plan runs as CTA pairs (tcgen05 cta_group::2, 256-row tiles), 1 for single-CTA tiles. */
+int mtrl_gemm_plan_ctas(const mtrl_gemm_plan_t* plan);
+/* Debug aid: device long long[8] receiving per-role cycle sums (see csrc/gemm_tcgen05.cu); NULL disables. */
+int mtrl_gemm_plan_set_debug(mtrl_gemm_plan_t* plan, long long* dbg);
 void mtrl_gemm_plan_destroy(mtrl_gemm_plan_t* plan);
 
 /* ------------------------------------------------------------------------------------------

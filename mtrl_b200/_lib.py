@@ -60,6 +60,8 @@ def _declare(l: C.CDLL) -> None:
     l.mtrl_gemm_plan_create.argtypes = [C.POINTER(vp), C.POINTER(GemmProblem), i]
     l.mtrl_gemm_plan_run.argtypes = [vp, vp]
     l.mtrl_gemm_plan_units.argtypes = [vp]
+    l.mtrl_gemm_plan_ctas.argtypes = [vp]
+    l.mtrl_gemm_plan_set_debug.argtypes = [vp, vp]
     l.mtrl_gemm_plan_destroy.argtypes = [vp]
     l.mtrl_gemm_plan_destroy.restype = None
     for name, spec in _EXTRA_DECLS.items():
@@ -102,6 +104,10 @@ class GemmPlan:
         check(lib().mtrl_gemm_plan_create(C.byref(h), arr, len(problems)))
         self._h = h
         self.units = lib().mtrl_gemm_plan_units(h)
+        self.ctas = lib().mtrl_gemm_plan_ctas(h)
+
+    def set_debug(self, ptr: int | None) -> None:
+        check(lib().mtrl_gemm_plan_set_debug(self._h, C.c_void_p(ptr)))
 
     def run(self, stream: int | None = None) -> None:
         check(lib().mtrl_gemm_plan_run(self._h, C.c_void_p(stream if stream is not None else current_stream_ptr())))

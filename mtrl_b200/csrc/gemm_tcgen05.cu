@@ -15,23 +15,33 @@
 // accumulation is fp32 in TMEM, epilogues are fp32.
 #include <cuda.h>  // CUtensorMap types only; the encode entry point is fetched at run time
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "mtrl_b200.h"
 
 namespace {
 
-constexpr int kBlockM = 128;
+constexpr int kBlockM = 128;         // accumulator rows per CTA (TMEM lanes)
 constexpr int kBlockK = 32;          // tf32 elements = 128 bytes = one SWIZZLE_128B row
 constexpr int kMaxBlockN = 256;
 constexpr int kUmmaK = 8;            // tf32: 32 bytes of K per tcgen05.mma
-constexpr int kStages = 4;
 constexpr int kABytes = kBlockM * kBlockK * 4;        // 16 KB
-constexpr int kBBytes = kMaxBlockN * kBlockK * 4;     // 32 KB
-constexpr int kStageBytes = kABytes + kBBytes;        // 48 KB
 constexpr int kChunkBytes = 32 * kBlockK * 4;         // one 32(MN) x 32(K) MN-major TMA box
 constexpr int kTmemCols = 512;                        // two 256-column fp32 accumulators
 constexpr int kThreads = 192;
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+
+// kCtas == 1: one CTA owns a 128 x block_n tile (A 16 KB + B 32 KB per stage, 4 stages).
+// kCtas == 2: a CTA pair (cta_group::2) owns a 256 x block_n tile; each CTA stages its own 128 rows of A and
+//             HALF of B's N, so a k-block costs 32 KB of L2->smem traffic per SM instead of 48 KB (the 1-CTA
+//             kernel is bound by that traffic, profiles/r01_gemm_1cta.txt) and 6 stages fit.
+template <int kCtas>
+struct Cfg {
+  static constexpr int kBBytes = (kMaxBlockN / kCtas) * kBlockK * 4;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = kCtas == 1 ? 4 : 6;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
 
 struct __align__(16) DevProblem {
   float* D;
@@ -47,8 +57,8 @@ struct __align__(16) DevProblem {
   int a_major, b_major;
   int unit_begin, unit_count;
   uint32_t idesc;
-  int b_chunks;  // number of 32-wide MN chunks of B per stage (MN-major B only)
-  int pad;
+  int b_chunks;  // 32-wide MN chunks of B each CTA loads per stage (MN-major B only)
+  int mn3d;      // bit 0 / 1: A / B is MN-major and described by a 3-D map (one TMA per stage instead of one per chunk)
 };
 
 // smem matrix descriptor (cute::UMMA::SmemDescriptor layout): start>>4 [0,14), LBO>>4 [16,30),
@@ -73,6 +83,7 @@ struct GemmParams {
   DevProblem probs[kMaxProblems];
   int nprob;
   int total_units;
+  long long* dbg;  // optional: 8 cycle counters summed over CTAs (see mtrl_gemm_plan_set_debug)
 };
 
 struct UnitCoord {
@@ -96,15 +107,59 @@ __device__ __forceinline__ UnitCoord decode_unit(const DevProblem* __restrict__ 
   return c;
 }
 
+// Epilogue of one 16-column chunk of one accumulator row.
+__device__ __forceinline__ void epilogue_chunk(const DevProblem& P, const uint32_t (&v)[16], float* drow,
+                                               const float* mrow, int col0) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int col = col0 + 4 * q;
+    if (col + 4 <= P.N) {
+      float4 o;
+      o.x = __uint_as_float(v[4 * q + 0]);
+      o.y = __uint_as_float(v[4 * q + 1]);
+      o.z = __uint_as_float(v[4 * q + 2]);
+      o.w = __uint_as_float(v[4 * q + 3]);
+      if (P.epilogue == MTRL_EPI_BIAS_RELU) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + col));
+        o.x = tf32_rna(fmaxf(o.x + b.x, 0.f));
+        o.y = tf32_rna(fmaxf(o.y + b.y, 0.f));
+        o.z = tf32_rna(fmaxf(o.z + b.z, 0.f));
+        o.w = tf32_rna(fmaxf(o.w + b.w, 0.f));
+        *reinterpret_cast<float4*>(drow + col) = o;
+      } else if (P.epilogue == MTRL_EPI_RELU_MASK) {
+        const float4 h = __ldg(reinterpret_cast<const float4*>(mrow + col));
+        o.x = h.x > 0.f ? tf32_rna(o.x) : 0.f;
+        o.y = h.y > 0.f ? tf32_rna(o.y) : 0.f;
+        o.z = h.z > 0.f ? tf32_rna(o.z) : 0.f;
+        o.w = h.w > 0.f ? tf32_rna(o.w) : 0.f;
+        *reinterpret_cast<float4*>(drow + col) = o;
+      } else if (P.epilogue == MTRL_EPI_ATOMIC_ADD) {
+        atomicAdd(reinterpret_cast<float4*>(drow + col), o);
+      } else if (P.epilogue == MTRL_EPI_STORE_TF32) {
+        o.x = tf32_rna(o.x);
+        o.y = tf32_rna(o.y);
+        o.z = tf32_rna(o.z);
+        o.w = tf32_rna(o.w);
+        *reinterpret_cast<float4*>(drow + col) = o;
+      } else {
+        *reinterpret_cast<float4*>(drow + col) = o;
+      }
+    }
+  }
+}
+
+template <int kCtas>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
+  using C = Cfg<kCtas>;
+  constexpr int kStages = C::kStages;
   const DevProblem* probs = params.probs;
   const CUtensorMap* maps = params.maps;
   const int nprob = params.nprob;
   const int total_units = params.total_units;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + kStages * kStageBytes;
+  const uint32_t bar_base = smem_base + kStages * C::kStageBytes;
   // barrier layout (8 bytes each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
@@ -116,76 +171,109 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = kCtas == 2 ? cluster_ctarank() : 0u;   // 0 = leader of the pair
+  const int worker = blockIdx.x / kCtas;                       // CTA (or pair) index
+  const int nworkers = gridDim.x / kCtas;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(full_bar(s), 1);   // the (leader's) producer arrive + TMA transaction bytes
+      mbar_init(empty_bar(s), 1);  // one tcgen05.commit
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(a), 4 * kCtas);  // one arrive per epilogue warp of every CTA of the pair
     }
     mbar_fence_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
+    if (kCtas == 2) {
+      tmem_alloc_pair(tmem_slot, kTmemCols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (kCtas == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (every CTA) =====================
+    // The whole warp walks the schedule (warp-uniform values stay in uniform registers); one elected lane issues.
+    {
       int stage = 0;
       uint32_t phase = 0;
-      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+      long long t_wait = 0, t_issue = 0;
+      for (int unit = worker; unit < total_units; unit += nworkers) {
         const UnitCoord c = decode_unit(probs, nprob, unit);
         const DevProblem& P = probs[c.p];
         const CUtensorMap* mapA = maps + 2 * c.p;
         const CUtensorMap* mapB = maps + 2 * c.p + 1;
-        const int m0 = c.m_tile * kBlockM;
-        const int n0 = c.n_tile * P.block_n;
-        const uint32_t b_bytes =
-            P.b_major ? static_cast<uint32_t>(P.b_chunks) * kChunkBytes
-                      : static_cast<uint32_t>(P.block_n) * kBlockK * 4u;
+        const int n_cta = P.block_n / kCtas;                       // B columns staged by this CTA
+        const int m0 = (c.m_tile * kCtas + static_cast<int>(rank)) * kBlockM;
+        const int n0 = c.n_tile * P.block_n + static_cast<int>(rank) * n_cta;
+        const uint32_t b_bytes = P.b_major ? static_cast<uint32_t>(P.b_chunks) * kChunkBytes
+                                           : static_cast<uint32_t>(n_cta) * kBlockK * 4u;
         for (int kb = c.kb0; kb < c.kb1; ++kb) {
+          const long long t0 = params.dbg ? clock64() : 0;
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t sa = smem_base + stage * kStageBytes;
+          const long long t1 = params.dbg ? clock64() : 0;
+          t_wait += t1 - t0;
+          const uint32_t sa = smem_base + stage * C::kStageBytes;
           const uint32_t sb = sa + kABytes;
-          mbar_expect_tx(full_bar(stage), kABytes + b_bytes);
+          const uint32_t fb = full_bar(stage);
           const int k0 = kb * kBlockK;
+          if (elect_one()) {
+          if (rank == 0) mbar_expect_tx(fb, kCtas * (kABytes + b_bytes));
+          auto load = [&](uint32_t dst, const CUtensorMap* map, int c0, int c1) {
+            if (kCtas == 2) tma_load_2d_pair(dst, map, fb, c0, c1);
+            else tma_load_2d(dst, map, fb, c0, c1);
+          };
+          auto load3 = [&](uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2) {
+            if (kCtas == 2) tma_load_3d_pair(dst, map, fb, c0, c1, c2);
+            else tma_load_3d(dst, map, fb, c0, c1, c2);
+          };
           if (!P.a_major) {
-            tma_load_2d(sa, mapA, full_bar(stage), k0, m0);
+            load(sa, mapA, k0, m0);
+          } else if (P.mn3d & 1) {
+            load3(sa, mapA, 0, k0, m0 >> 5);
           } else {
 #pragma unroll
-            for (int j = 0; j < kBlockM / 32; ++j)
-              tma_load_2d(sa + j * kChunkBytes, mapA, full_bar(stage), m0 + 32 * j, k0);
+            for (int j = 0; j < kBlockM / 32; ++j) load(sa + j * kChunkBytes, mapA, m0 + 32 * j, k0);
           }
           if (!P.b_major) {
-            tma_load_2d(sb, mapB, full_bar(stage), k0, n0);
+            load(sb, mapB, k0, n0);
+          } else if (P.mn3d & 2) {
+            load3(sb, mapB, 0, k0, n0 >> 5);
           } else {
-            for (int j = 0; j < P.b_chunks; ++j)
-              tma_load_2d(sb + j * kChunkBytes, mapB, full_bar(stage), n0 + 32 * j, k0);
+            for (int j = 0; j < P.b_chunks; ++j) load(sb + j * kChunkBytes, mapB, n0 + 32 * j, k0);
           }
+          }  // elect_one
+          __syncwarp();
+          if (params.dbg) t_issue += clock64() - t1;
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1u;
           }
         }
       }
+      if (params.dbg && lane == 0) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(params.dbg + 0), static_cast<unsigned long long>(t_wait));
+        atomicAdd(reinterpret_cast<unsigned long long*>(params.dbg + 1), static_cast<unsigned long long>(t_issue));
+      }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+      long long t_wfull = 0, t_wtempty = 0, t_issue = 0, t_total0 = params.dbg ? clock64() : 0;
+      for (int unit = worker; unit < total_units; unit += nworkers) {
         const UnitCoord c = decode_unit(probs, nprob, unit);
         const DevProblem& P = probs[c.p];
         const uint32_t idesc = P.idesc;
@@ -202,109 +290,150 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
         const uint32_t b_lt = P.b_major ? 1u : 2u;
         const uint32_t a_kstep = P.a_major ? 1024u : 32u;
         const uint32_t b_kstep = P.b_major ? 1024u : 32u;
+        const long long ta = params.dbg ? clock64() : 0;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        if (params.dbg) t_wtempty += clock64() - ta;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * kMaxBlockN;
         for (int kb = c.kb0; kb < c.kb1; ++kb) {
+          const long long t0 = params.dbg ? clock64() : 0;
           mbar_wait(full_bar(stage), phase);
+          const long long t1 = params.dbg ? clock64() : 0;
+          t_wfull += t1 - t0;
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * kStageBytes;
+          const uint32_t sa = smem_base + stage * C::kStageBytes;
           const uint32_t sb = sa + kABytes;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            const uint64_t adesc = make_smem_desc(sa + k * a_kstep, a_lbo, a_sbo, a_lt);
-            const uint64_t bdesc = make_smem_desc(sb + k * b_kstep, b_lbo, b_sbo, b_lt);
-            umma_tf32(d_tmem, adesc, bdesc, idesc, (kb > c.kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              const uint64_t adesc = make_smem_desc(sa + k * a_kstep, a_lbo, a_sbo, a_lt);
+              const uint64_t bdesc = make_smem_desc(sb + k * b_kstep, b_lbo, b_sbo, b_lt);
+              const uint32_t accum = (kb > c.kb0 || k > 0) ? 1u : 0u;
+              if (kCtas == 2) umma_tf32_pair(d_tmem, adesc, bdesc, idesc, accum);
+              else umma_tf32(d_tmem, adesc, bdesc, idesc, accum);
+            }
+            // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+            if (kCtas == 2) umma_commit_pair(empty_bar(stage), 3); else umma_commit(empty_bar(stage));
           }
-          umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+          __syncwarp();
+          if (params.dbg) t_issue += clock64() - t1;
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue warps (of both CTAs)
+        if (elect_one()) {
+          if (kCtas == 2) umma_commit_pair(tfull_bar(acc), 3); else umma_commit(tfull_bar(acc));
+        }
+        __syncwarp();
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1u;
         }
       }
+      if (params.dbg && lane == 0) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(params.dbg + 2), static_cast<unsigned long long>(t_wfull));
+        atomicAdd(reinterpret_cast<unsigned long long*>(params.dbg + 3), static_cast<unsigned long long>(t_wtempty));
+        atomicAdd(reinterpret_cast<unsigned long long*>(params.dbg + 4), static_cast<unsigned long long>(t_issue));
+        atomicAdd(reinterpret_cast<unsigned long long*>(params.dbg + 5), static_cast<unsigned long long>(clock64() - t_total0));
+      }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..5 of every CTA) =====================
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are this warp's
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+    long long t_wait = 0, t_work = 0;
+    for (int unit = worker; unit < total_units; unit += nworkers) {
       const UnitCoord c = decode_unit(probs, nprob, unit);
       const DevProblem& P = probs[c.p];
-      const int row = c.m_tile * kBlockM + quarter * 32 + lane;
+      const int row = (c.m_tile * kCtas + static_cast<int>(rank)) * kBlockM + quarter * 32 + lane;
       const int n0 = c.n_tile * P.block_n;
       const bool row_ok = row < P.M;
       float* drow = P.D + static_cast<long long>(row) * P.ldd;
       const float* mrow = P.mask ? P.mask + static_cast<long long>(row) * P.ldmask : nullptr;
+      const long long t0 = params.dbg ? clock64() : 0;
       mbar_wait(tfull_bar(acc), acc_phase);
+      const long long t1 = params.dbg ? clock64() : 0;
+      t_wait += t1 - t0;
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                              static_cast<uint32_t>(acc) * kMaxBlockN;
-      for (int cc = 0; cc < P.block_n; cc += 16) {
-        uint32_t v[16];
-        tmem_ld16(t_row + cc, v);
-        tmem_ld_wait();
-        const int col0 = n0 + cc;
-        if (row_ok) {
+      if (P.epilogue == MTRL_EPI_RELU_MASK) {
+        // ReLU VJP: the forward activation is fetched two 16-column chunks ahead of its use so the
+        // (per-thread-row, DRAM-latency) loads overlap the TMEM reads and stores of earlier chunks.
+        constexpr int kAhead = 2;
+        float4 pre[kAhead][4];
+        auto fetch = [&](int cc, float4 (&dst)[4]) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const int col = col0 + 4 * q;
-            if (col + 4 <= P.N) {
-              float4 o;
-              o.x = __uint_as_float(v[4 * q + 0]);
-              o.y = __uint_as_float(v[4 * q + 1]);
-              o.z = __uint_as_float(v[4 * q + 2]);
-              o.w = __uint_as_float(v[4 * q + 3]);
-              if (P.epilogue == MTRL_EPI_BIAS_RELU) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + col));
-                o.x = tf32_rna(fmaxf(o.x + b.x, 0.f));
-                o.y = tf32_rna(fmaxf(o.y + b.y, 0.f));
-                o.z = tf32_rna(fmaxf(o.z + b.z, 0.f));
-                o.w = tf32_rna(fmaxf(o.w + b.w, 0.f));
-                *reinterpret_cast<float4*>(drow + col) = o;
-              } else if (P.epilogue == MTRL_EPI_RELU_MASK) {
-                const float4 h = __ldg(reinterpret_cast<const float4*>(mrow + col));
-                o.x = h.x > 0.f ? tf32_rna(o.x) : 0.f;
-                o.y = h.y > 0.f ? tf32_rna(o.y) : 0.f;
-                o.z = h.z > 0.f ? tf32_rna(o.z) : 0.f;
-                o.w = h.w > 0.f ? tf32_rna(o.w) : 0.f;
-                *reinterpret_cast<float4*>(drow + col) = o;
-              } else if (P.epilogue == MTRL_EPI_ATOMIC_ADD) {
-                atomicAdd(reinterpret_cast<float4*>(drow + col), o);
-              } else if (P.epilogue == MTRL_EPI_STORE_TF32) {
-                o.x = tf32_rna(o.x);
-                o.y = tf32_rna(o.y);
-                o.z = tf32_rna(o.z);
-                o.w = tf32_rna(o.w);
-                *reinterpret_cast<float4*>(drow + col) = o;
-              } else {
-                *reinterpret_cast<float4*>(drow + col) = o;
+            const int col = n0 + cc + 4 * q;
+            dst[q] = (row_ok && cc < P.block_n && col + 4 <= P.N) ? __ldg(reinterpret_cast<const float4*>(mrow + col))
+                                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        };
+#pragma unroll
+        for (int a = 0; a < kAhead; ++a) fetch(16 * a, pre[a]);
+        for (int cc = 0; cc < P.block_n; cc += 16 * kAhead) {
+#pragma unroll
+          for (int a = 0; a < kAhead; ++a) {
+            const int c0 = cc + 16 * a;
+            if (c0 < P.block_n) {
+              uint32_t v[16];
+              tmem_ld16(t_row + c0, v);
+              float4 h[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) h[q] = pre[a][q];
+              fetch(c0 + 16 * kAhead, pre[a]);
+              tmem_ld_wait();
+              if (row_ok) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const int col = n0 + c0 + 4 * q;
+                  if (col + 4 <= P.N) {
+                    float4 o;
+                    o.x = h[q].x > 0.f ? tf32_rna(__uint_as_float(v[4 * q + 0])) : 0.f;
+                    o.y = h[q].y > 0.f ? tf32_rna(__uint_as_float(v[4 * q + 1])) : 0.f;
+                    o.z = h[q].z > 0.f ? tf32_rna(__uint_as_float(v[4 * q + 2])) : 0.f;
+                    o.w = h[q].w > 0.f ? tf32_rna(__uint_as_float(v[4 * q + 3])) : 0.f;
+                    *reinterpret_cast<float4*>(drow + col) = o;
+                  }
+                }
               }
             }
           }
         }
+      } else {
+        for (int cc = 0; cc < P.block_n; cc += 16) {
+          uint32_t v[16];
+          tmem_ld16(t_row + cc, v);
+          tmem_ld_wait();
+          if (row_ok) epilogue_chunk(P, v, drow, mrow, n0 + cc);
+        }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (kCtas == 2) mbar_arrive_cluster(tempty_bar(acc), 0); else mbar_arrive(tempty_bar(acc));
+      }
+      if (params.dbg) t_work += clock64() - t1;
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1u;
       }
     }
+    if (params.dbg && lane == 0 && quarter == 0) {
+      atomicAdd(reinterpret_cast<unsigned long long*>(params.dbg + 6), static_cast<unsigned long long>(t_wait));
+      atomicAdd(reinterpret_cast<unsigned long long*>(params.dbg + 7), static_cast<unsigned long long>(t_work));
+    }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (kCtas == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (kCtas == 2) tmem_dealloc_pair(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -352,21 +481,53 @@ int encode_map(CUtensorMap* map, const float* base, long long inner, long long o
   return MTRL_OK;
 }
 
+// MN-major operand [K rows][MN] viewed as (32, K, MN/32): one box {32, 32, chunks} fills `chunks` consecutive
+// 4 KB [32 k][32 mn] smem blocks, the layout the MN-major descriptors expect.  Needs MN % 32 == 0 (a partial
+// last chunk would alias the next row instead of being zero-filled).  Returns false if the driver refuses it.
+bool encode_map_mn3d(CUtensorMap* map, const float* base, long long mn, long long k, long long pitch, int chunks) {
+  EncodeTiledFn enc;
+  if (get_encode_fn(&enc) != MTRL_OK) return false;
+  if (mn % 32 != 0 || chunks < 1 || chunks > 8 || (reinterpret_cast<uintptr_t>(base) & 15u) || (pitch * 4) % 16) return false;
+  cuuint64_t dims[3] = {32, static_cast<cuuint64_t>(k), static_cast<cuuint64_t>(mn / 32)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(pitch) * 4u, 128u};
+  cuuint32_t box[3] = {32, static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(chunks)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 }  // namespace
 
 struct mtrl_gemm_plan {
   GemmParams params;
   int grid = 0;
+  int ctas = 1;  // 1: one CTA per tile; 2: CTA pairs (cta_group::2)
 };
+
+namespace {
+// MTRL_GEMM_CTAS=1 forces the single-CTA kernel (debugging / A-B comparison); default is CTA pairs.
+int preferred_ctas(int sms) {
+  const char* e = getenv("MTRL_GEMM_CTAS");
+  if (e && e[0] == '1') return 1;
+  return (sms % 2 == 0) ? 2 : 1;
+}
+}  // namespace
 
 extern "C" int mtrl_gemm_plan_create(mtrl_gemm_plan_t** out, const mtrl_gemm_problem_t* problems, int n) {
   MTRL_REQUIRE(out && problems && n >= 1 && n <= kMaxProblems,
                "mtrl_gemm_plan_create: need 1..%d problems per launch, got %d", kMaxProblems, n);
+  int dev_id = 0, sms = 148;
+  cudaGetDevice(&dev_id);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id);
+  const int ctas = preferred_ctas(sms);
   mtrl_gemm_plan* plan = new mtrl_gemm_plan();
   struct Guard {
     mtrl_gemm_plan* p;
     ~Guard() { delete p; }
   } guard{plan};
+  plan->ctas = ctas;
   GemmParams& P = plan->params;
   memset(&P, 0, sizeof(P));
   int units = 0;
@@ -383,6 +544,12 @@ extern "C" int mtrl_gemm_plan_create(mtrl_gemm_plan_t** out, const mtrl_gemm_pro
     MTRL_REQUIRE(p.epilogue != MTRL_EPI_RELU_MASK || p.mask, "problem %d: mask epilogue without mask", i);
     MTRL_REQUIRE((reinterpret_cast<uintptr_t>(p.D) & 15u) == 0 && p.ldd % 4 == 0,
                  "problem %d: D must be 16-byte aligned with ldd %% 4 == 0", i);
+    // A CTA of a pair stages block_n / 2 columns of B; MN-major B arrives in 32-column TMA boxes, so the
+    // half must be a multiple of 32 there.
+    int block_n = p.block_n;
+    if (ctas == 2 && p.b_major && block_n % 64 != 0) block_n = (block_n + 63) / 64 * 64;
+    const int tile_m = kBlockM * ctas;
+    const int n_cta = block_n / ctas;
     DevProblem& d = P.probs[i];
     d.D = p.D;
     d.bias = p.bias;
@@ -392,9 +559,9 @@ extern "C" int mtrl_gemm_plan_create(mtrl_gemm_plan_t** out, const mtrl_gemm_pro
     d.M = p.M;
     d.N = p.N;
     d.K = p.K;
-    d.block_n = p.block_n;
-    d.m_tiles = (p.M + kBlockM - 1) / kBlockM;
-    d.n_tiles = (p.N + p.block_n - 1) / p.block_n;
+    d.block_n = block_n;
+    d.m_tiles = (p.M + tile_m - 1) / tile_m;
+    d.n_tiles = (p.N + block_n - 1) / block_n;
     d.kb_total = (p.K + kBlockK - 1) / kBlockK;
     int splits = p.k_splits < d.kb_total ? p.k_splits : d.kb_total;
     d.kb_per_split = (d.kb_total + splits - 1) / splits;
@@ -402,38 +569,46 @@ extern "C" int mtrl_gemm_plan_create(mtrl_gemm_plan_t** out, const mtrl_gemm_pro
     d.epilogue = p.epilogue;
     d.a_major = p.a_major ? 1 : 0;
     d.b_major = p.b_major ? 1 : 0;
-    d.b_chunks = (p.block_n + 31) / 32;
+    d.b_chunks = (n_cta + 31) / 32;
     d.unit_begin = units;
     d.unit_count = d.m_tiles * d.n_tiles * d.k_splits;
     units += d.unit_count;
     // cute::UMMA::InstrDescriptor: c_format F32 (1) [4,6), a/b_format TF32 (2) [7,10)/[10,13),
-    // a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29).
+    // a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29)  (M = 256 for a CTA pair).
     d.idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(d.a_major) << 15) |
-              (static_cast<uint32_t>(d.b_major) << 16) | (static_cast<uint32_t>(p.block_n >> 3) << 17) |
-              (static_cast<uint32_t>(kBlockM >> 4) << 24);
-    // A: K-major -> [M][K] rows of K; MN-major -> [K][M] rows of M.
-    if (!d.a_major)
+              (static_cast<uint32_t>(d.b_major) << 16) | (static_cast<uint32_t>(block_n >> 3) << 17) |
+              (static_cast<uint32_t>(tile_m >> 4) << 24);
+    // A: K-major -> [M][K] rows of K; MN-major -> [K][M] rows of M.  Each CTA loads its own 128 rows.
+    const bool allow3d = !(getenv("MTRL_GEMM_NO_3D") && getenv("MTRL_GEMM_NO_3D")[0] == '1');
+    d.mn3d = 0;
+    if (!d.a_major) {
       MTRL_PROPAGATE(encode_map(&P.maps[2 * i], p.A, p.K, p.M, p.lda, kBlockK, kBlockM, CU_TENSOR_MAP_SWIZZLE_128B));
-    else
+    } else if (allow3d && encode_map_mn3d(&P.maps[2 * i], p.A, p.M, p.K, p.lda, kBlockM / 32)) {
+      d.mn3d |= 1;
+    } else {
       MTRL_PROPAGATE(encode_map(&P.maps[2 * i], p.A, p.M, p.K, p.lda, 32, kBlockK,
                                 CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
-    if (!d.b_major)
-      MTRL_PROPAGATE(encode_map(&P.maps[2 * i + 1], p.B, p.K, p.N, p.ldb, kBlockK, p.block_n,
+    }
+    if (!d.b_major) {
+      MTRL_PROPAGATE(encode_map(&P.maps[2 * i + 1], p.B, p.K, p.N, p.ldb, kBlockK, n_cta,
                                 CU_TENSOR_MAP_SWIZZLE_128B));
-    else
+    } else if (allow3d && n_cta % 32 == 0 && encode_map_mn3d(&P.maps[2 * i + 1], p.B, p.N, p.K, p.ldb, n_cta / 32)) {
+      d.mn3d |= 2;
+    } else {
       MTRL_PROPAGATE(encode_map(&P.maps[2 * i + 1], p.B, p.N, p.K, p.ldb, 32, kBlockK,
                                 CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+    }
   }
   P.nprob = n;
   P.total_units = units;
-  int dev_id = 0, sms = 148;
-  cudaGetDevice(&dev_id);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id);
-  plan->grid = units < sms ? units : sms;
+  const int workers = sms / ctas;
+  plan->grid = (units < workers ? units : workers) * ctas;
   static bool attr_set = false;
   if (!attr_set) {
-    MTRL_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kSmemBytes));
+    MTRL_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32_grouped_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg<1>::kSmemBytes));
+    MTRL_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32_grouped_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg<2>::kSmemBytes));
     attr_set = true;
   }
   guard.p = nullptr;
@@ -443,12 +618,40 @@ extern "C" int mtrl_gemm_plan_create(mtrl_gemm_plan_t** out, const mtrl_gemm_pro
 
 extern "C" int mtrl_gemm_plan_run(mtrl_gemm_plan_t* plan, void* stream) {
   MTRL_REQUIRE(plan, "mtrl_gemm_plan_run: null plan");
-  gemm_tf32_grouped_kernel<<<plan->grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(plan->params);
-  MTRL_CUDA_CHECK(cudaGetLastError());
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (plan->ctas == 1) {
+    gemm_tf32_grouped_kernel<1><<<plan->grid, kThreads, Cfg<1>::kSmemBytes, st>>>(plan->params);
+    MTRL_CUDA_CHECK(cudaGetLastError());
+    return MTRL_OK;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(plan->grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = Cfg<2>::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MTRL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tf32_grouped_kernel<2>, plan->params));
+  return MTRL_OK;
+}
+
+// Debug aid: dbg = device long long[8], zeroed by the caller.  Cycle sums over CTAs of
+// [0] producer wait-empty, [1] producer TMA issue, [2] MMA wait-full, [3] MMA wait-tmem-empty, [4] MMA issue,
+// [5] MMA thread total, [6] epilogue wait-tmem-full (warp 2), [7] epilogue work (warp 2).
+extern "C" int mtrl_gemm_plan_set_debug(mtrl_gemm_plan_t* plan, long long* dbg) {
+  MTRL_REQUIRE(plan, "mtrl_gemm_plan_set_debug: null plan");
+  plan->params.dbg = dbg;
   return MTRL_OK;
 }
 
 extern "C" int mtrl_gemm_plan_units(const mtrl_gemm_plan_t* plan) { return plan ? plan->params.total_units : 0; }
+extern "C" int mtrl_gemm_plan_ctas(const mtrl_gemm_plan_t* plan) { return plan ? plan->ctas : 0; }
 
 extern "C" void mtrl_gemm_plan_destroy(mtrl_gemm_plan_t* plan) {
   delete plan;
