@@ -130,6 +130,22 @@ def task_partition(num_tasks: int, world_size: int) -> list[tuple[int, int]]:
     return out
 
 
+SUMMABLE_LOGS = (0, 1, 4, 8, 9)  # per-rank partial sums: qf_values, qf_loss, actor_loss, alpha_loss, alpha
+
+
+def combine_rank_logs(local: torch.Tensor, summed: torch.Tensor) -> dict:
+    """Turn one rank's 16-float log vector and its sum over ranks into the reference's ten scalars.
+    Loss terms are partial sums already divided by the GLOBAL batch (summable); gradient norms are global on every
+    rank after the trunk all-reduce (take the local value); parameter norms combine the replicated trunk part
+    (slots 10 / 12, local) with the sum of every rank's head part (slots 11 / 13)."""
+    out = {}
+    for i, k in enumerate(LOG_KEYS):
+        out[k] = summed[i] if i in SUMMABLE_LOGS else local[i]
+    out["metrics/critic_params_norm"] = torch.sqrt(local[10] + summed[11])
+    out["metrics/actor_params_norm"] = torch.sqrt(local[12] + summed[13])
+    return out
+
+
 def _views(flat: torch.Tensor, lay: NetLayoutC, in_dim: int, ensemble: bool) -> dict:
     """Flax-named zero-copy views of one network's flat buffer."""
     W, D, T, E, hd = lay.width, lay.depth, lay.num_local_tasks, lay.members, lay.head_dim
@@ -361,13 +377,7 @@ class MTSAC:
 
             s = v.clone()
             dist.all_reduce(s, group=self.process_group)
-            out = {}
-            summable = {0, 1, 4, 8, 9}
-            for i, k in enumerate(LOG_KEYS):
-                out[k] = s[i] if i in summable else v[i]
-            out["metrics/critic_params_norm"] = torch.sqrt(v[10] + s[11])
-            out["metrics/actor_params_norm"] = torch.sqrt(v[12] + s[13])
-            return out
+            return combine_rank_logs(v, s)
         return {k: v[i] for i, k in enumerate(LOG_KEYS)}
 
     def launches_per_update(self) -> int:
