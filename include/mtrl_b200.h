@@ -53,6 +53,8 @@ typedef struct mtrl_gemm_problem {
   const float* bias;    /* device [N] for MTRL_EPI_BIAS_RELU                                        */
   const float* mask;    /* device [M][N] for MTRL_EPI_RELU_MASK                                     */
   long long ldmask;
+  float* colsum_partial; /* optional, MTRL_EPI_RELU_MASK only: device [ceil(M/32)][N] receiving the column sums of
+                            every 32-row group of D (bias gradients are their sum over groups); NULL to skip  */
 } mtrl_gemm_problem_t;
 
 typedef struct mtrl_gemm_plan mtrl_gemm_plan_t;

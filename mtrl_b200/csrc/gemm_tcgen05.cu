@@ -47,6 +47,7 @@ struct __align__(16) DevProblem {
   float* D;
   const float* bias;
   const float* mask;
+  float* colsum;   // optional [ceil(M/32)][N] partial column sums (ReLU-mask epilogue)
   long long ldd;
   long long ldmask;
   int M, N, K;
@@ -387,19 +388,37 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
               for (int q = 0; q < 4; ++q) h[q] = pre[a][q];
               fetch(c0 + 16 * kAhead, pre[a]);
               tmem_ld_wait();
-              if (row_ok) {
+              float r[16];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const int col = n0 + c0 + 4 * q;
-                  if (col + 4 <= P.N) {
-                    float4 o;
-                    o.x = h[q].x > 0.f ? tf32_rna(__uint_as_float(v[4 * q + 0])) : 0.f;
-                    o.y = h[q].y > 0.f ? tf32_rna(__uint_as_float(v[4 * q + 1])) : 0.f;
-                    o.z = h[q].z > 0.f ? tf32_rna(__uint_as_float(v[4 * q + 2])) : 0.f;
-                    o.w = h[q].w > 0.f ? tf32_rna(__uint_as_float(v[4 * q + 3])) : 0.f;
-                    *reinterpret_cast<float4*>(drow + col) = o;
+              for (int q = 0; q < 4; ++q) {
+                const int col = n0 + c0 + 4 * q;
+                const bool ok = row_ok && col + 4 <= P.N;
+                float4 o;
+                o.x = (ok && h[q].x > 0.f) ? tf32_rna(__uint_as_float(v[4 * q + 0])) : 0.f;
+                o.y = (ok && h[q].y > 0.f) ? tf32_rna(__uint_as_float(v[4 * q + 1])) : 0.f;
+                o.z = (ok && h[q].z > 0.f) ? tf32_rna(__uint_as_float(v[4 * q + 2])) : 0.f;
+                o.w = (ok && h[q].w > 0.f) ? tf32_rna(__uint_as_float(v[4 * q + 3])) : 0.f;
+                if (ok) *reinterpret_cast<float4*>(drow + col) = o;
+                r[4 * q + 0] = o.x; r[4 * q + 1] = o.y; r[4 * q + 2] = o.z; r[4 * q + 3] = o.w;
+              }
+              if (P.colsum) {
+                // Column sums over this warp's 32 rows (bias gradient partials): butterfly that halves the
+                // values a lane holds each step, 16 shuffles for 16 columns; lane L ends with column L >> 1.
+#pragma unroll
+                for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
+                  const bool upper = (lane & off) != 0;
+#pragma unroll
+                  for (int i = 0; i < half; ++i) {
+                    const float send = upper ? r[i] : r[i + half];
+                    const float keep = upper ? r[i + half] : r[i];
+                    r[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
                   }
                 }
+                r[0] += __shfl_xor_sync(0xffffffffu, r[0], 1);
+                const int col = n0 + c0 + (lane >> 1);
+                const int group = (c.m_tile * kCtas + static_cast<int>(rank)) * 4 + quarter;
+                if ((lane & 1) == 0 && col < P.N && group * 32 < P.M)
+                  P.colsum[static_cast<long long>(group) * P.N + col] = r[0];
               }
             }
           }
@@ -554,6 +573,7 @@ extern "C" int mtrl_gemm_plan_create(mtrl_gemm_plan_t** out, const mtrl_gemm_pro
     d.D = p.D;
     d.bias = p.bias;
     d.mask = p.mask;
+    d.colsum = p.epilogue == MTRL_EPI_RELU_MASK ? p.colsum_partial : nullptr;
     d.ldd = p.ldd;
     d.ldmask = p.ldmask;
     d.M = p.M;

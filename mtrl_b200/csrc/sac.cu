@@ -99,7 +99,7 @@ long long carve(const mtrl_sac_config_t& c, int Ka, int Kc, uint8_t* base, Works
   w.logstd = f(M * A);
   w.dq = f(E * M);
   w.dout = f(M * 2 * A);
-  w.colsum_part = f(static_cast<long long>(kColsumSplits) * kMaxE * W);
+  w.colsum_part = f(static_cast<long long>(kMaxE) * (M / 32) * W);  // per member: [M/32 row groups][W]
   w.alpha_val = f(c.num_local_tasks);
   w.task_w = f(c.num_local_tasks);
   w.inrange = reinterpret_cast<unsigned*>(take(M * 4));
@@ -180,7 +180,8 @@ mtrl_gemm_problem_t fwd_problem(const float* X, int ldx, int K, const float* Wsh
   return p;
 }
 // dZ_prev = (dZ W^T) * (H_prev > 0): A = dZ [M][W] K-major, B = W [in=N][W=K] K-major
-mtrl_gemm_problem_t dx_problem(const float* dZ, const float* Wsh, int n_in, const float* mask, float* out, int M, int W) {
+mtrl_gemm_problem_t dx_problem(const float* dZ, const float* Wsh, int n_in, const float* mask, float* out, int M, int W,
+                               float* colsum_partial) {
   mtrl_gemm_problem_t p;
   memset(&p, 0, sizeof(p));
   p.A = dZ; p.lda = W; p.a_major = 0;
@@ -188,6 +189,7 @@ mtrl_gemm_problem_t dx_problem(const float* dZ, const float* Wsh, int n_in, cons
   p.D = out; p.ldd = n_in;
   p.M = M; p.N = n_in; p.K = W;
   p.block_n = block_n_for(n_in); p.k_splits = 1; p.epilogue = MTRL_EPI_RELU_MASK; p.mask = mask; p.ldmask = n_in;
+  p.colsum_partial = colsum_partial;
   return p;
 }
 // dW = X^T dZ: A = X [rows][in] MN-major, B = dZ [rows][W] MN-major, K = rows
@@ -216,6 +218,10 @@ mtrl_gemm_problem_t dw_problem(const float* X, int ldx, int n_in, const float* d
   p.k_splits = splits;
   p.epilogue = splits > 1 ? MTRL_EPI_ATOMIC_ADD : MTRL_EPI_STORE;
   return p;
+}
+
+float* colsum_part(const mtrl_sac* h, int e) {
+  return h->ws.colsum_part + static_cast<long long>(e) * (h->cfg.max_rows / 32) * h->cfg.width;
 }
 
 int make_plan(std::vector<mtrl_gemm_plan_t*>& dst, const std::vector<mtrl_gemm_problem_t>& probs) {
@@ -269,8 +275,8 @@ int build_plans(mtrl_sac* h) {
     }
     for (int e = 0; e < E; ++e) {
       if (l > 0) {
-        pc.push_back(dx_problem(w.G[e][src], tk(csh, LC, e, l), W, w.C[e][l - 1], w.G[e][dst], M, W));
-        ppi.push_back(dx_problem(w.G[e][src], tk(csh, LC, e, l), W, w.C[e][l - 1], w.G[e][dst], M, W));
+        pc.push_back(dx_problem(w.G[e][src], tk(csh, LC, e, l), W, w.C[e][l - 1], w.G[e][dst], M, W, colsum_part(h, e)));
+        ppi.push_back(dx_problem(w.G[e][src], tk(csh, LC, e, l), W, w.C[e][l - 1], w.G[e][dst], M, W, nullptr));
       } else {
         // actor step: only dL/da = first action_dim input columns of dZ_0 W_0^T (N = 16 rows of W_0)
         mtrl_gemm_problem_t p;
@@ -284,7 +290,7 @@ int build_plans(mtrl_sac* h) {
     }
     pa.push_back(dw_problem(l == 0 ? w.Xa : w.Ao[l - 1], l == 0 ? Ka : W, l == 0 ? LA.in_dim : W, w.G[0][src],
                             tk(h->buf.actor_grads, LA, 0, l), M, W, h->sms, 0));
-    if (l > 0) pa.push_back(dx_problem(w.G[0][src], tk(ash, LA, 0, l), W, w.Ao[l - 1], w.G[0][dst], M, W));
+    if (l > 0) pa.push_back(dx_problem(w.G[0][src], tk(ash, LA, 0, l), W, w.Ao[l - 1], w.G[0][dst], M, W, colsum_part(h, 0)));
     MTRL_PROPAGATE(make_plan(h->bwd_critic, pc));
     MTRL_PROPAGATE(make_plan(h->bwd_pi, ppi));
     MTRL_PROPAGATE(make_plan(h->bwd_actor, pa));
@@ -331,6 +337,24 @@ int launch_actor_head(mtrl_sac* h, const float* H, const float* eps, float* Xdst
   a.W = c.width;
   a.ls_min = c.log_std_min;
   a.ls_max = c.log_std_max;
+  const size_t wbytes = static_cast<size_t>(c.width) * 2 * c.action_dim * sizeof(float);
+  if (wbytes <= 200 * 1024) {
+    dim3 grid(c.max_rows / 32), block(256);
+#define MTRL_AH_TILE(A_)                                                                                          \
+  case A_:                                                                                                        \
+    cudaFuncSetAttribute(actor_head_tile_kernel<A_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);    \
+    actor_head_tile_kernel<A_><<<grid, block, wbytes, st>>>(a);                                                   \
+    break;
+    switch (c.action_dim) {
+      MTRL_AH_TILE(1) MTRL_AH_TILE(2) MTRL_AH_TILE(3) MTRL_AH_TILE(4) MTRL_AH_TILE(5) MTRL_AH_TILE(6) MTRL_AH_TILE(7)
+      default: cudaFuncSetAttribute(actor_head_tile_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+               actor_head_tile_kernel<8><<<grid, block, wbytes, st>>>(a);
+    }
+#undef MTRL_AH_TILE
+    MTRL_CUDA_CHECK(cudaGetLastError());
+    LAUNCHED(h);
+    return MTRL_OK;
+  }
   const int wpb = 8;
   dim3 grid((c.max_rows + wpb - 1) / wpb), block(wpb * 32);
   switch (c.action_dim) {
@@ -373,31 +397,32 @@ int launch_head_bwd(mtrl_sac* h, const HeadBwdArgs& a, int hd, int E, cudaStream
   return MTRL_OK;
 }
 
-int launch_colsum(mtrl_sac* h, const ColsumJobs& jobs, cudaStream_t st) {
-  const int M = h->cfg.max_rows, W = h->cfg.width;
-  dim3 g1((W + 127) / 128, kColsumSplits, jobs.njobs);
-  colsum_partial_kernel<<<g1, 128, 0, st>>>(jobs, M, W, h->ws.colsum_part);
-  dim3 g2((W + 127) / 128, jobs.njobs);
-  colsum_final_kernel<<<g2, 128, 0, st>>>(jobs, kColsumSplits, W, h->ws.colsum_part);
+int launch_colsum(mtrl_sac* h, const ColsumJobs& jobs, int groups, cudaStream_t st) {
+  const int W = h->cfg.width;
+  dim3 g((W + 127) / 128, jobs.njobs);
+  colsum_final_kernel<<<g, 128, 0, st>>>(jobs, groups, W);
   MTRL_CUDA_CHECK(cudaGetLastError());
-  h->launches += 2;
+  LAUNCHED(h);
   return MTRL_OK;
 }
 
-// Trunk backward of one network: bias gradients (column sums of dZ_l) + the dW / dX GEMM plan per layer.
+// Trunk backward of one network: per layer, finish the bias gradient from the partial column sums its dZ producer
+// left behind (head VJP: per 128-row tile; previous layer's dX GEMM epilogue: per 32 rows), then the dW / dX plan.
 int run_trunk_backward(mtrl_sac* h, std::vector<mtrl_gemm_plan_t*>& plans, float* grads, const mtrl_net_layout_t& L, int E,
                        bool want_wgrad, cudaStream_t st) {
   const int D = h->cfg.depth;
   for (int l = D - 1, i = 0; l >= 0; --l, ++i) {
     const int src = (D - 1 - l) & 1;
+    (void)src;
     if (want_wgrad) {
       ColsumJobs jobs;
       jobs.njobs = E;
       for (int e = 0; e < E; ++e) {
-        jobs.src[e] = h->ws.G[e][src];
+        jobs.part[e] = colsum_part(h, e);
         jobs.dst[e] = tb(grads, L, e, l);
       }
-      MTRL_PROPAGATE(launch_colsum(h, jobs, st));
+      const int groups = l == D - 1 ? h->cfg.max_rows / kTileRows : h->cfg.max_rows / 32;
+      MTRL_PROPAGATE(launch_colsum(h, jobs, groups, st));
     }
     MTRL_PROPAGATE(run_plan(h, plans[i], st));
   }
@@ -507,9 +532,9 @@ extern "C" int mtrl_sac_phase1_critic_grads(mtrl_sac_t* h, const float* obs, con
     const int nchunks = (batch + 31) / 32;
     const size_t smem = (static_cast<size_t>(nchunks) * T + T + 1) * sizeof(int);
     MTRL_REQUIRE(smem <= 200 * 1024, "mtrl_sac_update: batch %d x %d tasks exceeds the packing kernel's shared memory", batch, T);
-    pack_plan_kernel<<<1, 1024, smem, st>>>(obs, batch, c.obs_dim, c.num_tasks, c.task_begin, T, M, w.row_slot, w.slot_src,
-                                            w.tile_task, w.seg_start, w.status);
-    LAUNCHED(h);
+    row_task_kernel<<<(batch + 7) / 8, 256, 0, st>>>(obs, batch, c.obs_dim, c.num_tasks, c.task_begin, T, w.row_slot, w.status);
+    pack_plan_kernel<<<1, 1024, smem, st>>>(batch, T, M, w.row_slot, w.slot_src, w.tile_task, w.seg_start, w.status);
+    h->launches += 2;
     PackArgs a;
     a.obs = obs; a.actions = actions; a.next_obs = next_obs; a.dones = dones; a.rewards = rewards;
     a.eps_c = eps_c; a.eps_a = eps_a;
@@ -560,6 +585,7 @@ extern "C" int mtrl_sac_phase1_critic_grads(mtrl_sac_t* h, const float* obs, con
       a.dZ[e] = w.G[e][0];
       a.dWh[e] = hk(h->buf.critic_grads, LC, e);
       a.dbh[e] = hb(h->buf.critic_grads, LC, e);
+      a.colsum[e] = colsum_part(h, e);
     }
     a.seg_start = w.seg_start; a.M = M; a.W = W;
     MTRL_PROPAGATE(launch_head_bwd(h, a, 1, E, st));
@@ -646,6 +672,7 @@ extern "C" int mtrl_sac_phase2_critic_step_actor_grads(mtrl_sac_t* h, void* stre
     a.dZ[0] = w.G[0][0];
     a.dWh[0] = hk(h->buf.actor_grads, LA, 0);
     a.dbh[0] = hb(h->buf.actor_grads, LA, 0);
+    a.colsum[0] = colsum_part(h, 0);
     a.seg_start = w.seg_start; a.M = M; a.W = W;
     MTRL_PROPAGATE(launch_head_bwd(h, a, 2 * c.action_dim, 1, st));
   }

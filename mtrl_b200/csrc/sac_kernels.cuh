@@ -56,9 +56,34 @@ __device__ __forceinline__ double block_sum(double v, double* smem) {
 // buffers.py:547-548); internally rows are task-major with each task padded to 128-row tiles so a
 // GEMM M tile belongs to one task (own-task head only).
 // ---------------------------------------------------------------------------------------------
-__global__ void pack_plan_kernel(const float* __restrict__ obs, int B, int obs_dim, int T, int task_begin, int T_local,
-                                 int max_rows, int* __restrict__ row_slot, int* __restrict__ slot_src,
-                                 int* __restrict__ tile_task, int* __restrict__ seg_start, int* __restrict__ status) {
+// Task of every row = first arg-max of its trailing one-hot (jnp.argmax, multi_head.py:65).  One warp per row.
+__global__ void row_task_kernel(const float* __restrict__ obs, int B, int obs_dim, int T, int task_begin, int T_local,
+                                int* __restrict__ row_slot, int* __restrict__ status) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const float* oh = obs + static_cast<long long>(row) * obs_dim + (obs_dim - T);
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int t = lane; t < T; t += 32) {
+    const float v = oh[t];
+    if (v > best) { best = v; bi = t; }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+  }
+  if (lane == 0) {
+    int task = bi - task_begin;
+    if (task < 0 || task >= T_local) { atomicExch(status, 1); task = -1; }
+    row_slot[row] = task;
+  }
+}
+
+__global__ void pack_plan_kernel(int B, int T_local, int max_rows, int* __restrict__ row_slot,
+                                 int* __restrict__ slot_src, int* __restrict__ tile_task, int* __restrict__ seg_start,
+                                 int* __restrict__ status) {
   extern __shared__ int sm[];
   const int nchunks = (B + 31) / 32;
   int* counts = sm;                       // [nchunks][T_local]
@@ -67,22 +92,10 @@ __global__ void pack_plan_kernel(const float* __restrict__ obs, int B, int obs_d
   for (int i = tid; i < nchunks * T_local; i += blockDim.x) counts[i] = 0;
   for (int i = tid; i < max_rows; i += blockDim.x) slot_src[i] = -1;
   __syncthreads();
-  // pass 1: task of every row (first arg-max of the one-hot, like jnp.argmax), per-chunk histograms
+  // pass 1: per-chunk histograms of the row tasks (row_task_kernel stashed them in row_slot)
   for (int c = warp; c < nchunks; c += nwarps) {
     const int row = c * 32 + lane;
-    int task = -1;
-    if (row < B) {
-      const float* oh = obs + static_cast<long long>(row) * obs_dim + (obs_dim - T);
-      float best = oh[0];
-      int bi = 0;
-      for (int t = 1; t < T; ++t) {
-        const float v = oh[t];
-        if (v > best) { best = v; bi = t; }
-      }
-      task = bi - task_begin;
-      if (task < 0 || task >= T_local) { atomicExch(status, 1); task = -1; }
-      row_slot[row] = task;  // stash
-    }
+    const int task = row < B ? row_slot[row] : -1;
     const unsigned peers = __match_any_sync(0xffffffffu, task);
     if (task >= 0 && lane == __ffs(peers) - 1) counts[c * T_local + task] = __popc(peers);
   }
@@ -299,6 +312,71 @@ __global__ void actor_head_kernel(const ActorHeadArgs p) {
   }
 }
 
+// Same computation, one block per 32 packed rows (all of one task): the task's (W, 2A) head matrix is staged in
+// shared memory once per block instead of being streamed from L2 for every row.
+template <int A>
+__global__ void actor_head_tile_kernel(const ActorHeadArgs p) {
+  extern __shared__ float sw[];  // [W][2A]
+  const int row0 = blockIdx.x * 32;
+  const int t = p.tile_task[row0 / kTileRows];
+  const float* wsrc = p.Wh + static_cast<long long>(t) * p.W * (2 * A);
+  for (int i = threadIdx.x; i < p.W * 2 * A / 4; i += blockDim.x)
+    reinterpret_cast<float4*>(sw)[i] = __ldg(reinterpret_cast<const float4*>(wsrc) + i);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int row = row0 + warp; row < row0 + 32 && row < p.M; row += nw) {
+    const bool valid = p.slot_src[row] >= 0;
+    float acc[2 * A];
+#pragma unroll
+    for (int j = 0; j < 2 * A; ++j) acc[j] = 0.f;
+    if (valid) {
+      const float* h = p.H + static_cast<long long>(row) * p.W;
+      for (int k = lane; k < p.W; k += 32) {
+        const float hv = h[k];
+        const float* wk = sw + k * (2 * A);
+#pragma unroll
+        for (int j = 0; j < 2 * A; ++j) acc[j] = fmaf(hv, wk[j], acc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 2 * A; ++j) acc[j] = warp_sum(acc[j]);
+    float lp = 0.f;
+    unsigned mask = 0;
+    if (lane < A) {
+      const int d = lane;
+      float mean = 0.f, ls_raw = 0.f;
+#pragma unroll
+      for (int j = 0; j < A; ++j) {
+        if (j == d) { mean = acc[j]; ls_raw = acc[A + j]; }
+      }
+      float a = 0.f, ls = 0.f;
+      if (valid) {
+        mean += p.bh[t * 2 * A + d];
+        ls_raw += p.bh[t * 2 * A + A + d];
+        ls = fminf(fmaxf(ls_raw, p.ls_min), p.ls_max);
+        const float sd = expf(ls);
+        const float e = p.eps[row * A + d];
+        const float x = fmaf(sd, e, mean);
+        a = tanhf(x);
+        const float z = -2.f * x;
+        const float softplus = z > 0.f ? z + log1pf(expf(-z)) : log1pf(expf(z));
+        const float fldj = 2.f * (0.69314718055994531f - x - softplus);
+        lp = -0.5f * e * e - 0.91893853320467274f - ls - fldj;
+        if (ls_raw > p.ls_min && ls_raw < p.ls_max) mask = 1u << d;
+      }
+      p.Xdst[static_cast<long long>(row) * p.ldx + d] = tf32_rna(a);
+      if (p.act) p.act[row * A + d] = a;
+      if (p.logstd) p.logstd[row * A + d] = ls;
+    }
+    lp = warp_sum(lp);
+    for (int o = 16; o > 0; o >>= 1) mask |= __shfl_xor_sync(0xffffffffu, mask, o);
+    if (lane == 0) {
+      p.logp[row] = lp;
+      if (p.inrange) p.inrange[row] = mask;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Critic heads + losses.  One warp per packed row; E members.
 // ---------------------------------------------------------------------------------------------
@@ -489,6 +567,7 @@ struct HeadBwdArgs {
   float* dZ[kMaxE];           // [M][W]
   float* dWh[kMaxE];          // may be null (no weight gradients)
   float* dbh[kMaxE];
+  float* colsum[kMaxE];       // may be null: [M/128][W] column sums of dZ per 128-row tile (trunk bias gradient partials)
   const int* seg_start;
   int M, W;
 };
@@ -515,6 +594,7 @@ __global__ void head_bwd_kernel(const HeadBwdArgs p) {
     for (int i = threadIdx.x; i < kTileRows * HD; i += blockDim.x) sd[i] = dout[static_cast<long long>(base) * HD + i];
     __syncthreads();
     if (kok) {
+      float csum = 0.f;
 #pragma unroll 4
       for (int r = 0; r < kTileRows; ++r) {
         const float h = H[static_cast<long long>(base + r) * p.W + k];
@@ -525,8 +605,11 @@ __global__ void head_bwd_kernel(const HeadBwdArgs p) {
           acc[j] = fmaf(h, d, acc[j]);
           dz = fmaf(d, w[j], dz);
         }
-        dZ[static_cast<long long>(base + r) * p.W + k] = h > 0.f ? tf32_rna(dz) : 0.f;
+        dz = h > 0.f ? tf32_rna(dz) : 0.f;
+        csum += dz;
+        dZ[static_cast<long long>(base + r) * p.W + k] = dz;
       }
+      if (p.colsum[e]) p.colsum[e][static_cast<long long>(base / kTileRows) * p.W + k] = csum;
     }
     if (blockIdx.x == 0 && threadIdx.x < HD)
       for (int r = 0; r < kTileRows; ++r) bsum += sd[r * HD + threadIdx.x];
@@ -541,40 +624,31 @@ __global__ void head_bwd_kernel(const HeadBwdArgs p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Bias gradients: column sums of dZ.  Two stages keep the sum order fixed (no float atomics).
+// Bias gradients: db[k] = sum over row groups of the partial column sums that the producers of dZ
+// emit (head_bwd_kernel: one row of partials per 128-row tile; the dX GEMM epilogue: one per 32 rows).
+// Fixed summation order, no float atomics.
 // ---------------------------------------------------------------------------------------------
 struct ColsumJobs {
-  const float* src[kMaxE];
+  const float* part[kMaxE];   // [groups][W]
   float* dst[kMaxE];
   int njobs;
 };
 
-__global__ void colsum_partial_kernel(const ColsumJobs jobs, int M, int W, float* __restrict__ part) {
-  const int job = blockIdx.z;
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= W) return;
-  const int rows_per = (M + gridDim.y - 1) / gridDim.y;
-  const int r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
-  const float* s = jobs.src[job];
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  int r = r0;
-  for (; r + 4 <= r1; r += 4) {
-    a0 += s[static_cast<long long>(r) * W + k];
-    a1 += s[static_cast<long long>(r + 1) * W + k];
-    a2 += s[static_cast<long long>(r + 2) * W + k];
-    a3 += s[static_cast<long long>(r + 3) * W + k];
-  }
-  for (; r < r1; ++r) a0 += s[static_cast<long long>(r) * W + k];
-  part[(static_cast<long long>(job) * gridDim.y + blockIdx.y) * W + k] = (a0 + a1) + (a2 + a3);
-}
-
-__global__ void colsum_final_kernel(const ColsumJobs jobs, int splits, int W, const float* __restrict__ part) {
+__global__ void colsum_final_kernel(const ColsumJobs jobs, int groups, int W) {
   const int job = blockIdx.y;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= W) return;
-  float a = 0.f;
-  for (int s = 0; s < splits; ++s) a += part[(static_cast<long long>(job) * splits + s) * W + k];
-  jobs.dst[job][k] = a;
+  const float* p = jobs.part[job];
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int g = 0;
+  for (; g + 4 <= groups; g += 4) {
+    a0 += p[static_cast<long long>(g) * W + k];
+    a1 += p[static_cast<long long>(g + 1) * W + k];
+    a2 += p[static_cast<long long>(g + 2) * W + k];
+    a3 += p[static_cast<long long>(g + 3) * W + k];
+  }
+  for (; g < groups; ++g) a0 += p[static_cast<long long>(g) * W + k];
+  jobs.dst[job][k] = (a0 + a1) + (a2 + a3);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -627,23 +701,41 @@ __global__ void adam_kernel(const AdamArgs a) {
   const float bc2 = static_cast<float>(1.0 - pow(static_cast<double>(a.b2), static_cast<double>(t)));
   double s_trunk = 0.0, s_head = 0.0;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n; i += stride) {
-    if (i >= a.trunk_n && i < a.trunk_n + 32) continue;
-    const float g = a.g[i] * scale;
-    const float m = a.b1 * a.m[i] + (1.f - a.b1) * g;
-    const float v = a.b2 * a.v[i] + (1.f - a.b2) * g * g;
-    const float p = a.p[i] - a.lr * (m / bc1) / (sqrtf(v / bc2) + a.eps);
-    a.m[i] = m;
-    a.v[i] = v;
-    a.p[i] = p;
-    a.shadow[i] = tf32_rna(p);
-    if (a.target) {
-      const float tg = a.tau * p + (1.f - a.tau) * a.target[i];
-      a.target[i] = tg;
-      a.target_shadow[i] = tf32_rna(tg);
+  // the flat buffers are 128-byte aligned and every region (trunk, 32 slots, heads) is a multiple of 32 floats
+  const long long n4 = a.n / 4, slot4 = a.trunk_n / 4;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    if (i >= slot4 && i < slot4 + 8) continue;
+    const float4 g4 = reinterpret_cast<const float4*>(a.g)[i];
+    const float4 m4 = reinterpret_cast<const float4*>(a.m)[i];
+    const float4 v4 = reinterpret_cast<const float4*>(a.v)[i];
+    const float4 p4 = reinterpret_cast<const float4*>(a.p)[i];
+    float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.target) t4 = reinterpret_cast<const float4*>(a.target)[i];
+    const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
+    float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w}, pp[4] = {p4.x, p4.y, p4.z, p4.w};
+    float tt[4] = {t4.x, t4.y, t4.z, t4.w}, sh[4], tsh[4];
+    float sq = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float g = gg[q] * scale;
+      mm[q] = a.b1 * mm[q] + (1.f - a.b1) * g;
+      vv[q] = a.b2 * vv[q] + (1.f - a.b2) * g * g;
+      pp[q] = pp[q] - a.lr * (mm[q] / bc1) / (sqrtf(vv[q] / bc2) + a.eps);
+      sh[q] = tf32_rna(pp[q]);
+      tt[q] = a.tau * pp[q] + (1.f - a.tau) * tt[q];
+      tsh[q] = tf32_rna(tt[q]);
+      sq += pp[q] * pp[q];
     }
-    if (i < a.trunk_n) s_trunk += static_cast<double>(p) * p;
-    else s_head += static_cast<double>(p) * p;
+    reinterpret_cast<float4*>(a.m)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    reinterpret_cast<float4*>(a.v)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    reinterpret_cast<float4*>(a.p)[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
+    reinterpret_cast<float4*>(a.shadow)[i] = make_float4(sh[0], sh[1], sh[2], sh[3]);
+    if (a.target) {
+      reinterpret_cast<float4*>(a.target)[i] = make_float4(tt[0], tt[1], tt[2], tt[3]);
+      reinterpret_cast<float4*>(a.target_shadow)[i] = make_float4(tsh[0], tsh[1], tsh[2], tsh[3]);
+    }
+    if (i < slot4) s_trunk += static_cast<double>(sq);
+    else s_head += static_cast<double>(sq);
   }
   s_trunk = block_sum(s_trunk, red);
   s_head = block_sum(s_head, red);

@@ -25,3 +25,22 @@ def test_gemm_grouped(cuda):
 
     for name, rel, _ in G.run_grouped():
         assert rel < 5e-4, f"{name}: rel err {rel}"
+
+
+def test_relu_mask_epilogue_emits_column_sum_partials(cuda):
+    """The dX epilogue also writes, per 32-row group, the column sums of what it stored (bias-gradient partials)."""
+    import torch
+
+    import gemm_cases as G
+    from mtrl_b200 import _lib as L
+
+    M, N, K = 384, 400, 160
+    p, D, ref, keep = G.make_problem(M, N, K, 0, 0, L.EPI_RELU_MASK, 208, 1, seed=3)
+    part = torch.full(((M + 31) // 32, N), float("nan"), device="cuda")
+    p.colsum_partial = part.data_ptr()
+    plan = L.GemmPlan([p])
+    plan.run()
+    torch.cuda.synchronize()
+    expect = D.double().reshape(M // 32, 32, N).sum(1)
+    assert torch.isfinite(part).all()
+    assert ((part.double() - expect).norm() / expect.norm()).item() < 1e-6
