@@ -29,7 +29,8 @@ constexpr int kUmmaK = 8;            // tf32: 32 bytes of K per tcgen05.mma
 constexpr int kABytes = kBlockM * kBlockK * 4;        // 16 KB
 constexpr int kChunkBytes = 32 * kBlockK * 4;         // one 32(MN) x 32(K) MN-major TMA box
 constexpr int kTmemCols = 512;                        // two 256-column fp32 accumulators
-constexpr int kThreads = 192;
+constexpr int kEpilogueWarps = 8;                      // two warps per TMEM lane quarter, each takes half the columns
+constexpr int kThreads = 64 + 32 * kEpilogueWarps;
 
 // kCtas == 1: one CTA owns a 128 x block_n tile (A 16 KB + B 32 KB per stage, 4 stages).
 // kCtas == 2: a CTA pair (cta_group::2) owns a 256 x block_n tile; each CTA stages its own 128 rows of A and
@@ -183,7 +184,7 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4 * kCtas);  // one arrive per epilogue warp of every CTA of the pair
+      mbar_init(tempty_bar(a), kEpilogueWarps * kCtas);  // one arrive per epilogue warp of every CTA of the pair
     }
     mbar_fence_init();
   }
@@ -341,8 +342,9 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5 of every CTA) =====================
-    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are this warp's
+    // ===================== epilogue (warps 2..9 of every CTA) =====================
+    const int quarter = warp & 3;          // TMEM lanes [32*quarter, 32*quarter+32) are this warp's
+    const int col_half = (warp - 2) >> 2;  // which half of the tile's 16-column chunks this warp drains
     int acc = 0;
     uint32_t acc_phase = 0;
     long long t_wait = 0, t_work = 0;
@@ -361,6 +363,9 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                              static_cast<uint32_t>(acc) * kMaxBlockN;
+      const int n_split = ((P.block_n / 16 + 1) / 2) * 16;
+      const int cbeg = col_half ? n_split : 0;
+      const int cend = col_half ? P.block_n : n_split;
       if (P.epilogue == MTRL_EPI_RELU_MASK) {
         // ReLU VJP: the forward activation is fetched two 16-column chunks ahead of its use so the
         // (per-thread-row, DRAM-latency) loads overlap the TMEM reads and stores of earlier chunks.
@@ -370,17 +375,17 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int col = n0 + cc + 4 * q;
-            dst[q] = (row_ok && cc < P.block_n && col + 4 <= P.N) ? __ldg(reinterpret_cast<const float4*>(mrow + col))
+            dst[q] = (row_ok && cc < cend && col + 4 <= P.N) ? __ldg(reinterpret_cast<const float4*>(mrow + col))
                                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         };
 #pragma unroll
-        for (int a = 0; a < kAhead; ++a) fetch(16 * a, pre[a]);
-        for (int cc = 0; cc < P.block_n; cc += 16 * kAhead) {
+        for (int a = 0; a < kAhead; ++a) fetch(cbeg + 16 * a, pre[a]);
+        for (int cc = cbeg; cc < cend; cc += 16 * kAhead) {
 #pragma unroll
           for (int a = 0; a < kAhead; ++a) {
             const int c0 = cc + 16 * a;
-            if (c0 < P.block_n) {
+            if (c0 < cend) {
               uint32_t v[16];
               tmem_ld16(t_row + c0, v);
               float4 h[4];
@@ -424,7 +429,7 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
           }
         }
       } else {
-        for (int cc = 0; cc < P.block_n; cc += 16) {
+        for (int cc = cbeg; cc < cend; cc += 16) {
           uint32_t v[16];
           tmem_ld16(t_row + cc, v);
           tmem_ld_wait();
@@ -442,7 +447,7 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
         acc_phase ^= 1u;
       }
     }
-    if (params.dbg && lane == 0 && quarter == 0) {
+    if (params.dbg && lane == 0 && warp == 2) {
       atomicAdd(reinterpret_cast<unsigned long long*>(params.dbg + 6), static_cast<unsigned long long>(t_wait));
       atomicAdd(reinterpret_cast<unsigned long long*>(params.dbg + 7), static_cast<unsigned long long>(t_work));
     }

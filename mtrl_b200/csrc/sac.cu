@@ -340,15 +340,11 @@ int launch_actor_head(mtrl_sac* h, const float* H, const float* eps, float* Xdst
   const size_t wbytes = static_cast<size_t>(c.width) * 2 * c.action_dim * sizeof(float);
   if (wbytes <= 200 * 1024) {
     dim3 grid(c.max_rows / 32), block(256);
-#define MTRL_AH_TILE(A_)                                                                                          \
-  case A_:                                                                                                        \
-    cudaFuncSetAttribute(actor_head_tile_kernel<A_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);    \
-    actor_head_tile_kernel<A_><<<grid, block, wbytes, st>>>(a);                                                   \
-    break;
+#define MTRL_AH_TILE(A_) \
+  case A_: actor_head_tile_kernel<A_><<<grid, block, wbytes, st>>>(a); break;
     switch (c.action_dim) {
       MTRL_AH_TILE(1) MTRL_AH_TILE(2) MTRL_AH_TILE(3) MTRL_AH_TILE(4) MTRL_AH_TILE(5) MTRL_AH_TILE(6) MTRL_AH_TILE(7)
-      default: cudaFuncSetAttribute(actor_head_tile_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-               actor_head_tile_kernel<8><<<grid, block, wbytes, st>>>(a);
+      default: actor_head_tile_kernel<8><<<grid, block, wbytes, st>>>(a);
     }
 #undef MTRL_AH_TILE
     MTRL_CUDA_CHECK(cudaGetLastError());
@@ -399,8 +395,8 @@ int launch_head_bwd(mtrl_sac* h, const HeadBwdArgs& a, int hd, int E, cudaStream
 
 int launch_colsum(mtrl_sac* h, const ColsumJobs& jobs, int groups, cudaStream_t st) {
   const int W = h->cfg.width;
-  dim3 g((W + 127) / 128, jobs.njobs);
-  colsum_final_kernel<<<g, 128, 0, st>>>(jobs, groups, W);
+  dim3 g((W + 31) / 32, jobs.njobs);
+  colsum_final_kernel<<<g, 256, 0, st>>>(jobs, groups, W);
   MTRL_CUDA_CHECK(cudaGetLastError());
   LAUNCHED(h);
   return MTRL_OK;
@@ -476,6 +472,14 @@ extern "C" int mtrl_sac_create(mtrl_sac_t** out, const mtrl_sac_config_t* cfg, c
   cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, dev);
   cudaMemset(b->workspace, 0, h->lay.workspace_bytes);
   cudaFuncSetAttribute(pack_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(actor_head_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(actor_head_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(actor_head_tile_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(actor_head_tile_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(actor_head_tile_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(actor_head_tile_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(actor_head_tile_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(actor_head_tile_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   rc = build_plans(h);
   if (rc != MTRL_OK) { mtrl_sac_destroy(h); return rc; }
   rc = mtrl_sac_refresh_shadows(h, nullptr);

@@ -634,21 +634,24 @@ struct ColsumJobs {
   int njobs;
 };
 
+// block = 32 columns x 8 group slices; slices are combined in a fixed order through shared memory.
 __global__ void colsum_final_kernel(const ColsumJobs jobs, int groups, int W) {
+  __shared__ float red[8][33];
   const int job = blockIdx.y;
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= W) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int k = blockIdx.x * 32 + tx;
   const float* p = jobs.part[job];
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  int g = 0;
-  for (; g + 4 <= groups; g += 4) {
-    a0 += p[static_cast<long long>(g) * W + k];
-    a1 += p[static_cast<long long>(g + 1) * W + k];
-    a2 += p[static_cast<long long>(g + 2) * W + k];
-    a3 += p[static_cast<long long>(g + 3) * W + k];
+  float a = 0.f;
+  if (k < W)
+    for (int g = ty; g < groups; g += 8) a += p[static_cast<long long>(g) * W + k];
+  red[ty][tx] = a;
+  __syncthreads();
+  if (ty == 0 && k < W) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += red[j][tx];
+    jobs.dst[job][k] = s;
   }
-  for (; g < groups; ++g) a0 += p[static_cast<long long>(g) * W + k];
-  jobs.dst[job][k] = (a0 + a1) + (a2 + a3);
 }
 
 // ---------------------------------------------------------------------------------------------

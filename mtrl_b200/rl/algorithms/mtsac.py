@@ -335,7 +335,8 @@ class MTSAC:
                check: bool = False):
         """`MTSAC.update` (mtsac.py:1249-1251).  Returns (self, logs) with logs as 0-dim device tensors in
         the reference's keys; nothing here synchronises the host unless `check=True`."""
-        self._check_status()
+        if not torch.cuda.is_current_stream_capturing():
+            self._check_status()
         obs, act, nxt, done, rew = (self._dev(x) for x in data)
         B = obs.shape[0]
         assert obs.shape[1] == self._cfg.obs_dim and act.shape == (B, self._cfg.action_dim)
@@ -359,12 +360,14 @@ class MTSAC:
             L.check(L.lib().mtrl_sac_phase2_critic_step_actor_grads(self._h, stream))
             dist.all_reduce(self._flat["actor_grads"][: la.trunk_total + 32], group=self.process_group)
             L.check(L.lib().mtrl_sac_phase3_actor_step_alpha(self._h, stream))
-        # asynchronous status read-back (checked at the next call, or now if check=True)
-        L.check(L.lib().mtrl_sac_read_status_async(self._h, _vp(self._status_host.data_ptr()), stream))
-        self._status_event.record()
-        self._pending_status = True
-        if check:
-            self._check_status()
+        # asynchronous status read-back (checked at the next call, or now if check=True); not while a CUDA graph
+        # is being captured (the captured update is replayed without host involvement)
+        if not torch.cuda.is_current_stream_capturing():
+            L.check(L.lib().mtrl_sac_read_status_async(self._h, _vp(self._status_host.data_ptr()), stream))
+            self._status_event.record()
+            self._pending_status = True
+            if check:
+                self._check_status()
         logs = self.logs()
         return self, logs
 
