@@ -109,6 +109,8 @@ int mtrl_sampler_sample_per_task(mtrl_sampler_t* s, int fill, const int* counts,
  * update (mtsac.py:607-613).
  * ------------------------------------------------------------------------------------------ */
 #define MTRL_MAX_DEPTH 4
+#define MTRL_VARIANT_MTSAC 0
+#define MTRL_VARIANT_SAC 1
 
 typedef struct mtrl_sac_config {
   int num_tasks;        /* T: width of the one-hot block that ends every observation             */
@@ -130,6 +132,10 @@ typedef struct mtrl_sac_config {
   int clip_q;           /* AlgorithmConfig.clip: clamp target and prediction to +-5000            */
   int use_task_weights; /* MTSACConfig.use_task_weights                                           */
   unsigned long long noise_seed; /* Philox seed used when eps_c / eps_a are NULL                  */
+  int variant;          /* MTRL_VARIANT_MTSAC: MTSAC._update_inner (mtsac.py:1173-1247);
+                           MTRL_VARIANT_SAC: single-task SAC._update_inner (sac.py:262-383): num_tasks = 1 (the network
+                           is a plain MLP, mtrl/nn/base.py:11-63, its last Dense is the one "head"), alpha updated first,
+                           critic loss 0.5 * sum_e mean_b, parameter-norm logs of the pre-update parameters        */
 } mtrl_sac_config_t;
 
 /* Flat fp32 layout of one network (all ensemble members).  [member trunks | 32 reduction slots |

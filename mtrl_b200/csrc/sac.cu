@@ -128,6 +128,9 @@ int validate(const mtrl_sac_config_t& c) {
   MTRL_REQUIRE(c.max_rows >= kTileRows && c.max_rows % kTileRows == 0, "sac config: max_rows %d must be a multiple of %d",
                c.max_rows, kTileRows);
   MTRL_REQUIRE(c.max_batch >= 1 && c.max_batch <= c.max_rows, "sac config: max_batch %d outside [1, max_rows]", c.max_batch);
+  MTRL_REQUIRE(c.variant == MTRL_VARIANT_MTSAC || c.variant == MTRL_VARIANT_SAC, "sac config: unknown variant %d", c.variant);
+  MTRL_REQUIRE(c.variant != MTRL_VARIANT_SAC || (c.num_tasks == 1 && c.num_local_tasks == 1 && !c.use_task_weights && !c.clip_q),
+               "sac config: the single-task variant needs num_tasks == 1, no task weights, no Q clipping");
   MTRL_REQUIRE(!(c.use_task_weights && c.num_local_tasks != c.num_tasks),
                "sac config: use_task_weights needs all tasks on one handle (softmax over every log_alpha)");
   return MTRL_OK;
@@ -507,54 +510,71 @@ extern "C" int mtrl_sac_refresh_shadows(mtrl_sac_t* h, void* stream) {
   return MTRL_OK;
 }
 
-extern "C" int mtrl_sac_phase1_critic_grads(mtrl_sac_t* h, const float* obs, const float* actions, const float* next_obs,
-                                            const float* dones, const float* rewards, int batch, int global_batch,
-                                            const float* eps_c, const float* eps_a, void* stream) {
+// ---------------------------------------------------------------------------------------------
+// Steps of the update.  MT-SAC (mtsac.py:1173-1247) runs them as
+//   begin -> critic_grads -> [all-reduce] -> critic_apply -> actor_sample -> actor_grads -> [all-reduce] -> actor_apply -> alpha
+// single-task SAC (sac.py:262-383) as
+//   begin -> actor_sample -> alpha -> critic_grads (NEW alpha) -> critic_apply -> actor_grads (NEW alpha, NEW critic) -> actor_apply
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+int step_alpha_prep(mtrl_sac* h, cudaStream_t st) {
+  alpha_prep_kernel<<<1, 256, 0, st>>>(h->buf.log_alpha, h->cfg.num_local_tasks, h->cfg.use_task_weights, h->ws.alpha_val,
+                                       h->ws.task_w);
+  MTRL_CUDA_CHECK(cudaGetLastError());
+  LAUNCHED(h);
+  return MTRL_OK;
+}
+
+// memsets, alpha values, packing, and the forward passes that only need the OLD actor / critic:
+// actor trunk on s' and s, critic trunk on (a_buffer, s).
+int step_begin(mtrl_sac* h, const float* obs, const float* actions, const float* next_obs, const float* dones,
+               const float* rewards, int batch, int global_batch, const float* eps_c, const float* eps_a, cudaStream_t st) {
   MTRL_REQUIRE(h && obs && actions && next_obs && dones && rewards, "mtrl_sac_update: null batch pointer");
   const mtrl_sac_config_t& c = h->cfg;
   MTRL_REQUIRE(batch >= 1 && batch <= c.max_batch, "mtrl_sac_update: batch %d outside [1, %d]", batch, c.max_batch);
   MTRL_REQUIRE(global_batch >= batch, "mtrl_sac_update: global_batch %d < batch %d", global_batch, batch);
   MTRL_REQUIRE((eps_c == nullptr) == (eps_a == nullptr), "mtrl_sac_update: pass both eps_c and eps_a or neither");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   Workspace& w = h->ws;
-  const mtrl_net_layout_t& LA = h->lay.actor;
-  const mtrl_net_layout_t& LC = h->lay.critic;
-  const int M = c.max_rows, W = c.width, D = c.depth, E = c.num_critics, T = c.num_local_tasks;
+  const int M = c.max_rows, D = c.depth, T = c.num_local_tasks;
   h->launches = 0;
   h->batch = batch;
   h->global_batch = global_batch;
-
   MTRL_CUDA_CHECK(cudaMemsetAsync(w.acc, 0, ACC_COUNT * sizeof(double), st));
   MTRL_CUDA_CHECK(cudaMemsetAsync(w.status, 0, 16, st));
-  MTRL_CUDA_CHECK(cudaMemsetAsync(h->buf.critic_grads, 0, LC.total * sizeof(float), st));
-  MTRL_CUDA_CHECK(cudaMemsetAsync(h->buf.actor_grads, 0, LA.total * sizeof(float), st));
+  MTRL_CUDA_CHECK(cudaMemsetAsync(h->buf.critic_grads, 0, h->lay.critic.total * sizeof(float), st));
+  MTRL_CUDA_CHECK(cudaMemsetAsync(h->buf.actor_grads, 0, h->lay.actor.total * sizeof(float), st));
   h->launches += 4;
-
-  alpha_prep_kernel<<<1, 256, 0, st>>>(h->buf.log_alpha, T, c.use_task_weights, w.alpha_val, w.task_w);
+  MTRL_PROPAGATE(step_alpha_prep(h, st));
+  const int nchunks = (batch + 31) / 32;
+  const size_t smem = (static_cast<size_t>(nchunks) * T + T + 1) * sizeof(int);
+  MTRL_REQUIRE(smem <= 200 * 1024, "mtrl_sac_update: batch %d x %d tasks exceeds the packing kernel's shared memory", batch, T);
+  row_task_kernel<<<(batch + 7) / 8, 256, 0, st>>>(obs, batch, c.obs_dim, c.num_tasks, c.task_begin, T, w.row_slot, w.status);
+  pack_plan_kernel<<<1, 1024, smem, st>>>(batch, T, M, w.row_slot, w.slot_src, w.tile_task, w.seg_start, w.status);
+  h->launches += 2;
+  PackArgs a;
+  a.obs = obs; a.actions = actions; a.next_obs = next_obs; a.dones = dones; a.rewards = rewards;
+  a.eps_c = eps_c; a.eps_a = eps_a;
+  a.Xa_next = w.Xa_next; a.Xa = w.Xa; a.Xc_next = w.Xc_next; a.Xc = w.Xc;
+  a.rew = w.rew; a.done = w.done; a.peps_c = w.eps_c; a.peps_a = w.eps_a;
+  a.slot_src = w.slot_src;
+  a.noise_counter = h->buf.steps + 3;
+  a.seed = c.noise_seed;
+  a.obs_dim = c.obs_dim; a.act_dim = c.action_dim; a.Ka = h->lay.k_actor; a.Kc = h->lay.k_critic;
+  pack_rows_kernel<<<M, 128, 0, st>>>(a);
   LAUNCHED(h);
-  {
-    const int nchunks = (batch + 31) / 32;
-    const size_t smem = (static_cast<size_t>(nchunks) * T + T + 1) * sizeof(int);
-    MTRL_REQUIRE(smem <= 200 * 1024, "mtrl_sac_update: batch %d x %d tasks exceeds the packing kernel's shared memory", batch, T);
-    row_task_kernel<<<(batch + 7) / 8, 256, 0, st>>>(obs, batch, c.obs_dim, c.num_tasks, c.task_begin, T, w.row_slot, w.status);
-    pack_plan_kernel<<<1, 1024, smem, st>>>(batch, T, M, w.row_slot, w.slot_src, w.tile_task, w.seg_start, w.status);
-    h->launches += 2;
-    PackArgs a;
-    a.obs = obs; a.actions = actions; a.next_obs = next_obs; a.dones = dones; a.rewards = rewards;
-    a.eps_c = eps_c; a.eps_a = eps_a;
-    a.Xa_next = w.Xa_next; a.Xa = w.Xa; a.Xc_next = w.Xc_next; a.Xc = w.Xc;
-    a.rew = w.rew; a.done = w.done; a.peps_c = w.eps_c; a.peps_a = w.eps_a;
-    a.slot_src = w.slot_src;
-    a.noise_counter = h->buf.steps + 3;
-    a.seed = c.noise_seed;
-    a.obs_dim = c.obs_dim; a.act_dim = c.action_dim; a.Ka = h->lay.k_actor; a.Kc = h->lay.k_critic;
-    pack_rows_kernel<<<M, 128, 0, st>>>(a);
-    LAUNCHED(h);
-    MTRL_CUDA_CHECK(cudaGetLastError());
-  }
-  // forward: actor on s' and s (old actor), critics on (a, s)
+  MTRL_CUDA_CHECK(cudaGetLastError());
   for (int l = 0; l < D; ++l) MTRL_PROPAGATE(run_plan(h, h->fwd[l], st));
-  // a' ~ pi(s'), log pi(a'|s')   (mtsac.py:526-528); a' lands in the action columns of the target critics' input
+  return MTRL_OK;
+}
+
+// Critic loss and gradients (mtsac.py:526-597 / sac.py:267-300): a' ~ pi_old(s'), target critics on (a', s'), Bellman
+// target with the CURRENT alpha_val, dL/dQ, head and trunk VJPs; leaves the head-gradient squared norm in the slot.
+int step_critic_grads(mtrl_sac* h, cudaStream_t st) {
+  const mtrl_sac_config_t& c = h->cfg;
+  Workspace& w = h->ws;
+  const mtrl_net_layout_t& LC = h->lay.critic;
+  const int M = c.max_rows, W = c.width, D = c.depth, E = c.num_critics;
   MTRL_PROPAGATE(launch_actor_head(h, w.An[D - 1], w.eps_c, w.Xc_next, w.logp_next, false, st));
   for (int l = 0; l < D; ++l) MTRL_PROPAGATE(run_plan(h, h->fwd_target[l], st));
   {
@@ -573,7 +593,9 @@ extern "C" int mtrl_sac_phase1_critic_grads(mtrl_sac_t* h, const float* obs, con
     a.dq = w.dq; a.acc = w.acc;
     a.M = M; a.W = W; a.E = E;
     a.gamma = c.gamma;
-    a.inv_eb = 1.f / (static_cast<float>(E) * static_cast<float>(global_batch));
+    const float B = static_cast<float>(h->global_batch);
+    // MT-SAC: L = mean over (E, B) of (q-y)^2 (mtsac.py:565); SAC: L = 0.5 * sum_e mean_b (q-y)^2 (sac.py:292)
+    a.dq_scale = c.variant == MTRL_VARIANT_SAC ? 1.f / B : 2.f / (static_cast<float>(E) * B);
     a.clip = c.clip_q;
     critic_loss_kernel<<<(M + 7) / 8, 256, 0, st>>>(a);
     MTRL_CUDA_CHECK(cudaGetLastError());
@@ -599,37 +621,58 @@ extern "C" int mtrl_sac_phase1_critic_grads(mtrl_sac_t* h, const float* obs, con
   return MTRL_OK;
 }
 
-extern "C" int mtrl_sac_phase2_critic_step_actor_grads(mtrl_sac_t* h, void* stream) {
-  MTRL_REQUIRE(h && h->batch > 0, "mtrl_sac_phase2: phase 1 has not run");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+// clip_by_global_norm + Adam on the critic, Polyak target update, log scalars (mtsac.py:599-621).
+int step_critic_apply(mtrl_sac* h, cudaStream_t st) {
+  const mtrl_sac_config_t& c = h->cfg;
+  Workspace& w = h->ws;
+  const mtrl_net_layout_t& LC = h->lay.critic;
+  const float EB = static_cast<float>(c.num_critics) * static_cast<float>(h->global_batch);
+  sumsq_kernel<<<h->sms * 2, 256, 0, st>>>(h->buf.critic_grads, LC.trunk_total, w.acc + ACC_CRITIC_G2);
+  LAUNCHED(h);
+  AdamArgs a;
+  a.p = h->buf.critic_params; a.m = h->buf.critic_m; a.v = h->buf.critic_v; a.shadow = h->buf.critic_shadow;
+  a.g = h->buf.critic_grads; a.target = h->buf.critic_target; a.target_shadow = h->buf.critic_target_shadow;
+  a.n = LC.total; a.trunk_n = LC.trunk_total;
+  a.g2_trunk = w.acc + ACC_CRITIC_G2; a.g2_heads = h->buf.critic_grads + LC.slots_off;
+  a.step = h->buf.steps + 1;
+  a.p2_trunk = w.acc + ACC_CRITIC_P2_TRUNK; a.p2_head = w.acc + ACC_CRITIC_P2_HEAD; a.p2_old = w.acc + ACC_CRITIC_P2_OLD;
+  a.lr = c.critic_lr; a.b1 = c.adam_b1; a.b2 = c.adam_b2; a.eps = c.adam_eps; a.max_norm = c.critic_max_grad_norm;
+  a.tau = c.tau;
+  adam_kernel<<<h->sms * 4, 256, 0, st>>>(a);
+  LAUNCHED(h);
+  const float loss_scale = c.variant == MTRL_VARIANT_SAC ? 0.5f / static_cast<float>(h->global_batch) : 1.f / EB;
+  finalize_critic_kernel<<<1, 1, 0, st>>>(w.acc, h->buf.critic_grads + LC.slots_off, h->buf.steps, h->buf.logs, 1.f / EB,
+                                          loss_scale, c.variant == MTRL_VARIANT_SAC);
+  LAUNCHED(h);
+  MTRL_CUDA_CHECK(cudaGetLastError());
+  return MTRL_OK;
+}
+
+// a ~ pi_old(s), log pi(a|s) and what the tanh-Gaussian VJP needs (mtsac.py:640-642).  With write_x the sampled
+// action also becomes the action columns of the critic input (only valid once the critic backward has consumed them).
+int step_actor_sample(mtrl_sac* h, bool write_x, cudaStream_t st) {
+  Workspace& w = h->ws;
+  return launch_actor_head(h, w.Ao[h->cfg.depth - 1], w.eps_a, write_x ? w.Xc : nullptr, w.logp, true, st);
+}
+
+int step_write_actions(mtrl_sac* h, cudaStream_t st) {
+  const mtrl_sac_config_t& c = h->cfg;
+  write_actions_kernel<<<(c.max_rows * c.action_dim + 255) / 256, 256, 0, st>>>(h->ws.act, h->ws.Xc, h->lay.k_critic,
+                                                                                c.max_rows, c.action_dim);
+  MTRL_CUDA_CHECK(cudaGetLastError());
+  LAUNCHED(h);
+  return MTRL_OK;
+}
+
+// Actor loss and gradients (mtsac.py:631-692): Q of the CURRENT critic params on (a, s), dL/da back through the
+// critics (input gradients only), tanh-Gaussian VJP, actor head and trunk VJPs.
+int step_actor_grads(mtrl_sac* h, cudaStream_t st) {
   const mtrl_sac_config_t& c = h->cfg;
   Workspace& w = h->ws;
   const mtrl_net_layout_t& LA = h->lay.actor;
   const mtrl_net_layout_t& LC = h->lay.critic;
   const int M = c.max_rows, W = c.width, D = c.depth, E = c.num_critics;
   const float inv_b = 1.f / static_cast<float>(h->global_batch);
-  // ---- critic optimiser step + Polyak (mtsac.py:599-613) ----
-  sumsq_kernel<<<h->sms * 2, 256, 0, st>>>(h->buf.critic_grads, LC.trunk_total, w.acc + ACC_CRITIC_G2);
-  LAUNCHED(h);
-  {
-    AdamArgs a;
-    a.p = h->buf.critic_params; a.m = h->buf.critic_m; a.v = h->buf.critic_v; a.shadow = h->buf.critic_shadow;
-    a.g = h->buf.critic_grads; a.target = h->buf.critic_target; a.target_shadow = h->buf.critic_target_shadow;
-    a.n = LC.total; a.trunk_n = LC.trunk_total;
-    a.g2_trunk = w.acc + ACC_CRITIC_G2; a.g2_heads = h->buf.critic_grads + LC.slots_off;
-    a.step = h->buf.steps + 1;
-    a.p2_trunk = w.acc + ACC_CRITIC_P2_TRUNK; a.p2_head = w.acc + ACC_CRITIC_P2_HEAD;
-    a.lr = c.critic_lr; a.b1 = c.adam_b1; a.b2 = c.adam_b2; a.eps = c.adam_eps; a.max_norm = c.critic_max_grad_norm;
-    a.tau = c.tau;
-    adam_kernel<<<h->sms * 4, 256, 0, st>>>(a);
-    LAUNCHED(h);
-    finalize_critic_kernel<<<1, 1, 0, st>>>(w.acc, h->buf.critic_grads + LC.slots_off, h->buf.steps, h->buf.logs,
-                                            1.f / (static_cast<float>(E) * static_cast<float>(h->global_batch)));
-    LAUNCHED(h);
-    MTRL_CUDA_CHECK(cudaGetLastError());
-  }
-  // ---- actor loss (mtsac.py:631-675): a ~ pi(s) with the old actor, Q from the NEW critic ----
-  MTRL_PROPAGATE(launch_actor_head(h, w.Ao[D - 1], w.eps_a, w.Xc, w.logp, true, st));
   for (int l = 0; l < D; ++l) MTRL_PROPAGATE(run_plan(h, h->fwd_pi[l], st));
   {
     ActorLossArgs a;
@@ -685,13 +728,10 @@ extern "C" int mtrl_sac_phase2_critic_step_actor_grads(mtrl_sac_t* h, void* stre
   return MTRL_OK;
 }
 
-extern "C" int mtrl_sac_phase3_actor_step_alpha(mtrl_sac_t* h, void* stream) {
-  MTRL_REQUIRE(h && h->batch > 0, "mtrl_sac_phase3: phase 1 has not run");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+int step_actor_apply(mtrl_sac* h, cudaStream_t st) {
   const mtrl_sac_config_t& c = h->cfg;
   Workspace& w = h->ws;
   const mtrl_net_layout_t& LA = h->lay.actor;
-  const float inv_b = 1.f / static_cast<float>(h->global_batch);
   sumsq_kernel<<<h->sms * 2, 256, 0, st>>>(h->buf.actor_grads, LA.trunk_total, w.acc + ACC_ACTOR_G2);
   LAUNCHED(h);
   AdamArgs a;
@@ -700,16 +740,25 @@ extern "C" int mtrl_sac_phase3_actor_step_alpha(mtrl_sac_t* h, void* stream) {
   a.n = LA.total; a.trunk_n = LA.trunk_total;
   a.g2_trunk = w.acc + ACC_ACTOR_G2; a.g2_heads = h->buf.actor_grads + LA.slots_off;
   a.step = h->buf.steps + 0;
-  a.p2_trunk = w.acc + ACC_ACTOR_P2_TRUNK; a.p2_head = w.acc + ACC_ACTOR_P2_HEAD;
+  a.p2_trunk = w.acc + ACC_ACTOR_P2_TRUNK; a.p2_head = w.acc + ACC_ACTOR_P2_HEAD; a.p2_old = w.acc + ACC_ACTOR_P2_OLD;
   a.lr = c.actor_lr; a.b1 = c.adam_b1; a.b2 = c.adam_b2; a.eps = c.adam_eps; a.max_norm = c.actor_max_grad_norm; a.tau = 0.f;
   adam_kernel<<<h->sms * 4, 256, 0, st>>>(a);
   LAUNCHED(h);
-  finalize_actor_kernel<<<1, 1, 0, st>>>(w.acc, h->buf.actor_grads + LA.slots_off, h->buf.steps, h->buf.logs, inv_b);
+  finalize_actor_kernel<<<1, 1, 0, st>>>(w.acc, h->buf.actor_grads + LA.slots_off, h->buf.steps, h->buf.logs,
+                                         1.f / static_cast<float>(h->global_batch), c.variant == MTRL_VARIANT_SAC);
   LAUNCHED(h);
+  MTRL_CUDA_CHECK(cudaGetLastError());
+  return MTRL_OK;
+}
+
+// Temperature step (mtsac.py:713-731 / sac.py:308-331) on the log-probs of step_actor_sample.
+int step_alpha(mtrl_sac* h, cudaStream_t st) {
+  const mtrl_sac_config_t& c = h->cfg;
+  Workspace& w = h->ws;
   AlphaArgs al;
   al.log_alpha = h->buf.log_alpha; al.m = h->buf.alpha_m; al.v = h->buf.alpha_v;
   al.logp = w.logp; al.seg_start = w.seg_start; al.slot_src = w.slot_src; al.steps = h->buf.steps; al.logs = h->buf.logs;
-  al.T_local = c.num_local_tasks; al.target_entropy = c.target_entropy; al.inv_b = inv_b;
+  al.T_local = c.num_local_tasks; al.target_entropy = c.target_entropy; al.inv_b = 1.f / static_cast<float>(h->global_batch);
   al.lr = c.alpha_lr; al.b1 = c.adam_b1; al.b2 = c.adam_b2; al.eps = c.adam_eps; al.max_norm = c.alpha_max_grad_norm;
   alpha_step_kernel<<<1, 1024, c.num_local_tasks * sizeof(float), st>>>(al);
   LAUNCHED(h);
@@ -717,9 +766,50 @@ extern "C" int mtrl_sac_phase3_actor_step_alpha(mtrl_sac_t* h, void* stream) {
   return MTRL_OK;
 }
 
+}  // namespace
+
+extern "C" int mtrl_sac_phase1_critic_grads(mtrl_sac_t* h, const float* obs, const float* actions, const float* next_obs,
+                                            const float* dones, const float* rewards, int batch, int global_batch,
+                                            const float* eps_c, const float* eps_a, void* stream) {
+  MTRL_REQUIRE(h, "mtrl_sac_phase1: null handle");
+  MTRL_REQUIRE(h->cfg.variant == MTRL_VARIANT_MTSAC, "the phase API is for the multi-task variant");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MTRL_PROPAGATE(step_begin(h, obs, actions, next_obs, dones, rewards, batch, global_batch, eps_c, eps_a, st));
+  return step_critic_grads(h, st);
+}
+
+extern "C" int mtrl_sac_phase2_critic_step_actor_grads(mtrl_sac_t* h, void* stream) {
+  MTRL_REQUIRE(h && h->batch > 0, "mtrl_sac_phase2: phase 1 has not run");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MTRL_PROPAGATE(step_critic_apply(h, st));
+  MTRL_PROPAGATE(step_actor_sample(h, true, st));
+  return step_actor_grads(h, st);
+}
+
+extern "C" int mtrl_sac_phase3_actor_step_alpha(mtrl_sac_t* h, void* stream) {
+  MTRL_REQUIRE(h && h->batch > 0, "mtrl_sac_phase3: phase 1 has not run");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MTRL_PROPAGATE(step_actor_apply(h, st));
+  return step_alpha(h, st);
+}
+
 extern "C" int mtrl_sac_update(mtrl_sac_t* h, const float* obs, const float* actions, const float* next_obs,
                                const float* dones, const float* rewards, int batch, int global_batch, const float* eps_c,
                                const float* eps_a, void* stream) {
+  MTRL_REQUIRE(h, "mtrl_sac_update: null handle");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (h->cfg.variant == MTRL_VARIANT_SAC) {
+    // sac.py:334-351: sample (a, logp) once; alpha first; critic with the new alpha; actor with new alpha and new critic
+    MTRL_PROPAGATE(step_begin(h, obs, actions, next_obs, dones, rewards, batch, global_batch, eps_c, eps_a, st));
+    MTRL_PROPAGATE(step_actor_sample(h, false, st));
+    MTRL_PROPAGATE(step_alpha(h, st));
+    MTRL_PROPAGATE(step_alpha_prep(h, st));
+    MTRL_PROPAGATE(step_critic_grads(h, st));
+    MTRL_PROPAGATE(step_critic_apply(h, st));
+    MTRL_PROPAGATE(step_write_actions(h, st));
+    MTRL_PROPAGATE(step_actor_grads(h, st));
+    return step_actor_apply(h, st);
+  }
   MTRL_PROPAGATE(mtrl_sac_phase1_critic_grads(h, obs, actions, next_obs, dones, rewards, batch, global_batch, eps_c, eps_a, stream));
   MTRL_PROPAGATE(mtrl_sac_phase2_critic_step_actor_grads(h, stream));
   MTRL_PROPAGATE(mtrl_sac_phase3_actor_step_alpha(h, stream));

@@ -20,6 +20,7 @@ constexpr int kColsumSplits = 32;
 enum {
   ACC_QLOSS = 0, ACC_QSUM, ACC_CRITIC_G2, ACC_CRITIC_P2_TRUNK, ACC_CRITIC_P2_HEAD, ACC_CRITIC_HEAD_G2,
   ACC_ACTOR_LOSS, ACC_ACTOR_G2, ACC_ACTOR_P2_TRUNK, ACC_ACTOR_P2_HEAD, ACC_ACTOR_HEAD_G2,
+  ACC_CRITIC_P2_OLD, ACC_ACTOR_P2_OLD,   // squared norm of the parameters BEFORE the step (sac.py:360-364 logs those)
   ACC_COUNT = 16
 };
 
@@ -300,7 +301,7 @@ __global__ void actor_head_kernel(const ActorHeadArgs p) {
       lp = -0.5f * e * e - 0.91893853320467274f - ls - fldj;
       if (ls_raw > p.ls_min && ls_raw < p.ls_max) mask = 1u << d;
     }
-    p.Xdst[static_cast<long long>(row) * p.ldx + d] = tf32_rna(a);
+    if (p.Xdst) p.Xdst[static_cast<long long>(row) * p.ldx + d] = tf32_rna(a);
     if (p.act) p.act[row * A + d] = a;
     if (p.logstd) p.logstd[row * A + d] = ls;
   }
@@ -364,7 +365,7 @@ __global__ void actor_head_tile_kernel(const ActorHeadArgs p) {
         lp = -0.5f * e * e - 0.91893853320467274f - ls - fldj;
         if (ls_raw > p.ls_min && ls_raw < p.ls_max) mask = 1u << d;
       }
-      p.Xdst[static_cast<long long>(row) * p.ldx + d] = tf32_rna(a);
+      if (p.Xdst) p.Xdst[static_cast<long long>(row) * p.ldx + d] = tf32_rna(a);
       if (p.act) p.act[row * A + d] = a;
       if (p.logstd) p.logstd[row * A + d] = ls;
     }
@@ -375,6 +376,13 @@ __global__ void actor_head_tile_kernel(const ActorHeadArgs p) {
       if (p.inrange) p.inrange[row] = mask;
     }
   }
+}
+
+// Copy saved policy actions into the action columns of the critic input (single-task SAC samples them before the
+// critic step, whose backward still needs the buffer actions there).
+__global__ void write_actions_kernel(const float* __restrict__ act, float* __restrict__ X, int ldx, int M, int A) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < M * A) X[static_cast<long long>(i / A) * ldx + (i % A)] = tf32_rna(act[i]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -409,7 +417,7 @@ struct CriticLossArgs {
   float* dq;       // [E][M]
   double* acc;
   int M, W, E;
-  float gamma, inv_eb;  // 1 / (E * B_global)
+  float gamma, dq_scale;  // dL/dQ_e = dq_scale * w * (Q_e - y)
   int clip;
 };
 
@@ -452,7 +460,7 @@ __global__ void critic_loss_kernel(const CriticLossArgs p) {
             const float diff = qc - y;
             loss += static_cast<double>(w * diff * diff);
             qsum += static_cast<double>(qc);
-            p.dq[static_cast<long long>(e) * p.M + row] = 2.f * w * diff * p.inv_eb * pass;
+            p.dq[static_cast<long long>(e) * p.M + row] = p.dq_scale * w * diff * pass;
           }
         }
       } else {
@@ -690,6 +698,7 @@ struct AdamArgs {
   const int* step;                   // Adam count before this step
   double* p2_trunk;
   double* p2_head;
+  double* p2_old;                    // squared norm of the parameters before the step
   float lr, b1, b2, eps, max_norm, tau;
 };
 
@@ -702,7 +711,7 @@ __global__ void adam_kernel(const AdamArgs a) {
   const int t = *a.step + 1;
   const float bc1 = static_cast<float>(1.0 - pow(static_cast<double>(a.b1), static_cast<double>(t)));
   const float bc2 = static_cast<float>(1.0 - pow(static_cast<double>(a.b2), static_cast<double>(t)));
-  double s_trunk = 0.0, s_head = 0.0;
+  double s_trunk = 0.0, s_head = 0.0, s_old = 0.0;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   // the flat buffers are 128-byte aligned and every region (trunk, 32 slots, heads) is a multiple of 32 floats
   const long long n4 = a.n / 4, slot4 = a.trunk_n / 4;
@@ -718,6 +727,7 @@ __global__ void adam_kernel(const AdamArgs a) {
     float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w}, pp[4] = {p4.x, p4.y, p4.z, p4.w};
     float tt[4] = {t4.x, t4.y, t4.z, t4.w}, sh[4], tsh[4];
     float sq = 0.f;
+    s_old += static_cast<double>(p4.x * p4.x + p4.y * p4.y + p4.z * p4.z + p4.w * p4.w);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const float g = gg[q] * scale;
@@ -742,9 +752,11 @@ __global__ void adam_kernel(const AdamArgs a) {
   }
   s_trunk = block_sum(s_trunk, red);
   s_head = block_sum(s_head, red);
+  s_old = block_sum(s_old, red);
   if (threadIdx.x == 0) {
     atomicAdd(a.p2_trunk, s_trunk);
     atomicAdd(a.p2_head, s_head);
+    atomicAdd(a.p2_old, s_old);
   }
 }
 
@@ -754,19 +766,24 @@ __global__ void shadow_kernel(const float* __restrict__ p, float* __restrict__ s
 }
 
 // Single thread: turn accumulators into the reference's log scalars and advance the Adam count.
-__global__ void finalize_critic_kernel(const double* acc, const float* g2_heads, int* steps, float* logs, float inv_eb) {
+__global__ void finalize_critic_kernel(const double* acc, const float* g2_heads, int* steps, float* logs, float inv_eb,
+                                       float loss_scale, int log_old_norm) {
   logs[MTRL_LOG_QF_VALUES] = static_cast<float>(acc[ACC_QSUM] * inv_eb);
-  logs[MTRL_LOG_QF_LOSS] = static_cast<float>(acc[ACC_QLOSS] * inv_eb);
+  logs[MTRL_LOG_QF_LOSS] = static_cast<float>(acc[ACC_QLOSS] * loss_scale);
   logs[MTRL_LOG_CRITIC_GRAD_MAGNITUDE] = static_cast<float>(sqrt(acc[ACC_CRITIC_G2] + static_cast<double>(*g2_heads)));
-  logs[MTRL_LOG_CRITIC_PARAMS_NORM] = static_cast<float>(sqrt(acc[ACC_CRITIC_P2_TRUNK] + acc[ACC_CRITIC_P2_HEAD]));
+  // mtsac.py:614,620 logs the norm of the UPDATED critic; sac.py:363-364 ravels self.critic.params, the old ones
+  logs[MTRL_LOG_CRITIC_PARAMS_NORM] = static_cast<float>(
+      sqrt(log_old_norm ? acc[ACC_CRITIC_P2_OLD] : acc[ACC_CRITIC_P2_TRUNK] + acc[ACC_CRITIC_P2_HEAD]));
   logs[LOG_X_CRITIC_P2_TRUNK] = static_cast<float>(acc[ACC_CRITIC_P2_TRUNK]);
   logs[LOG_X_CRITIC_P2_HEAD] = static_cast<float>(acc[ACC_CRITIC_P2_HEAD]);
   steps[1] += 1;
 }
-__global__ void finalize_actor_kernel(const double* acc, const float* g2_heads, int* steps, float* logs, float inv_b) {
+__global__ void finalize_actor_kernel(const double* acc, const float* g2_heads, int* steps, float* logs, float inv_b,
+                                      int log_old_norm) {
   logs[MTRL_LOG_ACTOR_LOSS] = static_cast<float>(acc[ACC_ACTOR_LOSS] * inv_b);
   logs[MTRL_LOG_ACTOR_GRAD_MAGNITUDE] = static_cast<float>(sqrt(acc[ACC_ACTOR_G2] + static_cast<double>(*g2_heads)));
-  logs[MTRL_LOG_ACTOR_PARAMS_NORM] = static_cast<float>(sqrt(acc[ACC_ACTOR_P2_TRUNK] + acc[ACC_ACTOR_P2_HEAD]));
+  logs[MTRL_LOG_ACTOR_PARAMS_NORM] = static_cast<float>(
+      sqrt(log_old_norm ? acc[ACC_ACTOR_P2_OLD] : acc[ACC_ACTOR_P2_TRUNK] + acc[ACC_ACTOR_P2_HEAD]));
   logs[LOG_X_ACTOR_P2_TRUNK] = static_cast<float>(acc[ACC_ACTOR_P2_TRUNK]);
   logs[LOG_X_ACTOR_P2_HEAD] = static_cast<float>(acc[ACC_ACTOR_P2_HEAD]);
   logs[MTRL_LOG_EXPLORE_LOSS] = 0.f;  // explore=False (mtsac.py:277, 671)

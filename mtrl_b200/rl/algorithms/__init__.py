@@ -1,11 +1,14 @@
-"""Mirror of mtrl/rl/algorithms/__init__.py:9-19 for the accelerated path."""
+"""Mirror of mtrl/rl/algorithms/__init__.py:9-19 for the accelerated paths."""
 from .mtsac import MTSAC, MTSACConfig
+from .sac import SAC, SACConfig
 
 
 def get_algorithm_for_config(config):
     if type(config) is MTSACConfig:
         return MTSAC
+    if type(config) is SACConfig:
+        return SAC
     raise ValueError(f"Unknown algorithm config type: {type(config)}")
 
 
-__all__ = ["MTSAC", "MTSACConfig", "get_algorithm_for_config"]
+__all__ = ["MTSAC", "MTSACConfig", "SAC", "SACConfig", "get_algorithm_for_config"]

@@ -48,7 +48,7 @@ class SacConfigC(C.Structure):
         ("adam_b1", C.c_float), ("adam_b2", C.c_float), ("adam_eps", C.c_float),
         ("actor_max_grad_norm", C.c_float), ("critic_max_grad_norm", C.c_float), ("alpha_max_grad_norm", C.c_float),
         ("log_std_min", C.c_float), ("log_std_max", C.c_float), ("target_entropy", C.c_float),
-        ("clip_q", C.c_int), ("use_task_weights", C.c_int), ("noise_seed", C.c_ulonglong),
+        ("clip_q", C.c_int), ("use_task_weights", C.c_int), ("noise_seed", C.c_ulonglong), ("variant", C.c_int),
     ]
 
 
@@ -237,18 +237,8 @@ class MTSAC:
             alpha_max_grad_norm=nm(t_opt.max_grad_norm), log_std_min=config.actor_config.log_std_min,
             log_std_max=config.actor_config.log_std_max, target_entropy=self.target_entropy,
             clip_q=int(config.clip), use_task_weights=int(config.use_task_weights), noise_seed=int(seed) & (2**63 - 1))
-        lay = SacLayoutC()
-        L.check(L.lib().mtrl_sac_query_layout(C.byref(self._cfg), C.byref(lay)))
-        self._lay = lay
-        z = lambda n, dt=torch.float32: torch.zeros(int(n), dtype=dt, device=dev)  # noqa: E731
-        self._flat = {f"actor_{k}": z(lay.actor.total) for k in ("params", "grads", "m", "v", "shadow")}
-        self._flat.update({f"critic_{k}": z(lay.critic.total)
-                           for k in ("params", "grads", "m", "v", "shadow", "target", "target_shadow")})
-        self._flat.update({"log_alpha": z(max(t_local, 4)), "alpha_m": z(max(t_local, 4)), "alpha_v": z(max(t_local, 4))})
-        self._steps = z(4, torch.int32)
-        self._logs = z(16)
-        self._workspace = z((lay.workspace_bytes + 3) // 4 + 64)
-        self._status_host = torch.zeros(4, dtype=torch.int32).pin_memory()
+        self._allocate(dev, t_local)
+        lay = self._lay
 
         # parameter views with the Flax names (mtsac.py:203-246 prints these trees)
         def ts(prefix, l, in_dim, ens, tx, step_idx):
@@ -281,6 +271,25 @@ class MTSAC:
         self._flat["critic_target"].copy_(self._flat["critic_params"])  # target_params=critic_init_params, mtsac.py:238-242
         la.fill_(math.log(config.initial_temperature))
 
+        self._create_handle()
+        return self
+
+    def _allocate(self, dev, t_local: int) -> None:
+        """Ask the library for the flat layouts of self._cfg and allocate every device buffer it needs."""
+        lay = SacLayoutC()
+        L.check(L.lib().mtrl_sac_query_layout(C.byref(self._cfg), C.byref(lay)))
+        self._lay = lay
+        z = lambda n, dt=torch.float32: torch.zeros(int(n), dtype=dt, device=dev)  # noqa: E731
+        self._flat = {f"actor_{k}": z(lay.actor.total) for k in ("params", "grads", "m", "v", "shadow")}
+        self._flat.update({f"critic_{k}": z(lay.critic.total)
+                           for k in ("params", "grads", "m", "v", "shadow", "target", "target_shadow")})
+        self._flat.update({"log_alpha": z(max(t_local, 4)), "alpha_m": z(max(t_local, 4)), "alpha_v": z(max(t_local, 4))})
+        self._steps = z(4, torch.int32)
+        self._logs = z(16)
+        self._workspace = z((lay.workspace_bytes + 3) // 4 + 64)
+        self._status_host = torch.zeros(4, dtype=torch.int32).pin_memory()
+
+    def _create_handle(self) -> None:
         bufs = SacBuffersC(**{k: v.data_ptr() for k, v in self._flat.items()}, steps=self._steps.data_ptr(),
                            logs=self._logs.data_ptr(), workspace=self._workspace.data_ptr())
         h = _vp()
@@ -288,7 +297,6 @@ class MTSAC:
         self._h = h
         self._status_event = torch.cuda.Event()
         self._pending_status = False
-        return self
 
     def __del__(self):
         if getattr(self, "_h", None) is not None and L._lib is not None:

@@ -291,3 +291,74 @@ class MultiTaskReplayBuffer:
         self._returns_max = d.get("returns_max", self._returns_max)
         self._norm_dev = None
         self._rng.__setstate__(ckpt["rng_state"])
+
+
+class ReplayBuffer:
+    """Mirror of the single-task `mtrl.rl.buffers.ReplayBuffer` (buffers.py:21-218), device resident.
+
+    The reference's `sample` reads `self.num_tasks`, which its `__init__` never sets (buffers.py:35-48 vs :197), so
+    calling it raises AttributeError in that snapshot; it is implemented here with the evident intent num_tasks = 1:
+    `batch_size` indices from `integers(0, max(fill, batch_size))`, rows gathered from all five arrays.  The index
+    stream is the same bit-exact PCG64 stream as the multi-task buffer."""
+
+    def __init__(self, capacity: int, env_obs_space, env_action_space, seed: int | None = None,
+                 device: str | torch.device = "cuda") -> None:
+        self._mt = MultiTaskReplayBuffer(capacity, 1, env_obs_space, env_action_space, seed=seed, device=device)
+        self.capacity = capacity
+        self.num_tasks = 1
+        self._rng = self._mt._rng
+        self._obs_shape, self._action_shape = self._mt._obs_shape, self._mt._action_shape
+
+    # storage views (capacity, dim), names of buffers.py:52-57
+    obs = property(lambda self: self._mt.obs[:, 0])
+    actions = property(lambda self: self._mt.actions[:, 0])
+    rewards = property(lambda self: self._mt.rewards[:, 0])
+    next_obs = property(lambda self: self._mt.next_obs[:, 0])
+    dones = property(lambda self: self._mt.dones[:, 0])
+    pos = property(lambda self: self._mt.pos, lambda self, v: setattr(self._mt, "pos", v))
+    full = property(lambda self: self._mt.full, lambda self, v: setattr(self._mt, "full", v))
+
+    def reset(self) -> None:
+        self._mt.reset()
+
+    def _advance_position(self, steps: int) -> None:  # buffers.py:83-93
+        self._mt._advance_position(steps)
+
+    def add(self, obs, next_obs, action, reward, done) -> None:
+        """buffers.py:95-140: a single transition (1-D inputs) or a batch with arbitrary leading dims."""
+        dev = self._mt.device
+        t = lambda x: torch.as_tensor(np.asarray(x) if not isinstance(x, torch.Tensor) else x, dtype=torch.float32).to(dev)  # noqa: E731
+        obs, next_obs, action, reward, done = t(obs), t(next_obs), t(action), t(reward), t(done)
+        if obs.ndim >= 2:
+            assert obs.shape[0] == action.shape[0] == reward.shape[0] == done.shape[0], \
+                "Batch size must be the same for all transition data."
+            fo, fn, fa = obs.reshape(-1, obs.shape[-1]), next_obs.reshape(-1, next_obs.shape[-1]), action.reshape(-1, action.shape[-1])
+            fr, fd = reward.reshape(-1, 1), done.reshape(-1, 1)
+            n = fo.shape[0]
+            idx = (self.pos + torch.arange(n, device=dev)) % self.capacity
+            self._mt.obs[idx, 0], self._mt.next_obs[idx, 0], self._mt.actions[idx, 0] = fo, fn, fa
+            self._mt.rewards[idx, 0], self._mt.dones[idx, 0] = fr, fd
+            self._advance_position(n)
+        else:
+            self._mt.obs[self.pos, 0], self._mt.actions[self.pos, 0], self._mt.next_obs[self.pos, 0] = obs, action, next_obs
+            self._mt.dones[self.pos, 0], self._mt.rewards[self.pos, 0] = done.reshape(-1), reward.reshape(-1)
+            self._advance_position(1)
+
+    def sample(self, batch_size: int) -> ReplayBufferSamples:
+        return self._mt.sample(int(batch_size))
+
+    def checkpoint(self) -> ReplayBufferCheckpoint:  # buffers.py:59-71
+        ck = self._mt.checkpoint()
+        d = ck["data"]
+        return {"data": {k: (d[k][:, 0] if k in ("obs", "actions", "rewards", "next_obs", "dones") else d[k])
+                         for k in ("obs", "actions", "rewards", "next_obs", "dones", "pos", "full")},
+                "rng_state": ck["rng_state"]}
+
+    def load_checkpoint(self, ckpt: ReplayBufferCheckpoint) -> None:  # buffers.py:73-81
+        for key in ["data", "rng_state"]:
+            assert key in ckpt
+        d = dict(ckpt["data"])
+        for k in ("obs", "actions", "rewards", "next_obs", "dones"):
+            assert k in d
+            d[k] = np.asarray(d[k])[:, None]
+        self._mt.load_checkpoint({"data": d, "rng_state": ckpt["rng_state"]})

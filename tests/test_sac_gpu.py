@@ -1,0 +1,121 @@
+"""Single-task SAC (sac.py:262-383) on the fused CUDA path vs the fp64 oracle, and the single-task ReplayBuffer
+mirror against the reference's own two tests (tests/test_rl_buffers.py:21-62)."""
+import dataclasses
+
+import numpy as np
+import pytest
+import torch
+
+import sac_util as SU
+from oracle import mtsac_oracle as O
+from oracle import sac_oracle as S
+
+pytestmark = pytest.mark.gpu
+
+
+def make_sac(cfg, max_batch, seed=1):
+    from mtrl_b200.config.networks import ContinuousActionPolicyConfig, QValueFunctionConfig
+    from mtrl_b200.config.nn import VanillaNetworkConfig
+    from mtrl_b200.config.optim import OptimizerConfig
+    from mtrl_b200.rl.algorithms import SAC, SACConfig
+
+    opt = OptimizerConfig(lr=cfg.lr, max_grad_norm=cfg.max_grad_norm, eps=cfg.adam_eps)
+    net = VanillaNetworkConfig(width=cfg.width, depth=cfg.depth, optimizer=opt)
+    sc = SACConfig(num_tasks=10, gamma=cfg.gamma, actor_config=ContinuousActionPolicyConfig(network_config=net),
+                   critic_config=QValueFunctionConfig(network_config=net), num_critics=cfg.num_critics, tau=cfg.tau,
+                   initial_temperature=cfg.initial_temperature)
+    return SAC.initialize(sc, SU.EnvSpec(cfg.obs_dim, cfg.action_dim), seed=seed, max_batch=max_batch)
+
+
+def mlp_pairs(otree, atree, ens):
+    p = atree["params"]
+    p = (p["VmapQValueFunction_0"] if ens else p)["VanillaNetwork_0"]["MLP_0"]
+    return [(f"{k}/{leaf}", otree[k][leaf], p[k][leaf]) for k in otree for leaf in ("kernel", "bias")]
+
+
+def load(agent, st):
+    for o, a, ens in ((st.actor, agent.actor.params, False), (st.critic, agent.critic.params, True),
+                      (st.critic_target, agent.critic.target_params, True)):
+        for _, src, dst in mlp_pairs(o, a, ens):
+            dst.copy_(src.float())
+    agent.alpha.params["params"]["log_alpha"].copy_(st.log_alpha.float())
+    agent.refresh()
+
+
+@pytest.mark.parametrize("width,batch", [(64, 96), (400, 1280)])
+def test_sac_update_matches_oracle(cuda, width, batch):
+    """(400, 1280) is experiments/baselines/mt10_sac_v2.py: MT10 observations (49 incl. one-hot) through a plain MLP."""
+    cfg = O.OracleConfig(num_tasks=1, obs_dim=49, action_dim=4, width=width, initial_temperature=0.8)
+    st = S.init_state(cfg, seed=2)
+    agent = make_sac(cfg, batch, seed=2)
+    load(agent, st)
+    st64 = st.to(torch.float64)
+    tcfg = dataclasses.replace(cfg, matmul_operands="tf32")
+    for step in range(2):
+        b, ec, ea = S.synthetic_batch(cfg, batch, seed=10 + step)
+        b64 = tuple(x.double() for x in b)
+        if step == 0:
+            _, _, tgr = S.sac_update(st64, b64, ec.double(), ea.double(), tcfg, return_grads=True)
+        old = st64
+        st64, logs64, gr = S.sac_update(st64, b64, ec.double(), ea.double(), cfg, return_grads=True)
+        _, logs = agent.update(tuple(x.cuda() for x in b), eps_c=ec.cuda(), eps_a=ea.cuda(), check=True)
+        assert set(logs) == set(S.SAC_LOG_KEYS)
+        for k in S.SAC_LOG_KEYS:
+            ref, got = float(logs64[k]), float(logs[k])
+            assert abs(got - ref) <= 1e-3 * (1 + step) * abs(ref) + 1e-5, f"step {step} {k}: {got} vs {ref}"
+        if step == 0:
+            for name, tree, ens in (("actor", agent.actor.grads, False), ("critic", agent.critic.grads, True)):
+                for leaf, o, a in mlp_pairs(tgr[name], tree, ens):
+                    assert SU.rel(a, o) <= 1e-2, f"grad vs tf32-operand oracle {name}/{leaf}: {SU.rel(a, o)}"
+                for leaf, o, a in mlp_pairs(gr[name], tree, ens):
+                    assert SU.rel(a, o) <= 8e-2, f"grad vs exact oracle {name}/{leaf}: {SU.rel(a, o)}"
+        for name, new_t, tree, ens in (("actor", st64.actor, agent.actor.params, False), ("critic", st64.critic, agent.critic.params, True),
+                                       ("target", st64.critic_target, agent.critic.target_params, True)):
+            pairs = mlp_pairs(new_t, tree, ens)
+            fa = torch.cat([a.detach().double().flatten().cpu() for _, _, a in pairs])
+            fo = torch.cat([o.flatten() for _, o, _ in pairs])
+            assert float((fa - fo).norm() / fo.norm()) <= 1e-3, f"{name} parameters"
+        la = agent.alpha.params["params"]["log_alpha"]
+        assert SU.rel(la - old.log_alpha.cuda().float(), st64.log_alpha - old.log_alpha) <= 1e-2
+    assert agent.get_num_params()["actor_num_params"] == O.num_params(st.actor)
+
+
+def _buffer(capacity):
+    from mtrl_b200.rl.buffers import ReplayBuffer
+
+    return ReplayBuffer(capacity=capacity, env_obs_space=SU._Space((3,)), env_action_space=SU._Space((2,)), seed=0)
+
+
+def test_replay_buffer_sets_full_flag_after_single_transitions(cuda):
+    """/root/reference/tests/test_rl_buffers.py:21-35."""
+    buffer = _buffer(4)
+    for idx in range(buffer.capacity):
+        value = float(idx)
+        buffer.add(obs=np.full((3,), value, dtype=np.float32), next_obs=np.full((3,), value + 1.0, dtype=np.float32),
+                   action=np.full((2,), -value, dtype=np.float32), reward=np.array([value], dtype=np.float32),
+                   done=np.array([idx % 2], dtype=np.float32))
+    assert buffer.full is True
+    assert buffer.pos == 0
+    assert torch.equal(buffer.obs[:, 0].cpu(), torch.arange(4.0))
+
+
+def test_replay_buffer_sets_full_flag_after_batched_transitions(cuda):
+    """/root/reference/tests/test_rl_buffers.py:38-62."""
+    buffer = _buffer(5)
+    n = buffer.capacity
+    obs = np.arange(n * 3, dtype=np.float32).reshape(n, 3)
+    next_obs = obs + 1.0
+    action = np.arange(n * 2, dtype=np.float32).reshape(n, 2)
+    reward = np.arange(n, dtype=np.float32)
+    done = np.zeros(n, dtype=np.float32)
+    buffer.add(obs=obs, next_obs=next_obs, action=action, reward=reward, done=done)
+    assert buffer.full is True
+    assert buffer.pos == 0
+    buffer.add(obs=obs[:2], next_obs=next_obs[:2], action=action[:2], reward=reward[:2], done=done[:2])
+    assert buffer.full is True
+    assert buffer.pos == 2
+    s = buffer.sample(4)
+    g = np.random.default_rng(0)
+    idx = g.integers(0, 5, size=(4,))
+    assert np.array_equal(s.observations.cpu().numpy(), buffer.obs.cpu().numpy()[idx])
+    assert s.rewards.shape == (4, 1) and s.actions.shape == (4, 2)
