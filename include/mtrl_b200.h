@@ -53,6 +53,10 @@ typedef struct mtrl_gemm_problem {
   const float* bias;    /* device [N] for MTRL_EPI_BIAS_RELU                                        */
   const float* mask;    /* device [M][N] for MTRL_EPI_RELU_MASK                                     */
   long long ldmask;
+  const unsigned* mask_bits; /* MTRL_EPI_RELU_MASK alternative to `mask`: bit (n % 32) of word [m][n / 32] set <=>
+                                the forward activation was > 0 (rows of ldbits words)                            */
+  unsigned* relu_bits_out;   /* optional, MTRL_EPI_BIAS_RELU: emit those bits for the backward pass               */
+  long long ldbits;
   float* colsum_partial; /* optional, MTRL_EPI_RELU_MASK only: device [ceil(M/32)][N] receiving the column sums of
                             every 32-row group of D (bias gradients are their sum over groups); NULL to skip  */
 } mtrl_gemm_problem_t;

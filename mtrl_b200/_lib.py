@@ -24,7 +24,8 @@ class GemmProblem(C.Structure):
         ("D", C.c_void_p), ("ldd", C.c_longlong),
         ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
         ("block_n", C.c_int), ("k_splits", C.c_int), ("epilogue", C.c_int),
-        ("bias", C.c_void_p), ("mask", C.c_void_p), ("ldmask", C.c_longlong), ("colsum_partial", C.c_void_p),
+        ("bias", C.c_void_p), ("mask", C.c_void_p), ("ldmask", C.c_longlong),
+        ("mask_bits", C.c_void_p), ("relu_bits_out", C.c_void_p), ("ldbits", C.c_longlong), ("colsum_partial", C.c_void_p),
     ]
 
 

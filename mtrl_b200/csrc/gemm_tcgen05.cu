@@ -36,12 +36,18 @@ constexpr int kThreads = 64 + 32 * kEpilogueWarps;
 // kCtas == 2: a CTA pair (cta_group::2) owns a 256 x block_n tile; each CTA stages its own 128 rows of A and
 //             HALF of B's N, so a k-block costs 32 KB of L2->smem traffic per SM instead of 48 KB (the 1-CTA
 //             kernel is bound by that traffic, profiles/r01_gemm_1cta.txt) and 6 stages fit.
+// Epilogue staging per epilogue warp: two 32 x 32 fp32 boxes (SWIZZLE_128B, 4 KB each) for TMA stores, 512 B of bias.
+constexpr int kEpiBoxBytes = 32 * 32 * 4;
+constexpr int kEpiStageBytes = kEpilogueWarps * 2 * kEpiBoxBytes;   // 64 KB
+constexpr int kEpiBiasBytes = kEpilogueWarps * 512;                 // 4 KB
+
 template <int kCtas>
 struct Cfg {
   static constexpr int kBBytes = (kMaxBlockN / kCtas) * kBlockK * 4;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = kCtas == 1 ? 4 : 6;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStages = kCtas == 1 ? 3 : 4;
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + kEpiStageBytes + kEpiBiasBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct __align__(16) DevProblem {
@@ -49,6 +55,9 @@ struct __align__(16) DevProblem {
   const float* bias;
   const float* mask;
   float* colsum;   // optional [ceil(M/32)][N] partial column sums (ReLU-mask epilogue)
+  const unsigned* mask_bits;  // ReLU-mask epilogue: bit (n % 32) of word [m][n / 32] set <=> forward activation > 0
+  unsigned* bits_out;         // bias+ReLU epilogue: optional, emits those bits
+  long long ldbits;
   long long ldd;
   long long ldmask;
   int M, N, K;
@@ -61,6 +70,8 @@ struct __align__(16) DevProblem {
   uint32_t idesc;
   int b_chunks;  // 32-wide MN chunks of B each CTA loads per stage (MN-major B only)
   int mn3d;      // bit 0 / 1: A / B is MN-major and described by a 3-D map (one TMA per stage instead of one per chunk)
+  int tma_out;   // output goes through smem staging + TMA store / reduce-add (needs block_n % 32 == 0)
+  int pad0, pad1, pad2;
 };
 
 // smem matrix descriptor (cute::UMMA::SmemDescriptor layout): start>>4 [0,14), LBO>>4 [16,30),
@@ -81,7 +92,7 @@ constexpr int kMaxProblems = 8;
 
 // Passed by value as a __grid_constant__ kernel parameter (the usual home of TMA descriptors).
 struct GemmParams {
-  CUtensorMap maps[2 * kMaxProblems];
+  CUtensorMap maps[3 * kMaxProblems];   // A, B, D of every problem
   DevProblem probs[kMaxProblems];
   int nprob;
   int total_units;
@@ -109,47 +120,6 @@ __device__ __forceinline__ UnitCoord decode_unit(const DevProblem* __restrict__ 
   return c;
 }
 
-// Epilogue of one 16-column chunk of one accumulator row.
-__device__ __forceinline__ void epilogue_chunk(const DevProblem& P, const uint32_t (&v)[16], float* drow,
-                                               const float* mrow, int col0) {
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int col = col0 + 4 * q;
-    if (col + 4 <= P.N) {
-      float4 o;
-      o.x = __uint_as_float(v[4 * q + 0]);
-      o.y = __uint_as_float(v[4 * q + 1]);
-      o.z = __uint_as_float(v[4 * q + 2]);
-      o.w = __uint_as_float(v[4 * q + 3]);
-      if (P.epilogue == MTRL_EPI_BIAS_RELU) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + col));
-        o.x = tf32_rna(fmaxf(o.x + b.x, 0.f));
-        o.y = tf32_rna(fmaxf(o.y + b.y, 0.f));
-        o.z = tf32_rna(fmaxf(o.z + b.z, 0.f));
-        o.w = tf32_rna(fmaxf(o.w + b.w, 0.f));
-        *reinterpret_cast<float4*>(drow + col) = o;
-      } else if (P.epilogue == MTRL_EPI_RELU_MASK) {
-        const float4 h = __ldg(reinterpret_cast<const float4*>(mrow + col));
-        o.x = h.x > 0.f ? tf32_rna(o.x) : 0.f;
-        o.y = h.y > 0.f ? tf32_rna(o.y) : 0.f;
-        o.z = h.z > 0.f ? tf32_rna(o.z) : 0.f;
-        o.w = h.w > 0.f ? tf32_rna(o.w) : 0.f;
-        *reinterpret_cast<float4*>(drow + col) = o;
-      } else if (P.epilogue == MTRL_EPI_ATOMIC_ADD) {
-        atomicAdd(reinterpret_cast<float4*>(drow + col), o);
-      } else if (P.epilogue == MTRL_EPI_STORE_TF32) {
-        o.x = tf32_rna(o.x);
-        o.y = tf32_rna(o.y);
-        o.z = tf32_rna(o.z);
-        o.w = tf32_rna(o.w);
-        *reinterpret_cast<float4*>(drow + col) = o;
-      } else {
-        *reinterpret_cast<float4*>(drow + col) = o;
-      }
-    }
-  }
-}
-
 template <int kCtas>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
@@ -161,7 +131,8 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
   const int total_units = params.total_units;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + kStages * C::kStageBytes;
+  const uint32_t epi_base = smem_base + kStages * C::kStageBytes;   // 1024-aligned staging boxes, then bias
+  const uint32_t bar_base = epi_base + kEpiStageBytes + kEpiBiasBytes;
   // barrier layout (8 bytes each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
@@ -212,8 +183,8 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
       for (int unit = worker; unit < total_units; unit += nworkers) {
         const UnitCoord c = decode_unit(probs, nprob, unit);
         const DevProblem& P = probs[c.p];
-        const CUtensorMap* mapA = maps + 2 * c.p;
-        const CUtensorMap* mapB = maps + 2 * c.p + 1;
+        const CUtensorMap* mapA = maps + 3 * c.p;
+        const CUtensorMap* mapB = maps + 3 * c.p + 1;
         const int n_cta = P.block_n / kCtas;                       // B columns staged by this CTA
         const int m0 = (c.m_tile * kCtas + static_cast<int>(rank)) * kBlockM;
         const int n0 = c.n_tile * P.block_n + static_cast<int>(rank) * n_cta;
@@ -343,19 +314,33 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
     }
   } else {
     // ===================== epilogue (warps 2..9 of every CTA) =====================
-    const int quarter = warp & 3;          // TMEM lanes [32*quarter, 32*quarter+32) are this warp's
-    const int col_half = (warp - 2) >> 2;  // which half of the tile's 16-column chunks this warp drains
+    // Warp (quarter, col_half) drains TMEM lanes [32*quarter, +32) x its half of the tile's columns in 32-column
+    // boxes: TMEM -> registers -> fused op -> swizzled smem box -> one TMA store (or reduce-add) per box, so global
+    // memory sees full 128-byte lines instead of 32 scattered 16-byte pieces per instruction.
+    const int quarter = warp & 3;
+    const int ew = warp - 2;
+    const int col_half = ew >> 2;
+    const uint32_t stg0 = epi_base + static_cast<uint32_t>(ew) * 2u * kEpiBoxBytes;
+    const uint32_t sbias = epi_base + kEpiStageBytes + static_cast<uint32_t>(ew) * 512u;
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t nbox = 0;  // running count of TMA boxes this warp has issued (selects the staging buffer)
     long long t_wait = 0, t_work = 0;
     for (int unit = worker; unit < total_units; unit += nworkers) {
       const UnitCoord c = decode_unit(probs, nprob, unit);
       const DevProblem& P = probs[c.p];
-      const int row = (c.m_tile * kCtas + static_cast<int>(rank)) * kBlockM + quarter * 32 + lane;
+      const CUtensorMap* mapD = maps + 3 * c.p + 2;
+      const int row0 = (c.m_tile * kCtas + static_cast<int>(rank)) * kBlockM + quarter * 32;
+      const int row = row0 + lane;
       const int n0 = c.n_tile * P.block_n;
       const bool row_ok = row < P.M;
       float* drow = P.D + static_cast<long long>(row) * P.ldd;
       const float* mrow = P.mask ? P.mask + static_cast<long long>(row) * P.ldmask : nullptr;
+      const int chunks = P.block_n >> 4;
+      const int c0 = min(((chunks + 3) >> 2) << 1, chunks);   // 16-column chunks of the first half (even unless tiny)
+      const int cbeg = col_half ? c0 * 16 : 0;
+      const int cend = col_half ? P.block_n : c0 * 16;
+      const int epi = P.epilogue;
       const long long t0 = params.dbg ? clock64() : 0;
       mbar_wait(tfull_bar(acc), acc_phase);
       const long long t1 = params.dbg ? clock64() : 0;
@@ -363,77 +348,127 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                              static_cast<uint32_t>(acc) * kMaxBlockN;
-      const int n_split = ((P.block_n / 16 + 1) / 2) * 16;
-      const int cbeg = col_half ? n_split : 0;
-      const int cend = col_half ? P.block_n : n_split;
-      if (P.epilogue == MTRL_EPI_RELU_MASK) {
-        // ReLU VJP: the forward activation is fetched two 16-column chunks ahead of its use so the
-        // (per-thread-row, DRAM-latency) loads overlap the TMEM reads and stores of earlier chunks.
-        constexpr int kAhead = 2;
-        float4 pre[kAhead][4];
-        auto fetch = [&](int cc, float4 (&dst)[4]) {
+      if (epi == MTRL_EPI_BIAS_RELU) {
+        // this warp's (<= 128) bias values, staged once per tile
+        const int col = n0 + cbeg + 4 * lane;
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cbeg + 4 * lane < cend && col + 4 <= P.N) b = __ldg(reinterpret_cast<const float4*>(P.bias + col));
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sbias + 16u * lane), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w)
+                     : "memory");
+        __syncwarp();
+      }
+      // ReLU bits of the forward activation for this warp's boxes (one 32-bit word per row and box)
+      unsigned mbits[4] = {0u, 0u, 0u, 0u};
+      if (epi == MTRL_EPI_RELU_MASK && P.mask_bits && row_ok) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int col = n0 + cc + 4 * q;
-            dst[q] = (row_ok && cc < cend && col + 4 <= P.N) ? __ldg(reinterpret_cast<const float4*>(mrow + col))
-                                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int b = 0; b < 4; ++b) {
+          const int col = n0 + cbeg + 32 * b;
+          if (cbeg + 32 * b < cend && col < P.N) mbits[b] = __ldg(P.mask_bits + static_cast<long long>(row) * P.ldbits + (col >> 5));
+        }
+      }
+      int bi = 0;
+      for (int cc = cbeg; cc < cend; cc += 32, ++bi) {
+        const int ncols = min(32, cend - cc);
+        uint32_t v0[16], v1[16];
+        tmem_ld16(t_row + cc, v0);
+        if (ncols == 32) tmem_ld16(t_row + cc + 16, v1);
+        tmem_ld_wait();
+        float o[32];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          o[i] = __uint_as_float(v0[i]);
+          o[16 + i] = ncols == 32 ? __uint_as_float(v1[i]) : 0.f;
+        }
+        const int col0 = n0 + cc;
+        if (epi == MTRL_EPI_BIAS_RELU) {
+          unsigned bits = 0u;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 b;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                         : "r"(sbias + static_cast<uint32_t>(cc - cbeg + 4 * j) * 4u));
+            o[4 * j + 0] = tf32_rna(fmaxf(o[4 * j + 0] + b.x, 0.f));
+            o[4 * j + 1] = tf32_rna(fmaxf(o[4 * j + 1] + b.y, 0.f));
+            o[4 * j + 2] = tf32_rna(fmaxf(o[4 * j + 2] + b.z, 0.f));
+            o[4 * j + 3] = tf32_rna(fmaxf(o[4 * j + 3] + b.w, 0.f));
           }
-        };
+          if (P.bits_out) {
 #pragma unroll
-        for (int a = 0; a < kAhead; ++a) fetch(cbeg + 16 * a, pre[a]);
-        for (int cc = cbeg; cc < cend; cc += 16 * kAhead) {
+            for (int i = 0; i < 32; ++i) bits |= (o[i] > 0.f ? 1u : 0u) << i;
+            if (row_ok && col0 < P.N) P.bits_out[static_cast<long long>(row) * P.ldbits + (col0 >> 5)] = bits;
+          }
+        } else if (epi == MTRL_EPI_RELU_MASK) {
+          if (P.mask_bits) {
+            const unsigned mb = bi == 0 ? mbits[0] : (bi == 1 ? mbits[1] : (bi == 2 ? mbits[2] : mbits[3]));
 #pragma unroll
-          for (int a = 0; a < kAhead; ++a) {
-            const int c0 = cc + 16 * a;
-            if (c0 < cend) {
-              uint32_t v[16];
-              tmem_ld16(t_row + c0, v);
-              float4 h[4];
+            for (int i = 0; i < 32; ++i) o[i] = ((mb >> i) & 1u) ? tf32_rna(o[i]) : 0.f;
+          } else {
 #pragma unroll
-              for (int q = 0; q < 4; ++q) h[q] = pre[a][q];
-              fetch(c0 + 16 * kAhead, pre[a]);
-              tmem_ld_wait();
-              float r[16];
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const int col = n0 + c0 + 4 * q;
-                const bool ok = row_ok && col + 4 <= P.N;
-                float4 o;
-                o.x = (ok && h[q].x > 0.f) ? tf32_rna(__uint_as_float(v[4 * q + 0])) : 0.f;
-                o.y = (ok && h[q].y > 0.f) ? tf32_rna(__uint_as_float(v[4 * q + 1])) : 0.f;
-                o.z = (ok && h[q].z > 0.f) ? tf32_rna(__uint_as_float(v[4 * q + 2])) : 0.f;
-                o.w = (ok && h[q].w > 0.f) ? tf32_rna(__uint_as_float(v[4 * q + 3])) : 0.f;
-                if (ok) *reinterpret_cast<float4*>(drow + col) = o;
-                r[4 * q + 0] = o.x; r[4 * q + 1] = o.y; r[4 * q + 2] = o.z; r[4 * q + 3] = o.w;
-              }
-              if (P.colsum) {
-                // Column sums over this warp's 32 rows (bias gradient partials): butterfly that halves the
-                // values a lane holds each step, 16 shuffles for 16 columns; lane L ends with column L >> 1.
-#pragma unroll
-                for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
-                  const bool upper = (lane & off) != 0;
-#pragma unroll
-                  for (int i = 0; i < half; ++i) {
-                    const float send = upper ? r[i] : r[i + half];
-                    const float keep = upper ? r[i + half] : r[i];
-                    r[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                  }
-                }
-                r[0] += __shfl_xor_sync(0xffffffffu, r[0], 1);
-                const int col = n0 + c0 + (lane >> 1);
-                const int group = (c.m_tile * kCtas + static_cast<int>(rank)) * 4 + quarter;
-                if ((lane & 1) == 0 && col < P.N && group * 32 < P.M)
-                  P.colsum[static_cast<long long>(group) * P.N + col] = r[0];
-              }
+            for (int j = 0; j < 8; ++j) {
+              const int col = col0 + 4 * j;
+              float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (row_ok && 4 * j < ncols && col + 4 <= P.N) h = __ldg(reinterpret_cast<const float4*>(mrow + col));
+              o[4 * j + 0] = h.x > 0.f ? tf32_rna(o[4 * j + 0]) : 0.f;
+              o[4 * j + 1] = h.y > 0.f ? tf32_rna(o[4 * j + 1]) : 0.f;
+              o[4 * j + 2] = h.z > 0.f ? tf32_rna(o[4 * j + 2]) : 0.f;
+              o[4 * j + 3] = h.w > 0.f ? tf32_rna(o[4 * j + 3]) : 0.f;
             }
           }
+          if (P.colsum) {
+            // Column sums over this warp's 32 rows (bias-gradient partials): butterfly that halves the values a lane
+            // holds each step, 31 shuffles for 32 columns; lane L ends with column L.
+            float r[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = (row_ok && col0 + i < P.N) ? o[i] : 0.f;
+#pragma unroll
+            for (int half = 16, off = 16; half >= 1; half >>= 1, off >>= 1) {
+              const bool upper = (lane & off) != 0;
+#pragma unroll
+              for (int i = 0; i < half; ++i) {
+                const float send = upper ? r[i] : r[i + half];
+                const float keep = upper ? r[i + half] : r[i];
+                r[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+              }
+            }
+            const int group = row0 >> 5;
+            if (lane < ncols && col0 + lane < P.N && row0 < P.M)
+              P.colsum[static_cast<long long>(group) * P.N + col0 + lane] = r[0];
+          }
+        } else if (epi == MTRL_EPI_STORE_TF32) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = tf32_rna(o[i]);
         }
-      } else {
-        for (int cc = cbeg; cc < cend; cc += 16) {
-          uint32_t v[16];
-          tmem_ld16(t_row + cc, v);
-          tmem_ld_wait();
-          if (row_ok) epilogue_chunk(P, v, drow, mrow, n0 + cc);
+        if (P.tma_out) {
+          const uint32_t stg = stg0 + (nbox & 1u) * kEpiBoxBytes;
+          if (nbox >= 2) {
+            if (lane == 0) tma_store_wait_read<1>();   // the store issued two boxes ago has released this buffer
+            __syncwarp();
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t dst = stg + static_cast<uint32_t>(lane) * 128u + (static_cast<uint32_t>(j ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(o[4 * j]), "f"(o[4 * j + 1]), "f"(o[4 * j + 2]),
+                         "f"(o[4 * j + 3])
+                         : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (epi == MTRL_EPI_ATOMIC_ADD) tma_reduce_add_2d(mapD, stg, col0, row0);
+            else tma_store_2d(mapD, stg, col0, row0);
+            tma_store_commit();
+          }
+          ++nbox;
+        } else if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int col = col0 + 4 * j;
+            if (4 * j < ncols && col + 4 <= P.N) {
+              const float4 q = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+              if (epi == MTRL_EPI_ATOMIC_ADD) atomicAdd(reinterpret_cast<float4*>(drow + col), q);
+              else *reinterpret_cast<float4*>(drow + col) = q;
+            }
+          }
         }
       }
       tc_fence_before();
@@ -447,6 +482,7 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
         acc_phase ^= 1u;
       }
     }
+    if (lane == 0) tma_store_wait<0>();   // all bulk stores of this warp have landed before the CTA retires
     if (params.dbg && lane == 0 && warp == 2) {
       atomicAdd(reinterpret_cast<unsigned long long*>(params.dbg + 6), static_cast<unsigned long long>(t_wait));
       atomicAdd(reinterpret_cast<unsigned long long*>(params.dbg + 7), static_cast<unsigned long long>(t_work));
@@ -565,7 +601,7 @@ extern "C" int mtrl_gemm_plan_create(mtrl_gemm_plan_t** out, const mtrl_gemm_pro
     MTRL_REQUIRE(p.k_splits == 1 || p.epilogue == MTRL_EPI_ATOMIC_ADD,
                  "problem %d: split-K needs the atomic-add epilogue", i);
     MTRL_REQUIRE(p.epilogue != MTRL_EPI_BIAS_RELU || p.bias, "problem %d: bias epilogue without bias", i);
-    MTRL_REQUIRE(p.epilogue != MTRL_EPI_RELU_MASK || p.mask, "problem %d: mask epilogue without mask", i);
+    MTRL_REQUIRE(p.epilogue != MTRL_EPI_RELU_MASK || p.mask || p.mask_bits, "problem %d: mask epilogue without mask", i);
     MTRL_REQUIRE((reinterpret_cast<uintptr_t>(p.D) & 15u) == 0 && p.ldd % 4 == 0,
                  "problem %d: D must be 16-byte aligned with ldd %% 4 == 0", i);
     // A CTA of a pair stages block_n / 2 columns of B; MN-major B arrives in 32-column TMA boxes, so the
@@ -579,6 +615,9 @@ extern "C" int mtrl_gemm_plan_create(mtrl_gemm_plan_t** out, const mtrl_gemm_pro
     d.bias = p.bias;
     d.mask = p.mask;
     d.colsum = p.epilogue == MTRL_EPI_RELU_MASK ? p.colsum_partial : nullptr;
+    d.mask_bits = p.epilogue == MTRL_EPI_RELU_MASK ? p.mask_bits : nullptr;
+    d.bits_out = p.epilogue == MTRL_EPI_BIAS_RELU ? p.relu_bits_out : nullptr;
+    d.ldbits = p.ldbits;
     d.ldd = p.ldd;
     d.ldmask = p.ldmask;
     d.M = p.M;
@@ -604,23 +643,31 @@ extern "C" int mtrl_gemm_plan_create(mtrl_gemm_plan_t** out, const mtrl_gemm_pro
               (static_cast<uint32_t>(d.b_major) << 16) | (static_cast<uint32_t>(block_n >> 3) << 17) |
               (static_cast<uint32_t>(tile_m >> 4) << 24);
     // A: K-major -> [M][K] rows of K; MN-major -> [K][M] rows of M.  Each CTA loads its own 128 rows.
+    MTRL_REQUIRE(!(d.mask_bits || d.bits_out) || (block_n % 32 == 0 && p.ldbits * 32 >= p.N),
+                 "problem %d: ReLU bit masks need block_n %% 32 == 0 and ldbits >= N / 32", i);
+    // output through TMA: 32 x 32 fp32 boxes of D [M][N] (rows of ldd floats), SWIZZLE_128B staging
+    const bool allow_tma_out = !(getenv("MTRL_GEMM_NO_TMA_OUT") && getenv("MTRL_GEMM_NO_TMA_OUT")[0] == '1');
+    d.tma_out = 0;
+    if (allow_tma_out && block_n % 32 == 0 &&
+        encode_map(&P.maps[3 * i + 2], p.D, p.N, p.M, p.ldd, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B) == MTRL_OK)
+      d.tma_out = 1;
     const bool allow3d = !(getenv("MTRL_GEMM_NO_3D") && getenv("MTRL_GEMM_NO_3D")[0] == '1');
     d.mn3d = 0;
     if (!d.a_major) {
-      MTRL_PROPAGATE(encode_map(&P.maps[2 * i], p.A, p.K, p.M, p.lda, kBlockK, kBlockM, CU_TENSOR_MAP_SWIZZLE_128B));
-    } else if (allow3d && encode_map_mn3d(&P.maps[2 * i], p.A, p.M, p.K, p.lda, kBlockM / 32)) {
+      MTRL_PROPAGATE(encode_map(&P.maps[3 * i], p.A, p.K, p.M, p.lda, kBlockK, kBlockM, CU_TENSOR_MAP_SWIZZLE_128B));
+    } else if (allow3d && encode_map_mn3d(&P.maps[3 * i], p.A, p.M, p.K, p.lda, kBlockM / 32)) {
       d.mn3d |= 1;
     } else {
-      MTRL_PROPAGATE(encode_map(&P.maps[2 * i], p.A, p.M, p.K, p.lda, 32, kBlockK,
+      MTRL_PROPAGATE(encode_map(&P.maps[3 * i], p.A, p.M, p.K, p.lda, 32, kBlockK,
                                 CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
     }
     if (!d.b_major) {
-      MTRL_PROPAGATE(encode_map(&P.maps[2 * i + 1], p.B, p.K, p.N, p.ldb, kBlockK, n_cta,
+      MTRL_PROPAGATE(encode_map(&P.maps[3 * i + 1], p.B, p.K, p.N, p.ldb, kBlockK, n_cta,
                                 CU_TENSOR_MAP_SWIZZLE_128B));
-    } else if (allow3d && n_cta % 32 == 0 && encode_map_mn3d(&P.maps[2 * i + 1], p.B, p.N, p.K, p.ldb, n_cta / 32)) {
+    } else if (allow3d && n_cta % 32 == 0 && encode_map_mn3d(&P.maps[3 * i + 1], p.B, p.N, p.K, p.ldb, n_cta / 32)) {
       d.mn3d |= 2;
     } else {
-      MTRL_PROPAGATE(encode_map(&P.maps[2 * i + 1], p.B, p.N, p.K, p.ldb, 32, kBlockK,
+      MTRL_PROPAGATE(encode_map(&P.maps[3 * i + 1], p.B, p.N, p.K, p.ldb, 32, kBlockK,
                                 CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
     }
   }

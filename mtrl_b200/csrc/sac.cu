@@ -56,6 +56,7 @@ struct Workspace {
   float* dXin;
   float *rew, *done, *eps_c, *eps_a, *logp_next, *logp, *act, *logstd, *dq, *dout, *colsum_part, *alpha_val, *task_w;
   unsigned* inrange;
+  unsigned *bits_Ao[MTRL_MAX_DEPTH], *bits_C[kMaxE][MTRL_MAX_DEPTH];  // ReLU sign bits of Ao[l] / C[e][l], [M][W/32]
   int *row_slot, *slot_src, *tile_task, *seg_start, *status;
   double* acc;
 };
@@ -103,6 +104,11 @@ long long carve(const mtrl_sac_config_t& c, int Ka, int Kc, uint8_t* base, Works
   w.alpha_val = f(c.num_local_tasks);
   w.task_w = f(c.num_local_tasks);
   w.inrange = reinterpret_cast<unsigned*>(take(M * 4));
+  const long long bit_words = M * ((W + 31) / 32);
+  for (int l = 0; l + 1 < c.depth; ++l) {
+    w.bits_Ao[l] = reinterpret_cast<unsigned*>(take(bit_words * 4));
+    for (int e = 0; e < E; ++e) w.bits_C[e][l] = reinterpret_cast<unsigned*>(take(bit_words * 4));
+  }
   w.row_slot = reinterpret_cast<int*>(take(static_cast<long long>(c.max_batch) * 4));
   w.slot_src = reinterpret_cast<int*>(take(M * 4));
   w.tile_task = reinterpret_cast<int*>(take(M / kTileRows * 4));
@@ -137,8 +143,9 @@ int validate(const mtrl_sac_config_t& c) {
 }
 
 int block_n_for(int n) {
+  if (n <= 16) return 16;
   const int tiles = (n + 255) / 256;
-  const int bn = static_cast<int>(round_up((n + tiles - 1) / tiles, 16));
+  const int bn = static_cast<int>(round_up((n + tiles - 1) / tiles, 32));  // 32-column epilogue boxes / ReLU bit words
   return bn > 256 ? 256 : bn;
 }
 
@@ -172,7 +179,8 @@ float* tb(float* base, const mtrl_net_layout_t& L, int e, int l) { return base +
 float* hk(float* base, const mtrl_net_layout_t& L, int e) { return base + L.heads_base + e * L.member_head_stride + L.head_kernel_off; }
 float* hb(float* base, const mtrl_net_layout_t& L, int e) { return base + L.heads_base + e * L.member_head_stride + L.head_bias_off; }
 
-mtrl_gemm_problem_t fwd_problem(const float* X, int ldx, int K, const float* Wsh, const float* bias, float* out, int M, int W) {
+mtrl_gemm_problem_t fwd_problem(const float* X, int ldx, int K, const float* Wsh, const float* bias, float* out, int M, int W,
+                                unsigned* bits_out = nullptr) {
   mtrl_gemm_problem_t p;
   memset(&p, 0, sizeof(p));
   p.A = X; p.lda = ldx; p.a_major = 0;
@@ -180,10 +188,11 @@ mtrl_gemm_problem_t fwd_problem(const float* X, int ldx, int K, const float* Wsh
   p.D = out; p.ldd = W;
   p.M = M; p.N = W; p.K = K;
   p.block_n = block_n_for(W); p.k_splits = 1; p.epilogue = MTRL_EPI_BIAS_RELU; p.bias = bias;
+  p.relu_bits_out = bits_out; p.ldbits = (W + 31) / 32;
   return p;
 }
 // dZ_prev = (dZ W^T) * (H_prev > 0): A = dZ [M][W] K-major, B = W [in=N][W=K] K-major
-mtrl_gemm_problem_t dx_problem(const float* dZ, const float* Wsh, int n_in, const float* mask, float* out, int M, int W,
+mtrl_gemm_problem_t dx_problem(const float* dZ, const float* Wsh, int n_in, const unsigned* mask_bits, float* out, int M, int W,
                                float* colsum_partial) {
   mtrl_gemm_problem_t p;
   memset(&p, 0, sizeof(p));
@@ -191,7 +200,8 @@ mtrl_gemm_problem_t dx_problem(const float* dZ, const float* Wsh, int n_in, cons
   p.B = Wsh; p.ldb = W; p.b_major = 0;
   p.D = out; p.ldd = n_in;
   p.M = M; p.N = n_in; p.K = W;
-  p.block_n = block_n_for(n_in); p.k_splits = 1; p.epilogue = MTRL_EPI_RELU_MASK; p.mask = mask; p.ldmask = n_in;
+  p.block_n = block_n_for(n_in); p.k_splits = 1; p.epilogue = MTRL_EPI_RELU_MASK;
+  p.mask_bits = mask_bits; p.ldbits = (n_in + 31) / 32;
   p.colsum_partial = colsum_partial;
   return p;
 }
@@ -250,10 +260,10 @@ int build_plans(mtrl_sac* h) {
     p.push_back(fwd_problem(l == 0 ? w.Xa_next : w.An[l - 1], K, l == 0 ? LA.in_dim : W, tk(ash, LA, 0, l),
                             tb(h->buf.actor_params, LA, 0, l), w.An[l], M, W));
     p.push_back(fwd_problem(l == 0 ? w.Xa : w.Ao[l - 1], K, l == 0 ? LA.in_dim : W, tk(ash, LA, 0, l),
-                            tb(h->buf.actor_params, LA, 0, l), w.Ao[l], M, W));
+                            tb(h->buf.actor_params, LA, 0, l), w.Ao[l], M, W, l + 1 < D ? w.bits_Ao[l] : nullptr));
     for (int e = 0; e < E; ++e)
       p.push_back(fwd_problem(l == 0 ? w.Xc : w.C[e][l - 1], l == 0 ? Kc : W, l == 0 ? LC.in_dim : W, tk(csh, LC, e, l),
-                              tb(h->buf.critic_params, LC, e, l), w.C[e][l], M, W));
+                              tb(h->buf.critic_params, LC, e, l), w.C[e][l], M, W, l + 1 < D ? w.bits_C[e][l] : nullptr));
     MTRL_PROPAGATE(make_plan(h->fwd, p));
   }
   for (int l = 0; l < D; ++l) {
@@ -262,7 +272,7 @@ int build_plans(mtrl_sac* h) {
       p.push_back(fwd_problem(l == 0 ? w.Xc_next : w.Tg[e][l - 1], l == 0 ? Kc : W, l == 0 ? LC.in_dim : W,
                               tk(tsh, LC, e, l), tb(h->buf.critic_target, LC, e, l), w.Tg[e][l], M, W));
       q.push_back(fwd_problem(l == 0 ? w.Xc : w.C[e][l - 1], l == 0 ? Kc : W, l == 0 ? LC.in_dim : W, tk(csh, LC, e, l),
-                              tb(h->buf.critic_params, LC, e, l), w.C[e][l], M, W));
+                              tb(h->buf.critic_params, LC, e, l), w.C[e][l], M, W, l + 1 < D ? w.bits_C[e][l] : nullptr));
     }
     MTRL_PROPAGATE(make_plan(h->fwd_target, p));
     MTRL_PROPAGATE(make_plan(h->fwd_pi, q));
@@ -278,8 +288,8 @@ int build_plans(mtrl_sac* h) {
     }
     for (int e = 0; e < E; ++e) {
       if (l > 0) {
-        pc.push_back(dx_problem(w.G[e][src], tk(csh, LC, e, l), W, w.C[e][l - 1], w.G[e][dst], M, W, colsum_part(h, e)));
-        ppi.push_back(dx_problem(w.G[e][src], tk(csh, LC, e, l), W, w.C[e][l - 1], w.G[e][dst], M, W, nullptr));
+        pc.push_back(dx_problem(w.G[e][src], tk(csh, LC, e, l), W, w.bits_C[e][l - 1], w.G[e][dst], M, W, colsum_part(h, e)));
+        ppi.push_back(dx_problem(w.G[e][src], tk(csh, LC, e, l), W, w.bits_C[e][l - 1], w.G[e][dst], M, W, nullptr));
       } else {
         // actor step: only dL/da = first action_dim input columns of dZ_0 W_0^T (N = 16 rows of W_0)
         mtrl_gemm_problem_t p;
@@ -293,7 +303,7 @@ int build_plans(mtrl_sac* h) {
     }
     pa.push_back(dw_problem(l == 0 ? w.Xa : w.Ao[l - 1], l == 0 ? Ka : W, l == 0 ? LA.in_dim : W, w.G[0][src],
                             tk(h->buf.actor_grads, LA, 0, l), M, W, h->sms, 0));
-    if (l > 0) pa.push_back(dx_problem(w.G[0][src], tk(ash, LA, 0, l), W, w.Ao[l - 1], w.G[0][dst], M, W, colsum_part(h, 0)));
+    if (l > 0) pa.push_back(dx_problem(w.G[0][src], tk(ash, LA, 0, l), W, w.bits_Ao[l - 1], w.G[0][dst], M, W, colsum_part(h, 0)));
     MTRL_PROPAGATE(make_plan(h->bwd_critic, pc));
     MTRL_PROPAGATE(make_plan(h->bwd_pi, ppi));
     MTRL_PROPAGATE(make_plan(h->bwd_actor, pa));

@@ -44,3 +44,34 @@ def test_relu_mask_epilogue_emits_column_sum_partials(cuda):
     expect = D.double().reshape(M // 32, 32, N).sum(1)
     assert torch.isfinite(part).all()
     assert ((part.double() - expect).norm() / expect.norm()).item() < 1e-6
+
+
+def test_relu_bits_roundtrip(cuda):
+    """Forward epilogue emits the ReLU sign bits; the dX epilogue consuming those bits equals the float-mask version."""
+    import torch
+
+    import gemm_cases as G
+    from mtrl_b200 import _lib as L
+
+    M, N, K = 384, 448, 192
+    pf, H, ref_h, keep_f = G.make_problem(M, N, K, 0, 1, L.EPI_BIAS_RELU, 224, 1, seed=5)
+    bits = torch.zeros(M, (N + 31) // 32, dtype=torch.int32, device="cuda")
+    pf.relu_bits_out = bits.data_ptr()
+    pf.ldbits = bits.shape[1]
+    L.GemmPlan([pf]).run()
+    torch.cuda.synchronize()
+    expect = (H > 0)
+    got = ((bits.unsqueeze(-1) >> torch.arange(32, device="cuda", dtype=torch.int32)) & 1).reshape(M, -1)[:, :N].bool()
+    assert torch.equal(got, expect)
+    # dX with bits vs dX with the float activation as mask
+    pb, D1, _, keep1 = G.make_problem(M, N, 256, 0, 0, L.EPI_RELU_MASK, 224, 1, seed=6)
+    pb.mask = None
+    pb.mask_bits = bits.data_ptr()
+    pb.ldbits = bits.shape[1]
+    pm, D2, _, keep2 = G.make_problem(M, N, 256, 0, 0, L.EPI_RELU_MASK, 224, 1, seed=6)
+    pm.mask = H.data_ptr()
+    pm.ldmask = H.stride(0)
+    L.GemmPlan([pb]).run()
+    L.GemmPlan([pm]).run()
+    torch.cuda.synchronize()
+    assert torch.equal(D1, D2)
