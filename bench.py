@@ -182,7 +182,7 @@ def cpu_update_rate(T: int, W: int, per_task: int, budget_s: float, threads: int
 
 
 # ---------------------------------------------------------------------------------------------
-def run_reference_arm(args) -> None:
+def run_reference_arm(args, out) -> None:
     """--impl reference: the reference's own update cannot be imported here or on the GPU box (no jax/flax/
     optax/distrax, no network), so the arm times its CPU restatement (oracle/) with all host threads."""
     rank = int(os.environ.get("RANK", "0"))
@@ -203,10 +203,20 @@ def run_reference_arm(args) -> None:
         "cpu_baseline": r,
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
+
+
+def protect_stdout():
+    """Libraries (NCCL prints its version banner to stdout) must not pollute the ONE JSON line: everything written to
+    fd 1 from here on goes to stderr; the JSON line is written to the saved original stdout."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
 
 
 def main() -> None:
+    out = protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -220,7 +230,7 @@ def main() -> None:
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
-        run_reference_arm(args)
+        run_reference_arm(args, out)
         return
 
     import torch
@@ -269,10 +279,10 @@ def main() -> None:
     launches_per_step = agent.launches_per_update() + 2  # + index draw and gather kernels of the sampler
 
     # ---------------- timed region 1: inputs resident in HBM ----------------
-    # One step (sampler kernels + the ~60 kernels of the update) is captured once into a CUDA graph and replayed:
-    # every piece of per-step state (PCG64 state, Adam counts, Philox counter) lives in device memory.  Single GPU
-    # only: with more ranks the NCCL all-reduces are issued between the phases by torch.distributed.
-    use_graph = (not args.no_graph) and world == 1
+    # One step (sampler kernels + the ~60 kernels of the update, and with several ranks the two NCCL all-reduces) is
+    # captured once into a CUDA graph and replayed: every piece of per-step state (PCG64 state, Adam counts, Philox
+    # counter) lives in device memory.
+    use_graph = (not args.no_graph) and (world == 1 or os.environ.get("MTRL_GRAPH_MULTI", "1") == "1")
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
@@ -392,9 +402,14 @@ def main() -> None:
             r.pop("_sec_per_update", None)
             r.pop("_n_timed", None)
             line["cpu_baseline"] = r
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=out, flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # A captured graph holds NCCL work; tearing the communicator down under it can block.  Drop the graph, meet
+        # at a barrier and leave without running NCCL's destructors.
+        graph = None
+        barrier()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
