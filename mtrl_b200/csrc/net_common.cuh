@@ -1,0 +1,146 @@
+// Host-side helpers shared by the update orchestrators (sac.cu, ppo.cu): flat parameter layout, GEMM problem
+// builders for the three trunk contractions, head-VJP launcher.
+#pragma once
+
+#include <vector>
+
+#include "common.cuh"
+#include "mtrl_b200.h"
+#include "sac_kernels.cuh"
+
+namespace netc {
+
+using namespace sac;
+
+inline long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
+
+
+inline void fill_net_layout(mtrl_net_layout_t* L, int in_dim, int head_dim, int members, int t_local, int width, int depth) {
+  memset(L, 0, sizeof(*L));
+  L->in_dim = in_dim;
+  L->head_dim = head_dim;
+  L->members = members;
+  L->num_local_tasks = t_local;
+  L->width = width;
+  L->depth = depth;
+  long long off = 0;
+  int d = in_dim;
+  for (int i = 0; i < depth; ++i) {
+    L->kernel_off[i] = off;
+    off = round_up(off + static_cast<long long>(d) * width, 32);
+    L->bias_off[i] = off;
+    off = round_up(off + width, 32);
+    d = width;
+  }
+  L->member_trunk_stride = off;
+  L->trunk_total = off * members;
+  L->slots_off = L->trunk_total;
+  L->heads_base = L->trunk_total + 32;
+  long long h = 0;
+  L->head_kernel_off = h;
+  h = round_up(h + static_cast<long long>(t_local) * width * head_dim, 32);
+  L->head_bias_off = h;
+  h = round_up(h + static_cast<long long>(t_local) * head_dim, 32);
+  L->member_head_stride = h;
+  L->total = L->heads_base + h * members;
+}
+
+inline int block_n_for(int n) {
+  if (n <= 16) return 16;
+  const int tiles = (n + 255) / 256;
+  const int bn = static_cast<int>(round_up((n + tiles - 1) / tiles, 32));  // 32-column epilogue boxes / ReLU bit words
+  return bn > 256 ? 256 : bn;
+}
+
+
+inline float* tk(float* base, const mtrl_net_layout_t& L, int e, int l) { return base + e * L.member_trunk_stride + L.kernel_off[l]; }
+inline float* tb(float* base, const mtrl_net_layout_t& L, int e, int l) { return base + e * L.member_trunk_stride + L.bias_off[l]; }
+inline float* hk(float* base, const mtrl_net_layout_t& L, int e) { return base + L.heads_base + e * L.member_head_stride + L.head_kernel_off; }
+inline float* hb(float* base, const mtrl_net_layout_t& L, int e) { return base + L.heads_base + e * L.member_head_stride + L.head_bias_off; }
+
+inline mtrl_gemm_problem_t fwd_problem(const float* X, int ldx, int K, const float* Wsh, const float* bias, float* out, int M, int W,
+                                unsigned* bits_out = nullptr) {
+  mtrl_gemm_problem_t p;
+  memset(&p, 0, sizeof(p));
+  p.A = X; p.lda = ldx; p.a_major = 0;
+  p.B = Wsh; p.ldb = W; p.b_major = 1;     // Flax kernel (in, out): N contiguous
+  p.D = out; p.ldd = W;
+  p.M = M; p.N = W; p.K = K;
+  p.block_n = block_n_for(W); p.k_splits = 1; p.epilogue = MTRL_EPI_BIAS_RELU; p.bias = bias;
+  p.relu_bits_out = bits_out; p.ldbits = (W + 31) / 32;
+  return p;
+}
+// dZ_prev = (dZ W^T) * (H_prev > 0): A = dZ [M][W] K-major, B = W [in=N][W=K] K-major
+inline mtrl_gemm_problem_t dx_problem(const float* dZ, const float* Wsh, int n_in, const unsigned* mask_bits, float* out, int M, int W,
+                               float* colsum_partial) {
+  mtrl_gemm_problem_t p;
+  memset(&p, 0, sizeof(p));
+  p.A = dZ; p.lda = W; p.a_major = 0;
+  p.B = Wsh; p.ldb = W; p.b_major = 0;
+  p.D = out; p.ldd = n_in;
+  p.M = M; p.N = n_in; p.K = W;
+  p.block_n = block_n_for(n_in); p.k_splits = 1; p.epilogue = MTRL_EPI_RELU_MASK;
+  p.mask_bits = mask_bits; p.ldbits = (n_in + 31) / 32;
+  p.colsum_partial = colsum_partial;
+  return p;
+}
+// dW = X^T dZ: A = X [rows][in] MN-major, B = dZ [rows][W] MN-major, K = rows
+inline mtrl_gemm_problem_t dw_problem(const float* X, int ldx, int n_in, const float* dZ, float* dW, int M, int W, int sms,
+                               int units_hint) {
+  mtrl_gemm_problem_t p;
+  memset(&p, 0, sizeof(p));
+  p.A = X; p.lda = ldx; p.a_major = 1;
+  p.B = dZ; p.ldb = W; p.b_major = 1;
+  p.D = dW; p.ldd = W;
+  p.M = n_in; p.N = W; p.K = M;
+  p.block_n = block_n_for(W);
+  const int kb = (M + 31) / 32;
+  const int tiles = ((n_in + 127) / 128) * ((W + p.block_n - 1) / p.block_n);
+  int splits;
+  if (n_in >= 128) {
+    // match the K depth of the dX units that share the launch (W/32 k-blocks) so units are uniform
+    splits = (kb + (W / 32) - 1) / (W / 32 > 0 ? W / 32 : 1);
+  } else {
+    splits = sms / (tiles > 0 ? tiles : 1);
+  }
+  const int max_splits = kb / 4 > 0 ? kb / 4 : 1;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  (void)units_hint;
+  p.k_splits = splits;
+  p.epilogue = splits > 1 ? MTRL_EPI_ATOMIC_ADD : MTRL_EPI_STORE;
+  return p;
+}
+
+inline int make_plan(std::vector<mtrl_gemm_plan_t*>& dst, const std::vector<mtrl_gemm_problem_t>& probs) {
+  mtrl_gemm_plan_t* plan = nullptr;
+  MTRL_PROPAGATE(mtrl_gemm_plan_create(&plan, probs.data(), static_cast<int>(probs.size())));
+  dst.push_back(plan);
+  return MTRL_OK;
+}
+
+template <int HD>
+inline void launch_head_bwd_t(const HeadBwdArgs& a, int T_local, int E, cudaStream_t st) {
+  dim3 grid((a.W + 127) / 128, T_local, E);
+  head_bwd_kernel<HD><<<grid, 128, 0, st>>>(a);
+}
+
+
+// Head VJP launch for head_dim hd (critic 1, actor 2A); returns false for an unsupported head_dim.
+inline bool launch_head_bwd_any(const HeadBwdArgs& a, int hd, int T_local, int E, cudaStream_t st) {
+  switch (hd) {
+    case 1: launch_head_bwd_t<1>(a, T_local, E, st); break;
+    case 2: launch_head_bwd_t<2>(a, T_local, E, st); break;
+    case 4: launch_head_bwd_t<4>(a, T_local, E, st); break;
+    case 6: launch_head_bwd_t<6>(a, T_local, E, st); break;
+    case 8: launch_head_bwd_t<8>(a, T_local, E, st); break;
+    case 10: launch_head_bwd_t<10>(a, T_local, E, st); break;
+    case 12: launch_head_bwd_t<12>(a, T_local, E, st); break;
+    case 14: launch_head_bwd_t<14>(a, T_local, E, st); break;
+    case 16: launch_head_bwd_t<16>(a, T_local, E, st); break;
+    default: return false;
+  }
+  return true;
+}
+
+}  // namespace netc

@@ -10,43 +10,13 @@
 
 #include "common.cuh"
 #include "mtrl_b200.h"
+#include "net_common.cuh"
 #include "sac_kernels.cuh"
 
 using namespace sac;
+using namespace netc;
 
 namespace {
-
-inline long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
-
-void fill_net_layout(mtrl_net_layout_t* L, int in_dim, int head_dim, int members, int t_local, int width, int depth) {
-  memset(L, 0, sizeof(*L));
-  L->in_dim = in_dim;
-  L->head_dim = head_dim;
-  L->members = members;
-  L->num_local_tasks = t_local;
-  L->width = width;
-  L->depth = depth;
-  long long off = 0;
-  int d = in_dim;
-  for (int i = 0; i < depth; ++i) {
-    L->kernel_off[i] = off;
-    off = round_up(off + static_cast<long long>(d) * width, 32);
-    L->bias_off[i] = off;
-    off = round_up(off + width, 32);
-    d = width;
-  }
-  L->member_trunk_stride = off;
-  L->trunk_total = off * members;
-  L->slots_off = L->trunk_total;
-  L->heads_base = L->trunk_total + 32;
-  long long h = 0;
-  L->head_kernel_off = h;
-  h = round_up(h + static_cast<long long>(t_local) * width * head_dim, 32);
-  L->head_bias_off = h;
-  h = round_up(h + static_cast<long long>(t_local) * head_dim, 32);
-  L->member_head_stride = h;
-  L->total = L->heads_base + h * members;
-}
 
 struct Workspace {
   float *Xa_next, *Xa, *Xc_next, *Xc;
@@ -142,13 +112,6 @@ int validate(const mtrl_sac_config_t& c) {
   return MTRL_OK;
 }
 
-int block_n_for(int n) {
-  if (n <= 16) return 16;
-  const int tiles = (n + 255) / 256;
-  const int bn = static_cast<int>(round_up((n + tiles - 1) / tiles, 32));  // 32-column epilogue boxes / ReLU bit words
-  return bn > 256 ? 256 : bn;
-}
-
 }  // namespace
 
 struct mtrl_sac {
@@ -174,74 +137,8 @@ struct mtrl_sac {
 
 namespace {
 
-float* tk(float* base, const mtrl_net_layout_t& L, int e, int l) { return base + e * L.member_trunk_stride + L.kernel_off[l]; }
-float* tb(float* base, const mtrl_net_layout_t& L, int e, int l) { return base + e * L.member_trunk_stride + L.bias_off[l]; }
-float* hk(float* base, const mtrl_net_layout_t& L, int e) { return base + L.heads_base + e * L.member_head_stride + L.head_kernel_off; }
-float* hb(float* base, const mtrl_net_layout_t& L, int e) { return base + L.heads_base + e * L.member_head_stride + L.head_bias_off; }
-
-mtrl_gemm_problem_t fwd_problem(const float* X, int ldx, int K, const float* Wsh, const float* bias, float* out, int M, int W,
-                                unsigned* bits_out = nullptr) {
-  mtrl_gemm_problem_t p;
-  memset(&p, 0, sizeof(p));
-  p.A = X; p.lda = ldx; p.a_major = 0;
-  p.B = Wsh; p.ldb = W; p.b_major = 1;     // Flax kernel (in, out): N contiguous
-  p.D = out; p.ldd = W;
-  p.M = M; p.N = W; p.K = K;
-  p.block_n = block_n_for(W); p.k_splits = 1; p.epilogue = MTRL_EPI_BIAS_RELU; p.bias = bias;
-  p.relu_bits_out = bits_out; p.ldbits = (W + 31) / 32;
-  return p;
-}
-// dZ_prev = (dZ W^T) * (H_prev > 0): A = dZ [M][W] K-major, B = W [in=N][W=K] K-major
-mtrl_gemm_problem_t dx_problem(const float* dZ, const float* Wsh, int n_in, const unsigned* mask_bits, float* out, int M, int W,
-                               float* colsum_partial) {
-  mtrl_gemm_problem_t p;
-  memset(&p, 0, sizeof(p));
-  p.A = dZ; p.lda = W; p.a_major = 0;
-  p.B = Wsh; p.ldb = W; p.b_major = 0;
-  p.D = out; p.ldd = n_in;
-  p.M = M; p.N = n_in; p.K = W;
-  p.block_n = block_n_for(n_in); p.k_splits = 1; p.epilogue = MTRL_EPI_RELU_MASK;
-  p.mask_bits = mask_bits; p.ldbits = (n_in + 31) / 32;
-  p.colsum_partial = colsum_partial;
-  return p;
-}
-// dW = X^T dZ: A = X [rows][in] MN-major, B = dZ [rows][W] MN-major, K = rows
-mtrl_gemm_problem_t dw_problem(const float* X, int ldx, int n_in, const float* dZ, float* dW, int M, int W, int sms,
-                               int units_hint) {
-  mtrl_gemm_problem_t p;
-  memset(&p, 0, sizeof(p));
-  p.A = X; p.lda = ldx; p.a_major = 1;
-  p.B = dZ; p.ldb = W; p.b_major = 1;
-  p.D = dW; p.ldd = W;
-  p.M = n_in; p.N = W; p.K = M;
-  p.block_n = block_n_for(W);
-  const int kb = (M + 31) / 32;
-  const int tiles = ((n_in + 127) / 128) * ((W + p.block_n - 1) / p.block_n);
-  int splits;
-  if (n_in >= 128) {
-    // match the K depth of the dX units that share the launch (W/32 k-blocks) so units are uniform
-    splits = (kb + (W / 32) - 1) / (W / 32 > 0 ? W / 32 : 1);
-  } else {
-    splits = sms / (tiles > 0 ? tiles : 1);
-  }
-  const int max_splits = kb / 4 > 0 ? kb / 4 : 1;
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
-  (void)units_hint;
-  p.k_splits = splits;
-  p.epilogue = splits > 1 ? MTRL_EPI_ATOMIC_ADD : MTRL_EPI_STORE;
-  return p;
-}
-
 float* colsum_part(const mtrl_sac* h, int e) {
   return h->ws.colsum_part + static_cast<long long>(e) * (h->cfg.max_rows / 32) * h->cfg.width;
-}
-
-int make_plan(std::vector<mtrl_gemm_plan_t*>& dst, const std::vector<mtrl_gemm_problem_t>& probs) {
-  mtrl_gemm_plan_t* plan = nullptr;
-  MTRL_PROPAGATE(mtrl_gemm_plan_create(&plan, probs.data(), static_cast<int>(probs.size())));
-  dst.push_back(plan);
-  return MTRL_OK;
 }
 
 int build_plans(mtrl_sac* h) {
@@ -381,25 +278,10 @@ int launch_actor_head(mtrl_sac* h, const float* H, const float* eps, float* Xdst
   return MTRL_OK;
 }
 
-template <int HD>
-void launch_head_bwd_t(const HeadBwdArgs& a, int T_local, int E, cudaStream_t st) {
-  dim3 grid((a.W + 127) / 128, T_local, E);
-  head_bwd_kernel<HD><<<grid, 128, 0, st>>>(a);
-}
-
 int launch_head_bwd(mtrl_sac* h, const HeadBwdArgs& a, int hd, int E, cudaStream_t st) {
-  const int T = h->cfg.num_local_tasks;
-  switch (hd) {
-    case 1: launch_head_bwd_t<1>(a, T, E, st); break;
-    case 2: launch_head_bwd_t<2>(a, T, E, st); break;
-    case 4: launch_head_bwd_t<4>(a, T, E, st); break;
-    case 6: launch_head_bwd_t<6>(a, T, E, st); break;
-    case 8: launch_head_bwd_t<8>(a, T, E, st); break;
-    case 10: launch_head_bwd_t<10>(a, T, E, st); break;
-    case 12: launch_head_bwd_t<12>(a, T, E, st); break;
-    case 14: launch_head_bwd_t<14>(a, T, E, st); break;
-    case 16: launch_head_bwd_t<16>(a, T, E, st); break;
-    default: mtrl_set_error("head_bwd: unsupported head_dim %d", hd); return MTRL_ERR_UNSUPPORTED;
+  if (!launch_head_bwd_any(a, hd, h->cfg.num_local_tasks, E, st)) {
+    mtrl_set_error("head_bwd: unsupported head_dim %d", hd);
+    return MTRL_ERR_UNSUPPORTED;
   }
   MTRL_CUDA_CHECK(cudaGetLastError());
   LAUNCHED(h);
