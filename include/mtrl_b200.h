@@ -229,6 +229,58 @@ int mtrl_sac_profile_read(mtrl_sac_t* h, double* total_ms, int* launches);
  * [0] == 0 ok, 1: a row's task is outside this handle's task range, 2: rows do not fit max_rows. */
 int mtrl_sac_read_status_async(const mtrl_sac_t* h, int* host_pinned4, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * MT-PPO update.  Replaces MTPPO.update / _update_inner (mtrl/rl/algorithms/mtppo.py:292-317):
+ * update_policy (:196-254) + update_value_function (:256-290), ContinuousActionPolicy with
+ * squash_tanh = False (mtrl/rl/networks.py:29-45) and ValueFunction (:188-205) on MultiHeadNetwork
+ * (num_tasks > 1) or a plain MLP (num_tasks = 1).  One full-batch step per network per call.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct mtrl_ppo_config {
+  int num_tasks;        /* heads; 1 = plain MLP (the observation then carries no one-hot)                    */
+  int obs_dim;          /* >= 16                                                                             */
+  int action_dim;       /* 1..8                                                                              */
+  int width, depth;
+  int steps_per_task;   /* rollout length per task; the batch is num_tasks * steps_per_task rows, task-major */
+  float clip_eps;       /* MTPPOConfig.clip_eps (0.2)                                                        */
+  int clip_vf_loss;
+  float entropy_coefficient, vf_coefficient;
+  int normalize_advantages;
+  float policy_lr, vf_lr;
+  float adam_b1, adam_b2, adam_eps;
+  float policy_max_grad_norm, vf_max_grad_norm;   /* <= 0: no clipping                                       */
+  float log_std_min, log_std_max;
+  unsigned long long noise_seed;
+} mtrl_ppo_config_t;
+
+typedef struct mtrl_ppo_layout {
+  mtrl_net_layout_t policy;
+  mtrl_net_layout_t vf;
+  long long workspace_bytes;
+  int k_in;      /* padded input pitch (floats)                     */
+  int max_rows;  /* packed rows = num_tasks * roundup(steps, 128)   */
+} mtrl_ppo_layout_t;
+
+typedef struct mtrl_ppo_buffers {
+  float *policy_params, *policy_grads, *policy_m, *policy_v, *policy_shadow;
+  float *vf_params, *vf_grads, *vf_m, *vf_v, *vf_shadow;
+  int* steps;     /* int[4]: policy, value-function Adam counts; unused; noise counter                       */
+  float* logs;    /* float[16]: entropy_loss, policy_loss, approx_kl, clip_fracs, value_function, values     */
+  void* workspace;
+} mtrl_ppo_buffers_t;
+
+typedef struct mtrl_ppo mtrl_ppo_t;
+
+int mtrl_ppo_query_layout(const mtrl_ppo_config_t* cfg, mtrl_ppo_layout_t* out);
+int mtrl_ppo_create(mtrl_ppo_t** out, const mtrl_ppo_config_t* cfg, const mtrl_ppo_buffers_t* buffers);
+void mtrl_ppo_destroy(mtrl_ppo_t* h);
+int mtrl_ppo_refresh_shadows(mtrl_ppo_t* h, void* stream);
+/* Rollout arrays: device fp32, flattened task-major (row = task * steps_per_task + step), the fields of
+ * mtrl/types.py:48-63: observations (B, obs_dim), log_probs, advantages, returns, values (B).  eps: (B, action_dim)
+ * standard normal draws for the fresh policy sample of mtppo.py:205-207, or NULL for in-kernel Philox. */
+int mtrl_ppo_update(mtrl_ppo_t* h, const float* obs, const float* log_probs, const float* advantages,
+                    const float* returns, const float* values, const float* eps, void* stream);
+int mtrl_ppo_launches_per_update(const mtrl_ppo_t* h);
+
 #ifdef __cplusplus
 }
 #endif

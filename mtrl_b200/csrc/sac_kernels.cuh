@@ -27,6 +27,8 @@ enum {
 // extra (non reference) log slots used to combine ranks: squared norms that are per-rank partial
 enum { LOG_X_CRITIC_P2_TRUNK = 10, LOG_X_CRITIC_P2_HEAD = 11, LOG_X_ACTOR_P2_TRUNK = 12, LOG_X_ACTOR_P2_HEAD = 13 };
 
+__device__ __forceinline__ float warp_sum_f(float v) { return warp_sum(v); }
+
 __device__ __forceinline__ float block_sum(float v, float* smem) {
   v = warp_sum(v);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -58,7 +60,7 @@ __device__ __forceinline__ double block_sum(double v, double* smem) {
 // GEMM M tile belongs to one task (own-task head only).
 // ---------------------------------------------------------------------------------------------
 // Task of every row = first arg-max of its trailing one-hot (jnp.argmax, multi_head.py:65).  One warp per row.
-__global__ void row_task_kernel(const float* __restrict__ obs, int B, int obs_dim, int T, int task_begin, int T_local,
+static __global__ void row_task_kernel(const float* __restrict__ obs, int B, int obs_dim, int T, int task_begin, int T_local,
                                 int* __restrict__ row_slot, int* __restrict__ status) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -82,7 +84,7 @@ __global__ void row_task_kernel(const float* __restrict__ obs, int B, int obs_di
   }
 }
 
-__global__ void pack_plan_kernel(int B, int T_local, int max_rows, int* __restrict__ row_slot,
+static __global__ void pack_plan_kernel(int B, int T_local, int max_rows, int* __restrict__ row_slot,
                                  int* __restrict__ slot_src, int* __restrict__ tile_task, int* __restrict__ seg_start,
                                  int* __restrict__ status) {
   extern __shared__ int sm[];
@@ -153,7 +155,7 @@ struct PackArgs {
 };
 
 // One block per packed row.  Inputs are rounded to tf32 here (they are GEMM A operands).
-__global__ void pack_rows_kernel(const PackArgs a) {
+static __global__ void pack_rows_kernel(const PackArgs a) {
   const int slot = blockIdx.x;
   const int src = a.slot_src[slot];
   const int A = a.act_dim, od = a.obs_dim;
@@ -210,7 +212,7 @@ __global__ void pack_rows_kernel(const PackArgs a) {
 
 // alpha_t = exp(log_alpha_t) (MultiTaskTemperature, mtsac.py:60-63); w_t = T * softmax(-log_alpha)_t
 // (extract_task_weights, mtsac.py:103-113) or 1.
-__global__ void alpha_prep_kernel(const float* __restrict__ log_alpha, int T_local, int use_w, float* __restrict__ alpha_val,
+static __global__ void alpha_prep_kernel(const float* __restrict__ log_alpha, int T_local, int use_w, float* __restrict__ alpha_val,
                                   float* __restrict__ task_w) {
   if (blockIdx.x != 0) return;
   __shared__ float red[32];
@@ -256,7 +258,7 @@ struct ActorHeadArgs {
 };
 
 template <int A>
-__global__ void actor_head_kernel(const ActorHeadArgs p) {
+static __global__ void actor_head_kernel(const ActorHeadArgs p) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= p.M) return;
@@ -316,7 +318,7 @@ __global__ void actor_head_kernel(const ActorHeadArgs p) {
 // Same computation, one block per 32 packed rows (all of one task): the task's (W, 2A) head matrix is staged in
 // shared memory once per block instead of being streamed from L2 for every row.
 template <int A>
-__global__ void actor_head_tile_kernel(const ActorHeadArgs p) {
+static __global__ void actor_head_tile_kernel(const ActorHeadArgs p) {
   extern __shared__ float sw[];  // [W][2A]
   const int row0 = blockIdx.x * 32;
   const int t = p.tile_task[row0 / kTileRows];
@@ -380,7 +382,7 @@ __global__ void actor_head_tile_kernel(const ActorHeadArgs p) {
 
 // Copy saved policy actions into the action columns of the critic input (single-task SAC samples them before the
 // critic step, whose backward still needs the buffer actions there).
-__global__ void write_actions_kernel(const float* __restrict__ act, float* __restrict__ X, int ldx, int M, int A) {
+static __global__ void write_actions_kernel(const float* __restrict__ act, float* __restrict__ X, int ldx, int M, int A) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < M * A) X[static_cast<long long>(i / A) * ldx + (i % A)] = tf32_rna(act[i]);
 }
@@ -423,7 +425,7 @@ struct CriticLossArgs {
 
 // y = r + (1-d) gamma (min_e Qbar_e - alpha logp')   (mtsac.py:547-553)
 // L = mean_{e,b} w (Q_e - y)^2                        (mtsac.py:562-565);  dq_e = dL/dQ_e
-__global__ void critic_loss_kernel(const CriticLossArgs p) {
+static __global__ void critic_loss_kernel(const CriticLossArgs p) {
   __shared__ double red[32];
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -488,7 +490,7 @@ struct ActorLossArgs {
 };
 
 // L = mean_b w (alpha logp - min_e Q_e(s, a))   (mtsac.py:659-666); min routes the gradient to the arg-min.
-__global__ void actor_loss_kernel(const ActorLossArgs p) {
+static __global__ void actor_loss_kernel(const ActorLossArgs p) {
   __shared__ double red[32];
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -540,7 +542,7 @@ struct ActorDoutArgs {
   float inv_b;
 };
 
-__global__ void actor_dout_kernel(const ActorDoutArgs p) {
+static __global__ void actor_dout_kernel(const ActorDoutArgs p) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= p.M) return;
   const int A = p.A;
@@ -581,7 +583,7 @@ struct HeadBwdArgs {
 };
 
 template <int HD>
-__global__ void head_bwd_kernel(const HeadBwdArgs p) {
+static __global__ void head_bwd_kernel(const HeadBwdArgs p) {
   __shared__ float sd[kTileRows * HD];
   const int e = blockIdx.z, t = blockIdx.y;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -643,7 +645,7 @@ struct ColsumJobs {
 };
 
 // block = 32 columns x 8 group slices; slices are combined in a fixed order through shared memory.
-__global__ void colsum_final_kernel(const ColsumJobs jobs, int groups, int W) {
+static __global__ void colsum_final_kernel(const ColsumJobs jobs, int groups, int W) {
   __shared__ float red[8][33];
   const int job = blockIdx.y;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -667,7 +669,7 @@ __global__ void colsum_final_kernel(const ColsumJobs jobs, int groups, int W) {
 // algorithms/utils.py:11-46) over the flat parameter buffer of a network, fused with the Polyak
 // target update (mtsac.py:607-613) and the tf32 operand copies the GEMMs read.
 // ---------------------------------------------------------------------------------------------
-__global__ void sumsq_kernel(const float* __restrict__ x, long long n, double* __restrict__ acc) {
+static __global__ void sumsq_kernel(const float* __restrict__ x, long long n, double* __restrict__ acc) {
   __shared__ double red[32];
   double s = 0.0;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -684,7 +686,7 @@ __global__ void sumsq_kernel(const float* __restrict__ x, long long n, double* _
 }
 
 // grads[slot] = local head-gradient squared norm, so one all-reduce of [trunk | slots] carries it.
-__global__ void write_slot_kernel(float* __restrict__ slot, const double* __restrict__ acc) { *slot = static_cast<float>(*acc); }
+static __global__ void write_slot_kernel(float* __restrict__ slot, const double* __restrict__ acc) { *slot = static_cast<float>(*acc); }
 
 struct AdamArgs {
   float *p, *m, *v, *shadow;
@@ -702,7 +704,7 @@ struct AdamArgs {
   float lr, b1, b2, eps, max_norm, tau;
 };
 
-__global__ void adam_kernel(const AdamArgs a) {
+static __global__ void adam_kernel(const AdamArgs a) {
   __shared__ double red[32];
   const double g2 = *a.g2_trunk + static_cast<double>(*a.g2_heads);
   const float gn = static_cast<float>(sqrt(g2));
@@ -760,13 +762,13 @@ __global__ void adam_kernel(const AdamArgs a) {
   }
 }
 
-__global__ void shadow_kernel(const float* __restrict__ p, float* __restrict__ s, long long n) {
+static __global__ void shadow_kernel(const float* __restrict__ p, float* __restrict__ s, long long n) {
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) s[i] = tf32_rna(p[i]);
 }
 
 // Single thread: turn accumulators into the reference's log scalars and advance the Adam count.
-__global__ void finalize_critic_kernel(const double* acc, const float* g2_heads, int* steps, float* logs, float inv_eb,
+static __global__ void finalize_critic_kernel(const double* acc, const float* g2_heads, int* steps, float* logs, float inv_eb,
                                        float loss_scale, int log_old_norm) {
   logs[MTRL_LOG_QF_VALUES] = static_cast<float>(acc[ACC_QSUM] * inv_eb);
   logs[MTRL_LOG_QF_LOSS] = static_cast<float>(acc[ACC_QLOSS] * loss_scale);
@@ -778,7 +780,7 @@ __global__ void finalize_critic_kernel(const double* acc, const float* g2_heads,
   logs[LOG_X_CRITIC_P2_HEAD] = static_cast<float>(acc[ACC_CRITIC_P2_HEAD]);
   steps[1] += 1;
 }
-__global__ void finalize_actor_kernel(const double* acc, const float* g2_heads, int* steps, float* logs, float inv_b,
+static __global__ void finalize_actor_kernel(const double* acc, const float* g2_heads, int* steps, float* logs, float inv_b,
                                       int log_old_norm) {
   logs[MTRL_LOG_ACTOR_LOSS] = static_cast<float>(acc[ACC_ACTOR_LOSS] * inv_b);
   logs[MTRL_LOG_ACTOR_GRAD_MAGNITUDE] = static_cast<float>(sqrt(acc[ACC_ACTOR_G2] + static_cast<double>(*g2_heads)));
@@ -804,7 +806,7 @@ struct AlphaArgs {
   float target_entropy, inv_b, lr, b1, b2, eps, max_norm;
 };
 
-__global__ void alpha_step_kernel(const AlphaArgs a) {
+static __global__ void alpha_step_kernel(const AlphaArgs a) {
   extern __shared__ float sg[];  // [T_local] gradients
   __shared__ float red[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;

@@ -13,6 +13,19 @@ class ReplayBufferSamples(NamedTuple):
     rewards: Any
 
 
+class Rollout(NamedTuple):  # types.py:48-63
+    observations: Any
+    actions: Any
+    rewards: Any
+    dones: Any
+    log_probs: Any = None
+    means: Any = None
+    stds: Any = None
+    values: Any = None
+    returns: Any = None
+    advantages: Any = None
+
+
 class ReplayBufferCheckpoint(TypedDict):  # types.py:72-74
     data: dict
     rng_state: Any
