@@ -259,7 +259,9 @@ def main() -> None:
     T_local = t1 - t0
     B_local = per_task * T_local
     mcfg, env = metaworld_mtmhsac(T, W)
-    agent = MTSAC.initialize(mcfg, env, seed=1, max_batch=B_local, rank=rank, world_size=world, process_group=pg)
+    exchange = os.environ.get("MTRL_EXCHANGE", "p2p")
+    agent = MTSAC.initialize(mcfg, env, seed=1, max_batch=B_local, rank=rank, world_size=world, process_group=pg,
+                             exchange=exchange)
     buf = MultiTaskReplayBuffer(args.capacity * T_local, T_local, _Space((39 + T,)), _Space((4,)), seed=1)
     synthetic_fill(buf, T_local, t0, T, seed=1234 + rank)
 
@@ -348,6 +350,9 @@ def main() -> None:
     h2d = sum(x.numel() * 4 for x in host_batches[0])
     d2h = 16 * 4
 
+    if world > 1 and agent.exchange_error() != 0:
+        print(f"rank {rank}: peer exchange timed out (code {agent.exchange_error()})", file=sys.stderr, flush=True)
+        os._exit(3)
     if world > 1:
         t = torch.tensor([ms, ms_e2e, gemm_ms, ms_stream], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -380,7 +385,9 @@ def main() -> None:
             "config": {"workload": args.workload, "num_tasks": T, "width": W, "depth": 3, "num_critics": 2,
                        "global_batch": B, "per_task_batch": per_task, "obs_dim": 39 + T, "action_dim": 4,
                        "ring_capacity_per_task": args.capacity,
-                       "parallelism": f"tasks sharded over {world} GPU(s), trunk gradients all-reduced (NCCL)" if world > 1 else "single GPU",
+                       "parallelism": (f"tasks sharded over {world} GPU(s); trunk gradients: " +
+                                       ("fused peer-memory reduce-scatter + sharded Adam + all-gather kernel (NVLink P2P, no NCCL)"
+                                        if exchange == "p2p" else "NCCL all-reduce between the phases")) if world > 1 else "single GPU",
                        "l2": "per-step working set (activations + parameters, ~%.1f GB) exceeds the 126 MB L2; no explicit flush"
                              % ((22 * B_local * W * 4 + 12 * 3 * W * W * 4) / 1e9),
                        "precision": "fp32 storage, tf32 tensor-core operands (round-to-nearest), fp32 accumulate",

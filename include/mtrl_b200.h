@@ -230,6 +230,33 @@ int mtrl_sac_profile_read(mtrl_sac_t* h, double* total_ms, int* launches);
 int mtrl_sac_read_status_async(const mtrl_sac_t* h, int* host_pinned4, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Multi-GPU exchange (nothing in the single-device reference corresponds to it).  Tasks are sharded over
+ * the GPUs of one box; the replicated trunk needs the sum of every rank's trunk gradients before
+ * optax.clip_by_global_norm + adam (mtrl/config/optim.py:26-43).  Instead of a library all-reduce, each rank owns a
+ * cudaMalloc "arena" that every other rank maps through CUDA IPC; ONE kernel per network then does
+ * reduce-scatter (peer loads over NVLink) -> clip -> Adam on the owned 1/N of the trunk -> all-gather (peer stores)
+ * -> Polyak / tf32 copies (csrc/comm.cuh).  Arena = [4096-byte header | caller-defined regions]; the four regions
+ * a handle exchanges (critic/actor gradients and parameters) must sit at the same offsets on every rank.
+ * ------------------------------------------------------------------------------------------ */
+#define MTRL_IPC_HANDLE_BYTES 64
+typedef struct mtrl_comm mtrl_comm_t;
+
+/* Allocates and zeroes the arena on the current device and writes its 64-byte IPC handle to handle_out. */
+int mtrl_comm_create(mtrl_comm_t** out, int rank, int world, long long arena_bytes, unsigned char* handle_out);
+/* Device pointer of the local arena. */
+void* mtrl_comm_arena(mtrl_comm_t* c);
+/* handles: world x 64 bytes, rank-major (the caller all-gathers what mtrl_comm_create returned). */
+int mtrl_comm_open_peers(mtrl_comm_t* c, const unsigned char* handles);
+/* Synchronous read of the arena's error word: 0 ok, otherwise the in-kernel wait that timed out (a peer never came). */
+int mtrl_comm_error(mtrl_comm_t* c, int* code);
+void mtrl_comm_destroy(mtrl_comm_t* c);
+/* Switches a multi-task handle to the fused peer-memory exchange.  The handle's critic_grads, actor_grads,
+ * critic_params and actor_params buffers must be arena + the given byte offsets (same offsets on every rank).
+ * Afterwards mtrl_sac_update runs the whole sharded update with no host-visible exchange points. */
+int mtrl_sac_attach_comm(mtrl_sac_t* h, mtrl_comm_t* c, long long off_critic_grads, long long off_actor_grads,
+                         long long off_critic_params, long long off_actor_params);
+
+/* ------------------------------------------------------------------------------------------
  * MT-PPO update.  Replaces MTPPO.update / _update_inner (mtrl/rl/algorithms/mtppo.py:292-317):
  * update_policy (:196-254) + update_value_function (:256-290), ContinuousActionPolicy with
  * squash_tanh = False (mtrl/rl/networks.py:29-45) and ValueFunction (:188-205) on MultiHeadNetwork

@@ -1,0 +1,298 @@
+// Trunk-gradient exchange between the task shards of one box WITHOUT a library collective:
+// every rank maps every peer's exchange arena (CUDA IPC over NVLink / NVSwitch) and ONE kernel per network does
+//
+//   reduce-scatter (peer loads)  ->  global-norm clip  ->  Adam on the owned 1/N of the trunk  ->
+//   all-gather (peer stores of the new parameters)      ->  local Polyak / tf32 operand copies
+//
+// i.e. optax.chain(clip_by_global_norm, adam) + apply_updates (mtrl/config/optim.py:26-43,
+// mtrl/rl/algorithms/utils.py:11-46) and incremental_update (mtrl/rl/algorithms/mtsac.py:607-613) with the Adam state
+// of the replicated trunk sharded over the ranks (each element is updated by exactly one rank, then broadcast, so the
+// replicas stay bit-identical).  Head parameters belong to one rank and are stepped locally in the same launch.
+#pragma once
+
+#include "common.cuh"
+#include "mtrl_b200.h"
+#include "sac_kernels.cuh"
+
+#define MTRL_COMM_MAX_RANKS 8
+#define MTRL_COMM_HEADER_BYTES 4096
+
+namespace comm {
+
+// First MTRL_COMM_HEADER_BYTES of every arena.  `flag`, `inbox_*` are written by peers; the rest is local.
+struct Header {
+  unsigned int flag[4][MTRL_COMM_MAX_RANKS];      // [barrier][source rank] = epoch stamp
+  double inbox_g2[MTRL_COMM_MAX_RANKS];           // squared norm of the reduced trunk shard rank q owns
+  float inbox_head_g2[MTRL_COMM_MAX_RANKS];       // squared norm of rank q's (local) head gradients
+  unsigned long long grid_count;                  // in-rank arrivals, monotonic
+  unsigned int epoch;                             // stamp of the next exchange (starts at 1)
+  int error;                                      // != 0: a wait timed out (peer missing)
+  double shard_g2[2];                             // this rank's shard accumulator, double-buffered by epoch parity
+};
+static_assert(sizeof(Header) <= MTRL_COMM_HEADER_BYTES, "comm header overflows its page");
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// Peer (or peer-written) data: always fetched from the owning GPU's L2, never from a local L1 line.
+__device__ __forceinline__ float4 ld_sys_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_sys_f64(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_sys_f32(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+constexpr unsigned long long kWaitTimeoutNs = 4000000000ull;  // 4 s: a missing peer must not hang the box
+
+struct TrunkStepArgs {
+  float *p, *m, *v, *shadow, *g, *target, *target_shadow;   // local buffers of this network (target may be null)
+  long long n, trunk_n;                                    // as AdamArgs
+  float* peer_g[MTRL_COMM_MAX_RANKS];                      // every rank's gradient buffer ([rank] == g)
+  float* peer_p[MTRL_COMM_MAX_RANKS];                      // every rank's parameter buffer ([rank] == p)
+  Header* peer_hdr[MTRL_COMM_MAX_RANKS];
+  int rank, world;
+  const int* step;
+  double* g2_trunk_out;                                    // global trunk gradient squared norm (log scalar input)
+  double *p2_trunk, *p2_head;
+  float lr, b1, b2, eps, max_norm, tau;
+};
+
+// All CTAs: wait until every rank has stamped barrier `b` of this rank's header with `epoch`.
+__device__ __forceinline__ void wait_ranks(Header* H, int b, int world, unsigned epoch) {
+  if (threadIdx.x < world) {
+    const unsigned long long t0 = globaltimer_ns();
+    while (static_cast<int>(ld_acquire_sys(&H->flag[b][threadIdx.x]) - epoch) < 0) {
+      if (globaltimer_ns() - t0 > kWaitTimeoutNs) {
+        atomicExch(&H->error, 1 + b);
+        break;
+      }
+      __nanosleep(100);
+    }
+  }
+  __syncthreads();
+}
+
+// Every CTA arrives; CTA 0 waits for the whole grid, then stamps barrier `b` in every rank's header.
+__device__ __forceinline__ void grid_arrive_then_signal(const TrunkStepArgs& a, Header* H, int b, unsigned epoch,
+                                                        unsigned long long target, bool with_norms) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    atomicAdd(&H->grid_count, 1ull);
+  }
+  if (blockIdx.x == 0) {
+    if (threadIdx.x == 0) {
+      const unsigned long long t0 = globaltimer_ns();
+      while (ld_acquire_gpu(&H->grid_count) < target) {
+        if (globaltimer_ns() - t0 > kWaitTimeoutNs) {
+          atomicExch(&H->error, 10 + b);
+          break;
+        }
+      }
+      __threadfence_system();
+    }
+    __syncthreads();
+    if (threadIdx.x < a.world) {
+      Header* R = a.peer_hdr[threadIdx.x];
+      if (with_norms) {
+        R->inbox_g2[a.rank] = ld_sys_f64(&H->shard_g2[epoch & 1]);
+        R->inbox_head_g2[a.rank] = a.g[a.trunk_n];   // slot 0: local head-gradient squared norm (write_slot_kernel)
+        __threadfence_system();
+      }
+      st_release_sys(&R->flag[b][a.rank], epoch);
+    }
+  }
+}
+
+template <int WORLD>
+__device__ __forceinline__ float4 reduce_ranks(const TrunkStepArgs& a, long long i4) {
+  float4 x[WORLD];
+#pragma unroll
+  for (int q = 0; q < WORLD; ++q) x[q] = ld_sys_f4(a.peer_g[q] + i4 * 4);
+  float4 s = x[0];
+#pragma unroll
+  for (int q = 1; q < WORLD; ++q) {
+    s.x += x[q].x; s.y += x[q].y; s.z += x[q].z; s.w += x[q].w;
+  }
+  return s;
+}
+template <>
+__device__ __forceinline__ float4 reduce_ranks<0>(const TrunkStepArgs& a, long long i4) {
+  float4 s = ld_sys_f4(a.peer_g[0] + i4 * 4);
+  for (int q = 1; q < a.world; ++q) {
+    const float4 x = ld_sys_f4(a.peer_g[q] + i4 * 4);
+    s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
+  }
+  return s;
+}
+
+__device__ __forceinline__ void adam4(const TrunkStepArgs& a, float scale, float bc1, float bc2, const float4& g4, float4& m4,
+                                      float4& v4, float4& p4) {
+  const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
+  float* mm = reinterpret_cast<float*>(&m4);
+  float* vv = reinterpret_cast<float*>(&v4);
+  float* pp = reinterpret_cast<float*>(&p4);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float g = gg[q] * scale;
+    mm[q] = a.b1 * mm[q] + (1.f - a.b1) * g;
+    vv[q] = a.b2 * vv[q] + (1.f - a.b2) * g * g;
+    pp[q] = pp[q] - a.lr * (mm[q] / bc1) / (sqrtf(vv[q] / bc2) + a.eps);
+  }
+}
+
+// shadow = tf32(p); target = tau p + (1 - tau) target; target_shadow = tf32(target); returns |p|^2
+__device__ __forceinline__ float derived4(const TrunkStepArgs& a, long long i4, const float4& p4) {
+  reinterpret_cast<float4*>(a.shadow)[i4] = make_float4(tf32_rna(p4.x), tf32_rna(p4.y), tf32_rna(p4.z), tf32_rna(p4.w));
+  if (a.target) {
+    float4 t4 = reinterpret_cast<const float4*>(a.target)[i4];
+    t4.x = a.tau * p4.x + (1.f - a.tau) * t4.x;
+    t4.y = a.tau * p4.y + (1.f - a.tau) * t4.y;
+    t4.z = a.tau * p4.z + (1.f - a.tau) * t4.z;
+    t4.w = a.tau * p4.w + (1.f - a.tau) * t4.w;
+    reinterpret_cast<float4*>(a.target)[i4] = t4;
+    reinterpret_cast<float4*>(a.target_shadow)[i4] = make_float4(tf32_rna(t4.x), tf32_rna(t4.y), tf32_rna(t4.z), tf32_rna(t4.w));
+  }
+  return p4.x * p4.x + p4.y * p4.y + p4.z * p4.z + p4.w * p4.w;
+}
+
+// Launch with one CTA per SM (all CTAs must be co-resident: they meet at in-kernel barriers).
+template <int WORLD>
+static __global__ void __launch_bounds__(512, 1) trunk_step_kernel(const TrunkStepArgs a) {
+  __shared__ double red[32];
+  __shared__ float s_scale;
+  Header* H = a.peer_hdr[a.rank];
+  const unsigned epoch = *reinterpret_cast<volatile unsigned*>(&H->epoch);
+  const unsigned long long grid_base = static_cast<unsigned long long>(epoch - 1) * 2ull * gridDim.x;
+  const int world = WORLD ? WORLD : a.world;
+  const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long trunk4 = a.trunk_n / 4;
+  long long per = (trunk4 + world - 1) / world;
+  per = (per + 31) / 32 * 32;
+  const long long s0 = min(per * a.rank, trunk4), s1 = min(s0 + per, trunk4);
+
+  // ---- barrier 0: every rank's gradients are complete (they are, by stream order, once its kernel runs) ----
+  if (blockIdx.x == 0 && threadIdx.x < world) st_release_sys(&a.peer_hdr[threadIdx.x]->flag[0][a.rank], epoch);
+  wait_ranks(H, 0, world, epoch);
+
+  // ---- reduce-scatter: this rank sums its shard over all ranks (fixed rank order), in place in its own buffer ----
+  {
+    double s = 0.0;
+    for (long long i = s0 + tid; i < s1; i += stride) {
+      const float4 g4 = reduce_ranks<WORLD>(a, i);
+      reinterpret_cast<float4*>(a.g)[i] = g4;
+      s += static_cast<double>(g4.x * g4.x + g4.y * g4.y) + static_cast<double>(g4.z * g4.z + g4.w * g4.w);
+    }
+    s = sac::block_sum(s, red);
+    if (threadIdx.x == 0) atomicAdd(&H->shard_g2[epoch & 1], s);
+  }
+  // ---- barrier 1: exchange the shard norms and the head norms ----
+  grid_arrive_then_signal(a, H, 1, epoch, grid_base + gridDim.x, true);
+  wait_ranks(H, 1, world, epoch);
+  if (threadIdx.x == 0) {
+    double g2 = 0.0, h2 = 0.0;
+    for (int q = 0; q < world; ++q) {
+      g2 += ld_sys_f64(&H->inbox_g2[q]);
+      h2 += static_cast<double>(ld_sys_f32(&H->inbox_head_g2[q]));
+    }
+    const float gn = static_cast<float>(sqrt(g2 + static_cast<double>(static_cast<float>(h2))));
+    // optax.clip_by_global_norm: g if norm < max else g / norm * max
+    s_scale = (a.max_norm > 0.f && !(gn < a.max_norm)) ? a.max_norm / gn : 1.f;
+    if (blockIdx.x == 0) {
+      *a.g2_trunk_out = g2;
+      a.g[a.trunk_n + 1] = static_cast<float>(h2);   // slot 1: head norm summed over ranks (read by the finalize kernel)
+    }
+  }
+  __syncthreads();
+  const float scale = s_scale;
+  const int t = *a.step + 1;
+  const float bc1 = static_cast<float>(1.0 - pow(static_cast<double>(a.b1), static_cast<double>(t)));
+  const float bc2 = static_cast<float>(1.0 - pow(static_cast<double>(a.b2), static_cast<double>(t)));
+
+  // ---- Adam on the owned trunk shard; all-gather by storing the new parameters into every rank ----
+  double p2_trunk = 0.0, p2_head = 0.0;
+  for (long long i = s0 + tid; i < s1; i += stride) {
+    const float4 g4 = reinterpret_cast<const float4*>(a.g)[i];
+    float4 m4 = reinterpret_cast<const float4*>(a.m)[i];
+    float4 v4 = reinterpret_cast<const float4*>(a.v)[i];
+    float4 p4 = reinterpret_cast<const float4*>(a.p)[i];
+    adam4(a, scale, bc1, bc2, g4, m4, v4, p4);
+    reinterpret_cast<float4*>(a.m)[i] = m4;
+    reinterpret_cast<float4*>(a.v)[i] = v4;
+#pragma unroll
+    for (int q = 0; q < (WORLD ? WORLD : MTRL_COMM_MAX_RANKS); ++q)
+      if (q < world) reinterpret_cast<float4*>(a.peer_p[q])[i] = p4;
+    p2_trunk += static_cast<double>(derived4(a, i, p4));
+  }
+  // ---- heads (local to this rank) ----
+  for (long long i = (a.trunk_n + 32) / 4 + tid; i < a.n / 4; i += stride) {
+    const float4 g4 = reinterpret_cast<const float4*>(a.g)[i];
+    float4 m4 = reinterpret_cast<const float4*>(a.m)[i];
+    float4 v4 = reinterpret_cast<const float4*>(a.v)[i];
+    float4 p4 = reinterpret_cast<const float4*>(a.p)[i];
+    adam4(a, scale, bc1, bc2, g4, m4, v4, p4);
+    reinterpret_cast<float4*>(a.m)[i] = m4;
+    reinterpret_cast<float4*>(a.v)[i] = v4;
+    reinterpret_cast<float4*>(a.p)[i] = p4;
+    p2_head += static_cast<double>(derived4(a, i, p4));
+  }
+  // ---- barrier 2: every rank has stored its shard everywhere ----
+  grid_arrive_then_signal(a, H, 2, epoch, grid_base + 2ull * gridDim.x, false);
+  wait_ranks(H, 2, world, epoch);
+
+  // ---- derived copies of the shards the peers own ----
+  for (long long i = tid; i < trunk4; i += stride) {
+    if (i >= s0 && i < s1) continue;
+    const float4 p4 = ld_sys_f4(a.p + i * 4);
+    p2_trunk += static_cast<double>(derived4(a, i, p4));
+  }
+  p2_trunk = sac::block_sum(p2_trunk, red);
+  p2_head = sac::block_sum(p2_head, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(a.p2_trunk, p2_trunk);
+    atomicAdd(a.p2_head, p2_head);
+    if (blockIdx.x == 0) {
+      H->shard_g2[(epoch + 1) & 1] = 0.0;   // next exchange's accumulator (nobody touches it during this one)
+      *reinterpret_cast<volatile unsigned*>(&H->epoch) = epoch + 1;
+    }
+  }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace comm
+
+struct mtrl_comm {
+  int rank = 0, world = 1;
+  long long arena_bytes = 0;
+  uint8_t* arena = nullptr;
+  uint8_t* peer[MTRL_COMM_MAX_RANKS] = {};
+  bool opened = false;
+};

@@ -8,6 +8,7 @@
 // own-task heads as CUDA-core row dots; critic input is (action, state) (mtrl/rl/networks.py:61).
 #include <vector>
 
+#include "comm.cuh"
 #include "common.cuh"
 #include "mtrl_b200.h"
 #include "net_common.cuh"
@@ -133,6 +134,9 @@ struct mtrl_sac {
   bool prof = false;
   std::vector<cudaEvent_t> ev;
   size_t ev_used = 0;
+  // fused peer-memory exchange (comm.cuh); null = single GPU, or the caller all-reduces between the phases
+  mtrl_comm* comm = nullptr;
+  long long off_critic_grads = 0, off_actor_grads = 0, off_critic_params = 0, off_actor_params = 0;
 };
 
 namespace {
@@ -329,6 +333,29 @@ int head_sumsq_to_slot(mtrl_sac* h, float* grads, const mtrl_net_layout_t& L, in
   return MTRL_OK;
 }
 
+
+// Sharded clip + Adam + Polyak fused with the trunk-gradient exchange over peer memory (comm.cuh).
+int launch_trunk_step(mtrl_sac* h, comm::TrunkStepArgs& a, long long off_grads, long long off_params, cudaStream_t st) {
+  mtrl_comm* c = h->comm;
+  a.rank = c->rank;
+  a.world = c->world;
+  for (int q = 0; q < c->world; ++q) {
+    a.peer_g[q] = reinterpret_cast<float*>(c->peer[q] + off_grads);
+    a.peer_p[q] = reinterpret_cast<float*>(c->peer[q] + off_params);
+    a.peer_hdr[q] = reinterpret_cast<comm::Header*>(c->peer[q]);
+  }
+  const dim3 grid(h->sms), block(512);
+  switch (c->world) {
+    case 2: comm::trunk_step_kernel<2><<<grid, block, 0, st>>>(a); break;
+    case 4: comm::trunk_step_kernel<4><<<grid, block, 0, st>>>(a); break;
+    case 8: comm::trunk_step_kernel<8><<<grid, block, 0, st>>>(a); break;
+    default: comm::trunk_step_kernel<0><<<grid, block, 0, st>>>(a); break;
+  }
+  MTRL_CUDA_CHECK(cudaGetLastError());
+  LAUNCHED(h);
+  return MTRL_OK;
+}
+
 }  // namespace
 
 extern "C" int mtrl_sac_query_layout(const mtrl_sac_config_t* cfg, mtrl_sac_layout_t* out) {
@@ -519,6 +546,24 @@ int step_critic_apply(mtrl_sac* h, cudaStream_t st) {
   Workspace& w = h->ws;
   const mtrl_net_layout_t& LC = h->lay.critic;
   const float EB = static_cast<float>(c.num_critics) * static_cast<float>(h->global_batch);
+  const float loss_scale = c.variant == MTRL_VARIANT_SAC ? 0.5f / static_cast<float>(h->global_batch) : 1.f / EB;
+  if (h->comm) {
+    comm::TrunkStepArgs t;
+    memset(&t, 0, sizeof(t));
+    t.p = h->buf.critic_params; t.m = h->buf.critic_m; t.v = h->buf.critic_v; t.shadow = h->buf.critic_shadow;
+    t.g = h->buf.critic_grads; t.target = h->buf.critic_target; t.target_shadow = h->buf.critic_target_shadow;
+    t.n = LC.total; t.trunk_n = LC.trunk_total;
+    t.step = h->buf.steps + 1;
+    t.g2_trunk_out = w.acc + ACC_CRITIC_G2; t.p2_trunk = w.acc + ACC_CRITIC_P2_TRUNK; t.p2_head = w.acc + ACC_CRITIC_P2_HEAD;
+    t.lr = c.critic_lr; t.b1 = c.adam_b1; t.b2 = c.adam_b2; t.eps = c.adam_eps; t.max_norm = c.critic_max_grad_norm;
+    t.tau = c.tau;
+    MTRL_PROPAGATE(launch_trunk_step(h, t, h->off_critic_grads, h->off_critic_params, st));
+    finalize_critic_kernel<<<1, 1, 0, st>>>(w.acc, h->buf.critic_grads + LC.slots_off + 1, h->buf.steps, h->buf.logs, 1.f / EB,
+                                            loss_scale, 0);
+    LAUNCHED(h);
+    MTRL_CUDA_CHECK(cudaGetLastError());
+    return MTRL_OK;
+  }
   sumsq_kernel<<<h->sms * 2, 256, 0, st>>>(h->buf.critic_grads, LC.trunk_total, w.acc + ACC_CRITIC_G2);
   LAUNCHED(h);
   AdamArgs a;
@@ -532,7 +577,6 @@ int step_critic_apply(mtrl_sac* h, cudaStream_t st) {
   a.tau = c.tau;
   adam_kernel<<<h->sms * 4, 256, 0, st>>>(a);
   LAUNCHED(h);
-  const float loss_scale = c.variant == MTRL_VARIANT_SAC ? 0.5f / static_cast<float>(h->global_batch) : 1.f / EB;
   finalize_critic_kernel<<<1, 1, 0, st>>>(w.acc, h->buf.critic_grads + LC.slots_off, h->buf.steps, h->buf.logs, 1.f / EB,
                                           loss_scale, c.variant == MTRL_VARIANT_SAC);
   LAUNCHED(h);
@@ -624,6 +668,22 @@ int step_actor_apply(mtrl_sac* h, cudaStream_t st) {
   const mtrl_sac_config_t& c = h->cfg;
   Workspace& w = h->ws;
   const mtrl_net_layout_t& LA = h->lay.actor;
+  if (h->comm) {
+    comm::TrunkStepArgs t;
+    memset(&t, 0, sizeof(t));
+    t.p = h->buf.actor_params; t.m = h->buf.actor_m; t.v = h->buf.actor_v; t.shadow = h->buf.actor_shadow;
+    t.g = h->buf.actor_grads;
+    t.n = LA.total; t.trunk_n = LA.trunk_total;
+    t.step = h->buf.steps + 0;
+    t.g2_trunk_out = w.acc + ACC_ACTOR_G2; t.p2_trunk = w.acc + ACC_ACTOR_P2_TRUNK; t.p2_head = w.acc + ACC_ACTOR_P2_HEAD;
+    t.lr = c.actor_lr; t.b1 = c.adam_b1; t.b2 = c.adam_b2; t.eps = c.adam_eps; t.max_norm = c.actor_max_grad_norm;
+    MTRL_PROPAGATE(launch_trunk_step(h, t, h->off_actor_grads, h->off_actor_params, st));
+    finalize_actor_kernel<<<1, 1, 0, st>>>(w.acc, h->buf.actor_grads + LA.slots_off + 1, h->buf.steps, h->buf.logs,
+                                           1.f / static_cast<float>(h->global_batch), 0);
+    LAUNCHED(h);
+    MTRL_CUDA_CHECK(cudaGetLastError());
+    return MTRL_OK;
+  }
   sumsq_kernel<<<h->sms * 2, 256, 0, st>>>(h->buf.actor_grads, LA.trunk_total, w.acc + ACC_ACTOR_G2);
   LAUNCHED(h);
   AdamArgs a;
@@ -705,6 +765,29 @@ extern "C" int mtrl_sac_update(mtrl_sac_t* h, const float* obs, const float* act
   MTRL_PROPAGATE(mtrl_sac_phase1_critic_grads(h, obs, actions, next_obs, dones, rewards, batch, global_batch, eps_c, eps_a, stream));
   MTRL_PROPAGATE(mtrl_sac_phase2_critic_step_actor_grads(h, stream));
   MTRL_PROPAGATE(mtrl_sac_phase3_actor_step_alpha(h, stream));
+  return MTRL_OK;
+}
+
+extern "C" int mtrl_sac_attach_comm(mtrl_sac_t* h, mtrl_comm_t* c, long long off_critic_grads, long long off_actor_grads,
+                                    long long off_critic_params, long long off_actor_params) {
+  MTRL_REQUIRE(h && c, "mtrl_sac_attach_comm: null argument");
+  MTRL_REQUIRE(h->cfg.variant == MTRL_VARIANT_MTSAC, "mtrl_sac_attach_comm: only the multi-task variant shards");
+  MTRL_REQUIRE(c->opened || c->world == 1, "mtrl_sac_attach_comm: call mtrl_comm_open_peers first");
+  const long long need_c = h->lay.critic.total * 4, need_a = h->lay.actor.total * 4;
+  const struct { const char* name; long long off; long long bytes; const float* ptr; } r[4] = {
+      {"critic_grads", off_critic_grads, need_c, h->buf.critic_grads}, {"actor_grads", off_actor_grads, need_a, h->buf.actor_grads},
+      {"critic_params", off_critic_params, need_c, h->buf.critic_params}, {"actor_params", off_actor_params, need_a, h->buf.actor_params}};
+  for (const auto& x : r) {
+    MTRL_REQUIRE(x.off >= MTRL_COMM_HEADER_BYTES && x.off % 128 == 0 && x.off + x.bytes <= c->arena_bytes,
+                 "mtrl_sac_attach_comm: %s region [%lld, +%lld) outside the arena or misaligned", x.name, x.off, x.bytes);
+    MTRL_REQUIRE(reinterpret_cast<const uint8_t*>(x.ptr) == c->arena + x.off,
+                 "mtrl_sac_attach_comm: the handle's %s buffer is not arena + %lld", x.name, x.off);
+  }
+  h->comm = c;
+  h->off_critic_grads = off_critic_grads;
+  h->off_actor_grads = off_actor_grads;
+  h->off_critic_params = off_critic_params;
+  h->off_actor_params = off_actor_params;
   return MTRL_OK;
 }
 

@@ -89,7 +89,35 @@ L._EXTRA_DECLS.update({
     "mtrl_sac_read_status_async": ([_vp, _vp, _vp],),
     "mtrl_sac_profile_gemms": ([_vp, _i],),
     "mtrl_sac_profile_read": ([_vp, C.POINTER(C.c_double), C.POINTER(_i)],),
+    "mtrl_comm_create": ([C.POINTER(_vp), _i, _i, C.c_longlong, _vp],),
+    "mtrl_comm_arena": ([_vp], _vp),
+    "mtrl_comm_open_peers": ([_vp, _vp],),
+    "mtrl_comm_error": ([_vp, C.POINTER(_i)],),
+    "mtrl_comm_destroy": ([_vp], None),
+    "mtrl_sac_attach_comm": ([_vp, _vp, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong],),
 })
+
+COMM_HEADER_BYTES = 4096
+IPC_HANDLE_BYTES = 64
+
+
+class _DeviceSpan:
+    """A raw device allocation (the exchange arena) exposed to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr: int, n_floats: int, owner):
+        self.__cuda_array_interface__ = {"shape": (int(n_floats),), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+        self._owner = owner
+
+
+def arena_plan(total_critic: int, total_actor: int) -> tuple[dict, int]:
+    """Byte offsets of the four exchanged regions inside every rank's arena (identical on all ranks: sized for the
+    rank with the most local tasks) and the arena size."""
+    off, plan = COMM_HEADER_BYTES, {}
+    for name, n in (("critic_grads", total_critic), ("actor_grads", total_actor), ("critic_params", total_critic),
+                    ("actor_params", total_actor)):
+        plan[name] = off
+        off = -(-(off + 4 * n) // 4096) * 4096
+    return plan, off
 
 
 @dataclasses.dataclass(frozen=True)
@@ -187,10 +215,14 @@ class MTSAC:
     @staticmethod
     def initialize(config: MTSACConfig, env_config, seed: int = 1, *, max_batch: int | None = None,
                    max_rows: int | None = None, rank: int = 0, world_size: int = 1, process_group=None,
-                   device: str | torch.device | None = None) -> "MTSAC":
+                   device: str | torch.device | None = None, exchange: str = "p2p") -> "MTSAC":
         """mtsac.py:152-284.  `env_config` needs `.observation_space.shape` and `.action_space.shape`
         (the observation includes the one-hot task id).  `max_batch` bounds the rows one update may
-        pass (default 128 per local task, the reference's batch).  rank/world_size shard the tasks."""
+        pass (default 128 per local task, the reference's batch).  rank/world_size shard the tasks;
+        `exchange` picks how the ranks sum trunk gradients: "p2p" = the fused peer-memory kernel
+        (csrc/comm.cuh, sharded Adam, no library collective), "nccl" = all-reduce between the phases."""
+        if exchange not in ("p2p", "nccl"):
+            raise ValueError(f"exchange must be 'p2p' or 'nccl', got {exchange!r}")
         if not torch.cuda.is_available():
             raise L.MtrlError("MTSAC needs a CUDA device; there is no CPU fallback")
         self = object.__new__(MTSAC)
@@ -199,6 +231,8 @@ class MTSAC:
         self.config = config
         self.num_tasks = config.num_tasks
         self.rank, self.world_size, self.process_group = rank, world_size, process_group
+        self.exchange = exchange if world_size > 1 else "none"
+        self._comm = None
         self.task_begin, self.task_end = task_partition(config.num_tasks, world_size)[rank]
         t_local = self.task_end - self.task_begin
         obs_dim = int(np.prod(env_config.observation_space.shape))
@@ -283,11 +317,45 @@ class MTSAC:
         self._flat = {f"actor_{k}": z(lay.actor.total) for k in ("params", "grads", "m", "v", "shadow")}
         self._flat.update({f"critic_{k}": z(lay.critic.total)
                            for k in ("params", "grads", "m", "v", "shadow", "target", "target_shadow")})
+        if self.exchange == "p2p":
+            self._flat.update(self._open_arena(dev))
         self._flat.update({"log_alpha": z(max(t_local, 4)), "alpha_m": z(max(t_local, 4)), "alpha_v": z(max(t_local, 4))})
         self._steps = z(4, torch.int32)
         self._logs = z(16)
         self._workspace = z((lay.workspace_bytes + 3) // 4 + 64)
         self._status_host = torch.zeros(4, dtype=torch.int32).pin_memory()
+
+    def _open_arena(self, dev) -> dict:
+        """Exchange arena for the fused peer-memory path: gradients and parameters of both networks live in one
+        cudaMalloc block per rank that every other rank maps through CUDA IPC (handles all-gathered over the
+        process group, which is the only use of torch.distributed on this path besides the log all-reduce)."""
+        import torch.distributed as dist
+
+        # every rank sizes the regions for the largest shard so the offsets agree
+        cfg_max = SacConfigC.from_buffer_copy(self._cfg)
+        cfg_max.num_local_tasks = -(-self.num_tasks // self.world_size)
+        cfg_max.task_begin = 0
+        cfg_max.max_batch = min(cfg_max.max_batch, cfg_max.max_rows)
+        lay_max = SacLayoutC()
+        L.check(L.lib().mtrl_sac_query_layout(C.byref(cfg_max), C.byref(lay_max)))
+        plan, nbytes = arena_plan(lay_max.critic.total, lay_max.actor.total)
+        comm, handle = _vp(), (C.c_ubyte * IPC_HANDLE_BYTES)()
+        L.check(L.lib().mtrl_comm_create(C.byref(comm), self.rank, self.world_size, nbytes, handle))
+        self._comm = comm
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
+        allh = [torch.empty_like(mine) for _ in range(self.world_size)]
+        dist.all_gather(allh, mine, group=self.process_group)
+        blob = bytes(torch.stack(allh).cpu().flatten().tolist())
+        L.check(L.lib().mtrl_comm_open_peers(comm, C.cast(C.c_char_p(blob), _vp)))
+        base = L.lib().mtrl_comm_arena(comm)
+        self._arena_plan = plan
+        lay = self._lay
+        out = {}
+        for name, n in (("critic_grads", lay.critic.total), ("actor_grads", lay.actor.total),
+                        ("critic_params", lay.critic.total), ("actor_params", lay.actor.total)):
+            out[name] = torch.as_tensor(_DeviceSpan(base + plan[name], n, self), device=dev)
+        dist.barrier(group=self.process_group)
+        return out
 
     def _create_handle(self) -> None:
         bufs = SacBuffersC(**{k: v.data_ptr() for k, v in self._flat.items()}, steps=self._steps.data_ptr(),
@@ -295,6 +363,10 @@ class MTSAC:
         h = _vp()
         L.check(L.lib().mtrl_sac_create(C.byref(h), C.byref(self._cfg), C.byref(bufs)))
         self._h = h
+        if self._comm is not None:
+            p = self._arena_plan
+            L.check(L.lib().mtrl_sac_attach_comm(h, self._comm, p["critic_grads"], p["actor_grads"], p["critic_params"],
+                                                 p["actor_params"]))
         self._status_event = torch.cuda.Event()
         self._pending_status = False
 
@@ -302,6 +374,15 @@ class MTSAC:
         if getattr(self, "_h", None) is not None and L._lib is not None:
             L._lib.mtrl_sac_destroy(self._h)
             self._h = None
+        # the arena itself is left to process exit: peers may still have it mapped
+
+    def exchange_error(self) -> int:
+        """0, or the code of the in-kernel wait that timed out waiting for a peer (synchronises)."""
+        if self._comm is None:
+            return 0
+        code = _i()
+        L.check(L.lib().mtrl_comm_error(self._comm, C.byref(code)))
+        return code.value
 
     # ------------------------------------------------------------------ reference surface
     def get_num_params(self) -> dict[str, int]:
@@ -354,14 +435,15 @@ class MTSAC:
         args = (self._h, _vp(obs.data_ptr()), _vp(act.data_ptr()), _vp(nxt.data_ptr()), _vp(done.data_ptr()),
                 _vp(rew.data_ptr()), B)
         p = lambda t: _vp(t.data_ptr() if t is not None else None)  # noqa: E731
-        if self.world_size == 1:
+        if self.world_size > 1 and global_batch is None:
+            raise ValueError("multi-GPU update needs global_batch (the B every loss mean divides by)")
+        if self.world_size == 1 or self.exchange == "p2p":
+            # one call: with several ranks the trunk-gradient exchange happens inside the fused kernels (comm.cuh)
             L.check(L.lib().mtrl_sac_update(*args, global_batch or B, p(ec), p(ea), stream))
         else:
             import torch.distributed as dist
 
             gb = global_batch
-            if gb is None:
-                raise ValueError("multi-GPU update needs global_batch (the B every loss mean divides by)")
             L.check(L.lib().mtrl_sac_phase1_critic_grads(*args, gb, p(ec), p(ea), stream))
             lc, la = self._lay.critic, self._lay.actor
             dist.all_reduce(self._flat["critic_grads"][: lc.trunk_total + 32], group=self.process_group)

@@ -25,8 +25,9 @@ def main():
     cfg = O.OracleConfig(num_tasks=T, obs_dim=39 + T, action_dim=4, width=W)
     st = O.init_state(cfg, seed=1, dtype=torch.float32)
     t0, t1 = task_partition(T, world)[rank]
+    exchange = os.environ.get("MG_EXCHANGE", "p2p")
     agent = SU.make_agent(cfg, per_task, seed=1, max_batch=per_task * (t1 - t0), rank=rank, world_size=world,
-                          process_group=dist.group.WORLD)
+                          process_group=dist.group.WORLD, exchange=exchange)
     SU.load_oracle_state(agent, st, task_slice=slice(t0, t1))
     st64 = st.to(torch.float64)
     steps = 2
@@ -54,9 +55,10 @@ def main():
     ref = trunk.clone()
     dist.broadcast(ref, src=0)
     assert torch.equal(trunk, ref), f"rank {rank}: critic trunk diverged from rank 0"
+    assert agent.exchange_error() == 0, f"rank {rank}: peer exchange timed out (code {agent.exchange_error()})"
     dist.barrier()
     if rank == 0:
-        print(f"multigpu_check ok: world={world} T={T} W={W}", flush=True)
+        print(f"multigpu_check ok: world={world} T={T} W={W} exchange={exchange}", flush=True)
     dist.destroy_process_group()
 
 
