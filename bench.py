@@ -242,6 +242,8 @@ def main() -> None:
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
+    # profiling aid: run rank 0's shard of an N-rank job alone on one GPU, without the exchange (not a bench line)
+    emulate = int(os.environ.get("MTRL_EMULATE_WORLD", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
@@ -255,12 +257,12 @@ def main() -> None:
 
     T, W, per_task = WORKLOADS[args.workload]
     B = per_task * T
-    t0, t1 = task_partition(T, world)[rank]
+    t0, t1 = task_partition(T, emulate or world)[rank]
     T_local = t1 - t0
     B_local = per_task * T_local
     mcfg, env = metaworld_mtmhsac(T, W)
-    exchange = os.environ.get("MTRL_EXCHANGE", "p2p")
-    agent = MTSAC.initialize(mcfg, env, seed=1, max_batch=B_local, rank=rank, world_size=world, process_group=pg,
+    exchange = "local" if emulate else os.environ.get("MTRL_EXCHANGE", "p2p")
+    agent = MTSAC.initialize(mcfg, env, seed=1, max_batch=B_local, rank=rank, world_size=emulate or world, process_group=pg,
                              exchange=exchange)
     buf = MultiTaskReplayBuffer(args.capacity * T_local, T_local, _Space((39 + T,)), _Space((4,)), seed=1)
     synthetic_fill(buf, T_local, t0, T, seed=1234 + rank)
@@ -367,7 +369,7 @@ def main() -> None:
         value = args.steps / (ms / 1e3)
         e2e_value = args.steps / (ms_e2e / 1e3)
         # dominant kernel: gemm_tf32_grouped_kernel (tensor bound).  Algorithmic trunk FLOPs of this rank's rows.
-        flops_rank = algorithmic_flops(T, W, B_local if world > 1 else B, trunk_only=True)
+        flops_rank = algorithmic_flops(T, W, B_local if (world > 1 or emulate) else B, trunk_only=True)
         n_l = max(gemm_launches, 1)
         achieved = flops_rank * args.steps / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
         tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
@@ -404,7 +406,10 @@ def main() -> None:
                          "algorithmic_flops_per_step": flops_rank},
             "clocks": clk,
         }
-        if not args.no_cpu_baseline and world == 1:
+        if emulate:
+            line["config"]["emulated_shard_of"] = emulate
+            line["config"]["note"] = "PROFILING AID: rank 0's shard alone, no exchange; not a benchmark result"
+        if not args.no_cpu_baseline and world == 1 and not emulate:
             r = cpu_update_rate(T, W, per_task, budget_s=float(os.environ.get("MTRL_CPU_BUDGET_S", "20")))
             r.pop("_sec_per_update", None)
             r.pop("_n_timed", None)

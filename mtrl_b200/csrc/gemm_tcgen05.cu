@@ -17,6 +17,9 @@
 
 #include <stdlib.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
 #include "mtrl_b200.h"
 
@@ -97,6 +100,9 @@ struct GemmParams {
   int nprob;
   int total_units;
   long long* dbg;  // optional: 8 cycle counters summed over CTAs (see mtrl_gemm_plan_set_debug)
+  // Static schedule built by the host (longest-processing-time-first over the workers): worker w runs units
+  // sched[nworkers + 1 + i] for i in [sched[w], sched[w + 1]).
+  const int* sched;
 };
 
 struct UnitCoord {
@@ -147,6 +153,8 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
   const uint32_t rank = kCtas == 2 ? cluster_ctarank() : 0u;   // 0 = leader of the pair
   const int worker = blockIdx.x / kCtas;                       // CTA (or pair) index
   const int nworkers = gridDim.x / kCtas;
+  const int* __restrict__ sched_units = params.sched + nworkers + 1;
+  const int sched_begin = params.sched[worker], sched_end = params.sched[worker + 1];
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -180,7 +188,8 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
       int stage = 0;
       uint32_t phase = 0;
       long long t_wait = 0, t_issue = 0;
-      for (int unit = worker; unit < total_units; unit += nworkers) {
+      for (int si = sched_begin; si < sched_end; ++si) {
+        const int unit = sched_units[si];
         const UnitCoord c = decode_unit(probs, nprob, unit);
         const DevProblem& P = probs[c.p];
         const CUtensorMap* mapA = maps + 3 * c.p;
@@ -246,7 +255,8 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
       int acc = 0;
       uint32_t acc_phase = 0;
       long long t_wfull = 0, t_wtempty = 0, t_issue = 0, t_total0 = params.dbg ? clock64() : 0;
-      for (int unit = worker; unit < total_units; unit += nworkers) {
+      for (int si = sched_begin; si < sched_end; ++si) {
+        const int unit = sched_units[si];
         const UnitCoord c = decode_unit(probs, nprob, unit);
         const DevProblem& P = probs[c.p];
         const uint32_t idesc = P.idesc;
@@ -326,7 +336,8 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
     uint32_t acc_phase = 0;
     uint32_t nbox = 0;  // running count of TMA boxes this warp has issued (selects the staging buffer)
     long long t_wait = 0, t_work = 0;
-    for (int unit = worker; unit < total_units; unit += nworkers) {
+    for (int si = sched_begin; si < sched_end; ++si) {
+        const int unit = sched_units[si];
       const UnitCoord c = decode_unit(probs, nprob, unit);
       const DevProblem& P = probs[c.p];
       const CUtensorMap* mapD = maps + 3 * c.p + 2;
@@ -564,6 +575,10 @@ struct mtrl_gemm_plan {
   GemmParams params;
   int grid = 0;
   int ctas = 1;  // 1: one CTA per tile; 2: CTA pairs (cta_group::2)
+  int* d_sched = nullptr;
+  ~mtrl_gemm_plan() {
+    if (d_sched) cudaFree(d_sched);
+  }
 };
 
 namespace {
@@ -674,7 +689,51 @@ extern "C" int mtrl_gemm_plan_create(mtrl_gemm_plan_t** out, const mtrl_gemm_pro
   P.nprob = n;
   P.total_units = units;
   const int workers = sms / ctas;
-  plan->grid = (units < workers ? units : workers) * ctas;
+  const int nworkers = units < workers ? units : workers;
+  plan->grid = nworkers * ctas;
+  {
+    // Longest-processing-time-first assignment.  Unit cost ~ k-blocks x tile width (narrow tiles are bounded by the
+    // per-k-block TMA / issue latency, not by the MMA) + a constant for prologue and epilogue drain.  Units of equal
+    // cost keep their index order, so a launch of uniform units degenerates to the round-robin it replaces
+    // (neighbouring workers share operand tiles in L2).
+    struct U { int unit; long long cost; };
+    std::vector<U> us;
+    us.reserve(units);
+    for (int i = 0; i < n; ++i) {
+      const DevProblem& d = P.probs[i];
+      for (int u = 0; u < d.unit_count; ++u) {
+        const int split = u / (d.n_tiles * d.m_tiles);
+        const int kb0 = split * d.kb_per_split;
+        const int kb1 = kb0 + d.kb_per_split < d.kb_total ? kb0 + d.kb_per_split : d.kb_total;
+        const long long per_kb = d.block_n > 160 ? d.block_n : 160;
+        us.push_back({d.unit_begin + u, static_cast<long long>(kb1 - kb0) * per_kb + 4 * 256});
+      }
+    }
+    const bool lpt = !(getenv("MTRL_GEMM_NO_LPT") && getenv("MTRL_GEMM_NO_LPT")[0] == '1');
+    if (lpt) std::stable_sort(us.begin(), us.end(), [](const U& a, const U& b) { return a.cost > b.cost; });
+    std::vector<std::vector<int>> lists(nworkers);
+    std::vector<long long> load(nworkers, 0);
+    for (size_t i = 0; i < us.size(); ++i) {
+      int best = static_cast<int>(i % nworkers);
+      if (lpt) {
+        best = 0;
+        for (int w = 1; w < nworkers; ++w)
+          if (load[w] < load[best]) best = w;
+      }
+      lists[best].push_back(us[i].unit);
+      load[best] += us[i].cost;
+    }
+    std::vector<int> table(nworkers + 1 + units);
+    int off = 0;
+    for (int w = 0; w < nworkers; ++w) {
+      table[w] = off;
+      for (int u : lists[w]) table[nworkers + 1 + off++] = u;
+    }
+    table[nworkers] = off;
+    MTRL_CUDA_CHECK(cudaMalloc(&plan->d_sched, table.size() * sizeof(int)));
+    MTRL_CUDA_CHECK(cudaMemcpy(plan->d_sched, table.data(), table.size() * sizeof(int), cudaMemcpyHostToDevice));
+    P.sched = plan->d_sched;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     MTRL_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32_grouped_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,

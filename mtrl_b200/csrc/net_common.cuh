@@ -122,7 +122,8 @@ inline int make_plan(std::vector<mtrl_gemm_plan_t*>& dst, const std::vector<mtrl
 template <int HD>
 inline void launch_head_bwd_t(const HeadBwdArgs& a, int T_local, int E, cudaStream_t st) {
   dim3 grid((a.W + 127) / 128, T_local, E);
-  head_bwd_kernel<HD><<<grid, 128, 0, st>>>(a);
+  constexpr int RG = HD <= 4 ? 16 : 8;   // wide heads keep (HD x 4) weights + sums per lane: fewer, fatter warps
+  head_bwd_kernel<HD, RG><<<grid, RG * 32, 0, st>>>(a);
 }
 
 

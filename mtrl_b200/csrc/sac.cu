@@ -198,7 +198,10 @@ int build_plans(mtrl_sac* h) {
         p.A = w.G[e][src]; p.lda = W; p.a_major = 0;
         p.B = tk(csh, LC, e, 0); p.ldb = W; p.b_major = 0;
         p.D = w.dXin + static_cast<long long>(e) * M * 16; p.ldd = 16;
-        p.M = M; p.N = 16; p.K = W; p.block_n = 16; p.k_splits = 1; p.epilogue = MTRL_EPI_STORE;
+        // a 16-column tile is latency-bound per k-block: split K so the (few) tiles spread over the SMs
+        p.M = M; p.N = 16; p.K = W; p.block_n = 16;
+        p.k_splits = W >= 1024 ? 8 : (W >= 256 ? 2 : 1);
+        p.epilogue = p.k_splits > 1 ? MTRL_EPI_ATOMIC_ADD : MTRL_EPI_STORE;
         ppi.push_back(p);
       }
     }
@@ -251,14 +254,16 @@ int launch_actor_head(mtrl_sac* h, const float* H, const float* eps, float* Xdst
   a.W = c.width;
   a.ls_min = c.log_std_min;
   a.ls_max = c.log_std_max;
-  const size_t wbytes = static_cast<size_t>(c.width) * 2 * c.action_dim * sizeof(float);
+  const size_t wbytes = static_cast<size_t>(c.width + 4) * 2 * c.action_dim * sizeof(float);
   if (wbytes <= 200 * 1024) {
-    dim3 grid(c.max_rows / 32), block(256);
+    // few rows (a task shard of a multi-GPU job): smaller blocks so the launch still covers the SMs
+    const int rpb = c.max_rows <= 4096 ? 16 : 32;
+    dim3 grid(c.max_rows / rpb), block(256);
 #define MTRL_AH_TILE(A_) \
-  case A_: actor_head_tile_kernel<A_><<<grid, block, wbytes, st>>>(a); break;
+  case A_: actor_head_tile_kernel<A_><<<grid, block, wbytes, st>>>(a, rpb); break;
     switch (c.action_dim) {
       MTRL_AH_TILE(1) MTRL_AH_TILE(2) MTRL_AH_TILE(3) MTRL_AH_TILE(4) MTRL_AH_TILE(5) MTRL_AH_TILE(6) MTRL_AH_TILE(7)
-      default: actor_head_tile_kernel<8><<<grid, block, wbytes, st>>>(a);
+      default: actor_head_tile_kernel<8><<<grid, block, wbytes, st>>>(a, rpb);
     }
 #undef MTRL_AH_TILE
     MTRL_CUDA_CHECK(cudaGetLastError());
@@ -609,6 +614,9 @@ int step_actor_grads(mtrl_sac* h, cudaStream_t st) {
   const mtrl_net_layout_t& LC = h->lay.critic;
   const int M = c.max_rows, W = c.width, D = c.depth, E = c.num_critics;
   const float inv_b = 1.f / static_cast<float>(h->global_batch);
+  // dL/da accumulates over K splits (see build_plans)
+  MTRL_CUDA_CHECK(cudaMemsetAsync(w.dXin, 0, static_cast<size_t>(E) * M * 16 * sizeof(float), st));
+  h->launches += 1;
   for (int l = 0; l < D; ++l) MTRL_PROPAGATE(run_plan(h, h->fwd_pi[l], st));
   {
     ActorLossArgs a;

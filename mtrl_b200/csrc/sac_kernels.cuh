@@ -315,67 +315,132 @@ static __global__ void actor_head_kernel(const ActorHeadArgs p) {
   }
 }
 
-// Same computation, one block per 32 packed rows (all of one task): the task's (W, 2A) head matrix is staged in
-// shared memory once per block instead of being streamed from L2 for every row.
+// Same computation, one block per `rows_per_block` packed rows (all of one task; rows_per_block divides 128 and is a
+// multiple of 16): the task's (W, 2A) head matrix is staged once per block in shared memory, transposed to
+// [2A][W + 4] so that a lane reads 4 consecutive hidden units of one output as a conflict-free float4.  A warp works
+// on two rows at a time (the weight reads are shared) with all of a row's float4 activation loads in flight.
 template <int A>
-static __global__ void actor_head_tile_kernel(const ActorHeadArgs p) {
-  extern __shared__ float sw[];  // [W][2A]
-  const int row0 = blockIdx.x * 32;
+static __global__ void __launch_bounds__(256) actor_head_tile_kernel(const ActorHeadArgs p, int rows_per_block) {
+  extern __shared__ __align__(16) float sw[];  // [2A][W + 4]
+  const int ldw = p.W + 4;
+  const int row0 = blockIdx.x * rows_per_block;
   const int t = p.tile_task[row0 / kTileRows];
   const float* wsrc = p.Wh + static_cast<long long>(t) * p.W * (2 * A);
-  for (int i = threadIdx.x; i < p.W * 2 * A / 4; i += blockDim.x)
-    reinterpret_cast<float4*>(sw)[i] = __ldg(reinterpret_cast<const float4*>(wsrc) + i);
+  if constexpr ((2 * A) % 4 == 0) {
+    // batches of 8 independent 16-byte loads per thread (a plain load-store loop would serialise on the L2 latency)
+    const int n4 = p.W * 2 * A / 4;
+    for (int i0 = threadIdx.x; i0 < n4; i0 += 8 * blockDim.x) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * blockDim.x;
+        v[u] = i < n4 ? __ldg(reinterpret_cast<const float4*>(wsrc) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * blockDim.x;
+        if (i < n4) {
+          const int k = (i * 4) / (2 * A), j = (i * 4) % (2 * A);
+          sw[j * ldw + k] = v[u].x;
+          sw[(j + 1) * ldw + k] = v[u].y;
+          sw[(j + 2) * ldw + k] = v[u].z;
+          sw[(j + 3) * ldw + k] = v[u].w;
+        }
+      }
+    }
+  } else {
+    const int n = p.W * 2 * A;
+    for (int i0 = threadIdx.x; i0 < n; i0 += 8 * blockDim.x) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * blockDim.x;
+        v[u] = i < n ? __ldg(wsrc + i) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * blockDim.x;
+        if (i < n) sw[(i % (2 * A)) * ldw + i / (2 * A)] = v[u];
+      }
+    }
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int row = row0 + warp; row < row0 + 32 && row < p.M; row += nw) {
-    const bool valid = p.slot_src[row] >= 0;
-    float acc[2 * A];
+  const int W4 = p.W / 4;
+  for (int rp = row0 + 2 * warp; rp < row0 + rows_per_block && rp < p.M; rp += 2 * nw) {
+    bool valid[2];
+    float acc[2][2 * A];
 #pragma unroll
-    for (int j = 0; j < 2 * A; ++j) acc[j] = 0.f;
-    if (valid) {
-      const float* h = p.H + static_cast<long long>(row) * p.W;
-      for (int k = lane; k < p.W; k += 32) {
-        const float hv = h[k];
-        const float* wk = sw + k * (2 * A);
+    for (int u = 0; u < 2; ++u) {
+      valid[u] = rp + u < p.M && p.slot_src[rp + u] >= 0;
 #pragma unroll
-        for (int j = 0; j < 2 * A; ++j) acc[j] = fmaf(hv, wk[j], acc[j]);
+      for (int j = 0; j < 2 * A; ++j) acc[u][j] = 0.f;
+    }
+    if (valid[0] || valid[1]) {
+      const float4* h0 = reinterpret_cast<const float4*>(p.H + static_cast<long long>(rp) * p.W);
+      const float4* h1 = reinterpret_cast<const float4*>(p.H + static_cast<long long>(rp + (rp + 1 < p.M ? 1 : 0)) * p.W);
+      for (int kb = lane; kb < W4; kb += 32 * 8) {
+        float4 a[8], b[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int k4 = kb + 32 * u;
+          a[u] = k4 < W4 ? h0[k4] : make_float4(0.f, 0.f, 0.f, 0.f);
+          b[u] = k4 < W4 ? h1[k4] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int k4 = kb + 32 * u;
+          if (k4 < W4) {
+#pragma unroll
+            for (int j = 0; j < 2 * A; ++j) {
+              const float4 wv = *reinterpret_cast<const float4*>(sw + j * ldw + k4 * 4);
+              acc[0][j] = fmaf(a[u].x, wv.x, fmaf(a[u].y, wv.y, fmaf(a[u].z, wv.z, fmaf(a[u].w, wv.w, acc[0][j]))));
+              acc[1][j] = fmaf(b[u].x, wv.x, fmaf(b[u].y, wv.y, fmaf(b[u].z, wv.z, fmaf(b[u].w, wv.w, acc[1][j]))));
+            }
+          }
+        }
       }
     }
 #pragma unroll
-    for (int j = 0; j < 2 * A; ++j) acc[j] = warp_sum(acc[j]);
-    float lp = 0.f;
-    unsigned mask = 0;
-    if (lane < A) {
-      const int d = lane;
-      float mean = 0.f, ls_raw = 0.f;
+    for (int u = 0; u < 2; ++u) {
+      const int row = rp + u;
+      if (row >= p.M) break;
 #pragma unroll
-      for (int j = 0; j < A; ++j) {
-        if (j == d) { mean = acc[j]; ls_raw = acc[A + j]; }
+      for (int j = 0; j < 2 * A; ++j) acc[u][j] = warp_sum(acc[u][j]);
+      float lp = 0.f;
+      unsigned mask = 0;
+      if (lane < A) {
+        const int d = lane;
+        float mean = 0.f, ls_raw = 0.f;
+#pragma unroll
+        for (int j = 0; j < A; ++j) {
+          if (j == d) { mean = acc[u][j]; ls_raw = acc[u][A + j]; }
+        }
+        float a = 0.f, ls = 0.f;
+        if (valid[u]) {
+          mean += p.bh[t * 2 * A + d];
+          ls_raw += p.bh[t * 2 * A + A + d];
+          ls = fminf(fmaxf(ls_raw, p.ls_min), p.ls_max);
+          const float sd = expf(ls);
+          const float e = p.eps[row * A + d];
+          const float x = fmaf(sd, e, mean);
+          a = tanhf(x);
+          const float z = -2.f * x;
+          const float softplus = z > 0.f ? z + log1pf(expf(-z)) : log1pf(expf(z));
+          const float fldj = 2.f * (0.69314718055994531f - x - softplus);
+          lp = -0.5f * e * e - 0.91893853320467274f - ls - fldj;
+          if (ls_raw > p.ls_min && ls_raw < p.ls_max) mask = 1u << d;
+        }
+        if (p.Xdst) p.Xdst[static_cast<long long>(row) * p.ldx + d] = tf32_rna(a);
+        if (p.act) p.act[row * A + d] = a;
+        if (p.logstd) p.logstd[row * A + d] = ls;
       }
-      float a = 0.f, ls = 0.f;
-      if (valid) {
-        mean += p.bh[t * 2 * A + d];
-        ls_raw += p.bh[t * 2 * A + A + d];
-        ls = fminf(fmaxf(ls_raw, p.ls_min), p.ls_max);
-        const float sd = expf(ls);
-        const float e = p.eps[row * A + d];
-        const float x = fmaf(sd, e, mean);
-        a = tanhf(x);
-        const float z = -2.f * x;
-        const float softplus = z > 0.f ? z + log1pf(expf(-z)) : log1pf(expf(z));
-        const float fldj = 2.f * (0.69314718055994531f - x - softplus);
-        lp = -0.5f * e * e - 0.91893853320467274f - ls - fldj;
-        if (ls_raw > p.ls_min && ls_raw < p.ls_max) mask = 1u << d;
+      lp = warp_sum(lp);
+      for (int o = 16; o > 0; o >>= 1) mask |= __shfl_xor_sync(0xffffffffu, mask, o);
+      if (lane == 0) {
+        p.logp[row] = lp;
+        if (p.inrange) p.inrange[row] = mask;
       }
-      if (p.Xdst) p.Xdst[static_cast<long long>(row) * p.ldx + d] = tf32_rna(a);
-      if (p.act) p.act[row * A + d] = a;
-      if (p.logstd) p.logstd[row * A + d] = ls;
-    }
-    lp = warp_sum(lp);
-    for (int o = 16; o > 0; o >>= 1) mask |= __shfl_xor_sync(0xffffffffu, mask, o);
-    if (lane == 0) {
-      p.logp[row] = lp;
-      if (p.inrange) p.inrange[row] = mask;
     }
   }
 }
@@ -396,19 +461,48 @@ struct QHeads {
   const float* b[kMaxE];   // (T_local, 1)
 };
 
-__device__ __forceinline__ float row_dot(const float* __restrict__ h, const float* __restrict__ w, int W, int lane) {
-  float s = 0.f;
-  const float4* h4 = reinterpret_cast<const float4*>(h);
-  const float4* w4 = reinterpret_cast<const float4*>(w);
-  for (int k = lane; k < W / 4; k += 32) {
-    const float4 a = h4[k];
-    const float4 c = __ldg(w4 + k);
-    s = fmaf(a.x, c.x, s);
-    s = fmaf(a.y, c.y, s);
-    s = fmaf(a.z, c.z, s);
-    s = fmaf(a.w, c.w, s);
+// N row-by-vector dot products at once (one warp, lanes stride the float4 columns): every pass issues the 2N loads of
+// 4 column groups before any arithmetic, so a warp keeps 8N 16-byte loads in flight instead of one dependent pair.
+template <int N>
+__device__ __forceinline__ void row_dots(const float* const (&h)[N], const float* const (&w)[N], int W, int lane, float (&out)[N]) {
+  float s[N];
+#pragma unroll
+  for (int n = 0; n < N; ++n) s[n] = 0.f;
+  const int W4 = W / 4;
+  int kb = lane;
+  for (; kb + 96 < W4; kb += 128) {
+    float4 a[N][4], c[N][4];
+#pragma unroll
+    for (int n = 0; n < N; ++n)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a[n][u] = reinterpret_cast<const float4*>(h[n])[kb + 32 * u];
+        c[n][u] = __ldg(reinterpret_cast<const float4*>(w[n]) + kb + 32 * u);
+      }
+#pragma unroll
+    for (int n = 0; n < N; ++n)
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        s[n] = fmaf(a[n][u].x, c[n][u].x, fmaf(a[n][u].y, c[n][u].y, fmaf(a[n][u].z, c[n][u].z, fmaf(a[n][u].w, c[n][u].w, s[n]))));
   }
-  return warp_sum(s);
+  for (; kb < W4; kb += 32) {
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      const float4 a = reinterpret_cast<const float4*>(h[n])[kb];
+      const float4 c = __ldg(reinterpret_cast<const float4*>(w[n]) + kb);
+      s[n] = fmaf(a.x, c.x, fmaf(a.y, c.y, fmaf(a.z, c.z, fmaf(a.w, c.w, s[n]))));
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < N; ++n) out[n] = warp_sum(s[n]);
+}
+
+__device__ __forceinline__ float row_dot(const float* __restrict__ h, const float* __restrict__ w, int W, int lane) {
+  const float* const hh[1] = {h};
+  const float* const ww[1] = {w};
+  float o[1];
+  row_dots<1>(hh, ww, W, lane, o);
+  return o[0];
 }
 
 struct CriticLossArgs {
@@ -440,9 +534,12 @@ static __global__ void critic_loss_kernel(const CriticLossArgs p) {
       q[e] = 0.f;
       if (e < p.E && valid) {
         const long long ro = static_cast<long long>(row) * p.W, wo = static_cast<long long>(t) * p.W;
-        const float qt = row_dot(p.target.H[e] + ro, p.target.w[e] + wo, p.W, lane) + p.target.b[e][t];
-        qt_min = fminf(qt_min, qt);
-        q[e] = row_dot(p.online.H[e] + ro, p.online.w[e] + wo, p.W, lane) + p.online.b[e][t];
+        const float* const hh[2] = {p.target.H[e] + ro, p.online.H[e] + ro};
+        const float* const ww[2] = {p.target.w[e] + wo, p.online.w[e] + wo};
+        float o[2];
+        row_dots<2>(hh, ww, p.W, lane, o);
+        qt_min = fminf(qt_min, o[0] + p.target.b[e][t]);
+        q[e] = o[1] + p.online.b[e][t];
       }
     }
     if (lane == 0) {
@@ -501,12 +598,23 @@ static __global__ void actor_loss_kernel(const ActorLossArgs p) {
     float q[kMaxE];
     float qmin = INFINITY;
 #pragma unroll
-    for (int e = 0; e < kMaxE; ++e) {
-      q[e] = INFINITY;
-      if (e < p.E && valid) {
-        q[e] = row_dot(p.online.H[e] + static_cast<long long>(row) * p.W, p.online.w[e] + static_cast<long long>(t) * p.W,
-                       p.W, lane) + p.online.b[e][t];
-        qmin = fminf(qmin, q[e]);
+    for (int e = 0; e < kMaxE; ++e) q[e] = INFINITY;
+    const long long ro = static_cast<long long>(row) * p.W, wo = static_cast<long long>(t) * p.W;
+    if (valid && p.E == 2) {   // the reference's ensemble size: both members' loads in flight together
+      const float* const hh[2] = {p.online.H[0] + ro, p.online.H[1] + ro};
+      const float* const ww[2] = {p.online.w[0] + wo, p.online.w[1] + wo};
+      float o[2];
+      row_dots<2>(hh, ww, p.W, lane, o);
+      q[0] = o[0] + p.online.b[0][t];
+      q[1] = o[1] + p.online.b[1][t];
+      qmin = fminf(q[0], q[1]);
+    } else if (valid) {
+#pragma unroll
+      for (int e = 0; e < kMaxE; ++e) {
+        if (e < p.E) {
+          q[e] = row_dot(p.online.H[e] + ro, p.online.w[e] + wo, p.W, lane) + p.online.b[e][t];
+          qmin = fminf(qmin, q[e]);
+        }
       }
     }
     if (lane == 0) {
@@ -568,7 +676,10 @@ static __global__ void actor_dout_kernel(const ActorDoutArgs p) {
 // Head VJP (nn.vmap(Dense) heads, multi_head.py:50-66, own-task rows only):
 //   dZ[row,k]   = (sum_j dout[row,j] Wh[t,k,j]) * (H[row,k] > 0)      (masked by the trunk's last ReLU)
 //   dWh[t,k,j]  = sum_{rows of t} H[row,k] dout[row,j];   dbh[t,j] = sum_{rows of t} dout[row,j]
-// grid (W/128, T_local, E); a thread owns one hidden unit k and walks the task's rows.
+// grid (W/128, T_local, E); block = RG warps.  A lane owns 4 consecutive hidden units (float4 traffic), warp w owns
+// rows [w * 128/RG, (w+1) * 128/RG) of every 128-row tile of the task and keeps 8 row loads in flight; the per-warp
+// partial sums (dWh, bias-gradient column sums) are combined through shared memory in a fixed order.
+// HBM-bound: reads H and writes dZ once (2 * rows * W * 4 bytes per member).
 // ---------------------------------------------------------------------------------------------
 struct HeadBwdArgs {
   const float* H[kMaxE];
@@ -582,52 +693,89 @@ struct HeadBwdArgs {
   int M, W;
 };
 
-template <int HD>
-static __global__ void head_bwd_kernel(const HeadBwdArgs p) {
+template <int HD, int RG>
+static __global__ void __launch_bounds__(RG * 32, (RG == 8 && HD <= 8) ? 2 : 1) head_bwd_kernel(const HeadBwdArgs p) {
+  constexpr int RPW = kTileRows / RG;   // rows per warp per tile
+  static_assert(RPW % 8 == 0, "rows per warp must be a multiple of the 8-row load batch");
   __shared__ float sd[kTileRows * HD];
+  __shared__ __align__(16) float red[RG][128];
   const int e = blockIdx.z, t = blockIdx.y;
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool kok = k < p.W;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k = blockIdx.x * 128 + lane * 4;
+  const bool kok = k < p.W;   // W is a multiple of 4
   const int r0 = p.seg_start[t], r1 = p.seg_start[t + 1];
   const float* H = p.H[e];
   const float* dout = p.dout[e];
   float* dZ = p.dZ[e];
-  float w[HD], acc[HD];
+  float w[HD][4], acc[HD][4];
 #pragma unroll
-  for (int j = 0; j < HD; ++j) {
-    acc[j] = 0.f;
-    w[j] = kok ? p.Wh[e][(static_cast<long long>(t) * p.W + k) * HD + j] : 0.f;
-  }
+  for (int j = 0; j < HD; ++j)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      acc[j][c] = 0.f;
+      w[j][c] = kok ? p.Wh[e][(static_cast<long long>(t) * p.W + k + c) * HD + j] : 0.f;
+    }
   float bsum = 0.f;  // threads j < HD of block x == 0 accumulate the bias gradient
   for (int base = r0; base < r1; base += kTileRows) {
     __syncthreads();
     for (int i = threadIdx.x; i < kTileRows * HD; i += blockDim.x) sd[i] = dout[static_cast<long long>(base) * HD + i];
     __syncthreads();
+    float csum[4] = {0.f, 0.f, 0.f, 0.f};
     if (kok) {
-      float csum = 0.f;
-#pragma unroll 4
-      for (int r = 0; r < kTileRows; ++r) {
-        const float h = H[static_cast<long long>(base + r) * p.W + k];
-        float dz = 0.f;
 #pragma unroll
-        for (int j = 0; j < HD; ++j) {
-          const float d = sd[r * HD + j];
-          acc[j] = fmaf(h, d, acc[j]);
-          dz = fmaf(d, w[j], dz);
+      for (int c0 = 0; c0 < RPW; c0 += 8) {
+        float4 h4[8];
+        const int rr = warp * RPW + c0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) h4[r] = *reinterpret_cast<const float4*>(H + static_cast<long long>(base + rr + r) * p.W + k);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const float hv[4] = {h4[r].x, h4[r].y, h4[r].z, h4[r].w};
+          float dz[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int j = 0; j < HD; ++j) {
+            const float d = sd[(rr + r) * HD + j];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              acc[j][c] = fmaf(hv[c], d, acc[j][c]);
+              dz[c] = fmaf(d, w[j][c], dz[c]);
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            dz[c] = hv[c] > 0.f ? tf32_rna(dz[c]) : 0.f;
+            csum[c] += dz[c];
+          }
+          *reinterpret_cast<float4*>(dZ + static_cast<long long>(base + rr + r) * p.W + k) = make_float4(dz[0], dz[1], dz[2], dz[3]);
         }
-        dz = h > 0.f ? tf32_rna(dz) : 0.f;
-        csum += dz;
-        dZ[static_cast<long long>(base + r) * p.W + k] = dz;
       }
-      if (p.colsum[e]) p.colsum[e][static_cast<long long>(base / kTileRows) * p.W + k] = csum;
+    }
+    if (p.colsum[e]) {
+      *reinterpret_cast<float4*>(&red[warp][lane * 4]) = make_float4(csum[0], csum[1], csum[2], csum[3]);
+      __syncthreads();
+      if (threadIdx.x < 128 && blockIdx.x * 128 + threadIdx.x < p.W) {
+        float s = 0.f;
+#pragma unroll
+        for (int g = 0; g < RG; ++g) s += red[g][threadIdx.x];
+        p.colsum[e][static_cast<long long>(base / kTileRows) * p.W + blockIdx.x * 128 + threadIdx.x] = s;
+      }
     }
     if (blockIdx.x == 0 && threadIdx.x < HD)
       for (int r = 0; r < kTileRows; ++r) bsum += sd[r * HD + threadIdx.x];
   }
   if (p.dWh[e]) {
-    if (kok) {
 #pragma unroll
-      for (int j = 0; j < HD; ++j) p.dWh[e][(static_cast<long long>(t) * p.W + k) * HD + j] = acc[j];
+    for (int j = 0; j < HD; ++j) {
+      __syncthreads();
+      *reinterpret_cast<float4*>(&red[warp][lane * 4]) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+      __syncthreads();
+      const int kk = blockIdx.x * 128 + threadIdx.x;
+      if (threadIdx.x < 128 && kk < p.W) {
+        float s = 0.f;
+#pragma unroll
+        for (int g = 0; g < RG; ++g) s += red[g][threadIdx.x];
+        p.dWh[e][(static_cast<long long>(t) * p.W + kk) * HD + j] = s;
+      }
     }
     if (blockIdx.x == 0 && threadIdx.x < HD) p.dbh[e][t * HD + threadIdx.x] = bsum;
   }

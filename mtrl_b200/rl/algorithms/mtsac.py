@@ -221,8 +221,10 @@ class MTSAC:
         pass (default 128 per local task, the reference's batch).  rank/world_size shard the tasks;
         `exchange` picks how the ranks sum trunk gradients: "p2p" = the fused peer-memory kernel
         (csrc/comm.cuh, sharded Adam, no library collective), "nccl" = all-reduce between the phases."""
-        if exchange not in ("p2p", "nccl"):
-            raise ValueError(f"exchange must be 'p2p' or 'nccl', got {exchange!r}")
+        if exchange not in ("p2p", "nccl", "local"):
+            raise ValueError(f"exchange must be 'p2p', 'nccl' or 'local', got {exchange!r}")
+        # "local" skips the exchange altogether: one rank's share of the kernels for profiling on a single GPU
+        # (scripts/shard_profile.sh); its numbers are not the sharded update's.
         if not torch.cuda.is_available():
             raise L.MtrlError("MTSAC needs a CUDA device; there is no CPU fallback")
         self = object.__new__(MTSAC)
@@ -317,7 +319,7 @@ class MTSAC:
         self._flat = {f"actor_{k}": z(lay.actor.total) for k in ("params", "grads", "m", "v", "shadow")}
         self._flat.update({f"critic_{k}": z(lay.critic.total)
                            for k in ("params", "grads", "m", "v", "shadow", "target", "target_shadow")})
-        if self.exchange == "p2p":
+        if getattr(self, "exchange", "none") == "p2p":
             self._flat.update(self._open_arena(dev))
         self._flat.update({"log_alpha": z(max(t_local, 4)), "alpha_m": z(max(t_local, 4)), "alpha_v": z(max(t_local, 4))})
         self._steps = z(4, torch.int32)
@@ -363,7 +365,7 @@ class MTSAC:
         h = _vp()
         L.check(L.lib().mtrl_sac_create(C.byref(h), C.byref(self._cfg), C.byref(bufs)))
         self._h = h
-        if self._comm is not None:
+        if getattr(self, "_comm", None) is not None:
             p = self._arena_plan
             L.check(L.lib().mtrl_sac_attach_comm(h, self._comm, p["critic_grads"], p["actor_grads"], p["critic_params"],
                                                  p["actor_params"]))
@@ -378,7 +380,7 @@ class MTSAC:
 
     def exchange_error(self) -> int:
         """0, or the code of the in-kernel wait that timed out waiting for a peer (synchronises)."""
-        if self._comm is None:
+        if getattr(self, "_comm", None) is None:
             return 0
         code = _i()
         L.check(L.lib().mtrl_comm_error(self._comm, C.byref(code)))
@@ -437,7 +439,7 @@ class MTSAC:
         p = lambda t: _vp(t.data_ptr() if t is not None else None)  # noqa: E731
         if self.world_size > 1 and global_batch is None:
             raise ValueError("multi-GPU update needs global_batch (the B every loss mean divides by)")
-        if self.world_size == 1 or self.exchange == "p2p":
+        if self.world_size == 1 or self.exchange in ("p2p", "local"):
             # one call: with several ranks the trunk-gradient exchange happens inside the fused kernels (comm.cuh)
             L.check(L.lib().mtrl_sac_update(*args, global_batch or B, p(ec), p(ea), stream))
         else:
@@ -465,7 +467,7 @@ class MTSAC:
         """The ten log scalars of the last update as 0-dim device tensors (keys of mtsac.py:616-621, 704-709, 728-731).
         With world_size > 1 the per-rank partial sums are combined here (one 16-float all-reduce)."""
         v = self._logs
-        if self.world_size > 1:
+        if self.world_size > 1 and self.exchange != "local":
             import torch.distributed as dist
 
             s = v.clone()
