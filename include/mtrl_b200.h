@@ -63,7 +63,7 @@ typedef struct mtrl_gemm_problem {
 
 typedef struct mtrl_gemm_plan mtrl_gemm_plan_t;
 
-/* Encodes the TMA descriptors for up to 8 problems that will run as one persistent launch. */
+/* Encodes the TMA descriptors for up to 24 problems that will run as one persistent launch. */
 int mtrl_gemm_plan_create(mtrl_gemm_plan_t** out, const mtrl_gemm_problem_t* problems, int n);
 int mtrl_gemm_plan_run(mtrl_gemm_plan_t* plan, void* stream);
 int mtrl_gemm_plan_units(const mtrl_gemm_plan_t* plan);

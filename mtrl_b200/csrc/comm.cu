@@ -28,6 +28,7 @@ extern "C" int mtrl_comm_create(mtrl_comm_t** out, int rank, int world, long lon
   comm::Header h;
   memset(&h, 0, sizeof(h));
   h.epoch = 1;
+  h.sync_epoch = 1;
   cudaMemcpy(p, &h, sizeof(h), cudaMemcpyHostToDevice);
   cudaIpcMemHandle_t ih;
   e = cudaIpcGetMemHandle(&ih, p);
@@ -60,6 +61,10 @@ extern "C" int mtrl_comm_open_peers(mtrl_comm_t* c, const unsigned char* handles
     }
     c->peer[q] = static_cast<uint8_t*>(p);
   }
+  comm::Header* hp[MTRL_COMM_MAX_RANKS] = {};
+  for (int q = 0; q < c->world; ++q) hp[q] = reinterpret_cast<comm::Header*>(c->peer[q]);
+  MTRL_CUDA_CHECK(cudaMalloc(&c->d_peer_hdr, sizeof(hp)));
+  MTRL_CUDA_CHECK(cudaMemcpy(c->d_peer_hdr, hp, sizeof(hp), cudaMemcpyHostToDevice));
   c->opened = true;
   return MTRL_OK;
 }
@@ -76,6 +81,7 @@ extern "C" void mtrl_comm_destroy(mtrl_comm_t* c) {
   if (!c) return;
   for (int q = 0; q < c->world; ++q)
     if (q != c->rank && c->peer[q]) cudaIpcCloseMemHandle(c->peer[q]);
+  if (c->d_peer_hdr) cudaFree(c->d_peer_hdr);
   if (c->arena) cudaFree(c->arena);
   delete c;
 }

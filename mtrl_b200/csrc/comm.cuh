@@ -28,6 +28,17 @@ struct Header {
   unsigned int epoch;                             // stamp of the next exchange (starts at 1)
   int error;                                      // != 0: a wait timed out (peer missing)
   double shard_g2[2];                             // this rank's shard accumulator, double-buffered by epoch parity
+  unsigned int sync_epoch;                        // stamp of the next rank_barrier_kernel (flag[3], starts at 1)
+};
+
+// Ownership of the replicated trunk: the flat buffer is cut into segments, each stepped (Adam) by exactly one rank.
+// pre_reduced segments are the row blocks of the hidden-layer kernels whose gradient every rank's dW GEMM epilogue
+// reduce-adds straight into the owner's buffer over NVLink (sac.cu build_plans); the rest (first-layer kernel,
+// biases: small) is summed by the owner with peer loads.
+struct Segment {
+  long long begin4, end4;   // float4 units into the flat network buffer
+  int owner;
+  int pre_reduced;
 };
 static_assert(sizeof(Header) <= MTRL_COMM_HEADER_BYTES, "comm header overflows its page");
 
@@ -76,6 +87,8 @@ struct TrunkStepArgs {
   float* peer_g[MTRL_COMM_MAX_RANKS];                      // every rank's gradient buffer ([rank] == g)
   float* peer_p[MTRL_COMM_MAX_RANKS];                      // every rank's parameter buffer ([rank] == p)
   Header* peer_hdr[MTRL_COMM_MAX_RANKS];
+  const Segment* segs;                                     // device table covering [0, trunk_n)
+  int nsegs;
   int rank, world;
   const int* step;
   double* g2_trunk_out;                                    // global trunk gradient squared norm (log scalar input)
@@ -182,6 +195,23 @@ __device__ __forceinline__ float derived4(const TrunkStepArgs& a, long long i4, 
   return p4.x * p4.x + p4.y * p4.y + p4.z * p4.z + p4.w * p4.w;
 }
 
+// Every rank has finished what precedes this kernel in its stream (one warp; used before the first gradient
+// GEMM of an update so that no rank reduce-adds into a peer buffer that is not zeroed yet).
+static __global__ void rank_barrier_kernel(Header* const* peer_hdr_dev, int rank, int world) {
+  __shared__ Header* hdr[MTRL_COMM_MAX_RANKS];
+  if (threadIdx.x < world) hdr[threadIdx.x] = peer_hdr_dev[threadIdx.x];
+  __syncthreads();
+  Header* H = hdr[rank];
+  const unsigned epoch = *reinterpret_cast<volatile unsigned*>(&H->sync_epoch);
+  __syncthreads();
+  if (threadIdx.x < world) {
+    __threadfence_system();
+    st_release_sys(&hdr[threadIdx.x]->flag[3][rank], epoch);
+  }
+  wait_ranks(H, 3, world, epoch);
+  if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned*>(&H->sync_epoch) = epoch + 1;
+}
+
 // Launch with one CTA per SM (all CTAs must be co-resident: they meet at in-kernel barriers).
 template <int WORLD>
 static __global__ void __launch_bounds__(512, 1) trunk_step_kernel(const TrunkStepArgs a) {
@@ -193,22 +223,30 @@ static __global__ void __launch_bounds__(512, 1) trunk_step_kernel(const TrunkSt
   const int world = WORLD ? WORLD : a.world;
   const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  const long long trunk4 = a.trunk_n / 4;
-  long long per = (trunk4 + world - 1) / world;
-  per = (per + 31) / 32 * 32;
-  const long long s0 = min(per * a.rank, trunk4), s1 = min(s0 + per, trunk4);
 
-  // ---- barrier 0: every rank's gradients are complete (they are, by stream order, once its kernel runs) ----
+  // ---- barrier 0: every rank's gradient kernels are complete (by stream order, once its kernel runs), so the
+  //      reduce-adds they sent into this rank's pre-reduced segments have landed too ----
   if (blockIdx.x == 0 && threadIdx.x < world) st_release_sys(&a.peer_hdr[threadIdx.x]->flag[0][a.rank], epoch);
   wait_ranks(H, 0, world, epoch);
 
-  // ---- reduce-scatter: this rank sums its shard over all ranks (fixed rank order), in place in its own buffer ----
+  // ---- owned segments: finish the reduction where the GEMMs have not done it, and take the squared norm ----
   {
     double s = 0.0;
-    for (long long i = s0 + tid; i < s1; i += stride) {
-      const float4 g4 = reduce_ranks<WORLD>(a, i);
-      reinterpret_cast<float4*>(a.g)[i] = g4;
-      s += static_cast<double>(g4.x * g4.x + g4.y * g4.y) + static_cast<double>(g4.z * g4.z + g4.w * g4.w);
+    for (int si = 0; si < a.nsegs; ++si) {
+      const Segment sg = a.segs[si];
+      if (sg.owner != a.rank) continue;
+      if (sg.pre_reduced) {
+        for (long long i = sg.begin4 + tid; i < sg.end4; i += stride) {
+          const float4 g4 = ld_sys_f4(a.g + i * 4);   // written by peers' reduce-adds: read at L2
+          s += static_cast<double>(g4.x * g4.x + g4.y * g4.y) + static_cast<double>(g4.z * g4.z + g4.w * g4.w);
+        }
+      } else {
+        for (long long i = sg.begin4 + tid; i < sg.end4; i += stride) {
+          const float4 g4 = reduce_ranks<WORLD>(a, i);
+          reinterpret_cast<float4*>(a.g)[i] = g4;
+          s += static_cast<double>(g4.x * g4.x + g4.y * g4.y) + static_cast<double>(g4.z * g4.z + g4.w * g4.w);
+        }
+      }
     }
     s = sac::block_sum(s, red);
     if (threadIdx.x == 0) atomicAdd(&H->shard_g2[epoch & 1], s);
@@ -236,20 +274,24 @@ static __global__ void __launch_bounds__(512, 1) trunk_step_kernel(const TrunkSt
   const float bc1 = static_cast<float>(1.0 - pow(static_cast<double>(a.b1), static_cast<double>(t)));
   const float bc2 = static_cast<float>(1.0 - pow(static_cast<double>(a.b2), static_cast<double>(t)));
 
-  // ---- Adam on the owned trunk shard; all-gather by storing the new parameters into every rank ----
+  // ---- Adam on the owned segments; all-gather by storing the new parameters into every rank ----
   double p2_trunk = 0.0, p2_head = 0.0;
-  for (long long i = s0 + tid; i < s1; i += stride) {
-    const float4 g4 = reinterpret_cast<const float4*>(a.g)[i];
-    float4 m4 = reinterpret_cast<const float4*>(a.m)[i];
-    float4 v4 = reinterpret_cast<const float4*>(a.v)[i];
-    float4 p4 = reinterpret_cast<const float4*>(a.p)[i];
-    adam4(a, scale, bc1, bc2, g4, m4, v4, p4);
-    reinterpret_cast<float4*>(a.m)[i] = m4;
-    reinterpret_cast<float4*>(a.v)[i] = v4;
+  for (int si = 0; si < a.nsegs; ++si) {
+    const Segment sg = a.segs[si];
+    if (sg.owner != a.rank) continue;
+    for (long long i = sg.begin4 + tid; i < sg.end4; i += stride) {
+      const float4 g4 = sg.pre_reduced ? ld_sys_f4(a.g + i * 4) : reinterpret_cast<const float4*>(a.g)[i];
+      float4 m4 = reinterpret_cast<const float4*>(a.m)[i];
+      float4 v4 = reinterpret_cast<const float4*>(a.v)[i];
+      float4 p4 = reinterpret_cast<const float4*>(a.p)[i];
+      adam4(a, scale, bc1, bc2, g4, m4, v4, p4);
+      reinterpret_cast<float4*>(a.m)[i] = m4;
+      reinterpret_cast<float4*>(a.v)[i] = v4;
 #pragma unroll
-    for (int q = 0; q < (WORLD ? WORLD : MTRL_COMM_MAX_RANKS); ++q)
-      if (q < world) reinterpret_cast<float4*>(a.peer_p[q])[i] = p4;
-    p2_trunk += static_cast<double>(derived4(a, i, p4));
+      for (int q = 0; q < (WORLD ? WORLD : MTRL_COMM_MAX_RANKS); ++q)
+        if (q < world) reinterpret_cast<float4*>(a.peer_p[q])[i] = p4;
+      p2_trunk += static_cast<double>(derived4(a, i, p4));
+    }
   }
   // ---- heads (local to this rank) ----
   for (long long i = (a.trunk_n + 32) / 4 + tid; i < a.n / 4; i += stride) {
@@ -263,15 +305,18 @@ static __global__ void __launch_bounds__(512, 1) trunk_step_kernel(const TrunkSt
     reinterpret_cast<float4*>(a.p)[i] = p4;
     p2_head += static_cast<double>(derived4(a, i, p4));
   }
-  // ---- barrier 2: every rank has stored its shard everywhere ----
+  // ---- barrier 2: every rank has stored its segments everywhere ----
   grid_arrive_then_signal(a, H, 2, epoch, grid_base + 2ull * gridDim.x, false);
   wait_ranks(H, 2, world, epoch);
 
-  // ---- derived copies of the shards the peers own ----
-  for (long long i = tid; i < trunk4; i += stride) {
-    if (i >= s0 && i < s1) continue;
-    const float4 p4 = ld_sys_f4(a.p + i * 4);
-    p2_trunk += static_cast<double>(derived4(a, i, p4));
+  // ---- derived copies of the segments the peers own ----
+  for (int si = 0; si < a.nsegs; ++si) {
+    const Segment sg = a.segs[si];
+    if (sg.owner == a.rank) continue;
+    for (long long i = sg.begin4 + tid; i < sg.end4; i += stride) {
+      const float4 p4 = ld_sys_f4(a.p + i * 4);
+      p2_trunk += static_cast<double>(derived4(a, i, p4));
+    }
   }
   p2_trunk = sac::block_sum(p2_trunk, red);
   p2_head = sac::block_sum(p2_head, red);
@@ -295,4 +340,5 @@ struct mtrl_comm {
   uint8_t* arena = nullptr;
   uint8_t* peer[MTRL_COMM_MAX_RANKS] = {};
   bool opened = false;
+  comm::Header** d_peer_hdr = nullptr;   // device copy of the header pointers (rank_barrier_kernel)
 };

@@ -91,7 +91,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   return d;
 }
 
-constexpr int kMaxProblems = 8;
+constexpr int kMaxProblems = 24;
 
 // Passed by value as a __grid_constant__ kernel parameter (the usual home of TMA descriptors).
 struct GemmParams {

@@ -137,12 +137,120 @@ struct mtrl_sac {
   // fused peer-memory exchange (comm.cuh); null = single GPU, or the caller all-reduces between the phases
   mtrl_comm* comm = nullptr;
   long long off_critic_grads = 0, off_actor_grads = 0, off_critic_params = 0, off_actor_params = 0;
+  comm::Segment *d_segs_critic = nullptr, *d_segs_actor = nullptr;   // ownership tables (device)
+  int nsegs_critic = 0, nsegs_actor = 0;
 };
 
 namespace {
 
 float* colsum_part(const mtrl_sac* h, int e) {
   return h->ws.colsum_part + static_cast<long long>(e) * (h->cfg.max_rows / 32) * h->cfg.width;
+}
+
+// Rows [r0, r1) of a hidden-layer kernel (in = W rows) that rank r owns when the trunk is sharded over G ranks.
+void row_block(int W, int G, int r, int* r0, int* r1) {
+  const int rb = static_cast<int>(round_up((W + G - 1) / G, 32));
+  *r0 = r * rb < W ? r * rb : W;
+  *r1 = *r0 + rb < W ? *r0 + rb : W;
+}
+
+// Ownership table of one network's trunk (comm.cuh Segment): hidden-layer kernels by row blocks (their gradients are
+// reduced by the dW GEMM epilogues), first-layer kernel + bias and the other biases as whole pieces dealt round-robin.
+std::vector<comm::Segment> trunk_segments(const mtrl_net_layout_t& L, int G) {
+  std::vector<comm::Segment> out;
+  int piece = 0;
+  for (int e = 0; e < L.members; ++e) {
+    const long long base = e * L.member_trunk_stride;
+    const long long first_end = L.depth > 1 ? L.kernel_off[1] : L.member_trunk_stride;
+    out.push_back({(base + 0) / 4, (base + first_end) / 4, piece++ % G, 0});
+    for (int l = 1; l < L.depth; ++l) {
+      for (int r = 0; r < G; ++r) {
+        int r0, r1;
+        row_block(L.width, G, r, &r0, &r1);
+        if (r1 <= r0) continue;
+        const long long b = base + L.kernel_off[l] + static_cast<long long>(r0) * L.width;
+        // the last block also takes the alignment padding between the kernel and its bias (always zero)
+        const long long e_ = r1 == L.width ? base + L.bias_off[l] : base + L.kernel_off[l] + static_cast<long long>(r1) * L.width;
+        out.push_back({b / 4, e_ / 4, r, 1});
+      }
+      const long long bias_end = l + 1 < L.depth ? L.kernel_off[l + 1] : L.member_trunk_stride;
+      out.push_back({(base + L.bias_off[l]) / 4, (base + bias_end) / 4, piece++ % G, 0});
+    }
+  }
+  return out;
+}
+
+// dW problems of layer l >= 1 of one member.  Single device: one problem into the local gradient buffer.  Sharded
+// with the peer-memory exchange: one problem per owner rank, whose epilogue reduce-adds (TMA cp.reduce over NVLink)
+// the owner's row block straight into the OWNER's gradient buffer -- the reduce-scatter happens tile by tile inside
+// the GEMM, overlapped with its main loop.
+void push_dw(mtrl_sac* h, std::vector<mtrl_gemm_problem_t>& dst, const float* X, int ldx, int n_in, const float* dZ, float* grads,
+             long long off_grads, const mtrl_net_layout_t& L, int e, int l) {
+  const int M = h->cfg.max_rows, W = h->cfg.width;
+  if (!h->comm || l == 0) {
+    dst.push_back(dw_problem(X, ldx, n_in, dZ, tk(grads, L, e, l), M, W, h->sms, 0));
+    return;
+  }
+  const mtrl_comm* c = h->comm;
+  for (int r = 0; r < c->world; ++r) {
+    int r0, r1;
+    row_block(W, c->world, r, &r0, &r1);
+    if (r1 <= r0) continue;
+    float* owner_grads = reinterpret_cast<float*>(c->peer[r] + off_grads);
+    mtrl_gemm_problem_t p = dw_problem(X + r0, ldx, r1 - r0, dZ, tk(owner_grads, L, e, l) + static_cast<long long>(r0) * W, M, W,
+                                       h->sms, 0);
+    p.epilogue = MTRL_EPI_ATOMIC_ADD;   // every rank adds its rows' contribution (the buffer is zeroed per update)
+    dst.push_back(p);
+  }
+}
+
+int build_backward_plans(mtrl_sac* h) {
+  const mtrl_sac_config_t& c = h->cfg;
+  const mtrl_net_layout_t& LA = h->lay.actor;
+  const mtrl_net_layout_t& LC = h->lay.critic;
+  const Workspace& w = h->ws;
+  const int M = c.max_rows, W = c.width, D = c.depth, E = c.num_critics;
+  const int Ka = h->lay.k_actor, Kc = h->lay.k_critic;
+  float* ash = h->buf.actor_shadow;
+  float* csh = h->buf.critic_shadow;
+  for (auto* v : {&h->bwd_critic, &h->bwd_pi, &h->bwd_actor}) {
+    for (auto* p : *v) mtrl_gemm_plan_destroy(p);
+    v->clear();
+  }
+  // Backward: dZ_{D-1} (masked head VJP) sits in G[e][0]; layer l reads G[e][(D-1-l)&1], writes G[e][(D-l)&1].
+  for (int l = D - 1; l >= 0; --l) {
+    const int src = (D - 1 - l) & 1, dst = src ^ 1;
+    std::vector<mtrl_gemm_problem_t> pc, ppi, pa;
+    for (int e = 0; e < E; ++e) {
+      const float* X = l == 0 ? w.Xc : w.C[e][l - 1];
+      push_dw(h, pc, X, l == 0 ? Kc : W, l == 0 ? LC.in_dim : W, w.G[e][src], h->buf.critic_grads, h->off_critic_grads, LC, e, l);
+    }
+    for (int e = 0; e < E; ++e) {
+      if (l > 0) {
+        pc.push_back(dx_problem(w.G[e][src], tk(csh, LC, e, l), W, w.bits_C[e][l - 1], w.G[e][dst], M, W, colsum_part(h, e)));
+        ppi.push_back(dx_problem(w.G[e][src], tk(csh, LC, e, l), W, w.bits_C[e][l - 1], w.G[e][dst], M, W, nullptr));
+      } else {
+        // actor step: only dL/da = first action_dim input columns of dZ_0 W_0^T (N = 16 rows of W_0)
+        mtrl_gemm_problem_t p;
+        memset(&p, 0, sizeof(p));
+        p.A = w.G[e][src]; p.lda = W; p.a_major = 0;
+        p.B = tk(csh, LC, e, 0); p.ldb = W; p.b_major = 0;
+        p.D = w.dXin + static_cast<long long>(e) * M * 16; p.ldd = 16;
+        // a 16-column tile is latency-bound per k-block: split K so the (few) tiles spread over the SMs
+        p.M = M; p.N = 16; p.K = W; p.block_n = 16;
+        p.k_splits = W >= 1024 ? 8 : (W >= 256 ? 2 : 1);
+        p.epilogue = p.k_splits > 1 ? MTRL_EPI_ATOMIC_ADD : MTRL_EPI_STORE;
+        ppi.push_back(p);
+      }
+    }
+    push_dw(h, pa, l == 0 ? w.Xa : w.Ao[l - 1], l == 0 ? Ka : W, l == 0 ? LA.in_dim : W, w.G[0][src], h->buf.actor_grads,
+            h->off_actor_grads, LA, 0, l);
+    if (l > 0) pa.push_back(dx_problem(w.G[0][src], tk(ash, LA, 0, l), W, w.bits_Ao[l - 1], w.G[0][dst], M, W, colsum_part(h, 0)));
+    MTRL_PROPAGATE(make_plan(h->bwd_critic, pc));
+    MTRL_PROPAGATE(make_plan(h->bwd_pi, ppi));
+    MTRL_PROPAGATE(make_plan(h->bwd_actor, pa));
+  }
+  return MTRL_OK;
 }
 
 int build_plans(mtrl_sac* h) {
@@ -178,41 +286,7 @@ int build_plans(mtrl_sac* h) {
     MTRL_PROPAGATE(make_plan(h->fwd_target, p));
     MTRL_PROPAGATE(make_plan(h->fwd_pi, q));
   }
-  // Backward: dZ_{D-1} (masked head VJP) sits in G[e][0]; layer l reads G[e][(D-1-l)&1], writes G[e][(D-l)&1].
-  for (int l = D - 1; l >= 0; --l) {
-    const int src = (D - 1 - l) & 1, dst = src ^ 1;
-    std::vector<mtrl_gemm_problem_t> pc, ppi, pa;
-    for (int e = 0; e < E; ++e) {
-      const float* X = l == 0 ? w.Xc : w.C[e][l - 1];
-      pc.push_back(dw_problem(X, l == 0 ? Kc : W, l == 0 ? LC.in_dim : W, w.G[e][src], tk(h->buf.critic_grads, LC, e, l), M, W,
-                              h->sms, 0));
-    }
-    for (int e = 0; e < E; ++e) {
-      if (l > 0) {
-        pc.push_back(dx_problem(w.G[e][src], tk(csh, LC, e, l), W, w.bits_C[e][l - 1], w.G[e][dst], M, W, colsum_part(h, e)));
-        ppi.push_back(dx_problem(w.G[e][src], tk(csh, LC, e, l), W, w.bits_C[e][l - 1], w.G[e][dst], M, W, nullptr));
-      } else {
-        // actor step: only dL/da = first action_dim input columns of dZ_0 W_0^T (N = 16 rows of W_0)
-        mtrl_gemm_problem_t p;
-        memset(&p, 0, sizeof(p));
-        p.A = w.G[e][src]; p.lda = W; p.a_major = 0;
-        p.B = tk(csh, LC, e, 0); p.ldb = W; p.b_major = 0;
-        p.D = w.dXin + static_cast<long long>(e) * M * 16; p.ldd = 16;
-        // a 16-column tile is latency-bound per k-block: split K so the (few) tiles spread over the SMs
-        p.M = M; p.N = 16; p.K = W; p.block_n = 16;
-        p.k_splits = W >= 1024 ? 8 : (W >= 256 ? 2 : 1);
-        p.epilogue = p.k_splits > 1 ? MTRL_EPI_ATOMIC_ADD : MTRL_EPI_STORE;
-        ppi.push_back(p);
-      }
-    }
-    pa.push_back(dw_problem(l == 0 ? w.Xa : w.Ao[l - 1], l == 0 ? Ka : W, l == 0 ? LA.in_dim : W, w.G[0][src],
-                            tk(h->buf.actor_grads, LA, 0, l), M, W, h->sms, 0));
-    if (l > 0) pa.push_back(dx_problem(w.G[0][src], tk(ash, LA, 0, l), W, w.bits_Ao[l - 1], w.G[0][dst], M, W, colsum_part(h, 0)));
-    MTRL_PROPAGATE(make_plan(h->bwd_critic, pc));
-    MTRL_PROPAGATE(make_plan(h->bwd_pi, ppi));
-    MTRL_PROPAGATE(make_plan(h->bwd_actor, pa));
-  }
-  return MTRL_OK;
+  return build_backward_plans(h);
 }
 
 #define LAUNCHED(h) ((h)->launches++)
@@ -340,8 +414,11 @@ int head_sumsq_to_slot(mtrl_sac* h, float* grads, const mtrl_net_layout_t& L, in
 
 
 // Sharded clip + Adam + Polyak fused with the trunk-gradient exchange over peer memory (comm.cuh).
-int launch_trunk_step(mtrl_sac* h, comm::TrunkStepArgs& a, long long off_grads, long long off_params, cudaStream_t st) {
+int launch_trunk_step(mtrl_sac* h, comm::TrunkStepArgs& a, long long off_grads, long long off_params,
+                      const comm::Segment* segs, int nsegs, cudaStream_t st) {
   mtrl_comm* c = h->comm;
+  a.segs = segs;
+  a.nsegs = nsegs;
   a.rank = c->rank;
   a.world = c->world;
   for (int q = 0; q < c->world; ++q) {
@@ -421,6 +498,8 @@ extern "C" void mtrl_sac_destroy(mtrl_sac_t* h) {
   for (auto* v : {&h->fwd, &h->fwd_target, &h->bwd_critic, &h->fwd_pi, &h->bwd_pi, &h->bwd_actor})
     for (auto* p : *v) mtrl_gemm_plan_destroy(p);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+  if (h->d_segs_critic) cudaFree(h->d_segs_critic);
+  if (h->d_segs_actor) cudaFree(h->d_segs_actor);
   delete h;
 }
 
@@ -540,6 +619,13 @@ int step_critic_grads(mtrl_sac* h, cudaStream_t st) {
     a.seg_start = w.seg_start; a.M = M; a.W = W;
     MTRL_PROPAGATE(launch_head_bwd(h, a, 1, E, st));
   }
+  if (h->comm) {
+    // the dW epilogues are about to reduce-add into peer gradient buffers: every rank must have zeroed its own
+    // (step_begin) first.  One warp; ranks left the previous update together, so this rarely waits.
+    comm::rank_barrier_kernel<<<1, 32, 0, st>>>(h->comm->d_peer_hdr, h->comm->rank, h->comm->world);
+    MTRL_CUDA_CHECK(cudaGetLastError());
+    LAUNCHED(h);
+  }
   MTRL_PROPAGATE(run_trunk_backward(h, h->bwd_critic, h->buf.critic_grads, LC, E, true, st));
   MTRL_PROPAGATE(head_sumsq_to_slot(h, h->buf.critic_grads, LC, ACC_CRITIC_HEAD_G2, st));
   return MTRL_OK;
@@ -562,7 +648,7 @@ int step_critic_apply(mtrl_sac* h, cudaStream_t st) {
     t.g2_trunk_out = w.acc + ACC_CRITIC_G2; t.p2_trunk = w.acc + ACC_CRITIC_P2_TRUNK; t.p2_head = w.acc + ACC_CRITIC_P2_HEAD;
     t.lr = c.critic_lr; t.b1 = c.adam_b1; t.b2 = c.adam_b2; t.eps = c.adam_eps; t.max_norm = c.critic_max_grad_norm;
     t.tau = c.tau;
-    MTRL_PROPAGATE(launch_trunk_step(h, t, h->off_critic_grads, h->off_critic_params, st));
+    MTRL_PROPAGATE(launch_trunk_step(h, t, h->off_critic_grads, h->off_critic_params, h->d_segs_critic, h->nsegs_critic, st));
     finalize_critic_kernel<<<1, 1, 0, st>>>(w.acc, h->buf.critic_grads + LC.slots_off + 1, h->buf.steps, h->buf.logs, 1.f / EB,
                                             loss_scale, 0);
     LAUNCHED(h);
@@ -685,7 +771,7 @@ int step_actor_apply(mtrl_sac* h, cudaStream_t st) {
     t.step = h->buf.steps + 0;
     t.g2_trunk_out = w.acc + ACC_ACTOR_G2; t.p2_trunk = w.acc + ACC_ACTOR_P2_TRUNK; t.p2_head = w.acc + ACC_ACTOR_P2_HEAD;
     t.lr = c.actor_lr; t.b1 = c.adam_b1; t.b2 = c.adam_b2; t.eps = c.adam_eps; t.max_norm = c.actor_max_grad_norm;
-    MTRL_PROPAGATE(launch_trunk_step(h, t, h->off_actor_grads, h->off_actor_params, st));
+    MTRL_PROPAGATE(launch_trunk_step(h, t, h->off_actor_grads, h->off_actor_params, h->d_segs_actor, h->nsegs_actor, st));
     finalize_actor_kernel<<<1, 1, 0, st>>>(w.acc, h->buf.actor_grads + LA.slots_off + 1, h->buf.steps, h->buf.logs,
                                            1.f / static_cast<float>(h->global_batch), 0);
     LAUNCHED(h);
@@ -780,7 +866,7 @@ extern "C" int mtrl_sac_attach_comm(mtrl_sac_t* h, mtrl_comm_t* c, long long off
                                     long long off_critic_params, long long off_actor_params) {
   MTRL_REQUIRE(h && c, "mtrl_sac_attach_comm: null argument");
   MTRL_REQUIRE(h->cfg.variant == MTRL_VARIANT_MTSAC, "mtrl_sac_attach_comm: only the multi-task variant shards");
-  MTRL_REQUIRE(c->opened || c->world == 1, "mtrl_sac_attach_comm: call mtrl_comm_open_peers first");
+  MTRL_REQUIRE(c->opened, "mtrl_sac_attach_comm: call mtrl_comm_open_peers first");
   const long long need_c = h->lay.critic.total * 4, need_a = h->lay.actor.total * 4;
   const struct { const char* name; long long off; long long bytes; const float* ptr; } r[4] = {
       {"critic_grads", off_critic_grads, need_c, h->buf.critic_grads}, {"actor_grads", off_actor_grads, need_a, h->buf.actor_grads},
@@ -791,12 +877,23 @@ extern "C" int mtrl_sac_attach_comm(mtrl_sac_t* h, mtrl_comm_t* c, long long off
     MTRL_REQUIRE(reinterpret_cast<const uint8_t*>(x.ptr) == c->arena + x.off,
                  "mtrl_sac_attach_comm: the handle's %s buffer is not arena + %lld", x.name, x.off);
   }
+  MTRL_REQUIRE(h->cfg.num_critics * (c->world + 1) <= 24,
+               "mtrl_sac_attach_comm: %d critics x %d ranks exceed the problems one grouped GEMM launch holds; use the "
+               "all-reduce exchange", h->cfg.num_critics, c->world);
   h->comm = c;
   h->off_critic_grads = off_critic_grads;
   h->off_actor_grads = off_actor_grads;
   h->off_critic_params = off_critic_params;
   h->off_actor_params = off_actor_params;
-  return MTRL_OK;
+  const std::vector<comm::Segment> sc = trunk_segments(h->lay.critic, c->world), sa = trunk_segments(h->lay.actor, c->world);
+  MTRL_CUDA_CHECK(cudaMalloc(&h->d_segs_critic, sc.size() * sizeof(comm::Segment)));
+  MTRL_CUDA_CHECK(cudaMalloc(&h->d_segs_actor, sa.size() * sizeof(comm::Segment)));
+  MTRL_CUDA_CHECK(cudaMemcpy(h->d_segs_critic, sc.data(), sc.size() * sizeof(comm::Segment), cudaMemcpyHostToDevice));
+  MTRL_CUDA_CHECK(cudaMemcpy(h->d_segs_actor, sa.data(), sa.size() * sizeof(comm::Segment), cudaMemcpyHostToDevice));
+  h->nsegs_critic = static_cast<int>(sc.size());
+  h->nsegs_actor = static_cast<int>(sa.size());
+  // the dW problems now target the owners' buffers
+  return build_backward_plans(h);
 }
 
 extern "C" int mtrl_sac_launches_per_update(const mtrl_sac_t* h) { return h ? h->launches : 0; }
