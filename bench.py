@@ -326,6 +326,7 @@ def main() -> None:
     barrier()
     ms_stream = p0.elapsed_time(p1)
     gemm_ms, gemm_launches = agent.profile_read()
+    xchg_ms, xchg_launches = agent.profile_exchange()
     agent.profile_gemms(False)
 
     # ---------------- timed region 2: end to end through the public API with host buffers ----------------
@@ -404,6 +405,11 @@ def main() -> None:
                          "measured_over": f"{args.steps} steps launched kernel by kernel ({ms_stream / args.steps:.3f} ms/step)",
                          "peak_source": f"{peaks['_source']}: bf16_tflops_sustained / 2 (tcgen05 kind::tf32 runs at half the bf16 rate)",
                          "algorithmic_flops_per_step": flops_rank},
+            "exchange": ({"kernels_per_step": xchg_launches / args.steps, "ms_per_step": xchg_ms / args.steps,
+                          "phase_us": agent.exchange_phase_times(),
+                          "note": "rank 0's fused exchange kernels (barrier waits included), event-bracketed in the roofline pass; "
+                                  "phase_us = in-kernel globaltimer stamps of the last update"}
+                         if world > 1 else None),
             "clocks": clk,
         }
         if emulate:

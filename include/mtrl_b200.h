@@ -225,6 +225,9 @@ int mtrl_sac_launches_per_update(const mtrl_sac_t* h);
  * (enable = 1) and read back their summed duration and count (synchronises on those events). */
 int mtrl_sac_profile_gemms(mtrl_sac_t* h, int enable);
 int mtrl_sac_profile_read(mtrl_sac_t* h, double* total_ms, int* launches);
+/* The exchange kernels (csrc/comm.cuh) bracketed in the same pass: their summed duration and count as of the last
+ * mtrl_sac_profile_read. */
+int mtrl_sac_profile_exchange(mtrl_sac_t* h, double* total_ms, int* launches);
 /* Asynchronous copy of the packing status of the last update into 4 pinned host ints:
  * [0] == 0 ok, 1: a row's task is outside this handle's task range, 2: rows do not fit max_rows. */
 int mtrl_sac_read_status_async(const mtrl_sac_t* h, int* host_pinned4, void* stream);
@@ -249,6 +252,10 @@ void* mtrl_comm_arena(mtrl_comm_t* c);
 int mtrl_comm_open_peers(mtrl_comm_t* c, const unsigned char* handles);
 /* Synchronous read of the arena's error word: 0 ok, otherwise the in-kernel wait that timed out (a peer never came). */
 int mtrl_comm_error(mtrl_comm_t* c, int* code);
+/* Synchronous read of the phase durations (microseconds, CTA 0 of this rank) of the last two fused trunk steps:
+ * us14[0..6] critic, us14[7..13] actor; per set: wait for all ranks' gradients, owned-segment norms, norm exchange,
+ * Adam + all-gather stores, wait for all ranks' stores, derived copies (Polyak / tf32), total. */
+int mtrl_comm_phase_times(mtrl_comm_t* c, double* us14);
 void mtrl_comm_destroy(mtrl_comm_t* c);
 /* Switches a multi-task handle to the fused peer-memory exchange.  The handle's critic_grads, actor_grads,
  * critic_params and actor_params buffers must be arena + the given byte offsets (same offsets on every rank).

@@ -77,6 +77,20 @@ extern "C" int mtrl_comm_error(mtrl_comm_t* c, int* code) {
   return MTRL_OK;
 }
 
+extern "C" int mtrl_comm_phase_times(mtrl_comm_t* c, double* us14) {
+  MTRL_REQUIRE(c && us14, "mtrl_comm_phase_times: null argument");
+  comm::Header h;
+  MTRL_CUDA_CHECK(cudaMemcpy(&h, c->arena, sizeof(h), cudaMemcpyDeviceToHost));
+  // the update runs critic then actor: the older stamp set is the critic's
+  const int first = h.phase_ns[0][0] <= h.phase_ns[1][0] ? 0 : 1;
+  for (int k = 0; k < 2; ++k) {
+    const unsigned long long* t = h.phase_ns[k == 0 ? first : 1 - first];
+    for (int i = 0; i < 6; ++i) us14[k * 7 + i] = t[i + 1] >= t[i] ? (t[i + 1] - t[i]) * 1e-3 : -1.0;
+    us14[k * 7 + 6] = t[6] >= t[0] ? (t[6] - t[0]) * 1e-3 : -1.0;
+  }
+  return MTRL_OK;
+}
+
 extern "C" void mtrl_comm_destroy(mtrl_comm_t* c) {
   if (!c) return;
   for (int q = 0; q < c->world; ++q)

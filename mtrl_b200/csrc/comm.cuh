@@ -29,6 +29,9 @@ struct Header {
   int error;                                      // != 0: a wait timed out (peer missing)
   double shard_g2[2];                             // this rank's shard accumulator, double-buffered by epoch parity
   unsigned int sync_epoch;                        // stamp of the next rank_barrier_kernel (flag[3], starts at 1)
+  unsigned long long phase_ns[2][8];              // [epoch parity][phase]: globaltimer stamps of CTA 0 in the last two
+                                                  // trunk steps: start, barrier 0, norms, barrier 1, Adam + all-gather,
+                                                  // barrier 2, derived copies (mtrl_comm_phase_times)
 };
 
 // Ownership of the replicated trunk: the flat buffer is cut into segments, each stepped (Adam) by exactly one rank.
@@ -57,12 +60,10 @@ __device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long
   asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-// Peer (or peer-written) data: always fetched from the owning GPU's L2, never from a local L1 line.
-__device__ __forceinline__ float4 ld_sys_f4(const float* p) {
-  float4 v;
-  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
-  return v;
-}
+// Bulk peer (or peer-written) data: ld.global.cg -- served by the L2 of the GPU that owns the line (peer memory is
+// not cached in the local L2), never by a possibly stale local L1 line.  A plain intrinsic rather than volatile asm so
+// that the compiler can keep several loads of an unrolled loop in flight.
+__device__ __forceinline__ float4 ld_sys_f4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ double ld_sys_f64(const double* p) {
   double v;
   asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
@@ -180,7 +181,20 @@ __device__ __forceinline__ void adam4(const TrunkStepArgs& a, float scale, float
   }
 }
 
-// shadow = tf32(p); target = tau p + (1 - tau) target; target_shadow = tf32(target); returns |p|^2
+// shadow = tf32(p); target = tau p + (1 - tau) target; target_shadow = tf32(target); returns |p|^2.
+// derived4t takes the already loaded target element.
+__device__ __forceinline__ float derived4t(const TrunkStepArgs& a, long long i4, const float4& p4, float4 t4) {
+  reinterpret_cast<float4*>(a.shadow)[i4] = make_float4(tf32_rna(p4.x), tf32_rna(p4.y), tf32_rna(p4.z), tf32_rna(p4.w));
+  if (a.target) {
+    t4.x = a.tau * p4.x + (1.f - a.tau) * t4.x;
+    t4.y = a.tau * p4.y + (1.f - a.tau) * t4.y;
+    t4.z = a.tau * p4.z + (1.f - a.tau) * t4.z;
+    t4.w = a.tau * p4.w + (1.f - a.tau) * t4.w;
+    reinterpret_cast<float4*>(a.target)[i4] = t4;
+    reinterpret_cast<float4*>(a.target_shadow)[i4] = make_float4(tf32_rna(t4.x), tf32_rna(t4.y), tf32_rna(t4.z), tf32_rna(t4.w));
+  }
+  return p4.x * p4.x + p4.y * p4.y + p4.z * p4.z + p4.w * p4.w;
+}
 __device__ __forceinline__ float derived4(const TrunkStepArgs& a, long long i4, const float4& p4) {
   reinterpret_cast<float4*>(a.shadow)[i4] = make_float4(tf32_rna(p4.x), tf32_rna(p4.y), tf32_rna(p4.z), tf32_rna(p4.w));
   if (a.target) {
@@ -224,10 +238,12 @@ static __global__ void __launch_bounds__(512, 1) trunk_step_kernel(const TrunkSt
   const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
 
+  if (blockIdx.x == 0 && threadIdx.x == 0) H->phase_ns[epoch & 1][0] = globaltimer_ns();
   // ---- barrier 0: every rank's gradient kernels are complete (by stream order, once its kernel runs), so the
   //      reduce-adds they sent into this rank's pre-reduced segments have landed too ----
   if (blockIdx.x == 0 && threadIdx.x < world) st_release_sys(&a.peer_hdr[threadIdx.x]->flag[0][a.rank], epoch);
   wait_ranks(H, 0, world, epoch);
+  if (blockIdx.x == 0 && threadIdx.x == 0) H->phase_ns[epoch & 1][1] = globaltimer_ns();
 
   // ---- owned segments: finish the reduction where the GEMMs have not done it, and take the squared norm ----
   {
@@ -236,6 +252,7 @@ static __global__ void __launch_bounds__(512, 1) trunk_step_kernel(const TrunkSt
       const Segment sg = a.segs[si];
       if (sg.owner != a.rank) continue;
       if (sg.pre_reduced) {
+#pragma unroll 4
         for (long long i = sg.begin4 + tid; i < sg.end4; i += stride) {
           const float4 g4 = ld_sys_f4(a.g + i * 4);   // written by peers' reduce-adds: read at L2
           s += static_cast<double>(g4.x * g4.x + g4.y * g4.y) + static_cast<double>(g4.z * g4.z + g4.w * g4.w);
@@ -251,9 +268,11 @@ static __global__ void __launch_bounds__(512, 1) trunk_step_kernel(const TrunkSt
     s = sac::block_sum(s, red);
     if (threadIdx.x == 0) atomicAdd(&H->shard_g2[epoch & 1], s);
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0) H->phase_ns[epoch & 1][2] = globaltimer_ns();
   // ---- barrier 1: exchange the shard norms and the head norms ----
   grid_arrive_then_signal(a, H, 1, epoch, grid_base + gridDim.x, true);
   wait_ranks(H, 1, world, epoch);
+  if (blockIdx.x == 0 && threadIdx.x == 0) H->phase_ns[epoch & 1][3] = globaltimer_ns();
   if (threadIdx.x == 0) {
     double g2 = 0.0, h2 = 0.0;
     for (int q = 0; q < world; ++q) {
@@ -305,15 +324,29 @@ static __global__ void __launch_bounds__(512, 1) trunk_step_kernel(const TrunkSt
     reinterpret_cast<float4*>(a.p)[i] = p4;
     p2_head += static_cast<double>(derived4(a, i, p4));
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0) H->phase_ns[epoch & 1][4] = globaltimer_ns();
   // ---- barrier 2: every rank has stored its segments everywhere ----
   grid_arrive_then_signal(a, H, 2, epoch, grid_base + 2ull * gridDim.x, false);
   wait_ranks(H, 2, world, epoch);
+  if (blockIdx.x == 0 && threadIdx.x == 0) H->phase_ns[epoch & 1][5] = globaltimer_ns();
 
   // ---- derived copies of the segments the peers own ----
   for (int si = 0; si < a.nsegs; ++si) {
     const Segment sg = a.segs[si];
     if (sg.owner == a.rank) continue;
-    for (long long i = sg.begin4 + tid; i < sg.end4; i += stride) {
+    // two elements per pass: both parameter and both target loads are issued before the dependent stores
+    long long i = sg.begin4 + tid;
+    for (; i + stride < sg.end4; i += 2 * stride) {
+      const float4 pa = ld_sys_f4(a.p + i * 4), pb = ld_sys_f4(a.p + (i + stride) * 4);
+      float4 ta = make_float4(0.f, 0.f, 0.f, 0.f), tb = ta;
+      if (a.target) {
+        ta = reinterpret_cast<const float4*>(a.target)[i];
+        tb = reinterpret_cast<const float4*>(a.target)[i + stride];
+      }
+      p2_trunk += static_cast<double>(derived4t(a, i, pa, ta));
+      p2_trunk += static_cast<double>(derived4t(a, i + stride, pb, tb));
+    }
+    for (; i < sg.end4; i += stride) {
       const float4 p4 = ld_sys_f4(a.p + i * 4);
       p2_trunk += static_cast<double>(derived4(a, i, p4));
     }
@@ -324,6 +357,7 @@ static __global__ void __launch_bounds__(512, 1) trunk_step_kernel(const TrunkSt
     atomicAdd(a.p2_trunk, p2_trunk);
     atomicAdd(a.p2_head, p2_head);
     if (blockIdx.x == 0) {
+      H->phase_ns[epoch & 1][6] = globaltimer_ns();
       H->shard_g2[(epoch + 1) & 1] = 0.0;   // next exchange's accumulator (nobody touches it during this one)
       *reinterpret_cast<volatile unsigned*>(&H->epoch) = epoch + 1;
     }

@@ -133,7 +133,10 @@ struct mtrl_sac {
   // optional CUDA-event bracketing of every GEMM launch (bench.py's live roofline measurement)
   bool prof = false;
   std::vector<cudaEvent_t> ev;
+  std::vector<int> ev_tag;   // per event pair: 0 = GEMM launch, 1 = exchange kernel (trunk step / rank barrier)
   size_t ev_used = 0;
+  double exchange_ms = 0.0;
+  int exchange_launches = 0;
   // fused peer-memory exchange (comm.cuh); null = single GPU, or the caller all-reduces between the phases
   mtrl_comm* comm = nullptr;
   long long off_critic_grads = 0, off_actor_grads = 0, off_critic_params = 0, off_actor_params = 0;
@@ -291,20 +294,30 @@ int build_plans(mtrl_sac* h) {
 
 #define LAUNCHED(h) ((h)->launches++)
 
+int prof_begin(mtrl_sac* h, int tag, cudaStream_t st) {
+  if (!h->prof) return MTRL_OK;
+  while (h->ev.size() < h->ev_used + 2) {
+    cudaEvent_t e;
+    MTRL_CUDA_CHECK(cudaEventCreate(&e));
+    h->ev.push_back(e);
+  }
+  if (h->ev_tag.size() < h->ev.size() / 2) h->ev_tag.resize(h->ev.size() / 2, 0);
+  h->ev_tag[h->ev_used / 2] = tag;
+  MTRL_CUDA_CHECK(cudaEventRecord(h->ev[h->ev_used], st));
+  return MTRL_OK;
+}
+
+int prof_end(mtrl_sac* h, cudaStream_t st) {
+  if (!h->prof) return MTRL_OK;
+  MTRL_CUDA_CHECK(cudaEventRecord(h->ev[h->ev_used + 1], st));
+  h->ev_used += 2;
+  return MTRL_OK;
+}
+
 int run_plan(mtrl_sac* h, mtrl_gemm_plan_t* plan, cudaStream_t st) {
-  if (h->prof) {
-    while (h->ev.size() < h->ev_used + 2) {
-      cudaEvent_t e;
-      MTRL_CUDA_CHECK(cudaEventCreate(&e));
-      h->ev.push_back(e);
-    }
-    MTRL_CUDA_CHECK(cudaEventRecord(h->ev[h->ev_used], st));
-  }
+  MTRL_PROPAGATE(prof_begin(h, 0, st));
   MTRL_PROPAGATE(mtrl_gemm_plan_run(plan, st));
-  if (h->prof) {
-    MTRL_CUDA_CHECK(cudaEventRecord(h->ev[h->ev_used + 1], st));
-    h->ev_used += 2;
-  }
+  MTRL_PROPAGATE(prof_end(h, st));
   LAUNCHED(h);
   return MTRL_OK;
 }
@@ -427,6 +440,7 @@ int launch_trunk_step(mtrl_sac* h, comm::TrunkStepArgs& a, long long off_grads, 
     a.peer_hdr[q] = reinterpret_cast<comm::Header*>(c->peer[q]);
   }
   const dim3 grid(h->sms), block(512);
+  MTRL_PROPAGATE(prof_begin(h, 1, st));
   switch (c->world) {
     case 2: comm::trunk_step_kernel<2><<<grid, block, 0, st>>>(a); break;
     case 4: comm::trunk_step_kernel<4><<<grid, block, 0, st>>>(a); break;
@@ -434,6 +448,7 @@ int launch_trunk_step(mtrl_sac* h, comm::TrunkStepArgs& a, long long off_grads, 
     default: comm::trunk_step_kernel<0><<<grid, block, 0, st>>>(a); break;
   }
   MTRL_CUDA_CHECK(cudaGetLastError());
+  MTRL_PROPAGATE(prof_end(h, st));
   LAUNCHED(h);
   return MTRL_OK;
 }
@@ -622,8 +637,10 @@ int step_critic_grads(mtrl_sac* h, cudaStream_t st) {
   if (h->comm) {
     // the dW epilogues are about to reduce-add into peer gradient buffers: every rank must have zeroed its own
     // (step_begin) first.  One warp; ranks left the previous update together, so this rarely waits.
+    MTRL_PROPAGATE(prof_begin(h, 1, st));
     comm::rank_barrier_kernel<<<1, 32, 0, st>>>(h->comm->d_peer_hdr, h->comm->rank, h->comm->world);
     MTRL_CUDA_CHECK(cudaGetLastError());
+    MTRL_PROPAGATE(prof_end(h, st));
     LAUNCHED(h);
   }
   MTRL_PROPAGATE(run_trunk_backward(h, h->bwd_critic, h->buf.critic_grads, LC, E, true, st));
@@ -908,16 +925,28 @@ extern "C" int mtrl_sac_profile_gemms(mtrl_sac_t* h, int enable) {
 // Sum of the event-bracketed GEMM launch durations since profiling was enabled (synchronises on the events).
 extern "C" int mtrl_sac_profile_read(mtrl_sac_t* h, double* total_ms, int* launches) {
   MTRL_REQUIRE(h && total_ms && launches, "mtrl_sac_profile_read: null argument");
-  double sum = 0.0;
+  double sum = 0.0, xsum = 0.0;
+  int n = 0, xn = 0;
   for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
     MTRL_CUDA_CHECK(cudaEventSynchronize(h->ev[i + 1]));
     float ms = 0.f;
     MTRL_CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]));
-    sum += ms;
+    if (h->ev_tag[i / 2] == 0) { sum += ms; ++n; } else { xsum += ms; ++xn; }
   }
   *total_ms = sum;
-  *launches = static_cast<int>(h->ev_used / 2);
+  *launches = n;
+  h->exchange_ms = xsum;
+  h->exchange_launches = xn;
   h->ev_used = 0;
+  return MTRL_OK;
+}
+
+// Summed duration / count of the exchange kernels (sharded-Adam trunk steps, rank barrier) seen by the last
+// mtrl_sac_profile_read.
+extern "C" int mtrl_sac_profile_exchange(mtrl_sac_t* h, double* total_ms, int* launches) {
+  MTRL_REQUIRE(h && total_ms && launches, "mtrl_sac_profile_exchange: null argument");
+  *total_ms = h->exchange_ms;
+  *launches = h->exchange_launches;
   return MTRL_OK;
 }
 // Device int[4] written by the packing kernel: [0] != 0 means the last batch was rejected

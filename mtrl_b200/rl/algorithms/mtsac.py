@@ -89,11 +89,13 @@ L._EXTRA_DECLS.update({
     "mtrl_sac_read_status_async": ([_vp, _vp, _vp],),
     "mtrl_sac_profile_gemms": ([_vp, _i],),
     "mtrl_sac_profile_read": ([_vp, C.POINTER(C.c_double), C.POINTER(_i)],),
+    "mtrl_sac_profile_exchange": ([_vp, C.POINTER(C.c_double), C.POINTER(_i)],),
     "mtrl_comm_create": ([C.POINTER(_vp), _i, _i, C.c_longlong, _vp],),
     "mtrl_comm_arena": ([_vp], _vp),
     "mtrl_comm_open_peers": ([_vp, _vp],),
     "mtrl_comm_error": ([_vp, C.POINTER(_i)],),
     "mtrl_comm_destroy": ([_vp], None),
+    "mtrl_comm_phase_times": ([_vp, C.POINTER(C.c_double)],),
     "mtrl_sac_attach_comm": ([_vp, _vp, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong],),
 })
 
@@ -485,6 +487,21 @@ class MTSAC:
         """(sum of GEMM-launch durations in ms, number of GEMM launches) since profile_gemms(True)."""
         ms, n = C.c_double(), _i()
         L.check(L.lib().mtrl_sac_profile_read(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def exchange_phase_times(self) -> dict | None:
+        """Microseconds spent in each phase of the last critic / actor trunk step on this rank (synchronises)."""
+        if getattr(self, "_comm", None) is None:
+            return None
+        buf = (C.c_double * 14)()
+        L.check(L.lib().mtrl_comm_phase_times(self._comm, buf))
+        names = ("wait_grads", "norms", "norm_exchange", "adam_allgather", "wait_stores", "derived", "total")
+        return {"critic": dict(zip(names, list(buf)[:7])), "actor": dict(zip(names, list(buf)[7:]))}
+
+    def profile_exchange(self) -> tuple[float, int]:
+        """(sum of exchange-kernel durations in ms, their count) as of the last profile_read()."""
+        ms, n = C.c_double(), _i()
+        L.check(L.lib().mtrl_sac_profile_exchange(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
     def sample_action(self, observation):
