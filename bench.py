@@ -262,8 +262,24 @@ def main() -> None:
     B_local = per_task * T_local
     mcfg, env = metaworld_mtmhsac(T, W)
     exchange = "local" if emulate else os.environ.get("MTRL_EXCHANGE", "p2p")
-    agent = MTSAC.initialize(mcfg, env, seed=1, max_batch=B_local, rank=rank, world_size=emulate or world, process_group=pg,
-                             exchange=exchange)
+    def make_agent(ex):
+        return MTSAC.initialize(mcfg, env, seed=1, max_batch=B_local, rank=rank, world_size=emulate or world,
+                                process_group=pg, exchange=ex)
+    agent, err = None, None
+    try:
+        agent = make_agent(exchange)
+    except Exception as e:  # noqa: BLE001  (CUDA IPC unavailable on this box: the all-reduce exchange still works)
+        if world == 1 or exchange != "p2p":
+            raise
+        err = e
+    if world > 1 and exchange == "p2p":
+        ok = torch.tensor([0 if agent is None else 1], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            print(f"rank {rank}: peer-memory exchange unavailable ({err}); ALL ranks fall back to the NCCL all-reduce exchange",
+                  file=sys.stderr, flush=True)
+            exchange = "nccl"
+            agent = make_agent(exchange)
     buf = MultiTaskReplayBuffer(args.capacity * T_local, T_local, _Space((39 + T,)), _Space((4,)), seed=1)
     synthetic_fill(buf, T_local, t0, T, seed=1234 + rank)
 
