@@ -219,6 +219,13 @@ int mtrl_sac_phase1_critic_grads(mtrl_sac_t* h, const float* obs, const float* a
                                  const float* eps_c, const float* eps_a, void* stream);
 int mtrl_sac_phase2_critic_step_actor_grads(mtrl_sac_t* h, void* stream);
 int mtrl_sac_phase3_actor_step_alpha(mtrl_sac_t* h, void* stream);
+/* MTSAC.sample_action / eval_action (mtsac.py:70-84, 299-311): actions for n observation rows (device fp32
+ * (n, obs_dim), any owned tasks, n <= max_rows).  deterministic = 0: a = tanh(mu + sigma eps) with eps = device
+ * (n, action_dim) standard normal draws or NULL for in-kernel Philox; deterministic = 1: the mode tanh(mu)
+ * (nn/distributions.py:15-16).  actions_out: device fp32 (n, action_dim).  Rows of a task this handle does not own
+ * set the status word (mtrl_sac_read_status_async) and come back as zeros.  Not re-entrant with mtrl_sac_update. */
+int mtrl_sac_act(mtrl_sac_t* h, const float* obs, int n, const float* eps, int deterministic, float* actions_out,
+                 void* stream);
 /* Number of kernels one mtrl_sac_update launches (for bench.py's gpu_launches). */
 int mtrl_sac_launches_per_update(const mtrl_sac_t* h);
 /* Bracket every GEMM launch of the following updates with CUDA events on the launch stream
@@ -262,6 +269,11 @@ void mtrl_comm_destroy(mtrl_comm_t* c);
  * Afterwards mtrl_sac_update runs the whole sharded update with no host-visible exchange points. */
 int mtrl_sac_attach_comm(mtrl_sac_t* h, mtrl_comm_t* c, long long off_critic_grads, long long off_actor_grads,
                          long long off_critic_params, long long off_actor_params);
+
+/* Checkpoint support for the sharded exchange: writes 1.0 / 0.0 over [0, trunk_total) of the actor (critic = 0) or
+ * critic (critic = 1) layout -- 1.0 where THIS handle holds the live Adam moments (everything without an attached
+ * arena).  sum over ranks of mask * moments is the full optimiser state of the reference's TrainState.  Synchronises. */
+int mtrl_sac_trunk_owner_mask(mtrl_sac_t* h, int critic, float* mask_dev);
 
 /* ------------------------------------------------------------------------------------------
  * MT-PPO update.  Replaces MTPPO.update / _update_inner (mtrl/rl/algorithms/mtppo.py:292-317):
@@ -314,6 +326,17 @@ int mtrl_ppo_refresh_shadows(mtrl_ppo_t* h, void* stream);
 int mtrl_ppo_update(mtrl_ppo_t* h, const float* obs, const float* log_probs, const float* advantages,
                     const float* returns, const float* values, const float* eps, void* stream);
 int mtrl_ppo_launches_per_update(const mtrl_ppo_t* h);
+
+/* ------------------------------------------------------------------------------------------
+ * Rollout advantages.  Replaces the GAE loop of MultiTaskRolloutBuffer.get (mtrl/rl/buffers.py:650-707).
+ * rewards / values / dones / advantages / returns: device fp32 (num_steps, num_tasks[, 1]) in the reference's
+ * storage order; last_values / last_dones: device fp32 (num_tasks).  The last step bootstraps from the `dones`
+ * argument (the reference reads the whole self.dones array there and cannot run for num_steps > 1).
+ * Bit-identical to NumPy's float32 evaluation order.
+ * ------------------------------------------------------------------------------------------ */
+int mtrl_gae(const float* rewards, const float* values, const float* dones, const float* last_values,
+             const float* last_dones, int num_steps, int num_tasks, float gamma, float gae_lambda, float* advantages,
+             float* returns, void* stream);
 
 #ifdef __cplusplus
 }

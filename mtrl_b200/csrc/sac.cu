@@ -6,6 +6,7 @@
 //   alpha  step (:713-731)  uses log-probs of the OLD actor (the ones the actor loss sampled)
 // Networks: MultiHeadNetwork (mtrl/nn/multi_head.py:21-68) trunk Dense+ReLU layers as tcgen05 GEMMs,
 // own-task heads as CUDA-core row dots; critic input is (action, state) (mtrl/rl/networks.py:61).
+#include <map>
 #include <vector>
 
 #include "comm.cuh"
@@ -140,6 +141,8 @@ struct mtrl_sac {
   // fused peer-memory exchange (comm.cuh); null = single GPU, or the caller all-reduces between the phases
   mtrl_comm* comm = nullptr;
   long long off_critic_grads = 0, off_actor_grads = 0, off_critic_params = 0, off_actor_params = 0;
+  std::map<int, std::vector<mtrl_gemm_plan_t*>> act_plans;   // actor forward plans of mtrl_sac_act, by row count
+  unsigned long long act_calls = 0;
   comm::Segment *d_segs_critic = nullptr, *d_segs_actor = nullptr;   // ownership tables (device)
   int nsegs_critic = 0, nsegs_actor = 0;
 };
@@ -330,6 +333,7 @@ int launch_actor_head(mtrl_sac* h, const float* H, const float* eps, float* Xdst
   a.bh = hb(h->buf.actor_params, h->lay.actor, 0);
   a.tile_task = h->ws.tile_task;
   a.slot_src = h->ws.slot_src;
+  a.row_task = nullptr;
   a.eps = eps;
   a.Xdst = Xdst;
   a.ldx = h->lay.k_critic;
@@ -512,6 +516,8 @@ extern "C" void mtrl_sac_destroy(mtrl_sac_t* h) {
   if (!h) return;
   for (auto* v : {&h->fwd, &h->fwd_target, &h->bwd_critic, &h->fwd_pi, &h->bwd_pi, &h->bwd_actor})
     for (auto* p : *v) mtrl_gemm_plan_destroy(p);
+  for (auto& kv : h->act_plans)
+    for (auto* p : kv.second) mtrl_gemm_plan_destroy(p);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   if (h->d_segs_critic) cudaFree(h->d_segs_critic);
   if (h->d_segs_actor) cudaFree(h->d_segs_actor);
@@ -911,6 +917,78 @@ extern "C" int mtrl_sac_attach_comm(mtrl_sac_t* h, mtrl_comm_t* c, long long off
   h->nsegs_actor = static_cast<int>(sa.size());
   // the dW problems now target the owners' buffers
   return build_backward_plans(h);
+}
+
+// Policy actions for arbitrary observations (ContinuousActionPolicy + TanhMultivariateNormalDiag, mtsac.py:70-84,
+// 299-311): a = tanh(mu + sigma eps) (sample) or tanh(mu) (mode).  Uses the update's actor buffers as scratch.
+extern "C" int mtrl_sac_act(mtrl_sac_t* h, const float* obs, int n, const float* eps, int deterministic, float* actions_out,
+                            void* stream) {
+  MTRL_REQUIRE(h && obs && actions_out, "mtrl_sac_act: null argument");
+  const mtrl_sac_config_t& c = h->cfg;
+  MTRL_REQUIRE(n >= 1 && n <= c.max_rows, "mtrl_sac_act: %d rows outside [1, max_rows = %d]", n, c.max_rows);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Workspace& w = h->ws;
+  const mtrl_net_layout_t& LA = h->lay.actor;
+  const int W = c.width, D = c.depth, Ka = h->lay.k_actor;
+  auto it = h->act_plans.find(n);
+  if (it == h->act_plans.end()) {
+    std::vector<mtrl_gemm_plan_t*> plans;
+    for (int l = 0; l < D; ++l) {
+      std::vector<mtrl_gemm_problem_t> p;
+      p.push_back(fwd_problem(l == 0 ? w.Xa : w.Ao[l - 1], l == 0 ? Ka : W, l == 0 ? LA.in_dim : W, tk(h->buf.actor_shadow, LA, 0, l),
+                              tb(h->buf.actor_params, LA, 0, l), w.Ao[l], n, W));
+      MTRL_PROPAGATE(make_plan(plans, p));
+    }
+    it = h->act_plans.emplace(n, plans).first;
+  }
+  MTRL_CUDA_CHECK(cudaMemsetAsync(w.status, 0, 16, st));
+  act_pack_kernel<<<n, 128, 0, st>>>(obs, n, c.obs_dim, Ka, c.num_tasks, c.task_begin, c.num_local_tasks, eps, deterministic,
+                                     c.action_dim, c.noise_seed, h->act_calls++, w.Xa, w.slot_src, w.eps_a, w.status);
+  MTRL_CUDA_CHECK(cudaGetLastError());
+  for (auto* plan : it->second) MTRL_PROPAGATE(mtrl_gemm_plan_run(plan, st));
+  ActorHeadArgs a;
+  memset(&a, 0, sizeof(a));
+  a.H = w.Ao[D - 1];
+  a.Wh = hk(h->buf.actor_params, LA, 0);
+  a.bh = hb(h->buf.actor_params, LA, 0);
+  a.row_task = w.slot_src;
+  a.eps = w.eps_a;
+  a.act = actions_out;
+  a.logp = w.logp;
+  a.M = n;
+  a.W = W;
+  a.ls_min = c.log_std_min;
+  a.ls_max = c.log_std_max;
+  const int wpb = 8;
+  dim3 grid((n + wpb - 1) / wpb), block(wpb * 32);
+  switch (c.action_dim) {
+    case 1: actor_head_kernel<1><<<grid, block, 0, st>>>(a); break;
+    case 2: actor_head_kernel<2><<<grid, block, 0, st>>>(a); break;
+    case 3: actor_head_kernel<3><<<grid, block, 0, st>>>(a); break;
+    case 4: actor_head_kernel<4><<<grid, block, 0, st>>>(a); break;
+    case 5: actor_head_kernel<5><<<grid, block, 0, st>>>(a); break;
+    case 6: actor_head_kernel<6><<<grid, block, 0, st>>>(a); break;
+    case 7: actor_head_kernel<7><<<grid, block, 0, st>>>(a); break;
+    default: actor_head_kernel<8><<<grid, block, 0, st>>>(a); break;
+  }
+  MTRL_CUDA_CHECK(cudaGetLastError());
+  return MTRL_OK;
+}
+
+// 1.0 over the trunk elements whose Adam moments this handle holds live (all of them unless the sharded exchange is
+// attached, then the segments it owns), 0.0 elsewhere: lets the host assemble the full optimiser state from the ranks
+// (sum over ranks of mask * moments) for a checkpoint.  Synchronises.
+extern "C" int mtrl_sac_trunk_owner_mask(mtrl_sac_t* h, int critic, float* mask_dev) {
+  MTRL_REQUIRE(h && mask_dev, "mtrl_sac_trunk_owner_mask: null argument");
+  const mtrl_net_layout_t& L = critic ? h->lay.critic : h->lay.actor;
+  std::vector<float> mask(static_cast<size_t>(L.trunk_total), h->comm ? 0.f : 1.f);
+  if (h->comm) {
+    for (const comm::Segment& sg : trunk_segments(L, h->comm->world))
+      if (sg.owner == h->comm->rank)
+        for (long long i = sg.begin4 * 4; i < sg.end4 * 4; ++i) mask[static_cast<size_t>(i)] = 1.f;
+  }
+  MTRL_CUDA_CHECK(cudaMemcpy(mask_dev, mask.data(), mask.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return MTRL_OK;
 }
 
 extern "C" int mtrl_sac_launches_per_update(const mtrl_sac_t* h) { return h ? h->launches : 0; }

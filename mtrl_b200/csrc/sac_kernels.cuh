@@ -210,6 +210,53 @@ static __global__ void pack_rows_kernel(const PackArgs a) {
   }
 }
 
+// Action sampling (mtsac.py:70-84, 299-311): observations of any tasks, one block per row.  Writes the tf32 actor
+// input row, the row's task (first arg-max of the trailing one-hot, relative to this handle's first task; -1 and
+// status 1 if it is not owned here) and the row's noise: caller's eps, zeros (mode) or Philox.
+static __global__ void act_pack_kernel(const float* __restrict__ obs, int n, int obs_dim, int Ka, int T, int task_begin,
+                                       int T_local, const float* __restrict__ eps_in, int deterministic, int A,
+                                       unsigned long long seed, unsigned long long call, float* __restrict__ Xa,
+                                       int* __restrict__ row_task, float* __restrict__ eps_out, int* __restrict__ status) {
+  const int row = blockIdx.x;
+  const float* o = obs + static_cast<long long>(row) * obs_dim;
+  float* xa = Xa + static_cast<long long>(row) * Ka;
+  for (int j = threadIdx.x; j < Ka; j += blockDim.x) xa[j] = j < obs_dim ? tf32_rna(o[j]) : 0.f;
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    const float* oh = o + (obs_dim - T);
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int t = lane; t < T; t += 32) {
+      const float v = oh[t];
+      if (v > best) { best = v; bi = t; }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) {
+      int task = bi - task_begin;
+      if (task < 0 || task >= T_local) { atomicExch(status, 1); task = -1; }
+      row_task[row] = task;
+      if (eps_in) {
+        for (int d = 0; d < A; ++d) eps_out[row * A + d] = eps_in[static_cast<long long>(row) * A + d];
+      } else if (deterministic) {
+        for (int d = 0; d < A; ++d) eps_out[row * A + d] = 0.f;
+      } else {
+        // subsequences above 2^40 are never used by the update's noise (one subsequence per batch row)
+        curandStatePhilox4_32_10_t st;
+        curand_init(seed, (1ull << 40) + static_cast<unsigned long long>(row), call * 8ull, &st);
+        for (int d = 0; d < A; d += 4) {
+          const float4 z = curand_normal4(&st);
+          const float zz[4] = {z.x, z.y, z.z, z.w};
+          for (int q = 0; q < 4 && d + q < A; ++q) eps_out[row * A + d + q] = zz[q];
+        }
+      }
+    }
+  }
+}
+
 // alpha_t = exp(log_alpha_t) (MultiTaskTemperature, mtsac.py:60-63); w_t = T * softmax(-log_alpha)_t
 // (extract_task_weights, mtsac.py:103-113) or 1.
 static __global__ void alpha_prep_kernel(const float* __restrict__ log_alpha, int T_local, int use_w, float* __restrict__ alpha_val,
@@ -246,6 +293,8 @@ struct ActorHeadArgs {
   const float* bh;       // (T_local, 2A)
   const int* tile_task;
   const int* slot_src;
+  const int* row_task;   // optional: task of every row (< 0 = skip) instead of tile_task / slot_src (action sampling, where
+                         // rows are not packed into per-task tiles)
   const float* eps;      // [M][A] packed
   float* Xdst;           // critic input buffer whose columns [0, A) receive tf32(a)
   int ldx;
@@ -262,8 +311,8 @@ static __global__ void actor_head_kernel(const ActorHeadArgs p) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= p.M) return;
-  const bool valid = p.slot_src[row] >= 0;
-  const int t = p.tile_task[row / kTileRows];
+  const bool valid = p.row_task ? p.row_task[row] >= 0 : p.slot_src[row] >= 0;
+  const int t = p.row_task ? max(p.row_task[row], 0) : p.tile_task[row / kTileRows];
   float acc[2 * A];
 #pragma unroll
   for (int j = 0; j < 2 * A; ++j) acc[j] = 0.f;

@@ -87,6 +87,8 @@ L._EXTRA_DECLS.update({
     "mtrl_sac_phase3_actor_step_alpha": ([_vp, _vp],),
     "mtrl_sac_launches_per_update": ([_vp],),
     "mtrl_sac_read_status_async": ([_vp, _vp, _vp],),
+    "mtrl_sac_act": ([_vp, _vp, _i, _vp, _i, _vp, _vp],),
+    "mtrl_sac_trunk_owner_mask": ([_vp, _i, _vp],),
     "mtrl_sac_profile_gemms": ([_vp, _i],),
     "mtrl_sac_profile_read": ([_vp, C.POINTER(C.c_double), C.POINTER(_i)],),
     "mtrl_sac_profile_exchange": ([_vp, C.POINTER(C.c_double), C.POINTER(_i)],),
@@ -504,8 +506,125 @@ class MTSAC:
         L.check(L.lib().mtrl_sac_profile_exchange(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
-    def sample_action(self, observation):
-        raise NotImplementedError("action sampling (mtsac.py:299-304) is env-side; SURVEY 8(f) row 2")
+    # ------------------------------------------------------------------ checkpoints
+    def _full_moments(self, prefix: str, critic: bool) -> dict[str, torch.Tensor]:
+        """Adam moments of one network with the trunk part complete on every rank: under the sharded exchange a rank
+        only keeps the moments of the trunk segments it owns, so they are summed over ranks (mask * moments)."""
+        out = {k: self._flat[f"{prefix}_{k}"] for k in ("m", "v")}
+        if self.exchange != "p2p":
+            return out
+        import torch.distributed as dist
 
-    def eval_action(self, observations):
-        raise NotImplementedError("eval_action (mtsac.py:306-311) is env-side; SURVEY 8(f) row 2")
+        lay = self._lay.critic if critic else self._lay.actor
+        mask = torch.empty(lay.trunk_total, dtype=torch.float32, device=self.device)
+        L.check(L.lib().mtrl_sac_trunk_owner_mask(self._h, int(critic), _vp(mask.data_ptr())))
+        full = {}
+        for k, flat in out.items():
+            f = flat.clone()
+            f[: lay.trunk_total] *= mask
+            dist.all_reduce(f[: lay.trunk_total], group=self.process_group)
+            full[k] = f
+        return full
+
+    def state_dict(self) -> dict:
+        """The agent as a host pytree in the reference's own names, the structure `ocp.args.PyTreeSave(agent)` writes
+        (mtrl/checkpoint.py:39-44, 66): `actor` / `critic` / `alpha` TrainStates (mtrl/rl/algorithms/utils.py:11-46) with
+        `step`, Flax-named `params` (`MultiHeadNetwork_0/layer_i/{kernel,bias}`, `VmapDense_0`; critic under
+        `VmapQValueFunction_0` with a leading ensemble axis, plus `target_params`) and the optax state of
+        `chain(clip_by_global_norm, adam)` as `opt_state = {"count", "mu", "nu"}`; `key` carries the Philox
+        counter.  Leaves are NumPy arrays.  With several ranks every rank calls this (collective); heads / log_alpha
+        are the rank's own tasks `[task_begin, task_end)`."""
+        def host(tree):
+            return {k: host(v) if isinstance(v, dict) else v.detach().cpu().numpy().copy() for k, v in tree.items()}
+
+        def views(flat, lay, in_dim, ens):
+            return self._wrap_tree(flat, lay, in_dim, ens)
+
+        c = self._cfg
+        out = {}
+        for name, prefix, lay, in_dim, ens, idx in (("actor", "actor", self._lay.actor, c.obs_dim, False, 0),
+                                                    ("critic", "critic", self._lay.critic, c.action_dim + c.obs_dim, True, 1)):
+            mom = self._full_moments(prefix, ens)
+            ts = {"step": int(self._steps[idx]), "params": host(views(self._flat[f"{prefix}_params"], lay, in_dim, ens)),
+                  "opt_state": {"count": int(self._steps[idx]), "mu": host(views(mom["m"], lay, in_dim, ens)),
+                                "nu": host(views(mom["v"], lay, in_dim, ens))}}
+            if ens:
+                ts["target_params"] = host(views(self._flat["critic_target"], lay, in_dim, ens))
+            out[name] = ts
+        out["alpha"] = {"step": int(self._steps[2]), "params": host(self.alpha.params),
+                        "opt_state": {"count": int(self._steps[2]), "mu": host(self.alpha.opt_state["mu"]),
+                                      "nu": host(self.alpha.opt_state["nu"])}}
+        out["key"] = {"noise_counter": int(self._steps[3]), "seed": int(c.noise_seed)}
+        out["task_range"] = (self.task_begin, self.task_end)
+        return out
+
+    def _wrap_tree(self, flat, lay, in_dim, ens):
+        return _wrap(_views(flat, lay, in_dim, ens), ens)
+
+    def load_state_dict(self, state: dict) -> None:
+        """Inverse of `state_dict` (also accepts a tree exported by the reference through `jax.device_get`, whose
+        leaves have the same names and shapes; full-T head tensors are sliced to this rank's tasks)."""
+        c = self._cfg
+        T_local = self.task_end - self.task_begin
+
+        def put(dst, src, ens):
+            for k, v in src.items():
+                if isinstance(v, dict):
+                    put(dst[k], v, ens)
+                    continue
+                t = torch.as_tensor(np.asarray(v), dtype=torch.float32)
+                if t.shape != dst[k].shape:   # a full-T head tensor: keep this rank's tasks
+                    axis = 1 if ens else 0
+                    t = t.narrow(axis, self.task_begin, T_local)
+                dst[k].copy_(t)
+
+        for name, prefix, lay, in_dim, ens, idx in (("actor", "actor", self._lay.actor, c.obs_dim, False, 0),
+                                                    ("critic", "critic", self._lay.critic, c.action_dim + c.obs_dim, True, 1)):
+            ts = state[name]
+            put(self._wrap_tree(self._flat[f"{prefix}_params"], lay, in_dim, ens), ts["params"], ens)
+            put(self._wrap_tree(self._flat[f"{prefix}_m"], lay, in_dim, ens), ts["opt_state"]["mu"], ens)
+            put(self._wrap_tree(self._flat[f"{prefix}_v"], lay, in_dim, ens), ts["opt_state"]["nu"], ens)
+            if ens:
+                put(self._wrap_tree(self._flat["critic_target"], lay, in_dim, ens), ts["target_params"], ens)
+            self._steps[idx] = int(ts["opt_state"]["count"])
+        a = state["alpha"]
+        for dst, src in ((self.alpha.params, a["params"]), (self.alpha.opt_state["mu"], a["opt_state"]["mu"]),
+                         (self.alpha.opt_state["nu"], a["opt_state"]["nu"])):
+            t = torch.as_tensor(np.asarray(src["params"]["log_alpha"]), dtype=torch.float32)
+            if t.shape[0] != T_local:
+                t = t[self.task_begin:self.task_end]
+            dst["params"]["log_alpha"].copy_(t)
+        self._steps[2] = int(a["opt_state"]["count"])
+        if "key" in state and isinstance(state["key"], dict):
+            self._steps[3] = int(state["key"].get("noise_counter", 0))
+        self.refresh()
+
+    def act_device(self, observation, eps=None, deterministic: bool = False) -> torch.Tensor:
+        """Actions for `observation` (n, obs_dim) as a CUDA tensor (n, action_dim), without synchronising the host:
+        tanh(mu + sigma eps) with `eps` (n, action_dim) or in-kernel Philox noise, or the mode tanh(mu)."""
+        obs = self._dev(observation)
+        if obs.dim() == 1:
+            obs = obs[None]
+        n = obs.shape[0]
+        assert obs.shape[1] == self._cfg.obs_dim
+        e = self._dev(eps) if eps is not None else None
+        out = torch.empty(n, self._cfg.action_dim, dtype=torch.float32, device=self.device)
+        L.check(L.lib().mtrl_sac_act(self._h, _vp(obs.data_ptr()), n, _vp(e.data_ptr() if e is not None else None),
+                                     int(deterministic), _vp(out.data_ptr()), _vp(L.current_stream_ptr())))
+        L.check(L.lib().mtrl_sac_read_status_async(self._h, _vp(self._status_host.data_ptr()), _vp(L.current_stream_ptr())))
+        self._status_event.record()
+        self._pending_status = True
+        return out
+
+    def sample_action(self, observation, task_ids=None, eps=None):
+        """mtsac.py:299-304: `(self, action)` with the action on the host as a NumPy array (the reference returns
+        `jax.device_get(action)`).  Noise: in-kernel Philox, or `eps` for a reproducible draw."""
+        a = self.act_device(observation, eps=eps).cpu().numpy()
+        self._check_status()
+        return self, a
+
+    def eval_action(self, observations, task_ids=None):
+        """mtsac.py:306-311: the mode of the tanh-Gaussian, tanh(mu) (nn/distributions.py:15-16), as a NumPy array."""
+        a = self.act_device(observations, deterministic=True).cpu().numpy()
+        self._check_status()
+        return a

@@ -136,6 +136,9 @@ class SAC(MTSAC):
         self._create_handle()
         return self
 
+    def _wrap_tree(self, flat, lay, in_dim, ens):   # state_dict / load_state_dict use the MLP's Flax names
+        return _wrap(_mlp_views(flat, lay, in_dim, ens), ens)
+
     def get_num_params(self) -> dict[str, int]:
         c = self._cfg
 

@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from .. import _lib as L
-from ..types import ReplayBufferCheckpoint, ReplayBufferSamples
+from ..types import ReplayBufferCheckpoint, ReplayBufferSamples, Rollout
 
 _vp, _i, _u32 = C.c_void_p, C.c_int, C.c_uint32
 L._EXTRA_DECLS.update({
@@ -362,3 +362,93 @@ class ReplayBuffer:
             assert k in d
             d[k] = np.asarray(d[k])[:, None]
         self._mt.load_checkpoint({"data": d, "rng_state": ckpt["rng_state"]})
+
+
+L._EXTRA_DECLS.update({
+    "mtrl_gae": ([_vp, _vp, _vp, _vp, _vp, _i, _i, C.c_float, C.c_float, _vp, _vp, _vp],),
+})
+
+
+class MultiTaskRolloutBuffer:
+    """Device-resident mirror of `mtrl.rl.buffers.MultiTaskRolloutBuffer` (/root/reference/mtrl/rl/buffers.py:552-707):
+    same constructor, attributes (`observations`, `actions`, `rewards`, `dones`, `values`, `log_probs`, `means`, `stds`
+    as (timestep, task, dim) fp32 arrays -- CUDA tensors here -- `pos`, `ready`) and methods.  `get` returns a
+    `Rollout` of (task, timestep, dim) CUDA views; advantages come from the CUDA scan `mtrl_gae` (csrc/rollout.cu),
+    bit-identical to NumPy's float32 evaluation of the reference loop.
+
+    The reference's `get` cannot run (see oracle/rollout_oracle.py); this implements what its annotations and the
+    upstream loop it cites say: fields transposed to (task, timestep, dim), last step bootstrapped from `dones`."""
+
+    def __init__(self, num_rollout_steps: int, num_tasks: int, env_obs_space, env_action_space, seed: int | None = None,
+                 device: str | torch.device | None = None) -> None:
+        if not torch.cuda.is_available():
+            raise L.MtrlError("MultiTaskRolloutBuffer needs a CUDA device; there is no CPU fallback")
+        L.lib()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.num_rollout_steps, self.num_tasks = num_rollout_steps, num_tasks
+        self._rng = np.random.default_rng(seed)
+        self._obs_shape = int(np.array(env_obs_space.shape).prod())
+        self._action_shape = int(np.array(env_action_space.shape).prod())
+        self.reset()
+
+    def reset(self) -> None:   # buffers.py:582-605
+        S, T = self.num_rollout_steps, self.num_tasks
+        f = lambda d: torch.zeros(S, T, d, dtype=torch.float32, device=self.device)  # noqa: E731
+        self.observations, self.actions = f(self._obs_shape), f(self._action_shape)
+        self.rewards, self.dones, self.log_probs, self.values = f(1), f(1), f(1), f(1)
+        self.means, self.stds = f(self._action_shape), f(self._action_shape)
+        self.pos = 0
+        self._values_pushed = False
+
+    @property
+    def ready(self) -> bool:
+        return self.pos == self.num_rollout_steps
+
+    def _row(self, x, shape) -> torch.Tensor:
+        if isinstance(x, torch.Tensor):
+            return x.detach().to(device=self.device, dtype=torch.float32, non_blocking=True).reshape(shape)
+        return torch.as_tensor(np.ascontiguousarray(np.asarray(x, dtype=np.float32))).to(self.device).reshape(shape)
+
+    def add(self, obs, action, reward, done, value=None, log_prob=None, mean=None, std=None) -> None:
+        """buffers.py:611-648.  Inputs may be NumPy arrays or torch tensors (host or CUDA)."""
+        assert obs.ndim == 2 and action.ndim == 2 and reward.ndim <= 2 and done.ndim <= 2
+        assert obs.shape[0] == action.shape[0] == reward.shape[0] == done.shape[0] == self.num_tasks
+        if self.pos >= self.num_rollout_steps:
+            raise IndexError(f"index {self.pos} is out of bounds for axis 0 with size {self.num_rollout_steps}")
+        T, p = self.num_tasks, self.pos
+        self.observations[p] = self._row(obs, (T, self._obs_shape))
+        self.actions[p] = self._row(action, (T, self._action_shape))
+        self.rewards[p] = self._row(reward, (T, 1))
+        self.dones[p] = self._row(done, (T, 1))
+        if value is not None:
+            self.values[p] = self._row(value, (T, 1))
+            self._values_pushed = True
+        if log_prob is not None:
+            self.log_probs[p] = self._row(log_prob, (T, 1))
+        if mean is not None:
+            self.means[p] = self._row(mean, (T, self._action_shape))
+        if std is not None:
+            self.stds[p] = self._row(std, (T, self._action_shape))
+        self.pos += 1
+
+    def get(self, compute_advantages: bool, last_values=None, dones=None, gamma: float = 0.99,
+            gae_lambda: float = 0.97) -> Rollout:
+        """buffers.py:650-707."""
+        returns = advantages = None
+        if compute_advantages:
+            assert last_values is not None, "Must provide final value estimates if compute_advantages=True."
+            assert dones is not None, "Must provide final value estimates if compute_advantages=True."
+            # the reference asserts `not np.all(values == 0)`; checked without a device round trip
+            assert self._values_pushed, "Values must have been pushed to the buffer if compute_advantages=True."
+            S, T = self.num_rollout_steps, self.num_tasks
+            lv = self._row(last_values, (T,)).contiguous()
+            ld = self._row(dones, (T,)).contiguous()
+            adv = torch.empty_like(self.rewards)
+            ret = torch.empty_like(self.rewards)
+            L.check(L.lib().mtrl_gae(_vp(self.rewards.data_ptr()), _vp(self.values.data_ptr()), _vp(self.dones.data_ptr()),
+                                     _vp(lv.data_ptr()), _vp(ld.data_ptr()), S, T, float(gamma), float(gae_lambda),
+                                     _vp(adv.data_ptr()), _vp(ret.data_ptr()), _vp(L.current_stream_ptr())))
+            returns, advantages = ret.transpose(0, 1), adv.transpose(0, 1)
+        tr = lambda x: x.transpose(0, 1)  # noqa: E731
+        return Rollout(tr(self.observations), tr(self.actions), tr(self.rewards), tr(self.dones), tr(self.log_probs),
+                       tr(self.means), tr(self.stds), tr(self.values), returns, advantages)

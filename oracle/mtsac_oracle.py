@@ -205,6 +205,16 @@ def actor_sample_and_log_prob(p: dict, obs: torch.Tensor, eps: torch.Tensor, cfg
     return torch.tanh(x), base_lp - fldj
 
 
+def actor_action(p: dict, obs: torch.Tensor, cfg: OracleConfig, eps: torch.Tensor | None = None) -> torch.Tensor:
+    """`_sample_action` / `_eval_action` (mtsac.py:70-84): dist.sample() = tanh(mu + sigma eps) for the given draw, or
+    with eps=None TanhMultivariateNormalDiag.mode() = tanh(mu) (mtrl/nn/distributions.py:15-16)."""
+    out = multihead_forward(p, obs, cfg.num_tasks, cfg.depth, False, cfg.matmul_operands)
+    mean, log_std = out[..., : cfg.action_dim], out[..., cfg.action_dim:]
+    if eps is None:
+        return torch.tanh(mean)
+    return torch.tanh(mean + torch.exp(torch.clamp(log_std, cfg.log_std_min, cfg.log_std_max)) * eps)
+
+
 # --------------------------------------------------------------------------------------------
 # Optimiser: optax.chain(clip_by_global_norm(max), adam(lr, eps)) (mtrl/config/optim.py:26-43),
 # applied by TrainState.apply_gradients (mtrl/rl/algorithms/utils.py:11-46).
