@@ -100,6 +100,9 @@ int mtrl_sampler_add(mtrl_sampler_t* s, int pos, const float* obs, const float* 
 int mtrl_sampler_sample(mtrl_sampler_t* s, int fill, int n_per_task, long long* idx_out, float* obs_out,
                         float* actions_out, float* next_obs_out, float* dones_out, float* rewards_out,
                         int norm_mode, const double* shift, const double* den, void* stream);
+/* The index draw alone, `rng.integers(0, high, size=n)` (buffers.py:523-527): n device int64 values, generator advanced
+ * exactly as numpy's PCG64 + 32-bit Lemire rejection does.  1 <= high < 2^32, n <= the sampler's index capacity. */
+int mtrl_sampler_draw(mtrl_sampler_t* s, unsigned long long high, int n, long long* idx_out, void* stream);
 /* buffers.py:496-519: counts is a host int[T]; independent draws per task, rows concatenated by task. */
 int mtrl_sampler_sample_per_task(mtrl_sampler_t* s, int fill, const int* counts, float* obs_out,
                                  float* actions_out, float* next_obs_out, float* dones_out, float* rewards_out,

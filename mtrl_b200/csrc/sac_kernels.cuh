@@ -743,7 +743,7 @@ struct HeadBwdArgs {
 };
 
 template <int HD, int RG>
-static __global__ void __launch_bounds__(RG * 32, (RG == 8 && HD <= 8) ? 2 : 1) head_bwd_kernel(const HeadBwdArgs p) {
+static __global__ void __launch_bounds__(RG * 32, ((RG == 8 && HD <= 8) || HD <= 2) ? 2 : 1) head_bwd_kernel(const HeadBwdArgs p) {
   constexpr int RPW = kTileRows / RG;   // rows per warp per tile
   static_assert(RPW % 8 == 0, "rows per warp must be a multiple of the 8-row load batch");
   __shared__ float sd[kTileRows * HD];

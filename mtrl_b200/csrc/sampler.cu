@@ -46,15 +46,46 @@ __device__ __forceinline__ unsigned int pcg_next32(PcgState& s) {
   return static_cast<unsigned int>(n & 0xffffffffull);
 }
 
-// One thread: the stream is a sequential 128-bit LCG and Lemire rejection consumes a data-dependent
-// number of draws, so n (=128) draws are simply done in order (~3 us).
-__global__ void draw_indices_kernel(PcgState* __restrict__ st, long long* __restrict__ out, int n,
-                                    unsigned int high) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  if (high <= 1u) {  // rng == 0: numpy fills with `low` and consumes nothing
-    for (int i = 0; i < n; ++i) out[i] = 0;
-    return;
+// ---- 128-bit helpers for jumping the LCG ahead (PCG's advance(): state_k = M_k * state_0 + P_k) ----
+struct U128 {
+  unsigned long long hi, lo;
+};
+__device__ __forceinline__ U128 mul128(U128 a, U128 b) {
+  U128 r;
+  r.lo = a.lo * b.lo;
+  r.hi = __umul64hi(a.lo, b.lo) + a.lo * b.hi + a.hi * b.lo;
+  return r;
+}
+__device__ __forceinline__ U128 add128(U128 a, U128 b) {
+  U128 r;
+  r.lo = a.lo + b.lo;
+  r.hi = a.hi + b.hi + (r.lo < a.lo ? 1ull : 0ull);
+  return r;
+}
+// (M, P) with state_{+delta} = M * state + P, O(log delta) (Brown, "Random number generation with arbitrary strides")
+__device__ __forceinline__ void lcg_jump(U128 inc, unsigned int delta, U128* M, U128* P) {
+  U128 acc_m = {0ull, 1ull}, acc_p = {0ull, 0ull};
+  U128 cur_m = {kMulHi, kMulLo}, cur_p = inc;
+  while (delta) {
+    if (delta & 1u) {
+      acc_m = mul128(acc_m, cur_m);
+      acc_p = add128(mul128(acc_p, cur_m), cur_p);
+    }
+    cur_p = mul128(add128(cur_m, U128{0ull, 1ull}), cur_p);
+    cur_m = mul128(cur_m, cur_m);
+    delta >>= 1;
   }
+  *M = acc_m;
+  *P = acc_p;
+}
+__device__ __forceinline__ unsigned long long xsl_rr(U128 s) {
+  const unsigned long long x = s.hi ^ s.lo;
+  const unsigned int rot = static_cast<unsigned int>(s.hi >> 58);
+  return (x >> rot) | (x << ((64u - rot) & 63u));
+}
+
+// The sequential definition (one thread): Lemire rejection consumes a data-dependent number of draws.
+__device__ void draw_indices_sequential(PcgState* __restrict__ st, long long* __restrict__ out, int n, unsigned int high) {
   PcgState s = *st;
   const unsigned int thr = static_cast<unsigned int>((0x100000000ull - high) % high);
   for (int i = 0; i < n; ++i) {
@@ -69,6 +100,75 @@ __global__ void draw_indices_kernel(PcgState* __restrict__ st, long long* __rest
     out[i] = static_cast<long long>(m >> 32);
   }
   *st = s;
+}
+
+// One warp.  The 32-bit stream numpy consumes is [buffered half, if any] ++ (low, high) halves of successive 64-bit
+// outputs, and draw i takes stream element i unless a Lemire rejection occurred before it (probability
+// (2^32 mod high) / 2^32 < 2.4e-5 per draw for ring sizes <= 1e5).  Every lane therefore jumps the 128-bit LCG straight
+// to the outputs its draws need (lcg_jump, O(log n)), and only if some lane sees a rejection does lane 0 redo the call
+// sequentially from the untouched state.  Same stream and same final state bit for bit, ~2 us instead of ~12.
+__global__ void draw_indices_kernel(PcgState* __restrict__ st, long long* __restrict__ out, int n,
+                                    unsigned int high) {
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
+  if (high <= 1u) {  // rng == 0: numpy fills with `low` and consumes nothing
+    for (int i = lane; i < n; i += 32) out[i] = 0;
+    return;
+  }
+  const PcgState s0 = *st;
+  const U128 inc = {s0.inc_hi, s0.inc_lo};
+  const U128 base = {s0.state_hi, s0.state_lo};
+  const unsigned int thr = static_cast<unsigned int>((0x100000000ull - high) % high);
+  const int has0 = s0.has_uint32 ? 1 : 0;
+  U128 M16, P16;
+  lcg_jump(inc, 16u, &M16, &P16);
+  bool rejected = false;
+  U128 cur = base;
+  bool have_cur = false;
+  for (int i = lane; i < n; i += 32) {
+    unsigned int v;
+    if (i == 0 && has0) {
+      v = s0.uinteger;
+    } else {
+      const int q = i - has0;            // index into the fresh 32-bit stream
+      if (!have_cur) {
+        U128 M, P;
+        lcg_jump(inc, static_cast<unsigned int>(q >> 1) + 1u, &M, &P);   // 64-bit output #j is produced by state_{j+1}
+        cur = add128(mul128(M, base), P);
+        have_cur = true;
+      } else {
+        cur = add128(mul128(M16, cur), P16);                             // i += 32  =>  j += 16, same half
+      }
+      const unsigned long long o = xsl_rr(cur);
+      v = (q & 1) ? static_cast<unsigned int>(o >> 32) : static_cast<unsigned int>(o & 0xffffffffull);
+    }
+    const unsigned long long m = static_cast<unsigned long long>(v) * high;
+    const unsigned int left = static_cast<unsigned int>(m);
+    if (left < high && left < thr) rejected = true;
+    out[i] = static_cast<long long>(m >> 32);
+  }
+  if (__any_sync(0xffffffffu, rejected)) {
+    __syncwarp();
+    if (lane == 0) draw_indices_sequential(st, out, n, high);
+    return;
+  }
+  if (lane == 0) {
+    const int fresh = n - has0;                  // fresh 32-bit values consumed
+    PcgState s = s0;
+    if (fresh > 0) {
+      const unsigned int total64 = static_cast<unsigned int>((fresh + 1) >> 1);
+      U128 M, P;
+      lcg_jump(inc, total64, &M, &P);
+      const U128 fin = add128(mul128(M, base), P);
+      s.state_hi = fin.hi;
+      s.state_lo = fin.lo;
+      s.uinteger = static_cast<unsigned int>(xsl_rr(fin) >> 32);   // the high half buffered by the last 64-bit output
+      s.has_uint32 = (fresh & 1) ? 1u : 0u;
+    } else {
+      s.has_uint32 = has0 && n >= 1 ? 0u : s0.has_uint32;          // only the buffered half was consumed
+    }
+    *st = s;
+  }
 }
 
 struct GatherArgs {
@@ -284,6 +384,19 @@ extern "C" int mtrl_sampler_sample(mtrl_sampler_t* s, int fill, int n_per_task, 
   dim3 grid((max_slab + chunk - 1) / chunk, n_per_task, 5);
   gather_slabs_kernel<<<grid, threads, 0, st>>>(g, s->idx, chunk);
   MTRL_CUDA_CHECK(cudaGetLastError());
+  return MTRL_OK;
+}
+
+// `self._rng.integers(low=0, high=high, size=n)` alone (buffers.py:523-527): n int64 draws into idx_out (device),
+// advancing the generator exactly as numpy does.  1 <= high <= 2^32.
+extern "C" int mtrl_sampler_draw(mtrl_sampler_t* s, unsigned long long high, int n, long long* idx_out, void* stream) {
+  MTRL_REQUIRE(s && idx_out, "mtrl_sampler_draw: null argument");
+  MTRL_REQUIRE(n > 0 && n <= s->idx_cap, "mtrl_sampler_draw: n %d outside (0, %d]", n, s->idx_cap);
+  MTRL_REQUIRE(high >= 1ull && high <= 0xffffffffull, "mtrl_sampler_draw: high outside [1, 2^32 - 1] (numpy's 32-bit path)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  draw_indices_kernel<<<1, 32, 0, st>>>(s->state, s->idx, n, static_cast<unsigned int>(high));
+  MTRL_CUDA_CHECK(cudaGetLastError());
+  MTRL_CUDA_CHECK(cudaMemcpyAsync(idx_out, s->idx, sizeof(long long) * n, cudaMemcpyDeviceToDevice, st));
   return MTRL_OK;
 }
 

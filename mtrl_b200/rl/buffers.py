@@ -30,6 +30,7 @@ L._EXTRA_DECLS.update({
     "mtrl_sampler_add": ([_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp],),
     "mtrl_sampler_sample": ([_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp],),
     "mtrl_sampler_sample_per_task": ([_vp, _i, C.POINTER(_i), _vp, _vp, _vp, _vp, _vp, _vp],),
+    "mtrl_sampler_draw": ([_vp, C.c_ulonglong, _i, _vp, _vp],),
 })
 
 _M64 = (1 << 64) - 1

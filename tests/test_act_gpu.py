@@ -7,7 +7,8 @@ import sac_util as SU
 from oracle import mtsac_oracle as O
 
 pytestmark = pytest.mark.gpu
-TOL = 1e-3   # tf32 trunk operands; actions are in (-1, 1)
+TOL_EXACT = 5e-3   # vs exact arithmetic: tf32 trunk operands (~1e-3 relative on the pre-tanh mean of magnitude ~1)
+TOL_TF32 = 5e-4    # vs the oracle run with tf32-rounded matmul operands: isolates the kernels' arithmetic
 
 
 def _setup(T=10, W=256, seed=3):
@@ -15,7 +16,7 @@ def _setup(T=10, W=256, seed=3):
     st = O.init_state(cfg, seed=seed, dtype=torch.float32)
     # the reference initialises heads at U(+-1e-3): scale them up so actions are not all ~0
     for k in ("kernel", "bias"):
-        st.actor["heads"][k] = st.actor["heads"][k] * 300.0
+        st.actor["heads"][k] = st.actor["heads"][k] * 100.0
     agent = SU.make_agent(cfg, 16, seed=seed)
     SU.load_oracle_state(agent, st)
     return cfg, st, agent
@@ -31,15 +32,22 @@ def test_sample_and_eval_action_match_oracle(cuda, n_per_task):
     obs[:, :39] = torch.randn(T * n_per_task, 39, generator=g)
     obs[torch.arange(obs.shape[0]), 39 + task] = 1.0
     eps = torch.randn(obs.shape[0], 4, generator=g)
+    import dataclasses
+
     p64 = O.tree_map(lambda x: x.double(), st.actor)
     ref_mode = O.actor_action(p64, obs.double(), cfg)
     ref_samp = O.actor_action(p64, obs.double(), cfg, eps.double())
+    cfg_t = dataclasses.replace(cfg, matmul_operands="tf32")
+    tf_mode = O.actor_action(p64, obs.double(), cfg_t)
+    tf_samp = O.actor_action(p64, obs.double(), cfg_t, eps.double())
     got_mode = agent.eval_action(obs.numpy())
     _, got_samp = agent.sample_action(obs.numpy(), eps=eps)
     assert isinstance(got_mode, np.ndarray) and got_mode.shape == (obs.shape[0], 4)
     assert float(ref_mode.abs().max()) > 0.05, "degenerate test: actions are all ~0"
-    assert np.abs(got_mode - ref_mode.numpy()).max() <= TOL
-    assert np.abs(got_samp - ref_samp.numpy()).max() <= TOL
+    assert np.abs(got_mode - ref_mode.numpy()).max() <= TOL_EXACT
+    assert np.abs(got_samp - ref_samp.numpy()).max() <= TOL_EXACT
+    assert np.abs(got_mode - tf_mode.numpy()).max() <= TOL_TF32
+    assert np.abs(got_samp - tf_samp.numpy()).max() <= TOL_TF32
     # Philox draws: bounded, different between calls, identical for the rows of one call with the same inputs
     _, a1 = agent.sample_action(obs.numpy())
     _, a2 = agent.sample_action(obs.numpy())

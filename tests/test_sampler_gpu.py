@@ -140,3 +140,28 @@ def test_edge_cases(cuda):
     with pytest.raises(AssertionError):
         buf.add(np.zeros((3, 3), np.float32), np.zeros((3, 3), np.float32), np.zeros((3, 1), np.float32),
                 np.zeros(3, np.float32), np.zeros(3, np.float32))
+
+
+@pytest.mark.parametrize("high", [1, 2, 3, 128, 99_999, 100_000, 1_500_000_000, 3_000_000_000, 4_294_967_295])
+def test_raw_draws_match_live_numpy_including_rejections(cuda, high):
+    """`rng.integers(0, high, n)` through the jump-ahead draw kernel vs numpy itself.  high = 1.5e9 / 3e9 reject ~30 % of
+    the draws (Lemire threshold 2^32 mod high), which exercises the sequential redo; odd sizes exercise the buffered
+    32-bit half across calls; the final generator state must equal numpy's."""
+    import ctypes as C
+
+    from mtrl_b200 import _lib as L
+
+    seed = 12345 + (high % 97)
+    buf = make(2, 1, 1, 64, seed)
+    rng = np.random.default_rng(seed)
+    out = torch.empty(4096, dtype=torch.int64, device="cuda")
+    for n in (1, 128, 127, 1, 2, 33, 1280, 4095, 64):
+        ref = rng.integers(low=0, high=high, size=(n,))
+        L.check(L.lib().mtrl_sampler_draw(buf._h, C.c_ulonglong(high), n, C.c_void_p(out.data_ptr()),
+                                          C.c_void_p(L.current_stream_ptr())))
+        got = out[:n].cpu().numpy()
+        assert np.array_equal(got, ref), f"high={high} n={n}"
+    st, ref_st = buf._rng.bit_generator.state, rng.bit_generator.state
+    assert st["state"] == ref_st["state"] and st["has_uint32"] == ref_st["has_uint32"]
+    if ref_st["has_uint32"]:
+        assert st["uinteger"] == ref_st["uinteger"]
