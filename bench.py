@@ -290,7 +290,7 @@ def main() -> None:
 
     def step_resident():
         data = buf.sample(B_local)
-        agent.update(data, global_batch=B)
+        agent.update(data, global_batch=B, graph=False)   # the whole step (sampler + update) is captured below
 
     # ---------------- warm-up ----------------
     for _ in range(args.warmup):
@@ -353,14 +353,15 @@ def main() -> None:
         host_batches.append(tuple(x.cpu().pin_memory() for x in s))
     barrier()
     log_host = torch.empty(16, dtype=torch.float32).pin_memory()
+    # the public call with HOST batches (pinned): update() copies them into its staging buffers (the H2D transfer)
+    # and replays its captured graph
     for i in range(3):
-        agent.update(tuple(x.cuda(non_blocking=True) for x in host_batches[i % n_host]), global_batch=B)
+        agent.update(host_batches[i % n_host], global_batch=B)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for i in range(args.steps):
-        hb = host_batches[i % n_host]
-        _, logs = agent.update(tuple(x.cuda(non_blocking=True) for x in hb), global_batch=B)
+        _, logs = agent.update(host_batches[i % n_host], global_batch=B)
         log_host.copy_(agent._logs, non_blocking=False)  # the reference's jax.device_get(logs) (base.py:223)
     f1.record()
     barrier()

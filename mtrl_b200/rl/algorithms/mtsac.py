@@ -16,6 +16,7 @@ from __future__ import annotations
 import ctypes as C
 import dataclasses
 import math
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -31,6 +32,7 @@ from ...nn.multi_head import uniform
 from ...types import ReplayBufferSamples
 
 MAX_DEPTH = 4
+_GRAPH_DEFAULT = os.environ.get("MTRL_UPDATE_GRAPH", "1") != "0"
 LOG_KEYS = (
     "losses/qf_values", "losses/qf_loss", "metrics/critic_grad_magnitude", "metrics/critic_params_norm",
     "losses/actor_loss", "metrics/actor_grad_magnitude", "metrics/actor_params_norm", "metrics/explore_loss",
@@ -375,6 +377,7 @@ class MTSAC:
                                                  p["actor_params"]))
         self._status_event = torch.cuda.Event()
         self._pending_status = False
+        self._graphs, self._graph_seen, self._prof_enabled = {}, set(), False
 
     def __del__(self):
         if getattr(self, "_h", None) is not None and L._lib is not None:
@@ -427,22 +430,60 @@ class MTSAC:
                 raise ValueError("update: the batch does not fit max_rows (rows per task are padded to 128)")
 
     def update(self, data: ReplayBufferSamples, eps_c=None, eps_a=None, *, global_batch: int | None = None,
-               check: bool = False):
+               check: bool = False, graph: bool | None = None):
         """`MTSAC.update` (mtsac.py:1249-1251).  Returns (self, logs) with logs as 0-dim device tensors in
-        the reference's keys; nothing here synchronises the host unless `check=True`."""
-        if not torch.cuda.is_current_stream_capturing():
+        the reference's keys; nothing here synchronises the host unless `check=True`.
+
+        Launch path: the ~65 kernels of one update are captured into a CUDA graph the second time a batch shape is
+        seen and replayed afterwards (inputs are first copied into fixed staging buffers -- for host batches that copy
+        IS the H2D transfer), which removes the per-kernel launch gaps.  `graph=False` (or MTRL_UPDATE_GRAPH=0)
+        launches kernel by kernel; that is also what happens while the caller is capturing a graph of its own."""
+        capturing = torch.cuda.is_current_stream_capturing()
+        if not capturing:
             self._check_status()
-        obs, act, nxt, done, rew = (self._dev(x) for x in data)
-        B = obs.shape[0]
-        assert obs.shape[1] == self._cfg.obs_dim and act.shape == (B, self._cfg.action_dim)
-        ec = self._dev(eps_c) if eps_c is not None else None
-        ea = self._dev(eps_a) if eps_a is not None else None
+        if self.world_size > 1 and global_batch is None:
+            raise ValueError("multi-GPU update needs global_batch (the B every loss mean divides by)")
+        B = int(data[0].shape[0])
+        assert data[0].shape[1] == self._cfg.obs_dim and tuple(data[1].shape) == (B, self._cfg.action_dim)
+        if graph is None:
+            graph = _GRAPH_DEFAULT
+        key = (B, eps_c is not None, global_batch)
+        entry = None
+        if graph and not capturing and self._prof_enabled is False:
+            entry = self._graphs.get(key)
+            if entry is None and key in self._graph_seen and len(self._graphs) < 4:
+                entry = self._capture(key, B, eps_c is not None, global_batch)
+            self._graph_seen.add(key)
+        if entry is not None:
+            src = list(data) + ([eps_c, eps_a] if eps_c is not None else [])
+            for dst, x in zip(entry["inputs"], src):
+                t = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(x, dtype=np.float32))
+                dst.copy_(t.reshape(dst.shape), non_blocking=True)
+            entry["graph"].replay()
+            logs = entry["logs"]
+        else:
+            obs, act, nxt, done, rew = (self._dev(x) for x in data)
+            ec = self._dev(eps_c) if eps_c is not None else None
+            ea = self._dev(eps_a) if eps_a is not None else None
+            self._launch_update((obs, act, nxt, done, rew), ec, ea, B, global_batch)
+            logs = self.logs()
+        # asynchronous status read-back (checked at the next call, or now if check=True); not while a CUDA graph
+        # is being captured (the captured update is replayed without host involvement)
+        if not capturing:
+            stream = _vp(L.current_stream_ptr())
+            L.check(L.lib().mtrl_sac_read_status_async(self._h, _vp(self._status_host.data_ptr()), stream))
+            self._status_event.record()
+            self._pending_status = True
+            if check:
+                self._check_status()
+        return self, logs
+
+    def _launch_update(self, tensors, ec, ea, B: int, global_batch: int | None) -> None:
+        obs, act, nxt, done, rew = tensors
         stream = _vp(L.current_stream_ptr())
         args = (self._h, _vp(obs.data_ptr()), _vp(act.data_ptr()), _vp(nxt.data_ptr()), _vp(done.data_ptr()),
                 _vp(rew.data_ptr()), B)
         p = lambda t: _vp(t.data_ptr() if t is not None else None)  # noqa: E731
-        if self.world_size > 1 and global_batch is None:
-            raise ValueError("multi-GPU update needs global_batch (the B every loss mean divides by)")
         if self.world_size == 1 or self.exchange in ("p2p", "local"):
             # one call: with several ranks the trunk-gradient exchange happens inside the fused kernels (comm.cuh)
             L.check(L.lib().mtrl_sac_update(*args, global_batch or B, p(ec), p(ea), stream))
@@ -456,16 +497,21 @@ class MTSAC:
             L.check(L.lib().mtrl_sac_phase2_critic_step_actor_grads(self._h, stream))
             dist.all_reduce(self._flat["actor_grads"][: la.trunk_total + 32], group=self.process_group)
             L.check(L.lib().mtrl_sac_phase3_actor_step_alpha(self._h, stream))
-        # asynchronous status read-back (checked at the next call, or now if check=True); not while a CUDA graph
-        # is being captured (the captured update is replayed without host involvement)
-        if not torch.cuda.is_current_stream_capturing():
-            L.check(L.lib().mtrl_sac_read_status_async(self._h, _vp(self._status_host.data_ptr()), stream))
-            self._status_event.record()
-            self._pending_status = True
-            if check:
-                self._check_status()
-        logs = self.logs()
-        return self, logs
+
+    def _capture(self, key, B: int, has_eps: bool, global_batch: int | None) -> dict:
+        """Capture one update on fixed staging buffers (the caller has already run this shape once kernel by kernel,
+        so every kernel is loaded and nothing initialises lazily under capture)."""
+        c = self._cfg
+        dims = [c.obs_dim, c.action_dim, c.obs_dim, 1, 1] + ([c.action_dim, c.action_dim] if has_eps else [])
+        inputs = [torch.zeros(B, d, dtype=torch.float32, device=self.device) for d in dims]
+        torch.cuda.current_stream().synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._launch_update(tuple(inputs[:5]), inputs[5] if has_eps else None, inputs[6] if has_eps else None, B, global_batch)
+            logs = self.logs()
+        entry = {"graph": g, "inputs": inputs, "logs": logs}
+        self._graphs[key] = entry
+        return entry
 
     def logs(self) -> dict:
         """The ten log scalars of the last update as 0-dim device tensors (keys of mtsac.py:616-621, 704-709, 728-731).
@@ -483,6 +529,7 @@ class MTSAC:
         return int(L.lib().mtrl_sac_launches_per_update(self._h))
 
     def profile_gemms(self, enable: bool) -> None:
+        self._prof_enabled = bool(enable)   # event bracketing needs kernel-by-kernel launches
         L.check(L.lib().mtrl_sac_profile_gemms(self._h, int(enable)))
 
     def profile_read(self) -> tuple[float, int]:
