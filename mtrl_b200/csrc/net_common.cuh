@@ -112,10 +112,76 @@ inline mtrl_gemm_problem_t dw_problem(const float* X, int ldx, int n_in, const f
   return p;
 }
 
-inline int make_plan(std::vector<mtrl_gemm_plan_t*>& dst, const std::vector<mtrl_gemm_problem_t>& probs) {
+inline int make_plan_plain(std::vector<mtrl_gemm_plan_t*>& dst, const std::vector<mtrl_gemm_problem_t>& probs) {
   mtrl_gemm_plan_t* plan = nullptr;
   MTRL_PROPAGATE(mtrl_gemm_plan_create(&plan, probs.data(), static_cast<int>(probs.size())));
   dst.push_back(plan);
+  return MTRL_OK;
+}
+
+// Tile-width selection by measurement.  A launch is a static schedule of equal-shaped units over 74 CTA pairs, so its
+// duration is (rounds of units) x (unit time): 80 units of width 256 take two rounds where 120 units of width 192 take
+// two SHORTER rounds.  Which width wins depends on the shapes grouped into the launch (batch rows, width, members) and on
+// how far narrower tiles are L2-bound, so every candidate width is built and timed once at plan creation (a few launches
+// on the real buffers: forward outputs are overwritten and gradient accumulators re-zeroed by every update) and the
+// fastest plan is kept.  MTRL_GEMM_AUTOTUNE=0 keeps the default width.
+inline int make_plan(std::vector<mtrl_gemm_plan_t*>& dst, const std::vector<mtrl_gemm_problem_t>& probs) {
+  const char* env = getenv("MTRL_GEMM_AUTOTUNE");
+  bool wide = false;
+  for (const auto& p : probs) wide = wide || p.N >= 256;
+  if ((env && env[0] == '0') || !wide) return make_plan_plain(dst, probs);
+  {
+    // many rounds of units: the last partial round costs little and every candidate launch would take milliseconds
+    mtrl_gemm_plan_t* probe = nullptr;
+    MTRL_PROPAGATE(mtrl_gemm_plan_create(&probe, probs.data(), static_cast<int>(probs.size())));
+    if (mtrl_gemm_plan_units(probe) >= 6 * 74) {
+      dst.push_back(probe);
+      return MTRL_OK;
+    }
+    mtrl_gemm_plan_destroy(probe);
+  }
+  cudaEvent_t e0, e1;
+  MTRL_CUDA_CHECK(cudaEventCreate(&e0));
+  MTRL_CUDA_CHECK(cudaEventCreate(&e1));
+  mtrl_gemm_plan_t* best = nullptr;
+  float best_ms = 0.f;
+  int rc = MTRL_OK;
+  const int cands[4] = {0, 192, 128, 64};   // 0 = the caller's default
+  for (int cand : cands) {
+    std::vector<mtrl_gemm_problem_t> q = probs;
+    bool changed = cand == 0;
+    for (auto& p : q)
+      if (cand && p.N >= 256 && p.block_n > cand) { p.block_n = cand; changed = true; }
+    if (!changed) continue;
+    mtrl_gemm_plan_t* plan = nullptr;
+    rc = mtrl_gemm_plan_create(&plan, q.data(), static_cast<int>(q.size()));
+    if (rc != MTRL_OK) break;
+    float ms = 1e30f;
+    for (int rep = 0; rep < 4 && rc == MTRL_OK; ++rep) {
+      cudaEventRecord(e0, nullptr);
+      rc = mtrl_gemm_plan_run(plan, nullptr);
+      cudaEventRecord(e1, nullptr);
+      if (cudaEventSynchronize(e1) != cudaSuccess) { mtrl_set_error("GEMM autotune launch failed"); rc = MTRL_ERR_CUDA; }
+      float t = 0.f;
+      cudaEventElapsedTime(&t, e0, e1);
+      if (rep > 0 && t < ms) ms = t;   // first run warms the instruction cache / L2
+    }
+    if (rc != MTRL_OK) { mtrl_gemm_plan_destroy(plan); break; }
+    if (!best || ms < best_ms * 0.97f) {   // prefer the default unless a narrower tile is clearly faster
+      if (best) mtrl_gemm_plan_destroy(best);
+      best = plan;
+      best_ms = ms;
+    } else {
+      mtrl_gemm_plan_destroy(plan);
+    }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (rc != MTRL_OK) {
+    if (best) mtrl_gemm_plan_destroy(best);
+    return rc;
+  }
+  dst.push_back(best);
   return MTRL_OK;
 }
 

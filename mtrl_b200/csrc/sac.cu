@@ -937,7 +937,7 @@ extern "C" int mtrl_sac_act(mtrl_sac_t* h, const float* obs, int n, const float*
       std::vector<mtrl_gemm_problem_t> p;
       p.push_back(fwd_problem(l == 0 ? w.Xa : w.Ao[l - 1], l == 0 ? Ka : W, l == 0 ? LA.in_dim : W, tk(h->buf.actor_shadow, LA, 0, l),
                               tb(h->buf.actor_params, LA, 0, l), w.Ao[l], n, W));
-      MTRL_PROPAGATE(make_plan(plans, p));
+      MTRL_PROPAGATE(make_plan_plain(plans, p));   // created lazily on the caller's stream: no timing launches here
     }
     it = h->act_plans.emplace(n, plans).first;
   }

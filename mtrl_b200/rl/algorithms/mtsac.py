@@ -375,6 +375,12 @@ class MTSAC:
             p = self._arena_plan
             L.check(L.lib().mtrl_sac_attach_comm(h, self._comm, p["critic_grads"], p["actor_grads"], p["critic_params"],
                                                  p["actor_params"]))
+            # attaching re-times the backward GEMM plans, whose epilogues add into the peers' gradient buffers: nobody
+            # may start an update before every rank is done with that
+            import torch.distributed as dist
+
+            torch.cuda.synchronize()
+            dist.barrier(group=self.process_group)
         self._status_event = torch.cuda.Event()
         self._pending_status = False
         self._graphs, self._graph_seen, self._prof_enabled = {}, set(), False
