@@ -455,6 +455,8 @@ class MTSAC:
             graph = _GRAPH_DEFAULT
         key = (B, eps_c is not None, global_batch)
         entry = None
+        if self.world_size > 1 and self.exchange == "nccl":
+            graph = False   # a graph holding NCCL collectives blocks the communicator's teardown
         if graph and not capturing and self._prof_enabled is False:
             entry = self._graphs.get(key)
             if entry is None and key in self._graph_seen and len(self._graphs) < 4:
@@ -466,7 +468,7 @@ class MTSAC:
                 t = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(x, dtype=np.float32))
                 dst.copy_(t.reshape(dst.shape), non_blocking=True)
             entry["graph"].replay()
-            logs = entry["logs"]
+            logs = entry["logs"] if entry["logs"] is not None else self.logs()
         else:
             obs, act, nxt, done, rew = (self._dev(x) for x in data)
             ec = self._dev(eps_c) if eps_c is not None else None
@@ -514,7 +516,8 @@ class MTSAC:
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self._launch_update(tuple(inputs[:5]), inputs[5] if has_eps else None, inputs[6] if has_eps else None, B, global_batch)
-            logs = self.logs()
+            # with several ranks the 16-float log all-reduce (NCCL) stays outside the graph
+            logs = self.logs() if self.world_size == 1 else None
         entry = {"graph": g, "inputs": inputs, "logs": logs}
         self._graphs[key] = entry
         return entry

@@ -16,6 +16,9 @@ from oracle import mtsac_oracle as O
 
 
 def main():
+    import faulthandler
+
+    faulthandler.dump_traceback_later(int(os.environ.get("MG_HANG_DUMP_S", "150")), exit=True)   # a hang must not eat the GPU budget
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
