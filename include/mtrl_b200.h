@@ -229,6 +229,15 @@ int mtrl_sac_phase3_actor_step_alpha(mtrl_sac_t* h, void* stream);
  * set the status word (mtrl_sac_read_status_async) and come back as zeros.  Not re-entrant with mtrl_sac_update. */
 int mtrl_sac_act(mtrl_sac_t* h, const float* obs, int n, const float* eps, int deterministic, float* actions_out,
                  void* stream);
+/* Per-task gradients, the first half of MTSAC.compute_weights (mtsac.py:870-1170: batch split by task,
+ * jax.vmap(jax.value_and_grad(critic_loss / actor_loss)) over tasks).  critic_tg: device fp32 (T, critic layout.total),
+ * actor_tg: (T, actor layout.total), row t = gradient of task t in the flat network layout (zero outside task t's own
+ * head).  Values are the full-batch gradients restricted to task t's rows = (n_t / B) x the reference's per-task-mean
+ * gradients.  No parameter is updated.  Needs every task on this handle and equally many rows per task (status 3
+ * otherwise, mtrl_sac_read_status_async). */
+int mtrl_sac_task_grads(mtrl_sac_t* h, const float* obs, const float* actions, const float* next_obs, const float* dones,
+                        const float* rewards, int batch, const float* eps_c, const float* eps_a, float* critic_tg,
+                        float* actor_tg, void* stream);
 /* Number of kernels one mtrl_sac_update launches (for bench.py's gpu_launches). */
 int mtrl_sac_launches_per_update(const mtrl_sac_t* h);
 /* Bracket every GEMM launch of the following updates with CUDA events on the launch stream

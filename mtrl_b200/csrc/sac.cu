@@ -6,6 +6,7 @@
 //   alpha  step (:713-731)  uses log-probs of the OLD actor (the ones the actor loss sampled)
 // Networks: MultiHeadNetwork (mtrl/nn/multi_head.py:21-68) trunk Dense+ReLU layers as tcgen05 GEMMs,
 // own-task heads as CUDA-core row dots; critic input is (action, state) (mtrl/rl/networks.py:61).
+#include <algorithm>
 #include <map>
 #include <vector>
 
@@ -143,6 +144,13 @@ struct mtrl_sac {
   long long off_critic_grads = 0, off_actor_grads = 0, off_critic_params = 0, off_actor_params = 0;
   std::map<int, std::vector<mtrl_gemm_plan_t*>> act_plans;   // actor forward plans of mtrl_sac_act, by row count
   unsigned long long act_calls = 0;
+  // per-task gradient path (mtrl_sac_task_grads): grouped per-task dW plans [critic/actor][layer] -> launches
+  struct TaskGradCache {
+    float *critic_tg = nullptr, *actor_tg = nullptr;
+    int rows_per_task = 0;
+    std::vector<std::vector<mtrl_gemm_plan_t*>> critic, actor;   // [layer index i = D-1-l][launch]
+  } tgc;
+  TaskGradCache* tg_active = nullptr;   // set while mtrl_sac_task_grads runs: the backward also fills the (T, P) rows
   comm::Segment *d_segs_critic = nullptr, *d_segs_actor = nullptr;   // ownership tables (device)
   int nsegs_critic = 0, nsegs_actor = 0;
 };
@@ -414,6 +422,19 @@ int run_trunk_backward(mtrl_sac* h, std::vector<mtrl_gemm_plan_t*>& plans, float
       }
       const int groups = l == D - 1 ? h->cfg.max_rows / kTileRows : h->cfg.max_rows / 32;
       MTRL_PROPAGATE(launch_colsum(h, jobs, groups, st));
+      if (h->tg_active) {
+        // row t of the (T, P) matrix: bias slice from the task's partial column sums, kernel slice from the per-task
+        // dW GEMMs (dZ of this layer is still in place; the plan below consumes it)
+        const bool critic = grads == h->buf.critic_grads;
+        float* tg = critic ? h->tg_active->critic_tg : h->tg_active->actor_tg;
+        const int R = h->tg_active->rows_per_task;
+        dim3 g((h->cfg.width + 255) / 256, h->cfg.num_local_tasks, E);
+        task_bias_kernel<<<g, 256, 0, st>>>(jobs, tg, L.total, L.member_trunk_stride, L.bias_off[l],
+                                            l == D - 1 ? R / kTileRows : R / 32, h->cfg.width);
+        MTRL_CUDA_CHECK(cudaGetLastError());
+        LAUNCHED(h);
+        for (auto* p : (critic ? h->tg_active->critic : h->tg_active->actor)[i]) MTRL_PROPAGATE(run_plan(h, p, st));
+      }
     }
     MTRL_PROPAGATE(run_plan(h, plans[i], st));
   }
@@ -518,6 +539,9 @@ extern "C" void mtrl_sac_destroy(mtrl_sac_t* h) {
     for (auto* p : *v) mtrl_gemm_plan_destroy(p);
   for (auto& kv : h->act_plans)
     for (auto* p : kv.second) mtrl_gemm_plan_destroy(p);
+  for (auto* v : {&h->tgc.critic, &h->tgc.actor})
+    for (auto& launches : *v)
+      for (auto* p : launches) mtrl_gemm_plan_destroy(p);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   if (h->d_segs_critic) cudaFree(h->d_segs_critic);
   if (h->d_segs_actor) cudaFree(h->d_segs_actor);
@@ -988,6 +1012,86 @@ extern "C" int mtrl_sac_trunk_owner_mask(mtrl_sac_t* h, int critic, float* mask_
         for (long long i = sg.begin4 * 4; i < sg.end4 * 4; ++i) mask[static_cast<size_t>(i)] = 1.f;
   }
   MTRL_CUDA_CHECK(cudaMemcpy(mask_dev, mask.data(), mask.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return MTRL_OK;
+}
+
+// Per-task gradients of the critic and actor losses (MTSAC.compute_weights, mtsac.py:870-1170): the batch split by
+// task, jax.vmap(jax.value_and_grad(loss)) over the task axis.  Writes row t of critic_tg (T, critic layout.total) and
+// actor_tg (T, actor layout.total) in the flat network layout; parameters are NOT updated.  Gradients are those of the
+// full-batch losses restricted to task t's rows, i.e. (n_t / B) x the reference's per-task-mean gradients (the caller
+// rescales).  Needs all tasks on this handle and the same number of rows for every task.
+extern "C" int mtrl_sac_task_grads(mtrl_sac_t* h, const float* obs, const float* actions, const float* next_obs,
+                                   const float* dones, const float* rewards, int batch, const float* eps_c,
+                                   const float* eps_a, float* critic_tg, float* actor_tg, void* stream) {
+  MTRL_REQUIRE(h && critic_tg && actor_tg, "mtrl_sac_task_grads: null argument");
+  const mtrl_sac_config_t& c = h->cfg;
+  MTRL_REQUIRE(c.variant == MTRL_VARIANT_MTSAC && c.num_local_tasks == c.num_tasks && !h->comm,
+               "mtrl_sac_task_grads: needs the multi-task variant with every task on one handle");
+  const int T = c.num_tasks, D = c.depth, E = c.num_critics, W = c.width;
+  MTRL_REQUIRE(batch % T == 0, "mtrl_sac_task_grads: batch %d is not a multiple of the %d tasks", batch, T);
+  const int R = static_cast<int>(round_up(batch / T, kTileRows));
+  MTRL_REQUIRE(static_cast<long long>(R) * T <= c.max_rows, "mtrl_sac_task_grads: %d rows per task do not fit max_rows", R);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Workspace& w = h->ws;
+  const mtrl_net_layout_t& LA = h->lay.actor;
+  const mtrl_net_layout_t& LC = h->lay.critic;
+  mtrl_sac::TaskGradCache& tc = h->tgc;
+  if (tc.critic_tg != critic_tg || tc.actor_tg != actor_tg || tc.rows_per_task != R) {
+    for (auto* v : {&tc.critic, &tc.actor}) {
+      for (auto& launches : *v)
+        for (auto* p : launches) mtrl_gemm_plan_destroy(p);
+      v->clear();
+    }
+    const int Ka = h->lay.k_actor, Kc = h->lay.k_critic;
+    for (int l = D - 1; l >= 0; --l) {
+      const int src = (D - 1 - l) & 1;
+      std::vector<mtrl_gemm_problem_t> pc, pa;
+      for (int e = 0; e < E; ++e)
+        for (int t = 0; t < T; ++t) {
+          const float* X = (l == 0 ? w.Xc : w.C[e][l - 1]) + static_cast<long long>(t) * R * (l == 0 ? Kc : W);
+          float* out = tk(critic_tg + static_cast<long long>(t) * LC.total, LC, e, l);
+          pc.push_back(dw_problem(X, l == 0 ? Kc : W, l == 0 ? LC.in_dim : W, w.G[e][src] + static_cast<long long>(t) * R * W, out, R, W,
+                                  h->sms, 0));
+        }
+      for (int t = 0; t < T; ++t) {
+        const float* X = (l == 0 ? w.Xa : w.Ao[l - 1]) + static_cast<long long>(t) * R * (l == 0 ? Ka : W);
+        float* out = tk(actor_tg + static_cast<long long>(t) * LA.total, LA, 0, l);
+        pa.push_back(dw_problem(X, l == 0 ? Ka : W, l == 0 ? LA.in_dim : W, w.G[0][src] + static_cast<long long>(t) * R * W, out, R, W,
+                                h->sms, 0));
+      }
+      for (auto* pr : {&pc, &pa}) {
+        std::vector<mtrl_gemm_plan_t*> launches;
+        for (size_t i0 = 0; i0 < pr->size(); i0 += 24) {
+          std::vector<mtrl_gemm_problem_t> chunk(pr->begin() + i0, pr->begin() + std::min(pr->size(), i0 + 24));
+          for (auto& q : chunk) { q.k_splits = 1; q.epilogue = MTRL_EPI_STORE; }
+          MTRL_PROPAGATE(make_plan_plain(launches, chunk));
+        }
+        (pr == &pc ? tc.critic : tc.actor).push_back(launches);
+      }
+    }
+    tc.critic_tg = critic_tg;
+    tc.actor_tg = actor_tg;
+    tc.rows_per_task = R;
+  }
+  MTRL_CUDA_CHECK(cudaMemsetAsync(critic_tg, 0, static_cast<size_t>(T) * LC.total * sizeof(float), st));
+  MTRL_CUDA_CHECK(cudaMemsetAsync(actor_tg, 0, static_cast<size_t>(T) * LA.total * sizeof(float), st));
+  MTRL_PROPAGATE(step_begin(h, obs, actions, next_obs, dones, rewards, batch, batch, eps_c, eps_a, st));
+  check_balanced_kernel<<<1, 64, 0, st>>>(w.seg_start, w.slot_src, T, R, batch / T, w.status);
+  MTRL_CUDA_CHECK(cudaGetLastError());
+  h->tg_active = &tc;
+  int rc = step_critic_grads(h, st);
+  if (rc == MTRL_OK) {
+    task_heads_kernel<<<dim3(T, E), 256, 0, st>>>(h->buf.critic_grads, critic_tg, LC.total, LC.heads_base, LC.member_head_stride,
+                                                  LC.head_kernel_off, LC.head_bias_off, W * 1, 1);
+    rc = step_actor_sample(h, true, st);
+  }
+  if (rc == MTRL_OK) rc = step_actor_grads(h, st);
+  if (rc == MTRL_OK)
+    task_heads_kernel<<<dim3(T, 1), 256, 0, st>>>(h->buf.actor_grads, actor_tg, LA.total, LA.heads_base, LA.member_head_stride,
+                                                  LA.head_kernel_off, LA.head_bias_off, W * 2 * c.action_dim, 2 * c.action_dim);
+  h->tg_active = nullptr;
+  MTRL_PROPAGATE(rc);
+  MTRL_CUDA_CHECK(cudaGetLastError());
   return MTRL_OK;
 }
 

@@ -862,6 +862,51 @@ static __global__ void colsum_final_kernel(const ColsumJobs jobs, int groups, in
 }
 
 // ---------------------------------------------------------------------------------------------
+// Per-task gradients (MTSAC.compute_weights, mtsac.py:870-1170: jax.vmap(jax.value_and_grad(loss)) over the batch split
+// by task).  A row's dZ does not depend on other rows, so task t's gradient is the ordinary backward restricted to
+// task t's rows: its dW comes from per-task GEMMs (sac.cu), and these two kernels fill in the bias and head slices of
+// row t of the (T, P) gradient matrix (flat network layout).
+// ---------------------------------------------------------------------------------------------
+// tg[t][bias_off + k] = sum of the task's partial column sums; grid (ceil(W/256), T, E)
+static __global__ void task_bias_kernel(const ColsumJobs parts, float* __restrict__ tg, long long row_stride, long long member_stride,
+                                        long long bias_off, int groups_per_task, int W) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.y, e = blockIdx.z;
+  if (k >= W) return;
+  const float* p = parts.part[e] + static_cast<long long>(t) * groups_per_task * W;
+  float s = 0.f;
+  for (int g = 0; g < groups_per_task; ++g) s += p[static_cast<long long>(g) * W + k];
+  tg[static_cast<long long>(t) * row_stride + e * member_stride + bias_off + k] = s;
+}
+
+// Head parameters of task t only receive gradient from task t: copy that slice of the (already per-task) head
+// gradients into row t.  grid (T, E); n_k = W * head_dim, n_b = head_dim.
+static __global__ void task_heads_kernel(const float* __restrict__ grads, float* __restrict__ tg, long long row_stride,
+                                         long long heads_base, long long member_head_stride, long long head_kernel_off,
+                                         long long head_bias_off, int n_k, int n_b) {
+  const int t = blockIdx.x, e = blockIdx.y;
+  const long long kbase = heads_base + e * member_head_stride + head_kernel_off + static_cast<long long>(t) * n_k;
+  const long long bbase = heads_base + e * member_head_stride + head_bias_off + static_cast<long long>(t) * n_b;
+  float* dst = tg + static_cast<long long>(t) * row_stride;
+  for (int i = threadIdx.x; i < n_k; i += blockDim.x) dst[kbase + i] = grads[kbase + i];
+  for (int i = threadIdx.x; i < n_b; i += blockDim.x) dst[bbase + i] = grads[bbase + i];
+}
+
+// status[0] = 3 unless every task owns exactly rows [t * R, (t + 1) * R) of the packed batch and n of them are real
+// (balanced batch: the reference reshapes the task-sorted batch to (num_tasks, -1, dim), mtsac.py:325).
+static __global__ void check_balanced_kernel(const int* __restrict__ seg_start, const int* __restrict__ slot_src, int T, int R, int n,
+                                             int* __restrict__ status) {
+  for (int t = threadIdx.x; t <= T; t += blockDim.x) {
+    if (seg_start[t] != t * R) atomicExch(status, 3);
+    if (t < T) {
+      int cnt = 0;
+      for (int r = t * R; r < (t + 1) * R; ++r) cnt += slot_src[r] >= 0 ? 1 : 0;
+      if (cnt != n) atomicExch(status, 3);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Optimiser: optax.chain(clip_by_global_norm, adam) + apply_updates (config/optim.py:26-43,
 // algorithms/utils.py:11-46) over the flat parameter buffer of a network, fused with the Polyak
 // target update (mtsac.py:607-613) and the tf32 operand copies the GEMMs read.

@@ -90,6 +90,7 @@ L._EXTRA_DECLS.update({
     "mtrl_sac_launches_per_update": ([_vp],),
     "mtrl_sac_read_status_async": ([_vp, _vp, _vp],),
     "mtrl_sac_act": ([_vp, _vp, _i, _vp, _i, _vp, _vp],),
+    "mtrl_sac_task_grads": ([_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp],),
     "mtrl_sac_trunk_owner_mask": ([_vp, _i, _vp],),
     "mtrl_sac_profile_gemms": ([_vp, _i],),
     "mtrl_sac_profile_read": ([_vp, C.POINTER(C.c_double), C.POINTER(_i)],),
@@ -184,14 +185,15 @@ def _views(flat: torch.Tensor, lay: NetLayoutC, in_dim: int, ensemble: bool) -> 
     """Flax-named zero-copy views of one network's flat buffer."""
     W, D, T, E, hd = lay.width, lay.depth, lay.num_local_tasks, lay.members, lay.head_dim
     tree = {}
+    o0 = flat.storage_offset()   # as_strided offsets are absolute in the storage: `flat` may be a row of a matrix
     d = in_dim
     for i in range(D):
-        k = flat.as_strided((E, d, W), (lay.member_trunk_stride, W, 1), lay.kernel_off[i])
-        b = flat.as_strided((E, W), (lay.member_trunk_stride, 1), lay.bias_off[i])
+        k = flat.as_strided((E, d, W), (lay.member_trunk_stride, W, 1), o0 + lay.kernel_off[i])
+        b = flat.as_strided((E, W), (lay.member_trunk_stride, 1), o0 + lay.bias_off[i])
         tree[f"layer_{i}"] = {"kernel": k if ensemble else k[0], "bias": b if ensemble else b[0]}
         d = W
-    hk = flat.as_strided((E, T, W, hd), (lay.member_head_stride, W * hd, hd, 1), lay.heads_base + lay.head_kernel_off)
-    hb = flat.as_strided((E, T, hd), (lay.member_head_stride, hd, 1), lay.heads_base + lay.head_bias_off)
+    hk = flat.as_strided((E, T, W, hd), (lay.member_head_stride, W * hd, hd, 1), o0 + lay.heads_base + lay.head_kernel_off)
+    hb = flat.as_strided((E, T, hd), (lay.member_head_stride, hd, 1), o0 + lay.heads_base + lay.head_bias_off)
     tree["VmapDense_0"] = {"kernel": hk if ensemble else hk[0], "bias": hb if ensemble else hb[0]}
     return tree
 
@@ -561,6 +563,80 @@ class MTSAC:
         ms, n = C.c_double(), _i()
         L.check(L.lib().mtrl_sac_profile_exchange(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    # ------------------------------------------------------------------ per-task gradients
+    def per_task_gradients(self, data: ReplayBufferSamples, eps_c=None, eps_a=None) -> dict:
+        """The (num_tasks, num_params) per-task gradient matrices of `compute_weights` (mtsac.py:870-1170: batch split
+        by task, `jax.vmap(jax.value_and_grad(loss))`), as CUDA tensors in the flat network layout:
+        {"critic": (T, P_critic), "actor": (T, P_actor)}.  Row t is the gradient of task t's mean loss.  Parameters are
+        not updated.  Needs all tasks on one GPU and the same number of rows per task (as the reference's reshape)."""
+        if self.world_size != 1:
+            raise NotImplementedError("per-task gradients need every task on one device")
+        self._check_status()
+        obs, act, nxt, done, rew = (self._dev(x) for x in data)
+        B, T = obs.shape[0], self.num_tasks
+        if B % T:
+            raise ValueError(f"batch of {B} rows cannot be split evenly over {T} tasks (mtsac.py:325 reshapes the same way)")
+        ec = self._dev(eps_c) if eps_c is not None else None
+        ea = self._dev(eps_a) if eps_a is not None else None
+        lc, la = self._lay.critic, self._lay.actor
+        if getattr(self, "_tg", None) is None:
+            self._tg = {"critic": torch.empty(T, lc.total, dtype=torch.float32, device=self.device),
+                        "actor": torch.empty(T, la.total, dtype=torch.float32, device=self.device)}
+        p = lambda t: _vp(t.data_ptr() if t is not None else None)  # noqa: E731
+        stream = _vp(L.current_stream_ptr())
+        L.check(L.lib().mtrl_sac_task_grads(self._h, p(obs), p(act), p(nxt), p(done), p(rew), B, p(ec), p(ea),
+                                            p(self._tg["critic"]), p(self._tg["actor"]), stream))
+        L.check(L.lib().mtrl_sac_read_status_async(self._h, _vp(self._status_host.data_ptr()), stream))
+        self._status_event.record()
+        self._status_event.synchronize()
+        code = int(self._status_host[0])
+        if code:
+            raise ValueError({1: "a batch row belongs to a task this agent does not own", 2: "the batch does not fit max_rows",
+                              3: "tasks have different numbers of rows (mtsac.py:325 needs an even split)"}.get(code, str(code)))
+        # the kernels differentiate the full-batch mean; the reference's per-task loss is the mean over the task's
+        # own B / T rows: scale by T
+        return {k: v * float(T) for k, v in self._tg.items()}
+
+    def task_gradient_view(self, flat_row: torch.Tensor, critic: bool) -> dict:
+        """Flax-named views of one row of a `per_task_gradients` matrix."""
+        c = self._cfg
+        lay = self._lay.critic if critic else self._lay.actor
+        return self._wrap_tree(flat_row, lay, (c.action_dim if critic else 0) + c.obs_dim, critic)
+
+    def compute_weights(self, data: ReplayBufferSamples, eps_c=None, eps_a=None):
+        """`MTSAC.compute_weights` (mtsac.py:870-1170), the metrics that derive from the per-task gradient matrix
+        through its Gram matrix: `{critic,actor}_avg_cos_sim`, `_avg_grad_magnitude`, `_conflict_rate`,
+        `_mean_conflict_magnitude`, `_mean_conflict_angle`, `_per_task_conflict_rate`, `_per_task_grad_magnitude`,
+        `_pairwise_conflict`, `_pairwise_cos_sim`, `_pairwise_angle`, `_pairwise_gram` (utils.py:49-72, 118-174).
+        Returns (self, logs) with device tensors.  The element-wise interference / support metrics are not built."""
+        grads = self.per_task_gradients(data, eps_c, eps_a)
+        logs = {}
+        T = self.num_tasks
+        for name, g in grads.items():
+            gram = g @ g.T
+            mag = torch.sqrt(torch.diagonal(gram).clamp_min(0))
+            cos = gram / (mag[:, None] * mag[None, :] + 1e-8)
+            off = 1 - torch.eye(T, device=g.device)
+            upper = torch.triu(torch.ones(T, T, device=g.device), diagonal=1)
+            conflict = (cos < 0).float()
+            n_off = T * (T - 1)
+            cm = torch.where((conflict * off).bool(), cos.abs() * (mag[:, None] * mag[None, :]), torch.zeros_like(cos))
+            angles = torch.rad2deg(torch.arccos(cos.clamp(-1.0, 1.0)))
+            logs.update({
+                f"{name}_avg_cos_sim": (upper * cos).sum() / (upper.sum() + 1e-8),
+                f"{name}_avg_grad_magnitude": mag.mean(),
+                f"{name}_conflict_rate": (conflict * off).sum() / n_off,
+                f"{name}_mean_conflict_magnitude": (cm * off).sum() / n_off,
+                f"{name}_mean_conflict_angle": (angles * off).sum() / n_off,
+                f"{name}_per_task_conflict_rate": (conflict * off).sum(dim=1) / (T - 1),
+                f"{name}_per_task_grad_magnitude": mag,
+                f"{name}_pairwise_conflict": conflict,
+                f"{name}_pairwise_cos_sim": cos,
+                f"{name}_pairwise_angle": angles,
+                f"{name}_pairwise_gram": gram,
+            })
+        return self, logs
 
     # ------------------------------------------------------------------ checkpoints (SURVEY 8f row 3)
     def _full_moments(self, prefix: str, critic: bool) -> dict[str, torch.Tensor]:

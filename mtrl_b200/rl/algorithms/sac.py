@@ -43,14 +43,15 @@ def _mlp_views(flat: torch.Tensor, lay, in_dim: int, ensemble: bool) -> dict:
     """Flax names of MLP (nn/base.py:38-58): layer_0..layer_{depth-1}, output Dense = layer_{depth}."""
     W, D, E, hd = lay.width, lay.depth, lay.members, lay.head_dim
     tree = {}
+    o0 = flat.storage_offset()   # as_strided offsets are absolute in the storage
     d = in_dim
     for i in range(D):
-        k = flat.as_strided((E, d, W), (lay.member_trunk_stride, W, 1), lay.kernel_off[i])
-        b = flat.as_strided((E, W), (lay.member_trunk_stride, 1), lay.bias_off[i])
+        k = flat.as_strided((E, d, W), (lay.member_trunk_stride, W, 1), o0 + lay.kernel_off[i])
+        b = flat.as_strided((E, W), (lay.member_trunk_stride, 1), o0 + lay.bias_off[i])
         tree[f"layer_{i}"] = {"kernel": k if ensemble else k[0], "bias": b if ensemble else b[0]}
         d = W
-    hk = flat.as_strided((E, W, hd), (lay.member_head_stride, hd, 1), lay.heads_base + lay.head_kernel_off)
-    hb = flat.as_strided((E, hd), (lay.member_head_stride, 1), lay.heads_base + lay.head_bias_off)
+    hk = flat.as_strided((E, W, hd), (lay.member_head_stride, hd, 1), o0 + lay.heads_base + lay.head_kernel_off)
+    hb = flat.as_strided((E, hd), (lay.member_head_stride, 1), o0 + lay.heads_base + lay.head_bias_off)
     tree[f"layer_{D}"] = {"kernel": hk if ensemble else hk[0], "bias": hb if ensemble else hb[0]}
     return tree
 

@@ -76,6 +76,26 @@ def ppo(out, steps):
                 "updates_per_s": 1e3 / ms, "trunk_tflops": flops / ms / 1e9, "workspace_gb": agent._lay.workspace_bytes / 1e9})
 
 
+def task_grads(out):
+    from mtrl_b200.presets import metaworld_mtmhsac
+    from mtrl_b200.rl.algorithms.mtsac import MTSAC
+
+    T, W, B = 50, 2048, 6400
+    mcfg, env = metaworld_mtmhsac(T, W)
+    agent = MTSAC.initialize(mcfg, env, seed=1, max_batch=B)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    obs = torch.zeros(B, 39 + T, device="cuda")
+    obs[:, :39] = torch.randn(B, 39, generator=g, device="cuda")
+    obs[torch.arange(B, device="cuda"), 39 + torch.arange(B, device="cuda") % T] = 1.0
+    batch = (obs, torch.rand(B, 4, generator=g, device="cuda") * 2 - 1, obs + 0.01, torch.zeros(B, 1, device="cuda"),
+             torch.rand(B, 1, generator=g, device="cuda") * 10)
+    ms_g = timed(lambda: agent.per_task_gradients(batch), warmup=2, steps=5)
+    ms_w = timed(lambda: agent.compute_weights(batch), warmup=1, steps=5)
+    out.append({"variant": "MT50/W2048 per-task gradient matrices (T x P) + Gram metrics (compute_weights, SURVEY 8f row 1)",
+                "rows": B, "ms_per_task_gradients": ms_g, "ms_compute_weights": ms_w,
+                "matrix_gb": (agent._lay.critic.total + agent._lay.actor.total) * T * 4 / 1e9})
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--ppo-steps", type=int, default=10_000)
@@ -85,6 +105,8 @@ if __name__ == "__main__":
     sac_baseline(res)
     torch.cuda.empty_cache()
     ppo(res, a.ppo_steps)
+    torch.cuda.empty_cache()
+    task_grads(res)
     for r in res:
         print(json.dumps(r))
     os.makedirs(os.path.dirname(a.out), exist_ok=True)

@@ -110,3 +110,25 @@ def test_input_state_not_mutated():
     assert st.opt["critic"]["count"] == 0
     for a, b in zip(O.tree_leaves(st.critic), O.tree_leaves(ref.critic)):
         assert torch.equal(a, b)
+
+
+def test_per_task_gradients_average_to_the_batch_gradient():
+    """oracle/taskgrad_oracle.py: with equally many rows per task the full-batch loss is the mean of the per-task
+    losses, so the per-task gradients must average to the gradients mtsac_update differentiates."""
+    from oracle import taskgrad_oracle as TG
+
+    cfg = O.OracleConfig(num_tasks=3, obs_dim=42, action_dim=4, width=32)
+    st = O.init_state(cfg, seed=4, dtype=torch.float64)
+    batch, ec, ea = O.synthetic_batch(cfg, 8, seed=9, dtype=torch.float64)
+    _, _, grads, _ = O.mtsac_update(st, batch, ec, ea, cfg, return_grads=True)
+    per = TG.per_task_grads(st, batch, ec, ea, cfg)
+    mean_c = O.tree_map(lambda *xs: sum(xs) / len(xs), *per["critic"])
+    for a, b in zip(O.tree_leaves(mean_c), O.tree_leaves(grads["critic"])):
+        assert torch.allclose(a, b, rtol=1e-9, atol=1e-12)
+    g = TG.flatten(per["critic"])
+    avg, cos = TG.vmap_cos_sim(g)
+    assert cos.shape == (3, 3) and torch.allclose(torch.diagonal(cos), torch.ones(3, dtype=torch.float64), atol=1e-6)
+    assert -1.0 <= float(avg) <= 1.0
+    # the actor's per-task gradients use the CURRENT critic (compute_weights, mtsac.py:1060), the update's the NEW one,
+    # so they are only compared in shape
+    assert TG.flatten(per["actor"]).shape[0] == 3

@@ -1,0 +1,67 @@
+"""Per-task gradients (MTSAC.compute_weights, mtsac.py:870-1170) from the CUDA backward + per-task dW GEMMs vs PyTorch
+autograd run one task at a time (oracle/taskgrad_oracle.py)."""
+import dataclasses
+
+import pytest
+import torch
+
+import sac_util as SU
+from oracle import mtsac_oracle as O
+from oracle import taskgrad_oracle as TG
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("T,W,per_task", [(4, 128, 32), (10, 256, 128)])
+def test_per_task_gradients_and_cos_sim(cuda, T, W, per_task):
+    cfg = O.OracleConfig(num_tasks=T, obs_dim=39 + T, action_dim=4, width=W)
+    st = O.init_state(cfg, seed=2, dtype=torch.float32)
+    # make the heads non-trivial so the tasks' gradients differ in direction
+    for net, scale in ((st.actor, 100.0), (st.critic, 30.0), (st.critic_target, 30.0)):
+        for k in ("kernel", "bias"):
+            net["heads"][k] = net["heads"][k] * scale
+    agent = SU.make_agent(cfg, per_task, seed=2)
+    SU.load_oracle_state(agent, st)
+    batch, ec, ea = O.synthetic_batch(cfg, per_task, seed=31, dtype=torch.float32)
+    before = agent._flat["critic_params"].clone()
+    got = agent.per_task_gradients(tuple(b.cuda() for b in batch), eps_c=ec.cuda(), eps_a=ea.cuda())
+    assert torch.equal(before, agent._flat["critic_params"]), "per_task_gradients must not update parameters"
+    tcfg = dataclasses.replace(cfg, matmul_operands="tf32")
+    st64 = st.to(torch.float64)
+    b64 = tuple(b.double() for b in batch)
+    ref = TG.per_task_grads(st64, b64, ec.double(), ea.double(), tcfg)
+    for name, ens in (("critic", True), ("actor", False)):
+        assert got[name].shape[0] == T
+        worst = 0.0
+        for t in range(T):
+            tree = agent.task_gradient_view(got[name][t], critic=ens)
+            for leaf, o, a in SU._pairs(ref[name][t], SU._net(tree, ens)):
+                if o.abs().max() == 0:
+                    assert float(a.abs().max()) == 0.0, (name, t, leaf)   # other tasks' heads
+                    continue
+                e = SU.rel(a, o)
+                worst = max(worst, e)
+                assert e <= 2e-2, (name, t, leaf, e)
+        # metrics: cosine-similarity matrix and its summaries (utils.py:49-72, 118-174)
+        g_ref = TG.flatten(ref[name])
+        avg_ref, cos_ref = TG.vmap_cos_sim(g_ref)
+        cm_ref = TG.conflict_metrics(cos_ref, g_ref)
+        _, logs = agent.compute_weights(tuple(b.cuda() for b in batch), eps_c=ec.cuda(), eps_a=ea.cuda())
+        cos = logs[f"{name}_pairwise_cos_sim"].double().cpu()
+        assert (cos - cos_ref).abs().max() <= 2e-2, (name, float((cos - cos_ref).abs().max()))
+        assert abs(float(logs[f"{name}_avg_cos_sim"]) - float(avg_ref)) <= 1e-2
+        mag = logs[f"{name}_per_task_grad_magnitude"].double().cpu()
+        assert SU.rel(mag, cm_ref["per_task_grad_magnitude"]) <= 1e-2
+        assert abs(float(logs[f"{name}_avg_grad_magnitude"]) - float(g_ref.norm(dim=1).mean())) <= 1e-2 * float(g_ref.norm(dim=1).mean())
+
+
+def test_uneven_split_is_rejected(cuda):
+    cfg = O.OracleConfig(num_tasks=4, obs_dim=43, action_dim=4, width=64)
+    agent = SU.make_agent(cfg, 16, seed=1)
+    batch, ec, ea = O.synthetic_batch(cfg, 16, seed=3)
+    task = batch[0][:, -4:].argmax(1)
+    keep = torch.ones(task.shape[0], dtype=torch.bool)
+    keep[(task == 1).nonzero().flatten()[:4]] = False
+    keep[(task == 2).nonzero().flatten()[:4]] = False      # 56 rows: 14 per task on average, but 16/12/12/16
+    with pytest.raises(ValueError):
+        agent.per_task_gradients(tuple(b[keep].cuda() for b in batch))
