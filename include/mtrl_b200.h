@@ -238,6 +238,16 @@ int mtrl_sac_act(mtrl_sac_t* h, const float* obs, int n, const float* eps, int d
 int mtrl_sac_task_grads(mtrl_sac_t* h, const float* obs, const float* actions, const float* next_obs, const float* dones,
                         const float* rewards, int batch, const float* eps_c, const float* eps_a, float* critic_tg,
                         float* actor_tg, void* stream);
+/* PCGradConfig (mtrl/config/optim.py:62-76): optax.chain(pcgrad(num_tasks), clip_by_global_norm, adam).  After this
+ * call mtrl_sac_update splits the critic's and / or the actor's loss by task (mtsac.py:568-585, 677-687), runs the
+ * per-task gradients through pcgrad (mtrl/optim/pcgrad.py:22-136, in coefficient space over the Gram matrix) and feeds
+ * its averaged output to clip + adam.  critic_tg / actor_tg: device fp32 (T, layout.total) work matrices; scratch: device
+ * fp32 of 2 T^2 + 2 T + 8 floats = [Gram critic | Gram actor | weights critic | weights actor | stats critic[4] |
+ * stats actor[4]], stats = n_grad_conflicts, avg_grad_magnitude, avg_grad_magnitude_before_surgery, norm of the plain
+ * mean gradient; perm_*: device int[T] row permutations (pcgrad.py:79) the caller rewrites before every update, or
+ * NULL for the identity.  T <= 64, every task on this handle, equally many rows per task. */
+int mtrl_sac_enable_pcgrad(mtrl_sac_t* h, int critic, int actor, float* critic_tg, float* actor_tg, float* scratch,
+                           const int* perm_critic, const int* perm_actor);
 /* Number of kernels one mtrl_sac_update launches (for bench.py's gpu_launches). */
 int mtrl_sac_launches_per_update(const mtrl_sac_t* h);
 /* Bracket every GEMM launch of the following updates with CUDA events on the launch stream

@@ -1,7 +1,7 @@
 """Mirror of mtrl/config/optim.py:14-43.  `spawn()` returns the description of
 optax.chain(clip_by_global_norm(max_grad_norm), adam(lr, eps)) that the fused CUDA optimiser
 (csrc/sac_kernels.cuh adam_kernel) executes; the gradient-surgery configs (optim.py:46-118) keep
-their names but are outside this hot path."""
+their names; PCGradConfig is implemented (per-task gradients + pcgrad in front of the same chain), the others raise."""
 from dataclasses import dataclass
 
 from .utils import Optimizer
@@ -16,6 +16,7 @@ class AdamChainSpec:
     b1: float = 0.9
     b2: float = 0.999
     max_grad_norm: float | None = None
+    pcgrad: bool = False   # optax.chain(pcgrad(num_tasks), clip, adam): mtrl/config/optim.py:62-76
 
 
 @dataclass(frozen=True, kw_only=True)
@@ -63,4 +64,9 @@ class PCGradConfig(OptimizerConfig):
     def requires_split_task_losses(self) -> bool:
         return True
 
-    spawn = _unsupported("PCGradConfig")
+    def spawn(self) -> AdamChainSpec:
+        """optax.chain(pcgrad(num_tasks, cosine_sim_logs), OptimizerConfig.spawn()) (optim.py:71-75) as data; the fused
+        update runs pcgrad in coefficient space over the per-task Gram matrix (csrc/sac_kernels.cuh)."""
+        import dataclasses
+
+        return dataclasses.replace(OptimizerConfig.spawn(self), pcgrad=True)

@@ -148,8 +148,13 @@ struct mtrl_sac {
   struct TaskGradCache {
     float *critic_tg = nullptr, *actor_tg = nullptr;
     int rows_per_task = 0;
+    bool fill_critic = true, fill_actor = true;                  // which networks' backward fills its matrix
     std::vector<std::vector<mtrl_gemm_plan_t*>> critic, actor;   // [layer index i = D-1-l][launch]
   } tgc;
+  // PCGrad (mtrl_sac_enable_pcgrad): which optimiser chains start with pcgrad, scratch and the row permutations
+  bool pcgrad_critic = false, pcgrad_actor = false;
+  float* pcgrad_scratch = nullptr;
+  const int *pcgrad_perm_critic = nullptr, *pcgrad_perm_actor = nullptr;
   TaskGradCache* tg_active = nullptr;   // set while mtrl_sac_task_grads runs: the backward also fills the (T, P) rows
   comm::Segment *d_segs_critic = nullptr, *d_segs_actor = nullptr;   // ownership tables (device)
   int nsegs_critic = 0, nsegs_actor = 0;
@@ -422,7 +427,7 @@ int run_trunk_backward(mtrl_sac* h, std::vector<mtrl_gemm_plan_t*>& plans, float
       }
       const int groups = l == D - 1 ? h->cfg.max_rows / kTileRows : h->cfg.max_rows / 32;
       MTRL_PROPAGATE(launch_colsum(h, jobs, groups, st));
-      if (h->tg_active) {
+      if (h->tg_active && (grads == h->buf.critic_grads ? h->tg_active->fill_critic : h->tg_active->fill_actor)) {
         // row t of the (T, P) matrix: bias slice from the task's partial column sums, kernel slice from the per-task
         // dW GEMMs (dZ of this layer is still in place; the plan below consumes it)
         const bool critic = grads == h->buf.critic_grads;
@@ -886,6 +891,9 @@ extern "C" int mtrl_sac_phase3_actor_step_alpha(mtrl_sac_t* h, void* stream) {
   return step_alpha(h, st);
 }
 
+int update_with_pcgrad(mtrl_sac* h, const float* obs, const float* actions, const float* next_obs, const float* dones,
+                       const float* rewards, int batch, const float* eps_c, const float* eps_a, cudaStream_t st);
+
 extern "C" int mtrl_sac_update(mtrl_sac_t* h, const float* obs, const float* actions, const float* next_obs,
                                const float* dones, const float* rewards, int batch, int global_batch, const float* eps_c,
                                const float* eps_a, void* stream) {
@@ -903,6 +911,7 @@ extern "C" int mtrl_sac_update(mtrl_sac_t* h, const float* obs, const float* act
     MTRL_PROPAGATE(step_actor_grads(h, st));
     return step_actor_apply(h, st);
   }
+  if (h->pcgrad_critic || h->pcgrad_actor) return update_with_pcgrad(h, obs, actions, next_obs, dones, rewards, batch, eps_c, eps_a, st);
   MTRL_PROPAGATE(mtrl_sac_phase1_critic_grads(h, obs, actions, next_obs, dones, rewards, batch, global_batch, eps_c, eps_a, stream));
   MTRL_PROPAGATE(mtrl_sac_phase2_critic_step_actor_grads(h, stream));
   MTRL_PROPAGATE(mtrl_sac_phase3_actor_step_alpha(h, stream));
@@ -1015,23 +1024,10 @@ extern "C" int mtrl_sac_trunk_owner_mask(mtrl_sac_t* h, int critic, float* mask_
   return MTRL_OK;
 }
 
-// Per-task gradients of the critic and actor losses (MTSAC.compute_weights, mtsac.py:870-1170): the batch split by
-// task, jax.vmap(jax.value_and_grad(loss)) over the task axis.  Writes row t of critic_tg (T, critic layout.total) and
-// actor_tg (T, actor layout.total) in the flat network layout; parameters are NOT updated.  Gradients are those of the
-// full-batch losses restricted to task t's rows, i.e. (n_t / B) x the reference's per-task-mean gradients (the caller
-// rescales).  Needs all tasks on this handle and the same number of rows for every task.
-extern "C" int mtrl_sac_task_grads(mtrl_sac_t* h, const float* obs, const float* actions, const float* next_obs,
-                                   const float* dones, const float* rewards, int batch, const float* eps_c,
-                                   const float* eps_a, float* critic_tg, float* actor_tg, void* stream) {
-  MTRL_REQUIRE(h && critic_tg && actor_tg, "mtrl_sac_task_grads: null argument");
+// Grouped per-task dW plans for the (T, P) gradient matrices at critic_tg / actor_tg with R packed rows per task.
+int ensure_task_plans(mtrl_sac* h, float* critic_tg, float* actor_tg, int R) {
   const mtrl_sac_config_t& c = h->cfg;
-  MTRL_REQUIRE(c.variant == MTRL_VARIANT_MTSAC && c.num_local_tasks == c.num_tasks && !h->comm,
-               "mtrl_sac_task_grads: needs the multi-task variant with every task on one handle");
   const int T = c.num_tasks, D = c.depth, E = c.num_critics, W = c.width;
-  MTRL_REQUIRE(batch % T == 0, "mtrl_sac_task_grads: batch %d is not a multiple of the %d tasks", batch, T);
-  const int R = static_cast<int>(round_up(batch / T, kTileRows));
-  MTRL_REQUIRE(static_cast<long long>(R) * T <= c.max_rows, "mtrl_sac_task_grads: %d rows per task do not fit max_rows", R);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   Workspace& w = h->ws;
   const mtrl_net_layout_t& LA = h->lay.actor;
   const mtrl_net_layout_t& LC = h->lay.critic;
@@ -1073,6 +1069,119 @@ extern "C" int mtrl_sac_task_grads(mtrl_sac_t* h, const float* obs, const float*
     tc.actor_tg = actor_tg;
     tc.rows_per_task = R;
   }
+  return MTRL_OK;
+}
+
+// pcgrad (mtrl/optim/pcgrad.py) on one network's (T, P) matrix: Gram -> projection coefficients -> the averaged
+// projected gradient written over the network's gradient buffer (what the rest of the chain, clip + adam, consumes).
+int pcgrad_combine(mtrl_sac* h, bool critic, cudaStream_t st) {
+  const int T = h->cfg.num_tasks;
+  const mtrl_net_layout_t& L = critic ? h->lay.critic : h->lay.actor;
+  float* tg = critic ? h->tgc.critic_tg : h->tgc.actor_tg;
+  float* grads = critic ? h->buf.critic_grads : h->buf.actor_grads;
+  float* gram = h->pcgrad_scratch + (critic ? 0 : T * T);
+  float* wts = h->pcgrad_scratch + 2 * T * T + (critic ? 0 : T);
+  float* stats = h->pcgrad_scratch + 2 * T * T + 2 * T + (critic ? 0 : 4);
+  MTRL_CUDA_CHECK(cudaMemsetAsync(gram, 0, static_cast<size_t>(T) * T * sizeof(float), st));
+  gram_kernel<<<h->sms * 2, 256, 0, st>>>(tg, L.total, T, L.total, gram, T);
+  pcgrad_coeff_kernel<<<1, 64, 2 * T * T * sizeof(float), st>>>(gram, T, T, static_cast<float>(T) * static_cast<float>(T),
+                                                                critic ? h->pcgrad_perm_critic : h->pcgrad_perm_actor, wts, stats);
+  weighted_rows_kernel<<<h->sms * 4, 256, 0, st>>>(tg, L.total, T, wts, grads, L.total);
+  MTRL_CUDA_CHECK(cudaGetLastError());
+  h->launches += 4;
+  return head_sumsq_to_slot(h, grads, L, critic ? ACC_CRITIC_HEAD_G2 : ACC_ACTOR_HEAD_G2, st);
+}
+
+// MTSAC.update when an optimiser chain starts with pcgrad (PCGradConfig, mtrl/config/optim.py:62-76): the losses are
+// split by task (mtsac.py:568-585, 677-687), the per-task gradients go through pcgrad and its output through clip + adam.
+int update_with_pcgrad(mtrl_sac* h, const float* obs, const float* actions, const float* next_obs, const float* dones,
+                       const float* rewards, int batch, const float* eps_c, const float* eps_a, cudaStream_t st) {
+  const mtrl_sac_config_t& c = h->cfg;
+  const int T = c.num_tasks, E = c.num_critics, W = c.width;
+  MTRL_REQUIRE(batch % T == 0, "pcgrad: batch %d is not a multiple of the %d tasks (the split losses reshape it)", batch, T);
+  const int R = static_cast<int>(round_up(batch / T, kTileRows));
+  MTRL_REQUIRE(static_cast<long long>(R) * T <= c.max_rows, "pcgrad: %d rows per task do not fit max_rows", R);
+  const mtrl_net_layout_t& LA = h->lay.actor;
+  const mtrl_net_layout_t& LC = h->lay.critic;
+  MTRL_PROPAGATE(ensure_task_plans(h, h->tgc.critic_tg, h->tgc.actor_tg, R));
+  mtrl_sac::TaskGradCache& tc = h->tgc;
+  tc.fill_critic = h->pcgrad_critic;
+  tc.fill_actor = h->pcgrad_actor;
+  MTRL_PROPAGATE(step_begin(h, obs, actions, next_obs, dones, rewards, batch, batch, eps_c, eps_a, st));
+  check_balanced_kernel<<<1, 64, 0, st>>>(h->ws.seg_start, h->ws.slot_src, T, R, batch / T, h->ws.status);
+  MTRL_CUDA_CHECK(cudaGetLastError());
+  if (h->pcgrad_critic) MTRL_CUDA_CHECK(cudaMemsetAsync(tc.critic_tg, 0, static_cast<size_t>(T) * LC.total * sizeof(float), st));
+  h->tg_active = &tc;
+  int rc = step_critic_grads(h, st);
+  h->tg_active = nullptr;
+  MTRL_PROPAGATE(rc);
+  if (h->pcgrad_critic) {
+    task_heads_kernel<<<dim3(T, E), 256, 0, st>>>(h->buf.critic_grads, tc.critic_tg, LC.total, LC.heads_base, LC.member_head_stride,
+                                                  LC.head_kernel_off, LC.head_bias_off, W, 1);
+    MTRL_PROPAGATE(pcgrad_combine(h, true, st));
+  }
+  MTRL_PROPAGATE(step_critic_apply(h, st));
+  MTRL_PROPAGATE(step_actor_sample(h, true, st));
+  if (h->pcgrad_actor) MTRL_CUDA_CHECK(cudaMemsetAsync(tc.actor_tg, 0, static_cast<size_t>(T) * LA.total * sizeof(float), st));
+  h->tg_active = &tc;
+  rc = step_actor_grads(h, st);
+  h->tg_active = nullptr;
+  MTRL_PROPAGATE(rc);
+  if (h->pcgrad_actor) {
+    task_heads_kernel<<<dim3(T, 1), 256, 0, st>>>(h->buf.actor_grads, tc.actor_tg, LA.total, LA.heads_base, LA.member_head_stride,
+                                                  LA.head_kernel_off, LA.head_bias_off, W * 2 * c.action_dim, 2 * c.action_dim);
+    MTRL_PROPAGATE(pcgrad_combine(h, false, st));
+  }
+  MTRL_PROPAGATE(step_actor_apply(h, st));
+  return step_alpha(h, st);
+}
+
+// Puts pcgrad in front of the critic's and / or the actor's optimiser chain.  critic_tg / actor_tg: device fp32
+// (T, layout.total) matrices; scratch: device fp32, 2 T^2 + 2 T + 8 floats (Gram matrices, weights, statistics: per
+// network n_grad_conflicts, avg_grad_magnitude, avg_grad_magnitude_before_surgery, norm of the plain mean gradient);
+// perm_*: device int[T] row permutations (pcgrad.py:79), rewritten by the caller before every update, or NULL.
+extern "C" int mtrl_sac_enable_pcgrad(mtrl_sac_t* h, int critic, int actor, float* critic_tg, float* actor_tg, float* scratch,
+                                      const int* perm_critic, const int* perm_actor) {
+  MTRL_REQUIRE(h && critic_tg && actor_tg && scratch, "mtrl_sac_enable_pcgrad: null argument");
+  MTRL_REQUIRE(h->cfg.variant == MTRL_VARIANT_MTSAC && h->cfg.num_local_tasks == h->cfg.num_tasks && !h->comm,
+               "mtrl_sac_enable_pcgrad: needs the multi-task variant with every task on one handle");
+  MTRL_REQUIRE(h->cfg.num_tasks <= 64, "mtrl_sac_enable_pcgrad: at most 64 tasks");
+  h->pcgrad_critic = critic != 0;
+  h->pcgrad_actor = actor != 0;
+  if (h->tgc.critic_tg != critic_tg || h->tgc.actor_tg != actor_tg) {
+    h->tgc.critic_tg = critic_tg;
+    h->tgc.actor_tg = actor_tg;
+    h->tgc.rows_per_task = 0;   // plans are rebuilt for the new matrices at the next update
+  }
+  h->pcgrad_scratch = scratch;
+  h->pcgrad_perm_critic = perm_critic;
+  h->pcgrad_perm_actor = perm_actor;
+  return MTRL_OK;
+}
+
+// Per-task gradients of the critic and actor losses (MTSAC.compute_weights, mtsac.py:870-1170): the batch split by
+// task, jax.vmap(jax.value_and_grad(loss)) over the task axis.  Writes row t of critic_tg (T, critic layout.total) and
+// actor_tg (T, actor layout.total) in the flat network layout; parameters are NOT updated.  Gradients are those of the
+// full-batch losses restricted to task t's rows, i.e. (n_t / B) x the reference's per-task-mean gradients (the caller
+// rescales).  Needs all tasks on this handle and the same number of rows for every task.
+extern "C" int mtrl_sac_task_grads(mtrl_sac_t* h, const float* obs, const float* actions, const float* next_obs,
+                                   const float* dones, const float* rewards, int batch, const float* eps_c,
+                                   const float* eps_a, float* critic_tg, float* actor_tg, void* stream) {
+  MTRL_REQUIRE(h && critic_tg && actor_tg, "mtrl_sac_task_grads: null argument");
+  const mtrl_sac_config_t& c = h->cfg;
+  MTRL_REQUIRE(c.variant == MTRL_VARIANT_MTSAC && c.num_local_tasks == c.num_tasks && !h->comm,
+               "mtrl_sac_task_grads: needs the multi-task variant with every task on one handle");
+  const int T = c.num_tasks, D = c.depth, E = c.num_critics, W = c.width;
+  MTRL_REQUIRE(batch % T == 0, "mtrl_sac_task_grads: batch %d is not a multiple of the %d tasks", batch, T);
+  const int R = static_cast<int>(round_up(batch / T, kTileRows));
+  MTRL_REQUIRE(static_cast<long long>(R) * T <= c.max_rows, "mtrl_sac_task_grads: %d rows per task do not fit max_rows", R);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Workspace& w = h->ws;
+  const mtrl_net_layout_t& LA = h->lay.actor;
+  const mtrl_net_layout_t& LC = h->lay.critic;
+  MTRL_PROPAGATE(ensure_task_plans(h, critic_tg, actor_tg, R));
+  mtrl_sac::TaskGradCache& tc = h->tgc;
+  tc.fill_critic = tc.fill_actor = true;
   MTRL_CUDA_CHECK(cudaMemsetAsync(critic_tg, 0, static_cast<size_t>(T) * LC.total * sizeof(float), st));
   MTRL_CUDA_CHECK(cudaMemsetAsync(actor_tg, 0, static_cast<size_t>(T) * LA.total * sizeof(float), st));
   MTRL_PROPAGATE(step_begin(h, obs, actions, next_obs, dones, rewards, batch, batch, eps_c, eps_a, st));

@@ -907,6 +907,130 @@ static __global__ void check_balanced_kernel(const int* __restrict__ seg_start, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// PCGrad (mtrl/optim/pcgrad.py:22-136) in coefficient space.  Every projected gradient stays in the span of the task
+// gradients, g_i_pc = sum_k c_ik g_k, so the whole sequential projection loop (:58-69) only needs the Gram matrix
+// G = g g^T: <g_i_pc, g_j> = sum_k c_ik G_kj.  One block, thread i owns row i of C (in shared memory).
+//   gram   : (T, ldg) of the UNSCALED rows; gscale = T^2 turns it into the Gram of the reference's per-task-mean
+//            gradients (the 1e-8 in the projection denominator is not scale free)
+//   perm   : the row permutation of :79 (position -> task); identity when null
+//   w_out  : (T) weights with  mean_i g_i_pc(reference scale) = sum_k w_out[k] * (unscaled row k)
+//   stats  : [0] n_grad_conflicts (:71), [1] avg_grad_magnitude after surgery (:85), [2] before (:86-88),
+//            [3] norm of the plain mean gradient (what the algorithm logs as grad magnitude, mtsac.py:583-585, 619)
+// ---------------------------------------------------------------------------------------------
+static __global__ void pcgrad_coeff_kernel(const float* __restrict__ gram, int ldg, int T, float gscale, const int* __restrict__ perm,
+                                           float* __restrict__ w_out, float* __restrict__ stats) {
+  extern __shared__ float pcg_sm[];   // G[T][T] (permuted, scaled) then C[T][T]
+  float* G = pcg_sm;
+  float* Cm = pcg_sm + T * T;
+  __shared__ float red_conf[64], red_after[64], red_before[64];
+  const int i = threadIdx.x;
+  for (int idx = threadIdx.x; idx < T * T; idx += blockDim.x) {
+    const int a = idx / T, b = idx % T;
+    const int ta = perm ? perm[a] : a, tb = perm ? perm[b] : b;
+    G[idx] = gram[static_cast<long long>(ta) * ldg + tb] * gscale;
+    Cm[idx] = a == b ? 1.f : 0.f;
+  }
+  __syncthreads();
+  float conf = 0.f, after = 0.f, before = 0.f;
+  if (i < T) {
+    float* c = Cm + i * T;
+    for (int j = 0; j < T; ++j) {
+      float dot = 0.f;
+      for (int k = 0; k < T; ++k) dot = fmaf(c[k], G[k * T + j], dot);
+      const float proj = dot / (G[j * T + j] + 1e-8f);
+      if (proj < 0.f) {
+        c[j] -= proj;
+        conf += 1.f;
+      }
+    }
+    float q = 0.f;
+    for (int a = 0; a < T; ++a) {
+      float r = 0.f;
+      for (int b = 0; b < T; ++b) r = fmaf(G[a * T + b], c[b], r);
+      q = fmaf(c[a], r, q);
+    }
+    after = sqrtf(fmaxf(q, 0.f));
+    before = sqrtf(fmaxf(G[i * T + i], 0.f));
+  }
+  if (i < 64) { red_conf[i] = conf; red_after[i] = after; red_before[i] = before; }
+  __syncthreads();
+  if (i < T) {
+    // column sums of C: position k of the permuted order is task perm[k]
+    float wsum = 0.f;
+    for (int r = 0; r < T; ++r) wsum += Cm[r * T + i];
+    // mean over tasks (1 / T) of reference-scale rows (T x unscaled) -> plain sum of unscaled rows
+    w_out[perm ? perm[i] : i] = wsum;
+  }
+  if (i == 0) {
+    float sc = 0.f, sa = 0.f, sb = 0.f, all = 0.f;
+    for (int r = 0; r < T; ++r) { sc += red_conf[r]; sa += red_after[r]; sb += red_before[r]; }
+    for (int idx = 0; idx < T * T; ++idx) all += G[idx];
+    stats[0] = sc * 0.5f;
+    stats[1] = sa / T;
+    stats[2] = sb / T;
+    stats[3] = sqrtf(fmaxf(all, 0.f)) / T;
+  }
+}
+
+// out[p] = sum_k w[k] * rows[k][p]   (HBM-bound: reads the (T, P) matrix once)
+static __global__ void weighted_rows_kernel(const float* __restrict__ rows, long long ld, int T, const float* __restrict__ w,
+                                            float* __restrict__ out, long long P) {
+  __shared__ float sw[64];
+  if (threadIdx.x < T) sw[threadIdx.x] = w[threadIdx.x];
+  __syncthreads();
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < P / 4; i += stride) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int k = 0; k < T; ++k) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(rows + k * ld) + i);
+      acc.x = fmaf(sw[k], v.x, acc.x); acc.y = fmaf(sw[k], v.y, acc.y);
+      acc.z = fmaf(sw[k], v.z, acc.z); acc.w = fmaf(sw[k], v.w, acc.w);
+    }
+    reinterpret_cast<float4*>(out)[i] = acc;
+  }
+}
+
+// G[a][b] += sum_p rows[a][p] rows[b][p] over this block's column range (fp32 CUDA cores; T <= 64).
+// grid.x blocks of 256 threads; thread (a, b-group) register-tiles 4 x 4 Gram entries over a shared (T x 64) tile.
+static __global__ void gram_kernel(const float* __restrict__ rows, long long ld, int T, long long P, float* __restrict__ gram, int ldg) {
+  __shared__ float tile[64][65];
+  const int ta = (threadIdx.x / 16) * 4, tb = (threadIdx.x % 16) * 4;   // 16 x 16 threads cover 64 x 64 entries
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  const long long per = ((P + gridDim.x - 1) / gridDim.x + 63) / 64 * 64;
+  const long long p0 = per * blockIdx.x, p1 = min(P, p0 + per);
+  for (long long c0 = p0; c0 < p1; c0 += 64) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 64 * 64; idx += blockDim.x) {
+      const int r = idx / 64, cc = idx % 64;
+      tile[r][cc] = (r < T && c0 + cc < p1) ? rows[r * ld + c0 + cc] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int cc = 0; cc < 64; ++cc) {
+      float va[4], vb[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) va[a] = tile[ta + a][cc];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) vb[b] = tile[tb + b][cc];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(va[a], vb[b], acc[a][b]);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      if (ta + a < T && tb + b < T) atomicAdd(&gram[(ta + a) * ldg + tb + b], acc[a][b]);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Optimiser: optax.chain(clip_by_global_norm, adam) + apply_updates (config/optim.py:26-43,
 // algorithms/utils.py:11-46) over the flat parameter buffer of a network, fused with the Polyak
 // target update (mtsac.py:607-613) and the tf32 operand copies the GEMMs read.

@@ -91,6 +91,7 @@ L._EXTRA_DECLS.update({
     "mtrl_sac_read_status_async": ([_vp, _vp, _vp],),
     "mtrl_sac_act": ([_vp, _vp, _i, _vp, _i, _vp, _vp],),
     "mtrl_sac_task_grads": ([_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp],),
+    "mtrl_sac_enable_pcgrad": ([_vp, _i, _i, _vp, _vp, _vp, _vp, _vp],),
     "mtrl_sac_trunk_owner_mask": ([_vp, _i, _vp],),
     "mtrl_sac_profile_gemms": ([_vp, _i],),
     "mtrl_sac_profile_read": ([_vp, C.POINTER(C.c_double), C.POINTER(_i)],),
@@ -316,7 +317,40 @@ class MTSAC:
         la.fill_(math.log(config.initial_temperature))
 
         self._create_handle()
+        self._pcgrad = (bool(c_opt.pcgrad), bool(a_opt.pcgrad))
+        if any(self._pcgrad):
+            if world_size != 1:
+                raise NotImplementedError("PCGradConfig needs every task on one device (split losses)")
+            if config.num_tasks > 64:
+                raise NotImplementedError("PCGradConfig: at most 64 tasks")
+            self._enable_pcgrad(seed)
         return self
+
+    def _task_matrices(self) -> dict:
+        """(T, P) work matrices of the per-task gradient path, allocated on first use."""
+        if getattr(self, "_tg", None) is None:
+            T = self.num_tasks
+            self._tg = {"critic": torch.zeros(T, self._lay.critic.total, dtype=torch.float32, device=self.device),
+                        "actor": torch.zeros(T, self._lay.actor.total, dtype=torch.float32, device=self.device)}
+        return self._tg
+
+    def _enable_pcgrad(self, seed: int) -> None:
+        T = self.num_tasks
+        tg = self._task_matrices()
+        self._pc_scratch = torch.zeros(2 * T * T + 2 * T + 8, dtype=torch.float32, device=self.device)
+        self._pc_perm = torch.arange(T, dtype=torch.int32, device=self.device).repeat(2, 1).contiguous()
+        self._pc_gen = torch.Generator().manual_seed(int(seed) + 7919)
+        L.check(L.lib().mtrl_sac_enable_pcgrad(self._h, int(self._pcgrad[0]), int(self._pcgrad[1]), _vp(tg["critic"].data_ptr()),
+                                               _vp(tg["actor"].data_ptr()), _vp(self._pc_scratch.data_ptr()),
+                                               _vp(self._pc_perm[0].data_ptr()), _vp(self._pc_perm[1].data_ptr())))
+
+    def pcgrad_stats(self) -> dict:
+        """PCGradState of the last update per network (pcgrad.py:12-17, 83-90) as device scalars, plus the norm of the
+        plain mean gradient."""
+        T, s = self.num_tasks, self._pc_scratch
+        base = 2 * T * T + 2 * T
+        names = ("n_grad_conflicts", "avg_grad_magnitude", "avg_grad_magnitude_before_surgery", "mean_grad_norm")
+        return {net: dict(zip(names, s[base + 4 * i: base + 4 * i + 4])) for i, net in enumerate(("critic", "actor")) if self._pcgrad[i]}
 
     def _allocate(self, dev, t_local: int) -> None:
         """Ask the library for the flat layouts of self._cfg and allocate every device buffer it needs."""
@@ -438,7 +472,7 @@ class MTSAC:
                 raise ValueError("update: the batch does not fit max_rows (rows per task are padded to 128)")
 
     def update(self, data: ReplayBufferSamples, eps_c=None, eps_a=None, *, global_batch: int | None = None,
-               check: bool = False, graph: bool | None = None):
+               check: bool = False, graph: bool | None = None, pcgrad_perm=None):
         """`MTSAC.update` (mtsac.py:1249-1251).  Returns (self, logs) with logs as 0-dim device tensors in
         the reference's keys; nothing here synchronises the host unless `check=True`.
 
@@ -455,6 +489,13 @@ class MTSAC:
         assert data[0].shape[1] == self._cfg.obs_dim and tuple(data[1].shape) == (B, self._cfg.action_dim)
         if graph is None:
             graph = _GRAPH_DEFAULT
+        if any(getattr(self, "_pcgrad", (False, False))):
+            # the row permutation pcgrad draws every step (pcgrad.py:79; jax key there, a seeded host generator here),
+            # one per network, or the caller's `pcgrad_perm = (critic_perm, actor_perm)`
+            T = self.num_tasks
+            perms = pcgrad_perm if pcgrad_perm is not None else (torch.randperm(T, generator=self._pc_gen),
+                                                                 torch.randperm(T, generator=self._pc_gen))
+            self._pc_perm.copy_(torch.stack([torch.as_tensor(x).to(torch.int32) for x in perms]), non_blocking=True)
         key = (B, eps_c is not None, global_batch)
         entry = None
         if self.world_size > 1 and self.exchange == "nccl":
@@ -580,9 +621,7 @@ class MTSAC:
         ec = self._dev(eps_c) if eps_c is not None else None
         ea = self._dev(eps_a) if eps_a is not None else None
         lc, la = self._lay.critic, self._lay.actor
-        if getattr(self, "_tg", None) is None:
-            self._tg = {"critic": torch.empty(T, lc.total, dtype=torch.float32, device=self.device),
-                        "actor": torch.empty(T, la.total, dtype=torch.float32, device=self.device)}
+        self._task_matrices()
         p = lambda t: _vp(t.data_ptr() if t is not None else None)  # noqa: E731
         stream = _vp(L.current_stream_ptr())
         L.check(L.lib().mtrl_sac_task_grads(self._h, p(obs), p(act), p(nxt), p(done), p(rew), B, p(ec), p(ea),

@@ -14,33 +14,58 @@ import torch
 from . import mtsac_oracle as O
 
 
-def per_task_grads(state: O.OracleState, batch, eps_c, eps_a, cfg: O.OracleConfig):
-    """({'critic': [tree per task], 'actor': [tree per task]}): gradients of the per-task mean losses."""
+def _targets(state: O.OracleState, batch, eps_c, cfg: O.OracleConfig):
     obs, actions, next_obs, dones, rewards = batch
     T = cfg.num_tasks
-    task = obs[..., -T:].argmax(dim=-1)
     alpha_vals = torch.exp(obs[..., -T:] @ state.log_alpha.reshape(-1, 1))
-    with torch.no_grad():   # mtsac.py:995-1006: target computed once from the current actor and target critic
+    with torch.no_grad():   # mtsac.py:995-1006 / :526-553: target computed once from the current actor and target critic
         next_actions, next_logp = O.actor_sample_and_log_prob(state.actor, next_obs, eps_c, cfg)
         q_t = O.critic_forward(state.critic_target, next_obs, next_actions, cfg)
         target = rewards + (1 - dones) * cfg.gamma * (q_t.min(dim=0).values - alpha_vals * next_logp.reshape(-1, 1))
         if cfg.clip:
             target = torch.clamp(target, -5000, 5000)
-    out = {"critic": [], "actor": []}
-    for t in range(T):
+    return alpha_vals, target
+
+
+def critic_task_grads(critic: dict, batch, target, cfg: O.OracleConfig) -> list:
+    """Per-task gradients of the critic loss (mean over the task's rows and the ensemble, :1022-1025 / :562-566)."""
+    obs, actions = batch[0], batch[1]
+    task = obs[..., -cfg.num_tasks:].argmax(dim=-1)
+    out = []
+    for t in range(cfg.num_tasks):
         rows = task == t
-        cp = O._with_grad(state.critic)
+        cp = O._with_grad(critic)
         q_pred = O.critic_forward(cp, obs[rows], actions[rows], cfg)
         if cfg.clip:
             q_pred = torch.clamp(q_pred, -5000, 5000)
-        ((q_pred - target[rows]) ** 2).mean().backward()                      # :1022-1025 (mean over ensemble and rows)
-        out["critic"].append(O._grads_of(cp))
-        ap = O._with_grad(state.actor)
-        a, logp = O.actor_sample_and_log_prob(ap, obs[rows], eps_a[rows], cfg)
-        q_pi = O.critic_forward(state.critic, obs[rows], a, cfg)              # :1060-1062: the CURRENT critic params
-        (alpha_vals[rows] * logp.reshape(-1, 1) - q_pi.min(dim=0).values).mean().backward()   # :1067
-        out["actor"].append(O._grads_of(ap))
+        ((q_pred - target[rows]) ** 2).mean().backward()
+        out.append(O._grads_of(cp))
     return out
+
+
+def actor_task_grads(actor: dict, critic: dict, batch, alpha_vals, eps_a, cfg: O.OracleConfig):
+    """Per-task gradients of the actor loss (:1049-1069 / :631-666) against the given critic parameters; also returns
+    the (detached) log-probs in batch order, which the temperature step consumes."""
+    obs = batch[0]
+    task = obs[..., -cfg.num_tasks:].argmax(dim=-1)
+    out, logp_all = [], torch.zeros(obs.shape[0], dtype=obs.dtype)
+    for t in range(cfg.num_tasks):
+        rows = task == t
+        ap = O._with_grad(actor)
+        a, logp = O.actor_sample_and_log_prob(ap, obs[rows], eps_a[rows], cfg)
+        q_pi = O.critic_forward(critic, obs[rows], a, cfg)
+        (alpha_vals[rows] * logp.reshape(-1, 1) - q_pi.min(dim=0).values).mean().backward()
+        out.append(O._grads_of(ap))
+        logp_all[rows] = logp.detach()
+    return out, logp_all
+
+
+def per_task_grads(state: O.OracleState, batch, eps_c, eps_a, cfg: O.OracleConfig):
+    """compute_weights (:870-1170): {'critic': [tree per task], 'actor': [tree per task]}; the actor loss is taken
+    against the CURRENT critic parameters (:1060-1062)."""
+    alpha_vals, target = _targets(state, batch, eps_c, cfg)
+    return {"critic": critic_task_grads(state.critic, batch, target, cfg),
+            "actor": actor_task_grads(state.actor, state.critic, batch, alpha_vals, eps_a, cfg)[0]}
 
 
 def flatten(trees) -> torch.Tensor:
@@ -69,3 +94,68 @@ def conflict_metrics(cos: torch.Tensor, g: torch.Tensor) -> dict:
     return {"conflict_rate": (conflict * off).sum() / n_off, "mean_conflict_magnitude": (cm * off).sum() / n_off,
             "mean_conflict_angle": (angles * off).sum() / n_off,
             "per_task_conflict_rate": (conflict * off).sum(dim=1) / (T - 1), "per_task_grad_magnitude": mag}
+
+
+# --------------------------------------------------------------------------------------------
+# pcgrad (mtrl/optim/pcgrad.py:22-136) and the update that uses it (PCGradConfig, mtrl/config/optim.py:62-76)
+# --------------------------------------------------------------------------------------------
+def pcgrad(flat: torch.Tensor, perm: torch.Tensor | None = None):
+    """pcgrad.py:58-83 literally: rows permuted (:79; the reference draws the permutation from a jax key, here it is an
+    argument), every row projected sequentially against ALL rows in that order (:60-69), result averaged over tasks (:81).
+    Returns (avg_grad, stats)."""
+    g = flat if perm is None else flat[perm]
+    T = g.shape[0]
+    out, total = [], 0
+    for i in range(T):
+        gi = g[i].clone()
+        for j in range(T):
+            proj = torch.dot(gi, g[j]) / ((g[j] ** 2).sum() + 1e-8)
+            gi = gi - torch.minimum(proj, torch.zeros_like(proj)) * g[j]
+            total += int(proj < 0)
+        out.append(gi)
+    final = torch.stack(out)
+    stats = {"n_grad_conflicts": total / 2, "avg_grad_magnitude": final.norm(dim=1).mean(),
+             "avg_grad_magnitude_before_surgery": g.norm(dim=1).mean()}
+    return final.mean(dim=0), stats
+
+
+def _unflatten(flat: torch.Tensor, like) -> dict:
+    leaves, off = [], 0
+    for x in O.tree_leaves(like):
+        leaves.append(flat[off:off + x.numel()].reshape(x.shape))
+        off += x.numel()
+    it = iter(leaves)
+    return O.tree_map(lambda x: next(it), like)
+
+
+def mtsac_update_pcgrad(state: O.OracleState, batch, eps_c, eps_a, cfg: O.OracleConfig, perm_c=None, perm_a=None,
+                        critic: bool = True, actor: bool = True):
+    """MTSAC.update (mtsac.py:1173-1251) with split losses and optax.chain(pcgrad, clip_by_global_norm, adam) on the
+    chosen networks; the other network keeps the plain chain.  Returns (new_state, stats)."""
+    obs = batch[0]
+    T = cfg.num_tasks
+    opt = dict(state.opt)
+    alpha_vals, target = _targets(state, batch, eps_c, cfg)
+    stats = {}
+    ctg = critic_task_grads(state.critic, batch, target, cfg)
+    if critic:
+        flat, stats["critic"] = pcgrad(flatten(ctg), perm_c)
+        cgrads = _unflatten(flat, state.critic)
+    else:
+        cgrads = O.tree_map(lambda *xs: sum(xs) / len(xs), *ctg)
+    new_critic, opt["critic"] = O.adam_step(state.critic, cgrads, opt["critic"], cfg.lr, cfg.adam_eps, cfg.b1, cfg.b2,
+                                            cfg.max_grad_norm)
+    new_target = O.tree_map(lambda n, t: cfg.tau * n + (1 - cfg.tau) * t, new_critic, state.critic_target)
+    atg, logp = actor_task_grads(state.actor, new_critic, batch, alpha_vals, eps_a, cfg)
+    if actor:
+        flat, stats["actor"] = pcgrad(flatten(atg), perm_a)
+        agrads = _unflatten(flat, state.actor)
+    else:
+        agrads = O.tree_map(lambda *xs: sum(xs) / len(xs), *atg)
+    new_actor, opt["actor"] = O.adam_step(state.actor, agrads, opt["actor"], cfg.lr, cfg.adam_eps, cfg.b1, cfg.b2,
+                                          cfg.max_grad_norm)
+    la = state.log_alpha.detach().clone().requires_grad_(True)
+    (-(obs[..., -T:] @ la.reshape(-1, 1)) * (logp.reshape(-1, 1) + cfg.target_entropy)).mean().backward()
+    new_la, opt["alpha"] = O.adam_step(state.log_alpha, la.grad, opt["alpha"], cfg.alpha_lr, cfg.adam_eps, cfg.b1, cfg.b2,
+                                       cfg.alpha_max_grad_norm)
+    return O.OracleState(new_actor, new_critic, new_target, new_la, opt), stats

@@ -91,6 +91,20 @@ def task_grads(out):
              torch.rand(B, 1, generator=g, device="cuda") * 10)
     ms_g = timed(lambda: agent.per_task_gradients(batch), warmup=2, steps=5)
     ms_w = timed(lambda: agent.compute_weights(batch), warmup=1, steps=5)
+    # the same update with PCGradConfig on both networks
+    import dataclasses
+
+    from mtrl_b200.config.optim import PCGradConfig
+    pc = PCGradConfig(max_grad_norm=1.0, num_tasks=T)
+    net = dataclasses.replace(mcfg.actor_config.network_config, optimizer=pc)
+    pcfg = dataclasses.replace(mcfg, actor_config=dataclasses.replace(mcfg.actor_config, network_config=net),
+                               critic_config=dataclasses.replace(mcfg.critic_config, network_config=net))
+    del agent
+    torch.cuda.empty_cache()
+    pagent = MTSAC.initialize(pcfg, env, seed=1, max_batch=B)
+    ms_pc = timed(lambda: pagent.update(batch), warmup=3, steps=10)
+    out.append({"variant": "MT50/W2048 MT-SAC update with PCGradConfig on actor and critic", "rows": B, "ms_per_update": ms_pc,
+                "updates_per_s": 1e3 / ms_pc, "n_grad_conflicts_critic": float(pagent.pcgrad_stats()["critic"]["n_grad_conflicts"])})
     out.append({"variant": "MT50/W2048 per-task gradient matrices (T x P) + Gram metrics (compute_weights, SURVEY 8f row 1)",
                 "rows": B, "ms_per_task_gradients": ms_g, "ms_compute_weights": ms_w,
                 "matrix_gb": (agent._lay.critic.total + agent._lay.actor.total) * T * 4 / 1e9})

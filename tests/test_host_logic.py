@@ -72,6 +72,11 @@ def test_optimizer_configs_outside_the_path_fail_loudly():
 
     with pytest.raises(NotImplementedError):
         OptimizerConfig(optimizer=Optimizer.SGD).spawn()
+    from mtrl_b200.config.optim import DummyMultiTaskConfig
+
     assert PCGradConfig(num_tasks=3).requires_split_task_losses
+    spec = PCGradConfig(num_tasks=3, max_grad_norm=1.0).spawn()   # chain(pcgrad, clip, adam) as data (optim.py:71-75)
+    assert spec.pcgrad and spec.max_grad_norm == 1.0 and spec.eps == 1e-5
+    assert not OptimizerConfig().spawn().pcgrad
     with pytest.raises(NotImplementedError):
-        PCGradConfig(num_tasks=3).spawn()
+        DummyMultiTaskConfig().spawn()

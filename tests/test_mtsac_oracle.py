@@ -132,3 +132,23 @@ def test_per_task_gradients_average_to_the_batch_gradient():
     # the actor's per-task gradients use the CURRENT critic (compute_weights, mtsac.py:1060), the update's the NEW one,
     # so they are only compared in shape
     assert TG.flatten(per["actor"]).shape[0] == 3
+
+
+def test_split_update_without_surgery_equals_plain_update():
+    """oracle/taskgrad_oracle.py: averaging the per-task gradients (what the split-loss branch does without pcgrad,
+    mtsac.py:581-585) must reproduce mtsac_update exactly; with pcgrad the conflict count is symmetric (pairs / 2)."""
+    from oracle import taskgrad_oracle as TG
+
+    cfg = O.OracleConfig(num_tasks=3, obs_dim=42, action_dim=4, width=32)
+    st = O.init_state(cfg, seed=4, dtype=torch.float64)
+    batch, ec, ea = O.synthetic_batch(cfg, 8, seed=9, dtype=torch.float64)
+    ns, _ = TG.mtsac_update_pcgrad(st, batch, ec, ea, cfg, critic=False, actor=False)
+    ref, _ = O.mtsac_update(st, batch, ec, ea, cfg)
+    for a, b in zip(O.tree_leaves(ns.critic) + O.tree_leaves(ns.actor), O.tree_leaves(ref.critic) + O.tree_leaves(ref.actor)):
+        assert torch.allclose(a, b, rtol=1e-9, atol=1e-12)
+    assert torch.allclose(ns.log_alpha, ref.log_alpha)
+    g = torch.tensor([[1.0, 0.0], [-1.0, 1.0], [0.0, 2.0]], dtype=torch.float64)
+    avg, stats = TG.pcgrad(g)
+    # g0 vs g1 conflict (dot = -1): g0 -> g0 + 0.5 g1 = (0.5, 0.5); g1 -> g1 + g0 = (0, 1); g2 untouched
+    assert stats["n_grad_conflicts"] == 1.0
+    assert torch.allclose(avg, torch.tensor([0.5 / 3, 3.5 / 3], dtype=torch.float64), atol=1e-7)
