@@ -231,6 +231,15 @@ template <int WORLD>
 static __global__ void __launch_bounds__(512, 1) trunk_step_kernel(const TrunkStepArgs a) {
   __shared__ double red[32];
   __shared__ float s_scale;
+  // the ownership table is walked three times: keep it in shared memory (a dependent global load per entry costs more
+  // than the entry's work once the segments are small)
+  constexpr int kMaxSmemSegs = 128;
+  __shared__ Segment s_segs[kMaxSmemSegs];
+  const bool segs_in_smem = a.nsegs <= kMaxSmemSegs;
+  if (segs_in_smem)
+    for (int i = threadIdx.x; i < a.nsegs; i += blockDim.x) s_segs[i] = a.segs[i];
+  __syncthreads();
+  const Segment* segs = segs_in_smem ? s_segs : a.segs;
   Header* H = a.peer_hdr[a.rank];
   const unsigned epoch = *reinterpret_cast<volatile unsigned*>(&H->epoch);
   const unsigned long long grid_base = static_cast<unsigned long long>(epoch - 1) * 2ull * gridDim.x;
@@ -249,7 +258,7 @@ static __global__ void __launch_bounds__(512, 1) trunk_step_kernel(const TrunkSt
   {
     double s = 0.0;
     for (int si = 0; si < a.nsegs; ++si) {
-      const Segment sg = a.segs[si];
+      const Segment sg = segs[si];
       if (sg.owner != a.rank) continue;
       if (sg.pre_reduced) {
 #pragma unroll 4
@@ -296,7 +305,7 @@ static __global__ void __launch_bounds__(512, 1) trunk_step_kernel(const TrunkSt
   // ---- Adam on the owned segments; all-gather by storing the new parameters into every rank ----
   double p2_trunk = 0.0, p2_head = 0.0;
   for (int si = 0; si < a.nsegs; ++si) {
-    const Segment sg = a.segs[si];
+    const Segment sg = segs[si];
     if (sg.owner != a.rank) continue;
     for (long long i = sg.begin4 + tid; i < sg.end4; i += stride) {
       const float4 g4 = sg.pre_reduced ? ld_sys_f4(a.g + i * 4) : reinterpret_cast<const float4*>(a.g)[i];
@@ -332,7 +341,7 @@ static __global__ void __launch_bounds__(512, 1) trunk_step_kernel(const TrunkSt
 
   // ---- derived copies of the segments the peers own ----
   for (int si = 0; si < a.nsegs; ++si) {
-    const Segment sg = a.segs[si];
+    const Segment sg = segs[si];
     if (sg.owner == a.rank) continue;
     // two elements per pass: both parameter and both target loads are issued before the dependent stores
     long long i = sg.begin4 + tid;

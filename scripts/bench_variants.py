@@ -91,6 +91,7 @@ def task_grads(out):
              torch.rand(B, 1, generator=g, device="cuda") * 10)
     ms_g = timed(lambda: agent.per_task_gradients(batch), warmup=2, steps=5)
     ms_w = timed(lambda: agent.compute_weights(batch), warmup=1, steps=5)
+    matrix_gb = (agent._lay.critic.total + agent._lay.actor.total) * T * 4 / 1e9
     # the same update with PCGradConfig on both networks
     import dataclasses
 
@@ -107,7 +108,7 @@ def task_grads(out):
                 "updates_per_s": 1e3 / ms_pc, "n_grad_conflicts_critic": float(pagent.pcgrad_stats()["critic"]["n_grad_conflicts"])})
     out.append({"variant": "MT50/W2048 per-task gradient matrices (T x P) + Gram metrics (compute_weights, SURVEY 8f row 1)",
                 "rows": B, "ms_per_task_gradients": ms_g, "ms_compute_weights": ms_w,
-                "matrix_gb": (agent._lay.critic.total + agent._lay.actor.total) * T * 4 / 1e9})
+                "matrix_gb": matrix_gb})
 
 
 if __name__ == "__main__":
