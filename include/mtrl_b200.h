@@ -292,6 +292,11 @@ void mtrl_comm_destroy(mtrl_comm_t* c);
 int mtrl_sac_attach_comm(mtrl_sac_t* h, mtrl_comm_t* c, long long off_critic_grads, long long off_actor_grads,
                          long long off_critic_params, long long off_actor_params);
 
+/* Host-only: the ownership table the sharded exchange uses for one network layout (from mtrl_sac_query_layout) and
+ * `world` ranks, as rows {begin, end, owner rank, pre_reduced} in floats into the flat buffer.  The segments tile
+ * [0, trunk_total) exactly; pre_reduced rows are hidden-layer kernel row blocks whose gradient the dW GEMM epilogues
+ * reduce into the owner's buffer. */
+int mtrl_trunk_segments(const mtrl_net_layout_t* layout, int world, long long* out4, int max_segments, int* n_out);
 /* Checkpoint support for the sharded exchange: writes 1.0 / 0.0 over [0, trunk_total) of the actor (critic = 0) or
  * critic (critic = 1) layout -- 1.0 where THIS handle holds the live Adam moments (everything without an attached
  * arena).  sum over ranks of mask * moments is the full optimiser state of the reference's TrainState.  Synchronises. */

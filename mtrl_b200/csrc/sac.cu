@@ -1008,6 +1008,24 @@ extern "C" int mtrl_sac_act(mtrl_sac_t* h, const float* obs, int n, const float*
   return MTRL_OK;
 }
 
+// The ownership table of one network's trunk for `world` ranks (host only; no device, no handle): rows of
+// {begin, end, owner, pre_reduced} in floats.  Used by tests and by hosts that want to gather sharded optimiser state.
+extern "C" int mtrl_trunk_segments(const mtrl_net_layout_t* layout, int world, long long* out4, int max_segments, int* n_out) {
+  MTRL_REQUIRE(layout && out4 && n_out, "mtrl_trunk_segments: null argument");
+  MTRL_REQUIRE(world >= 1 && world <= MTRL_COMM_MAX_RANKS, "mtrl_trunk_segments: world %d outside [1, %d]", world, MTRL_COMM_MAX_RANKS);
+  const std::vector<comm::Segment> segs = trunk_segments(*layout, world);
+  MTRL_REQUIRE(static_cast<int>(segs.size()) <= max_segments, "mtrl_trunk_segments: %d segments, room for %d",
+               static_cast<int>(segs.size()), max_segments);
+  for (size_t i = 0; i < segs.size(); ++i) {
+    out4[4 * i + 0] = segs[i].begin4 * 4;
+    out4[4 * i + 1] = segs[i].end4 * 4;
+    out4[4 * i + 2] = segs[i].owner;
+    out4[4 * i + 3] = segs[i].pre_reduced;
+  }
+  *n_out = static_cast<int>(segs.size());
+  return MTRL_OK;
+}
+
 // 1.0 over the trunk elements whose Adam moments this handle holds live (all of them unless the sharded exchange is
 // attached, then the segments it owns), 0.0 elsewhere: lets the host assemble the full optimiser state from the ranks
 // (sum over ranks of mask * moments) for a checkpoint.  Synchronises.

@@ -80,3 +80,51 @@ def test_optimizer_configs_outside_the_path_fail_loudly():
     assert not OptimizerConfig().spawn().pcgrad
     with pytest.raises(NotImplementedError):
         DummyMultiTaskConfig().spawn()
+
+
+@pytest.mark.parametrize("T,W,depth,E", [(50, 2048, 3, 2), (10, 400, 3, 2), (10, 256, 2, 1), (7, 100, 4, 3), (50, 4096, 3, 2)])
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+def test_trunk_ownership_segments_tile_the_trunk(T, W, depth, E, world):
+    """csrc/sac.cu trunk_segments (host logic of the sharded exchange): every trunk element belongs to exactly one
+    segment and one owner; hidden-layer kernels are cut into contiguous row blocks (the dW problems' outputs)."""
+    import ctypes as C
+
+    from mtrl_b200 import _lib as L
+    from mtrl_b200.rl.algorithms.mtsac import SacConfigC, SacLayoutC
+
+    t_local = -(-T // world)
+    cfg = SacConfigC(num_tasks=T, task_begin=0, num_local_tasks=t_local, obs_dim=39 + T, action_dim=4, width=W, depth=depth,
+                     num_critics=E, max_rows=128 * t_local, max_batch=128 * t_local, gamma=0.99, tau=0.005, actor_lr=3e-4,
+                     critic_lr=3e-4, alpha_lr=3e-4, adam_b1=0.9, adam_b2=0.999, adam_eps=1e-5, actor_max_grad_norm=1.0,
+                     critic_max_grad_norm=1.0, alpha_max_grad_norm=-1.0, log_std_min=-20.0, log_std_max=2.0,
+                     target_entropy=-4.0, clip_q=0, use_task_weights=0, noise_seed=1, variant=0)
+    lay = SacLayoutC()
+    L.check(L.lib().mtrl_sac_query_layout(C.byref(cfg), C.byref(lay)))
+    fn = L.lib().mtrl_trunk_segments
+    fn.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_longlong), C.c_int, C.POINTER(C.c_int)]
+    for net in (lay.critic, lay.actor):
+        out = (C.c_longlong * (4 * 512))()
+        n = C.c_int()
+        L.check(fn(C.byref(net), world, out, 512, C.byref(n)))
+        segs = sorted((out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]) for i in range(n.value))
+        pos = 0
+        for b, e, owner, pre in segs:
+            assert b == pos and e > b and b % 4 == 0 and e % 4 == 0, (b, e, pos)
+            assert 0 <= owner < world
+            pos = e
+        assert pos == net.trunk_total
+        pre_floats = sum(e - b for b, e, _, pre in segs if pre)
+        hidden = net.members * (depth - 1) * W * W
+        assert hidden <= pre_floats <= hidden + net.members * (depth - 1) * 32   # + alignment padding of the last block
+        owned = [sum(e - b for b, e, o, _ in segs if o == r) for r in range(world)]
+        if depth > 1 and W >= 32 * world:
+            assert max(owned) <= 1.6 * (net.trunk_total / world) + 64 * W, owned   # balanced up to the small pieces
+
+
+def test_arena_plan_offsets():
+    from mtrl_b200.rl.algorithms.mtsac import COMM_HEADER_BYTES, arena_plan
+
+    plan, size = arena_plan(1000, 333)
+    offs = [plan[k] for k in ("critic_grads", "actor_grads", "critic_params", "actor_params")]
+    assert offs[0] == COMM_HEADER_BYTES and all(o % 4096 == 0 for o in offs) and offs == sorted(offs)
+    assert offs[1] - offs[0] >= 4000 and offs[2] - offs[1] >= 1332 and size - offs[3] >= 1332 and size % 4096 == 0
