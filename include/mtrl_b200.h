@@ -248,6 +248,12 @@ int mtrl_sac_task_grads(mtrl_sac_t* h, const float* obs, const float* actions, c
  * NULL for the identity.  T <= 64, every task on this handle, equally many rows per task. */
 int mtrl_sac_enable_pcgrad(mtrl_sac_t* h, int critic, int actor, float* critic_tg, float* actor_tg, float* scratch,
                            const int* perm_critic, const int* perm_actor);
+/* CAGradConfig (mtrl/config/optim.py:104-124): optax.chain(cagrad(num_tasks), clip_by_global_norm, adam), same wiring
+ * as mtrl_sac_enable_pcgrad with cagrad's defaults (mtrl/optim/cagrad.py:20-41: c = 0.5, 21 SGD iterations on the task
+ * weights, lr 25 / 50, momentum 0.5).  scratch: 2 T^2 + 4 T + 8 floats = the pcgrad layout (stats = norm of the
+ * combined gradient, mean clipped per-task norm, best objective) followed by the critic's and the actor's softmax task
+ * weights (CAGradState.task_weights). */
+int mtrl_sac_enable_cagrad(mtrl_sac_t* h, int critic, int actor, float* critic_tg, float* actor_tg, float* scratch);
 /* Number of kernels one mtrl_sac_update launches (for bench.py's gpu_launches). */
 int mtrl_sac_launches_per_update(const mtrl_sac_t* h);
 /* Bracket every GEMM launch of the following updates with CUDA events on the launch stream

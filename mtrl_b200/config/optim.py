@@ -1,7 +1,7 @@
 """Mirror of mtrl/config/optim.py:14-43.  `spawn()` returns the description of
 optax.chain(clip_by_global_norm(max_grad_norm), adam(lr, eps)) that the fused CUDA optimiser
 (csrc/sac_kernels.cuh adam_kernel) executes; the gradient-surgery configs (optim.py:46-118) keep
-their names; PCGradConfig is implemented (per-task gradients + pcgrad in front of the same chain), the others raise."""
+their names; PCGradConfig and CAGradConfig are implemented (per-task gradients + the surgery in front of the same chain), the others raise."""
 from dataclasses import dataclass
 
 from .utils import Optimizer
@@ -17,6 +17,7 @@ class AdamChainSpec:
     b2: float = 0.999
     max_grad_norm: float | None = None
     pcgrad: bool = False   # optax.chain(pcgrad(num_tasks), clip, adam): mtrl/config/optim.py:62-76
+    cagrad: bool = False   # optax.chain(cagrad(num_tasks), clip, adam): mtrl/config/optim.py:104-124
 
 
 @dataclass(frozen=True, kw_only=True)
@@ -70,3 +71,22 @@ class PCGradConfig(OptimizerConfig):
         import dataclasses
 
         return dataclasses.replace(OptimizerConfig.spawn(self), pcgrad=True)
+
+
+@dataclass(frozen=True, kw_only=True)
+class CAGradConfig(OptimizerConfig):   # optim.py:104-124
+    num_tasks: int
+    cagrad_optimizer: OptimizerConfig | None = None   # carried but unused by the reference's spawn() (:117-123)
+    initial_weights: object | None = None
+    max_grad_norm: float | None = None
+
+    @property
+    def requires_split_task_losses(self) -> bool:
+        return True
+
+    def spawn(self) -> AdamChainSpec:
+        """optax.chain(cagrad(num_tasks), OptimizerConfig.spawn()) as data; cagrad runs with its defaults (c = 0.5,
+        21 iterations, lr 25 / 50, momentum 0.5: mtrl/optim/cagrad.py:20-41) on the per-task Gram matrix."""
+        import dataclasses
+
+        return dataclasses.replace(OptimizerConfig.spawn(self), cagrad=True)

@@ -153,6 +153,7 @@ struct mtrl_sac {
   } tgc;
   // PCGrad (mtrl_sac_enable_pcgrad): which optimiser chains start with pcgrad, scratch and the row permutations
   bool pcgrad_critic = false, pcgrad_actor = false;
+  int surgery_mode = 0;   // 0: pcgrad, 1: cagrad
   float* pcgrad_scratch = nullptr;
   const int *pcgrad_perm_critic = nullptr, *pcgrad_perm_actor = nullptr;
   TaskGradCache* tg_active = nullptr;   // set while mtrl_sac_task_grads runs: the backward also fills the (T, P) rows
@@ -1102,12 +1103,24 @@ int pcgrad_combine(mtrl_sac* h, bool critic, cudaStream_t st) {
   float* stats = h->pcgrad_scratch + 2 * T * T + 2 * T + (critic ? 0 : 4);
   MTRL_CUDA_CHECK(cudaMemsetAsync(gram, 0, static_cast<size_t>(T) * T * sizeof(float), st));
   gram_kernel<<<h->sms * 2, 256, 0, st>>>(tg, L.total, T, L.total, gram, T);
-  pcgrad_coeff_kernel<<<1, 64, 2 * T * T * sizeof(float), st>>>(gram, T, T, static_cast<float>(T) * static_cast<float>(T),
-                                                                critic ? h->pcgrad_perm_critic : h->pcgrad_perm_actor, wts, stats);
+  const float gscale = static_cast<float>(T) * static_cast<float>(T);
+  if (h->surgery_mode == 1) {
+    // cagrad(num_tasks) defaults (cagrad.py:20-41): c = 0.5, 21 iterations, lr 25 (< 50 tasks) or 50, momentum 0.5;
+    // the softmax task weights go where the other network's Gram matrix is not (scratch tail)
+    float* tw = h->pcgrad_scratch + 2 * T * T + 2 * T + 8 + (critic ? 0 : T);
+    cagrad_coeff_kernel<<<1, 32, (static_cast<size_t>(T) * T + 7 * T) * sizeof(double), st>>>(gram, T, T, gscale, 0.5f, 21,
+                                                                                          T < 50 ? 25.f : 50.f, 0.5f, wts, stats, tw);
+  } else {
+    pcgrad_coeff_kernel<<<1, 64, 2 * T * T * sizeof(float), st>>>(gram, T, T, gscale,
+                                                                  critic ? h->pcgrad_perm_critic : h->pcgrad_perm_actor, wts, stats);
+  }
   weighted_rows_kernel<<<h->sms * 4, 256, 0, st>>>(tg, L.total, T, wts, grads, L.total);
   MTRL_CUDA_CHECK(cudaGetLastError());
   h->launches += 4;
-  return head_sumsq_to_slot(h, grads, L, critic ? ACC_CRITIC_HEAD_G2 : ACC_ACTOR_HEAD_G2, st);
+  // the head-gradient norm that rides in the slot was accumulated from the pre-surgery gradients: start it over
+  const int acc_idx = critic ? ACC_CRITIC_HEAD_G2 : ACC_ACTOR_HEAD_G2;
+  MTRL_CUDA_CHECK(cudaMemsetAsync(h->ws.acc + acc_idx, 0, sizeof(double), st));
+  return head_sumsq_to_slot(h, grads, L, acc_idx, st);
 }
 
 // MTSAC.update when an optimiser chain starts with pcgrad (PCGradConfig, mtrl/config/optim.py:62-76): the losses are
@@ -1174,6 +1187,16 @@ extern "C" int mtrl_sac_enable_pcgrad(mtrl_sac_t* h, int critic, int actor, floa
   h->pcgrad_scratch = scratch;
   h->pcgrad_perm_critic = perm_critic;
   h->pcgrad_perm_actor = perm_actor;
+  h->surgery_mode = 0;
+  return MTRL_OK;
+}
+
+// Same wiring with cagrad (mtrl/optim/cagrad.py, CAGradConfig mtrl/config/optim.py:104-124) in front of the chain.
+// scratch needs 2 T^2 + 4 T + 8 floats: the pcgrad layout followed by the two networks' softmax task weights.
+extern "C" int mtrl_sac_enable_cagrad(mtrl_sac_t* h, int critic, int actor, float* critic_tg, float* actor_tg, float* scratch) {
+  MTRL_PROPAGATE(mtrl_sac_enable_pcgrad(h, critic, actor, critic_tg, actor_tg, scratch, nullptr, nullptr));
+  h->surgery_mode = 1;
+  cudaFuncSetAttribute(cagrad_coeff_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   return MTRL_OK;
 }
 

@@ -972,6 +972,108 @@ static __global__ void pcgrad_coeff_kernel(const float* __restrict__ gram, int l
   }
 }
 
+// CAGrad (mtrl/optim/cagrad.py:20-237), also a function of the Gram matrix only: per-task clipping to unit norm
+// (:181-187) scales rows, the 21-step momentum SGD on the T task weights (:56-123) works on GG = G / scale^2, and the
+// result (:125-163) is a weighted sum of the clipped rows.  One thread, double precision (T <= 64: ~1e5 flops).
+//   w_out : weights on the UNSCALED rows;  stats: [0] |g| of the result, [1] mean clipped-row norm, [2] best objective,
+//   [3] unused;  tw_out (T): the softmax task weights (CAGradState.task_weights)
+static __global__ void cagrad_coeff_kernel(const float* __restrict__ gram, int ldg, int T, float gscale, float c, int iterations,
+                                           float lr, float momentum, float* __restrict__ w_out, float* __restrict__ stats,
+                                           float* __restrict__ tw_out) {
+  extern __shared__ float pcg_sm[];
+  double* GG = reinterpret_cast<double*>(pcg_sm);          // [T][T]
+  double* clipc = GG + T * T;                                // [T]
+  double* Gg = clipc + T;                                    // [T]
+  double* w = Gg + T;
+  double* vel = w + T;
+  double* wbest = vel + T;
+  double* ww = wbest + T;
+  double* d = ww + T;
+  if (threadIdx.x != 0) return;
+  // clipped, normalised Gram
+  for (int i = 0; i < T; ++i) {
+    const double n = sqrt(fmax(static_cast<double>(gram[i * ldg + i]) * gscale, 0.0));
+    clipc[i] = fmin(1.0, 1.0 / (n + 1e-8));
+  }
+  double scale = 0.0, before = 0.0;
+  for (int i = 0; i < T; ++i) {
+    for (int j = 0; j < T; ++j) GG[i * T + j] = static_cast<double>(gram[i * ldg + j]) * gscale * clipc[i] * clipc[j];
+    scale += sqrt(GG[i * T + i] + 1e-4);
+    before += sqrt(fmax(GG[i * T + i], 0.0));
+  }
+  scale /= T;
+  double gg = 0.0;
+  for (int i = 0; i < T; ++i) {
+    double r = 0.0;
+    for (int j = 0; j < T; ++j) {
+      GG[i * T + j] /= scale * scale;
+      r += GG[i * T + j];
+    }
+    Gg[i] = r / T;
+    gg += Gg[i];
+  }
+  gg /= T;
+  const double cn = sqrt(gg + 1e-4) * c;
+  auto objective = [&](const double* wv, bool want_grad, double* grad) {
+    double s = 1e-8;
+    for (int i = 0; i < T; ++i) s += wv[i];
+    double t1 = 0.0;
+    for (int i = 0; i < T; ++i) { ww[i] = wv[i] / s; t1 += ww[i] * Gg[i]; }
+    double q = 0.0;
+    for (int i = 0; i < T; ++i) {
+      double r = 0.0;
+      for (int j = 0; j < T; ++j) r += GG[i * T + j] * ww[j];
+      d[i] = r;
+      q += ww[i] * r;
+    }
+    const double root = sqrt(q + 1e-4);
+    if (want_grad) {
+      double dot = 0.0;
+      for (int i = 0; i < T; ++i) { d[i] = Gg[i] + cn * d[i] / root; dot += d[i] * ww[i]; }
+      for (int j = 0; j < T; ++j) grad[j] = (d[j] - dot) / s;
+    }
+    return t1 + cn * root;
+  };
+  for (int i = 0; i < T; ++i) { w[i] = 0.0; vel[i] = 0.0; wbest[i] = 0.0; }
+  double obj_best = INFINITY;
+  double* grad = d;   // objective() leaves the gradient in d
+  for (int it = 0; it < iterations - 1; ++it) {
+    const double o = objective(w, true, grad);
+    if (o < obj_best) { obj_best = o; for (int i = 0; i < T; ++i) wbest[i] = w[i]; }
+    for (int i = 0; i < T; ++i) { vel[i] = momentum * vel[i] + grad[i]; w[i] -= lr * vel[i]; }
+  }
+  {
+    const double o = objective(w, false, nullptr);
+    if (o < obj_best) { obj_best = o; for (int i = 0; i < T; ++i) wbest[i] = w[i]; }
+  }
+  // softmax(w_best) and the combination weights (:139-161)
+  double mx = -INFINITY, den = 0.0;
+  for (int i = 0; i < T; ++i) mx = fmax(mx, wbest[i]);
+  for (int i = 0; i < T; ++i) { w[i] = exp(wbest[i] - mx); den += w[i]; }
+  double q = 0.0;
+  for (int i = 0; i < T; ++i) w[i] /= den;
+  for (int i = 0; i < T; ++i) {
+    double r = 0.0;
+    for (int j = 0; j < T; ++j) r += GG[i * T + j] * w[j];
+    q += w[i] * r;
+  }
+  const double lmbda = cn / (sqrt(q + 1e-4) + 1e-4);
+  for (int i = 0; i < T; ++i) {
+    const double comb = (1.0 / T + w[i] * lmbda) / (1.0 + static_cast<double>(c) * c);
+    // reference-scale clipped row = clip_i * sqrt(gscale) * unscaled row
+    vel[i] = comb * clipc[i] * sqrt(static_cast<double>(gscale));
+    w_out[i] = static_cast<float>(vel[i]);
+    tw_out[i] = static_cast<float>(w[i]);
+  }
+  double n2 = 0.0;
+  for (int i = 0; i < T; ++i)
+    for (int j = 0; j < T; ++j) n2 += vel[i] * vel[j] * static_cast<double>(gram[i * ldg + j]);
+  stats[0] = static_cast<float>(sqrt(fmax(n2, 0.0)));
+  stats[1] = static_cast<float>(before / T);
+  stats[2] = static_cast<float>(obj_best);
+  stats[3] = 0.f;
+}
+
 // out[p] = sum_k w[k] * rows[k][p]   (HBM-bound: reads the (T, P) matrix once)
 static __global__ void weighted_rows_kernel(const float* __restrict__ rows, long long ld, int T, const float* __restrict__ w,
                                             float* __restrict__ out, long long P) {

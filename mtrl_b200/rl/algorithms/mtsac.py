@@ -92,6 +92,7 @@ L._EXTRA_DECLS.update({
     "mtrl_sac_act": ([_vp, _vp, _i, _vp, _i, _vp, _vp],),
     "mtrl_sac_task_grads": ([_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp],),
     "mtrl_sac_enable_pcgrad": ([_vp, _i, _i, _vp, _vp, _vp, _vp, _vp],),
+    "mtrl_sac_enable_cagrad": ([_vp, _i, _i, _vp, _vp, _vp],),
     "mtrl_sac_trunk_owner_mask": ([_vp, _i, _vp],),
     "mtrl_sac_profile_gemms": ([_vp, _i],),
     "mtrl_sac_profile_read": ([_vp, C.POINTER(C.c_double), C.POINTER(_i)],),
@@ -317,7 +318,11 @@ class MTSAC:
         la.fill_(math.log(config.initial_temperature))
 
         self._create_handle()
-        self._pcgrad = (bool(c_opt.pcgrad), bool(a_opt.pcgrad))
+        self._pcgrad = (bool(c_opt.pcgrad or c_opt.cagrad), bool(a_opt.pcgrad or a_opt.cagrad))   # (critic, actor) use surgery
+        kinds = {k for o in (c_opt, a_opt) for k in ("pcgrad", "cagrad") if getattr(o, k)}
+        if len(kinds) > 1:
+            raise NotImplementedError("one gradient-surgery optimiser per agent (PCGradConfig or CAGradConfig)")
+        self._surgery = next(iter(kinds), None)
         if any(self._pcgrad):
             if world_size != 1:
                 raise NotImplementedError("PCGradConfig needs every task on one device (split losses)")
@@ -337,9 +342,13 @@ class MTSAC:
     def _enable_pcgrad(self, seed: int) -> None:
         T = self.num_tasks
         tg = self._task_matrices()
-        self._pc_scratch = torch.zeros(2 * T * T + 2 * T + 8, dtype=torch.float32, device=self.device)
+        self._pc_scratch = torch.zeros(2 * T * T + 4 * T + 8, dtype=torch.float32, device=self.device)
         self._pc_perm = torch.arange(T, dtype=torch.int32, device=self.device).repeat(2, 1).contiguous()
         self._pc_gen = torch.Generator().manual_seed(int(seed) + 7919)
+        if self._surgery == "cagrad":
+            L.check(L.lib().mtrl_sac_enable_cagrad(self._h, int(self._pcgrad[0]), int(self._pcgrad[1]), _vp(tg["critic"].data_ptr()),
+                                                   _vp(tg["actor"].data_ptr()), _vp(self._pc_scratch.data_ptr())))
+            return
         L.check(L.lib().mtrl_sac_enable_pcgrad(self._h, int(self._pcgrad[0]), int(self._pcgrad[1]), _vp(tg["critic"].data_ptr()),
                                                _vp(tg["actor"].data_ptr()), _vp(self._pc_scratch.data_ptr()),
                                                _vp(self._pc_perm[0].data_ptr()), _vp(self._pc_perm[1].data_ptr())))
@@ -349,6 +358,10 @@ class MTSAC:
         plain mean gradient."""
         T, s = self.num_tasks, self._pc_scratch
         base = 2 * T * T + 2 * T
+        if self._surgery == "cagrad":   # CAGradState (cagrad.py:13-18, 195-203)
+            names = ("avg_grad_magnitude", "avg_grad_magnitude_before_surgery", "cagrad_objective")
+            return {net: dict(zip(names, s[base + 4 * i: base + 4 * i + 3]), task_weights=s[base + 8 + T * i: base + 8 + T * (i + 1)])
+                    for i, net in enumerate(("critic", "actor")) if self._pcgrad[i]}
         names = ("n_grad_conflicts", "avg_grad_magnitude", "avg_grad_magnitude_before_surgery", "mean_grad_norm")
         return {net: dict(zip(names, s[base + 4 * i: base + 4 * i + 4])) for i, net in enumerate(("critic", "actor")) if self._pcgrad[i]}
 
@@ -489,7 +502,7 @@ class MTSAC:
         assert data[0].shape[1] == self._cfg.obs_dim and tuple(data[1].shape) == (B, self._cfg.action_dim)
         if graph is None:
             graph = _GRAPH_DEFAULT
-        if any(getattr(self, "_pcgrad", (False, False))):
+        if any(getattr(self, "_pcgrad", (False, False))) and self._surgery == "pcgrad":
             # the row permutation pcgrad draws every step (pcgrad.py:79; jax key there, a seeded host generator here),
             # one per network, or the caller's `pcgrad_perm = (critic_perm, actor_perm)`
             T = self.num_tasks

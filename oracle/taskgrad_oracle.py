@@ -119,6 +119,51 @@ def pcgrad(flat: torch.Tensor, perm: torch.Tensor | None = None):
     return final.mean(dim=0), stats
 
 
+def cagrad(flat: torch.Tensor, c: float = 0.5, num_iterations: int = 21, learning_rate: float | None = None,
+           momentum: float = 0.5):
+    """mtrl/optim/cagrad.py:165-203 with its defaults (:20-41): per-task clipping to unit norm (:181-187), 21 momentum-SGD
+    steps on the task weights starting from zero with the gradient of the objective by autodiff (:56-123), softmax,
+    combination (:125-163).  Returns (combined_grad, stats)."""
+    T = flat.shape[0]
+    lr = learning_rate if learning_rate is not None else (25.0 if T < 50 else 50.0)
+    g = flat * torch.clamp(1.0 / (flat.norm(dim=1, keepdim=True) + 1e-8), max=1.0)          # :181-187
+
+    def normalised():
+        GG = g @ g.T
+        scale = torch.sqrt(torch.diag(GG) + 1e-4).mean()
+        GG = GG / scale ** 2
+        Gg = GG.mean(dim=1, keepdim=True)
+        return GG, Gg, torch.sqrt(Gg.mean() + 1e-4) * c
+
+    GG, Gg, cn = normalised()
+
+    def objective(w):
+        ww = w / (w.sum() + 1e-8)
+        return (ww.T @ Gg + cn * torch.sqrt(ww.T @ GG @ ww + 1e-4)).squeeze()
+
+    w = torch.zeros(T, 1, dtype=flat.dtype)
+    vel = torch.zeros_like(w)
+    w_best, obj_best = w.clone(), torch.tensor(float("inf"), dtype=flat.dtype)
+    for _ in range(num_iterations - 1):
+        wv = w.clone().requires_grad_(True)
+        o = objective(wv)
+        o.backward()
+        if o < obj_best:
+            w_best, obj_best = w.clone(), o.detach()
+        vel = momentum * vel + wv.grad
+        w = w - lr * vel
+    o = objective(w)
+    if o < obj_best:
+        w_best, obj_best = w.clone(), o
+    tw = torch.softmax(w_best.squeeze(), dim=0)
+    gw_norm = torch.sqrt(tw.reshape(1, -1) @ GG @ tw.reshape(-1, 1) + 1e-4)
+    lmbda = cn / (gw_norm + 1e-4)
+    comb = 1.0 / T + tw * lmbda.squeeze()
+    out = (comb.reshape(-1, 1) * g).sum(dim=0) / (1 + c ** 2)
+    return out, {"task_weights": tw, "avg_grad_magnitude": out.norm(), "avg_grad_magnitude_before_surgery": g.norm(dim=1).mean(),
+                 "cagrad_objective": obj_best}
+
+
 def _unflatten(flat: torch.Tensor, like) -> dict:
     leaves, off = [], 0
     for x in O.tree_leaves(like):
@@ -129,9 +174,10 @@ def _unflatten(flat: torch.Tensor, like) -> dict:
 
 
 def mtsac_update_pcgrad(state: O.OracleState, batch, eps_c, eps_a, cfg: O.OracleConfig, perm_c=None, perm_a=None,
-                        critic: bool = True, actor: bool = True):
+                        critic: bool = True, actor: bool = True, surgery: str = "pcgrad"):
     """MTSAC.update (mtsac.py:1173-1251) with split losses and optax.chain(pcgrad, clip_by_global_norm, adam) on the
-    chosen networks; the other network keeps the plain chain.  Returns (new_state, stats)."""
+    chosen networks (surgery="cagrad": cagrad instead, CAGradConfig optim.py:104-124); the other network keeps the plain
+    chain.  Returns (new_state, stats)."""
     obs = batch[0]
     T = cfg.num_tasks
     opt = dict(state.opt)
@@ -139,19 +185,21 @@ def mtsac_update_pcgrad(state: O.OracleState, batch, eps_c, eps_a, cfg: O.Oracle
     stats = {}
     ctg = critic_task_grads(state.critic, batch, target, cfg)
     if critic:
-        flat, stats["critic"] = pcgrad(flatten(ctg), perm_c)
+        flat, stats["critic"] = pcgrad(flatten(ctg), perm_c) if surgery == "pcgrad" else cagrad(flatten(ctg))
         cgrads = _unflatten(flat, state.critic)
     else:
         cgrads = O.tree_map(lambda *xs: sum(xs) / len(xs), *ctg)
+    stats.setdefault("critic", {})["grad_tree"] = cgrads
     new_critic, opt["critic"] = O.adam_step(state.critic, cgrads, opt["critic"], cfg.lr, cfg.adam_eps, cfg.b1, cfg.b2,
                                             cfg.max_grad_norm)
     new_target = O.tree_map(lambda n, t: cfg.tau * n + (1 - cfg.tau) * t, new_critic, state.critic_target)
     atg, logp = actor_task_grads(state.actor, new_critic, batch, alpha_vals, eps_a, cfg)
     if actor:
-        flat, stats["actor"] = pcgrad(flatten(atg), perm_a)
+        flat, stats["actor"] = pcgrad(flatten(atg), perm_a) if surgery == "pcgrad" else cagrad(flatten(atg))
         agrads = _unflatten(flat, state.actor)
     else:
         agrads = O.tree_map(lambda *xs: sum(xs) / len(xs), *atg)
+    stats.setdefault("actor", {})["grad_tree"] = agrads
     new_actor, opt["actor"] = O.adam_step(state.actor, agrads, opt["actor"], cfg.lr, cfg.adam_eps, cfg.b1, cfg.b2,
                                           cfg.max_grad_norm)
     la = state.log_alpha.detach().clone().requires_grad_(True)

@@ -105,9 +105,58 @@ def test_pcgrad_update_matches_oracle(cuda):
         for k in ("avg_grad_magnitude", "avg_grad_magnitude_before_surgery"):
             assert abs(float(got[net][k]) - float(stats[net][k])) <= 1e-2 * float(stats[net][k]), (net, k)
     # the Adam step (new - old) of the trunk kernels, the part pcgrad changes
+    # the combined gradient the surgery hands to clip + adam, leaf by leaf
+    for name, ens, tree in (("critic", True, agent.critic.grads), ("actor", False, agent.actor.grads)):
+        for leaf, e in SU.compare_trees(stats[name]["grad_tree"], tree, ens).items():
+            assert e <= 1e-2, (name, leaf, e)
     for name, old_t, new_t, tree, ens in (("critic", st64.critic, new.critic, agent.critic.params, True),
                                           ("actor", st64.actor, new.actor, agent.actor.params, False)):
         for leaf, e in SU.compare_deltas(old_t, new_t, tree, ens).items():
             if leaf.startswith("layer_") and leaf.endswith("kernel"):
                 assert e <= 3e-2, (name, leaf, e)
     assert SU.rel(agent.alpha.params["params"]["log_alpha"], new.log_alpha) <= 1e-3
+
+
+def test_cagrad_update_matches_oracle(cuda):
+    """CAGradConfig on both networks (mtrl/config/optim.py:104-124): per-task clip, weight SGD and combination of
+    cagrad.py computed from the Gram matrix on the GPU vs the literal restatement on autograd per-task gradients."""
+    from mtrl_b200.config.networks import ContinuousActionPolicyConfig, QValueFunctionConfig
+    from mtrl_b200.config.nn import MultiHeadConfig
+    from mtrl_b200.config.optim import CAGradConfig, OptimizerConfig
+    from mtrl_b200.rl.algorithms import MTSAC, MTSACConfig
+
+    T, W, per_task = 6, 128, 32
+    cfg = O.OracleConfig(num_tasks=T, obs_dim=39 + T, action_dim=4, width=W)
+    st = O.init_state(cfg, seed=6, dtype=torch.float32)
+    for net, scale in ((st.actor, 100.0), (st.critic, 30.0), (st.critic_target, 30.0)):
+        for k in ("kernel", "bias"):
+            net["heads"][k] = net["heads"][k] * scale
+    opt = CAGradConfig(lr=cfg.lr, max_grad_norm=cfg.max_grad_norm, eps=cfg.adam_eps, num_tasks=T)
+    netc = MultiHeadConfig(width=W, depth=cfg.depth, num_tasks=T, optimizer=opt)
+    mc = MTSACConfig(num_tasks=T, gamma=cfg.gamma, actor_config=ContinuousActionPolicyConfig(network_config=netc),
+                     critic_config=QValueFunctionConfig(network_config=netc),
+                     temperature_optimizer_config=OptimizerConfig(lr=cfg.alpha_lr, max_grad_norm=None, eps=cfg.adam_eps))
+    agent = MTSAC.initialize(mc, SU.EnvSpec(cfg.obs_dim, 4), seed=6, max_batch=per_task * T)
+    SU.load_oracle_state(agent, st)
+    batch, ec, ea = O.synthetic_batch(cfg, per_task, seed=78, dtype=torch.float32)
+    task = batch[0][:, -T:].argmax(1)
+    rew = batch[4] * torch.where(task % 2 == 0, 1.0, -1.0).reshape(-1, 1)
+    batch = (batch[0], batch[1], batch[2], batch[3], rew)
+    tcfg = dataclasses.replace(cfg, matmul_operands="tf32")
+    st64 = st.to(torch.float64)
+    new, stats = TG.mtsac_update_pcgrad(st64, tuple(b.double() for b in batch), ec.double(), ea.double(), tcfg, surgery="cagrad")
+    agent.update(tuple(b.cuda() for b in batch), eps_c=ec.cuda(), eps_a=ea.cuda(), check=True)
+    got = agent.pcgrad_stats()
+    for net in ("critic", "actor"):
+        assert (got[net]["task_weights"].double().cpu() - stats[net]["task_weights"]).abs().max() <= 1e-3, net
+        for k in ("avg_grad_magnitude", "avg_grad_magnitude_before_surgery", "cagrad_objective"):
+            assert abs(float(got[net][k]) - float(stats[net][k])) <= 1e-2 * abs(float(stats[net][k])) + 1e-6, (net, k)
+    # the combined gradient the surgery hands to clip + adam, leaf by leaf
+    for name, ens, tree in (("critic", True, agent.critic.grads), ("actor", False, agent.actor.grads)):
+        for leaf, e in SU.compare_trees(stats[name]["grad_tree"], tree, ens).items():
+            assert e <= 1e-2, (name, leaf, e)
+    for name, old_t, new_t, tree, ens in (("critic", st64.critic, new.critic, agent.critic.params, True),
+                                          ("actor", st64.actor, new.actor, agent.actor.params, False)):
+        for leaf, e in SU.compare_deltas(old_t, new_t, tree, ens).items():
+            if leaf.startswith("layer_") and leaf.endswith("kernel"):
+                assert e <= 3e-2, (name, leaf, e)
