@@ -254,6 +254,13 @@ int mtrl_sac_enable_pcgrad(mtrl_sac_t* h, int critic, int actor, float* critic_t
  * combined gradient, mean clipped per-task norm, best objective) followed by the critic's and the actor's softmax task
  * weights (CAGradState.task_weights). */
 int mtrl_sac_enable_cagrad(mtrl_sac_t* h, int critic, int actor, float* critic_tg, float* actor_tg, float* scratch);
+/* GradNormConfig (mtrl/config/optim.py:79-102): optax.chain(gradnorm(...), clip_by_global_norm, adam).  The reference's
+ * gradnorm loss is independent of the task weights (mtrl/optim/gradnorm.py:134-142), so the weights never move from 1
+ * and the transformation returns the SUM of the per-task gradients, each clipped to unit norm first when
+ * clip_per_task (its max_grad_norm) is set (:40-57, 106-107, 155-157).  scratch as for pcgrad; stats = norm of the sum,
+ * mean per-task norm after clipping. */
+int mtrl_sac_enable_gradnorm(mtrl_sac_t* h, int critic, int actor, int clip_per_task, float* critic_tg, float* actor_tg,
+                             float* scratch);
 /* Number of kernels one mtrl_sac_update launches (for bench.py's gpu_launches). */
 int mtrl_sac_launches_per_update(const mtrl_sac_t* h);
 /* Bracket every GEMM launch of the following updates with CUDA events on the launch stream

@@ -1,7 +1,7 @@
 """Mirror of mtrl/config/optim.py:14-43.  `spawn()` returns the description of
 optax.chain(clip_by_global_norm(max_grad_norm), adam(lr, eps)) that the fused CUDA optimiser
 (csrc/sac_kernels.cuh adam_kernel) executes; the gradient-surgery configs (optim.py:46-118) keep
-their names; PCGradConfig and CAGradConfig are implemented (per-task gradients + the surgery in front of the same chain), the others raise."""
+their names; PCGradConfig, CAGradConfig and GradNormConfig are implemented (per-task gradients + the surgery in front of the same chain), the others raise."""
 from dataclasses import dataclass
 
 from .utils import Optimizer
@@ -18,6 +18,8 @@ class AdamChainSpec:
     max_grad_norm: float | None = None
     pcgrad: bool = False   # optax.chain(pcgrad(num_tasks), clip, adam): mtrl/config/optim.py:62-76
     cagrad: bool = False   # optax.chain(cagrad(num_tasks), clip, adam): mtrl/config/optim.py:104-124
+    gradnorm: bool = False           # optax.chain(gradnorm(...), clip, adam): mtrl/config/optim.py:79-102
+    gradnorm_clip_per_task: bool = False
 
 
 @dataclass(frozen=True, kw_only=True)
@@ -90,3 +92,26 @@ class CAGradConfig(OptimizerConfig):   # optim.py:104-124
         import dataclasses
 
         return dataclasses.replace(OptimizerConfig.spawn(self), cagrad=True)
+
+
+@dataclass(frozen=True, kw_only=True)
+class GradNormConfig(OptimizerConfig):   # optim.py:79-102
+    num_tasks: int
+    gradnorm_optimizer: OptimizerConfig | None = None
+    initial_weights: object | None = None
+    asymmetry: float = 0.12
+    max_grad_norm: float | None = None
+
+    @property
+    def requires_split_task_losses(self) -> bool:
+        return True
+
+    def spawn(self) -> AdamChainSpec:
+        """optax.chain(gradnorm(optim, num_tasks, asymmetry, initial_weights, max_grad_norm), OptimizerConfig.spawn())
+        as data.  As written in the reference the task weights receive a zero gradient (gradnorm.py:134-142), stay at
+        their normalised initial value, and the transformation is the weighted SUM of the per-task gradients."""
+        import dataclasses
+
+        if self.initial_weights is not None:
+            raise NotImplementedError("GradNormConfig.initial_weights other than ones")
+        return dataclasses.replace(OptimizerConfig.spawn(self), gradnorm=True, gradnorm_clip_per_task=bool(self.max_grad_norm))

@@ -153,7 +153,7 @@ struct mtrl_sac {
   } tgc;
   // PCGrad (mtrl_sac_enable_pcgrad): which optimiser chains start with pcgrad, scratch and the row permutations
   bool pcgrad_critic = false, pcgrad_actor = false;
-  int surgery_mode = 0;   // 0: pcgrad, 1: cagrad
+  int surgery_mode = 0;   // 0: pcgrad, 1: cagrad, 2: gradnorm (3: gradnorm with per-task clipping)
   float* pcgrad_scratch = nullptr;
   const int *pcgrad_perm_critic = nullptr, *pcgrad_perm_actor = nullptr;
   TaskGradCache* tg_active = nullptr;   // set while mtrl_sac_task_grads runs: the backward also fills the (T, P) rows
@@ -1110,6 +1110,8 @@ int pcgrad_combine(mtrl_sac* h, bool critic, cudaStream_t st) {
     float* tw = h->pcgrad_scratch + 2 * T * T + 2 * T + 8 + (critic ? 0 : T);
     cagrad_coeff_kernel<<<1, 32, (static_cast<size_t>(T) * T + 7 * T) * sizeof(double), st>>>(gram, T, T, gscale, 0.5f, 21,
                                                                                           T < 50 ? 25.f : 50.f, 0.5f, wts, stats, tw);
+  } else if (h->surgery_mode >= 2) {
+    gradnorm_coeff_kernel<<<1, 64, 0, st>>>(gram, T, T, gscale, h->surgery_mode == 3, wts, stats);
   } else {
     pcgrad_coeff_kernel<<<1, 64, 2 * T * T * sizeof(float), st>>>(gram, T, T, gscale,
                                                                   critic ? h->pcgrad_perm_critic : h->pcgrad_perm_actor, wts, stats);
@@ -1188,6 +1190,14 @@ extern "C" int mtrl_sac_enable_pcgrad(mtrl_sac_t* h, int critic, int actor, floa
   h->pcgrad_perm_critic = perm_critic;
   h->pcgrad_perm_actor = perm_actor;
   h->surgery_mode = 0;
+  return MTRL_OK;
+}
+
+// Same wiring with the reference's gradnorm (mtrl/optim/gradnorm.py, GradNormConfig mtrl/config/optim.py:79-102).
+extern "C" int mtrl_sac_enable_gradnorm(mtrl_sac_t* h, int critic, int actor, int clip_per_task, float* critic_tg, float* actor_tg,
+                                        float* scratch) {
+  MTRL_PROPAGATE(mtrl_sac_enable_pcgrad(h, critic, actor, critic_tg, actor_tg, scratch, nullptr, nullptr));
+  h->surgery_mode = clip_per_task ? 3 : 2;
   return MTRL_OK;
 }
 

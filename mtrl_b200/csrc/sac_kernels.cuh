@@ -1074,6 +1074,34 @@ static __global__ void cagrad_coeff_kernel(const float* __restrict__ gram, int l
   stats[3] = 0.f;
 }
 
+// GradNorm as the reference implements it (mtrl/optim/gradnorm.py:60-163): its gradnorm_loss does not depend on the task
+// weights (:134-142), so their gradient is zero, Adam leaves them at their normalised initial value 1 (:72-80, 145-153)
+// and the transformation returns sum_i 1 * g_i (:155-157) of the (optionally, max_grad_norm set) per-task clipped
+// gradients (:40-57, 106-107).  stats: [0] norm of that sum, [1] mean per-task norm after clipping.
+static __global__ void gradnorm_coeff_kernel(const float* __restrict__ gram, int ldg, int T, float gscale, int clip_per_task,
+                                             float* __restrict__ w_out, float* __restrict__ stats) {
+  __shared__ float wv[64];
+  const int i = threadIdx.x;
+  if (i < T) {
+    const float n = sqrtf(fmaxf(gram[i * ldg + i] * gscale, 0.f));
+    const float clipc = clip_per_task ? fminf(1.f, 1.f / (n + 1e-8f)) : 1.f;
+    wv[i] = clipc * sqrtf(gscale);   // weight 1 on the reference-scale row = sqrt(gscale) x the unscaled row
+    w_out[i] = wv[i];
+  }
+  __syncthreads();
+  if (i == 0) {
+    double n2 = 0.0, before = 0.0;
+    for (int a = 0; a < T; ++a) {
+      before += static_cast<double>(wv[a]) * sqrt(fmax(static_cast<double>(gram[a * ldg + a]), 0.0));
+      for (int b = 0; b < T; ++b) n2 += static_cast<double>(wv[a]) * wv[b] * gram[a * ldg + b];
+    }
+    stats[0] = static_cast<float>(sqrt(fmax(n2, 0.0)));
+    stats[1] = static_cast<float>(before / T);
+    stats[2] = 0.f;
+    stats[3] = 0.f;
+  }
+}
+
 // out[p] = sum_k w[k] * rows[k][p]   (HBM-bound: reads the (T, P) matrix once)
 static __global__ void weighted_rows_kernel(const float* __restrict__ rows, long long ld, int T, const float* __restrict__ w,
                                             float* __restrict__ out, long long P) {

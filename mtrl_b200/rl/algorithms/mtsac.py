@@ -93,6 +93,7 @@ L._EXTRA_DECLS.update({
     "mtrl_sac_task_grads": ([_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp],),
     "mtrl_sac_enable_pcgrad": ([_vp, _i, _i, _vp, _vp, _vp, _vp, _vp],),
     "mtrl_sac_enable_cagrad": ([_vp, _i, _i, _vp, _vp, _vp],),
+    "mtrl_sac_enable_gradnorm": ([_vp, _i, _i, _i, _vp, _vp, _vp],),
     "mtrl_sac_trunk_owner_mask": ([_vp, _i, _vp],),
     "mtrl_sac_profile_gemms": ([_vp, _i],),
     "mtrl_sac_profile_read": ([_vp, C.POINTER(C.c_double), C.POINTER(_i)],),
@@ -318,10 +319,12 @@ class MTSAC:
         la.fill_(math.log(config.initial_temperature))
 
         self._create_handle()
-        self._pcgrad = (bool(c_opt.pcgrad or c_opt.cagrad), bool(a_opt.pcgrad or a_opt.cagrad))   # (critic, actor) use surgery
-        kinds = {k for o in (c_opt, a_opt) for k in ("pcgrad", "cagrad") if getattr(o, k)}
+        surg = lambda o: bool(o.pcgrad or o.cagrad or o.gradnorm)  # noqa: E731
+        self._pcgrad = (surg(c_opt), surg(a_opt))   # (critic, actor) start their chain with a multi-task transformation
+        kinds = {k for o in (c_opt, a_opt) for k in ("pcgrad", "cagrad", "gradnorm") if getattr(o, k)}
+        self._gradnorm_clip = bool(c_opt.gradnorm_clip_per_task or a_opt.gradnorm_clip_per_task)
         if len(kinds) > 1:
-            raise NotImplementedError("one gradient-surgery optimiser per agent (PCGradConfig or CAGradConfig)")
+            raise NotImplementedError("one multi-task optimiser kind per agent (PCGradConfig, CAGradConfig or GradNormConfig)")
         self._surgery = next(iter(kinds), None)
         if any(self._pcgrad):
             if world_size != 1:
@@ -345,6 +348,11 @@ class MTSAC:
         self._pc_scratch = torch.zeros(2 * T * T + 4 * T + 8, dtype=torch.float32, device=self.device)
         self._pc_perm = torch.arange(T, dtype=torch.int32, device=self.device).repeat(2, 1).contiguous()
         self._pc_gen = torch.Generator().manual_seed(int(seed) + 7919)
+        if self._surgery == "gradnorm":
+            L.check(L.lib().mtrl_sac_enable_gradnorm(self._h, int(self._pcgrad[0]), int(self._pcgrad[1]), int(self._gradnorm_clip),
+                                                     _vp(tg["critic"].data_ptr()), _vp(tg["actor"].data_ptr()),
+                                                     _vp(self._pc_scratch.data_ptr())))
+            return
         if self._surgery == "cagrad":
             L.check(L.lib().mtrl_sac_enable_cagrad(self._h, int(self._pcgrad[0]), int(self._pcgrad[1]), _vp(tg["critic"].data_ptr()),
                                                    _vp(tg["actor"].data_ptr()), _vp(self._pc_scratch.data_ptr())))
@@ -358,6 +366,10 @@ class MTSAC:
         plain mean gradient."""
         T, s = self.num_tasks, self._pc_scratch
         base = 2 * T * T + 2 * T
+        if self._surgery == "gradnorm":
+            names = ("grad_magnitude", "avg_grad_magnitude_per_task")
+            return {net: dict(zip(names, s[base + 4 * i: base + 4 * i + 2]), task_weights=torch.ones(T, device=self.device))
+                    for i, net in enumerate(("critic", "actor")) if self._pcgrad[i]}
         if self._surgery == "cagrad":   # CAGradState (cagrad.py:13-18, 195-203)
             names = ("avg_grad_magnitude", "avg_grad_magnitude_before_surgery", "cagrad_objective")
             return {net: dict(zip(names, s[base + 4 * i: base + 4 * i + 3]), task_weights=s[base + 8 + T * i: base + 8 + T * (i + 1)])

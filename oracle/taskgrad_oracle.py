@@ -164,6 +164,28 @@ def cagrad(flat: torch.Tensor, c: float = 0.5, num_iterations: int = 21, learnin
                  "cagrad_objective": obj_best}
 
 
+def gradnorm(flat: torch.Tensor, task_losses: torch.Tensor, max_grad_norm: float | None = None, asymmetry: float = 0.12,
+             lr: float = 3e-4):
+    """mtrl/optim/gradnorm.py:86-161 for the first update from init_fn's state (:68-81), literally: per-task clip when
+    max_grad_norm is set (:106-107), relative inverse rates (:109-116), the gradnorm loss differentiated with respect to
+    the task weights by autograd (:134-144; the loss does not use them, so the gradient is zero), Adam on the weights,
+    renormalisation (:150-153) and the weighted sum (:155-157)."""
+    T = flat.shape[0]
+    g = flat * torch.clamp(1.0 / (flat.norm(dim=1, keepdim=True) + 1e-8), max=1.0) if max_grad_norm else flat
+    weights = torch.ones(T, dtype=flat.dtype, requires_grad=True)
+    original = task_losses.clone()                       # first step: inf -> the current losses
+    improvement = task_losses / (original + 1e-12)
+    rate = improvement / (improvement.mean() + 1e-12)
+    norms = g.norm(dim=1)
+    loss = (norms - norms.mean() * rate ** asymmetry).abs().sum() + 0.0 * weights.sum()   # (the reference's loss ignores `weights`)
+    loss.backward()
+    grad_w = weights.grad
+    m, v = 0.1 * grad_w, 0.001 * grad_w ** 2
+    new_w = weights.detach() - lr * (m / 0.1) / (torch.sqrt(v / 0.001) + 1e-5)
+    new_w = new_w / new_w.sum() * T
+    return (new_w.reshape(-1, 1) * g).sum(dim=0), {"task_weights": new_w, "grad_magnitude": (new_w.reshape(-1, 1) * g).sum(dim=0).norm()}
+
+
 def _unflatten(flat: torch.Tensor, like) -> dict:
     leaves, off = [], 0
     for x in O.tree_leaves(like):
@@ -173,8 +195,17 @@ def _unflatten(flat: torch.Tensor, like) -> dict:
     return O.tree_map(lambda x: next(it), like)
 
 
+def _surgery(kind: str, flat: torch.Tensor, perm, gradnorm_clip: bool):
+    if kind == "pcgrad":
+        return pcgrad(flat, perm)
+    if kind == "cagrad":
+        return cagrad(flat)
+    # gradnorm: the per-task losses only enter through bookkeeping that cannot move the weights (see gradnorm())
+    return gradnorm(flat, torch.ones(flat.shape[0], dtype=flat.dtype), max_grad_norm=1.0 if gradnorm_clip else None)
+
+
 def mtsac_update_pcgrad(state: O.OracleState, batch, eps_c, eps_a, cfg: O.OracleConfig, perm_c=None, perm_a=None,
-                        critic: bool = True, actor: bool = True, surgery: str = "pcgrad"):
+                        critic: bool = True, actor: bool = True, surgery: str = "pcgrad", gradnorm_clip: bool = False):
     """MTSAC.update (mtsac.py:1173-1251) with split losses and optax.chain(pcgrad, clip_by_global_norm, adam) on the
     chosen networks (surgery="cagrad": cagrad instead, CAGradConfig optim.py:104-124); the other network keeps the plain
     chain.  Returns (new_state, stats)."""
@@ -185,7 +216,7 @@ def mtsac_update_pcgrad(state: O.OracleState, batch, eps_c, eps_a, cfg: O.Oracle
     stats = {}
     ctg = critic_task_grads(state.critic, batch, target, cfg)
     if critic:
-        flat, stats["critic"] = pcgrad(flatten(ctg), perm_c) if surgery == "pcgrad" else cagrad(flatten(ctg))
+        flat, stats["critic"] = _surgery(surgery, flatten(ctg), perm_c, gradnorm_clip)
         cgrads = _unflatten(flat, state.critic)
     else:
         cgrads = O.tree_map(lambda *xs: sum(xs) / len(xs), *ctg)
@@ -195,7 +226,7 @@ def mtsac_update_pcgrad(state: O.OracleState, batch, eps_c, eps_a, cfg: O.Oracle
     new_target = O.tree_map(lambda n, t: cfg.tau * n + (1 - cfg.tau) * t, new_critic, state.critic_target)
     atg, logp = actor_task_grads(state.actor, new_critic, batch, alpha_vals, eps_a, cfg)
     if actor:
-        flat, stats["actor"] = pcgrad(flatten(atg), perm_a) if surgery == "pcgrad" else cagrad(flatten(atg))
+        flat, stats["actor"] = _surgery(surgery, flatten(atg), perm_a, gradnorm_clip)
         agrads = _unflatten(flat, state.actor)
     else:
         agrads = O.tree_map(lambda *xs: sum(xs) / len(xs), *atg)

@@ -160,3 +160,41 @@ def test_cagrad_update_matches_oracle(cuda):
         for leaf, e in SU.compare_deltas(old_t, new_t, tree, ens).items():
             if leaf.startswith("layer_") and leaf.endswith("kernel"):
                 assert e <= 3e-2, (name, leaf, e)
+
+
+@pytest.mark.parametrize("clip", [False, True])
+def test_gradnorm_update_matches_oracle(cuda, clip):
+    """GradNormConfig (mtrl/config/optim.py:79-102).  The reference's gradnorm loss ignores the task weights
+    (gradnorm.py:134-142): the literal restatement (autograd gives a zero weight gradient) reduces to the sum of the
+    per-task gradients, per-task clipped when max_grad_norm is set -- which is what the GPU path must hand to clip + adam."""
+    from mtrl_b200.config.networks import ContinuousActionPolicyConfig, QValueFunctionConfig
+    from mtrl_b200.config.nn import MultiHeadConfig
+    from mtrl_b200.config.optim import GradNormConfig, OptimizerConfig
+    from mtrl_b200.rl.algorithms import MTSAC, MTSACConfig
+
+    T, W, per_task = 5, 128, 32
+    cfg = O.OracleConfig(num_tasks=T, obs_dim=39 + T, action_dim=4, width=W, max_grad_norm=1.0 if clip else None)
+    st = O.init_state(cfg, seed=8, dtype=torch.float32)
+    for net, scale in ((st.actor, 100.0), (st.critic, 30.0), (st.critic_target, 30.0)):
+        for k in ("kernel", "bias"):
+            net["heads"][k] = net["heads"][k] * scale
+    opt = GradNormConfig(lr=cfg.lr, max_grad_norm=cfg.max_grad_norm, eps=cfg.adam_eps, num_tasks=T, gradnorm_optimizer=OptimizerConfig())
+    netc = MultiHeadConfig(width=W, depth=cfg.depth, num_tasks=T, optimizer=opt)
+    mc = MTSACConfig(num_tasks=T, gamma=cfg.gamma, actor_config=ContinuousActionPolicyConfig(network_config=netc),
+                     critic_config=QValueFunctionConfig(network_config=netc),
+                     temperature_optimizer_config=OptimizerConfig(lr=cfg.alpha_lr, max_grad_norm=None, eps=cfg.adam_eps))
+    agent = MTSAC.initialize(mc, SU.EnvSpec(cfg.obs_dim, 4), seed=8, max_batch=per_task * T)
+    SU.load_oracle_state(agent, st)
+    batch, ec, ea = O.synthetic_batch(cfg, per_task, seed=79, dtype=torch.float32)
+    tcfg = dataclasses.replace(cfg, matmul_operands="tf32")
+    st64 = st.to(torch.float64)
+    new, stats = TG.mtsac_update_pcgrad(st64, tuple(b.double() for b in batch), ec.double(), ea.double(), tcfg, surgery="gradnorm",
+                                        gradnorm_clip=clip)
+    agent.update(tuple(b.cuda() for b in batch), eps_c=ec.cuda(), eps_a=ea.cuda(), check=True)
+    got = agent.pcgrad_stats()
+    for net in ("critic", "actor"):
+        assert torch.allclose(stats[net]["task_weights"], torch.ones(T, dtype=torch.float64))   # the weights cannot move
+        assert abs(float(got[net]["grad_magnitude"]) - float(stats[net]["grad_magnitude"])) <= 1e-2 * float(stats[net]["grad_magnitude"])
+    for name, ens, tree in (("critic", True, agent.critic.grads), ("actor", False, agent.actor.grads)):
+        for leaf, e in SU.compare_trees(stats[name]["grad_tree"], tree, ens).items():
+            assert e <= 1e-2, (name, leaf, e)
