@@ -43,19 +43,17 @@ class OptimizerConfig:
         return AdamChainSpec(lr=self.lr, eps=eps, max_grad_norm=self.max_grad_norm)
 
 
-def _unsupported(name):
-    def spawn(self):
-        raise NotImplementedError(f"{name} needs per-task gradients (split losses); not on the accelerated path yet")
-    return spawn
-
-
 @dataclass(frozen=True, kw_only=True)
-class DummyMultiTaskConfig(OptimizerConfig):
+class DummyMultiTaskConfig(OptimizerConfig):   # optim.py:46-59
     @property
     def requires_split_task_losses(self) -> bool:
         return True
 
-    spawn = _unsupported("DummyMultiTaskConfig")
+    def spawn(self) -> AdamChainSpec:
+        """optax.chain(dummy_multitask_optimizer(), OptimizerConfig.spawn()): the dummy transformation averages the
+        per-task gradients (mtrl/optim/dummy.py:18), and with the equal per-task batches the split losses require
+        (mtsac.py:325) that average IS the gradient of the un-split loss -- so the plain fused chain computes it."""
+        return OptimizerConfig.spawn(self)
 
 
 @dataclass(frozen=True, kw_only=True)

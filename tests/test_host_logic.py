@@ -78,8 +78,12 @@ def test_optimizer_configs_outside_the_path_fail_loudly():
     spec = PCGradConfig(num_tasks=3, max_grad_norm=1.0).spawn()   # chain(pcgrad, clip, adam) as data (optim.py:71-75)
     assert spec.pcgrad and spec.max_grad_norm == 1.0 and spec.eps == 1e-5
     assert not OptimizerConfig().spawn().pcgrad
-    with pytest.raises(NotImplementedError):
-        DummyMultiTaskConfig().spawn()
+    from mtrl_b200.config.optim import CAGradConfig, GradNormConfig
+
+    assert DummyMultiTaskConfig(max_grad_norm=1.0).spawn() == OptimizerConfig(max_grad_norm=1.0).spawn()   # mean of per-task grads
+    assert CAGradConfig(num_tasks=3).spawn().cagrad and CAGradConfig(num_tasks=3).requires_split_task_losses
+    g = GradNormConfig(num_tasks=3, max_grad_norm=1.0).spawn()
+    assert g.gradnorm and g.gradnorm_clip_per_task and not GradNormConfig(num_tasks=3).spawn().gradnorm_clip_per_task
 
 
 @pytest.mark.parametrize("T,W,depth,E", [(50, 2048, 3, 2), (10, 400, 3, 2), (10, 256, 2, 1), (7, 100, 4, 3), (50, 4096, 3, 2)])
