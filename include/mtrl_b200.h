@@ -238,6 +238,10 @@ int mtrl_sac_act(mtrl_sac_t* h, const float* obs, int n, const float* eps, int d
 int mtrl_sac_task_grads(mtrl_sac_t* h, const float* obs, const float* actions, const float* next_obs, const float* dones,
                         const float* rewards, int batch, const float* eps_c, const float* eps_a, float* critic_tg,
                         float* actor_tg, void* stream);
+/* Gram matrix of a per-task gradient matrix: gram (T, T) = rows rows^T, fp32 (flat_grads @ flat_grads.T of
+ * compute_gram_metrics, mtsac.py:747; the input of vmap_cos_sim and compute_conflict_metrics, utils.py:49-174).
+ * rows: device fp32 (T, ld) with P valid columns, T <= 64. */
+int mtrl_task_gram(const float* rows, long long ld, int T, long long P, float* gram, void* stream);
 /* PCGradConfig (mtrl/config/optim.py:62-76): optax.chain(pcgrad(num_tasks), clip_by_global_norm, adam).  After this
  * call mtrl_sac_update splits the critic's and / or the actor's loss by task (mtsac.py:568-585, 677-687), runs the
  * per-task gradients through pcgrad (mtrl/optim/pcgrad.py:22-136, in coefficient space over the Gram matrix) and feeds

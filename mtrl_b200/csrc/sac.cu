@@ -1169,6 +1169,21 @@ int update_with_pcgrad(mtrl_sac* h, const float* obs, const float* actions, cons
   return step_alpha(h, st);
 }
 
+// Gram matrix of a (T, P) per-task gradient matrix (rows of ld floats): gram[T][T] = rows rows^T in fp32
+// (compute_gram_metrics, mtsac.py:733-771; the input of vmap_cos_sim / compute_conflict_metrics, utils.py:49-174).
+extern "C" int mtrl_task_gram(const float* rows, long long ld, int T, long long P, float* gram, void* stream) {
+  MTRL_REQUIRE(rows && gram, "mtrl_task_gram: null argument");
+  MTRL_REQUIRE(T >= 1 && T <= 64 && P >= 1 && ld >= P, "mtrl_task_gram: T %d outside [1, 64] or bad row length", T);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  MTRL_CUDA_CHECK(cudaMemsetAsync(gram, 0, static_cast<size_t>(T) * T * sizeof(float), st));
+  gram_kernel<<<sms * 2, 256, 0, st>>>(rows, ld, T, P, gram, T);
+  MTRL_CUDA_CHECK(cudaGetLastError());
+  return MTRL_OK;
+}
+
 // Puts pcgrad in front of the critic's and / or the actor's optimiser chain.  critic_tg / actor_tg: device fp32
 // (T, layout.total) matrices; scratch: device fp32, 2 T^2 + 2 T + 8 floats (Gram matrices, weights, statistics: per
 // network n_grad_conflicts, avg_grad_magnitude, avg_grad_magnitude_before_surgery, norm of the plain mean gradient);

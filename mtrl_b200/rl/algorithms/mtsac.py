@@ -94,6 +94,7 @@ L._EXTRA_DECLS.update({
     "mtrl_sac_enable_pcgrad": ([_vp, _i, _i, _vp, _vp, _vp, _vp, _vp],),
     "mtrl_sac_enable_cagrad": ([_vp, _i, _i, _vp, _vp, _vp],),
     "mtrl_sac_enable_gradnorm": ([_vp, _i, _i, _i, _vp, _vp, _vp],),
+    "mtrl_task_gram": ([_vp, C.c_longlong, _i, C.c_longlong, _vp, _vp],),
     "mtrl_sac_trunk_owner_mask": ([_vp, _i, _vp],),
     "mtrl_sac_profile_gemms": ([_vp, _i],),
     "mtrl_sac_profile_read": ([_vp, C.POINTER(C.c_double), C.POINTER(_i)],),
@@ -672,13 +673,18 @@ class MTSAC:
         """`MTSAC.compute_weights` (mtsac.py:870-1170), the metrics that derive from the per-task gradient matrix
         through its Gram matrix: `{critic,actor}_avg_cos_sim`, `_avg_grad_magnitude`, `_conflict_rate`,
         `_mean_conflict_magnitude`, `_mean_conflict_angle`, `_per_task_conflict_rate`, `_per_task_grad_magnitude`,
-        `_pairwise_conflict`, `_pairwise_cos_sim`, `_pairwise_angle`, `_pairwise_gram` (utils.py:49-72, 118-174).
-        Returns (self, logs) with device tensors.  The element-wise interference / support metrics are not built."""
+        `_pairwise_conflict`, `_pairwise_cos_sim`, `_pairwise_angle`, `_effective_rank` (utils.py:49-72, 104-174) and the
+        `compute_gram_metrics` set (`_avg_cosine_gram`, `_gram_diag`, `_gram_off_diag_mean/_std`, `_pairwise_gram`,
+        `_pairwise_cosine_gram`, mtsac.py:733-771).  Returns (self, logs) with device tensors.  The Gram matrix comes from
+        `mtrl_task_gram`; what follows is T x T bookkeeping.  The element-wise interference / participation / support
+        metrics (which the reference forms through (T, T, P) boolean tensors) are not built."""
         grads = self.per_task_gradients(data, eps_c, eps_a)
         logs = {}
         T = self.num_tasks
         for name, g in grads.items():
-            gram = g @ g.T
+            gram = torch.empty(T, T, dtype=torch.float32, device=self.device)
+            L.check(L.lib().mtrl_task_gram(_vp(g.data_ptr()), g.stride(0), T, g.shape[1], _vp(gram.data_ptr()),
+                                           _vp(L.current_stream_ptr())))
             mag = torch.sqrt(torch.diagonal(gram).clamp_min(0))
             cos = gram / (mag[:, None] * mag[None, :] + 1e-8)
             off = 1 - torch.eye(T, device=g.device)
@@ -687,10 +693,13 @@ class MTSAC:
             n_off = T * (T - 1)
             cm = torch.where((conflict * off).bool(), cos.abs() * (mag[:, None] * mag[None, :]), torch.zeros_like(cos))
             angles = torch.rad2deg(torch.arccos(cos.clamp(-1.0, 1.0)))
+            off_mean = (gram * off).sum() / n_off
+            sv = torch.linalg.svdvals(gram.double())                     # compute_effective_rank (utils.py:104-115) on the Gram
+            sv_dist = sv / sv.sum().clamp_min(1e-10)
             logs.update({
-                f"{name}_avg_cos_sim": (upper * cos).sum() / (upper.sum() + 1e-8),
-                f"{name}_avg_grad_magnitude": mag.mean(),
-                f"{name}_conflict_rate": (conflict * off).sum() / n_off,
+                f"{name}_avg_cos_sim": (upper * cos).sum() / (upper.sum() + 1e-8),                   # utils.py:49-72
+                f"{name}_avg_grad_magnitude": mag.mean(),                                            # mtsac.py:1043
+                f"{name}_conflict_rate": (conflict * off).sum() / n_off,                             # utils.py:118-145
                 f"{name}_mean_conflict_magnitude": (cm * off).sum() / n_off,
                 f"{name}_mean_conflict_angle": (angles * off).sum() / n_off,
                 f"{name}_per_task_conflict_rate": (conflict * off).sum(dim=1) / (T - 1),
@@ -698,7 +707,13 @@ class MTSAC:
                 f"{name}_pairwise_conflict": conflict,
                 f"{name}_pairwise_cos_sim": cos,
                 f"{name}_pairwise_angle": angles,
+                f"{name}_effective_rank": torch.exp(-(sv_dist * torch.log(sv_dist + 1e-10)).sum()).float(),
+                f"{name}_avg_cosine_gram": (cos * off).sum() / n_off,                                # mtsac.py:733-771
+                f"{name}_gram_diag": torch.diagonal(gram),
+                f"{name}_gram_off_diag_mean": off_mean,
+                f"{name}_gram_off_diag_std": torch.sqrt((((gram - off_mean) ** 2) * off).sum() / n_off),
                 f"{name}_pairwise_gram": gram,
+                f"{name}_pairwise_cosine_gram": cos,
             })
         return self, logs
 

@@ -53,6 +53,15 @@ def test_per_task_gradients_and_cos_sim(cuda, T, W, per_task):
         mag = logs[f"{name}_per_task_grad_magnitude"].double().cpu()
         assert SU.rel(mag, cm_ref["per_task_grad_magnitude"]) <= 1e-2
         assert abs(float(logs[f"{name}_avg_grad_magnitude"]) - float(g_ref.norm(dim=1).mean())) <= 1e-2 * float(g_ref.norm(dim=1).mean())
+        # compute_gram_metrics (mtsac.py:733-771) and compute_effective_rank (utils.py:104-115)
+        gram_ref = g_ref @ g_ref.T
+        assert SU.rel(logs[f"{name}_pairwise_gram"], gram_ref) <= 2e-2
+        sv = torch.linalg.svdvals(gram_ref)
+        sd = sv / sv.sum()
+        assert abs(float(logs[f"{name}_effective_rank"]) - float(torch.exp(-(sd * torch.log(sd + 1e-10)).sum()))) <= 5e-2
+        off = 1 - torch.eye(T, dtype=torch.float64)
+        assert abs(float(logs[f"{name}_gram_off_diag_mean"]) - float((gram_ref * off).sum() / (T * (T - 1)))) <= \
+            2e-2 * float(gram_ref.abs().max())
 
 
 def test_uneven_split_is_rejected(cuda):
