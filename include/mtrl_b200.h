@@ -242,6 +242,13 @@ int mtrl_sac_task_grads(mtrl_sac_t* h, const float* obs, const float* actions, c
  * compute_gram_metrics, mtsac.py:747; the input of vmap_cos_sim and compute_conflict_metrics, utils.py:49-174).
  * rows: device fp32 (T, ld) with P valid columns, T <= 64. */
 int mtrl_task_gram(const float* rows, long long ld, int T, long long P, float* gram, void* stream);
+/* The element-wise reductions of compute_conflict_metrics (mtrl/rl/algorithms/utils.py:75-101) over a per-task gradient
+ * matrix rows (T, ld), P valid columns, every element multiplied by `scale` first:
+ *   mismatch (T, T) fp32 : #{p : |x_a| < eps and |x_b| > tau}   (compute_sparsity_mismatch before its normalisation)
+ *   row_stats (T, 2) f64 : {sum_p |x_t|, #{p : |x_t| < eps}}     (participation ratio l1, near-zero counts)
+ * Columns that are layout padding are zero and therefore counted as near-zero: the caller subtracts them. */
+int mtrl_task_elementwise(const float* rows, long long ld, int T, long long P, float scale, float eps, float tau,
+                          float* mismatch, double* row_stats, void* stream);
 /* PCGradConfig (mtrl/config/optim.py:62-76): optax.chain(pcgrad(num_tasks), clip_by_global_norm, adam).  After this
  * call mtrl_sac_update splits the critic's and / or the actor's loss by task (mtsac.py:568-585, 677-687), runs the
  * per-task gradients through pcgrad (mtrl/optim/pcgrad.py:22-136, in coefficient space over the Gram matrix) and feeds

@@ -1102,7 +1102,7 @@ int pcgrad_combine(mtrl_sac* h, bool critic, cudaStream_t st) {
   float* wts = h->pcgrad_scratch + 2 * T * T + (critic ? 0 : T);
   float* stats = h->pcgrad_scratch + 2 * T * T + 2 * T + (critic ? 0 : 4);
   MTRL_CUDA_CHECK(cudaMemsetAsync(gram, 0, static_cast<size_t>(T) * T * sizeof(float), st));
-  gram_kernel<<<h->sms * 2, 256, 0, st>>>(tg, L.total, T, L.total, gram, T);
+  pairwise_kernel<0><<<h->sms * 2, 256, 0, st>>>(tg, L.total, T, L.total, gram, T, 1.f, 0.f, 0.f);
   const float gscale = static_cast<float>(T) * static_cast<float>(T);
   if (h->surgery_mode == 1) {
     // cagrad(num_tasks) defaults (cagrad.py:20-41): c = 0.5, 21 iterations, lr 25 (< 50 tasks) or 50, momentum 0.5;
@@ -1179,7 +1179,28 @@ extern "C" int mtrl_task_gram(const float* rows, long long ld, int T, long long 
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   MTRL_CUDA_CHECK(cudaMemsetAsync(gram, 0, static_cast<size_t>(T) * T * sizeof(float), st));
-  gram_kernel<<<sms * 2, 256, 0, st>>>(rows, ld, T, P, gram, T);
+  pairwise_kernel<0><<<sms * 2, 256, 0, st>>>(rows, ld, T, P, gram, T, 1.f, 0.f, 0.f);
+  MTRL_CUDA_CHECK(cudaGetLastError());
+  return MTRL_OK;
+}
+
+// The element-wise part of compute_conflict_metrics (utils.py:75-101, 146-156) on a (T, P) per-task gradient matrix:
+// mismatch[a][b] = #{p : |s rows[a][p]| < eps and |s rows[b][p]| > tau} (compute_sparsity_mismatch before the division by
+// the near-zero counts) and row_stats[t] = {sum_p |s rows[t][p]|, #{p : |s rows[t][p]| < eps}} (participation ratio,
+// near-zero counts).  `pad` = columns of the flat layout that are alignment padding (always zero): they are removed from
+// the near-zero counts here so the caller sees the reference's d = P - pad parameters.
+extern "C" int mtrl_task_elementwise(const float* rows, long long ld, int T, long long P, float scale, float eps, float tau,
+                                     float* mismatch, double* row_stats, void* stream) {
+  MTRL_REQUIRE(rows && mismatch && row_stats, "mtrl_task_elementwise: null argument");
+  MTRL_REQUIRE(T >= 1 && T <= 64 && P >= 1 && ld >= P, "mtrl_task_elementwise: T %d outside [1, 64] or bad row length", T);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  MTRL_CUDA_CHECK(cudaMemsetAsync(mismatch, 0, static_cast<size_t>(T) * T * sizeof(float), st));
+  MTRL_CUDA_CHECK(cudaMemsetAsync(row_stats, 0, static_cast<size_t>(T) * 2 * sizeof(double), st));
+  pairwise_kernel<1><<<sms * 2, 256, 0, st>>>(rows, ld, T, P, mismatch, T, scale, eps, tau);
+  row_stats_kernel<<<dim3(sms, T), 256, 0, st>>>(rows, ld, P, scale, eps, row_stats);
   MTRL_CUDA_CHECK(cudaGetLastError());
   return MTRL_OK;
 }

@@ -1121,9 +1121,14 @@ static __global__ void weighted_rows_kernel(const float* __restrict__ rows, long
   }
 }
 
-// G[a][b] += sum_p rows[a][p] rows[b][p] over this block's column range (fp32 CUDA cores; T <= 64).
-// grid.x blocks of 256 threads; thread (a, b-group) register-tiles 4 x 4 Gram entries over a shared (T x 64) tile.
-static __global__ void gram_kernel(const float* __restrict__ rows, long long ld, int T, long long P, float* __restrict__ gram, int ldg) {
+// Pairwise reductions over the columns of a (T, P) matrix, T <= 64:  out[a][b] += sum_p f(rows[a][p], rows[b][p]).
+//   MODE 0: f = x y                                   Gram matrix (fp32 CUDA cores)
+//   MODE 1: f = [|s x| < eps] [|s y| > tau]           compute_sparsity_mismatch (utils.py:75-91): a's near-zero elements
+//                                                     that b updates strongly (s = row scale, counts exact per block)
+// grid.x blocks of 256 threads; thread (a-group, b-group) register-tiles 4 x 4 entries over a shared (64 x 64) tile.
+template <int MODE>
+static __global__ void pairwise_kernel(const float* __restrict__ rows, long long ld, int T, long long P, float* __restrict__ out, int ldo,
+                                       float s, float eps, float tau) {
   __shared__ float tile[64][65];
   const int ta = (threadIdx.x / 16) * 4, tb = (threadIdx.x % 16) * 4;   // 16 x 16 threads cover 64 x 64 entries
   float acc[4][4];
@@ -1137,7 +1142,8 @@ static __global__ void gram_kernel(const float* __restrict__ rows, long long ld,
     __syncthreads();
     for (int idx = threadIdx.x; idx < 64 * 64; idx += blockDim.x) {
       const int r = idx / 64, cc = idx % 64;
-      tile[r][cc] = (r < T && c0 + cc < p1) ? rows[r * ld + c0 + cc] : 0.f;
+      // MODE 1: out-of-range entries must be neither "near zero" nor "large": NaN fails both comparisons
+      tile[r][cc] = (r < T && c0 + cc < p1) ? rows[r * ld + c0 + cc] : (MODE == 0 ? 0.f : __int_as_float(0x7fc00000));
     }
     __syncthreads();
 #pragma unroll 8
@@ -1147,17 +1153,47 @@ static __global__ void gram_kernel(const float* __restrict__ rows, long long ld,
       for (int a = 0; a < 4; ++a) va[a] = tile[ta + a][cc];
 #pragma unroll
       for (int b = 0; b < 4; ++b) vb[b] = tile[tb + b][cc];
+      if (MODE == 0) {
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(va[a], vb[b], acc[a][b]);
+          for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(va[a], vb[b], acc[a][b]);
+      } else {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const float nz = fabsf(va[a] * s) < eps ? 1.f : 0.f;
+#pragma unroll
+          for (int b = 0; b < 4; ++b) acc[a][b] += (fabsf(vb[b] * s) > tau) ? nz : 0.f;
+        }
+      }
     }
   }
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b)
-      if (ta + a < T && tb + b < T) atomicAdd(&gram[(ta + a) * ldg + tb + b], acc[a][b]);
+      if (ta + a < T && tb + b < T) atomicAdd(&out[(ta + a) * ldo + tb + b], acc[a][b]);
+}
+
+// Per-row sums over the columns: out[t] = {sum |s x|, count(|s x| < eps)}   (participation ratio, near-zero counts:
+// utils.py:86-87, 94-101).  grid (blocks, T)
+static __global__ void row_stats_kernel(const float* __restrict__ rows, long long ld, long long P, float s, float eps,
+                                        double* __restrict__ out2) {
+  __shared__ double red[32];
+  const int t = blockIdx.y;
+  const float* r = rows + t * ld;
+  double l1 = 0.0, nz = 0.0;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < P; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float v = fabsf(r[i] * s);
+    l1 += v;
+    nz += v < eps ? 1.0 : 0.0;
+  }
+  l1 = block_sum(l1, red);
+  nz = block_sum(nz, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(&out2[2 * t], l1);
+    atomicAdd(&out2[2 * t + 1], nz);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -95,6 +95,7 @@ L._EXTRA_DECLS.update({
     "mtrl_sac_enable_cagrad": ([_vp, _i, _i, _vp, _vp, _vp],),
     "mtrl_sac_enable_gradnorm": ([_vp, _i, _i, _i, _vp, _vp, _vp],),
     "mtrl_task_gram": ([_vp, C.c_longlong, _i, C.c_longlong, _vp, _vp],),
+    "mtrl_task_elementwise": ([_vp, C.c_longlong, _i, C.c_longlong, C.c_float, C.c_float, C.c_float, _vp, _vp, _vp],),
     "mtrl_sac_trunk_owner_mask": ([_vp, _i, _vp],),
     "mtrl_sac_profile_gemms": ([_vp, _i],),
     "mtrl_sac_profile_read": ([_vp, C.POINTER(C.c_double), C.POINTER(_i)],),
@@ -676,8 +677,10 @@ class MTSAC:
         `_pairwise_conflict`, `_pairwise_cos_sim`, `_pairwise_angle`, `_effective_rank` (utils.py:49-72, 104-174) and the
         `compute_gram_metrics` set (`_avg_cosine_gram`, `_gram_diag`, `_gram_off_diag_mean/_std`, `_pairwise_gram`,
         `_pairwise_cosine_gram`, mtsac.py:733-771).  Returns (self, logs) with device tensors.  The Gram matrix comes from
-        `mtrl_task_gram`; what follows is T x T bookkeeping.  The element-wise interference / participation / support
-        metrics (which the reference forms through (T, T, P) boolean tensors) are not built."""
+        `mtrl_task_gram`; the element-wise set (`_avg_interference_rate`, `_interference_asymmetry`,
+        `_per_task_interference_in/_out`, `_pairwise_interference_rate`, `_avg/_per_task_participation_ratio`,
+        utils.py:75-101, 146-156) from `mtrl_task_elementwise`; what follows is T x T bookkeeping.  Only
+        `compute_support_metrics` (per-task 0.8-quantile supports, mtsac.py:774-860) is not built."""
         grads = self.per_task_gradients(data, eps_c, eps_a)
         logs = {}
         T = self.num_tasks
@@ -714,6 +717,24 @@ class MTSAC:
                 f"{name}_gram_off_diag_std": torch.sqrt((((gram - off_mean) ** 2) * off).sum() / n_off),
                 f"{name}_pairwise_gram": gram,
                 f"{name}_pairwise_cosine_gram": cos,
+            })
+            # element-wise part (utils.py:75-101, 146-156; eps = 1e-3, tau = 1.0 as compute_conflict_metrics' defaults)
+            mism = torch.empty(T, T, dtype=torch.float32, device=self.device)
+            rstat = torch.empty(T, 2, dtype=torch.float64, device=self.device)
+            L.check(L.lib().mtrl_task_elementwise(_vp(g.data_ptr()), g.stride(0), T, g.shape[1], 1.0, 1e-3, 1.0,
+                                                  _vp(mism.data_ptr()), _vp(rstat.data_ptr()), _vp(L.current_stream_ptr())))
+            d = self.get_num_params()[f"{name}_num_params"]          # the reference's num_params (no layout padding)
+            nz_counts = (rstat[:, 1] - (g.shape[1] - d)).clamp_min(1.0)
+            rate = (mism.double() / nz_counts[:, None]) * off.double()
+            pr = rstat[:, 0] ** 2 / (d * torch.diagonal(gram).double().clamp_min(1e-10))
+            logs.update({
+                f"{name}_avg_interference_rate": (rate.sum() / n_off).float(),
+                f"{name}_interference_asymmetry": ((rate - rate.T).abs().sum() / n_off).float(),
+                f"{name}_per_task_interference_in": (rate.sum(dim=0) / (T - 1)).float(),
+                f"{name}_per_task_interference_out": (rate.sum(dim=1) / (T - 1)).float(),
+                f"{name}_pairwise_interference_rate": rate.float(),
+                f"{name}_avg_participation_ratio": pr.mean().float(),
+                f"{name}_per_task_participation_ratio": pr.float(),
             })
         return self, logs
 

@@ -96,6 +96,21 @@ def conflict_metrics(cos: torch.Tensor, g: torch.Tensor) -> dict:
             "per_task_conflict_rate": (conflict * off).sum(dim=1) / (T - 1), "per_task_grad_magnitude": mag}
 
 
+def elementwise_metrics(g: torch.Tensor, eps: float = 1e-3, tau: float = 1.0) -> dict:
+    """compute_sparsity_mismatch, compute_participation_ratio and their summaries in compute_conflict_metrics
+    (utils.py:75-101, 146-156)."""
+    T, n = g.shape
+    off = 1 - torch.eye(T, dtype=g.dtype)
+    near_zero, large = g.abs() < eps, g.abs() > tau
+    mismatch = (near_zero[:, None, :] & large[None, :, :]).sum(dim=-1).to(g.dtype)
+    rate = mismatch / near_zero.sum(dim=1).clamp(min=1).to(g.dtype)[:, None] * off
+    n_off = T * (T - 1)
+    pr = g.abs().sum(dim=1) ** 2 / (n * (g ** 2).sum(dim=1).clamp(min=1e-10))
+    return {"avg_interference_rate": (rate * off).sum() / n_off, "interference_asymmetry": ((rate - rate.T).abs() * off).sum() / n_off,
+            "per_task_interference_in": (rate * off).sum(dim=0) / (T - 1), "per_task_interference_out": (rate * off).sum(dim=1) / (T - 1),
+            "pairwise_interference_rate": rate, "avg_participation_ratio": pr.mean(), "per_task_participation_ratio": pr}
+
+
 # --------------------------------------------------------------------------------------------
 # pcgrad (mtrl/optim/pcgrad.py:22-136) and the update that uses it (PCGradConfig, mtrl/config/optim.py:62-76)
 # --------------------------------------------------------------------------------------------

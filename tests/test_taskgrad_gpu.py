@@ -59,6 +59,13 @@ def test_per_task_gradients_and_cos_sim(cuda, T, W, per_task):
         sv = torch.linalg.svdvals(gram_ref)
         sd = sv / sv.sum()
         assert abs(float(logs[f"{name}_effective_rank"]) - float(torch.exp(-(sd * torch.log(sd + 1e-10)).sum()))) <= 5e-2
+        # element-wise metrics (utils.py:75-101, 146-156): thresholds at 1e-3 / 1.0, so tf32 noise moves a few elements
+        em = TG.elementwise_metrics(g_ref)
+        assert SU.rel(logs[f"{name}_per_task_participation_ratio"], em["per_task_participation_ratio"]) <= 1e-2
+        rate = logs[f"{name}_pairwise_interference_rate"].double().cpu()
+        assert (rate - em["pairwise_interference_rate"]).abs().max() <= 2e-3 + 2e-2 * float(em["pairwise_interference_rate"].max())
+        assert abs(float(logs[f"{name}_avg_interference_rate"]) - float(em["avg_interference_rate"])) <= \
+            1e-3 + 2e-2 * float(em["avg_interference_rate"])
         off = 1 - torch.eye(T, dtype=torch.float64)
         assert abs(float(logs[f"{name}_gram_off_diag_mean"]) - float((gram_ref * off).sum() / (T * (T - 1)))) <= \
             2e-2 * float(gram_ref.abs().max())
