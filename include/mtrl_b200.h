@@ -249,6 +249,15 @@ int mtrl_task_gram(const float* rows, long long ld, int T, long long P, float* g
  * Columns that are layout padding are zero and therefore counted as near-zero: the caller subtracts them. */
 int mtrl_task_elementwise(const float* rows, long long ld, int T, long long P, float scale, float eps, float tau,
                           float* mismatch, double* row_stats, void* stream);
+/* compute_support_metrics (mtrl/rl/algorithms/mtsac.py:774-860) building blocks on a per-task gradient matrix rows (T, ld):
+ * mtrl_task_abs_order_stats: out2 (T, 2) device fp32 = the ranks[t]-th and (ranks[t] + 1)-th smallest |x| of row t (radix
+ *   select; the two neighbours jnp.quantile(|g|, 0.8) interpolates between, :804-806).  ranks: HOST long long[T];
+ *   scratch: device, T * (32 + 2048) bytes.  Synchronises the stream once.
+ * mtrl_task_support_pairs: out3 (3, T, T) device fp32 = for supports {|x_t| >= thr[t]}: support intersections, sign
+ *   conflicts (x_a x_b < 0), genuine conflicts (both in support and sign conflict) (:809-835). */
+int mtrl_task_abs_order_stats(const float* rows, long long ld, int T, long long P, const long long* ranks, float* out2,
+                              void* scratch, void* stream);
+int mtrl_task_support_pairs(const float* rows, long long ld, int T, long long P, const float* thr, float* out3, void* stream);
 /* PCGradConfig (mtrl/config/optim.py:62-76): optax.chain(pcgrad(num_tasks), clip_by_global_norm, adam).  After this
  * call mtrl_sac_update splits the critic's and / or the actor's loss by task (mtsac.py:568-585, 677-687), runs the
  * per-task gradients through pcgrad (mtrl/optim/pcgrad.py:22-136, in coefficient space over the Gram matrix) and feeds

@@ -1205,6 +1205,53 @@ extern "C" int mtrl_task_elementwise(const float* rows, long long ld, int T, lon
   return MTRL_OK;
 }
 
+// Per-row order statistics of |rows| (radix select on the float bits, 4 one-byte passes): out2[t] = {the rank0[t]-th and
+// the (rank0[t] + 1)-th smallest |x| of row t} -- the two neighbours jnp.quantile interpolates between
+// (compute_support_metrics, mtsac.py:804-806).  ranks: host long long[T]; scratch: device, T * (32 + 2048) bytes.
+extern "C" int mtrl_task_abs_order_stats(const float* rows, long long ld, int T, long long P, const long long* ranks, float* out2,
+                                         void* scratch, void* stream) {
+  MTRL_REQUIRE(rows && ranks && out2 && scratch, "mtrl_task_abs_order_stats: null argument");
+  MTRL_REQUIRE(T >= 1 && T <= 64 && P >= 2 && ld >= P, "mtrl_task_abs_order_stats: T %d outside [1, 64] or bad row length", T);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  unsigned long long* state = static_cast<unsigned long long*>(scratch);                 // [T][2]{prefix, rank}
+  unsigned int* hist = reinterpret_cast<unsigned int*>(state + static_cast<size_t>(T) * 4);   // [T][2][256]
+  std::vector<unsigned long long> init(static_cast<size_t>(T) * 4, 0ull);
+  for (int t = 0; t < T; ++t) {
+    MTRL_REQUIRE(ranks[t] >= 0 && ranks[t] + 1 < P, "mtrl_task_abs_order_stats: rank %lld outside [0, P - 2]", ranks[t]);
+    init[(t * 2 + 0) * 2 + 1] = static_cast<unsigned long long>(ranks[t]);
+    init[(t * 2 + 1) * 2 + 1] = static_cast<unsigned long long>(ranks[t] + 1);
+  }
+  MTRL_CUDA_CHECK(cudaMemcpyAsync(state, init.data(), init.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+  MTRL_CUDA_CHECK(cudaStreamSynchronize(st));   // `init` is a pageable host vector
+  MTRL_CUDA_CHECK(cudaMemsetAsync(hist, 0, static_cast<size_t>(T) * 512 * sizeof(unsigned int), st));
+  for (int pass = 0; pass < 4; ++pass) {
+    select_hist_kernel<<<dim3(sms, T), 256, 0, st>>>(rows, ld, P, pass, state, hist);
+    select_scan_kernel<<<T, 256, 0, st>>>(pass, state, hist);
+  }
+  order_stats_out_kernel<<<1, 64, 0, st>>>(state, T, out2);
+  MTRL_CUDA_CHECK(cudaGetLastError());
+  return MTRL_OK;
+}
+
+// compute_support_metrics' pairwise counts (mtsac.py:809-835) for supports {|x_t| >= thr[t]}: out3 (3, T, T) fp32 =
+// support intersections, sign conflicts, genuine conflicts (sign conflict with both elements in their supports).
+extern "C" int mtrl_task_support_pairs(const float* rows, long long ld, int T, long long P, const float* thr, float* out3,
+                                       void* stream) {
+  MTRL_REQUIRE(rows && thr && out3, "mtrl_task_support_pairs: null argument");
+  MTRL_REQUIRE(T >= 1 && T <= 64 && P >= 1 && ld >= P, "mtrl_task_support_pairs: T %d outside [1, 64] or bad row length", T);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  MTRL_CUDA_CHECK(cudaMemsetAsync(out3, 0, static_cast<size_t>(3) * T * T * sizeof(float), st));
+  support_pairs_kernel<<<sms * 2, 256, 0, st>>>(rows, ld, T, P, thr, out3);
+  MTRL_CUDA_CHECK(cudaGetLastError());
+  return MTRL_OK;
+}
+
 // Puts pcgrad in front of the critic's and / or the actor's optimiser chain.  critic_tg / actor_tg: device fp32
 // (T, layout.total) matrices; scratch: device fp32, 2 T^2 + 2 T + 8 floats (Gram matrices, weights, statistics: per
 // network n_grad_conflicts, avg_grad_magnitude, avg_grad_magnitude_before_surgery, norm of the plain mean gradient);

@@ -1175,6 +1175,116 @@ static __global__ void pairwise_kernel(const float* __restrict__ rows, long long
       if (ta + a < T && tb + b < T) atomicAdd(&out[(ta + a) * ldo + tb + b], acc[a][b]);
 }
 
+// compute_support_metrics (mtsac.py:774-860): with per-row support thresholds thr[t] (the 0.8-quantile of |x|),
+//   out3[0][a][b] += #{p : |x_a| >= thr_a and |x_b| >= thr_b}             support intersection
+//   out3[1][a][b] += #{p : x_a x_b < 0}                                   sign conflicts
+//   out3[2][a][b] += #{p : both in support and x_a x_b < 0}              genuine conflicts
+static __global__ void support_pairs_kernel(const float* __restrict__ rows, long long ld, int T, long long P, const float* __restrict__ thr,
+                                            float* __restrict__ out3) {
+  __shared__ float tile[64][65];
+  __shared__ float sthr[64];
+  if (threadIdx.x < 64) sthr[threadIdx.x] = threadIdx.x < T ? thr[threadIdx.x] : INFINITY;
+  const int ta = (threadIdx.x / 16) * 4, tb = (threadIdx.x % 16) * 4;
+  float inter[4][4], conf[4][4], genu[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) { inter[a][b] = 0.f; conf[a][b] = 0.f; genu[a][b] = 0.f; }
+  const long long per = ((P + gridDim.x - 1) / gridDim.x + 63) / 64 * 64;
+  const long long p0 = per * blockIdx.x, p1 = min(P, p0 + per);
+  for (long long c0 = p0; c0 < p1; c0 += 64) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 64 * 64; idx += blockDim.x) {
+      const int r = idx / 64, cc = idx % 64;
+      tile[r][cc] = (r < T && c0 + cc < p1) ? rows[r * ld + c0 + cc] : __int_as_float(0x7fc00000);   // NaN: in no set
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int cc = 0; cc < 64; ++cc) {
+      float va[4], vb[4];
+      bool sa[4], sb[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) { va[a] = tile[ta + a][cc]; sa[a] = fabsf(va[a]) >= sthr[ta + a]; }
+#pragma unroll
+      for (int b = 0; b < 4; ++b) { vb[b] = tile[tb + b][cc]; sb[b] = fabsf(vb[b]) >= sthr[tb + b]; }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const bool both = sa[a] && sb[b];
+          const bool neg = va[a] * vb[b] < 0.f;
+          inter[a][b] += both ? 1.f : 0.f;
+          conf[a][b] += neg ? 1.f : 0.f;
+          genu[a][b] += (both && neg) ? 1.f : 0.f;
+        }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      if (ta + a < T && tb + b < T) {
+        const int o = (ta + a) * T + tb + b;
+        atomicAdd(&out3[o], inter[a][b]);
+        atomicAdd(&out3[T * T + o], conf[a][b]);
+        atomicAdd(&out3[2 * T * T + o], genu[a][b]);
+      }
+}
+
+// Order statistics of |x| per row by radix select on the float bits (non-negative floats order like their uint32 bits):
+// 4 passes of one byte, most significant first.  state[t][s] = {prefix, remaining rank} for two targets s = 0, 1 per row
+// (the two neighbours the linear-interpolation quantile needs).  select_hist_kernel: grid (blocks, T); histograms of the
+// current byte among the elements matching each target's prefix.  select_scan_kernel: grid T, picks the bin.
+static __global__ void select_hist_kernel(const float* __restrict__ rows, long long ld, long long P, int pass,
+                                          const unsigned long long* __restrict__ state, unsigned int* __restrict__ hist) {
+  __shared__ unsigned int sh[2][256];
+  const int t = blockIdx.y;
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) (&sh[0][0])[i] = 0u;
+  __syncthreads();
+  const int shift = 24 - 8 * pass;
+  const unsigned int mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+  const unsigned int pre0 = static_cast<unsigned int>(state[(t * 2 + 0) * 2]), pre1 = static_cast<unsigned int>(state[(t * 2 + 1) * 2]);
+  const float* r = rows + t * ld;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < P; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const unsigned int key = __float_as_uint(fabsf(r[i]));
+    const unsigned int b = (key >> shift) & 0xffu;
+    if ((key & mask) == (pre0 & mask)) atomicAdd(&sh[0][b], 1u);
+    if ((key & mask) == (pre1 & mask)) atomicAdd(&sh[1][b], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+    const unsigned int v = (&sh[0][0])[i];
+    if (v) atomicAdd(&hist[t * 512 + i], v);
+  }
+}
+
+static __global__ void select_scan_kernel(int pass, unsigned long long* __restrict__ state, unsigned int* __restrict__ hist) {
+  const int t = blockIdx.x, s = threadIdx.x;   // 2 threads: one per target
+  if (s < 2) {
+    unsigned int* h = hist + t * 512 + s * 256;
+    unsigned long long rank = state[(t * 2 + s) * 2 + 1];
+    const int shift = 24 - 8 * pass;
+    unsigned int prefix = static_cast<unsigned int>(state[(t * 2 + s) * 2]);
+    for (int b = 0; b < 256; ++b) {
+      const unsigned int c = h[b];
+      if (rank < c) { prefix |= static_cast<unsigned int>(b) << shift; break; }
+      rank -= c;
+    }
+    state[(t * 2 + s) * 2] = prefix;
+    state[(t * 2 + s) * 2 + 1] = rank;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) hist[t * 512 + i] = 0u;   // ready for the next pass
+}
+
+static __global__ void order_stats_out_kernel(const unsigned long long* __restrict__ state, int T, float* __restrict__ out2) {
+  const int t = threadIdx.x;
+  if (t < T) {
+    out2[2 * t] = __uint_as_float(static_cast<unsigned int>(state[(t * 2 + 0) * 2]));
+    out2[2 * t + 1] = __uint_as_float(static_cast<unsigned int>(state[(t * 2 + 1) * 2]));
+  }
+}
+
 // Per-row sums over the columns: out[t] = {sum |s x|, count(|s x| < eps)}   (participation ratio, near-zero counts:
 // utils.py:86-87, 94-101).  grid (blocks, T)
 static __global__ void row_stats_kernel(const float* __restrict__ rows, long long ld, long long P, float s, float eps,

@@ -96,6 +96,8 @@ L._EXTRA_DECLS.update({
     "mtrl_sac_enable_gradnorm": ([_vp, _i, _i, _i, _vp, _vp, _vp],),
     "mtrl_task_gram": ([_vp, C.c_longlong, _i, C.c_longlong, _vp, _vp],),
     "mtrl_task_elementwise": ([_vp, C.c_longlong, _i, C.c_longlong, C.c_float, C.c_float, C.c_float, _vp, _vp, _vp],),
+    "mtrl_task_abs_order_stats": ([_vp, C.c_longlong, _i, C.c_longlong, C.POINTER(C.c_longlong), _vp, _vp, _vp],),
+    "mtrl_task_support_pairs": ([_vp, C.c_longlong, _i, C.c_longlong, _vp, _vp, _vp],),
     "mtrl_sac_trunk_owner_mask": ([_vp, _i, _vp],),
     "mtrl_sac_profile_gemms": ([_vp, _i],),
     "mtrl_sac_profile_read": ([_vp, C.POINTER(C.c_double), C.POINTER(_i)],),
@@ -679,8 +681,11 @@ class MTSAC:
         `_pairwise_cosine_gram`, mtsac.py:733-771).  Returns (self, logs) with device tensors.  The Gram matrix comes from
         `mtrl_task_gram`; the element-wise set (`_avg_interference_rate`, `_interference_asymmetry`,
         `_per_task_interference_in/_out`, `_pairwise_interference_rate`, `_avg/_per_task_participation_ratio`,
-        utils.py:75-101, 146-156) from `mtrl_task_elementwise`; what follows is T x T bookkeeping.  Only
-        `compute_support_metrics` (per-task 0.8-quantile supports, mtsac.py:774-860) is not built."""
+        utils.py:75-101, 146-156) from `mtrl_task_elementwise`; the `compute_support_metrics` set (`_avg_jaccard`,
+        `_pairwise_jaccard`, `_avg_genuine/_ghost_conflict_rate`, `_ghost_to_genuine_ratio`, `_per_task/_avg_support_size`,
+        `_pairwise_genuine/_ghost_conflict_rate`, mtsac.py:774-860) from `mtrl_task_abs_order_stats` (radix select of
+        the 0.8-quantile) and `mtrl_task_support_pairs`; what follows is T x T bookkeeping.  All 66 keys of the
+        reference's dictionary (mtsac.py:1085-1170) are present (tests/golden/compute_weights_keys.json)."""
         grads = self.per_task_gradients(data, eps_c, eps_a)
         logs = {}
         T = self.num_tasks
@@ -735,6 +740,40 @@ class MTSAC:
                 f"{name}_pairwise_interference_rate": rate.float(),
                 f"{name}_avg_participation_ratio": pr.mean().float(),
                 f"{name}_per_task_participation_ratio": pr.float(),
+            })
+            # compute_support_metrics (mtsac.py:774-860): support = top 20 % of |g| per task (0.8-quantile, linear
+            # interpolation between two order statistics found by radix select), then pairwise counts
+            P, pad = g.shape[1], g.shape[1] - d
+            pos = 0.8 * (d - 1)
+            k, frac = int(math.floor(pos)), pos - math.floor(pos)
+            ranks = (C.c_longlong * T)(*([pad + k] * T))      # the layout's padding zeros sort first
+            ostat = torch.empty(T, 2, dtype=torch.float32, device=self.device)
+            scratch = torch.empty(T * (32 + 2048) // 4, dtype=torch.int32, device=self.device)
+            L.check(L.lib().mtrl_task_abs_order_stats(_vp(g.data_ptr()), g.stride(0), T, P, ranks, _vp(ostat.data_ptr()),
+                                                      _vp(scratch.data_ptr()), _vp(L.current_stream_ptr())))
+            thr = (ostat[:, 0] + frac * (ostat[:, 1] - ostat[:, 0])).contiguous()
+            pairs = torch.empty(3, T, T, dtype=torch.float32, device=self.device)
+            L.check(L.lib().mtrl_task_support_pairs(_vp(g.data_ptr()), g.stride(0), T, P, _vp(thr.data_ptr()), _vp(pairs.data_ptr()),
+                                                    _vp(L.current_stream_ptr())))
+            inter, conf_cnt, genuine = pairs[0].double(), pairs[1].double(), pairs[2].double()
+            zero_thr = (thr <= 0).double()                      # a zero threshold puts the padding zeros in the support
+            inter = inter - pad * zero_thr[:, None] * zero_thr[None, :]
+            size = torch.diagonal(inter)
+            union = size[:, None] + size[None, :] - inter
+            jacc = inter / (union + 1e-8)
+            ghost = conf_cnt - genuine
+            tot = genuine + ghost + 1e-8
+            offd = off.double()
+            logs.update({
+                f"{name}_avg_jaccard": ((jacc * offd).sum() / n_off).float(),
+                f"{name}_pairwise_jaccard": jacc.float(),
+                f"{name}_avg_genuine_conflict_rate": (((genuine / tot) * offd).sum() / n_off).float(),
+                f"{name}_avg_ghost_conflict_rate": (((ghost / tot) * offd).sum() / n_off).float(),
+                f"{name}_ghost_to_genuine_ratio": (ghost.sum() / (genuine.sum() + 1e-8)).float(),
+                f"{name}_per_task_support_size": size.float(),
+                f"{name}_avg_support_size": size.mean().float(),
+                f"{name}_pairwise_genuine_conflict_rate": (genuine / tot).float(),
+                f"{name}_pairwise_ghost_conflict_rate": (ghost / tot).float(),
             })
         return self, logs
 

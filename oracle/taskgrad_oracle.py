@@ -111,6 +111,29 @@ def elementwise_metrics(g: torch.Tensor, eps: float = 1e-3, tau: float = 1.0) ->
             "pairwise_interference_rate": rate, "avg_participation_ratio": pr.mean(), "per_task_participation_ratio": pr}
 
 
+def support_metrics(g: torch.Tensor, support_percentile: float = 0.8) -> dict:
+    """compute_support_metrics (mtsac.py:774-860)."""
+    T = g.shape[0]
+    thr = torch.quantile(g.abs(), support_percentile, dim=1, keepdim=True)          # :804-806 (linear interpolation)
+    sup = g.abs() >= thr
+    si, sj = sup[:, None, :], sup[None, :, :]
+    inter = (si & sj).sum(dim=-1).to(g.dtype)
+    union = (si | sj).sum(dim=-1).to(g.dtype)
+    jacc = inter / (union + 1e-8)
+    off = 1 - torch.eye(T, dtype=g.dtype)
+    n_pairs = T * (T - 1)
+    conflict = (g[:, None, :] * g[None, :, :]) < 0
+    genuine = ((si & sj) & conflict).sum(dim=-1).to(g.dtype)
+    ghost = (~(si & sj) & conflict).sum(dim=-1).to(g.dtype)
+    tot = genuine + ghost + 1e-8
+    return {"pairwise_jaccard": jacc, "avg_jaccard": (jacc * off).sum() / n_pairs,
+            "genuine_conflict_rate": genuine / tot, "ghost_conflict_rate": ghost / tot,
+            "avg_genuine_conflict_rate": ((genuine / tot) * off).sum() / n_pairs,
+            "avg_ghost_conflict_rate": ((ghost / tot) * off).sum() / n_pairs,
+            "ghost_to_genuine_ratio": ghost.sum() / (genuine.sum() + 1e-8),
+            "per_task_support_size": sup.sum(dim=-1).to(g.dtype), "avg_support_size": sup.sum(dim=-1).to(g.dtype).mean()}
+
+
 # --------------------------------------------------------------------------------------------
 # pcgrad (mtrl/optim/pcgrad.py:22-136) and the update that uses it (PCGradConfig, mtrl/config/optim.py:62-76)
 # --------------------------------------------------------------------------------------------

@@ -47,6 +47,11 @@ def test_per_task_gradients_and_cos_sim(cuda, T, W, per_task):
         avg_ref, cos_ref = TG.vmap_cos_sim(g_ref)
         cm_ref = TG.conflict_metrics(cos_ref, g_ref)
         _, logs = agent.compute_weights(tuple(b.cuda() for b in batch), eps_c=ec.cuda(), eps_a=ea.cuda())
+        import json
+        import os
+
+        ref_keys = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "compute_weights_keys.json")))
+        assert set(logs) == set(ref_keys), (set(ref_keys) - set(logs), set(logs) - set(ref_keys))   # mtsac.py:1085-1170
         cos = logs[f"{name}_pairwise_cos_sim"].double().cpu()
         assert (cos - cos_ref).abs().max() <= 2e-2, (name, float((cos - cos_ref).abs().max()))
         assert abs(float(logs[f"{name}_avg_cos_sim"]) - float(avg_ref)) <= 1e-2
@@ -66,6 +71,14 @@ def test_per_task_gradients_and_cos_sim(cuda, T, W, per_task):
         assert (rate - em["pairwise_interference_rate"]).abs().max() <= 2e-3 + 2e-2 * float(em["pairwise_interference_rate"].max())
         assert abs(float(logs[f"{name}_avg_interference_rate"]) - float(em["avg_interference_rate"])) <= \
             1e-3 + 2e-2 * float(em["avg_interference_rate"])
+        # support metrics (mtsac.py:774-860): the 0.8-quantile threshold by radix select, then pairwise counts
+        sm = TG.support_metrics(g_ref)
+        assert SU.rel(logs[f"{name}_per_task_support_size"], sm["per_task_support_size"]) <= 1e-3
+        assert (logs[f"{name}_pairwise_jaccard"].double().cpu() - sm["pairwise_jaccard"]).abs().max() <= 2e-2
+        assert (logs[f"{name}_pairwise_genuine_conflict_rate"].double().cpu() - sm["genuine_conflict_rate"]).abs().max() <= 2e-2
+        assert abs(float(logs[f"{name}_ghost_to_genuine_ratio"]) - float(sm["ghost_to_genuine_ratio"])) <= \
+            3e-2 * float(sm["ghost_to_genuine_ratio"]) + 1e-3
+        assert abs(float(logs[f"{name}_avg_jaccard"]) - float(sm["avg_jaccard"])) <= 1e-2
         off = 1 - torch.eye(T, dtype=torch.float64)
         assert abs(float(logs[f"{name}_gram_off_diag_mean"]) - float((gram_ref * off).sum() / (T * (T - 1)))) <= \
             2e-2 * float(gram_ref.abs().max())
