@@ -257,6 +257,19 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t cta_mask
       : "memory");
 }
 
+// ---- programmatic dependent launch (PDL) ----
+// Every kernel of the update path starts with MTRL_PDL_PROLOGUE(): `launch_dependents` lets the NEXT kernel in the
+// stream be launched and its CTAs become resident while this one still runs; `wait` blocks until every prerequisite
+// grid has completed and its memory is visible -- so nothing a kernel reads or writes moves ahead of its predecessor,
+// only launch latency and CTA start-up overlap.  (A kernel launched without the attribute sees both as no-ops.)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#define MTRL_PDL_PROLOGUE() \
+  do {                      \
+    pdl_launch_dependents(); \
+    pdl_wait();             \
+  } while (0)
+
 // ---- reductions ----
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -270,3 +283,34 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 #endif  // __CUDACC__
+
+#ifdef __CUDACC__
+#include <stdlib.h>
+
+#include <utility>
+// Host-side launch with the programmatic-stream-serialization attribute (MTRL_PDL=0 launches plainly).  The kernel
+// must begin with MTRL_PDL_PROLOGUE().
+inline bool mtrl_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MTRL_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t mtrl_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = mtrl_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#endif

@@ -135,6 +135,7 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
   const CUtensorMap* maps = params.maps;
   const int nprob = params.nprob;
   const int total_units = params.total_units;
+  pdl_launch_dependents();   // the next kernel may be launched (it waits for this grid's completion itself)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t epi_base = smem_base + kStages * C::kStageBytes;   // 1024-aligned staging boxes, then bias
@@ -180,6 +181,9 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
   if (kCtas == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation) touches no memory another kernel
+  // writes, so it may run while the previous kernel of the stream drains; from here on its results are needed.
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer (every CTA) =====================
@@ -751,8 +755,7 @@ extern "C" int mtrl_gemm_plan_run(mtrl_gemm_plan_t* plan, void* stream) {
   MTRL_REQUIRE(plan, "mtrl_gemm_plan_run: null plan");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (plan->ctas == 1) {
-    gemm_tf32_grouped_kernel<1><<<plan->grid, kThreads, Cfg<1>::kSmemBytes, st>>>(plan->params);
-    MTRL_CUDA_CHECK(cudaGetLastError());
+    MTRL_CUDA_CHECK(mtrl_launch(gemm_tf32_grouped_kernel<1>, dim3(plan->grid), dim3(kThreads), Cfg<1>::kSmemBytes, st, plan->params));
     return MTRL_OK;
   }
   cudaLaunchConfig_t cfg;
@@ -761,13 +764,15 @@ extern "C" int mtrl_gemm_plan_run(mtrl_gemm_plan_t* plan, void* stream) {
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = Cfg<2>::kSmemBytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = mtrl_pdl_enabled() ? 2 : 1;
   MTRL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tf32_grouped_kernel<2>, plan->params));
   return MTRL_OK;
 }

@@ -189,7 +189,7 @@ template <int HD>
 inline void launch_head_bwd_t(const HeadBwdArgs& a, int T_local, int E, cudaStream_t st) {
   dim3 grid((a.W + 127) / 128, T_local, E);
   constexpr int RG = HD <= 4 ? 16 : 8;   // wide heads keep (HD x 4) weights + sums per lane: fewer, fatter warps
-  head_bwd_kernel<HD, RG><<<grid, RG * 32, 0, st>>>(a);
+  mtrl_launch(head_bwd_kernel<HD, RG>, grid, dim3(RG * 32), 0, st, a);
 }
 
 

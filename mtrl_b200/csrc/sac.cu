@@ -365,10 +365,10 @@ int launch_actor_head(mtrl_sac* h, const float* H, const float* eps, float* Xdst
     const int rpb = c.max_rows <= 4096 ? 16 : 32;
     dim3 grid(c.max_rows / rpb), block(256);
 #define MTRL_AH_TILE(A_) \
-  case A_: actor_head_tile_kernel<A_><<<grid, block, wbytes, st>>>(a, rpb); break;
+  case A_: mtrl_launch(actor_head_tile_kernel<A_>, grid, block, wbytes, st, a, rpb); break;
     switch (c.action_dim) {
       MTRL_AH_TILE(1) MTRL_AH_TILE(2) MTRL_AH_TILE(3) MTRL_AH_TILE(4) MTRL_AH_TILE(5) MTRL_AH_TILE(6) MTRL_AH_TILE(7)
-      default: actor_head_tile_kernel<8><<<grid, block, wbytes, st>>>(a, rpb);
+      default: mtrl_launch(actor_head_tile_kernel<8>, grid, block, wbytes, st, a, rpb);
     }
 #undef MTRL_AH_TILE
     MTRL_CUDA_CHECK(cudaGetLastError());
@@ -405,7 +405,7 @@ int launch_head_bwd(mtrl_sac* h, const HeadBwdArgs& a, int hd, int E, cudaStream
 int launch_colsum(mtrl_sac* h, const ColsumJobs& jobs, int groups, cudaStream_t st) {
   const int W = h->cfg.width;
   dim3 g((W + 31) / 32, jobs.njobs);
-  colsum_final_kernel<<<g, 256, 0, st>>>(jobs, groups, W);
+  mtrl_launch(colsum_final_kernel, g, dim3(256), 0, st, jobs, groups, W);
   MTRL_CUDA_CHECK(cudaGetLastError());
   LAUNCHED(h);
   return MTRL_OK;
@@ -449,8 +449,8 @@ int run_trunk_backward(mtrl_sac* h, std::vector<mtrl_gemm_plan_t*>& plans, float
 
 int head_sumsq_to_slot(mtrl_sac* h, float* grads, const mtrl_net_layout_t& L, int acc_idx, cudaStream_t st) {
   const long long n = L.total - L.heads_base;
-  sumsq_kernel<<<64, 256, 0, st>>>(grads + L.heads_base, n, h->ws.acc + acc_idx);
-  write_slot_kernel<<<1, 1, 0, st>>>(grads + L.slots_off, h->ws.acc + acc_idx);
+  mtrl_launch(sumsq_kernel, dim3(64), dim3(256), 0, st, grads + L.heads_base, n, h->ws.acc + acc_idx);
+  mtrl_launch(write_slot_kernel, dim3(1), dim3(1), 0, st, grads + L.slots_off, h->ws.acc + acc_idx);
   MTRL_CUDA_CHECK(cudaGetLastError());
   h->launches += 2;
   return MTRL_OK;
@@ -573,7 +573,7 @@ extern "C" int mtrl_sac_refresh_shadows(mtrl_sac_t* h, void* stream) {
 namespace {
 
 int step_alpha_prep(mtrl_sac* h, cudaStream_t st) {
-  alpha_prep_kernel<<<1, 256, 0, st>>>(h->buf.log_alpha, h->cfg.num_local_tasks, h->cfg.use_task_weights, h->ws.alpha_val,
+  mtrl_launch(alpha_prep_kernel, dim3(1), dim3(256), 0, st, h->buf.log_alpha, h->cfg.num_local_tasks, h->cfg.use_task_weights, h->ws.alpha_val,
                                        h->ws.task_w);
   MTRL_CUDA_CHECK(cudaGetLastError());
   LAUNCHED(h);
@@ -603,8 +603,8 @@ int step_begin(mtrl_sac* h, const float* obs, const float* actions, const float*
   const int nchunks = (batch + 31) / 32;
   const size_t smem = (static_cast<size_t>(nchunks) * T + T + 1) * sizeof(int);
   MTRL_REQUIRE(smem <= 200 * 1024, "mtrl_sac_update: batch %d x %d tasks exceeds the packing kernel's shared memory", batch, T);
-  row_task_kernel<<<(batch + 7) / 8, 256, 0, st>>>(obs, batch, c.obs_dim, c.num_tasks, c.task_begin, T, w.row_slot, w.status);
-  pack_plan_kernel<<<1, 1024, smem, st>>>(batch, T, M, w.row_slot, w.slot_src, w.tile_task, w.seg_start, w.status);
+  mtrl_launch(row_task_kernel, dim3((batch + 7) / 8), dim3(256), 0, st, obs, batch, c.obs_dim, c.num_tasks, c.task_begin, T, w.row_slot, w.status);
+  mtrl_launch(pack_plan_kernel, dim3(1), dim3(1024), smem, st, batch, T, M, w.row_slot, w.slot_src, w.tile_task, w.seg_start, w.status);
   h->launches += 2;
   PackArgs a;
   a.obs = obs; a.actions = actions; a.next_obs = next_obs; a.dones = dones; a.rewards = rewards;
@@ -615,7 +615,7 @@ int step_begin(mtrl_sac* h, const float* obs, const float* actions, const float*
   a.noise_counter = h->buf.steps + 3;
   a.seed = c.noise_seed;
   a.obs_dim = c.obs_dim; a.act_dim = c.action_dim; a.Ka = h->lay.k_actor; a.Kc = h->lay.k_critic;
-  pack_rows_kernel<<<M, 128, 0, st>>>(a);
+  mtrl_launch(pack_rows_kernel, M, dim3(128), 0, st, a);
   LAUNCHED(h);
   MTRL_CUDA_CHECK(cudaGetLastError());
   for (int l = 0; l < D; ++l) MTRL_PROPAGATE(run_plan(h, h->fwd[l], st));
@@ -651,7 +651,7 @@ int step_critic_grads(mtrl_sac* h, cudaStream_t st) {
     // MT-SAC: L = mean over (E, B) of (q-y)^2 (mtsac.py:565); SAC: L = 0.5 * sum_e mean_b (q-y)^2 (sac.py:292)
     a.dq_scale = c.variant == MTRL_VARIANT_SAC ? 1.f / B : 2.f / (static_cast<float>(E) * B);
     a.clip = c.clip_q;
-    critic_loss_kernel<<<(M + 7) / 8, 256, 0, st>>>(a);
+    mtrl_launch(critic_loss_kernel, dim3((M + 7) / 8), dim3(256), 0, st, a);
     MTRL_CUDA_CHECK(cudaGetLastError());
     LAUNCHED(h);
   }
@@ -702,13 +702,13 @@ int step_critic_apply(mtrl_sac* h, cudaStream_t st) {
     t.lr = c.critic_lr; t.b1 = c.adam_b1; t.b2 = c.adam_b2; t.eps = c.adam_eps; t.max_norm = c.critic_max_grad_norm;
     t.tau = c.tau;
     MTRL_PROPAGATE(launch_trunk_step(h, t, h->off_critic_grads, h->off_critic_params, h->d_segs_critic, h->nsegs_critic, st));
-    finalize_critic_kernel<<<1, 1, 0, st>>>(w.acc, h->buf.critic_grads + LC.slots_off + 1, h->buf.steps, h->buf.logs, 1.f / EB,
+    mtrl_launch(finalize_critic_kernel, dim3(1), dim3(1), 0, st, w.acc, h->buf.critic_grads + LC.slots_off + 1, h->buf.steps, h->buf.logs, 1.f / EB,
                                             loss_scale, 0);
     LAUNCHED(h);
     MTRL_CUDA_CHECK(cudaGetLastError());
     return MTRL_OK;
   }
-  sumsq_kernel<<<h->sms * 2, 256, 0, st>>>(h->buf.critic_grads, LC.trunk_total, w.acc + ACC_CRITIC_G2);
+  mtrl_launch(sumsq_kernel, dim3(h->sms * 2), dim3(256), 0, st, h->buf.critic_grads, LC.trunk_total, w.acc + ACC_CRITIC_G2);
   LAUNCHED(h);
   AdamArgs a;
   a.p = h->buf.critic_params; a.m = h->buf.critic_m; a.v = h->buf.critic_v; a.shadow = h->buf.critic_shadow;
@@ -719,9 +719,9 @@ int step_critic_apply(mtrl_sac* h, cudaStream_t st) {
   a.p2_trunk = w.acc + ACC_CRITIC_P2_TRUNK; a.p2_head = w.acc + ACC_CRITIC_P2_HEAD; a.p2_old = w.acc + ACC_CRITIC_P2_OLD;
   a.lr = c.critic_lr; a.b1 = c.adam_b1; a.b2 = c.adam_b2; a.eps = c.adam_eps; a.max_norm = c.critic_max_grad_norm;
   a.tau = c.tau;
-  adam_kernel<<<h->sms * 4, 256, 0, st>>>(a);
+  mtrl_launch(adam_kernel, dim3(h->sms * 4), dim3(256), 0, st, a);
   LAUNCHED(h);
-  finalize_critic_kernel<<<1, 1, 0, st>>>(w.acc, h->buf.critic_grads + LC.slots_off, h->buf.steps, h->buf.logs, 1.f / EB,
+  mtrl_launch(finalize_critic_kernel, dim3(1), dim3(1), 0, st, w.acc, h->buf.critic_grads + LC.slots_off, h->buf.steps, h->buf.logs, 1.f / EB,
                                           loss_scale, c.variant == MTRL_VARIANT_SAC);
   LAUNCHED(h);
   MTRL_CUDA_CHECK(cudaGetLastError());
@@ -767,7 +767,7 @@ int step_actor_grads(mtrl_sac* h, cudaStream_t st) {
     }
     a.tile_task = w.tile_task; a.slot_src = w.slot_src; a.logp = w.logp; a.alpha_val = w.alpha_val; a.task_w = w.task_w;
     a.dq = w.dq; a.acc = w.acc; a.M = M; a.W = W; a.E = E; a.inv_b = inv_b;
-    actor_loss_kernel<<<(M + 7) / 8, 256, 0, st>>>(a);
+    mtrl_launch(actor_loss_kernel, dim3((M + 7) / 8), dim3(256), 0, st, a);
     MTRL_CUDA_CHECK(cudaGetLastError());
     LAUNCHED(h);
   }
@@ -789,7 +789,7 @@ int step_actor_grads(mtrl_sac* h, cudaStream_t st) {
     a.dXin = w.dXin; a.act = w.act; a.logstd = w.logstd; a.eps = w.eps_a; a.alpha_val = w.alpha_val; a.task_w = w.task_w;
     a.inrange = w.inrange; a.tile_task = w.tile_task; a.slot_src = w.slot_src; a.dout = w.dout;
     a.M = M; a.E = E; a.A = c.action_dim; a.inv_b = inv_b;
-    actor_dout_kernel<<<(M + 127) / 128, 128, 0, st>>>(a);
+    mtrl_launch(actor_dout_kernel, dim3((M + 127) / 128), dim3(128), 0, st, a);
     MTRL_CUDA_CHECK(cudaGetLastError());
     LAUNCHED(h);
   }
@@ -825,13 +825,13 @@ int step_actor_apply(mtrl_sac* h, cudaStream_t st) {
     t.g2_trunk_out = w.acc + ACC_ACTOR_G2; t.p2_trunk = w.acc + ACC_ACTOR_P2_TRUNK; t.p2_head = w.acc + ACC_ACTOR_P2_HEAD;
     t.lr = c.actor_lr; t.b1 = c.adam_b1; t.b2 = c.adam_b2; t.eps = c.adam_eps; t.max_norm = c.actor_max_grad_norm;
     MTRL_PROPAGATE(launch_trunk_step(h, t, h->off_actor_grads, h->off_actor_params, h->d_segs_actor, h->nsegs_actor, st));
-    finalize_actor_kernel<<<1, 1, 0, st>>>(w.acc, h->buf.actor_grads + LA.slots_off + 1, h->buf.steps, h->buf.logs,
+    mtrl_launch(finalize_actor_kernel, dim3(1), dim3(1), 0, st, w.acc, h->buf.actor_grads + LA.slots_off + 1, h->buf.steps, h->buf.logs,
                                            1.f / static_cast<float>(h->global_batch), 0);
     LAUNCHED(h);
     MTRL_CUDA_CHECK(cudaGetLastError());
     return MTRL_OK;
   }
-  sumsq_kernel<<<h->sms * 2, 256, 0, st>>>(h->buf.actor_grads, LA.trunk_total, w.acc + ACC_ACTOR_G2);
+  mtrl_launch(sumsq_kernel, dim3(h->sms * 2), dim3(256), 0, st, h->buf.actor_grads, LA.trunk_total, w.acc + ACC_ACTOR_G2);
   LAUNCHED(h);
   AdamArgs a;
   a.p = h->buf.actor_params; a.m = h->buf.actor_m; a.v = h->buf.actor_v; a.shadow = h->buf.actor_shadow;
@@ -841,9 +841,9 @@ int step_actor_apply(mtrl_sac* h, cudaStream_t st) {
   a.step = h->buf.steps + 0;
   a.p2_trunk = w.acc + ACC_ACTOR_P2_TRUNK; a.p2_head = w.acc + ACC_ACTOR_P2_HEAD; a.p2_old = w.acc + ACC_ACTOR_P2_OLD;
   a.lr = c.actor_lr; a.b1 = c.adam_b1; a.b2 = c.adam_b2; a.eps = c.adam_eps; a.max_norm = c.actor_max_grad_norm; a.tau = 0.f;
-  adam_kernel<<<h->sms * 4, 256, 0, st>>>(a);
+  mtrl_launch(adam_kernel, dim3(h->sms * 4), dim3(256), 0, st, a);
   LAUNCHED(h);
-  finalize_actor_kernel<<<1, 1, 0, st>>>(w.acc, h->buf.actor_grads + LA.slots_off, h->buf.steps, h->buf.logs,
+  mtrl_launch(finalize_actor_kernel, dim3(1), dim3(1), 0, st, w.acc, h->buf.actor_grads + LA.slots_off, h->buf.steps, h->buf.logs,
                                          1.f / static_cast<float>(h->global_batch), c.variant == MTRL_VARIANT_SAC);
   LAUNCHED(h);
   MTRL_CUDA_CHECK(cudaGetLastError());
@@ -859,7 +859,7 @@ int step_alpha(mtrl_sac* h, cudaStream_t st) {
   al.logp = w.logp; al.seg_start = w.seg_start; al.slot_src = w.slot_src; al.steps = h->buf.steps; al.logs = h->buf.logs;
   al.T_local = c.num_local_tasks; al.target_entropy = c.target_entropy; al.inv_b = 1.f / static_cast<float>(h->global_batch);
   al.lr = c.alpha_lr; al.b1 = c.adam_b1; al.b2 = c.adam_b2; al.eps = c.adam_eps; al.max_norm = c.alpha_max_grad_norm;
-  alpha_step_kernel<<<1, 1024, c.num_local_tasks * sizeof(float), st>>>(al);
+  mtrl_launch(alpha_step_kernel, dim3(1), dim3(1024), c.num_local_tasks * sizeof(float), st, al);
   LAUNCHED(h);
   MTRL_CUDA_CHECK(cudaGetLastError());
   return MTRL_OK;

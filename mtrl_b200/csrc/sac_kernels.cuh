@@ -62,6 +62,7 @@ __device__ __forceinline__ double block_sum(double v, double* smem) {
 // Task of every row = first arg-max of its trailing one-hot (jnp.argmax, multi_head.py:65).  One warp per row.
 static __global__ void row_task_kernel(const float* __restrict__ obs, int B, int obs_dim, int T, int task_begin, int T_local,
                                 int* __restrict__ row_slot, int* __restrict__ status) {
+  MTRL_PDL_PROLOGUE();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= B) return;
@@ -87,6 +88,7 @@ static __global__ void row_task_kernel(const float* __restrict__ obs, int B, int
 static __global__ void pack_plan_kernel(int B, int T_local, int max_rows, int* __restrict__ row_slot,
                                  int* __restrict__ slot_src, int* __restrict__ tile_task, int* __restrict__ seg_start,
                                  int* __restrict__ status) {
+  MTRL_PDL_PROLOGUE();
   extern __shared__ int sm[];
   const int nchunks = (B + 31) / 32;
   int* counts = sm;                       // [nchunks][T_local]
@@ -156,6 +158,7 @@ struct PackArgs {
 
 // One block per packed row.  Inputs are rounded to tf32 here (they are GEMM A operands).
 static __global__ void pack_rows_kernel(const PackArgs a) {
+  MTRL_PDL_PROLOGUE();
   const int slot = blockIdx.x;
   const int src = a.slot_src[slot];
   const int A = a.act_dim, od = a.obs_dim;
@@ -261,6 +264,7 @@ static __global__ void act_pack_kernel(const float* __restrict__ obs, int n, int
 // (extract_task_weights, mtsac.py:103-113) or 1.
 static __global__ void alpha_prep_kernel(const float* __restrict__ log_alpha, int T_local, int use_w, float* __restrict__ alpha_val,
                                   float* __restrict__ task_w) {
+  MTRL_PDL_PROLOGUE();
   if (blockIdx.x != 0) return;
   __shared__ float red[32];
   float mx = -INFINITY;
@@ -370,6 +374,7 @@ static __global__ void actor_head_kernel(const ActorHeadArgs p) {
 // on two rows at a time (the weight reads are shared) with all of a row's float4 activation loads in flight.
 template <int A>
 static __global__ void __launch_bounds__(256) actor_head_tile_kernel(const ActorHeadArgs p, int rows_per_block) {
+  MTRL_PDL_PROLOGUE();
   extern __shared__ __align__(16) float sw[];  // [2A][W + 4]
   const int ldw = p.W + 4;
   const int row0 = blockIdx.x * rows_per_block;
@@ -569,6 +574,7 @@ struct CriticLossArgs {
 // y = r + (1-d) gamma (min_e Qbar_e - alpha logp')   (mtsac.py:547-553)
 // L = mean_{e,b} w (Q_e - y)^2                        (mtsac.py:562-565);  dq_e = dL/dQ_e
 static __global__ void critic_loss_kernel(const CriticLossArgs p) {
+  MTRL_PDL_PROLOGUE();
   __shared__ double red[32];
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -637,6 +643,7 @@ struct ActorLossArgs {
 
 // L = mean_b w (alpha logp - min_e Q_e(s, a))   (mtsac.py:659-666); min routes the gradient to the arg-min.
 static __global__ void actor_loss_kernel(const ActorLossArgs p) {
+  MTRL_PDL_PROLOGUE();
   __shared__ double red[32];
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -700,6 +707,7 @@ struct ActorDoutArgs {
 };
 
 static __global__ void actor_dout_kernel(const ActorDoutArgs p) {
+  MTRL_PDL_PROLOGUE();
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= p.M) return;
   const int A = p.A;
@@ -744,6 +752,7 @@ struct HeadBwdArgs {
 
 template <int HD, int RG>
 static __global__ void __launch_bounds__(RG * 32, ((RG == 8 && HD <= 8) || HD <= 2) ? 2 : 1) head_bwd_kernel(const HeadBwdArgs p) {
+  MTRL_PDL_PROLOGUE();
   constexpr int RPW = kTileRows / RG;   // rows per warp per tile
   static_assert(RPW % 8 == 0, "rows per warp must be a multiple of the 8-row load batch");
   __shared__ float sd[kTileRows * HD];
@@ -843,6 +852,7 @@ struct ColsumJobs {
 
 // block = 32 columns x 8 group slices; slices are combined in a fixed order through shared memory.
 static __global__ void colsum_final_kernel(const ColsumJobs jobs, int groups, int W) {
+  MTRL_PDL_PROLOGUE();
   __shared__ float red[8][33];
   const int job = blockIdx.y;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -1312,6 +1322,7 @@ static __global__ void row_stats_kernel(const float* __restrict__ rows, long lon
 // target update (mtsac.py:607-613) and the tf32 operand copies the GEMMs read.
 // ---------------------------------------------------------------------------------------------
 static __global__ void sumsq_kernel(const float* __restrict__ x, long long n, double* __restrict__ acc) {
+  MTRL_PDL_PROLOGUE();
   __shared__ double red[32];
   double s = 0.0;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -1328,7 +1339,10 @@ static __global__ void sumsq_kernel(const float* __restrict__ x, long long n, do
 }
 
 // grads[slot] = local head-gradient squared norm, so one all-reduce of [trunk | slots] carries it.
-static __global__ void write_slot_kernel(float* __restrict__ slot, const double* __restrict__ acc) { *slot = static_cast<float>(*acc); }
+static __global__ void write_slot_kernel(float* __restrict__ slot, const double* __restrict__ acc) {
+  MTRL_PDL_PROLOGUE();
+  *slot = static_cast<float>(*acc);
+}
 
 struct AdamArgs {
   float *p, *m, *v, *shadow;
@@ -1347,6 +1361,7 @@ struct AdamArgs {
 };
 
 static __global__ void adam_kernel(const AdamArgs a) {
+  MTRL_PDL_PROLOGUE();
   __shared__ double red[32];
   const double g2 = *a.g2_trunk + static_cast<double>(*a.g2_heads);
   const float gn = static_cast<float>(sqrt(g2));
@@ -1412,6 +1427,7 @@ static __global__ void shadow_kernel(const float* __restrict__ p, float* __restr
 // Single thread: turn accumulators into the reference's log scalars and advance the Adam count.
 static __global__ void finalize_critic_kernel(const double* acc, const float* g2_heads, int* steps, float* logs, float inv_eb,
                                        float loss_scale, int log_old_norm) {
+  MTRL_PDL_PROLOGUE();
   logs[MTRL_LOG_QF_VALUES] = static_cast<float>(acc[ACC_QSUM] * inv_eb);
   logs[MTRL_LOG_QF_LOSS] = static_cast<float>(acc[ACC_QLOSS] * loss_scale);
   logs[MTRL_LOG_CRITIC_GRAD_MAGNITUDE] = static_cast<float>(sqrt(acc[ACC_CRITIC_G2] + static_cast<double>(*g2_heads)));
@@ -1424,6 +1440,7 @@ static __global__ void finalize_critic_kernel(const double* acc, const float* g2
 }
 static __global__ void finalize_actor_kernel(const double* acc, const float* g2_heads, int* steps, float* logs, float inv_b,
                                       int log_old_norm) {
+  MTRL_PDL_PROLOGUE();
   logs[MTRL_LOG_ACTOR_LOSS] = static_cast<float>(acc[ACC_ACTOR_LOSS] * inv_b);
   logs[MTRL_LOG_ACTOR_GRAD_MAGNITUDE] = static_cast<float>(sqrt(acc[ACC_ACTOR_G2] + static_cast<double>(*g2_heads)));
   logs[MTRL_LOG_ACTOR_PARAMS_NORM] = static_cast<float>(
@@ -1449,6 +1466,7 @@ struct AlphaArgs {
 };
 
 static __global__ void alpha_step_kernel(const AlphaArgs a) {
+  MTRL_PDL_PROLOGUE();
   extern __shared__ float sg[];  // [T_local] gradients
   __shared__ float red[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;

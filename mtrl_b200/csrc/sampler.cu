@@ -109,6 +109,7 @@ __device__ void draw_indices_sequential(PcgState* __restrict__ st, long long* __
 // sequentially from the untouched state.  Same stream and same final state bit for bit, ~2 us instead of ~12.
 __global__ void draw_indices_kernel(PcgState* __restrict__ st, long long* __restrict__ out, int n,
                                     unsigned int high) {
+  MTRL_PDL_PROLOGUE();
   if (blockIdx.x != 0 || threadIdx.x >= 32) return;
   const int lane = threadIdx.x;
   if (high <= 1u) {  // rng == 0: numpy fills with `low` and consumes nothing
@@ -200,6 +201,7 @@ __device__ __forceinline__ void copy_vec(float* __restrict__ d, const float* __r
 
 // grid = (chunks, samples, 5 arrays).  Output row (i*T + t) = storage[idx[i], t, :]  (buffers.py:540-548).
 __global__ void gather_slabs_kernel(const GatherArgs a, const long long* __restrict__ idx, int chunk_elems) {
+  MTRL_PDL_PROLOGUE();
   const int arr = blockIdx.z;
   const int i = blockIdx.y;
   const int slab = a.num_tasks * a.dim[arr];
@@ -374,16 +376,14 @@ extern "C" int mtrl_sampler_sample(mtrl_sampler_t* s, int fill, int n_per_task, 
   float* outs[5] = {obs_out, actions_out, next_obs_out, dones_out, rewards_out};
   GatherArgs g;
   MTRL_PROPAGATE(fill_gather_args(s, &g, outs, norm_mode, shift, den));
-  draw_indices_kernel<<<1, 32, 0, st>>>(s->state, s->idx, n_per_task, static_cast<unsigned int>(high));
-  MTRL_CUDA_CHECK(cudaGetLastError());
+  MTRL_CUDA_CHECK(mtrl_launch(draw_indices_kernel, dim3(1), dim3(32), 0, st, s->state, s->idx, n_per_task, static_cast<unsigned int>(high)));
   if (idx_out)
     MTRL_CUDA_CHECK(cudaMemcpyAsync(idx_out, s->idx, sizeof(long long) * n_per_task, cudaMemcpyDeviceToDevice, st));
   const int threads = 256;
   const int chunk = threads * 4 * 4;  // 4 float4 per thread per block
   const int max_slab = s->num_tasks * s->obs_dim;
   dim3 grid((max_slab + chunk - 1) / chunk, n_per_task, 5);
-  gather_slabs_kernel<<<grid, threads, 0, st>>>(g, s->idx, chunk);
-  MTRL_CUDA_CHECK(cudaGetLastError());
+  MTRL_CUDA_CHECK(mtrl_launch(gather_slabs_kernel, grid, dim3(threads), 0, st, g, s->idx, chunk));
   return MTRL_OK;
 }
 
