@@ -288,15 +288,26 @@ __device__ __forceinline__ double warp_sum(double v) {
 #include <stdlib.h>
 
 #include <utility>
-// Host-side launch with the programmatic-stream-serialization attribute (MTRL_PDL=0 launches plainly).  The kernel
-// must begin with MTRL_PDL_PROLOGUE().
-inline bool mtrl_pdl_enabled() {
-  static int v = -1;
-  if (v < 0) {
+// Host-side launch with the programmatic-stream-serialization attribute.  The kernel must begin with
+// MTRL_PDL_PROLOGUE().  Whether the attribute is set: MTRL_PDL=0 / 1 forces it off / on; otherwise the update entry points
+// decide per call (mtrl_pdl_auto): measured on one box, PDL gains 6 % where an update is ~65 short kernels (width <= 1024)
+// and LOSES 1.5-2 % at width 2048, where early-resident dependents only get in the way of long kernels.
+inline int& mtrl_pdl_thread_state() {
+  static thread_local int on = 0;
+  return on;
+}
+inline int mtrl_pdl_env() {
+  static int v = -2;
+  if (v == -2) {
     const char* e = getenv("MTRL_PDL");
-    v = (e && e[0] == '0') ? 0 : 1;
+    v = !e ? -1 : (e[0] == '0' ? 0 : 1);
   }
-  return v != 0;
+  return v;
+}
+inline void mtrl_pdl_auto(bool launch_bound) { mtrl_pdl_thread_state() = launch_bound ? 1 : 0; }
+inline bool mtrl_pdl_enabled() {
+  const int e = mtrl_pdl_env();
+  return e >= 0 ? e != 0 : mtrl_pdl_thread_state() != 0;
 }
 template <typename... KArgs, typename... Args>
 inline cudaError_t mtrl_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {

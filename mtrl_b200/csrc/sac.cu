@@ -591,6 +591,7 @@ int step_begin(mtrl_sac* h, const float* obs, const float* actions, const float*
   MTRL_REQUIRE((eps_c == nullptr) == (eps_a == nullptr), "mtrl_sac_update: pass both eps_c and eps_a or neither");
   Workspace& w = h->ws;
   const int M = c.max_rows, D = c.depth, T = c.num_local_tasks;
+  mtrl_pdl_auto(c.width <= 1024);   // programmatic dependent launch only where the update is launch-latency bound
   h->launches = 0;
   h->batch = batch;
   h->global_batch = global_batch;
