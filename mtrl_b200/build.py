@@ -74,7 +74,6 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     if failed:
         raise RuntimeError("nvcc failed; see mtrl_b200/build/nvcc.log")
     link = [nvcc, "-shared", "-o", str(LIB), *map(str, objs), "-lcudart"]
-    nccl = os.environ.get("MTRL_NCCL_LIB")
     subprocess.run(link, check=True)
     STAMP.write_text(digest)
     return LIB

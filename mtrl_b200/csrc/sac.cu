@@ -339,6 +339,20 @@ int run_plan(mtrl_sac* h, mtrl_gemm_plan_t* plan, cudaStream_t st) {
   return MTRL_OK;
 }
 
+// One warp per row, weights streamed from L2 (any width; also the action-sampling path).
+void launch_actor_head_rows(const ActorHeadArgs& a, int action_dim, dim3 grid, dim3 block, cudaStream_t st) {
+  switch (action_dim) {
+    case 1: actor_head_kernel<1><<<grid, block, 0, st>>>(a); break;
+    case 2: actor_head_kernel<2><<<grid, block, 0, st>>>(a); break;
+    case 3: actor_head_kernel<3><<<grid, block, 0, st>>>(a); break;
+    case 4: actor_head_kernel<4><<<grid, block, 0, st>>>(a); break;
+    case 5: actor_head_kernel<5><<<grid, block, 0, st>>>(a); break;
+    case 6: actor_head_kernel<6><<<grid, block, 0, st>>>(a); break;
+    case 7: actor_head_kernel<7><<<grid, block, 0, st>>>(a); break;
+    default: actor_head_kernel<8><<<grid, block, 0, st>>>(a); break;
+  }
+}
+
 int launch_actor_head(mtrl_sac* h, const float* H, const float* eps, float* Xdst, float* logp, bool save, cudaStream_t st) {
   const mtrl_sac_config_t& c = h->cfg;
   ActorHeadArgs a;
@@ -377,16 +391,7 @@ int launch_actor_head(mtrl_sac* h, const float* H, const float* eps, float* Xdst
   }
   const int wpb = 8;
   dim3 grid((c.max_rows + wpb - 1) / wpb), block(wpb * 32);
-  switch (c.action_dim) {
-    case 1: actor_head_kernel<1><<<grid, block, 0, st>>>(a); break;
-    case 2: actor_head_kernel<2><<<grid, block, 0, st>>>(a); break;
-    case 3: actor_head_kernel<3><<<grid, block, 0, st>>>(a); break;
-    case 4: actor_head_kernel<4><<<grid, block, 0, st>>>(a); break;
-    case 5: actor_head_kernel<5><<<grid, block, 0, st>>>(a); break;
-    case 6: actor_head_kernel<6><<<grid, block, 0, st>>>(a); break;
-    case 7: actor_head_kernel<7><<<grid, block, 0, st>>>(a); break;
-    default: actor_head_kernel<8><<<grid, block, 0, st>>>(a); break;
-  }
+  launch_actor_head_rows(a, c.action_dim, grid, block, st);
   MTRL_CUDA_CHECK(cudaGetLastError());
   LAUNCHED(h);
   return MTRL_OK;
@@ -996,16 +1001,7 @@ extern "C" int mtrl_sac_act(mtrl_sac_t* h, const float* obs, int n, const float*
   a.ls_max = c.log_std_max;
   const int wpb = 8;
   dim3 grid((n + wpb - 1) / wpb), block(wpb * 32);
-  switch (c.action_dim) {
-    case 1: actor_head_kernel<1><<<grid, block, 0, st>>>(a); break;
-    case 2: actor_head_kernel<2><<<grid, block, 0, st>>>(a); break;
-    case 3: actor_head_kernel<3><<<grid, block, 0, st>>>(a); break;
-    case 4: actor_head_kernel<4><<<grid, block, 0, st>>>(a); break;
-    case 5: actor_head_kernel<5><<<grid, block, 0, st>>>(a); break;
-    case 6: actor_head_kernel<6><<<grid, block, 0, st>>>(a); break;
-    case 7: actor_head_kernel<7><<<grid, block, 0, st>>>(a); break;
-    default: actor_head_kernel<8><<<grid, block, 0, st>>>(a); break;
-  }
+  launch_actor_head_rows(a, c.action_dim, grid, block, st);
   MTRL_CUDA_CHECK(cudaGetLastError());
   return MTRL_OK;
 }
