@@ -68,3 +68,42 @@ def test_get_without_values_asserts(cuda):
         buf.get(True, np.zeros(3, np.float32), np.zeros(3, np.float32))
     out = buf.get(False)
     assert out.returns is None and out.advantages is None and out.actions.shape == (3, 2, 2)
+
+
+def test_rollout_feeds_mtppo_update(cuda):
+    """On-policy side end to end: device rollout buffer -> GAE kernel -> `Rollout` of (task, timestep,
+    dim) views -> MTPPO.update, equal to the update on the same arrays flattened task-major by hand."""
+    from mtrl_b200.config.networks import ContinuousActionPolicyConfig, ValueFunctionConfig
+    from mtrl_b200.config.nn import MultiHeadConfig
+    from mtrl_b200.config.optim import OptimizerConfig
+    from mtrl_b200.rl.algorithms import MTPPO, MTPPOConfig
+    from mtrl_b200.rl.buffers import MultiTaskRolloutBuffer
+    from mtrl_b200.types import Rollout
+
+    T, S, W, od, ad = 3, 128, 64, 16 + 3, 4
+    rng = np.random.default_rng(5)
+    buf = MultiTaskRolloutBuffer(S, T, SU._Space((od,)), SU._Space((ad,)), seed=0)
+    for _ in range(S):
+        obs = rng.standard_normal((T, od)).astype(np.float32)
+        obs[:, -T:] = np.eye(T, dtype=np.float32)
+        buf.add(obs, rng.uniform(-1, 1, (T, ad)).astype(np.float32), rng.uniform(0, 1, T).astype(np.float32),
+                (rng.uniform(size=T) < 0.02).astype(np.float32), value=rng.standard_normal((T, 1)).astype(np.float32),
+                log_prob=(rng.standard_normal(T) - 4).astype(np.float32))
+    roll = buf.get(True, rng.standard_normal(T).astype(np.float32), np.zeros(T, np.float32))
+    assert roll.advantages.shape == (T, S, 1) and not roll.advantages.is_contiguous()
+
+    def agent():
+        opt = OptimizerConfig(max_grad_norm=1.0)
+        net = MultiHeadConfig(width=W, depth=2, num_tasks=T, optimizer=opt)
+        cfg = MTPPOConfig(num_tasks=T, policy_config=ContinuousActionPolicyConfig(network_config=net, squash_tanh=False),
+                          vf_config=ValueFunctionConfig(network_config=net))
+        return MTPPO.initialize(cfg, SU.EnvSpec(od, ad), seed=3, rollout_steps=S)
+
+    eps = torch.randn(T * S, ad, generator=torch.Generator().manual_seed(1))
+    a, b = agent(), agent()
+    _, logs_a = a.update(roll, eps=eps)
+    flat = Rollout(*(None if x is None else x.reshape(T * S, -1).contiguous() for x in roll))
+    _, logs_b = b.update(flat, eps=eps)
+    for k in logs_a:
+        assert torch.isfinite(logs_a[k]) and float(logs_a[k]) == float(logs_b[k]), k
+    assert torch.equal(a._flat["policy_params"], b._flat["policy_params"])
