@@ -1140,7 +1140,19 @@ template <int MODE>
 static __global__ void pairwise_kernel(const float* __restrict__ rows, long long ld, int T, long long P, float* __restrict__ out, int ldo,
                                        float s, float eps, float tau) {
   __shared__ float tile[64][65];
-  const int ta = (threadIdx.x / 16) * 4, tb = (threadIdx.x % 16) * 4;   // 16 x 16 threads cover 64 x 64 entries
+  // 4 x 4 register tiles.  MODE 1: 16 x 16 threads cover the 64 x 64 entries.  MODE 0 (symmetric): only the tiles on or
+  // above the diagonal are computed -- enumerated densely over the first threads so that whole warps go idle -- and
+  // mirrored at the end.
+  int ta = (threadIdx.x / 16) * 4, tb = (threadIdx.x % 16) * 4;
+  bool active = true;
+  if (MODE == 0) {
+    const int nt = (T + 3) / 4;
+    int i = threadIdx.x, r = 0;
+    while (r < nt && i >= nt - r) { i -= nt - r; ++r; }
+    active = r < nt;
+    ta = 4 * r;
+    tb = 4 * (r + i);
+  }
   float acc[4][4];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
@@ -1156,6 +1168,7 @@ static __global__ void pairwise_kernel(const float* __restrict__ rows, long long
       tile[r][cc] = (r < T && c0 + cc < p1) ? rows[r * ld + c0 + cc] : (MODE == 0 ? 0.f : __int_as_float(0x7fc00000));
     }
     __syncthreads();
+    if (!active) continue;
 #pragma unroll 8
     for (int cc = 0; cc < 64; ++cc) {
       float va[4], vb[4];
@@ -1182,7 +1195,10 @@ static __global__ void pairwise_kernel(const float* __restrict__ rows, long long
   for (int a = 0; a < 4; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b)
-      if (ta + a < T && tb + b < T) atomicAdd(&out[(ta + a) * ldo + tb + b], acc[a][b]);
+      if (active && ta + a < T && tb + b < T) {
+        atomicAdd(&out[(ta + a) * ldo + tb + b], acc[a][b]);
+        if (MODE == 0 && ta < tb) atomicAdd(&out[(tb + b) * ldo + ta + a], acc[a][b]);
+      }
 }
 
 // compute_support_metrics (mtsac.py:774-860): with per-row support thresholds thr[t] (the 0.8-quantile of |x|),
