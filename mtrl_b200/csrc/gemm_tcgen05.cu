@@ -38,7 +38,7 @@ constexpr int kThreads = 64 + 32 * kEpilogueWarps;
 // kCtas == 1: one CTA owns a 128 x block_n tile (A 16 KB + B 32 KB per stage, 4 stages).
 // kCtas == 2: a CTA pair (cta_group::2) owns a 256 x block_n tile; each CTA stages its own 128 rows of A and
 //             HALF of B's N, so a k-block costs 32 KB of L2->smem traffic per SM instead of 48 KB (the 1-CTA
-//             kernel is bound by that traffic, profiles/r01_gemm_1cta.txt) and 6 stages fit.
+//             kernel is bound by that traffic, profiles/r01_gemm_1cta_ncu_full.txt).
 // Epilogue staging per epilogue warp: two 32 x 32 fp32 boxes (SWIZZLE_128B, 4 KB each) for TMA stores, 512 B of bias.
 constexpr int kEpiBoxBytes = 32 * 32 * 4;
 constexpr int kEpiStageBytes = kEpilogueWarps * 2 * kEpiBoxBytes;   // 64 KB
