@@ -59,6 +59,9 @@ typedef struct mtrl_gemm_problem {
   long long ldbits;
   float* colsum_partial; /* optional, MTRL_EPI_RELU_MASK only: device [ceil(M/32)][N] receiving the column sums of
                             every 32-row group of D (bias gradients are their sum over groups); NULL to skip  */
+  int schedule_first;    /* != 0: this problem's tiles are dealt to the workers before all others (outputs that travel
+                            over NVLink: their stores then overlap the remaining tiles instead of the launch's tail)  */
+  int reserved;
 } mtrl_gemm_problem_t;
 
 typedef struct mtrl_gemm_plan mtrl_gemm_plan_t;

@@ -700,7 +700,7 @@ extern "C" int mtrl_gemm_plan_create(mtrl_gemm_plan_t** out, const mtrl_gemm_pro
     // per-k-block TMA / issue latency, not by the MMA) + a constant for prologue and epilogue drain.  Units of equal
     // cost keep their index order, so a launch of uniform units degenerates to the round-robin it replaces
     // (neighbouring workers share operand tiles in L2).
-    struct U { int unit; long long cost; };
+    struct U { int unit; long long cost; int first; };
     std::vector<U> us;
     us.reserve(units);
     for (int i = 0; i < n; ++i) {
@@ -710,11 +710,13 @@ extern "C" int mtrl_gemm_plan_create(mtrl_gemm_plan_t** out, const mtrl_gemm_pro
         const int kb0 = split * d.kb_per_split;
         const int kb1 = kb0 + d.kb_per_split < d.kb_total ? kb0 + d.kb_per_split : d.kb_total;
         const long long per_kb = d.block_n > 160 ? d.block_n : 160;
-        us.push_back({d.unit_begin + u, static_cast<long long>(kb1 - kb0) * per_kb + 4 * 256});
+        us.push_back({d.unit_begin + u, static_cast<long long>(kb1 - kb0) * per_kb + 4 * 256, problems[i].schedule_first ? 1 : 0});
       }
     }
     const bool lpt = !(getenv("MTRL_GEMM_NO_LPT") && getenv("MTRL_GEMM_NO_LPT")[0] == '1');
-    if (lpt) std::stable_sort(us.begin(), us.end(), [](const U& a, const U& b) { return a.cost > b.cost; });
+    // schedule_first problems (outputs reduce-added into a peer GPU) lead every worker's list; cost order within a class
+    if (lpt)
+      std::stable_sort(us.begin(), us.end(), [](const U& a, const U& b) { return a.first != b.first ? a.first > b.first : a.cost > b.cost; });
     std::vector<std::vector<int>> lists(nworkers);
     std::vector<long long> load(nworkers, 0);
     for (size_t i = 0; i < us.size(); ++i) {
