@@ -104,6 +104,8 @@ def test_rollout_feeds_mtppo_update(cuda):
     _, logs_a = a.update(roll, eps=eps)
     flat = Rollout(*(None if x is None else x.reshape(T * S, -1).contiguous() for x in roll))
     _, logs_b = b.update(flat, eps=eps)
+    # split-K weight gradients accumulate with atomics, so two runs agree to rounding, not bit for bit
     for k in logs_a:
-        assert torch.isfinite(logs_a[k]) and float(logs_a[k]) == float(logs_b[k]), k
-    assert torch.equal(a._flat["policy_params"], b._flat["policy_params"])
+        assert torch.isfinite(logs_a[k]) and abs(float(logs_a[k]) - float(logs_b[k])) <= 1e-5 * abs(float(logs_b[k])) + 1e-7, k
+    assert torch.allclose(a._flat["policy_params"], b._flat["policy_params"], rtol=1e-4, atol=1e-6)
+    assert torch.allclose(a._flat["vf_params"], b._flat["vf_params"], rtol=1e-4, atol=1e-6)
