@@ -105,3 +105,96 @@ def test_combine_rank_logs():
     assert out["losses/qf_loss"] == (a + b)[1] and out["metrics/critic_grad_magnitude"] == a[2]
     assert torch.isclose(out["metrics/critic_params_norm"], torch.sqrt(a[10] + (a + b)[11]))
     assert torch.isclose(out["metrics/actor_params_norm"], torch.sqrt(a[12] + (a + b)[13]))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The peer-memory exchange protocol (csrc/comm.cuh trunk_step_kernel + the per-owner dW reduce-adds), emulated with gloo:
+# every trunk element is stepped by exactly one owner (table from the library's host-only mtrl_trunk_segments), the
+# global norm is assembled from per-owner partial norms plus every rank's head norm, and the owners' new parameters
+# are broadcast.  Must equal clip_by_global_norm + adam on the summed gradient, and leave all replicas identical.
+# ---------------------------------------------------------------------------------------------------------------------
+def _segments(world, T=5, W=64, depth=3, E=2):
+    import ctypes as C
+
+    from mtrl_b200 import _lib as L
+    from mtrl_b200.rl.algorithms.mtsac import SacConfigC, SacLayoutC
+
+    t_local = -(-T // world)
+    cfg = SacConfigC(num_tasks=T, task_begin=0, num_local_tasks=t_local, obs_dim=11 + T, action_dim=3, width=W, depth=depth,
+                     num_critics=E, max_rows=128 * t_local, max_batch=128 * t_local, gamma=0.99, tau=0.005, actor_lr=3e-4,
+                     critic_lr=3e-4, alpha_lr=3e-4, adam_b1=0.9, adam_b2=0.999, adam_eps=1e-5, actor_max_grad_norm=1.0,
+                     critic_max_grad_norm=1.0, alpha_max_grad_norm=-1.0, log_std_min=-20.0, log_std_max=2.0,
+                     target_entropy=-3.0, clip_q=0, use_task_weights=0, noise_seed=1, variant=0)
+    lay = SacLayoutC()
+    L.check(L.lib().mtrl_sac_query_layout(C.byref(cfg), C.byref(lay)))
+    fn = L.lib().mtrl_trunk_segments
+    fn.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_longlong), C.c_int, C.POINTER(C.c_int)]
+    out = (C.c_longlong * (4 * 256))()
+    n = C.c_int()
+    L.check(fn(C.byref(lay.critic), world, out, 256, C.byref(n)))
+    return [(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]) for i in range(n.value)], int(lay.critic.trunk_total)
+
+
+def _exchange_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        segs, n = _segments(world)
+        gen = torch.Generator().manual_seed(100)           # same stream on every rank: the replicated state
+        p = torch.randn(n, generator=gen, dtype=torch.float64)
+        m = torch.randn(n, generator=gen, dtype=torch.float64) * 1e-3
+        v = torch.rand(n, generator=gen, dtype=torch.float64) * 1e-4
+        g_all = [torch.randn(n, generator=torch.Generator().manual_seed(200 + r), dtype=torch.float64) * 3 for r in range(world)]
+        head_g2 = [float(r + 1) * 0.37 for r in range(world)]            # every rank's local head-gradient squared norm
+        lr, b1, b2, eps, max_norm, t = 3e-4, 0.9, 0.999, 1e-5, 1.0, 7
+        # --- reference: one process, summed gradient ---
+        gs = sum(g_all)
+        gn = torch.sqrt((gs ** 2).sum() + sum(head_g2))
+        gc = gs if gn < max_norm else gs / gn * max_norm
+        m_ref, v_ref = b1 * m + (1 - b1) * gc, b2 * v + (1 - b2) * gc ** 2
+        p_ref = p - lr * (m_ref / (1 - b1 ** t)) / (torch.sqrt(v_ref / (1 - b2 ** t)) + eps)
+        # --- protocol on this rank ---
+        g = g_all[rank].clone()
+        owned = [(b, e) for b, e, o, _ in segs if o == rank]
+        # reduce-scatter: GEMM epilogue reduce-adds (pre_reduced) or owner peer loads -- either way the owner ends up with the sum
+        for b, e, o, _ in segs:
+            piece = g[b:e].clone()
+            dist.reduce(piece, dst=o)
+            if o == rank:
+                g[b:e] = piece
+        part = torch.tensor([sum(float((g[b:e] ** 2).sum()) for b, e in owned), head_g2[rank]], dtype=torch.float64)
+        parts = [torch.zeros(2, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(parts, part)                                     # the inbox_g2 / inbox_head_g2 exchange
+        gnorm = torch.sqrt(sum(x[0] for x in parts) + sum(x[1] for x in parts))
+        scale = 1.0 if gnorm < max_norm else max_norm / gnorm
+        p_new = p.clone()
+        for b, e in owned:
+            gg = g[b:e] * scale
+            m[b:e] = b1 * m[b:e] + (1 - b1) * gg
+            v[b:e] = b2 * v[b:e] + (1 - b2) * gg ** 2
+            p_new[b:e] = p[b:e] - lr * (m[b:e] / (1 - b1 ** t)) / (torch.sqrt(v[b:e] / (1 - b2 ** t)) + eps)
+        for b, e, o, _ in segs:                                          # all-gather: the owner's stores into every replica
+            piece = p_new[b:e].clone()
+            dist.broadcast(piece, src=o)
+            p_new[b:e] = piece
+        assert torch.allclose(gnorm, gn, rtol=1e-12)
+        assert torch.allclose(p_new, p_ref, rtol=1e-12, atol=1e-15), "replica differs from the unsharded Adam step"
+        for b, e in owned:
+            assert torch.allclose(m[b:e], m_ref[b:e], rtol=1e-12) and torch.allclose(v[b:e], v_ref[b:e], rtol=1e-12)
+        assert sum(e - b for b, e in owned) > 0
+        chk = p_new.clone()
+        dist.broadcast(chk, src=0)
+        assert torch.equal(chk, p_new), "replicas must be bit-identical"
+        ret[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_adam_exchange_protocol(world):
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_exchange_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert dict(ret) == {r: "ok" for r in range(world)}
