@@ -152,3 +152,58 @@ def test_split_update_without_surgery_equals_plain_update():
     # g0 vs g1 conflict (dot = -1): g0 -> g0 + 0.5 g1 = (0.5, 0.5); g1 -> g1 + g0 = (0, 1); g2 untouched
     assert stats["n_grad_conflicts"] == 1.0
     assert torch.allclose(avg, torch.tensor([0.5 / 3, 3.5 / 3], dtype=torch.float64), atol=1e-7)
+
+
+def test_tanh_gaussian_log_prob_agrees_with_torch_distributions():
+    """Row a7: the oracle restates distrax's Transformed(MultivariateNormalDiag, Block(Tanh, 1)).sample_and_log_prob
+    (mtrl/nn/distributions.py:6-16).  PyTorch ships an independent implementation of the same distribution
+    (TransformedDistribution(Independent(Normal), TanhTransform)); the two must agree on the log-density of the sample."""
+    import torch.distributions as D
+
+    cfg = O.OracleConfig(num_tasks=4, obs_dim=43, action_dim=4, width=32)
+    st = O.init_state(cfg, seed=3, dtype=torch.float64)
+    for k in ("kernel", "bias"):
+        st.actor["heads"][k] = st.actor["heads"][k] * 200.0          # non-trivial means / log-stds
+    batch, _, ea = O.synthetic_batch(cfg, 16, seed=12, dtype=torch.float64)
+    obs = batch[0]
+    a, logp = O.actor_sample_and_log_prob(st.actor, obs, ea, cfg)
+    out = O.multihead_forward(st.actor, obs, cfg.num_tasks, cfg.depth)
+    mean, log_std = out[..., :4], torch.clamp(out[..., 4:], cfg.log_std_min, cfg.log_std_max)
+    dist = D.TransformedDistribution(D.Independent(D.Normal(mean, torch.exp(log_std)), 1), [D.TanhTransform(cache_size=1)])
+    x = mean + torch.exp(log_std) * ea
+    y = torch.tanh(x)
+    assert torch.allclose(a, y)
+    # evaluate the density through the pre-image to avoid atanh round-off near +-1
+    ref = dist.base_dist.log_prob(x) - D.TanhTransform().log_abs_det_jacobian(x, y).sum(-1)
+    assert torch.allclose(logp, ref, rtol=1e-10, atol=1e-10)
+    inside = y.abs().max(dim=-1).values < 0.999
+    assert inside.any() and torch.allclose(dist.log_prob(y)[inside], logp[inside], rtol=1e-6, atol=1e-6)
+
+
+def test_adam_restatement_agrees_with_torch_optim_adam():
+    """Rows a14: the oracle restates optax.adam(lr, b1, b2, eps, eps_root=0) (mtrl/config/optim.py:26-43).  torch.optim.Adam
+    is an independent implementation of the same update (eps added to sqrt of the bias-corrected second moment): three
+    unclipped steps on the same gradients must coincide.  The global-norm clip is checked against its definition."""
+    g = torch.Generator().manual_seed(0)
+    p0 = {"a": {"kernel": torch.randn(7, 5, generator=g, dtype=torch.float64), "bias": torch.randn(5, generator=g, dtype=torch.float64)}}
+    grads = [O.tree_map(lambda x: torch.randn(x.shape, generator=g, dtype=torch.float64) * (10.0 ** (i - 1)), p0) for i in range(3)]
+    opt = {"count": 0, "m": O.tree_map(torch.zeros_like, p0), "v": O.tree_map(torch.zeros_like, p0)}
+    leaves = [x.clone().requires_grad_(True) for x in O.tree_leaves(p0)]
+    ref = torch.optim.Adam(leaves, lr=3e-4, betas=(0.9, 0.999), eps=1e-5)
+    p = p0
+    for gr in grads:
+        p, opt = O.adam_step(p, gr, opt, 3e-4, 1e-5, 0.9, 0.999, None)
+        for leaf, gl in zip(leaves, O.tree_leaves(gr)):
+            leaf.grad = gl.clone()
+        ref.step()
+        for a, b in zip(O.tree_leaves(p), leaves):
+            assert torch.allclose(a, b.detach(), rtol=1e-12, atol=1e-15)
+    # optax.clip_by_global_norm(1.0): untouched below the threshold, rescaled to exactly the threshold above it
+    big = O.tree_map(lambda x: x * 100, grads[1])
+    opt0 = {"count": 0, "m": O.tree_map(torch.zeros_like, p0), "v": O.tree_map(torch.zeros_like, p0)}
+    _, o_big = O.adam_step(p0, big, opt0, 3e-4, 1e-5, 0.9, 0.999, 1.0)
+    m_norm = O.global_norm(o_big["m"]) / 0.1            # m = (1 - b1) * clipped gradient
+    assert abs(float(m_norm) - 1.0) < 1e-9
+    small = O.tree_map(lambda x: x * 1e-3, grads[1])
+    _, o_small = O.adam_step(p0, small, opt0, 3e-4, 1e-5, 0.9, 0.999, 1.0)
+    assert torch.allclose(O.tree_leaves(o_small["m"])[0], 0.1 * O.tree_leaves(small)[0])
