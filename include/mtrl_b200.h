@@ -27,7 +27,7 @@ int mtrl_abi_version(void);
  * Grouped TF32 GEMM (tcgen05 / TMEM / TMA).  Replaces the dot_generals XLA emits for
  * nn.Dense in MultiHeadNetwork (mtrl/nn/multi_head.py:34-44) and their VJPs
  * (jax.value_and_grad at mtrl/rl/algorithms/mtsac.py:587-596, 689-691).
- * D[M][N] = sum_k A(m,k) * B(n,k); fp32 storage, tf32 operands, fp32 accumulate.
+ * D[M][N] = sum_k A(m,k) * B(n,k); fp32 storage, tf32 operands (or hi + lo tf32 pairs, see A_lo), fp32 accumulate.
  * ------------------------------------------------------------------------------------------ */
 enum {
   MTRL_EPI_STORE = 0,       /* D = acc                                                      */
@@ -62,6 +62,15 @@ typedef struct mtrl_gemm_problem {
   int schedule_first;    /* != 0: this problem's tiles are dealt to the workers before all others (outputs that travel
                             over NVLink: their stores then overlap the remaining tiles instead of the launch's tail)  */
   int reserved;
+  /* fp32x3 mode ("3xTF32", the precision the reference's fp32 CPU dots have).  A_lo / B_lo: the tf32 remainders of the
+   * operands (x = hi + lo, both tf32; same shape, pitch and layout as A / B).  Both set: the contraction accumulates
+   * A B + A B_lo + A_lo B in the same fp32 TMEM accumulator (three tcgen05.mma passes per k-block).  D_lo (needs an
+   * epilogue that rounds: BIAS_RELU, RELU_MASK, STORE_TF32; same pitch as D): also emit the tf32 remainder of the
+   * unrounded result, so that D / D_lo feed the next contraction as a hi / lo pair; column-sum partials are then taken
+   * from the unrounded values. */
+  const float* A_lo;
+  const float* B_lo;
+  float* D_lo;
 } mtrl_gemm_problem_t;
 
 typedef struct mtrl_gemm_plan mtrl_gemm_plan_t;
@@ -121,6 +130,13 @@ int mtrl_sampler_sample_per_task(mtrl_sampler_t* s, int fill, const int* counts,
 #define MTRL_MAX_DEPTH 4
 #define MTRL_VARIANT_MTSAC 0
 #define MTRL_VARIANT_SAC 1
+/* Arithmetic of the trunk contractions (storage and accumulation are fp32 in both):
+ *   MTRL_PRECISION_TF32   operands rounded to tf32 (what XLA's default f32 dot precision does on NVIDIA GPUs), fastest;
+ *   MTRL_PRECISION_FP32X3 every operand kept as a (hi, lo) pair of tf32 values and three tensor-core passes per k-block
+ *                         ("3xTF32"): reproduces fp32 products to ~2^-22, i.e. the numerics of the reference's fp32 CPU
+ *                         path, at 3x the tensor time.  The parity mode for the 1e-3 tolerance on every parameter leaf. */
+#define MTRL_PRECISION_TF32 0
+#define MTRL_PRECISION_FP32X3 1
 
 typedef struct mtrl_sac_config {
   int num_tasks;        /* T: width of the one-hot block that ends every observation             */
@@ -146,6 +162,7 @@ typedef struct mtrl_sac_config {
                            MTRL_VARIANT_SAC: single-task SAC._update_inner (sac.py:262-383): num_tasks = 1 (the network
                            is a plain MLP, mtrl/nn/base.py:11-63, its last Dense is the one "head"), alpha updated first,
                            critic loss 0.5 * sum_e mean_b, parameter-norm logs of the pre-update parameters        */
+  int precision;        /* MTRL_PRECISION_*                                                                        */
 } mtrl_sac_config_t;
 
 /* Flat fp32 layout of one network (all ensemble members).  [member trunks | 32 reduction slots |

@@ -27,26 +27,36 @@ class GemmProblem(C.Structure):
         ("bias", C.c_void_p), ("mask", C.c_void_p), ("ldmask", C.c_longlong),
         ("mask_bits", C.c_void_p), ("relu_bits_out", C.c_void_p), ("ldbits", C.c_longlong), ("colsum_partial", C.c_void_p),
         ("schedule_first", C.c_int), ("reserved", C.c_int),
+        ("A_lo", C.c_void_p), ("B_lo", C.c_void_p), ("D_lo", C.c_void_p),
     ]
 
 
 EPI_STORE, EPI_BIAS_RELU, EPI_RELU_MASK, EPI_ATOMIC_ADD, EPI_STORE_TF32 = range(5)
 
 
+ABI_VERSION = 5   # mtrl_abi_version() of the library these ctypes structures were written for
+
+
 def lib() -> C.CDLL:
-    """Load (building first if the .so is absent and nvcc is present) and return the library."""
+    """Load and return the library.  The build step runs first whenever nvcc is there: it is a digest comparison
+    (sources + header + flags against build/stamp.txt) when the binary is current and a rebuild when it is stale, so a
+    shipped .so can never run against newer struct layouts; ranks importing at once serialise on a file lock."""
     global _lib
     if _lib is not None:
         return _lib
-    if not _LIB_PATH.exists() or os.environ.get("MTRL_B200_REBUILD"):
-        from . import build as _build
+    from . import build as _build
 
-        _build.build_library()
+    if _build.have_nvcc():
+        _build.build_library(force=bool(os.environ.get("MTRL_B200_REBUILD")))
+    elif _LIB_PATH.exists() and not _build.is_current():
+        raise MtrlError(f"{_LIB_PATH} was built from different sources than the ones in csrc/ and nvcc is not available to rebuild it")
     if not _LIB_PATH.exists():
         raise MtrlError(f"{_LIB_PATH} is missing: the CUDA extension was not built; there is no CPU fallback")
     l = C.CDLL(str(_LIB_PATH), mode=C.RTLD_GLOBAL)
     l.mtrl_last_error.restype = C.c_char_p
     l.mtrl_abi_version.restype = C.c_int
+    if l.mtrl_abi_version() != ABI_VERSION:
+        raise MtrlError(f"{_LIB_PATH} has ABI version {l.mtrl_abi_version()}, this package expects {ABI_VERSION}")
     _declare(l)
     _lib = l
     return l

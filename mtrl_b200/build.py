@@ -46,13 +46,36 @@ def _digest() -> str:
     return h.hexdigest()
 
 
+def have_nvcc() -> bool:
+    return bool(shutil.which("nvcc")) or os.path.exists("/usr/local/cuda/bin/nvcc")
+
+
+def is_current() -> bool:
+    """True when the shared library was built from exactly the sources, header and flags that are on disk now."""
+    return LIB.exists() and STAMP.exists() and STAMP.read_text().strip() == _digest()
+
+
 def build_library(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every .cu to an object (in parallel) and link the shared library."""
-    digest = _digest()
-    if not force and LIB.exists() and STAMP.exists() and STAMP.read_text().strip() == digest:
+    """Compile every .cu to an object (in parallel) and link the shared library.  A no-op when the stamp matches;
+    otherwise the build runs under an exclusive file lock (several ranks may import the package at the same time)."""
+    if not force and is_current():
         return LIB
+    import fcntl
+
     objdir = PKG / "build"
     objdir.mkdir(exist_ok=True)
+    with open(objdir / ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and is_current():   # another process built it while this one waited
+                return LIB
+            return _build_locked(objdir, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(objdir: Path, verbose: bool) -> Path:
+    digest = _digest()
     nvcc = _nvcc()
     procs = []
     objs = []

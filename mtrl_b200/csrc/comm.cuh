@@ -84,6 +84,7 @@ constexpr unsigned long long kWaitTimeoutNs = 4000000000ull;  // 4 s: a missing 
 
 struct TrunkStepArgs {
   float *p, *m, *v, *shadow, *g, *target, *target_shadow;   // local buffers of this network (target may be null)
+  float *shadow_lo, *target_shadow_lo;                      // fp32x3: tf32 remainders of the operand copies (or null)
   long long n, trunk_n;                                    // as AdamArgs
   float* peer_g[MTRL_COMM_MAX_RANKS];                      // every rank's gradient buffer ([rank] == g)
   float* peer_p[MTRL_COMM_MAX_RANKS];                      // every rank's parameter buffer ([rank] == p)
@@ -183,30 +184,28 @@ __device__ __forceinline__ void adam4(const TrunkStepArgs& a, float scale, float
 
 // shadow = tf32(p); target = tau p + (1 - tau) target; target_shadow = tf32(target); returns |p|^2.
 // derived4t takes the already loaded target element.
+// hi (and, when lo is non-null, remainder) operand copies of four values
+__device__ __forceinline__ void store_operand4(float* hi, float* lo, long long i4, const float4& x) {
+  const float4 h = make_float4(tf32_rna(x.x), tf32_rna(x.y), tf32_rna(x.z), tf32_rna(x.w));
+  reinterpret_cast<float4*>(hi)[i4] = h;
+  if (lo) reinterpret_cast<float4*>(lo)[i4] = make_float4(tf32_lo(x.x, h.x), tf32_lo(x.y, h.y), tf32_lo(x.z, h.z), tf32_lo(x.w, h.w));
+}
 __device__ __forceinline__ float derived4t(const TrunkStepArgs& a, long long i4, const float4& p4, float4 t4) {
-  reinterpret_cast<float4*>(a.shadow)[i4] = make_float4(tf32_rna(p4.x), tf32_rna(p4.y), tf32_rna(p4.z), tf32_rna(p4.w));
+  store_operand4(a.shadow, a.shadow_lo, i4, p4);
   if (a.target) {
     t4.x = a.tau * p4.x + (1.f - a.tau) * t4.x;
     t4.y = a.tau * p4.y + (1.f - a.tau) * t4.y;
     t4.z = a.tau * p4.z + (1.f - a.tau) * t4.z;
     t4.w = a.tau * p4.w + (1.f - a.tau) * t4.w;
     reinterpret_cast<float4*>(a.target)[i4] = t4;
-    reinterpret_cast<float4*>(a.target_shadow)[i4] = make_float4(tf32_rna(t4.x), tf32_rna(t4.y), tf32_rna(t4.z), tf32_rna(t4.w));
+    store_operand4(a.target_shadow, a.target_shadow_lo, i4, t4);
   }
   return p4.x * p4.x + p4.y * p4.y + p4.z * p4.z + p4.w * p4.w;
 }
 __device__ __forceinline__ float derived4(const TrunkStepArgs& a, long long i4, const float4& p4) {
-  reinterpret_cast<float4*>(a.shadow)[i4] = make_float4(tf32_rna(p4.x), tf32_rna(p4.y), tf32_rna(p4.z), tf32_rna(p4.w));
-  if (a.target) {
-    float4 t4 = reinterpret_cast<const float4*>(a.target)[i4];
-    t4.x = a.tau * p4.x + (1.f - a.tau) * t4.x;
-    t4.y = a.tau * p4.y + (1.f - a.tau) * t4.y;
-    t4.z = a.tau * p4.z + (1.f - a.tau) * t4.z;
-    t4.w = a.tau * p4.w + (1.f - a.tau) * t4.w;
-    reinterpret_cast<float4*>(a.target)[i4] = t4;
-    reinterpret_cast<float4*>(a.target_shadow)[i4] = make_float4(tf32_rna(t4.x), tf32_rna(t4.y), tf32_rna(t4.z), tf32_rna(t4.w));
-  }
-  return p4.x * p4.x + p4.y * p4.y + p4.z * p4.z + p4.w * p4.w;
+  float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (a.target) t4 = reinterpret_cast<const float4*>(a.target)[i4];
+  return derived4t(a, i4, p4, t4);
 }
 
 // Every rank has finished what precedes this kernel in its stream (one warp; used before the first gradient

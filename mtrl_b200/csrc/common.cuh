@@ -55,6 +55,11 @@ __device__ __forceinline__ float tf32_rna(float x) {
   return __uint_as_float(r);
 }
 
+// fp32x3 ("3xTF32") operand split: x = hi + lo + O(2^-23 |x|) with hi, lo both exactly representable in tf32.  A GEMM
+// that accumulates a_hi b_hi + a_hi b_lo + a_lo b_hi in fp32 then reproduces the fp32 product to ~2^-22 relative (the
+// dropped a_lo b_lo term), which is what the reference's CPU dots compute (SURVEY 7 "Precision vs 1e-3").
+__device__ __forceinline__ float tf32_lo(float x, float hi) { return tf32_rna(x - hi); }
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -192,6 +197,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
+}
+// The reverse direction (registers -> TMEM), same shape; used to keep an fp32 running sum beside the accumulators.
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32"
+      " [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
 // ---- thread-block clusters / CTA pairs (cta_group::2) ----

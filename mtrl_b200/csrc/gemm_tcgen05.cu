@@ -13,6 +13,18 @@
 //
 // Operands are fp32 containers already rounded to tf32 by their producers (common.cuh tf32_rna),
 // accumulation is fp32 in TMEM, epilogues are fp32.
+//
+// fp32x3 mode (problem.A_lo / B_lo set): every operand arrives as a (hi, lo) pair of tf32 tensors with x = hi + lo to
+// 2^-23, and the contraction is A B + A B_lo + A_lo B (three tensor-core passes; the dropped A_lo B_lo is 2^-22).  The
+// tensor core adds into its fp32 accumulator with truncation, a bias that grows linearly with the number of k-steps
+// (measured: 7e-9 K relative, profiles/r02_precision_table.md), so the mode does NOT let one accumulator run over K:
+// the k-range is cut into chunks of `chunk_kb` k-blocks, every chunk is two sub-units with their own TMEM accumulator --
+// MAIN = the (A, B) pass, SMALL = the (A, B_lo) and (A_lo, B) passes, whose sum is 2^-11 of MAIN so its truncation
+// error is too -- and the epilogue warps add the finished accumulators into an fp32 RUNNING SUM (round-to-nearest, in
+// registers, parked in a third TMEM region at columns [128, 256), hence block_n <= 128).  The last sub-unit's
+// epilogue adds the running sum and applies the fused op.  Producer and MMA issuer see sub-units as ordinary pipeline
+// stages (only the tensor maps switch).  Epilogues that round their output can also emit the remainder tensor (D_lo)
+// so the next contraction gets its pair.
 #include <cuda.h>  // CUtensorMap types only; the encode entry point is fetched at run time
 
 #include <stdlib.h>
@@ -74,7 +86,9 @@ struct __align__(16) DevProblem {
   int b_chunks;  // 32-wide MN chunks of B each CTA loads per stage (MN-major B only)
   int mn3d;      // bit 0 / 1: A / B is MN-major and described by a 3-D map (one TMA per stage instead of one per chunk)
   int tma_out;   // output goes through smem staging + TMA store / reduce-add (needs block_n % 32 == 0)
-  int pad0, pad1, pad2;
+  int x3;        // fp32x3: > 0 = k-blocks per chunk (maps 3 / 4 = A_lo / B_lo); every chunk is a MAIN and a SMALL sub-unit
+  int d_lo;      // the epilogue also stores the tf32 remainder of the unrounded output through map 5
+  int pad2;
 };
 
 // smem matrix descriptor (cute::UMMA::SmemDescriptor layout): start>>4 [0,14), LBO>>4 [16,30),
@@ -92,10 +106,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 }
 
 constexpr int kMaxProblems = 24;
+constexpr int kMapsPer = 6;
 
 // Passed by value as a __grid_constant__ kernel parameter (the usual home of TMA descriptors).
 struct GemmParams {
-  CUtensorMap maps[3 * kMaxProblems];   // A, B, D of every problem
+  CUtensorMap maps[kMapsPer * kMaxProblems];   // A, B, D, A_lo, B_lo, D_lo of every problem
   DevProblem probs[kMaxProblems];
   int nprob;
   int total_units;
@@ -124,6 +139,32 @@ __device__ __forceinline__ UnitCoord decode_unit(const DevProblem* __restrict__ 
   c.kb0 = split * P.kb_per_split;
   c.kb1 = min(P.kb_total, c.kb0 + P.kb_per_split);
   return c;
+}
+
+// A unit's k-range [kb0, kb1) runs as `nsub` sub-units, each with its own accumulator: one in tf32 mode; in fp32x3 mode
+// two per chunk of P.x3 k-blocks (see the header comment).  Sub-unit `sub` covers k-blocks [s0, s1) in `nst` pipeline
+// stages; stage `st` loads k-block kk with operand pass 0 (A, B), 1 (A, B_lo) or 2 (A_lo, B).
+struct SubUnit {
+  int s0, nst, small;
+  __device__ __forceinline__ void stage(int st, int* kk, int* pass) const {
+    *kk = s0 + (small ? st >> 1 : st);
+    *pass = small ? 1 + (st & 1) : 0;
+  }
+};
+__device__ __forceinline__ int num_subunits(const DevProblem& P, const UnitCoord& c) {
+  return P.x3 ? 2 * ((c.kb1 - c.kb0 + P.x3 - 1) / P.x3) : 1;
+}
+__device__ __forceinline__ SubUnit get_subunit(const DevProblem& P, const UnitCoord& c, int sub) {
+  SubUnit u;
+  if (!P.x3) {
+    u.s0 = c.kb0; u.nst = c.kb1 - c.kb0; u.small = 0;
+    return u;
+  }
+  u.small = sub & 1;
+  u.s0 = c.kb0 + (sub >> 1) * P.x3;
+  const int s1 = min(c.kb1, u.s0 + P.x3);
+  u.nst = (s1 - u.s0) * (u.small ? 2 : 1);
+  return u;
 }
 
 template <int kCtas>
@@ -196,14 +237,18 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
         const int unit = sched_units[si];
         const UnitCoord c = decode_unit(probs, nprob, unit);
         const DevProblem& P = probs[c.p];
-        const CUtensorMap* mapA = maps + 3 * c.p;
-        const CUtensorMap* mapB = maps + 3 * c.p + 1;
+        const CUtensorMap* mapA0 = maps + kMapsPer * c.p;
         const int n_cta = P.block_n / kCtas;                       // B columns staged by this CTA
         const int m0 = (c.m_tile * kCtas + static_cast<int>(rank)) * kBlockM;
         const int n0 = c.n_tile * P.block_n + static_cast<int>(rank) * n_cta;
         const uint32_t b_bytes = P.b_major ? static_cast<uint32_t>(P.b_chunks) * kChunkBytes
                                            : static_cast<uint32_t>(n_cta) * kBlockK * 4u;
-        for (int kb = c.kb0; kb < c.kb1; ++kb) {
+        const int nsub = num_subunits(P, c);
+        for (int sub = 0; sub < nsub; ++sub) {
+        const SubUnit su = get_subunit(P, c, sub);
+        for (int sst = 0; sst < su.nst; ++sst) {
+          int kk, pass;
+          su.stage(sst, &kk, &pass);
           const long long t0 = params.dbg ? clock64() : 0;
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const long long t1 = params.dbg ? clock64() : 0;
@@ -211,7 +256,9 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
           const uint32_t sa = smem_base + stage * C::kStageBytes;
           const uint32_t sb = sa + kABytes;
           const uint32_t fb = full_bar(stage);
-          const int k0 = kb * kBlockK;
+          const CUtensorMap* mapA = mapA0 + (pass == 2 ? 3 : 0);
+          const CUtensorMap* mapB = mapA0 + (pass == 1 ? 4 : 1);
+          const int k0 = kk * kBlockK;
           if (elect_one()) {
           if (rank == 0) mbar_expect_tx(fb, kCtas * (kABytes + b_bytes));
           auto load = [&](uint32_t dst, const CUtensorMap* map, int c0, int c1) {
@@ -245,6 +292,7 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
             phase ^= 1u;
           }
         }
+        }  // sub-units
       }
       if (params.dbg && lane == 0) {
         atomicAdd(reinterpret_cast<unsigned long long*>(params.dbg + 0), static_cast<unsigned long long>(t_wait));
@@ -277,12 +325,15 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
         const uint32_t b_lt = P.b_major ? 1u : 2u;
         const uint32_t a_kstep = P.a_major ? 1024u : 32u;
         const uint32_t b_kstep = P.b_major ? 1024u : 32u;
+        const int nsub = num_subunits(P, c);
+        for (int sub = 0; sub < nsub; ++sub) {
+        const SubUnit su = get_subunit(P, c, sub);
         const long long ta = params.dbg ? clock64() : 0;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         if (params.dbg) t_wtempty += clock64() - ta;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * kMaxBlockN;
-        for (int kb = c.kb0; kb < c.kb1; ++kb) {
+        for (int sst = 0; sst < su.nst; ++sst) {
           const long long t0 = params.dbg ? clock64() : 0;
           mbar_wait(full_bar(stage), phase);
           const long long t1 = params.dbg ? clock64() : 0;
@@ -295,7 +346,7 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
             for (int k = 0; k < kBlockK / kUmmaK; ++k) {
               const uint64_t adesc = make_smem_desc(sa + k * a_kstep, a_lbo, a_sbo, a_lt);
               const uint64_t bdesc = make_smem_desc(sb + k * b_kstep, b_lbo, b_sbo, b_lt);
-              const uint32_t accum = (kb > c.kb0 || k > 0) ? 1u : 0u;
+              const uint32_t accum = (sst > 0 || k > 0) ? 1u : 0u;
               if (kCtas == 2) umma_tf32_pair(d_tmem, adesc, bdesc, idesc, accum);
               else umma_tf32(d_tmem, adesc, bdesc, idesc, accum);
             }
@@ -318,6 +369,7 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
           acc = 0;
           acc_phase ^= 1u;
         }
+        }  // sub-units
       }
       if (params.dbg && lane == 0) {
         atomicAdd(reinterpret_cast<unsigned long long*>(params.dbg + 2), static_cast<unsigned long long>(t_wfull));
@@ -344,7 +396,9 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
         const int unit = sched_units[si];
       const UnitCoord c = decode_unit(probs, nprob, unit);
       const DevProblem& P = probs[c.p];
-      const CUtensorMap* mapD = maps + 3 * c.p + 2;
+      const CUtensorMap* mapD = maps + kMapsPer * c.p + 2;
+      const CUtensorMap* mapDlo = maps + kMapsPer * c.p + 5;
+      const bool d_lo = P.d_lo != 0;
       const int row0 = (c.m_tile * kCtas + static_cast<int>(rank)) * kBlockM + quarter * 32;
       const int row = row0 + lane;
       const int n0 = c.n_tile * P.block_n;
@@ -356,6 +410,38 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
       const int cbeg = col_half ? c0 * 16 : 0;
       const int cend = col_half ? P.block_n : c0 * 16;
       const int epi = P.epilogue;
+      // fp32x3: all sub-units but the last are added (fp32, round to nearest) into the running sum this warp keeps for
+      // its lanes x columns in the third TMEM region, columns [128, 256) (block_n <= 128 in that mode)
+      const int nsub = num_subunits(P, c);
+      const uint32_t t_sum = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + 128u;
+      for (int sub = 0; sub + 1 < nsub; ++sub) {
+        const long long ts0 = params.dbg ? clock64() : 0;
+        mbar_wait(tfull_bar(acc), acc_phase);
+        if (params.dbg) t_wait += clock64() - ts0;
+        tc_fence_after();
+        const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc) * kMaxBlockN;
+        for (int cc = cbeg; cc < cend; cc += 16) {
+          uint32_t v[16], sv[16];
+          tmem_ld16(t_acc + cc, v);
+          if (sub > 0) tmem_ld16(t_sum + cc, sv);
+          tmem_ld_wait();
+          if (sub > 0) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(sv[i]));
+          }
+          tmem_st16(t_sum + cc, v);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (kCtas == 2) mbar_arrive_cluster(tempty_bar(acc), 0); else mbar_arrive(tempty_bar(acc));
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
       const long long t0 = params.dbg ? clock64() : 0;
       mbar_wait(tfull_bar(acc), acc_phase);
       const long long t1 = params.dbg ? clock64() : 0;
@@ -394,7 +480,18 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
           o[i] = __uint_as_float(v0[i]);
           o[16 + i] = ncols == 32 ? __uint_as_float(v1[i]) : 0.f;
         }
+        if (nsub > 1) {   // the earlier sub-units of this tile
+          tmem_ld16(t_sum + cc, v0);
+          if (ncols == 32) tmem_ld16(t_sum + cc + 16, v1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            o[i] += __uint_as_float(v0[i]);
+            if (ncols == 32) o[16 + i] += __uint_as_float(v1[i]);
+          }
+        }
         const int col0 = n0 + cc;
+        // d_lo: o[] keeps the UNROUNDED fp32 result through the fused op; the (hi, lo) split happens at the store
         if (epi == MTRL_EPI_BIAS_RELU) {
           unsigned bits = 0u;
 #pragma unroll
@@ -402,10 +499,14 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
             float4 b;
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
                          : "r"(sbias + static_cast<uint32_t>(cc - cbeg + 4 * j) * 4u));
-            o[4 * j + 0] = tf32_rna(fmaxf(o[4 * j + 0] + b.x, 0.f));
-            o[4 * j + 1] = tf32_rna(fmaxf(o[4 * j + 1] + b.y, 0.f));
-            o[4 * j + 2] = tf32_rna(fmaxf(o[4 * j + 2] + b.z, 0.f));
-            o[4 * j + 3] = tf32_rna(fmaxf(o[4 * j + 3] + b.w, 0.f));
+            o[4 * j + 0] = fmaxf(o[4 * j + 0] + b.x, 0.f);
+            o[4 * j + 1] = fmaxf(o[4 * j + 1] + b.y, 0.f);
+            o[4 * j + 2] = fmaxf(o[4 * j + 2] + b.z, 0.f);
+            o[4 * j + 3] = fmaxf(o[4 * j + 3] + b.w, 0.f);
+          }
+          if (!d_lo) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = tf32_rna(o[i]);
           }
           if (P.bits_out) {
 #pragma unroll
@@ -416,17 +517,17 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
           if (P.mask_bits) {
             const unsigned mb = bi == 0 ? mbits[0] : (bi == 1 ? mbits[1] : (bi == 2 ? mbits[2] : mbits[3]));
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = ((mb >> i) & 1u) ? tf32_rna(o[i]) : 0.f;
+            for (int i = 0; i < 32; ++i) o[i] = ((mb >> i) & 1u) ? (d_lo ? o[i] : tf32_rna(o[i])) : 0.f;
           } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int col = col0 + 4 * j;
               float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
               if (row_ok && 4 * j < ncols && col + 4 <= P.N) h = __ldg(reinterpret_cast<const float4*>(mrow + col));
-              o[4 * j + 0] = h.x > 0.f ? tf32_rna(o[4 * j + 0]) : 0.f;
-              o[4 * j + 1] = h.y > 0.f ? tf32_rna(o[4 * j + 1]) : 0.f;
-              o[4 * j + 2] = h.z > 0.f ? tf32_rna(o[4 * j + 2]) : 0.f;
-              o[4 * j + 3] = h.w > 0.f ? tf32_rna(o[4 * j + 3]) : 0.f;
+              o[4 * j + 0] = h.x > 0.f ? (d_lo ? o[4 * j + 0] : tf32_rna(o[4 * j + 0])) : 0.f;
+              o[4 * j + 1] = h.y > 0.f ? (d_lo ? o[4 * j + 1] : tf32_rna(o[4 * j + 1])) : 0.f;
+              o[4 * j + 2] = h.z > 0.f ? (d_lo ? o[4 * j + 2] : tf32_rna(o[4 * j + 2])) : 0.f;
+              o[4 * j + 3] = h.w > 0.f ? (d_lo ? o[4 * j + 3] : tf32_rna(o[4 * j + 3])) : 0.f;
             }
           }
           if (P.colsum) {
@@ -450,10 +551,42 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
               P.colsum[static_cast<long long>(group) * P.N + col0 + lane] = r[0];
           }
         } else if (epi == MTRL_EPI_STORE_TF32) {
+          if (!d_lo) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = tf32_rna(o[i]);
+            for (int i = 0; i < 32; ++i) o[i] = tf32_rna(o[i]);
+          }
         }
-        if (P.tma_out) {
+        if (P.tma_out && d_lo) {
+          // (hi, lo) pair: both staging boxes of this warp per iteration, so the previous pair must have been read
+          if (nbox >= 2) {
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float hi[4], lo[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              hi[q] = tf32_rna(o[4 * j + q]);
+              lo[q] = tf32_lo(o[4 * j + q], hi[q]);
+            }
+            const uint32_t dst = stg0 + static_cast<uint32_t>(lane) * 128u + (static_cast<uint32_t>(j ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(hi[0]), "f"(hi[1]), "f"(hi[2]), "f"(hi[3]) : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + kEpiBoxBytes), "f"(lo[0]), "f"(lo[1]), "f"(lo[2]), "f"(lo[3])
+                         : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            // one bulk group per box, in box order: the single-box path's wait_read<1> bookkeeping stays valid when a
+            // launch mixes problems with and without D_lo
+            tma_store_2d(mapD, stg0, col0, row0);
+            tma_store_commit();
+            tma_store_2d(mapDlo, stg0 + kEpiBoxBytes, col0, row0);
+            tma_store_commit();
+          }
+          nbox += 2;
+        } else if (P.tma_out) {
           const uint32_t stg = stg0 + (nbox & 1u) * kEpiBoxBytes;
           if (nbox >= 2) {
             if (lane == 0) tma_store_wait_read<1>();   // the store issued two boxes ago has released this buffer
@@ -607,9 +740,14 @@ extern "C" int mtrl_gemm_plan_create(mtrl_gemm_plan_t** out, const mtrl_gemm_pro
     ~Guard() { delete p; }
   } guard{plan};
   plan->ctas = ctas;
+  // fp32x3: k-blocks (of 32) one accumulator runs over before it is folded into the running sum (MTRL_X3_CHUNK, 1..64)
+  int x3_chunk = 4;
+  if (const char* e = getenv("MTRL_X3_CHUNK")) x3_chunk = atoi(e) < 1 ? 1 : (atoi(e) > 64 ? 64 : atoi(e));
   GemmParams& P = plan->params;
   memset(&P, 0, sizeof(P));
   int units = 0;
+  bool any_x3 = false;
+  for (int i = 0; i < n; ++i) any_x3 = any_x3 || problems[i].A_lo != nullptr;
   for (int i = 0; i < n; ++i) {
     const mtrl_gemm_problem_t& p = problems[i];
     MTRL_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "problem %d: empty shape", i);
@@ -626,6 +764,10 @@ extern "C" int mtrl_gemm_plan_create(mtrl_gemm_plan_t** out, const mtrl_gemm_pro
     // A CTA of a pair stages block_n / 2 columns of B; MN-major B arrives in 32-column TMA boxes, so the
     // half must be a multiple of 32 there.
     int block_n = p.block_n;
+    MTRL_REQUIRE((p.A_lo == nullptr) == (p.B_lo == nullptr), "problem %d: fp32x3 needs both A_lo and B_lo", i);
+    // columns [128, 256) of TMEM hold the running sum of fp32x3 tiles; the MMA issuer runs up to two accumulators ahead of
+    // the epilogue, so a wider tile of ANY problem of the launch could overwrite a sum that is still needed
+    if (any_x3 && block_n > 128) block_n = 128;
     if (ctas == 2 && p.b_major && block_n % 64 != 0) block_n = (block_n + 63) / 64 * 64;
     const int tile_m = kBlockM * ctas;
     const int n_cta = block_n / ctas;
@@ -645,6 +787,7 @@ extern "C" int mtrl_gemm_plan_create(mtrl_gemm_plan_t** out, const mtrl_gemm_pro
     d.block_n = block_n;
     d.m_tiles = (p.M + tile_m - 1) / tile_m;
     d.n_tiles = (p.N + block_n - 1) / block_n;
+    d.x3 = p.A_lo ? x3_chunk : 0;
     d.kb_total = (p.K + kBlockK - 1) / kBlockK;
     int splits = p.k_splits < d.kb_total ? p.k_splits : d.kb_total;
     d.kb_per_split = (d.kb_total + splits - 1) / splits;
@@ -668,26 +811,40 @@ extern "C" int mtrl_gemm_plan_create(mtrl_gemm_plan_t** out, const mtrl_gemm_pro
     const bool allow_tma_out = !(getenv("MTRL_GEMM_NO_TMA_OUT") && getenv("MTRL_GEMM_NO_TMA_OUT")[0] == '1');
     d.tma_out = 0;
     if (allow_tma_out && block_n % 32 == 0 &&
-        encode_map(&P.maps[3 * i + 2], p.D, p.N, p.M, p.ldd, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B) == MTRL_OK)
+        encode_map(&P.maps[kMapsPer * i + 2], p.D, p.N, p.M, p.ldd, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B) == MTRL_OK)
       d.tma_out = 1;
+    d.d_lo = 0;
+    if (p.D_lo) {
+      MTRL_REQUIRE(p.epilogue == MTRL_EPI_BIAS_RELU || p.epilogue == MTRL_EPI_RELU_MASK || p.epilogue == MTRL_EPI_STORE_TF32,
+                   "problem %d: D_lo needs an epilogue that rounds its output", i);
+      MTRL_REQUIRE(d.tma_out, "problem %d: D_lo needs the TMA output path (block_n %% 32 == 0)", i);
+      MTRL_PROPAGATE(encode_map(&P.maps[kMapsPer * i + 5], p.D_lo, p.N, p.M, p.ldd, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B));
+      d.d_lo = 1;
+    }
     const bool allow3d = !(getenv("MTRL_GEMM_NO_3D") && getenv("MTRL_GEMM_NO_3D")[0] == '1');
     d.mn3d = 0;
-    if (!d.a_major) {
-      MTRL_PROPAGATE(encode_map(&P.maps[3 * i], p.A, p.K, p.M, p.lda, kBlockK, kBlockM, CU_TENSOR_MAP_SWIZZLE_128B));
-    } else if (allow3d && encode_map_mn3d(&P.maps[3 * i], p.A, p.M, p.K, p.lda, kBlockM / 32)) {
-      d.mn3d |= 1;
-    } else {
-      MTRL_PROPAGATE(encode_map(&P.maps[3 * i], p.A, p.M, p.K, p.lda, 32, kBlockK,
-                                CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
-    }
-    if (!d.b_major) {
-      MTRL_PROPAGATE(encode_map(&P.maps[3 * i + 1], p.B, p.K, p.N, p.ldb, kBlockK, n_cta,
-                                CU_TENSOR_MAP_SWIZZLE_128B));
-    } else if (allow3d && n_cta % 32 == 0 && encode_map_mn3d(&P.maps[3 * i + 1], p.B, p.N, p.K, p.ldb, n_cta / 32)) {
-      d.mn3d |= 2;
-    } else {
-      MTRL_PROPAGATE(encode_map(&P.maps[3 * i + 1], p.B, p.N, p.K, p.ldb, 32, kBlockK,
-                                CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+    // the remainder operands (fp32x3) share shape, pitch and layout with their hi tensors: same map kinds
+    for (int part = 0; part < (d.x3 ? 2 : 1); ++part) {
+      const float* pa = part ? p.A_lo : p.A;
+      const float* pb = part ? p.B_lo : p.B;
+      CUtensorMap* ma = &P.maps[kMapsPer * i + (part ? 3 : 0)];
+      CUtensorMap* mb = &P.maps[kMapsPer * i + (part ? 4 : 1)];
+      if (!d.a_major) {
+        MTRL_PROPAGATE(encode_map(ma, pa, p.K, p.M, p.lda, kBlockK, kBlockM, CU_TENSOR_MAP_SWIZZLE_128B));
+      } else if ((part ? (d.mn3d & 1) != 0 : allow3d) && encode_map_mn3d(ma, pa, p.M, p.K, p.lda, kBlockM / 32)) {
+        d.mn3d |= 1;
+      } else {
+        MTRL_REQUIRE(!(part && (d.mn3d & 1)), "problem %d: A_lo cannot use the 3-D map its hi tensor uses", i);
+        MTRL_PROPAGATE(encode_map(ma, pa, p.M, p.K, p.lda, 32, kBlockK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+      }
+      if (!d.b_major) {
+        MTRL_PROPAGATE(encode_map(mb, pb, p.K, p.N, p.ldb, kBlockK, n_cta, CU_TENSOR_MAP_SWIZZLE_128B));
+      } else if ((part ? (d.mn3d & 2) != 0 : (allow3d && n_cta % 32 == 0)) && encode_map_mn3d(mb, pb, p.N, p.K, p.ldb, n_cta / 32)) {
+        d.mn3d |= 2;
+      } else {
+        MTRL_REQUIRE(!(part && (d.mn3d & 2)), "problem %d: B_lo cannot use the 3-D map its hi tensor uses", i);
+        MTRL_PROPAGATE(encode_map(mb, pb, p.N, p.K, p.ldb, 32, kBlockK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+      }
     }
   }
   P.nprob = n;
@@ -710,7 +867,8 @@ extern "C" int mtrl_gemm_plan_create(mtrl_gemm_plan_t** out, const mtrl_gemm_pro
         const int kb0 = split * d.kb_per_split;
         const int kb1 = kb0 + d.kb_per_split < d.kb_total ? kb0 + d.kb_per_split : d.kb_total;
         const long long per_kb = d.block_n > 160 ? d.block_n : 160;
-        us.push_back({d.unit_begin + u, static_cast<long long>(kb1 - kb0) * per_kb + 4 * 256, problems[i].schedule_first ? 1 : 0});
+        us.push_back({d.unit_begin + u, static_cast<long long>(kb1 - kb0) * per_kb * (d.x3 ? 3 : 1) + 4 * 256,
+                      problems[i].schedule_first ? 1 : 0});
       }
     }
     const bool lpt = !(getenv("MTRL_GEMM_NO_LPT") && getenv("MTRL_GEMM_NO_LPT")[0] == '1');

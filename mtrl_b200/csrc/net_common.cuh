@@ -58,8 +58,11 @@ inline float* tb(float* base, const mtrl_net_layout_t& L, int e, int l) { return
 inline float* hk(float* base, const mtrl_net_layout_t& L, int e) { return base + L.heads_base + e * L.member_head_stride + L.head_kernel_off; }
 inline float* hb(float* base, const mtrl_net_layout_t& L, int e) { return base + L.heads_base + e * L.member_head_stride + L.head_bias_off; }
 
+// The trailing *_lo arguments are the tf32 remainders of the operands / the output (fp32x3 mode, mtrl_b200.h); all
+// null = plain tf32.
 inline mtrl_gemm_problem_t fwd_problem(const float* X, int ldx, int K, const float* Wsh, const float* bias, float* out, int M, int W,
-                                unsigned* bits_out = nullptr) {
+                                unsigned* bits_out = nullptr, const float* X_lo = nullptr, const float* Wsh_lo = nullptr,
+                                float* out_lo = nullptr) {
   mtrl_gemm_problem_t p;
   memset(&p, 0, sizeof(p));
   p.A = X; p.lda = ldx; p.a_major = 0;
@@ -68,11 +71,13 @@ inline mtrl_gemm_problem_t fwd_problem(const float* X, int ldx, int K, const flo
   p.M = M; p.N = W; p.K = K;
   p.block_n = block_n_for(W); p.k_splits = 1; p.epilogue = MTRL_EPI_BIAS_RELU; p.bias = bias;
   p.relu_bits_out = bits_out; p.ldbits = (W + 31) / 32;
+  p.A_lo = X_lo; p.B_lo = Wsh_lo; p.D_lo = out_lo;
   return p;
 }
 // dZ_prev = (dZ W^T) * (H_prev > 0): A = dZ [M][W] K-major, B = W [in=N][W=K] K-major
 inline mtrl_gemm_problem_t dx_problem(const float* dZ, const float* Wsh, int n_in, const unsigned* mask_bits, float* out, int M, int W,
-                               float* colsum_partial) {
+                               float* colsum_partial, const float* dZ_lo = nullptr, const float* Wsh_lo = nullptr,
+                               float* out_lo = nullptr) {
   mtrl_gemm_problem_t p;
   memset(&p, 0, sizeof(p));
   p.A = dZ; p.lda = W; p.a_major = 0;
@@ -82,11 +87,12 @@ inline mtrl_gemm_problem_t dx_problem(const float* dZ, const float* Wsh, int n_i
   p.block_n = block_n_for(n_in); p.k_splits = 1; p.epilogue = MTRL_EPI_RELU_MASK;
   p.mask_bits = mask_bits; p.ldbits = (n_in + 31) / 32;
   p.colsum_partial = colsum_partial;
+  p.A_lo = dZ_lo; p.B_lo = Wsh_lo; p.D_lo = out_lo;
   return p;
 }
 // dW = X^T dZ: A = X [rows][in] MN-major, B = dZ [rows][W] MN-major, K = rows
 inline mtrl_gemm_problem_t dw_problem(const float* X, int ldx, int n_in, const float* dZ, float* dW, int M, int W, int sms,
-                               int units_hint) {
+                               int units_hint, const float* X_lo = nullptr, const float* dZ_lo = nullptr) {
   mtrl_gemm_problem_t p;
   memset(&p, 0, sizeof(p));
   p.A = X; p.lda = ldx; p.a_major = 1;
@@ -109,6 +115,7 @@ inline mtrl_gemm_problem_t dw_problem(const float* X, int ldx, int n_in, const f
   (void)units_hint;
   p.k_splits = splits;
   p.epilogue = splits > 1 ? MTRL_EPI_ATOMIC_ADD : MTRL_EPI_STORE;
+  p.A_lo = X_lo; p.B_lo = dZ_lo;
   return p;
 }
 

@@ -104,8 +104,8 @@ extern "C" void mtrl_ppo_destroy(mtrl_ppo_t* h) {
 extern "C" int mtrl_ppo_refresh_shadows(mtrl_ppo_t* h, void* stream) {
   MTRL_REQUIRE(h, "mtrl_ppo_refresh_shadows: null handle");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  sac::shadow_kernel<<<h->sms * 4, 256, 0, st>>>(h->buf.policy_params, h->buf.policy_shadow, h->lay.policy.total);
-  sac::shadow_kernel<<<h->sms * 4, 256, 0, st>>>(h->buf.vf_params, h->buf.vf_shadow, h->lay.vf.total);
+  sac::shadow_kernel<<<h->sms * 4, 256, 0, st>>>(h->buf.policy_params, h->buf.policy_shadow, nullptr, h->lay.policy.total);
+  sac::shadow_kernel<<<h->sms * 4, 256, 0, st>>>(h->buf.vf_params, h->buf.vf_shadow, nullptr, h->lay.vf.total);
   MTRL_CUDA_CHECK(cudaGetLastError());
   return MTRL_OK;
 }
@@ -270,6 +270,7 @@ extern "C" int mtrl_ppo_update(mtrl_ppo_t* h, const float* obs, const float* log
     sac::write_slot_kernel<<<1, 1, 0, st>>>(n.g + n.L->slots_off, w.acc + n.hg2);
     sac::sumsq_kernel<<<h->sms * 2, 256, 0, st>>>(n.g, n.L->trunk_total, w.acc + n.g2);
     sac::AdamArgs a;
+    memset(&a, 0, sizeof(a));
     a.p = n.p; a.m = n.m; a.v = n.v; a.shadow = n.sh; a.g = n.g; a.target = nullptr; a.target_shadow = nullptr;
     a.n = n.L->total; a.trunk_n = n.L->trunk_total;
     a.g2_trunk = w.acc + n.g2; a.g2_heads = n.g + n.L->slots_off; a.step = h->buf.steps + n.step;

@@ -27,15 +27,21 @@ struct Workspace {
   float *C[kMaxE][MTRL_MAX_DEPTH], *Tg[kMaxE][MTRL_MAX_DEPTH];
   float* G[kMaxE][2];
   float* dXin;
-  float *rew, *done, *eps_c, *eps_a, *logp_next, *logp, *act, *logstd, *dq, *dout, *colsum_part, *alpha_val, *task_w;
+  float *rew, *done, *eps_c, *eps_a, *logp_next, *logp, *act, *act_data, *logstd, *dq, *dout, *colsum_part, *alpha_val, *task_w;
   unsigned* inrange;
   unsigned *bits_Ao[MTRL_MAX_DEPTH], *bits_C[kMaxE][MTRL_MAX_DEPTH];  // ReLU sign bits of Ao[l] / C[e][l], [M][W/32]
   int *row_slot, *slot_src, *tile_task, *seg_start, *status;
   double* acc;
+  // fp32x3 (MTRL_PRECISION_FP32X3): every GEMM operand buffer above (inputs, activations, dZ) has its tf32 remainder at
+  // the same offset in a mirror region, `lo_delta` floats further on (0 in tf32 mode); the remainders of the three
+  // parameter operand copies (shadows) follow.
+  long long lo_delta;
+  float *ash_lo, *csh_lo, *tsh_lo;
 };
 
 // Bump allocation; with base == nullptr only the size is computed.
-long long carve(const mtrl_sac_config_t& c, int Ka, int Kc, uint8_t* base, Workspace* ws) {
+long long carve(const mtrl_sac_config_t& c, int Ka, int Kc, long long actor_total, long long critic_total, uint8_t* base,
+                Workspace* ws) {
   long long off = 0;
   auto take = [&](long long bytes) -> uint8_t* {
     uint8_t* p = base ? base + off : nullptr;
@@ -62,6 +68,7 @@ long long carve(const mtrl_sac_config_t& c, int Ka, int Kc, uint8_t* base, Works
     w.G[e][0] = f(M * W);
     w.G[e][1] = f(M * W);
   }
+  const long long mirror_bytes = off;   // everything above is a GEMM operand
   w.dXin = f(E * M * 16);
   w.rew = f(M);
   w.done = f(M);
@@ -70,6 +77,7 @@ long long carve(const mtrl_sac_config_t& c, int Ka, int Kc, uint8_t* base, Works
   w.logp_next = f(M);
   w.logp = f(M);
   w.act = f(M * A);
+  w.act_data = f(M * A);
   w.logstd = f(M * A);
   w.dq = f(E * M);
   w.dout = f(M * 2 * A);
@@ -88,6 +96,13 @@ long long carve(const mtrl_sac_config_t& c, int Ka, int Kc, uint8_t* base, Works
   w.seg_start = reinterpret_cast<int*>(take((c.num_local_tasks + 1) * 4));
   w.status = reinterpret_cast<int*>(take(16));
   w.acc = reinterpret_cast<double*>(take(ACC_COUNT * 8));
+  if (c.precision == MTRL_PRECISION_FP32X3) {
+    w.lo_delta = off / 4;
+    take(mirror_bytes);
+    w.ash_lo = f(actor_total);
+    w.csh_lo = f(critic_total);
+    w.tsh_lo = f(critic_total);
+  }
   if (ws) *ws = w;
   return off;
 }
@@ -112,6 +127,8 @@ int validate(const mtrl_sac_config_t& c) {
                "sac config: the single-task variant needs num_tasks == 1, no task weights, no Q clipping");
   MTRL_REQUIRE(!(c.use_task_weights && c.num_local_tasks != c.num_tasks),
                "sac config: use_task_weights needs all tasks on one handle (softmax over every log_alpha)");
+  MTRL_REQUIRE(c.precision == MTRL_PRECISION_TF32 || c.precision == MTRL_PRECISION_FP32X3, "sac config: unknown precision %d",
+               c.precision);
   return MTRL_OK;
 }
 
@@ -157,6 +174,12 @@ struct mtrl_sac {
   float* pcgrad_scratch = nullptr;
   const int *pcgrad_perm_critic = nullptr, *pcgrad_perm_actor = nullptr;
   TaskGradCache* tg_active = nullptr;   // set while mtrl_sac_task_grads runs: the backward also fills the (T, P) rows
+  // The reference's split-loss branches (taken when an optimiser requires per-task losses, and by compute_weights) are not
+  // the un-split loss evaluated per task; both differences are reproduced:
+  //   split_critic: a' and log pi(a'|.) are sampled from the actor on data.OBSERVATIONS, not next_observations
+  //                 (mtsac.py:515-523, 995-1003), while the target critics still see next_observations;
+  //   split_actor:  the vmapped actor loss runs with `_explore` at its default True (mtsac.py:631-637, 676-682).
+  bool split_critic = false, split_actor = false;
   comm::Segment *d_segs_critic = nullptr, *d_segs_actor = nullptr;   // ownership tables (device)
   int nsegs_critic = 0, nsegs_actor = 0;
 };
@@ -166,6 +189,12 @@ namespace {
 float* colsum_part(const mtrl_sac* h, int e) {
   return h->ws.colsum_part + static_cast<long long>(e) * (h->cfg.max_rows / 32) * h->cfg.width;
 }
+
+// fp32x3: the tf32 remainder of a workspace operand buffer (nullptr in tf32 mode); works for interior pointers.
+template <typename Ptr>
+Ptr lo(const mtrl_sac* h, Ptr p) { return h->ws.lo_delta ? p + h->ws.lo_delta : nullptr; }
+// ... and of a trunk kernel inside one of the three parameter operand copies
+float* tk_lo(float* base_lo, const mtrl_net_layout_t& L, int e, int l) { return base_lo ? tk(base_lo, L, e, l) : nullptr; }
 
 // Rows [r0, r1) of a hidden-layer kernel (in = W rows) that rank r owns when the trunk is sharded over G ranks.
 void row_block(int W, int G, int r, int* r0, int* r1) {
@@ -208,7 +237,7 @@ void push_dw(mtrl_sac* h, std::vector<mtrl_gemm_problem_t>& dst, const float* X,
              long long off_grads, const mtrl_net_layout_t& L, int e, int l) {
   const int M = h->cfg.max_rows, W = h->cfg.width;
   if (!h->comm || l == 0) {
-    dst.push_back(dw_problem(X, ldx, n_in, dZ, tk(grads, L, e, l), M, W, h->sms, 0));
+    dst.push_back(dw_problem(X, ldx, n_in, dZ, tk(grads, L, e, l), M, W, h->sms, 0, lo(h, X), lo(h, dZ)));
     return;
   }
   const mtrl_comm* c = h->comm;
@@ -218,7 +247,7 @@ void push_dw(mtrl_sac* h, std::vector<mtrl_gemm_problem_t>& dst, const float* X,
     if (r1 <= r0) continue;
     float* owner_grads = reinterpret_cast<float*>(c->peer[r] + off_grads);
     mtrl_gemm_problem_t p = dw_problem(X + r0, ldx, r1 - r0, dZ, tk(owner_grads, L, e, l) + static_cast<long long>(r0) * W, M, W,
-                                       h->sms, 0);
+                                       h->sms, 0, lo(h, X + r0), lo(h, dZ));
     p.epilogue = MTRL_EPI_ATOMIC_ADD;   // every rank adds its rows' contribution (the buffer is zeroed per update)
     // MTRL_REMOTE_FIRST=1 (experiment): deal the tiles whose reduce-adds cross NVLink first so the transfers overlap the
     // launch's other tiles.  Measured SLOWER at 2 GPUs (2.04 vs 1.98 ms/step: the long dX units then go last and unbalance
@@ -237,6 +266,8 @@ int build_backward_plans(mtrl_sac* h) {
   const int Ka = h->lay.k_actor, Kc = h->lay.k_critic;
   float* ash = h->buf.actor_shadow;
   float* csh = h->buf.critic_shadow;
+  float* ash_lo = w.ash_lo;
+  float* csh_lo = w.csh_lo;
   for (auto* v : {&h->bwd_critic, &h->bwd_pi, &h->bwd_actor}) {
     for (auto* p : *v) mtrl_gemm_plan_destroy(p);
     v->clear();
@@ -251,8 +282,10 @@ int build_backward_plans(mtrl_sac* h) {
     }
     for (int e = 0; e < E; ++e) {
       if (l > 0) {
-        pc.push_back(dx_problem(w.G[e][src], tk(csh, LC, e, l), W, w.bits_C[e][l - 1], w.G[e][dst], M, W, colsum_part(h, e)));
-        ppi.push_back(dx_problem(w.G[e][src], tk(csh, LC, e, l), W, w.bits_C[e][l - 1], w.G[e][dst], M, W, nullptr));
+        pc.push_back(dx_problem(w.G[e][src], tk(csh, LC, e, l), W, w.bits_C[e][l - 1], w.G[e][dst], M, W, colsum_part(h, e),
+                                lo(h, w.G[e][src]), tk_lo(csh_lo, LC, e, l), lo(h, w.G[e][dst])));
+        ppi.push_back(dx_problem(w.G[e][src], tk(csh, LC, e, l), W, w.bits_C[e][l - 1], w.G[e][dst], M, W, nullptr,
+                                 lo(h, w.G[e][src]), tk_lo(csh_lo, LC, e, l), lo(h, w.G[e][dst])));
       } else {
         // actor step: only dL/da = first action_dim input columns of dZ_0 W_0^T (N = 16 rows of W_0)
         mtrl_gemm_problem_t p;
@@ -264,12 +297,16 @@ int build_backward_plans(mtrl_sac* h) {
         p.M = M; p.N = 16; p.K = W; p.block_n = 16;
         p.k_splits = W >= 1024 ? 8 : (W >= 256 ? 2 : 1);
         p.epilogue = p.k_splits > 1 ? MTRL_EPI_ATOMIC_ADD : MTRL_EPI_STORE;
+        p.A_lo = lo(h, w.G[e][src]);
+        p.B_lo = tk_lo(csh_lo, LC, e, 0);
         ppi.push_back(p);
       }
     }
     push_dw(h, pa, l == 0 ? w.Xa : w.Ao[l - 1], l == 0 ? Ka : W, l == 0 ? LA.in_dim : W, w.G[0][src], h->buf.actor_grads,
             h->off_actor_grads, LA, 0, l);
-    if (l > 0) pa.push_back(dx_problem(w.G[0][src], tk(ash, LA, 0, l), W, w.bits_Ao[l - 1], w.G[0][dst], M, W, colsum_part(h, 0)));
+    if (l > 0)
+      pa.push_back(dx_problem(w.G[0][src], tk(ash, LA, 0, l), W, w.bits_Ao[l - 1], w.G[0][dst], M, W, colsum_part(h, 0),
+                              lo(h, w.G[0][src]), tk_lo(ash_lo, LA, 0, l), lo(h, w.G[0][dst])));
     MTRL_PROPAGATE(make_plan(h->bwd_critic, pc));
     MTRL_PROPAGATE(make_plan(h->bwd_pi, ppi));
     MTRL_PROPAGATE(make_plan(h->bwd_actor, pa));
@@ -287,25 +324,30 @@ int build_plans(mtrl_sac* h) {
   float* ash = h->buf.actor_shadow;
   float* csh = h->buf.critic_shadow;
   float* tsh = h->buf.critic_target_shadow;
+  // forward problem of one trunk layer: input / kernel / output with their fp32x3 remainders (null in tf32 mode)
+  auto fwd = [&](float* X0, float* Hprev, int K0, int in_dim, float* sh, float* sh_lo, float* params, const mtrl_net_layout_t& L,
+                 int e, int l, float* out, unsigned* bits) {
+    float* X = l == 0 ? X0 : Hprev;
+    return fwd_problem(X, l == 0 ? K0 : W, l == 0 ? in_dim : W, tk(sh, L, e, l), tb(params, L, e, l), out, M, W, bits, lo(h, X),
+                       tk_lo(sh_lo, L, e, l), lo(h, out));
+  };
   for (int l = 0; l < D; ++l) {
     std::vector<mtrl_gemm_problem_t> p;
-    const int K = l == 0 ? Ka : W;
-    p.push_back(fwd_problem(l == 0 ? w.Xa_next : w.An[l - 1], K, l == 0 ? LA.in_dim : W, tk(ash, LA, 0, l),
-                            tb(h->buf.actor_params, LA, 0, l), w.An[l], M, W));
-    p.push_back(fwd_problem(l == 0 ? w.Xa : w.Ao[l - 1], K, l == 0 ? LA.in_dim : W, tk(ash, LA, 0, l),
-                            tb(h->buf.actor_params, LA, 0, l), w.Ao[l], M, W, l + 1 < D ? w.bits_Ao[l] : nullptr));
+    p.push_back(fwd(w.Xa_next, l ? w.An[l - 1] : nullptr, Ka, LA.in_dim, ash, w.ash_lo, h->buf.actor_params, LA, 0, l, w.An[l], nullptr));
+    p.push_back(fwd(w.Xa, l ? w.Ao[l - 1] : nullptr, Ka, LA.in_dim, ash, w.ash_lo, h->buf.actor_params, LA, 0, l, w.Ao[l],
+                    l + 1 < D ? w.bits_Ao[l] : nullptr));
     for (int e = 0; e < E; ++e)
-      p.push_back(fwd_problem(l == 0 ? w.Xc : w.C[e][l - 1], l == 0 ? Kc : W, l == 0 ? LC.in_dim : W, tk(csh, LC, e, l),
-                              tb(h->buf.critic_params, LC, e, l), w.C[e][l], M, W, l + 1 < D ? w.bits_C[e][l] : nullptr));
+      p.push_back(fwd(w.Xc, l ? w.C[e][l - 1] : nullptr, Kc, LC.in_dim, csh, w.csh_lo, h->buf.critic_params, LC, e, l, w.C[e][l],
+                      l + 1 < D ? w.bits_C[e][l] : nullptr));
     MTRL_PROPAGATE(make_plan(h->fwd, p));
   }
   for (int l = 0; l < D; ++l) {
     std::vector<mtrl_gemm_problem_t> p, q;
     for (int e = 0; e < E; ++e) {
-      p.push_back(fwd_problem(l == 0 ? w.Xc_next : w.Tg[e][l - 1], l == 0 ? Kc : W, l == 0 ? LC.in_dim : W,
-                              tk(tsh, LC, e, l), tb(h->buf.critic_target, LC, e, l), w.Tg[e][l], M, W));
-      q.push_back(fwd_problem(l == 0 ? w.Xc : w.C[e][l - 1], l == 0 ? Kc : W, l == 0 ? LC.in_dim : W, tk(csh, LC, e, l),
-                              tb(h->buf.critic_params, LC, e, l), w.C[e][l], M, W, l + 1 < D ? w.bits_C[e][l] : nullptr));
+      p.push_back(fwd(w.Xc_next, l ? w.Tg[e][l - 1] : nullptr, Kc, LC.in_dim, tsh, w.tsh_lo, h->buf.critic_target, LC, e, l, w.Tg[e][l],
+                      nullptr));
+      q.push_back(fwd(w.Xc, l ? w.C[e][l - 1] : nullptr, Kc, LC.in_dim, csh, w.csh_lo, h->buf.critic_params, LC, e, l, w.C[e][l],
+                      l + 1 < D ? w.bits_C[e][l] : nullptr));
     }
     MTRL_PROPAGATE(make_plan(h->fwd_target, p));
     MTRL_PROPAGATE(make_plan(h->fwd_pi, q));
@@ -360,6 +402,7 @@ void launch_actor_head_rows(const ActorHeadArgs& a, int action_dim, dim3 grid, d
 int launch_actor_head(mtrl_sac* h, const float* H, const float* eps, float* Xdst, float* logp, bool save, cudaStream_t st) {
   const mtrl_sac_config_t& c = h->cfg;
   ActorHeadArgs a;
+  a.h_lo_delta = h->ws.lo_delta;
   a.H = H;
   a.Wh = hk(h->buf.actor_params, h->lay.actor, 0);
   a.bh = hb(h->buf.actor_params, h->lay.actor, 0);
@@ -368,6 +411,7 @@ int launch_actor_head(mtrl_sac* h, const float* H, const float* eps, float* Xdst
   a.row_task = nullptr;
   a.eps = eps;
   a.Xdst = Xdst;
+  a.xdst_lo_delta = h->ws.lo_delta;
   a.ldx = h->lay.k_critic;
   a.act = save ? h->ws.act : nullptr;
   a.logp = logp;
@@ -504,7 +548,7 @@ extern "C" int mtrl_sac_query_layout(const mtrl_sac_config_t* cfg, mtrl_sac_layo
                   cfg->depth);
   out->k_actor = static_cast<int>(round_up(cfg->obs_dim, 32));
   out->k_critic = static_cast<int>(round_up(cfg->action_dim + cfg->obs_dim, 32));
-  out->workspace_bytes = carve(*cfg, out->k_actor, out->k_critic, nullptr, nullptr);
+  out->workspace_bytes = carve(*cfg, out->k_actor, out->k_critic, out->actor.total, out->critic.total, nullptr, nullptr);
   return MTRL_OK;
 }
 
@@ -525,7 +569,7 @@ extern "C" int mtrl_sac_create(mtrl_sac_t** out, const mtrl_sac_config_t* cfg, c
       return MTRL_ERR_INVALID;
     }
   }
-  carve(*cfg, h->lay.k_actor, h->lay.k_critic, static_cast<uint8_t*>(b->workspace), &h->ws);
+  carve(*cfg, h->lay.k_actor, h->lay.k_critic, h->lay.actor.total, h->lay.critic.total, static_cast<uint8_t*>(b->workspace), &h->ws);
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, dev);
@@ -566,9 +610,9 @@ extern "C" void mtrl_sac_destroy(mtrl_sac_t* h) {
 extern "C" int mtrl_sac_refresh_shadows(mtrl_sac_t* h, void* stream) {
   MTRL_REQUIRE(h, "mtrl_sac_refresh_shadows: null handle");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  shadow_kernel<<<h->sms * 4, 256, 0, st>>>(h->buf.actor_params, h->buf.actor_shadow, h->lay.actor.total);
-  shadow_kernel<<<h->sms * 4, 256, 0, st>>>(h->buf.critic_params, h->buf.critic_shadow, h->lay.critic.total);
-  shadow_kernel<<<h->sms * 4, 256, 0, st>>>(h->buf.critic_target, h->buf.critic_target_shadow, h->lay.critic.total);
+  shadow_kernel<<<h->sms * 4, 256, 0, st>>>(h->buf.actor_params, h->buf.actor_shadow, h->ws.ash_lo, h->lay.actor.total);
+  shadow_kernel<<<h->sms * 4, 256, 0, st>>>(h->buf.critic_params, h->buf.critic_shadow, h->ws.csh_lo, h->lay.critic.total);
+  shadow_kernel<<<h->sms * 4, 256, 0, st>>>(h->buf.critic_target, h->buf.critic_target_shadow, h->ws.tsh_lo, h->lay.critic.total);
   MTRL_CUDA_CHECK(cudaGetLastError());
   return MTRL_OK;
 }
@@ -620,10 +664,12 @@ int step_begin(mtrl_sac* h, const float* obs, const float* actions, const float*
   a.obs = obs; a.actions = actions; a.next_obs = next_obs; a.dones = dones; a.rewards = rewards;
   a.eps_c = eps_c; a.eps_a = eps_a;
   a.Xa_next = w.Xa_next; a.Xa = w.Xa; a.Xc_next = w.Xc_next; a.Xc = w.Xc;
-  a.rew = w.rew; a.done = w.done; a.peps_c = w.eps_c; a.peps_a = w.eps_a;
+  a.rew = w.rew; a.done = w.done; a.peps_c = w.eps_c; a.peps_a = w.eps_a; a.act_data = w.act_data;
   a.slot_src = w.slot_src;
   a.noise_counter = h->buf.steps + 3;
   a.seed = c.noise_seed;
+  a.noise_stream = static_cast<unsigned long long>(c.task_begin);
+  a.lo_delta = w.lo_delta;
   a.obs_dim = c.obs_dim; a.act_dim = c.action_dim; a.Ka = h->lay.k_actor; a.Kc = h->lay.k_critic;
   mtrl_launch(pack_rows_kernel, M, dim3(128), 0, st, a);
   LAUNCHED(h);
@@ -639,7 +685,7 @@ int step_critic_grads(mtrl_sac* h, cudaStream_t st) {
   Workspace& w = h->ws;
   const mtrl_net_layout_t& LC = h->lay.critic;
   const int M = c.max_rows, W = c.width, D = c.depth, E = c.num_critics;
-  MTRL_PROPAGATE(launch_actor_head(h, w.An[D - 1], w.eps_c, w.Xc_next, w.logp_next, false, st));
+  MTRL_PROPAGATE(launch_actor_head(h, h->split_critic ? w.Ao[D - 1] : w.An[D - 1], w.eps_c, w.Xc_next, w.logp_next, false, st));
   for (int l = 0; l < D; ++l) MTRL_PROPAGATE(run_plan(h, h->fwd_target[l], st));
   {
     CriticLossArgs a;
@@ -656,6 +702,7 @@ int step_critic_grads(mtrl_sac* h, cudaStream_t st) {
     a.rew = w.rew; a.done = w.done; a.logp_next = w.logp_next; a.alpha_val = w.alpha_val; a.task_w = w.task_w;
     a.dq = w.dq; a.acc = w.acc;
     a.M = M; a.W = W; a.E = E;
+    a.h_lo_delta = w.lo_delta;
     a.gamma = c.gamma;
     const float B = static_cast<float>(h->global_batch);
     // MT-SAC: L = mean over (E, B) of (q-y)^2 (mtsac.py:565); SAC: L = 0.5 * sum_e mean_b (q-y)^2 (sac.py:292)
@@ -677,7 +724,7 @@ int step_critic_grads(mtrl_sac* h, cudaStream_t st) {
       a.dbh[e] = hb(h->buf.critic_grads, LC, e);
       a.colsum[e] = colsum_part(h, e);
     }
-    a.seg_start = w.seg_start; a.M = M; a.W = W;
+    a.seg_start = w.seg_start; a.M = M; a.W = W; a.dz_lo_delta = w.lo_delta;
     MTRL_PROPAGATE(launch_head_bwd(h, a, 1, E, st));
   }
   if (h->comm) {
@@ -706,6 +753,7 @@ int step_critic_apply(mtrl_sac* h, cudaStream_t st) {
     memset(&t, 0, sizeof(t));
     t.p = h->buf.critic_params; t.m = h->buf.critic_m; t.v = h->buf.critic_v; t.shadow = h->buf.critic_shadow;
     t.g = h->buf.critic_grads; t.target = h->buf.critic_target; t.target_shadow = h->buf.critic_target_shadow;
+    t.shadow_lo = w.csh_lo; t.target_shadow_lo = w.tsh_lo;
     t.n = LC.total; t.trunk_n = LC.trunk_total;
     t.step = h->buf.steps + 1;
     t.g2_trunk_out = w.acc + ACC_CRITIC_G2; t.p2_trunk = w.acc + ACC_CRITIC_P2_TRUNK; t.p2_head = w.acc + ACC_CRITIC_P2_HEAD;
@@ -721,8 +769,10 @@ int step_critic_apply(mtrl_sac* h, cudaStream_t st) {
   mtrl_launch(sumsq_kernel, dim3(h->sms * 2), dim3(256), 0, st, h->buf.critic_grads, LC.trunk_total, w.acc + ACC_CRITIC_G2);
   LAUNCHED(h);
   AdamArgs a;
+  memset(&a, 0, sizeof(a));
   a.p = h->buf.critic_params; a.m = h->buf.critic_m; a.v = h->buf.critic_v; a.shadow = h->buf.critic_shadow;
   a.g = h->buf.critic_grads; a.target = h->buf.critic_target; a.target_shadow = h->buf.critic_target_shadow;
+  a.shadow_lo = w.csh_lo; a.target_shadow_lo = w.tsh_lo;
   a.n = LC.total; a.trunk_n = LC.trunk_total;
   a.g2_trunk = w.acc + ACC_CRITIC_G2; a.g2_heads = h->buf.critic_grads + LC.slots_off;
   a.step = h->buf.steps + 1;
@@ -748,7 +798,7 @@ int step_actor_sample(mtrl_sac* h, bool write_x, cudaStream_t st) {
 int step_write_actions(mtrl_sac* h, cudaStream_t st) {
   const mtrl_sac_config_t& c = h->cfg;
   write_actions_kernel<<<(c.max_rows * c.action_dim + 255) / 256, 256, 0, st>>>(h->ws.act, h->ws.Xc, h->lay.k_critic,
-                                                                                c.max_rows, c.action_dim);
+                                                                                c.max_rows, c.action_dim, h->ws.lo_delta);
   MTRL_CUDA_CHECK(cudaGetLastError());
   LAUNCHED(h);
   return MTRL_OK;
@@ -776,7 +826,7 @@ int step_actor_grads(mtrl_sac* h, cudaStream_t st) {
       a.online.b[e] = hb(h->buf.critic_params, LC, e);
     }
     a.tile_task = w.tile_task; a.slot_src = w.slot_src; a.logp = w.logp; a.alpha_val = w.alpha_val; a.task_w = w.task_w;
-    a.dq = w.dq; a.acc = w.acc; a.M = M; a.W = W; a.E = E; a.inv_b = inv_b;
+    a.dq = w.dq; a.acc = w.acc; a.M = M; a.W = W; a.E = E; a.inv_b = inv_b; a.h_lo_delta = w.lo_delta;
     mtrl_launch(actor_loss_kernel, dim3((M + 7) / 8), dim3(256), 0, st, a);
     MTRL_CUDA_CHECK(cudaGetLastError());
     LAUNCHED(h);
@@ -790,7 +840,7 @@ int step_actor_grads(mtrl_sac* h, cudaStream_t st) {
       a.Wh[e] = hk(h->buf.critic_params, LC, e);
       a.dZ[e] = w.G[e][0];
     }
-    a.seg_start = w.seg_start; a.M = M; a.W = W;
+    a.seg_start = w.seg_start; a.M = M; a.W = W; a.dz_lo_delta = w.lo_delta;
     MTRL_PROPAGATE(launch_head_bwd(h, a, 1, E, st));
   }
   MTRL_PROPAGATE(run_trunk_backward(h, h->bwd_pi, nullptr, LC, E, false, st));
@@ -798,6 +848,7 @@ int step_actor_grads(mtrl_sac* h, cudaStream_t st) {
     ActorDoutArgs a;
     a.dXin = w.dXin; a.act = w.act; a.logstd = w.logstd; a.eps = w.eps_a; a.alpha_val = w.alpha_val; a.task_w = w.task_w;
     a.inrange = w.inrange; a.tile_task = w.tile_task; a.slot_src = w.slot_src; a.dout = w.dout;
+    a.act_data = w.act_data; a.explore = h->split_actor ? 1 : 0; a.acc = w.acc;
     a.M = M; a.E = E; a.A = c.action_dim; a.inv_b = inv_b;
     mtrl_launch(actor_dout_kernel, dim3((M + 127) / 128), dim3(128), 0, st, a);
     MTRL_CUDA_CHECK(cudaGetLastError());
@@ -813,7 +864,7 @@ int step_actor_grads(mtrl_sac* h, cudaStream_t st) {
     a.dWh[0] = hk(h->buf.actor_grads, LA, 0);
     a.dbh[0] = hb(h->buf.actor_grads, LA, 0);
     a.colsum[0] = colsum_part(h, 0);
-    a.seg_start = w.seg_start; a.M = M; a.W = W;
+    a.seg_start = w.seg_start; a.M = M; a.W = W; a.dz_lo_delta = w.lo_delta;
     MTRL_PROPAGATE(launch_head_bwd(h, a, 2 * c.action_dim, 1, st));
   }
   MTRL_PROPAGATE(run_trunk_backward(h, h->bwd_actor, h->buf.actor_grads, LA, 1, true, st));
@@ -830,13 +881,14 @@ int step_actor_apply(mtrl_sac* h, cudaStream_t st) {
     memset(&t, 0, sizeof(t));
     t.p = h->buf.actor_params; t.m = h->buf.actor_m; t.v = h->buf.actor_v; t.shadow = h->buf.actor_shadow;
     t.g = h->buf.actor_grads;
+    t.shadow_lo = w.ash_lo;
     t.n = LA.total; t.trunk_n = LA.trunk_total;
     t.step = h->buf.steps + 0;
     t.g2_trunk_out = w.acc + ACC_ACTOR_G2; t.p2_trunk = w.acc + ACC_ACTOR_P2_TRUNK; t.p2_head = w.acc + ACC_ACTOR_P2_HEAD;
     t.lr = c.actor_lr; t.b1 = c.adam_b1; t.b2 = c.adam_b2; t.eps = c.adam_eps; t.max_norm = c.actor_max_grad_norm;
     MTRL_PROPAGATE(launch_trunk_step(h, t, h->off_actor_grads, h->off_actor_params, h->d_segs_actor, h->nsegs_actor, st));
     mtrl_launch(finalize_actor_kernel, dim3(1), dim3(1), 0, st, w.acc, h->buf.actor_grads + LA.slots_off + 1, h->buf.steps, h->buf.logs,
-                                           1.f / static_cast<float>(h->global_batch), 0);
+                                           1.f / static_cast<float>(h->global_batch), 0, 1.f / static_cast<float>(c.action_dim));
     LAUNCHED(h);
     MTRL_CUDA_CHECK(cudaGetLastError());
     return MTRL_OK;
@@ -844,8 +896,10 @@ int step_actor_apply(mtrl_sac* h, cudaStream_t st) {
   mtrl_launch(sumsq_kernel, dim3(h->sms * 2), dim3(256), 0, st, h->buf.actor_grads, LA.trunk_total, w.acc + ACC_ACTOR_G2);
   LAUNCHED(h);
   AdamArgs a;
+  memset(&a, 0, sizeof(a));
   a.p = h->buf.actor_params; a.m = h->buf.actor_m; a.v = h->buf.actor_v; a.shadow = h->buf.actor_shadow;
   a.g = h->buf.actor_grads; a.target = nullptr; a.target_shadow = nullptr;
+  a.shadow_lo = w.ash_lo;
   a.n = LA.total; a.trunk_n = LA.trunk_total;
   a.g2_trunk = w.acc + ACC_ACTOR_G2; a.g2_heads = h->buf.actor_grads + LA.slots_off;
   a.step = h->buf.steps + 0;
@@ -854,7 +908,8 @@ int step_actor_apply(mtrl_sac* h, cudaStream_t st) {
   mtrl_launch(adam_kernel, dim3(h->sms * 4), dim3(256), 0, st, a);
   LAUNCHED(h);
   mtrl_launch(finalize_actor_kernel, dim3(1), dim3(1), 0, st, w.acc, h->buf.actor_grads + LA.slots_off, h->buf.steps, h->buf.logs,
-                                         1.f / static_cast<float>(h->global_batch), c.variant == MTRL_VARIANT_SAC);
+                                         1.f / static_cast<float>(h->global_batch), c.variant == MTRL_VARIANT_SAC,
+                                         1.f / static_cast<float>(c.action_dim));
   LAUNCHED(h);
   MTRL_CUDA_CHECK(cudaGetLastError());
   return MTRL_OK;
@@ -979,20 +1034,23 @@ extern "C" int mtrl_sac_act(mtrl_sac_t* h, const float* obs, int n, const float*
     std::vector<mtrl_gemm_plan_t*> plans;
     for (int l = 0; l < D; ++l) {
       std::vector<mtrl_gemm_problem_t> p;
-      p.push_back(fwd_problem(l == 0 ? w.Xa : w.Ao[l - 1], l == 0 ? Ka : W, l == 0 ? LA.in_dim : W, tk(h->buf.actor_shadow, LA, 0, l),
-                              tb(h->buf.actor_params, LA, 0, l), w.Ao[l], n, W));
+      float* X = l == 0 ? w.Xa : w.Ao[l - 1];
+      p.push_back(fwd_problem(X, l == 0 ? Ka : W, l == 0 ? LA.in_dim : W, tk(h->buf.actor_shadow, LA, 0, l),
+                              tb(h->buf.actor_params, LA, 0, l), w.Ao[l], n, W, nullptr, lo(h, X), tk_lo(w.ash_lo, LA, 0, l),
+                              lo(h, w.Ao[l])));
       MTRL_PROPAGATE(make_plan_plain(plans, p));   // created lazily on the caller's stream: no timing launches here
     }
     it = h->act_plans.emplace(n, plans).first;
   }
   MTRL_CUDA_CHECK(cudaMemsetAsync(w.status, 0, 16, st));
   act_pack_kernel<<<n, 128, 0, st>>>(obs, n, c.obs_dim, Ka, c.num_tasks, c.task_begin, c.num_local_tasks, eps, deterministic,
-                                     c.action_dim, c.noise_seed, h->act_calls++, w.Xa, w.slot_src, w.eps_a, w.status);
+                                     c.action_dim, c.noise_seed, h->act_calls++, w.Xa, w.slot_src, w.eps_a, w.status, w.lo_delta);
   MTRL_CUDA_CHECK(cudaGetLastError());
   for (auto* plan : it->second) MTRL_PROPAGATE(mtrl_gemm_plan_run(plan, st));
   ActorHeadArgs a;
   memset(&a, 0, sizeof(a));
   a.H = w.Ao[D - 1];
+  a.h_lo_delta = w.lo_delta;
   a.Wh = hk(h->buf.actor_params, LA, 0);
   a.bh = hb(h->buf.actor_params, LA, 0);
   a.row_task = w.slot_src;
@@ -1066,14 +1124,14 @@ int ensure_task_plans(mtrl_sac* h, float* critic_tg, float* actor_tg, int R) {
         for (int t = 0; t < T; ++t) {
           const float* X = (l == 0 ? w.Xc : w.C[e][l - 1]) + static_cast<long long>(t) * R * (l == 0 ? Kc : W);
           float* out = tk(critic_tg + static_cast<long long>(t) * LC.total, LC, e, l);
-          pc.push_back(dw_problem(X, l == 0 ? Kc : W, l == 0 ? LC.in_dim : W, w.G[e][src] + static_cast<long long>(t) * R * W, out, R, W,
-                                  h->sms, 0));
+          const float* dZt = w.G[e][src] + static_cast<long long>(t) * R * W;
+          pc.push_back(dw_problem(X, l == 0 ? Kc : W, l == 0 ? LC.in_dim : W, dZt, out, R, W, h->sms, 0, lo(h, X), lo(h, dZt)));
         }
       for (int t = 0; t < T; ++t) {
         const float* X = (l == 0 ? w.Xa : w.Ao[l - 1]) + static_cast<long long>(t) * R * (l == 0 ? Ka : W);
         float* out = tk(actor_tg + static_cast<long long>(t) * LA.total, LA, 0, l);
-        pa.push_back(dw_problem(X, l == 0 ? Ka : W, l == 0 ? LA.in_dim : W, w.G[0][src] + static_cast<long long>(t) * R * W, out, R, W,
-                                h->sms, 0));
+        const float* dZt = w.G[0][src] + static_cast<long long>(t) * R * W;
+        pa.push_back(dw_problem(X, l == 0 ? Ka : W, l == 0 ? LA.in_dim : W, dZt, out, R, W, h->sms, 0, lo(h, X), lo(h, dZt)));
       }
       for (auto* pr : {&pc, &pa}) {
         std::vector<mtrl_gemm_plan_t*> launches;
@@ -1146,7 +1204,9 @@ int update_with_pcgrad(mtrl_sac* h, const float* obs, const float* actions, cons
   MTRL_CUDA_CHECK(cudaGetLastError());
   if (h->pcgrad_critic) MTRL_CUDA_CHECK(cudaMemsetAsync(tc.critic_tg, 0, static_cast<size_t>(T) * LC.total * sizeof(float), st));
   h->tg_active = &tc;
+  h->split_critic = h->pcgrad_critic;   // split_critic_losses = the critic optimiser's requires_split_task_losses (mtsac.py:273)
   int rc = step_critic_grads(h, st);
+  h->split_critic = false;
   h->tg_active = nullptr;
   MTRL_PROPAGATE(rc);
   if (h->pcgrad_critic) {
@@ -1158,7 +1218,9 @@ int update_with_pcgrad(mtrl_sac* h, const float* obs, const float* actions, cons
   MTRL_PROPAGATE(step_actor_sample(h, true, st));
   if (h->pcgrad_actor) MTRL_CUDA_CHECK(cudaMemsetAsync(tc.actor_tg, 0, static_cast<size_t>(T) * LA.total * sizeof(float), st));
   h->tg_active = &tc;
+  h->split_actor = h->pcgrad_actor;     // split_actor_losses (mtsac.py:272)
   rc = step_actor_grads(h, st);
+  h->split_actor = false;
   h->tg_active = nullptr;
   MTRL_PROPAGATE(rc);
   if (h->pcgrad_actor) {
@@ -1323,7 +1385,9 @@ extern "C" int mtrl_sac_task_grads(mtrl_sac_t* h, const float* obs, const float*
   check_balanced_kernel<<<1, 64, 0, st>>>(w.seg_start, w.slot_src, T, R, batch / T, w.status);
   MTRL_CUDA_CHECK(cudaGetLastError());
   h->tg_active = &tc;
+  h->split_critic = true;   // compute_weights samples a' on split_data.observations too (mtsac.py:995-1003); no explore term there
   int rc = step_critic_grads(h, st);
+  h->split_critic = false;
   if (rc == MTRL_OK) {
     task_heads_kernel<<<dim3(T, E), 256, 0, st>>>(h->buf.critic_grads, critic_tg, LC.total, LC.heads_base, LC.member_head_stride,
                                                   LC.head_kernel_off, LC.head_bias_off, W * 1, 1);

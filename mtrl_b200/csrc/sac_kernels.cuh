@@ -21,6 +21,7 @@ enum {
   ACC_QLOSS = 0, ACC_QSUM, ACC_CRITIC_G2, ACC_CRITIC_P2_TRUNK, ACC_CRITIC_P2_HEAD, ACC_CRITIC_HEAD_G2,
   ACC_ACTOR_LOSS, ACC_ACTOR_G2, ACC_ACTOR_P2_TRUNK, ACC_ACTOR_P2_HEAD, ACC_ACTOR_HEAD_G2,
   ACC_CRITIC_P2_OLD, ACC_ACTOR_P2_OLD,   // squared norm of the parameters BEFORE the step (sac.py:360-364 logs those)
+  ACC_EXPLORE,                           // sum over rows and action dims of (a_data - a_pi)^2 (split actor loss, mtsac.py:668-673)
   ACC_COUNT = 16
 };
 
@@ -150,11 +151,22 @@ static __global__ void pack_plan_kernel(int B, int T_local, int max_rows, int* _
 struct PackArgs {
   const float *obs, *actions, *next_obs, *dones, *rewards, *eps_c, *eps_a;
   float *Xa_next, *Xa, *Xc_next, *Xc, *rew, *done, *peps_c, *peps_a;
+  float* act_data;                   // [M][A] the batch actions in packed order, unrounded (explore term of the split actor loss)
   const int* slot_src;
   const int* noise_counter;
   unsigned long long seed;
+  unsigned long long noise_stream;   // mixed into the Philox subsequence: the first task this handle owns (shards draw
+                                     // independent noise although they share the seed, which initialises the trunk)
+  long long lo_delta;                // fp32x3: the tf32 remainder of X[i] goes to X[i + lo_delta] (0 = tf32 mode)
   int obs_dim, act_dim, Ka, Kc;
 };
+
+// Store an operand value as its tf32 hi part and, in fp32x3 mode, the remainder at p[lo_delta].
+__device__ __forceinline__ void store_operand(float* p, long long lo_delta, float v) {
+  const float hi = tf32_rna(v);
+  *p = hi;
+  if (lo_delta) p[lo_delta] = tf32_lo(v, hi);
+}
 
 // One block per packed row.  Inputs are rounded to tf32 here (they are GEMM A operands).
 static __global__ void pack_rows_kernel(const PackArgs a) {
@@ -166,27 +178,27 @@ static __global__ void pack_rows_kernel(const PackArgs a) {
   float* xan = a.Xa_next + static_cast<long long>(slot) * a.Ka;
   float* xc = a.Xc + static_cast<long long>(slot) * a.Kc;
   float* xcn = a.Xc_next + static_cast<long long>(slot) * a.Kc;
+  const long long ld = a.lo_delta;
   if (src < 0) {
-    for (int j = threadIdx.x; j < a.Ka; j += blockDim.x) { xa[j] = 0.f; xan[j] = 0.f; }
-    for (int j = threadIdx.x; j < a.Kc; j += blockDim.x) { xc[j] = 0.f; xcn[j] = 0.f; }
-    if (threadIdx.x < A) { a.peps_c[slot * A + threadIdx.x] = 0.f; a.peps_a[slot * A + threadIdx.x] = 0.f; }
+    for (int j = threadIdx.x; j < a.Ka; j += blockDim.x) { store_operand(xa + j, ld, 0.f); store_operand(xan + j, ld, 0.f); }
+    for (int j = threadIdx.x; j < a.Kc; j += blockDim.x) { store_operand(xc + j, ld, 0.f); store_operand(xcn + j, ld, 0.f); }
+    if (threadIdx.x < A) { a.peps_c[slot * A + threadIdx.x] = 0.f; a.peps_a[slot * A + threadIdx.x] = 0.f; a.act_data[slot * A + threadIdx.x] = 0.f; }
     if (threadIdx.x == 0) { a.rew[slot] = 0.f; a.done[slot] = 0.f; }
     return;
   }
+  if (threadIdx.x < A) a.act_data[slot * A + threadIdx.x] = a.actions[static_cast<long long>(src) * A + threadIdx.x];
   const float* o = a.obs + static_cast<long long>(src) * od;
   const float* on = a.next_obs + static_cast<long long>(src) * od;
   for (int j = threadIdx.x; j < a.Ka; j += blockDim.x) {
-    const float v = j < od ? tf32_rna(o[j]) : 0.f;
-    const float vn = j < od ? tf32_rna(on[j]) : 0.f;
-    xa[j] = v;
-    xan[j] = vn;
+    store_operand(xa + j, ld, j < od ? o[j] : 0.f);
+    store_operand(xan + j, ld, j < od ? on[j] : 0.f);
   }
   for (int j = threadIdx.x; j < a.Kc; j += blockDim.x) {
     float v = 0.f, vn = 0.f;
-    if (j < A) v = tf32_rna(a.actions[static_cast<long long>(src) * A + j]);   // (action, state) order, networks.py:61
-    else if (j < A + od) { v = tf32_rna(o[j - A]); vn = tf32_rna(on[j - A]); }
-    xc[j] = v;
-    xcn[j] = vn;  // action columns of the next-state input are filled by the actor sample
+    if (j < A) v = a.actions[static_cast<long long>(src) * A + j];   // (action, state) order, networks.py:61
+    else if (j < A + od) { v = o[j - A]; vn = on[j - A]; }
+    store_operand(xc + j, ld, v);
+    store_operand(xcn + j, ld, vn);  // action columns of the next-state input are filled by the actor sample
   }
   if (threadIdx.x == 0) {
     a.rew[slot] = a.rewards[src];
@@ -198,7 +210,8 @@ static __global__ void pack_rows_kernel(const PackArgs a) {
       }
     } else {
       curandStatePhilox4_32_10_t st;
-      curand_init(a.seed, static_cast<unsigned long long>(src), static_cast<unsigned long long>(*a.noise_counter) * 32ull, &st);
+      curand_init(a.seed, (a.noise_stream << 32) | static_cast<unsigned long long>(src),
+                  static_cast<unsigned long long>(*a.noise_counter) * 32ull, &st);
       for (int d = 0; d < A; d += 4) {
         const float4 n = curand_normal4(&st);
         const float nn[4] = {n.x, n.y, n.z, n.w};
@@ -219,11 +232,12 @@ static __global__ void pack_rows_kernel(const PackArgs a) {
 static __global__ void act_pack_kernel(const float* __restrict__ obs, int n, int obs_dim, int Ka, int T, int task_begin,
                                        int T_local, const float* __restrict__ eps_in, int deterministic, int A,
                                        unsigned long long seed, unsigned long long call, float* __restrict__ Xa,
-                                       int* __restrict__ row_task, float* __restrict__ eps_out, int* __restrict__ status) {
+                                       int* __restrict__ row_task, float* __restrict__ eps_out, int* __restrict__ status,
+                                       long long lo_delta) {
   const int row = blockIdx.x;
   const float* o = obs + static_cast<long long>(row) * obs_dim;
   float* xa = Xa + static_cast<long long>(row) * Ka;
-  for (int j = threadIdx.x; j < Ka; j += blockDim.x) xa[j] = j < obs_dim ? tf32_rna(o[j]) : 0.f;
+  for (int j = threadIdx.x; j < Ka; j += blockDim.x) store_operand(xa + j, lo_delta, j < obs_dim ? o[j] : 0.f);
   if (threadIdx.x < 32) {
     const int lane = threadIdx.x;
     const float* oh = o + (obs_dim - T);
@@ -247,9 +261,10 @@ static __global__ void act_pack_kernel(const float* __restrict__ obs, int n, int
       } else if (deterministic) {
         for (int d = 0; d < A; ++d) eps_out[row * A + d] = 0.f;
       } else {
-        // subsequences above 2^40 are never used by the update's noise (one subsequence per batch row)
+        // subsequences above 2^60 are never used by the update's noise ((first owned task << 32) | batch row)
         curandStatePhilox4_32_10_t st;
-        curand_init(seed, (1ull << 40) + static_cast<unsigned long long>(row), call * 8ull, &st);
+        curand_init(seed, (1ull << 60) + (static_cast<unsigned long long>(task_begin) << 32) + static_cast<unsigned long long>(row),
+                    call * 8ull, &st);
         for (int d = 0; d < A; d += 4) {
           const float4 z = curand_normal4(&st);
           const float zz[4] = {z.x, z.y, z.z, z.w};
@@ -292,6 +307,7 @@ static __global__ void alpha_prep_kernel(const float* __restrict__ log_alpha, in
 // One warp per packed row.
 // ---------------------------------------------------------------------------------------------
 struct ActorHeadArgs {
+  long long h_lo_delta;  // fp32x3: H[i + h_lo_delta] is the tf32 remainder of H[i]; the heads then see hi + lo (0 = tf32 mode)
   const float* H;        // [M][W] last trunk activation
   const float* Wh;       // (T_local, W, 2A)
   const float* bh;       // (T_local, 2A)
@@ -301,6 +317,7 @@ struct ActorHeadArgs {
                          // rows are not packed into per-task tiles)
   const float* eps;      // [M][A] packed
   float* Xdst;           // critic input buffer whose columns [0, A) receive tf32(a)
+  long long xdst_lo_delta;  // fp32x3: the remainder of a goes to Xdst[... + xdst_lo_delta] (0 = tf32 mode)
   int ldx;
   float* act;            // [M][A] (may be null)
   float* logp;           // [M]
@@ -324,7 +341,7 @@ static __global__ void actor_head_kernel(const ActorHeadArgs p) {
     const float* h = p.H + static_cast<long long>(row) * p.W;
     const float* w = p.Wh + static_cast<long long>(t) * p.W * (2 * A);
     for (int k = lane; k < p.W; k += 32) {
-      const float hv = h[k];
+      const float hv = p.h_lo_delta ? h[k] + h[k + p.h_lo_delta] : h[k];
       const float* wk = w + static_cast<long long>(k) * (2 * A);
 #pragma unroll
       for (int j = 0; j < 2 * A; ++j) acc[j] = fmaf(hv, __ldg(wk + j), acc[j]);
@@ -356,7 +373,7 @@ static __global__ void actor_head_kernel(const ActorHeadArgs p) {
       lp = -0.5f * e * e - 0.91893853320467274f - ls - fldj;
       if (ls_raw > p.ls_min && ls_raw < p.ls_max) mask = 1u << d;
     }
-    if (p.Xdst) p.Xdst[static_cast<long long>(row) * p.ldx + d] = tf32_rna(a);
+    if (p.Xdst) store_operand(p.Xdst + static_cast<long long>(row) * p.ldx + d, p.xdst_lo_delta, a);
     if (p.act) p.act[row * A + d] = a;
     if (p.logstd) p.logstd[row * A + d] = ls;
   }
@@ -441,6 +458,19 @@ static __global__ void __launch_bounds__(256) actor_head_tile_kernel(const Actor
           a[u] = k4 < W4 ? h0[k4] : make_float4(0.f, 0.f, 0.f, 0.f);
           b[u] = k4 < W4 ? h1[k4] : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        if (p.h_lo_delta) {
+          const float4* l0 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(h0) + p.h_lo_delta);
+          const float4* l1 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(h1) + p.h_lo_delta);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int k4 = kb + 32 * u;
+            if (k4 < W4) {
+              const float4 x = l0[k4], y = l1[k4];
+              a[u].x += x.x; a[u].y += x.y; a[u].z += x.z; a[u].w += x.w;
+              b[u].x += y.x; b[u].y += y.y; b[u].z += y.z; b[u].w += y.w;
+            }
+          }
+        }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const int k4 = kb + 32 * u;
@@ -485,7 +515,7 @@ static __global__ void __launch_bounds__(256) actor_head_tile_kernel(const Actor
           lp = -0.5f * e * e - 0.91893853320467274f - ls - fldj;
           if (ls_raw > p.ls_min && ls_raw < p.ls_max) mask = 1u << d;
         }
-        if (p.Xdst) p.Xdst[static_cast<long long>(row) * p.ldx + d] = tf32_rna(a);
+        if (p.Xdst) store_operand(p.Xdst + static_cast<long long>(row) * p.ldx + d, p.xdst_lo_delta, a);
         if (p.act) p.act[row * A + d] = a;
         if (p.logstd) p.logstd[row * A + d] = ls;
       }
@@ -501,9 +531,10 @@ static __global__ void __launch_bounds__(256) actor_head_tile_kernel(const Actor
 
 // Copy saved policy actions into the action columns of the critic input (single-task SAC samples them before the
 // critic step, whose backward still needs the buffer actions there).
-static __global__ void write_actions_kernel(const float* __restrict__ act, float* __restrict__ X, int ldx, int M, int A) {
+static __global__ void write_actions_kernel(const float* __restrict__ act, float* __restrict__ X, int ldx, int M, int A,
+                                            long long lo_delta) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < M * A) X[static_cast<long long>(i / A) * ldx + (i % A)] = tf32_rna(act[i]);
+  if (i < M * A) store_operand(X + static_cast<long long>(i / A) * ldx + (i % A), lo_delta, act[i]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -517,8 +548,18 @@ struct QHeads {
 
 // N row-by-vector dot products at once (one warp, lanes stride the float4 columns): every pass issues the 2N loads of
 // 4 column groups before any arithmetic, so a warp keeps 8N 16-byte loads in flight instead of one dependent pair.
+__device__ __forceinline__ float4 ld_hi_lo(const float* h, int k4, long long lo_delta) {
+  float4 a = reinterpret_cast<const float4*>(h)[k4];
+  if (lo_delta) {
+    const float4 l = reinterpret_cast<const float4*>(h + lo_delta)[k4];
+    a.x += l.x; a.y += l.y; a.z += l.z; a.w += l.w;
+  }
+  return a;
+}
+
 template <int N>
-__device__ __forceinline__ void row_dots(const float* const (&h)[N], const float* const (&w)[N], int W, int lane, float (&out)[N]) {
+__device__ __forceinline__ void row_dots(const float* const (&h)[N], const float* const (&w)[N], int W, int lane, float (&out)[N],
+                                         long long h_lo_delta = 0) {
   float s[N];
 #pragma unroll
   for (int n = 0; n < N; ++n) s[n] = 0.f;
@@ -530,7 +571,7 @@ __device__ __forceinline__ void row_dots(const float* const (&h)[N], const float
     for (int n = 0; n < N; ++n)
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        a[n][u] = reinterpret_cast<const float4*>(h[n])[kb + 32 * u];
+        a[n][u] = ld_hi_lo(h[n], kb + 32 * u, h_lo_delta);
         c[n][u] = __ldg(reinterpret_cast<const float4*>(w[n]) + kb + 32 * u);
       }
 #pragma unroll
@@ -542,7 +583,7 @@ __device__ __forceinline__ void row_dots(const float* const (&h)[N], const float
   for (; kb < W4; kb += 32) {
 #pragma unroll
     for (int n = 0; n < N; ++n) {
-      const float4 a = reinterpret_cast<const float4*>(h[n])[kb];
+      const float4 a = ld_hi_lo(h[n], kb, h_lo_delta);
       const float4 c = __ldg(reinterpret_cast<const float4*>(w[n]) + kb);
       s[n] = fmaf(a.x, c.x, fmaf(a.y, c.y, fmaf(a.z, c.z, fmaf(a.w, c.w, s[n]))));
     }
@@ -551,11 +592,12 @@ __device__ __forceinline__ void row_dots(const float* const (&h)[N], const float
   for (int n = 0; n < N; ++n) out[n] = warp_sum(s[n]);
 }
 
-__device__ __forceinline__ float row_dot(const float* __restrict__ h, const float* __restrict__ w, int W, int lane) {
+__device__ __forceinline__ float row_dot(const float* __restrict__ h, const float* __restrict__ w, int W, int lane,
+                                         long long h_lo_delta = 0) {
   const float* const hh[1] = {h};
   const float* const ww[1] = {w};
   float o[1];
-  row_dots<1>(hh, ww, W, lane, o);
+  row_dots<1>(hh, ww, W, lane, o, h_lo_delta);
   return o[0];
 }
 
@@ -569,6 +611,7 @@ struct CriticLossArgs {
   int M, W, E;
   float gamma, dq_scale;  // dL/dQ_e = dq_scale * w * (Q_e - y)
   int clip;
+  long long h_lo_delta;   // fp32x3: remainders of the activations (see ActorHeadArgs)
 };
 
 // y = r + (1-d) gamma (min_e Qbar_e - alpha logp')   (mtsac.py:547-553)
@@ -592,7 +635,7 @@ static __global__ void critic_loss_kernel(const CriticLossArgs p) {
         const float* const hh[2] = {p.target.H[e] + ro, p.online.H[e] + ro};
         const float* const ww[2] = {p.target.w[e] + wo, p.online.w[e] + wo};
         float o[2];
-        row_dots<2>(hh, ww, p.W, lane, o);
+        row_dots<2>(hh, ww, p.W, lane, o, p.h_lo_delta);
         qt_min = fminf(qt_min, o[0] + p.target.b[e][t]);
         q[e] = o[1] + p.online.b[e][t];
       }
@@ -639,6 +682,7 @@ struct ActorLossArgs {
   double* acc;
   int M, W, E;
   float inv_b;  // 1 / B_global
+  long long h_lo_delta;
 };
 
 // L = mean_b w (alpha logp - min_e Q_e(s, a))   (mtsac.py:659-666); min routes the gradient to the arg-min.
@@ -660,7 +704,7 @@ static __global__ void actor_loss_kernel(const ActorLossArgs p) {
       const float* const hh[2] = {p.online.H[0] + ro, p.online.H[1] + ro};
       const float* const ww[2] = {p.online.w[0] + wo, p.online.w[1] + wo};
       float o[2];
-      row_dots<2>(hh, ww, p.W, lane, o);
+      row_dots<2>(hh, ww, p.W, lane, o, p.h_lo_delta);
       q[0] = o[0] + p.online.b[0][t];
       q[1] = o[1] + p.online.b[1][t];
       qmin = fminf(q[0], q[1]);
@@ -668,7 +712,7 @@ static __global__ void actor_loss_kernel(const ActorLossArgs p) {
 #pragma unroll
       for (int e = 0; e < kMaxE; ++e) {
         if (e < p.E) {
-          q[e] = row_dot(p.online.H[e] + ro, p.online.w[e] + wo, p.W, lane) + p.online.b[e][t];
+          q[e] = row_dot(p.online.H[e] + ro, p.online.w[e] + wo, p.W, lane, p.h_lo_delta) + p.online.b[e][t];
           qmin = fminf(qmin, q[e]);
         }
       }
@@ -702,30 +746,48 @@ struct ActorDoutArgs {
   const int* tile_task;
   const int* slot_src;
   float* dout;         // [M][2A]
+  // split actor loss (gradient-surgery optimisers): the reference's vmapped call leaves `_explore` at its default True
+  // (mtsac.py:631-637, 676-682), so every task's loss also carries  - mean_{rows, dims} (a_data - a_pi)^2
+  const float* act_data;   // [M][A] batch actions, packed
+  int explore;
+  double* acc;
   int M, E, A;
   float inv_b;
 };
 
 static __global__ void actor_dout_kernel(const ActorDoutArgs p) {
   MTRL_PDL_PROLOGUE();
+  __shared__ double red[32];
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= p.M) return;
   const int A = p.A;
-  if (p.slot_src[row] < 0) {
-    for (int j = 0; j < 2 * A; ++j) p.dout[row * 2 * A + j] = 0.f;
-    return;
+  double ex = 0.0;
+  if (row < p.M) {
+    if (p.slot_src[row] < 0) {
+      for (int j = 0; j < 2 * A; ++j) p.dout[row * 2 * A + j] = 0.f;
+    } else {
+      const int t = p.tile_task[row / kTileRows];
+      const float gl = p.alpha_val[t] * p.task_w[t] * p.inv_b;
+      const unsigned m = p.inrange[row];
+      const float gex = 2.f * p.inv_b / static_cast<float>(A);   // d/da of -(1/(B A)) sum (a_data - a)^2 = gex (a_data - a)
+      for (int d = 0; d < A; ++d) {
+        float da = 0.f;
+        for (int e = 0; e < p.E; ++e) da += p.dXin[(static_cast<long long>(e) * p.M + row) * 16 + d];
+        const float a = p.act[row * A + d];
+        if (p.explore) {
+          const float diff = p.act_data[row * A + d] - a;
+          da += gex * diff;
+          ex += static_cast<double>(diff * diff);
+        }
+        const float gx = da * (1.f - a * a) + gl * 2.f * a;
+        const float sd = expf(p.logstd[row * A + d]);
+        p.dout[row * 2 * A + d] = gx;
+        p.dout[row * 2 * A + A + d] = ((m >> d) & 1u) ? (gx * sd * p.eps[row * A + d] - gl) : 0.f;
+      }
+    }
   }
-  const int t = p.tile_task[row / kTileRows];
-  const float gl = p.alpha_val[t] * p.task_w[t] * p.inv_b;
-  const unsigned m = p.inrange[row];
-  for (int d = 0; d < A; ++d) {
-    float da = 0.f;
-    for (int e = 0; e < p.E; ++e) da += p.dXin[(static_cast<long long>(e) * p.M + row) * 16 + d];
-    const float a = p.act[row * A + d];
-    const float gx = da * (1.f - a * a) + gl * 2.f * a;
-    const float sd = expf(p.logstd[row * A + d]);
-    p.dout[row * 2 * A + d] = gx;
-    p.dout[row * 2 * A + A + d] = ((m >> d) & 1u) ? (gx * sd * p.eps[row * A + d] - gl) : 0.f;
+  if (p.explore) {
+    ex = block_sum(ex, red);
+    if (threadIdx.x == 0) atomicAdd(p.acc + ACC_EXPLORE, ex);
   }
 }
 
@@ -747,6 +809,7 @@ struct HeadBwdArgs {
   float* dbh[kMaxE];
   float* colsum[kMaxE];       // may be null: [M/128][W] column sums of dZ per 128-row tile (trunk bias gradient partials)
   const int* seg_start;
+  long long dz_lo_delta;      // fp32x3: remainder of dZ at dZ[... + dz_lo_delta]; column sums then use the unrounded values
   int M, W;
 };
 
@@ -786,6 +849,13 @@ static __global__ void __launch_bounds__(RG * 32, ((RG == 8 && HD <= 8) || HD <=
         const int rr = warp * RPW + c0;
 #pragma unroll
         for (int r = 0; r < 8; ++r) h4[r] = *reinterpret_cast<const float4*>(H + static_cast<long long>(base + rr + r) * p.W + k);
+        if (p.dz_lo_delta) {   // fp32x3: the activation is hi + lo (both buffers mirror each other at dz_lo_delta)
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const float4 l = *reinterpret_cast<const float4*>(H + p.dz_lo_delta + static_cast<long long>(base + rr + r) * p.W + k);
+            h4[r].x += l.x; h4[r].y += l.y; h4[r].z += l.z; h4[r].w += l.w;
+          }
+        }
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           const float hv[4] = {h4[r].x, h4[r].y, h4[r].z, h4[r].w};
@@ -799,12 +869,17 @@ static __global__ void __launch_bounds__(RG * 32, ((RG == 8 && HD <= 8) || HD <=
               dz[c] = fmaf(d, w[j][c], dz[c]);
             }
           }
+          float dlo[4];
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            dz[c] = hv[c] > 0.f ? tf32_rna(dz[c]) : 0.f;
-            csum[c] += dz[c];
+            const float full = hv[c] > 0.f ? dz[c] : 0.f;
+            dz[c] = tf32_rna(full);
+            dlo[c] = tf32_lo(full, dz[c]);
+            csum[c] += p.dz_lo_delta ? full : dz[c];
           }
-          *reinterpret_cast<float4*>(dZ + static_cast<long long>(base + rr + r) * p.W + k) = make_float4(dz[0], dz[1], dz[2], dz[3]);
+          float* dzp = dZ + static_cast<long long>(base + rr + r) * p.W + k;
+          *reinterpret_cast<float4*>(dzp) = make_float4(dz[0], dz[1], dz[2], dz[3]);
+          if (p.dz_lo_delta) *reinterpret_cast<float4*>(dzp + p.dz_lo_delta) = make_float4(dlo[0], dlo[1], dlo[2], dlo[3]);
         }
       }
     }
@@ -1364,6 +1439,7 @@ struct AdamArgs {
   float *p, *m, *v, *shadow;
   const float* g;
   float *target, *target_shadow;     // null for networks without a target
+  float *shadow_lo, *target_shadow_lo;   // fp32x3: tf32 remainders of the operand copies (null in tf32 mode)
   long long n;
   long long trunk_n;                 // elements [0, trunk_n) count into the trunk param norm, the rest into the head norm;
                                      // [trunk_n, trunk_n + 32) are the reduction slots, not parameters
@@ -1400,7 +1476,7 @@ static __global__ void adam_kernel(const AdamArgs a) {
     if (a.target) t4 = reinterpret_cast<const float4*>(a.target)[i];
     const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
     float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w}, pp[4] = {p4.x, p4.y, p4.z, p4.w};
-    float tt[4] = {t4.x, t4.y, t4.z, t4.w}, sh[4], tsh[4];
+    float tt[4] = {t4.x, t4.y, t4.z, t4.w}, sh[4], tsh[4], shl[4], tshl[4];
     float sq = 0.f;
     s_old += static_cast<double>(p4.x * p4.x + p4.y * p4.y + p4.z * p4.z + p4.w * p4.w);
 #pragma unroll
@@ -1410,17 +1486,21 @@ static __global__ void adam_kernel(const AdamArgs a) {
       vv[q] = a.b2 * vv[q] + (1.f - a.b2) * g * g;
       pp[q] = pp[q] - a.lr * (mm[q] / bc1) / (sqrtf(vv[q] / bc2) + a.eps);
       sh[q] = tf32_rna(pp[q]);
+      shl[q] = tf32_lo(pp[q], sh[q]);
       tt[q] = a.tau * pp[q] + (1.f - a.tau) * tt[q];
       tsh[q] = tf32_rna(tt[q]);
+      tshl[q] = tf32_lo(tt[q], tsh[q]);
       sq += pp[q] * pp[q];
     }
     reinterpret_cast<float4*>(a.m)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
     reinterpret_cast<float4*>(a.v)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
     reinterpret_cast<float4*>(a.p)[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
     reinterpret_cast<float4*>(a.shadow)[i] = make_float4(sh[0], sh[1], sh[2], sh[3]);
+    if (a.shadow_lo) reinterpret_cast<float4*>(a.shadow_lo)[i] = make_float4(shl[0], shl[1], shl[2], shl[3]);
     if (a.target) {
       reinterpret_cast<float4*>(a.target)[i] = make_float4(tt[0], tt[1], tt[2], tt[3]);
       reinterpret_cast<float4*>(a.target_shadow)[i] = make_float4(tsh[0], tsh[1], tsh[2], tsh[3]);
+      if (a.target_shadow_lo) reinterpret_cast<float4*>(a.target_shadow_lo)[i] = make_float4(tshl[0], tshl[1], tshl[2], tshl[3]);
     }
     if (i < slot4) s_trunk += static_cast<double>(sq);
     else s_head += static_cast<double>(sq);
@@ -1435,9 +1515,13 @@ static __global__ void adam_kernel(const AdamArgs a) {
   }
 }
 
-static __global__ void shadow_kernel(const float* __restrict__ p, float* __restrict__ s, long long n) {
+static __global__ void shadow_kernel(const float* __restrict__ p, float* __restrict__ s, float* __restrict__ s_lo, long long n) {
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) s[i] = tf32_rna(p[i]);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float hi = tf32_rna(p[i]);
+    s[i] = hi;
+    if (s_lo) s_lo[i] = tf32_lo(p[i], hi);
+  }
 }
 
 // Single thread: turn accumulators into the reference's log scalars and advance the Adam count.
@@ -1455,15 +1539,19 @@ static __global__ void finalize_critic_kernel(const double* acc, const float* g2
   steps[1] += 1;
 }
 static __global__ void finalize_actor_kernel(const double* acc, const float* g2_heads, int* steps, float* logs, float inv_b,
-                                      int log_old_norm) {
+                                      int log_old_norm, float inv_a) {
   MTRL_PDL_PROLOGUE();
-  logs[MTRL_LOG_ACTOR_LOSS] = static_cast<float>(acc[ACC_ACTOR_LOSS] * inv_b);
+  // split actor loss: every task's loss is reduced by its explore term (ACC_EXPLORE stays 0 otherwise); the log is the
+  // mean over tasks (mtsac.py:704 actor_loss_value.mean(); the reference's explore_loss log is the per-task vector, whose
+  // mean this is)
+  const double explore = acc[ACC_EXPLORE] * inv_b * inv_a;
+  logs[MTRL_LOG_ACTOR_LOSS] = static_cast<float>(acc[ACC_ACTOR_LOSS] * inv_b - explore);
   logs[MTRL_LOG_ACTOR_GRAD_MAGNITUDE] = static_cast<float>(sqrt(acc[ACC_ACTOR_G2] + static_cast<double>(*g2_heads)));
   logs[MTRL_LOG_ACTOR_PARAMS_NORM] = static_cast<float>(
       sqrt(log_old_norm ? acc[ACC_ACTOR_P2_OLD] : acc[ACC_ACTOR_P2_TRUNK] + acc[ACC_ACTOR_P2_HEAD]));
   logs[LOG_X_ACTOR_P2_TRUNK] = static_cast<float>(acc[ACC_ACTOR_P2_TRUNK]);
   logs[LOG_X_ACTOR_P2_HEAD] = static_cast<float>(acc[ACC_ACTOR_P2_HEAD]);
-  logs[MTRL_LOG_EXPLORE_LOSS] = 0.f;  // explore=False (mtsac.py:277, 671)
+  logs[MTRL_LOG_EXPLORE_LOSS] = static_cast<float>(explore);  // 0 on the non-split path: explore=False (mtsac.py:277, 671)
   steps[0] += 1;
   steps[3] += 1;  // noise counter
 }

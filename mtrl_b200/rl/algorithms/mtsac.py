@@ -51,7 +51,21 @@ class SacConfigC(C.Structure):
         ("actor_max_grad_norm", C.c_float), ("critic_max_grad_norm", C.c_float), ("alpha_max_grad_norm", C.c_float),
         ("log_std_min", C.c_float), ("log_std_max", C.c_float), ("target_entropy", C.c_float),
         ("clip_q", C.c_int), ("use_task_weights", C.c_int), ("noise_seed", C.c_ulonglong), ("variant", C.c_int),
+        ("precision", C.c_int),
     ]
+
+
+PRECISIONS = {"tf32": 0, "fp32x3": 1}   # MTRL_PRECISION_* (include/mtrl_b200.h)
+
+
+def precision_code(precision: str | None) -> int:
+    """`precision` argument of the agents' initialize(): "tf32" (default; MTRL_PRECISION overrides the default) rounds the
+    trunk-GEMM operands to tf32 as XLA does for f32 dots on NVIDIA GPUs; "fp32x3" splits every operand into two tf32
+    values and runs three tensor-core passes, the numerics of the reference's fp32 CPU path at 3x the GEMM time."""
+    name = precision if precision is not None else os.environ.get("MTRL_PRECISION", "tf32")
+    if name not in PRECISIONS:
+        raise ValueError(f"precision must be one of {sorted(PRECISIONS)}, got {name!r}")
+    return PRECISIONS[name]
 
 
 class NetLayoutC(C.Structure):
@@ -230,12 +244,13 @@ class MTSAC:
     @staticmethod
     def initialize(config: MTSACConfig, env_config, seed: int = 1, *, max_batch: int | None = None,
                    max_rows: int | None = None, rank: int = 0, world_size: int = 1, process_group=None,
-                   device: str | torch.device | None = None, exchange: str = "p2p") -> "MTSAC":
+                   device: str | torch.device | None = None, exchange: str = "p2p", precision: str | None = None) -> "MTSAC":
         """mtsac.py:152-284.  `env_config` needs `.observation_space.shape` and `.action_space.shape`
         (the observation includes the one-hot task id).  `max_batch` bounds the rows one update may
         pass (default 128 per local task, the reference's batch).  rank/world_size shard the tasks;
         `exchange` picks how the ranks sum trunk gradients: "p2p" = the fused peer-memory kernel
-        (csrc/comm.cuh, sharded Adam, no library collective), "nccl" = all-reduce between the phases."""
+        (csrc/comm.cuh, sharded Adam, no library collective), "nccl" = all-reduce between the phases.
+        `precision`: "tf32" or "fp32x3" (see `precision_code`)."""
         if exchange not in ("p2p", "nccl", "local"):
             raise ValueError(f"exchange must be 'p2p', 'nccl' or 'local', got {exchange!r}")
         # "local" skips the exchange altogether: one rank's share of the kernels for profiling on a single GPU
@@ -287,7 +302,9 @@ class MTSAC:
             actor_max_grad_norm=nm(a_opt.max_grad_norm), critic_max_grad_norm=nm(c_opt.max_grad_norm),
             alpha_max_grad_norm=nm(t_opt.max_grad_norm), log_std_min=config.actor_config.log_std_min,
             log_std_max=config.actor_config.log_std_max, target_entropy=self.target_entropy,
-            clip_q=int(config.clip), use_task_weights=int(config.use_task_weights), noise_seed=int(seed) & (2**63 - 1))
+            clip_q=int(config.clip), use_task_weights=int(config.use_task_weights), noise_seed=int(seed) & (2**63 - 1),
+            precision=precision_code(precision))
+        self.precision = "fp32x3" if self._cfg.precision else "tf32"
         self._allocate(dev, t_local)
         lay = self._lay
 

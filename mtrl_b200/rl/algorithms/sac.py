@@ -21,7 +21,7 @@ from ...config.optim import OptimizerConfig
 from ...config.rl import AlgorithmConfig
 from ...nn.multi_head import _kernel_init, uniform
 from ...config.utils import Activation, Initializer
-from .mtsac import MTSAC, SacConfigC, TrainState, _tree_copy_
+from .mtsac import MTSAC, SacConfigC, TrainState, _tree_copy_, precision_code
 
 SAC_LOG_KEYS = (
     "losses/alpha_loss", "alpha", "losses/qf_values", "losses/qf_loss", "metrics/critic_grad_magnitude",
@@ -66,7 +66,7 @@ class SAC(MTSAC):
 
     @staticmethod
     def initialize(config: SACConfig, env_config, seed: int = 1, *, max_batch: int = 1280,
-                   device: str | torch.device | None = None) -> "SAC":
+                   device: str | torch.device | None = None, precision: str | None = None) -> "SAC":
         """sac.py:118-200.  `max_batch` bounds the rows one update may pass (reference batch: 1280)."""
         if not torch.cuda.is_available():
             raise L.MtrlError("SAC needs a CUDA device; there is no CPU fallback")
@@ -101,7 +101,8 @@ class SAC(MTSAC):
             adam_eps=a_opt.eps, actor_max_grad_norm=nm(a_opt.max_grad_norm), critic_max_grad_norm=nm(c_opt.max_grad_norm),
             alpha_max_grad_norm=nm(t_opt.max_grad_norm), log_std_min=config.actor_config.log_std_min,
             log_std_max=config.actor_config.log_std_max, target_entropy=self.target_entropy, clip_q=0, use_task_weights=0,
-            noise_seed=int(seed) & (2**63 - 1), variant=1)
+            noise_seed=int(seed) & (2**63 - 1), variant=1, precision=precision_code(precision))
+        self.precision = "fp32x3" if self._cfg.precision else "tf32"
         self._allocate(dev, 1)
         lay = self._lay
 

@@ -14,12 +14,17 @@ import torch
 from . import mtsac_oracle as O
 
 
-def _targets(state: O.OracleState, batch, eps_c, cfg: O.OracleConfig):
+def _targets(state: O.OracleState, batch, eps_c, cfg: O.OracleConfig, split: bool = True):
+    """Bellman targets.  `split=True` restates the reference's split / compute_weights branches LITERALLY: there a' and
+    log pi(a') are sampled from the actor on `data.observations` (mtsac.py:515-520, 995-999) although the target critics
+    are then evaluated on `data.next_observations` (:521-523, 1000-1002); the un-split branch (:526-536) uses
+    next_observations for both.  (The reference draws that noise with one key under jax.vmap, i.e. the same draw for
+    every task; here the noise is the caller's `eps_c`.)"""
     obs, actions, next_obs, dones, rewards = batch
     T = cfg.num_tasks
     alpha_vals = torch.exp(obs[..., -T:] @ state.log_alpha.reshape(-1, 1))
-    with torch.no_grad():   # mtsac.py:995-1006 / :526-553: target computed once from the current actor and target critic
-        next_actions, next_logp = O.actor_sample_and_log_prob(state.actor, next_obs, eps_c, cfg)
+    with torch.no_grad():   # mtsac.py:995-1006 / :515-553: target computed once from the current actor and target critic
+        next_actions, next_logp = O.actor_sample_and_log_prob(state.actor, obs if split else next_obs, eps_c, cfg)
         q_t = O.critic_forward(state.critic_target, next_obs, next_actions, cfg)
         target = rewards + (1 - dones) * cfg.gamma * (q_t.min(dim=0).values - alpha_vals * next_logp.reshape(-1, 1))
         if cfg.clip:
@@ -43,27 +48,39 @@ def critic_task_grads(critic: dict, batch, target, cfg: O.OracleConfig) -> list:
     return out
 
 
-def actor_task_grads(actor: dict, critic: dict, batch, alpha_vals, eps_a, cfg: O.OracleConfig):
+def actor_task_grads(actor: dict, critic: dict, batch, alpha_vals, eps_a, cfg: O.OracleConfig, explore: bool = False,
+                     return_losses: bool = False):
     """Per-task gradients of the actor loss (:1049-1069 / :631-666) against the given critic parameters; also returns
-    the (detached) log-probs in batch order, which the temperature step consumes."""
-    obs = batch[0]
+    the (detached) log-probs in batch order, which the temperature step consumes.  `explore=True` is the split branch of
+    `update_actor`: its vmapped call passes four arguments, so `_explore` keeps its default True (:631-637, 676-682) and
+    each task's loss is reduced by mean((data.actions - action_samples)^2) (:668-673).  compute_weights' own actor loss
+    (:1049-1069) has no such term."""
+    obs, actions = batch[0], batch[1]
     task = obs[..., -cfg.num_tasks:].argmax(dim=-1)
     out, logp_all = [], torch.zeros(obs.shape[0], dtype=obs.dtype)
+    losses, explores = [], []
     for t in range(cfg.num_tasks):
         rows = task == t
         ap = O._with_grad(actor)
         a, logp = O.actor_sample_and_log_prob(ap, obs[rows], eps_a[rows], cfg)
         q_pi = O.critic_forward(critic, obs[rows], a, cfg)
-        (alpha_vals[rows] * logp.reshape(-1, 1) - q_pi.min(dim=0).values).mean().backward()
+        loss = (alpha_vals[rows] * logp.reshape(-1, 1) - q_pi.min(dim=0).values).mean()
+        exp_loss = ((actions[rows] - a) ** 2).mean() if explore else torch.zeros((), dtype=obs.dtype)
+        loss = loss - exp_loss
+        loss.backward()
         out.append(O._grads_of(ap))
         logp_all[rows] = logp.detach()
+        losses.append(loss.detach())
+        explores.append(exp_loss.detach())
+    if return_losses:
+        return out, logp_all, torch.stack(losses), torch.stack(explores)
     return out, logp_all
 
 
 def per_task_grads(state: O.OracleState, batch, eps_c, eps_a, cfg: O.OracleConfig):
     """compute_weights (:870-1170): {'critic': [tree per task], 'actor': [tree per task]}; the actor loss is taken
     against the CURRENT critic parameters (:1060-1062)."""
-    alpha_vals, target = _targets(state, batch, eps_c, cfg)
+    alpha_vals, target = _targets(state, batch, eps_c, cfg, split=True)
     return {"critic": critic_task_grads(state.critic, batch, target, cfg),
             "actor": actor_task_grads(state.actor, state.critic, batch, alpha_vals, eps_a, cfg)[0]}
 
@@ -246,11 +263,14 @@ def mtsac_update_pcgrad(state: O.OracleState, batch, eps_c, eps_a, cfg: O.Oracle
                         critic: bool = True, actor: bool = True, surgery: str = "pcgrad", gradnorm_clip: bool = False):
     """MTSAC.update (mtsac.py:1173-1251) with split losses and optax.chain(pcgrad, clip_by_global_norm, adam) on the
     chosen networks (surgery="cagrad": cagrad instead, CAGradConfig optim.py:104-124); the other network keeps the plain
-    chain.  Returns (new_state, stats)."""
+    chain.  The split flags follow the reference: split_critic_losses / split_actor_losses are each network's optimiser's
+    `requires_split_task_losses` (mtsac.py:272-273), and the split branches differ from the plain ones (see `_targets` and
+    `actor_task_grads`).  Returns (new_state, stats); stats["logs"] holds actor_loss / explore_loss as update_actor logs
+    them (:704-709; explore_loss as the mean of the reference's per-task vector)."""
     obs = batch[0]
     T = cfg.num_tasks
     opt = dict(state.opt)
-    alpha_vals, target = _targets(state, batch, eps_c, cfg)
+    alpha_vals, target = _targets(state, batch, eps_c, cfg, split=critic)
     stats = {}
     ctg = critic_task_grads(state.critic, batch, target, cfg)
     if critic:
@@ -262,7 +282,9 @@ def mtsac_update_pcgrad(state: O.OracleState, batch, eps_c, eps_a, cfg: O.Oracle
     new_critic, opt["critic"] = O.adam_step(state.critic, cgrads, opt["critic"], cfg.lr, cfg.adam_eps, cfg.b1, cfg.b2,
                                             cfg.max_grad_norm)
     new_target = O.tree_map(lambda n, t: cfg.tau * n + (1 - cfg.tau) * t, new_critic, state.critic_target)
-    atg, logp = actor_task_grads(state.actor, new_critic, batch, alpha_vals, eps_a, cfg)
+    atg, logp, a_losses, a_explore = actor_task_grads(state.actor, new_critic, batch, alpha_vals, eps_a, cfg, explore=actor,
+                                                      return_losses=True)
+    stats["logs"] = {"losses/actor_loss": a_losses.mean(), "metrics/explore_loss": a_explore.mean()}
     if actor:
         flat, stats["actor"] = _surgery(surgery, flatten(atg), perm_a, gradnorm_clip)
         agrads = _unflatten(flat, state.actor)

@@ -36,6 +36,49 @@ def make_problem(M, N, K, a_major, b_major, epilogue, block_n=256, k_splits=1, s
     return p, D, ref, keep
 
 
+def split_tf32(x: torch.Tensor):
+    """(hi, lo) with hi = tf32(x), lo = tf32(x - hi): the operand pair of the fp32x3 mode."""
+    hi = tf32_round(x)
+    return hi, tf32_round(x - hi)
+
+
+def make_problem_x3(M, N, K, a_major, b_major, epilogue, block_n=256, k_splits=1, seed=0, dev="cuda", with_d_lo=True):
+    """Same contraction on FULL fp32 operands given as (hi, lo) tf32 pairs; the reference is the fp64 product of the
+    unsplit fp32 values.  Rounding epilogues also emit D_lo (returned) so that D + D_lo is the unrounded result."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    A = torch.randn(M, K, generator=g).to(dev)
+    B = torch.randn(N, K, generator=g).to(dev)
+    bias = torch.randn(N, generator=g).to(dev)
+    mask = torch.randn(M, N, generator=g).to(dev)
+    lay = lambda X, major: X.t().contiguous() if major else X.contiguous()  # noqa: E731
+    (Ah, Al), (Bh, Bl) = split_tf32(A), split_tf32(B)
+    Ah, Al, Bh, Bl = lay(Ah, a_major), lay(Al, a_major), lay(Bh, b_major), lay(Bl, b_major)
+    D = torch.zeros(M, N, device=dev)
+    rounds = epilogue in (L.EPI_BIAS_RELU, L.EPI_RELU_MASK, L.EPI_STORE_TF32)
+    D_lo = torch.zeros(M, N, device=dev) if (rounds and with_d_lo) else None
+    ref = A.double() @ B.double().t()
+    if epilogue == L.EPI_BIAS_RELU:
+        ref = torch.relu(ref + bias.double())
+    elif epilogue == L.EPI_RELU_MASK:
+        ref = ref * (mask > 0)
+    p = L.GemmProblem(
+        A=Ah.data_ptr(), lda=Ah.stride(0), a_major=a_major, B=Bh.data_ptr(), ldb=Bh.stride(0), b_major=b_major,
+        D=D.data_ptr(), ldd=D.stride(0), M=M, N=N, K=K, block_n=block_n, k_splits=k_splits, epilogue=epilogue,
+        bias=bias.data_ptr(), mask=mask.data_ptr(), ldmask=mask.stride(0),
+        A_lo=Al.data_ptr(), B_lo=Bl.data_ptr(), D_lo=D_lo.data_ptr() if D_lo is not None else None,
+    )
+    return p, D, D_lo, ref, (Ah, Al, Bh, Bl, bias, mask)
+
+
+def run_case_x3(case, dev="cuda", with_d_lo=True):
+    name, M, N, K, am, bm, epi, bn, ks = case
+    p, D, D_lo, ref, keep = make_problem_x3(M, N, K, am, bm, epi, bn, ks, dev=dev, with_d_lo=with_d_lo)
+    L.GemmPlan([p]).run()
+    torch.cuda.synchronize()
+    out = D.double() + (D_lo.double() if D_lo is not None else 0)
+    return ((out - ref).norm() / ref.norm().clamp_min(1e-30)).item(), D, D_lo
+
+
 def rel_err(D, ref, epilogue):
     out = D.double()
     if epilogue in (L.EPI_BIAS_RELU, L.EPI_RELU_MASK, L.EPI_STORE_TF32):

@@ -20,6 +20,46 @@ def test_gemm_case(cuda, idx):
     assert rel < 5e-4, f"{case[0]}: rel err {rel}"
 
 
+@pytest.mark.parametrize("idx", range(16))
+def test_gemm_case_fp32x3(cuda, idx):
+    """fp32x3 mode (A_lo / B_lo / D_lo): full fp32 operands as (hi, lo) tf32 pairs, three tensor-core passes; the result
+    (D + D_lo where the epilogue rounds) must match the fp64 product of the UNSPLIT operands to fp32-level accuracy."""
+    import gemm_cases as G
+    import torch
+    from mtrl_b200 import _lib as L
+
+    case = G.CASES[idx]
+    if case[6] in (L.EPI_BIAS_RELU, L.EPI_RELU_MASK, L.EPI_STORE_TF32) and case[7] % 32 != 0:
+        rel, D, _ = G.run_case_x3(case, with_d_lo=False)   # D_lo needs the TMA output path; D alone is tf32-rounded
+        assert rel < 5e-4, f"{case[0]}: rel err {rel}"
+        return
+    rel, D, D_lo = G.run_case_x3(case)
+    assert rel < 3e-6, f"{case[0]}: rel err {rel}"
+    if D_lo is not None:   # D is exactly tf32 and D_lo its (tf32) remainder
+        assert torch.equal(G.tf32_round(D), D) and torch.equal(G.tf32_round(D_lo), D_lo)
+        assert float(D_lo.abs().max()) <= float(D.abs().max()) * 2.0 ** -11
+
+
+def test_gemm_grouped_mixed_precision(cuda):
+    """One launch mixing tf32 and fp32x3 problems (with and without D_lo): the staging-box bookkeeping of the epilogue."""
+    import gemm_cases as G
+    import torch
+    from mtrl_b200 import _lib as L
+
+    c = G.CASES
+    p1, D1, ref1, k1 = G.make_problem(*c[3][1:], seed=21)
+    p2, D2, D2lo, ref2, k2 = G.make_problem_x3(*c[3][1:], seed=22)
+    p3, D3, ref3, k3 = G.make_problem(*c[8][1:], seed=23)
+    p4, D4, D4lo, ref4, k4 = G.make_problem_x3(*c[8][1:], seed=24)
+    p5, D5, _, ref5, k5 = G.make_problem_x3(*c[7][1:], seed=25)
+    L.GemmPlan([p1, p2, p3, p4, p5]).run()
+    torch.cuda.synchronize()
+    r = lambda out, ref: float((out.double() - ref).norm() / ref.norm())  # noqa: E731
+    assert r(D1, ref1) < 5e-4 and r(D3, ref3) < 5e-4
+    assert r(D2.double() + D2lo.double(), ref2) < 3e-6 and r(D4.double() + D4lo.double(), ref4) < 3e-6
+    assert r(D5, ref5) < 3e-6
+
+
 def test_gemm_grouped(cuda):
     import gemm_cases as G
 

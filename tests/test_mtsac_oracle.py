@@ -121,10 +121,17 @@ def test_per_task_gradients_average_to_the_batch_gradient():
     st = O.init_state(cfg, seed=4, dtype=torch.float64)
     batch, ec, ea = O.synthetic_batch(cfg, 8, seed=9, dtype=torch.float64)
     _, _, grads, _ = O.mtsac_update(st, batch, ec, ea, cfg, return_grads=True)
-    per = TG.per_task_grads(st, batch, ec, ea, cfg)
-    mean_c = O.tree_map(lambda *xs: sum(xs) / len(xs), *per["critic"])
+    # with the UN-split branch's targets (a' sampled on next_observations, mtsac.py:526-536) the per-task losses are the
+    # batch loss cut by task ...
+    _, target = TG._targets(st, batch, ec, cfg, split=False)
+    mean_c = O.tree_map(lambda *xs: sum(xs) / len(xs), *TG.critic_task_grads(st.critic, batch, target, cfg))
     for a, b in zip(O.tree_leaves(mean_c), O.tree_leaves(grads["critic"])):
         assert torch.allclose(a, b, rtol=1e-9, atol=1e-12)
+    # ... whereas the reference's split / compute_weights branches sample a' on data.observations (mtsac.py:515-520,
+    # 995-999): restated literally, so their mean is NOT the un-split gradient
+    per = TG.per_task_grads(st, batch, ec, ea, cfg)
+    mean_q = O.tree_map(lambda *xs: sum(xs) / len(xs), *per["critic"])
+    assert any(not torch.allclose(a, b, rtol=1e-6, atol=1e-12) for a, b in zip(O.tree_leaves(mean_q), O.tree_leaves(grads["critic"])))
     g = TG.flatten(per["critic"])
     avg, cos = TG.vmap_cos_sim(g)
     assert cos.shape == (3, 3) and torch.allclose(torch.diagonal(cos), torch.ones(3, dtype=torch.float64), atol=1e-6)

@@ -126,9 +126,14 @@ def test_pcgrad_update_matches_oracle(cuda):
     tcfg = dataclasses.replace(cfg, matmul_operands="tf32")
     st64 = st.to(torch.float64)
     new, stats = TG.mtsac_update_pcgrad(st64, tuple(b.double() for b in batch), ec.double(), ea.double(), tcfg, perm_c, perm_a)
-    agent.update(tuple(b.cuda() for b in batch), eps_c=ec.cuda(), eps_a=ea.cuda(), check=True, pcgrad_perm=(perm_c, perm_a))
+    _, logs = agent.update(tuple(b.cuda() for b in batch), eps_c=ec.cuda(), eps_a=ea.cuda(), check=True, pcgrad_perm=(perm_c, perm_a))
     got = agent.pcgrad_stats()
     assert stats["critic"]["n_grad_conflicts"] > 0, "degenerate test: no conflicting task gradients"
+    # the split actor branch carries the explore term (mtsac.py:631-637, 668-682): logged, and part of the actor loss
+    ex_ref, al_ref = float(stats["logs"]["metrics/explore_loss"]), float(stats["logs"]["losses/actor_loss"])
+    assert ex_ref > 1e-2, "degenerate test: no explore term"
+    assert abs(float(logs["metrics/explore_loss"]) - ex_ref) <= 1e-3 * ex_ref
+    assert abs(float(logs["losses/actor_loss"]) - al_ref) <= 1e-3 * abs(al_ref)
     for net in ("critic", "actor"):
         assert float(got[net]["n_grad_conflicts"]) == stats[net]["n_grad_conflicts"], net
         for k in ("avg_grad_magnitude", "avg_grad_magnitude_before_surgery"):
