@@ -301,6 +301,21 @@ int mtrl_sac_enable_cagrad(mtrl_sac_t* h, int critic, int actor, float* critic_t
  * mean per-task norm after clipping. */
 int mtrl_sac_enable_gradnorm(mtrl_sac_t* h, int critic, int actor, int clip_per_task, float* critic_tg, float* actor_tg,
                              float* scratch);
+/* DummyMultiTaskConfig (mtrl/config/optim.py:46-59): optax.chain(dummy_multitask_optimizer(), clip_by_global_norm, adam);
+ * the transformation is the mean over tasks of the per-task gradients (mtrl/optim/dummy.py:5-20) of the split losses. */
+int mtrl_sac_enable_dummy(mtrl_sac_t* h, int critic, int actor, float* critic_tg, float* actor_tg, float* scratch);
+/* The gradient transformations of mtrl/optim as one stand-alone operator (what the optax-protocol objects of
+ * mtrl_b200.optim call): rows (T, ld) device fp32 = per-task gradients (updates with a leading task axis, raveled), P valid
+ * columns (P and ld multiples of 4, T <= 64); out (P) = the transformed gradient:
+ *   kind 0  pcgrad  (mtrl/optim/pcgrad.py:20-136): mean of the sequentially projected rows; perm = device int[T] row
+ *           permutation (:79) or NULL for the identity
+ *   kind 1  cagrad  (mtrl/optim/cagrad.py:20-237) with its defaults
+ *   kind 2  gradnorm (mtrl/optim/gradnorm.py:61-163): sum of the rows, each clipped to unit norm first if clip_per_task
+ *   kind 3  dummy   (mtrl/optim/dummy.py:5-20): mean of the rows
+ * scratch: device fp32, T*T + 2*T + 4 floats = [Gram | weights on the rows | stats[4] | cagrad task weights]; stats as in
+ * mtrl_sac_enable_pcgrad / _cagrad / _gradnorm. */
+int mtrl_task_combine(int kind, const float* rows, long long ld, int T, long long P, const int* perm, int clip_per_task,
+                      float* out, float* scratch, void* stream);
 /* Number of kernels one mtrl_sac_update launches (for bench.py's gpu_launches). */
 int mtrl_sac_launches_per_update(const mtrl_sac_t* h);
 /* Bracket every GEMM launch of the following updates with CUDA events on the launch stream

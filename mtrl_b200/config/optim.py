@@ -1,7 +1,9 @@
-"""Mirror of mtrl/config/optim.py:14-43.  `spawn()` returns the description of
+"""Mirror of mtrl/config/optim.py:14-124.  `spawn()` returns the description of
 optax.chain(clip_by_global_norm(max_grad_norm), adam(lr, eps)) that the fused CUDA optimiser
-(csrc/sac_kernels.cuh adam_kernel) executes; the gradient-surgery configs (optim.py:46-118) keep
-their names; PCGradConfig, CAGradConfig and GradNormConfig are implemented (per-task gradients + the surgery in front of the same chain), the others raise."""
+(csrc/sac_kernels.cuh adam_kernel) executes; the multi-task configs (optim.py:46-124: DummyMultiTaskConfig, PCGradConfig,
+GradNormConfig, CAGradConfig) put their transformation in front of the same chain (per-task gradients of the split losses
++ the transformation in coefficient space).  The transformations themselves are also available as optax-protocol
+objects in `mtrl_b200.optim`."""
 from dataclasses import dataclass
 
 from .utils import Optimizer
@@ -20,6 +22,7 @@ class AdamChainSpec:
     cagrad: bool = False   # optax.chain(cagrad(num_tasks), clip, adam): mtrl/config/optim.py:104-124
     gradnorm: bool = False           # optax.chain(gradnorm(...), clip, adam): mtrl/config/optim.py:79-102
     gradnorm_clip_per_task: bool = False
+    dummy: bool = False    # optax.chain(dummy_multitask_optimizer(), clip, adam): mtrl/config/optim.py:46-59
 
 
 @dataclass(frozen=True, kw_only=True)
@@ -50,10 +53,13 @@ class DummyMultiTaskConfig(OptimizerConfig):   # optim.py:46-59
         return True
 
     def spawn(self) -> AdamChainSpec:
-        """optax.chain(dummy_multitask_optimizer(), OptimizerConfig.spawn()): the dummy transformation averages the
-        per-task gradients (mtrl/optim/dummy.py:18), and with the equal per-task batches the split losses require
-        (mtsac.py:325) that average IS the gradient of the un-split loss -- so the plain fused chain computes it."""
-        return OptimizerConfig.spawn(self)
+        """optax.chain(dummy_multitask_optimizer(), OptimizerConfig.spawn()) as data: the dummy transformation averages
+        the per-task gradients (mtrl/optim/dummy.py:18).  Those are gradients of the reference's SPLIT losses, which differ
+        from the un-split loss (a' sampled on data.observations, mtsac.py:515-523; explore term in the actor loss,
+        :631-637, 676-682), so the fused update takes its split path for this config as well."""
+        import dataclasses
+
+        return dataclasses.replace(OptimizerConfig.spawn(self), dummy=True)
 
 
 @dataclass(frozen=True, kw_only=True)

@@ -170,7 +170,7 @@ struct mtrl_sac {
   } tgc;
   // PCGrad (mtrl_sac_enable_pcgrad): which optimiser chains start with pcgrad, scratch and the row permutations
   bool pcgrad_critic = false, pcgrad_actor = false;
-  int surgery_mode = 0;   // 0: pcgrad, 1: cagrad, 2: gradnorm (3: gradnorm with per-task clipping)
+  int surgery_mode = 0;   // 0: pcgrad, 1: cagrad, 2: gradnorm (3: gradnorm with per-task clipping), 4: dummy (mean)
   float* pcgrad_scratch = nullptr;
   const int *pcgrad_perm_critic = nullptr, *pcgrad_perm_actor = nullptr;
   TaskGradCache* tg_active = nullptr;   // set while mtrl_sac_task_grads runs: the backward also fills the (T, P) rows
@@ -1150,8 +1150,32 @@ int ensure_task_plans(mtrl_sac* h, float* critic_tg, float* actor_tg, int R) {
   return MTRL_OK;
 }
 
-// pcgrad (mtrl/optim/pcgrad.py) on one network's (T, P) matrix: Gram -> projection coefficients -> the averaged
-// projected gradient written over the network's gradient buffer (what the rest of the chain, clip + adam, consumes).
+// One of the reference's multi-task gradient transformations (mtrl/optim/{pcgrad,cagrad,gradnorm,dummy}.py) on a (T, P)
+// matrix of per-task gradients, in coefficient space: Gram matrix -> T weights -> out = sum_k w_k rows[k].
+//   mode 0 pcgrad, 1 cagrad, 2 gradnorm, 3 gradnorm with per-task clipping, 4 dummy (plain mean over tasks)
+//   gscale: rows x sqrt(gscale) are the reference-scale per-task gradients (T^2 inside the update, whose rows are the
+//           full-batch gradient restricted to a task; 1 for rows that already are per-task-mean gradients)
+//   gram (T, T), wts (T), stats (4), tw (T; cagrad's softmax task weights, may be null otherwise): device scratch
+int combine_rows(int sms, int mode, const float* tg, long long ld, int T, long long P, float gscale, const int* perm, float* gram,
+                 float* wts, float* stats, float* tw, float* out, cudaStream_t st) {
+  MTRL_CUDA_CHECK(cudaMemsetAsync(gram, 0, static_cast<size_t>(T) * T * sizeof(float), st));
+  pairwise_kernel<0><<<sms * 2, 256, 0, st>>>(tg, ld, T, P, gram, T, 1.f, 0.f, 0.f);
+  if (mode == 1) {
+    // cagrad(num_tasks) defaults (cagrad.py:20-41): c = 0.5, 21 iterations, lr 25 (< 50 tasks) or 50, momentum 0.5
+    cagrad_coeff_kernel<<<1, 32, (static_cast<size_t>(T) * T + 7 * T) * sizeof(double), st>>>(gram, T, T, gscale, 0.5f, 21,
+                                                                                          T < 50 ? 25.f : 50.f, 0.5f, wts, stats, tw);
+  } else if (mode >= 2) {
+    gradnorm_coeff_kernel<<<1, 64, 0, st>>>(gram, T, T, gscale, mode == 3, mode == 4, wts, stats);
+  } else {
+    pcgrad_coeff_kernel<<<1, 64, 2 * T * T * sizeof(float), st>>>(gram, T, T, gscale, perm, wts, stats);
+  }
+  weighted_rows_kernel<<<sms * 4, 256, 0, st>>>(tg, ld, T, wts, out, P);
+  MTRL_CUDA_CHECK(cudaGetLastError());
+  return MTRL_OK;
+}
+
+// The transformation in front of one network's optimiser chain: the combined gradient is written over the network's
+// gradient buffer (what the rest of the chain, clip + adam, consumes).
 int pcgrad_combine(mtrl_sac* h, bool critic, cudaStream_t st) {
   const int T = h->cfg.num_tasks;
   const mtrl_net_layout_t& L = critic ? h->lay.critic : h->lay.actor;
@@ -1160,23 +1184,10 @@ int pcgrad_combine(mtrl_sac* h, bool critic, cudaStream_t st) {
   float* gram = h->pcgrad_scratch + (critic ? 0 : T * T);
   float* wts = h->pcgrad_scratch + 2 * T * T + (critic ? 0 : T);
   float* stats = h->pcgrad_scratch + 2 * T * T + 2 * T + (critic ? 0 : 4);
-  MTRL_CUDA_CHECK(cudaMemsetAsync(gram, 0, static_cast<size_t>(T) * T * sizeof(float), st));
-  pairwise_kernel<0><<<h->sms * 2, 256, 0, st>>>(tg, L.total, T, L.total, gram, T, 1.f, 0.f, 0.f);
-  const float gscale = static_cast<float>(T) * static_cast<float>(T);
-  if (h->surgery_mode == 1) {
-    // cagrad(num_tasks) defaults (cagrad.py:20-41): c = 0.5, 21 iterations, lr 25 (< 50 tasks) or 50, momentum 0.5;
-    // the softmax task weights go where the other network's Gram matrix is not (scratch tail)
-    float* tw = h->pcgrad_scratch + 2 * T * T + 2 * T + 8 + (critic ? 0 : T);
-    cagrad_coeff_kernel<<<1, 32, (static_cast<size_t>(T) * T + 7 * T) * sizeof(double), st>>>(gram, T, T, gscale, 0.5f, 21,
-                                                                                          T < 50 ? 25.f : 50.f, 0.5f, wts, stats, tw);
-  } else if (h->surgery_mode >= 2) {
-    gradnorm_coeff_kernel<<<1, 64, 0, st>>>(gram, T, T, gscale, h->surgery_mode == 3, wts, stats);
-  } else {
-    pcgrad_coeff_kernel<<<1, 64, 2 * T * T * sizeof(float), st>>>(gram, T, T, gscale,
-                                                                  critic ? h->pcgrad_perm_critic : h->pcgrad_perm_actor, wts, stats);
-  }
-  weighted_rows_kernel<<<h->sms * 4, 256, 0, st>>>(tg, L.total, T, wts, grads, L.total);
-  MTRL_CUDA_CHECK(cudaGetLastError());
+  // cagrad's softmax task weights go where the other network's Gram matrix is not (scratch tail)
+  float* tw = h->pcgrad_scratch + 2 * T * T + 2 * T + 8 + (critic ? 0 : T);
+  MTRL_PROPAGATE(combine_rows(h->sms, h->surgery_mode, tg, L.total, T, L.total, static_cast<float>(T) * static_cast<float>(T),
+                              critic ? h->pcgrad_perm_critic : h->pcgrad_perm_actor, gram, wts, stats, tw, grads, st));
   h->launches += 4;
   // the head-gradient norm that rides in the slot was accumulated from the pre-surgery gradients: start it over
   const int acc_idx = critic ? ACC_CRITIC_HEAD_G2 : ACC_ACTOR_HEAD_G2;
@@ -1345,6 +1356,34 @@ extern "C" int mtrl_sac_enable_gradnorm(mtrl_sac_t* h, int critic, int actor, in
   MTRL_PROPAGATE(mtrl_sac_enable_pcgrad(h, critic, actor, critic_tg, actor_tg, scratch, nullptr, nullptr));
   h->surgery_mode = clip_per_task ? 3 : 2;
   return MTRL_OK;
+}
+
+// DummyMultiTaskConfig (mtrl/config/optim.py:46-59): optax.chain(dummy_multitask_optimizer(), clip, adam) -- the plain
+// mean of the per-task gradients of the SPLIT losses (which are not the un-split loss, see mtrl_sac::split_critic).
+extern "C" int mtrl_sac_enable_dummy(mtrl_sac_t* h, int critic, int actor, float* critic_tg, float* actor_tg, float* scratch) {
+  MTRL_PROPAGATE(mtrl_sac_enable_pcgrad(h, critic, actor, critic_tg, actor_tg, scratch, nullptr, nullptr));
+  h->surgery_mode = 4;
+  return MTRL_OK;
+}
+
+// The reference's gradient transformations as a stand-alone operator (the optax protocol objects of mtrl_b200.optim):
+// rows (T, ld) = per-task gradients at reference scale; out (P) = the transformed gradient.
+extern "C" int mtrl_task_combine(int kind, const float* rows, long long ld, int T, long long P, const int* perm, int clip_per_task,
+                                 float* out, float* scratch, void* stream) {
+  MTRL_REQUIRE(rows && out && scratch, "mtrl_task_combine: null argument");
+  MTRL_REQUIRE(kind >= 0 && kind <= 3, "mtrl_task_combine: kind %d outside 0 (pcgrad) .. 3 (dummy)", kind);
+  MTRL_REQUIRE(T >= 1 && T <= 64 && P >= 4 && P % 4 == 0 && ld >= P && ld % 4 == 0,
+               "mtrl_task_combine: T %d outside [1, 64] or row length %lld / pitch %lld not a multiple of 4", T, P, ld);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (kind == 1) cudaFuncSetAttribute(cagrad_coeff_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  const int mode = kind == 0 ? 0 : (kind == 1 ? 1 : (kind == 2 ? (clip_per_task ? 3 : 2) : 4));
+  float* gram = scratch;
+  float* wts = scratch + T * T;
+  float* stats = wts + T;
+  float* tw = stats + 4;
+  return combine_rows(sms, mode, rows, ld, T, P, 1.f, perm, gram, wts, stats, tw, out, static_cast<cudaStream_t>(stream));
 }
 
 // Same wiring with cagrad (mtrl/optim/cagrad.py, CAGradConfig mtrl/config/optim.py:104-124) in front of the chain.

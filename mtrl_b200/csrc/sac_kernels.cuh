@@ -1043,8 +1043,9 @@ static __global__ void pcgrad_coeff_kernel(const float* __restrict__ gram, int l
     // column sums of C: position k of the permuted order is task perm[k]
     float wsum = 0.f;
     for (int r = 0; r < T; ++r) wsum += Cm[r * T + i];
-    // mean over tasks (1 / T) of reference-scale rows (T x unscaled) -> plain sum of unscaled rows
-    w_out[perm ? perm[i] : i] = wsum;
+    // mean over tasks (1 / T) of reference-scale rows (sqrt(gscale) x the given rows); inside the update gscale = T^2,
+    // i.e. the plain sum of the given rows
+    w_out[perm ? perm[i] : i] = wsum * (sqrtf(gscale) / static_cast<float>(T));
   }
   if (i == 0) {
     float sc = 0.f, sa = 0.f, sb = 0.f, all = 0.f;
@@ -1163,14 +1164,16 @@ static __global__ void cagrad_coeff_kernel(const float* __restrict__ gram, int l
 // weights (:134-142), so their gradient is zero, Adam leaves them at their normalised initial value 1 (:72-80, 145-153)
 // and the transformation returns sum_i 1 * g_i (:155-157) of the (optionally, max_grad_norm set) per-task clipped
 // gradients (:40-57, 106-107).  stats: [0] norm of that sum, [1] mean per-task norm after clipping.
-static __global__ void gradnorm_coeff_kernel(const float* __restrict__ gram, int ldg, int T, float gscale, int clip_per_task,
+static __global__ void gradnorm_coeff_kernel(const float* __restrict__ gram, int ldg, int T, float gscale, int clip_per_task, int mean,
                                              float* __restrict__ w_out, float* __restrict__ stats) {
   __shared__ float wv[64];
   const int i = threadIdx.x;
   if (i < T) {
     const float n = sqrtf(fmaxf(gram[i * ldg + i] * gscale, 0.f));
     const float clipc = clip_per_task ? fminf(1.f, 1.f / (n + 1e-8f)) : 1.f;
-    wv[i] = clipc * sqrtf(gscale);   // weight 1 on the reference-scale row = sqrt(gscale) x the unscaled row
+    // weight 1 on the reference-scale row = sqrt(gscale) x the unscaled row; `mean`: the dummy multi-task optimiser's
+    // plain average over tasks instead (mtrl/optim/dummy.py:18)
+    wv[i] = clipc * sqrtf(gscale) / (mean ? static_cast<float>(T) : 1.f);
     w_out[i] = wv[i];
   }
   __syncthreads();

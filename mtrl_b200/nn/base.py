@@ -1,5 +1,7 @@
-"""`MLP` / `VanillaNetwork` (mtrl/nn/base.py:11-89): kept as descriptions for the single-task SAC
-baseline; their fused path is a SURVEY 8(f) "next" row and is not built yet."""
+"""`MLP` / `VanillaNetwork` (mtrl/nn/base.py:11-89) as descriptions: the networks of the single-task SAC baseline
+(`mtrl_b200.rl.algorithms.SAC`) and of MT-PPO on `VanillaNetworkConfig`.  Their forward / backward run inside the fused
+updates (csrc/sac.cu with MTRL_VARIANT_SAC, csrc/ppo.cu): the trunk `layer_0 .. layer_{depth-1}` as tcgen05 GEMMs, the
+output Dense `layer_{depth}` as the single "head"."""
 from dataclasses import dataclass
 
 from ..config.nn import VanillaNetworkConfig

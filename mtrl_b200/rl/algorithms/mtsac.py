@@ -108,6 +108,7 @@ L._EXTRA_DECLS.update({
     "mtrl_sac_enable_pcgrad": ([_vp, _i, _i, _vp, _vp, _vp, _vp, _vp],),
     "mtrl_sac_enable_cagrad": ([_vp, _i, _i, _vp, _vp, _vp],),
     "mtrl_sac_enable_gradnorm": ([_vp, _i, _i, _i, _vp, _vp, _vp],),
+    "mtrl_sac_enable_dummy": ([_vp, _i, _i, _vp, _vp, _vp],),
     "mtrl_task_gram": ([_vp, C.c_longlong, _i, C.c_longlong, _vp, _vp],),
     "mtrl_task_elementwise": ([_vp, C.c_longlong, _i, C.c_longlong, C.c_float, C.c_float, C.c_float, _vp, _vp, _vp],),
     "mtrl_task_abs_order_stats": ([_vp, C.c_longlong, _i, C.c_longlong, C.POINTER(C.c_longlong), _vp, _vp, _vp],),
@@ -340,18 +341,20 @@ class MTSAC:
         la.fill_(math.log(config.initial_temperature))
 
         self._create_handle()
-        surg = lambda o: bool(o.pcgrad or o.cagrad or o.gradnorm)  # noqa: E731
+        surg = lambda o: bool(o.pcgrad or o.cagrad or o.gradnorm or o.dummy)  # noqa: E731
         self._pcgrad = (surg(c_opt), surg(a_opt))   # (critic, actor) start their chain with a multi-task transformation
-        kinds = {k for o in (c_opt, a_opt) for k in ("pcgrad", "cagrad", "gradnorm") if getattr(o, k)}
+        kinds = {k for o in (c_opt, a_opt) for k in ("pcgrad", "cagrad", "gradnorm", "dummy") if getattr(o, k)}
         self._gradnorm_clip = bool(c_opt.gradnorm_clip_per_task or a_opt.gradnorm_clip_per_task)
         if len(kinds) > 1:
             raise NotImplementedError("one multi-task optimiser kind per agent (PCGradConfig, CAGradConfig or GradNormConfig)")
         self._surgery = next(iter(kinds), None)
         if any(self._pcgrad):
             if world_size != 1:
-                raise NotImplementedError("PCGradConfig needs every task on one device (split losses)")
+                raise NotImplementedError("multi-task optimiser configs need every task on one device (split losses)")
             if config.num_tasks > 64:
-                raise NotImplementedError("PCGradConfig: at most 64 tasks")
+                raise NotImplementedError("multi-task optimiser configs: at most 64 tasks")
+            # split_actor_losses / split_critic_losses (mtsac.py:272-273)
+            self.split_critic_losses, self.split_actor_losses = self._pcgrad
             self._enable_pcgrad(seed)
         return self
 
@@ -374,6 +377,10 @@ class MTSAC:
                                                      _vp(tg["critic"].data_ptr()), _vp(tg["actor"].data_ptr()),
                                                      _vp(self._pc_scratch.data_ptr())))
             return
+        if self._surgery == "dummy":
+            L.check(L.lib().mtrl_sac_enable_dummy(self._h, int(self._pcgrad[0]), int(self._pcgrad[1]), _vp(tg["critic"].data_ptr()),
+                                                  _vp(tg["actor"].data_ptr()), _vp(self._pc_scratch.data_ptr())))
+            return
         if self._surgery == "cagrad":
             L.check(L.lib().mtrl_sac_enable_cagrad(self._h, int(self._pcgrad[0]), int(self._pcgrad[1]), _vp(tg["critic"].data_ptr()),
                                                    _vp(tg["actor"].data_ptr()), _vp(self._pc_scratch.data_ptr())))
@@ -387,6 +394,8 @@ class MTSAC:
         plain mean gradient."""
         T, s = self.num_tasks, self._pc_scratch
         base = 2 * T * T + 2 * T
+        if self._surgery == "dummy":    # the reference's dummy state is {} (dummy.py:8-10); the combined-gradient norm is a by-product
+            return {net: {"grad_magnitude": s[base + 4 * i]} for i, net in enumerate(("critic", "actor")) if self._pcgrad[i]}
         if self._surgery == "gradnorm":
             names = ("grad_magnitude", "avg_grad_magnitude_per_task")
             return {net: dict(zip(names, s[base + 4 * i: base + 4 * i + 2]), task_weights=torch.ones(T, device=self.device))

@@ -255,6 +255,8 @@ def _surgery(kind: str, flat: torch.Tensor, perm, gradnorm_clip: bool):
         return pcgrad(flat, perm)
     if kind == "cagrad":
         return cagrad(flat)
+    if kind == "dummy":   # mtrl/optim/dummy.py:18: jax.tree.map(lambda x: x.mean(axis=0), updates)
+        return flat.mean(dim=0), {"grad_magnitude": flat.mean(dim=0).norm()}
     # gradnorm: the per-task losses only enter through bookkeeping that cannot move the weights (see gradnorm())
     return gradnorm(flat, torch.ones(flat.shape[0], dtype=flat.dtype), max_grad_norm=1.0 if gradnorm_clip else None)
 

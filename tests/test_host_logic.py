@@ -80,7 +80,8 @@ def test_optimizer_configs_outside_the_path_fail_loudly():
     assert not OptimizerConfig().spawn().pcgrad
     from mtrl_b200.config.optim import CAGradConfig, GradNormConfig
 
-    assert DummyMultiTaskConfig(max_grad_norm=1.0).spawn() == OptimizerConfig(max_grad_norm=1.0).spawn()   # mean of per-task grads
+    d = DummyMultiTaskConfig(max_grad_norm=1.0)     # chain(dummy_multitask_optimizer(), clip, adam): takes the split path
+    assert d.requires_split_task_losses and d.spawn().dummy and d.spawn().max_grad_norm == 1.0
     assert CAGradConfig(num_tasks=3).spawn().cagrad and CAGradConfig(num_tasks=3).requires_split_task_losses
     g = GradNormConfig(num_tasks=3, max_grad_norm=1.0).spawn()
     assert g.gradnorm and g.gradnorm_clip_per_task and not GradNormConfig(num_tasks=3).spawn().gradnorm_clip_per_task
