@@ -54,6 +54,21 @@ def measured_peaks() -> dict:
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "_source": "fallback"}
 
 
+def tf32_peak(peaks: dict) -> tuple[float, str]:
+    """Roofline denominator of the tf32 GEMM.  profiles/tf32_peak.json, when present, is a cuBLAS TF32 measurement taken
+    on this pool's B200s with the MEASURED_PEAKS recipe (scripts/measure_tf32_peak.py: torch.matmul, TF32 allowed,
+    8192^3, burst = best of 10, sustained = back to back for 4 s); otherwise half the measured bf16 rate."""
+    p = os.path.join(ROOT, "profiles", "tf32_peak.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["tf32_tflops_sustained"]), ("measured: cuBLAS TF32 8192^3 sustained (profiles/tf32_peak.json; burst "
+                                                       f"{d['tf32_tflops']:.0f}); bf16_tflops_sustained / 2 = {peaks['bf16_tflops_sustained'] / 2:.0f}")
+        except Exception:  # noqa: BLE001
+            pass
+    return peaks["bf16_tflops_sustained"] / 2.0, f"{peaks['_source']}: bf16_tflops_sustained / 2 (tcgen05 kind::tf32 runs at half the bf16 rate)"
+
+
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
@@ -130,9 +145,14 @@ def synthetic_fill(buf, T_local: int, task_begin: int, T: int, seed: int) -> Non
     buf.pos = 0
 
 
-def cpu_update_rate(T: int, W: int, per_task: int, budget_s: float, threads: int | None = None) -> dict:
+def cpu_update_rate(T: int, W: int, per_task: int, budget_s: float, threads: int | None = None, steps: int | None = None,
+                    warmup: int = 1) -> dict:
     """The reference's CPU update path (fp32 PyTorch-CPU restatement, heads evaluated for all T tasks
-    and gathered exactly like mtrl/nn/multi_head.py:50-66, plus the NumPy sampler) on the host cores."""
+    and gathered exactly like mtrl/nn/multi_head.py:50-66, plus the NumPy sampler) on the host cores.
+
+    steps=None: one warm-up, then as many full updates as fit `budget_s` (at most 20) -- the `cpu_baseline` leg.
+    steps=K: exactly `warmup` + K steps (the reference arm); if K full updates would exceed the budget a step becomes the
+    same update on a fraction 1/2^j of every task's rows, counted as that fraction of an update."""
     import numpy as np
     import torch
 
@@ -156,9 +176,9 @@ def cpu_update_rate(T: int, W: int, per_task: int, budget_s: float, threads: int
     buf.rewards[:] = rng.uniform(0, 10, buf.rewards.shape).astype(np.float32)
     buf.full = True
     g = torch.Generator().manual_seed(0)
-    B = per_task * T
 
-    def one(state):
+    def one(state, rows_per_task):
+        B = rows_per_task * T
         s = buf.sample(B)
         batch = tuple(torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)) for x in s)
         ec = torch.randn(B, 4, generator=g)
@@ -168,17 +188,37 @@ def cpu_update_rate(T: int, W: int, per_task: int, budget_s: float, threads: int
         return new
 
     t0 = time.perf_counter()
-    st = one(st)  # warm-up (allocator, thread pool)
+    st = one(st, per_task)  # first warm-up (allocator, thread pool)
     t_first = time.perf_counter() - t0
-    n_timed = max(1, min(20, int(budget_s / max(t_first, 1e-3))))
+    rows = per_task
+    if steps is None:
+        n_timed, n_warm = max(1, min(20, int(budget_s / max(t_first, 1e-3)))), 0
+    else:
+        n_timed, n_warm = steps, max(warmup - 1, 0)
+        est = t_first
+        while (n_timed + n_warm) * est > budget_s and rows > 8:
+            rows //= 2
+            est /= 2
+    for _ in range(n_warm):
+        st = one(st, rows)
     t0 = time.perf_counter()
     for _ in range(n_timed):
-        st = one(st)
-    dt = (time.perf_counter() - t0) / n_timed
-    return {"value": 1.0 / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"1 warm-up + {n_timed} full updates (B={B}, incl. NumPy sample) of the fp32 torch-CPU oracle, "
-                      f"{dt*1e3:.0f} ms each, torch threads={torch.get_num_threads()}",
+        st = one(st, rows)
+    dt_step = (time.perf_counter() - t0) / n_timed
+    frac = rows / per_task
+    dt = dt_step / frac          # seconds per FULL update
+    sample = (f"{n_warm + 1} warm-up + {n_timed} timed steps of the fp32 torch-CPU oracle incl. the NumPy sample; a step = the update on "
+              f"{rows} of {per_task} rows per task (B = {rows * T}" + (", a full update" if frac == 1 else f", counted as {frac:g} of an update") +
+              f"), {dt_step * 1e3:.0f} ms each, torch threads={torch.get_num_threads()}")
+    return {"value": 1.0 / dt, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
             "_sec_per_update": dt, "_n_timed": n_timed}
+
+
+def workload_config(args) -> dict:
+    """The `config` object both arms print (same keys, so the driver can tell they measured the same workload)."""
+    T, W, per_task = WORKLOADS[args.workload]
+    return {"workload": args.workload, "num_tasks": T, "width": W, "depth": 3, "num_critics": 2, "global_batch": per_task * T,
+            "per_task_batch": per_task, "obs_dim": 39 + T, "action_dim": 4, "ring_capacity_per_task": args.capacity}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -189,21 +229,99 @@ def run_reference_arm(args, out) -> None:
     if rank != 0:
         return
     T, W, per_task = WORKLOADS[args.workload]
-    budget = float(os.environ.get("MTRL_REF_BUDGET_S", "150"))
-    # every step is a full update; the number of timed steps is bounded by the budget
-    r = cpu_update_rate(T, W, per_task, budget_s=budget)
+    budget = float(os.environ.get("MTRL_REF_BUDGET_S", "200"))
+    # EXACTLY args.warmup + args.steps steps; a step is a full update (B = 128 T rows) when that fits the time budget,
+    # otherwise a bounded sample of it: the same update on 1/2, 1/4, ... of the rows of every task, counted as that fraction
+    r = cpu_update_rate(T, W, per_task, budget_s=budget, steps=args.steps, warmup=args.warmup)
     dt = r.pop("_sec_per_update")
-    n_timed = r.pop("_n_timed")
+    r.pop("_n_timed")
+    cfg = workload_config(args)
+    cfg["note"] = "CPU restatement of MTSAC.update + NumPy sampler (the reference itself needs jax, absent here): " + r["sample"]
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": n_timed, "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "num_tasks": T, "width": W, "global_batch": per_task * T,
-                   "note": "CPU restatement of MTSAC.update + NumPy sampler; steps bounded by a time budget: " + r["sample"]},
+        "config": cfg,
         "cpu_baseline": r,
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), file=out, flush=True)
+
+
+def multi_rank_parity_check(rank: int, world: int, pg, exchange: str) -> dict:
+    """After the timed regions of an N > 1 run: the sharded update itself against the UNSHARDED fp64 oracle (checker use
+    of oracle/, as in tests/multigpu_check.py).  T = 50 tasks so that the uneven 7/6 (13/12) task blocks of the benchmark
+    are exercised, width 256, two updates, in both precisions:
+      tf32:   ten log scalars to 1e-3 (2e-3 at the 2nd step), trunk kernels to 2e-3
+      fp32x3: ten log scalars and EVERY parameter leaf (this rank's heads included) to 1e-3
+    plus: critic and actor trunk replicas bit-identical on all ranks, no exchange time-out.  Every rank checks; the
+    verdicts are combined over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import sac_util as SU
+    from mtrl_b200.rl.algorithms.mtsac import task_partition
+    from oracle import mtsac_oracle as O
+
+    T, W, per_task = 50, 256, 32
+    cfg = O.OracleConfig(num_tasks=T, obs_dim=39 + T, action_dim=4, width=W)
+    t0, t1 = task_partition(T, world)[rank]
+    sl = slice(t0, t1)
+    out = {"ok": True, "config": {"num_tasks": T, "width": W, "global_batch": per_task * T, "updates": 2, "exchange": exchange,
+                                  "tasks_per_rank": [b - a for a, b in task_partition(T, world)]}, "worst": {}, "failures": []}
+    for precision in ("tf32", "fp32x3"):
+        st = O.init_state(cfg, seed=1, dtype=torch.float32)
+        agent = SU.make_agent(cfg, per_task, seed=1, max_batch=per_task * (t1 - t0), rank=rank, world_size=world,
+                              process_group=pg, exchange=exchange, precision=precision)
+        SU.load_oracle_state(agent, st, task_slice=sl)
+        st64 = st.to(torch.float64)
+        worst_log = worst_leaf = 0.0
+        try:
+            for step in range(2):
+                batch, ec, ea = O.synthetic_batch(cfg, per_task, seed=50 + step, dtype=torch.float32)
+                task = batch[0][:, -T:].argmax(1)
+                rows = (task >= t0) & (task < t1)
+                st64, logs64 = O.mtsac_update(st64, tuple(b.double() for b in batch), ec.double(), ea.double(), cfg)
+                _, logs = agent.update(tuple(b[rows].cuda() for b in batch), eps_c=ec[rows].cuda(), eps_a=ea[rows].cuda(),
+                                       global_batch=batch[0].shape[0], check=True)
+                for k in O.LOG_KEYS:
+                    ref, got = float(logs64[k]), float(logs[k])
+                    err = abs(got - ref) / max(abs(ref), 1e-12) if ref != 0 else abs(got)
+                    worst_log = max(worst_log, err)
+                    if err > 1e-3 * (1 + step if precision == "tf32" else 1):
+                        out["failures"].append(f"rank {rank} {precision} step {step} {k}: {got} vs {ref}")
+            for name, new_t, tree, ens in (("actor", st64.actor, agent.actor.params, False), ("critic", st64.critic, agent.critic.params, True),
+                                           ("target", st64.critic_target, agent.critic.target_params, True)):
+                for leaf, e in SU.compare_trees(new_t, tree, ens, task_slice=sl).items():
+                    strict = precision == "fp32x3" or (leaf.startswith("layer_") and leaf.endswith("kernel"))
+                    if strict:
+                        worst_leaf = max(worst_leaf, e)
+                        if e > (1e-3 if precision == "fp32x3" else 2e-3):
+                            out["failures"].append(f"rank {rank} {precision} {name}/{leaf}: rel {e:.2e}")
+            if SU.rel(agent.alpha.params["params"]["log_alpha"], st64.log_alpha[sl]) > 1e-3:
+                out["failures"].append(f"rank {rank} {precision} log_alpha")
+            for net in ("critic", "actor"):
+                lay = getattr(agent._lay, net)
+                trunk = agent._flat[f"{net}_params"][: lay.trunk_total].clone()
+                ref = trunk.clone()
+                dist.broadcast(ref, src=0)
+                if not torch.equal(trunk, ref):
+                    out["failures"].append(f"rank {rank} {precision}: {net} trunk replica differs from rank 0")
+            if agent.exchange_error() != 0:
+                out["failures"].append(f"rank {rank} {precision}: peer exchange timed out (code {agent.exchange_error()})")
+        except Exception as e:  # noqa: BLE001
+            out["failures"].append(f"rank {rank} {precision}: {type(e).__name__}: {e}")
+        w = torch.tensor([worst_log, worst_leaf, float(len(out["failures"]))], device="cuda", dtype=torch.float64)
+        dist.all_reduce(w, op=dist.ReduceOp.MAX)
+        out["worst"][precision] = {"log_scalar": float(w[0]), "checked_leaf": float(w[1])}
+        if float(w[2]) > 0:
+            out["ok"] = False
+        del agent
+        torch.cuda.synchronize()
+        dist.barrier()
+    out["checked"] = "logs + parameter leaves vs the unsharded fp64 oracle on every rank; trunk replicas bit-identical; no exchange time-out"
+    return out
 
 
 def protect_stdout():
@@ -219,8 +337,8 @@ def main() -> None:
     out = protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)    # >= 200 graph replays after 20 warm-ups
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("MTRL_WORKLOAD", "mt50_w2048"), choices=sorted(WORKLOADS))
     ap.add_argument("--capacity", type=int, default=int(os.environ.get("MTRL_BENCH_CAPACITY", "100000")),
@@ -368,6 +486,21 @@ def main() -> None:
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
+    # the same call fed the way the reference's loop feeds it: PAGEABLE NumPy arrays straight from a host-side sample()
+    # (base.py:220-221 hands `update` what buffers.py:547-549 returns); torch stages them through its own pinned pool
+    np_batches = [tuple(x.numpy().copy() for x in hb) for hb in host_batches]
+    for i in range(3):
+        agent.update(np_batches[i % n_host], global_batch=B)
+    barrier()
+    n_page = min(args.steps, 50)
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for i in range(n_page):
+        agent.update(np_batches[i % n_host], global_batch=B)
+        log_host.copy_(agent._logs, non_blocking=False)
+    g1.record()
+    barrier()
+    ms_page = g0.elapsed_time(g1) / n_page
     clk = clocks.stop() if rank == 0 else None
     h2d = sum(x.numel() * 4 for x in host_batches[0])
     d2h = 16 * 4
@@ -376,14 +509,17 @@ def main() -> None:
         print(f"rank {rank}: peer exchange timed out (code {agent.exchange_error()})", file=sys.stderr, flush=True)
         os._exit(3)
     if world > 1:
-        t = torch.tensor([ms, ms_e2e, gemm_ms, ms_stream], device="cuda", dtype=torch.float64)
+        t = torch.tensor([ms, ms_e2e, gemm_ms, ms_stream, ms_page], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e, gemm_ms, ms_stream = (float(x) for x in t)
+        ms, ms_e2e, gemm_ms, ms_stream, ms_page = (float(x) for x in t)
         hb = torch.tensor([h2d], device="cuda", dtype=torch.float64)
         dist.all_reduce(hb)
         h2d = int(hb.item())
         d2h *= world
 
+    parity = None
+    if world > 1 and not emulate:
+        parity = multi_rank_parity_check(rank, world, pg, exchange)
     if rank == 0:
         peaks = measured_peaks()
         value = args.steps / (ms / 1e3)
@@ -392,10 +528,12 @@ def main() -> None:
         flops_rank = algorithmic_flops(T, W, B_local if (world > 1 or emulate) else B, trunk_only=True)
         n_l = max(gemm_launches, 1)
         achieved = flops_rank * args.steps / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
-        tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
+        peak_tf32, peak_src = tf32_peak(peaks)
+        # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture -- quoted only on the line
+        # whose launch shapes that capture has (one GPU, MT50 / W2048, tf32); other shapes were not captured
         traffic = None
         prof_json = os.path.join(ROOT, "profiles", "gemm_ncu_summary.json")
-        if os.path.exists(prof_json):
+        if os.path.exists(prof_json) and world == 1 and not emulate and args.workload == "mt50_w2048" and args.precision == "tf32":
             try:
                 traffic = json.load(open(prof_json)).get("dram_bytes_per_launch")
             except Exception:  # noqa: BLE001
@@ -404,9 +542,7 @@ def main() -> None:
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": args.workload, "num_tasks": T, "width": W, "depth": 3, "num_critics": 2,
-                       "global_batch": B, "per_task_batch": per_task, "obs_dim": 39 + T, "action_dim": 4,
-                       "ring_capacity_per_task": args.capacity,
+            "config": dict(workload_config(args), **{
                        "parallelism": (f"tasks sharded over {world} GPU(s); trunk gradients: " +
                                        ("fused peer-memory reduce-scatter + sharded Adam + all-gather kernel (NVLink P2P, no NCCL)"
                                         if exchange == "p2p" else "NCCL all-reduce between the phases")) if world > 1 else "single GPU",
@@ -415,16 +551,20 @@ def main() -> None:
                        "precision": ("fp32 storage, tf32 tensor-core operands (round-to-nearest), fp32 accumulate" if args.precision == "tf32"
                                      else "fp32 storage, every operand a (hi, lo) pair of tf32 values, three tensor-core passes per "
                                           "k-block (3xTF32), fp32 accumulate; roofline.achieved still counts the algorithmic FLOPs once"),
-                       "launch": "one CUDA graph replay per step" if graph is not None else "stream launches"},
+                       "launch": "one CUDA graph replay per step" if graph is not None else "stream launches"}),
             "gpu_launches": launches_per_step * args.steps,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps},
-            "roofline": {"bound": "tensor", "kernel": "gemm_tf32_grouped_kernel", "achieved": achieved, "peak": tf32_peak,
-                         "unit": "TFLOP/s", "frac": (achieved / tf32_peak) if achieved else None, "traffic": traffic,
+                    "ms_per_step": ms_e2e / args.steps,
+                    "host_buffers": f"{n_host} pre-sampled batches in pinned host memory (the replay sampler is not in this region); "
+                                    "update() copies them H2D into its staging buffers and replays its graph; logs read back every step",
+                    "pageable_value": 1e3 / ms_page, "pageable_ms_per_step": ms_page,
+                    "pageable_note": f"same call with pageable NumPy batches, as the reference's loop passes them ({n_page} steps)"},
+            "roofline": {"bound": "tensor", "kernel": "gemm_tf32_grouped_kernel", "achieved": achieved, "peak": peak_tf32,
+                         "unit": "TFLOP/s", "frac": (achieved / peak_tf32) if achieved else None, "traffic": traffic,
                          "launches_per_step": n_l / args.steps, "avg_launch_ms": gemm_ms / n_l,
                          "gemm_share_of_step": gemm_ms / ms_stream,
                          "measured_over": f"{args.steps} steps launched kernel by kernel ({ms_stream / args.steps:.3f} ms/step)",
-                         "peak_source": f"{peaks['_source']}: bf16_tflops_sustained / 2 (tcgen05 kind::tf32 runs at half the bf16 rate)",
+                         "peak_source": peak_src,
                          "algorithmic_flops_per_step": flops_rank},
             "exchange": ({"kernels_per_step": xchg_launches / args.steps, "ms_per_step": xchg_ms / args.steps,
                           "phase_us": agent.exchange_phase_times(),
@@ -433,6 +573,8 @@ def main() -> None:
                          if world > 1 else None),
             "clocks": clk,
         }
+        if parity is not None:
+            line["parity_check"] = parity
         if emulate:
             line["config"]["emulated_shard_of"] = emulate
             line["config"]["note"] = "PROFILING AID: rank 0's shard alone, no exchange; not a benchmark result"
@@ -442,6 +584,10 @@ def main() -> None:
             r.pop("_n_timed", None)
             line["cpu_baseline"] = r
         print(json.dumps(line), file=out, flush=True)
+    if parity is not None and not parity["ok"]:
+        print(f"rank {rank}: multi-rank parity check FAILED: {parity}", file=sys.stderr, flush=True)
+        sys.stderr.flush()
+        os._exit(4)
     if world > 1:
         # A captured graph holds NCCL work; tearing the communicator down under it can block.  Drop the graph, meet
         # at a barrier and leave without running NCCL's destructors.

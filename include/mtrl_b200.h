@@ -77,6 +77,10 @@ typedef struct mtrl_gemm_plan mtrl_gemm_plan_t;
 
 /* Encodes the TMA descriptors for up to 24 problems that will run as one persistent launch. */
 int mtrl_gemm_plan_create(mtrl_gemm_plan_t** out, const mtrl_gemm_problem_t* problems, int n);
+/* Same with the tile shape chosen by the caller: ctas = 2 -> 256-row tiles over CTA pairs (cta_group::2; fewest operand
+ * bytes per flop, the default), 1 -> 128-row tiles on single CTAs (twice as many, half-size units: better when a launch
+ * has too few 256-row units to fill the 74 pairs evenly, e.g. one rank's rows of a task-sharded batch), 0 -> default. */
+int mtrl_gemm_plan_create_ex(mtrl_gemm_plan_t** out, const mtrl_gemm_problem_t* problems, int n, int ctas);
 int mtrl_gemm_plan_run(mtrl_gemm_plan_t* plan, void* stream);
 int mtrl_gemm_plan_units(const mtrl_gemm_plan_t* plan);
 /* 2 when the plan runs as CTA pairs (tcgen05 cta_group::2, 256-row tiles), 1 for single-CTA tiles. */
@@ -325,8 +329,11 @@ int mtrl_sac_profile_read(mtrl_sac_t* h, double* total_ms, int* launches);
 /* The exchange kernels (csrc/comm.cuh) bracketed in the same pass: their summed duration and count as of the last
  * mtrl_sac_profile_read. */
 int mtrl_sac_profile_exchange(mtrl_sac_t* h, double* total_ms, int* launches);
-/* Asynchronous copy of the packing status of the last update into 4 pinned host ints:
- * [0] == 0 ok, 1: a row's task is outside this handle's task range, 2: rows do not fit max_rows. */
+/* Asynchronous copy of the status words of the last update into 4 pinned host ints:
+ * [0] == 0 ok, 1: a row's task is outside this handle's task range, 2: rows do not fit max_rows, 3: unbalanced split;
+ * [1] != 0: the peer exchange is dead -- an in-kernel wait for another rank timed out (code = 1 + barrier, 10 + barrier
+ *     for the in-rank grid barrier); no rank has applied the step that was in flight, every later update is a no-op for
+ *     the trunk, and the host must stop (mtrl_comm_error reads the same word synchronously). */
 int mtrl_sac_read_status_async(const mtrl_sac_t* h, int* host_pinned4, void* stream);
 
 /* ------------------------------------------------------------------------------------------

@@ -70,6 +70,7 @@ def check(rc: int) -> None:
 def _declare(l: C.CDLL) -> None:
     vp, i, ll = C.c_void_p, C.c_int, C.c_longlong
     l.mtrl_gemm_plan_create.argtypes = [C.POINTER(vp), C.POINTER(GemmProblem), i]
+    l.mtrl_gemm_plan_create_ex.argtypes = [C.POINTER(vp), C.POINTER(GemmProblem), i, i]
     l.mtrl_gemm_plan_run.argtypes = [vp, vp]
     l.mtrl_gemm_plan_units.argtypes = [vp]
     l.mtrl_gemm_plan_ctas.argtypes = [vp]
@@ -110,10 +111,10 @@ def current_stream_ptr() -> int:
 class GemmPlan:
     """One persistent grouped launch; holds the encoded TMA descriptors."""
 
-    def __init__(self, problems: list[GemmProblem]):
+    def __init__(self, problems: list[GemmProblem], ctas: int = 0):
         arr = (GemmProblem * len(problems))(*problems)
         h = C.c_void_p()
-        check(lib().mtrl_gemm_plan_create(C.byref(h), arr, len(problems)))
+        check(lib().mtrl_gemm_plan_create_ex(C.byref(h), arr, len(problems), ctas))
         self._h = h
         self.units = lib().mtrl_gemm_plan_units(h)
         self.ctas = lib().mtrl_gemm_plan_ctas(h)

@@ -1,6 +1,8 @@
 // Exchange arena: one cudaMalloc block per rank, exported to the other ranks of the box through CUDA IPC so that
 // kernels can load / store peer memory over NVLink (comm.cuh).  Replaces nothing in the reference (it is single
 // device); it is the multi-GPU plumbing of SURVEY 8(e).
+#include <stdlib.h>
+
 #include "comm.cuh"
 
 static_assert(sizeof(cudaIpcMemHandle_t) == MTRL_IPC_HANDLE_BYTES, "IPC handle size");
@@ -29,6 +31,9 @@ extern "C" int mtrl_comm_create(mtrl_comm_t** out, int rank, int world, long lon
   memset(&h, 0, sizeof(h));
   h.epoch = 1;
   h.sync_epoch = 1;
+  double timeout_s = 30.0;
+  if (const char* e = getenv("MTRL_COMM_TIMEOUT_S")) timeout_s = atof(e) > 0.0 ? atof(e) : timeout_s;
+  h.timeout_ns = static_cast<unsigned long long>(timeout_s * 1e9);
   cudaMemcpy(p, &h, sizeof(h), cudaMemcpyHostToDevice);
   cudaIpcMemHandle_t ih;
   e = cudaIpcGetMemHandle(&ih, p);

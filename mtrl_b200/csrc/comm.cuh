@@ -32,6 +32,7 @@ struct Header {
   unsigned long long phase_ns[2][8];              // [epoch parity][phase]: globaltimer stamps of CTA 0 in the last two
                                                   // trunk steps: start, barrier 0, norms, barrier 1, Adam + all-gather,
                                                   // barrier 2, derived copies (mtrl_comm_phase_times)
+  unsigned long long timeout_ns;                  // how long an in-kernel wait for a peer may last (MTRL_COMM_TIMEOUT_S)
 };
 
 // Ownership of the replicated trunk: the flat buffer is cut into segments, each stepped (Adam) by exactly one rank.
@@ -80,7 +81,11 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
-constexpr unsigned long long kWaitTimeoutNs = 4000000000ull;  // 4 s: a missing peer must not hang the box
+// A wait for a peer that exceeds Header::timeout_ns (default 30 s, MTRL_COMM_TIMEOUT_S; a missing peer must not hang the
+// box) sets Header::error.  The error is STICKY and fatal for the exchange: the kernel that saw it, and every later
+// exchange kernel of this rank, returns without reducing, stepping Adam or broadcasting anything (a late peer then times
+// out at its next barrier too, so no rank applies a step the others did not), and the code is copied into the update's
+// status word, where the host's normal status check raises (mtrl_sac_read_status_async, word 1).
 
 struct TrunkStepArgs {
   float *p, *m, *v, *shadow, *g, *target, *target_shadow;   // local buffers of this network (target may be null)
@@ -93,6 +98,7 @@ struct TrunkStepArgs {
   int nsegs;
   int rank, world;
   const int* step;
+  int* status;                                             // the update's status words: [1] receives Header::error
   double* g2_trunk_out;                                    // global trunk gradient squared norm (log scalar input)
   double *p2_trunk, *p2_head;
   float lr, b1, b2, eps, max_norm, tau;
@@ -102,8 +108,9 @@ struct TrunkStepArgs {
 __device__ __forceinline__ void wait_ranks(Header* H, int b, int world, unsigned epoch) {
   if (threadIdx.x < world) {
     const unsigned long long t0 = globaltimer_ns();
+    const unsigned long long limit = H->timeout_ns;
     while (static_cast<int>(ld_acquire_sys(&H->flag[b][threadIdx.x]) - epoch) < 0) {
-      if (globaltimer_ns() - t0 > kWaitTimeoutNs) {
+      if (globaltimer_ns() - t0 > limit || *reinterpret_cast<volatile int*>(&H->error) != 0) {
         atomicExch(&H->error, 1 + b);
         break;
       }
@@ -124,8 +131,9 @@ __device__ __forceinline__ void grid_arrive_then_signal(const TrunkStepArgs& a, 
   if (blockIdx.x == 0) {
     if (threadIdx.x == 0) {
       const unsigned long long t0 = globaltimer_ns();
+      const unsigned long long limit = H->timeout_ns;
       while (ld_acquire_gpu(&H->grid_count) < target) {
-        if (globaltimer_ns() - t0 > kWaitTimeoutNs) {
+        if (globaltimer_ns() - t0 > limit) {
           atomicExch(&H->error, 10 + b);
           break;
         }
@@ -210,11 +218,15 @@ __device__ __forceinline__ float derived4(const TrunkStepArgs& a, long long i4, 
 
 // Every rank has finished what precedes this kernel in its stream (one warp; used before the first gradient
 // GEMM of an update so that no rank reduce-adds into a peer buffer that is not zeroed yet).
-static __global__ void rank_barrier_kernel(Header* const* peer_hdr_dev, int rank, int world) {
+static __global__ void rank_barrier_kernel(Header* const* peer_hdr_dev, int rank, int world, int* status) {
   __shared__ Header* hdr[MTRL_COMM_MAX_RANKS];
   if (threadIdx.x < world) hdr[threadIdx.x] = peer_hdr_dev[threadIdx.x];
   __syncthreads();
   Header* H = hdr[rank];
+  if (*reinterpret_cast<volatile int*>(&H->error) != 0) {   // sticky: the exchange is dead
+    if (threadIdx.x == 0) status[1] = H->error;
+    return;
+  }
   const unsigned epoch = *reinterpret_cast<volatile unsigned*>(&H->sync_epoch);
   __syncthreads();
   if (threadIdx.x < world) {
@@ -222,7 +234,10 @@ static __global__ void rank_barrier_kernel(Header* const* peer_hdr_dev, int rank
     st_release_sys(&hdr[threadIdx.x]->flag[3][rank], epoch);
   }
   wait_ranks(H, 3, world, epoch);
-  if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned*>(&H->sync_epoch) = epoch + 1;
+  if (threadIdx.x == 0) {
+    *reinterpret_cast<volatile unsigned*>(&H->sync_epoch) = epoch + 1;
+    if (*reinterpret_cast<volatile int*>(&H->error) != 0) status[1] = H->error;
+  }
 }
 
 // Launch with one CTA per SM (all CTAs must be co-resident: they meet at in-kernel barriers).
@@ -240,6 +255,13 @@ static __global__ void __launch_bounds__(512, 1) trunk_step_kernel(const TrunkSt
   __syncthreads();
   const Segment* segs = segs_in_smem ? s_segs : a.segs;
   Header* H = a.peer_hdr[a.rank];
+  // every CTA reads the (sticky) error word at the same points, right after a barrier wait, so they agree on leaving
+  auto dead = [&]() {
+    const int e = *reinterpret_cast<volatile int*>(&H->error);
+    if (e != 0 && blockIdx.x == 0 && threadIdx.x == 0) a.status[1] = e;
+    return e != 0;
+  };
+  if (dead()) return;
   const unsigned epoch = *reinterpret_cast<volatile unsigned*>(&H->epoch);
   const unsigned long long grid_base = static_cast<unsigned long long>(epoch - 1) * 2ull * gridDim.x;
   const int world = WORLD ? WORLD : a.world;
@@ -251,6 +273,7 @@ static __global__ void __launch_bounds__(512, 1) trunk_step_kernel(const TrunkSt
   //      reduce-adds they sent into this rank's pre-reduced segments have landed too ----
   if (blockIdx.x == 0 && threadIdx.x < world) st_release_sys(&a.peer_hdr[threadIdx.x]->flag[0][a.rank], epoch);
   wait_ranks(H, 0, world, epoch);
+  if (dead()) return;   // a peer never finished its gradient kernels: nothing has been touched yet
   if (blockIdx.x == 0 && threadIdx.x == 0) H->phase_ns[epoch & 1][1] = globaltimer_ns();
 
   // ---- owned segments: finish the reduction where the GEMMs have not done it, and take the squared norm ----
@@ -280,6 +303,7 @@ static __global__ void __launch_bounds__(512, 1) trunk_step_kernel(const TrunkSt
   // ---- barrier 1: exchange the shard norms and the head norms ----
   grid_arrive_then_signal(a, H, 1, epoch, grid_base + gridDim.x, true);
   wait_ranks(H, 1, world, epoch);
+  if (dead()) return;   // incomplete norms: no clip scale, no Adam, no broadcast
   if (blockIdx.x == 0 && threadIdx.x == 0) H->phase_ns[epoch & 1][3] = globaltimer_ns();
   if (threadIdx.x == 0) {
     double g2 = 0.0, h2 = 0.0;
@@ -336,6 +360,7 @@ static __global__ void __launch_bounds__(512, 1) trunk_step_kernel(const TrunkSt
   // ---- barrier 2: every rank has stored its segments everywhere ----
   grid_arrive_then_signal(a, H, 2, epoch, grid_base + 2ull * gridDim.x, false);
   wait_ranks(H, 2, world, epoch);
+  if (dead()) return;   // a peer's segments never arrived: leave the replicas' derived copies alone, the host raises
   if (blockIdx.x == 0 && threadIdx.x == 0) H->phase_ns[epoch & 1][5] = globaltimer_ns();
 
   // ---- derived copies of the segments the peers own ----

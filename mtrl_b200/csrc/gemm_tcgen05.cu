@@ -728,12 +728,17 @@ int preferred_ctas(int sms) {
 }  // namespace
 
 extern "C" int mtrl_gemm_plan_create(mtrl_gemm_plan_t** out, const mtrl_gemm_problem_t* problems, int n) {
+  return mtrl_gemm_plan_create_ex(out, problems, n, 0);
+}
+
+extern "C" int mtrl_gemm_plan_create_ex(mtrl_gemm_plan_t** out, const mtrl_gemm_problem_t* problems, int n, int ctas_req) {
   MTRL_REQUIRE(out && problems && n >= 1 && n <= kMaxProblems,
                "mtrl_gemm_plan_create: need 1..%d problems per launch, got %d", kMaxProblems, n);
+  MTRL_REQUIRE(ctas_req >= 0 && ctas_req <= 2, "mtrl_gemm_plan_create_ex: ctas %d outside {0, 1, 2}", ctas_req);
   int dev_id = 0, sms = 148;
   cudaGetDevice(&dev_id);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id);
-  const int ctas = preferred_ctas(sms);
+  const int ctas = (ctas_req == 2 && sms % 2) ? 1 : (ctas_req ? ctas_req : preferred_ctas(sms));
   mtrl_gemm_plan* plan = new mtrl_gemm_plan();
   struct Guard {
     mtrl_gemm_plan* p;

@@ -126,12 +126,14 @@ inline int make_plan_plain(std::vector<mtrl_gemm_plan_t*>& dst, const std::vecto
   return MTRL_OK;
 }
 
-// Tile-width selection by measurement.  A launch is a static schedule of equal-shaped units over 74 CTA pairs, so its
-// duration is (rounds of units) x (unit time): 80 units of width 256 take two rounds where 120 units of width 192 take
-// two SHORTER rounds.  Which width wins depends on the shapes grouped into the launch (batch rows, width, members) and on
-// how far narrower tiles are L2-bound, so every candidate width is built and timed once at plan creation (a few launches
-// on the real buffers: forward outputs are overwritten and gradient accumulators re-zeroed by every update) and the
-// fastest plan is kept.  MTRL_GEMM_AUTOTUNE=0 keeps the default width.
+// Tile-shape selection by measurement.  A launch is a static schedule of units over the SMs, so its duration is (rounds of
+// units) x (unit time): 80 units of 256 x 256 on 74 CTA pairs take two rounds where 120 units of width 192 take two
+// SHORTER rounds, and the 112 units of 128 x 256 that one rank's 896 rows of a task-sharded batch give fit ONE round of
+// 148 single CTAs where the 64 padded 256-row units need a full round of pairs at twice the unit time.  Which shape wins
+// depends on the shapes grouped into the launch (batch rows, width, members) and on how far smaller tiles are L2-bound, so
+// every candidate (CTA pairs or single CTAs) x (tile width) is built and timed once at plan creation (a few launches on the
+// real buffers: forward outputs are overwritten and gradient accumulators re-zeroed by every update) and the fastest plan
+// is kept.  MTRL_GEMM_AUTOTUNE=0 keeps the default shape; MTRL_GEMM_CTAS=1|2 restricts the candidates to one kind.
 inline int make_plan(std::vector<mtrl_gemm_plan_t*>& dst, const std::vector<mtrl_gemm_problem_t>& probs) {
   const char* env = getenv("MTRL_GEMM_AUTOTUNE");
   bool wide = false;
@@ -153,34 +155,44 @@ inline int make_plan(std::vector<mtrl_gemm_plan_t*>& dst, const std::vector<mtrl
   mtrl_gemm_plan_t* best = nullptr;
   float best_ms = 0.f;
   int rc = MTRL_OK;
+  const char* force = getenv("MTRL_GEMM_CTAS");
+  const int kinds[2] = {2, 1};
   const int cands[4] = {0, 192, 128, 64};   // 0 = the caller's default
-  for (int cand : cands) {
-    std::vector<mtrl_gemm_problem_t> q = probs;
-    bool changed = cand == 0;
-    for (auto& p : q)
-      if (cand && p.N >= 256 && p.block_n > cand) { p.block_n = cand; changed = true; }
-    if (!changed) continue;
-    mtrl_gemm_plan_t* plan = nullptr;
-    rc = mtrl_gemm_plan_create(&plan, q.data(), static_cast<int>(q.size()));
+  for (int kind : kinds) {
+    if (force && (force[0] == '1' || force[0] == '2') && force[0] - '0' != kind) continue;
+    for (int cand : cands) {
+      std::vector<mtrl_gemm_problem_t> q = probs;
+      bool changed = cand == 0;
+      for (auto& p : q)
+        if (cand && p.N >= 256 && p.block_n > cand) { p.block_n = cand; changed = true; }
+      if (!changed) continue;
+      mtrl_gemm_plan_t* plan = nullptr;
+      rc = mtrl_gemm_plan_create_ex(&plan, q.data(), static_cast<int>(q.size()), kind);
+      if (rc != MTRL_OK) break;
+      if (mtrl_gemm_plan_ctas(plan) != kind) {   // an odd SM count turns pairs into single CTAs: already covered
+        mtrl_gemm_plan_destroy(plan);
+        continue;
+      }
+      float ms = 1e30f;
+      for (int rep = 0; rep < 4 && rc == MTRL_OK; ++rep) {
+        cudaEventRecord(e0, nullptr);
+        rc = mtrl_gemm_plan_run(plan, nullptr);
+        cudaEventRecord(e1, nullptr);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { mtrl_set_error("GEMM autotune launch failed"); rc = MTRL_ERR_CUDA; }
+        float t = 0.f;
+        cudaEventElapsedTime(&t, e0, e1);
+        if (rep > 0 && t < ms) ms = t;   // first run warms the instruction cache / L2
+      }
+      if (rc != MTRL_OK) { mtrl_gemm_plan_destroy(plan); break; }
+      if (!best || ms < best_ms * 0.97f) {   // prefer the earlier candidate unless a later one is clearly faster
+        if (best) mtrl_gemm_plan_destroy(best);
+        best = plan;
+        best_ms = ms;
+      } else {
+        mtrl_gemm_plan_destroy(plan);
+      }
+    }
     if (rc != MTRL_OK) break;
-    float ms = 1e30f;
-    for (int rep = 0; rep < 4 && rc == MTRL_OK; ++rep) {
-      cudaEventRecord(e0, nullptr);
-      rc = mtrl_gemm_plan_run(plan, nullptr);
-      cudaEventRecord(e1, nullptr);
-      if (cudaEventSynchronize(e1) != cudaSuccess) { mtrl_set_error("GEMM autotune launch failed"); rc = MTRL_ERR_CUDA; }
-      float t = 0.f;
-      cudaEventElapsedTime(&t, e0, e1);
-      if (rep > 0 && t < ms) ms = t;   // first run warms the instruction cache / L2
-    }
-    if (rc != MTRL_OK) { mtrl_gemm_plan_destroy(plan); break; }
-    if (!best || ms < best_ms * 0.97f) {   // prefer the default unless a narrower tile is clearly faster
-      if (best) mtrl_gemm_plan_destroy(best);
-      best = plan;
-      best_ms = ms;
-    } else {
-      mtrl_gemm_plan_destroy(plan);
-    }
   }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
@@ -188,6 +200,9 @@ inline int make_plan(std::vector<mtrl_gemm_plan_t*>& dst, const std::vector<mtrl
     if (best) mtrl_gemm_plan_destroy(best);
     return rc;
   }
+  if (getenv("MTRL_GEMM_AUTOTUNE_LOG"))
+    fprintf(stderr, "[mtrl gemm autotune] %zu problems (M %d N %d K %d ...): ctas %d, %d units, %.1f us\n", probs.size(), probs[0].M,
+            probs[0].N, probs[0].K, mtrl_gemm_plan_ctas(best), mtrl_gemm_plan_units(best), best_ms * 1e3f);
   dst.push_back(best);
   return MTRL_OK;
 }

@@ -516,6 +516,7 @@ int launch_trunk_step(mtrl_sac* h, comm::TrunkStepArgs& a, long long off_grads, 
   mtrl_comm* c = h->comm;
   a.segs = segs;
   a.nsegs = nsegs;
+  a.status = h->ws.status;
   a.rank = c->rank;
   a.world = c->world;
   for (int q = 0; q < c->world; ++q) {
@@ -731,7 +732,7 @@ int step_critic_grads(mtrl_sac* h, cudaStream_t st) {
     // the dW epilogues are about to reduce-add into peer gradient buffers: every rank must have zeroed its own
     // (step_begin) first.  One warp; ranks left the previous update together, so this rarely waits.
     MTRL_PROPAGATE(prof_begin(h, 1, st));
-    comm::rank_barrier_kernel<<<1, 32, 0, st>>>(h->comm->d_peer_hdr, h->comm->rank, h->comm->world);
+    comm::rank_barrier_kernel<<<1, 32, 0, st>>>(h->comm->d_peer_hdr, h->comm->rank, h->comm->world, h->ws.status);
     MTRL_CUDA_CHECK(cudaGetLastError());
     MTRL_PROPAGATE(prof_end(h, st));
     LAUNCHED(h);

@@ -520,6 +520,10 @@ class MTSAC:
             self._status_event.synchronize()
             self._pending_status = False
             code = int(self._status_host[0])
+            if int(self._status_host[1]) != 0:
+                raise L.MtrlError(f"rank {self.rank}: the peer-memory exchange timed out waiting for another rank (code "
+                                  f"{int(self._status_host[1])}); no rank applied the step in flight and the exchange is disabled -- "
+                                  "restart the job (MTRL_COMM_TIMEOUT_S sets how long a straggler is waited for)")
             if code == 1:
                 raise ValueError("update: a batch row belongs to a task outside this rank's range "
                                  f"[{self.task_begin}, {self.task_end})")

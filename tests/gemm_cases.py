@@ -70,10 +70,10 @@ def make_problem_x3(M, N, K, a_major, b_major, epilogue, block_n=256, k_splits=1
     return p, D, D_lo, ref, (Ah, Al, Bh, Bl, bias, mask)
 
 
-def run_case_x3(case, dev="cuda", with_d_lo=True):
+def run_case_x3(case, dev="cuda", with_d_lo=True, ctas=0):
     name, M, N, K, am, bm, epi, bn, ks = case
     p, D, D_lo, ref, keep = make_problem_x3(M, N, K, am, bm, epi, bn, ks, dev=dev, with_d_lo=with_d_lo)
-    L.GemmPlan([p]).run()
+    L.GemmPlan([p], ctas=ctas).run()
     torch.cuda.synchronize()
     out = D.double() + (D_lo.double() if D_lo is not None else 0)
     return ((out - ref).norm() / ref.norm().clamp_min(1e-30)).item(), D, D_lo
@@ -108,10 +108,11 @@ CASES = [
 ]
 
 
-def run_case(case, dev="cuda"):
+def run_case(case, dev="cuda", ctas=0):
     name, M, N, K, am, bm, epi, bn, ks = case
     p, D, ref, keep = make_problem(M, N, K, am, bm, epi, bn, ks, dev=dev)
-    plan = L.GemmPlan([p])
+    plan = L.GemmPlan([p], ctas=ctas)
+    assert ctas == 0 or plan.ctas == ctas
     plan.run()
     torch.cuda.synchronize()
     r, a = rel_err(D, ref, epi)

@@ -21,6 +21,20 @@ def test_gemm_case(cuda, idx):
 
 
 @pytest.mark.parametrize("idx", range(16))
+def test_gemm_case_single_cta_tiles(cuda, idx):
+    """The 128-row single-CTA tile shape (mtrl_gemm_plan_create_ex ctas = 1), which the plan autotuner picks for launches
+    with too few 256-row units (one rank's rows of a sharded batch)."""
+    import gemm_cases as G
+
+    case = G.CASES[idx]
+    rel, _ = G.run_case(case, ctas=1)
+    assert rel < 5e-4, f"{case[0]}: rel err {rel}"
+    if idx in (3, 6, 8):
+        rel3, _, _ = G.run_case_x3(case, ctas=1)
+        assert rel3 < 3e-6, f"{case[0]} fp32x3: rel err {rel3}"
+
+
+@pytest.mark.parametrize("idx", range(16))
 def test_gemm_case_fp32x3(cuda, idx):
     """fp32x3 mode (A_lo / B_lo / D_lo): full fp32 operands as (hi, lo) tf32 pairs, three tensor-core passes; the result
     (D + D_lo where the epilogue rounds) must match the fp64 product of the UNSPLIT operands to fp32-level accuracy."""
