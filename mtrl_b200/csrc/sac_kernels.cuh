@@ -896,6 +896,21 @@ static __global__ void __launch_bounds__(RG * 32, ((RG == 8 && HD <= 8) || HD <=
     if (blockIdx.x == 0 && threadIdx.x < HD)
       for (int r = 0; r < kTileRows; ++r) bsum += sd[r * HD + threadIdx.x];
   }
+  // Tiles past the last task's rows (max_rows leaves room for uneven batches) belong to nobody: their dZ rows and
+  // column-sum partials must read as zero for the dW / dX GEMMs and the bias-gradient sum, which run over all max_rows
+  // rows -- otherwise they would see whatever an earlier kernel left there (the partials buffer is shared with the
+  // 32-row partials of the dX epilogue).  The last task's blocks clear them.
+  if (t == gridDim.y - 1 && kok) {
+    for (int base = r1; base + kTileRows <= p.M; base += kTileRows) {
+      for (int r = warp; r < kTileRows; r += RG) {
+        float* dzp = dZ + static_cast<long long>(base + r) * p.W + k;
+        *reinterpret_cast<float4*>(dzp) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.dz_lo_delta) *reinterpret_cast<float4*>(dzp + p.dz_lo_delta) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (p.colsum[e] && warp == 0)
+        *reinterpret_cast<float4*>(p.colsum[e] + static_cast<long long>(base / kTileRows) * p.W + k) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
   if (p.dWh[e]) {
 #pragma unroll
     for (int j = 0; j < HD; ++j) {

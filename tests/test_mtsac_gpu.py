@@ -129,7 +129,7 @@ def run_case_x3(cfg, per_task, seed=1, steps=1, shuffle=False, counts=None, tol=
         if counts is not None:
             task = batch[0][:, -cfg.num_tasks:].argmax(1)
             keep = torch.zeros(task.shape[0], dtype=torch.bool)
-            for t, n in enumerate(counts):
+            for t, n in enumerate(counts[step] if isinstance(counts[0], (list, tuple)) else counts):
                 keep[(task == t).nonzero().flatten()[:n]] = True
             batch, ec, ea = tuple(b[keep] for b in batch), ec[keep], ea[keep]
         if shuffle:
@@ -180,6 +180,14 @@ def test_fp32x3_mt10_w400_reference_config_every_leaf(cuda):
 def test_fp32x3_shuffled_uneven_rows_every_leaf(cuda):
     cfg = O.OracleConfig(num_tasks=5, obs_dim=20 + 5, action_dim=3, width=96)
     run_case_x3(cfg, per_task=40, shuffle=True, counts=[40, 1, 17, 33, 8])
+
+
+def test_fp32x3_spare_tiles_and_shrinking_batches_every_leaf(cuda):
+    """max_rows leaves room for uneven batches, so some 128-row tiles belong to no task, and which ones changes from update
+    to update (task 1 needs two tiles in the first update, one afterwards).  Their dZ rows and bias-gradient partials must
+    not leak stale values into dW / the bias gradients: three updates, every leaf (biases included) to 1e-3."""
+    cfg = O.OracleConfig(num_tasks=5, obs_dim=20 + 5, action_dim=3, width=96)
+    run_case_x3(cfg, per_task=130, steps=3, shuffle=True, counts=[[40, 130, 17, 33, 8], [40, 1, 17, 33, 8], [3, 2, 1, 60, 8]])
 
 
 def test_fp32x3_task_weights_clip_depth2_one_critic_every_leaf(cuda):
