@@ -253,6 +253,50 @@ int mtrl_sac_phase3_actor_step_alpha(mtrl_sac_t* h, void* stream);
  * set the status word (mtrl_sac_read_status_async) and come back as zeros.  Not re-entrant with mtrl_sac_update. */
 int mtrl_sac_act(mtrl_sac_t* h, const float* obs, int n, const float* eps, int deterministic, float* actions_out,
                  void* stream);
+/* MultiHeadNetwork.__call__ (mtrl/nn/multi_head.py:21-68) of one of the handle's networks on n arbitrary rows (device fp32
+ * obs (n, obs_dim), actions (n, action_dim) for the critics; any owned tasks, any order; n <= max_rows):
+ *   net 0  the actor          -> out (n, 2 * action_dim): what ContinuousActionPolicy splits into mean / log_std (networks.py:36-37)
+ *   net 1  the critic ensemble -> out (num_critics, n, 1): QValueFunction on concatenate((actions, obs)) (networks.py:55-67, 208-222)
+ *   net 2  the target critics, same shape
+ * Trunk layers run as the update's tcgen05 GEMMs in the handle's precision, then each row's own head.  Uses the update's
+ * activation buffers as scratch: not re-entrant with mtrl_sac_update.  Rows of tasks this handle does not own set status
+ * word 0 (mtrl_sac_read_status_async) and come back as zeros. */
+int mtrl_mlp_forward(mtrl_sac_t* h, int net, const float* obs, const float* actions, int n, float* out, void* stream);
+/* optax.chain(clip_by_global_norm(max_grad_norm), adam(lr, b1, b2, eps)) + apply_updates (mtrl/config/optim.py:26-43,
+ * mtrl/rl/algorithms/utils.py:11-46), optionally followed by optax.incremental_update(params, target, tau)
+ * (mtsac.py:607-613), on caller-owned flat device fp32 buffers of n elements (n % 4 == 0, 16-byte aligned; target may be
+ * NULL; max_grad_norm <= 0: no clipping).  step: device int, the Adam count, incremented.  scratch: device double[5]
+ * receiving [0] the squared gradient norm (before clipping), [1] |params'|^2, [3] |params|^2 before the step. */
+int mtrl_adam_polyak_step(float* params, const float* grads, float* m, float* v, float* target, long long n, int* step, float lr,
+                          float b1, float b2, float eps, float max_grad_norm, float tau, double* scratch, void* stream);
+/* The fused SAC loss pass alone: min over the target ensemble, entropy term, Bellman target, clip, weighted MSE and dL/dQ
+ * (mode 0: mtsac.py:547-566) or the actor loss alpha logp - min_e Q_e with the arg-min routing of its gradient (mode 1:
+ * mtsac.py:659-666), from the LAST trunk activations and the heads' parameters.  Rows are packed in 128-row tiles, all
+ * rows of a tile belonging to one task (tile_task), padding rows marked by row_valid < 0. */
+typedef struct mtrl_sac_losses_args {
+  int mode;                      /* 0 critic loss, 1 actor loss                                                    */
+  int rows, width, num_critics;  /* rows: multiple of 128                                                          */
+  int global_batch;              /* the B every mean divides by                                                    */
+  int clip_q;                    /* mode 0: clamp target and prediction to +-5000 (AlgorithmConfig.clip)           */
+  float gamma;
+  const float* H_target[4];      /* mode 0: [rows][width] last trunk activation of every target critic             */
+  const float* H_online[4];      /* [rows][width] of every online critic                                           */
+  const float* w_target[4];      /* (T, width, 1) head kernels                                                     */
+  const float* b_target[4];      /* (T, 1)                                                                         */
+  const float* w_online[4];
+  const float* b_online[4];
+  const int* tile_task;          /* [rows / 128]                                                                   */
+  const int* row_valid;          /* [rows]: < 0 marks a padding row                                                */
+  const float* rewards;          /* mode 0: [rows]                                                                 */
+  const float* dones;            /* mode 0: [rows]                                                                 */
+  const float* logp_next;        /* mode 0: [rows] log pi(a'|s')                                                   */
+  const float* logp;             /* mode 1: [rows] log pi(a|s)                                                     */
+  const float* alpha;            /* [T] exp(log_alpha)                                                             */
+  const float* task_weights;     /* [T] (ones when use_task_weights is off)                                        */
+  float* dq;                     /* out [num_critics][rows]: dL/dQ_e                                               */
+  double* acc;                   /* out double[4]: mode 0: [0] sum w (Q - y)^2, [1] sum Q; mode 1: [2] sum w (alpha logp - min Q) */
+} mtrl_sac_losses_args_t;
+int mtrl_sac_losses_fwd_bwd(const mtrl_sac_losses_args_t* args, void* stream);
 /* Per-task gradients, the first half of MTSAC.compute_weights (mtsac.py:870-1170: batch split by task,
  * jax.vmap(jax.value_and_grad(critic_loss / actor_loss)) over tasks).  critic_tg: device fp32 (T, critic layout.total),
  * actor_tg: (T, actor layout.total), row t = gradient of task t in the flat network layout (zero outside task t's own

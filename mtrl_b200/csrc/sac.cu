@@ -160,6 +160,7 @@ struct mtrl_sac {
   mtrl_comm* comm = nullptr;
   long long off_critic_grads = 0, off_actor_grads = 0, off_critic_params = 0, off_actor_params = 0;
   std::map<int, std::vector<mtrl_gemm_plan_t*>> act_plans;   // actor forward plans of mtrl_sac_act, by row count
+  std::map<std::pair<int, int>, std::vector<mtrl_gemm_plan_t*>> mlp_plans;   // mtrl_mlp_forward plans by (network, rows)
   unsigned long long act_calls = 0;
   // per-task gradient path (mtrl_sac_task_grads): grouped per-task dW plans [critic/actor][layer] -> launches
   struct TaskGradCache {
@@ -598,6 +599,8 @@ extern "C" void mtrl_sac_destroy(mtrl_sac_t* h) {
   for (auto* v : {&h->fwd, &h->fwd_target, &h->bwd_critic, &h->fwd_pi, &h->bwd_pi, &h->bwd_actor})
     for (auto* p : *v) mtrl_gemm_plan_destroy(p);
   for (auto& kv : h->act_plans)
+    for (auto* p : kv.second) mtrl_gemm_plan_destroy(p);
+  for (auto& kv : h->mlp_plans)
     for (auto* p : kv.second) mtrl_gemm_plan_destroy(p);
   for (auto* v : {&h->tgc.critic, &h->tgc.actor})
     for (auto& launches : *v)
@@ -1065,6 +1068,141 @@ extern "C" int mtrl_sac_act(mtrl_sac_t* h, const float* obs, int n, const float*
   const int wpb = 8;
   dim3 grid((n + wpb - 1) / wpb), block(wpb * 32);
   launch_actor_head_rows(a, c.action_dim, grid, block, st);
+  MTRL_CUDA_CHECK(cudaGetLastError());
+  return MTRL_OK;
+}
+
+// MultiHeadNetwork.__call__ (mtrl/nn/multi_head.py:21-68) of one of the handle's networks on arbitrary rows, alone:
+// trunk layers as the tcgen05 GEMMs of the update (same precision mode), then the row's own head.
+//   net 0: the actor   -> out (n, 2 A)   = the head outputs ContinuousActionPolicy splits into mean / log_std (networks.py:36-37)
+//   net 1: the critics -> out (E, n, 1)  = QValueFunction on concatenate((actions, obs)) (networks.py:55-67), ensemble axis first
+//   net 2: the target critics, same shape
+// Uses the update's activation buffers as scratch (not re-entrant with mtrl_sac_update); rows of tasks this handle does
+// not own set status word 0 and give zeros.
+extern "C" int mtrl_mlp_forward(mtrl_sac_t* h, int net, const float* obs, const float* actions, int n, float* out, void* stream) {
+  MTRL_REQUIRE(h && obs && out, "mtrl_mlp_forward: null argument");
+  MTRL_REQUIRE(net >= 0 && net <= 2, "mtrl_mlp_forward: net %d outside {0 actor, 1 critic, 2 target critic}", net);
+  MTRL_REQUIRE(net == 0 || actions, "mtrl_mlp_forward: the critic needs actions");
+  const mtrl_sac_config_t& c = h->cfg;
+  MTRL_REQUIRE(n >= 1 && n <= c.max_rows, "mtrl_mlp_forward: %d rows outside [1, max_rows = %d]", n, c.max_rows);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Workspace& w = h->ws;
+  const bool actor = net == 0;
+  const mtrl_net_layout_t& L = actor ? h->lay.actor : h->lay.critic;
+  const int W = c.width, D = c.depth, E = actor ? 1 : c.num_critics, K = actor ? h->lay.k_actor : h->lay.k_critic;
+  float* X = actor ? w.Xa : (net == 1 ? w.Xc : w.Xc_next);
+  float* params = actor ? h->buf.actor_params : (net == 1 ? h->buf.critic_params : h->buf.critic_target);
+  float* sh = actor ? h->buf.actor_shadow : (net == 1 ? h->buf.critic_shadow : h->buf.critic_target_shadow);
+  float* sh_lo = actor ? w.ash_lo : (net == 1 ? w.csh_lo : w.tsh_lo);
+  auto act_buf = [&](int e, int l) { return actor ? w.Ao[l] : (net == 1 ? w.C[e][l] : w.Tg[e][l]); };
+  auto key = std::make_pair(net, n);
+  auto it = h->mlp_plans.find(key);
+  if (it == h->mlp_plans.end()) {
+    std::vector<mtrl_gemm_plan_t*> plans;
+    for (int l = 0; l < D; ++l) {
+      std::vector<mtrl_gemm_problem_t> p;
+      for (int e = 0; e < E; ++e) {
+        float* in = l == 0 ? X : act_buf(e, l - 1);
+        p.push_back(fwd_problem(in, l == 0 ? K : W, l == 0 ? L.in_dim : W, tk(sh, L, e, l), tb(params, L, e, l), act_buf(e, l), n, W,
+                                nullptr, lo(h, in), tk_lo(sh_lo, L, e, l), lo(h, act_buf(e, l))));
+      }
+      MTRL_PROPAGATE(make_plan_plain(plans, p));
+    }
+    it = h->mlp_plans.emplace(key, plans).first;
+  }
+  MTRL_CUDA_CHECK(cudaMemsetAsync(w.status, 0, 16, st));
+  mlp_pack_kernel<<<n, 128, 0, st>>>(obs, actor ? nullptr : actions, c.obs_dim, c.action_dim, K, c.num_tasks, c.task_begin,
+                                     c.num_local_tasks, X, w.slot_src, w.status, w.lo_delta);
+  MTRL_CUDA_CHECK(cudaGetLastError());
+  for (auto* plan : it->second) MTRL_PROPAGATE(mtrl_gemm_plan_run(plan, st));
+  HeadFwdArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int e = 0; e < E; ++e) {
+    a.H[e] = act_buf(e, D - 1);
+    a.Wh[e] = hk(params, L, e);
+    a.bh[e] = hb(params, L, e);
+  }
+  a.row_task = w.slot_src; a.out = out; a.h_lo_delta = w.lo_delta; a.n = n; a.W = W; a.HD = L.head_dim; a.E = E;
+  head_fwd_kernel<<<(n * E + 7) / 8, 256, 0, st>>>(a);
+  MTRL_CUDA_CHECK(cudaGetLastError());
+  return MTRL_OK;
+}
+
+// optax.chain(clip_by_global_norm(max_grad_norm), adam(lr, b1, b2, eps)) + apply_updates (mtrl/config/optim.py:26-43,
+// mtrl/rl/algorithms/utils.py:11-46) and optax.incremental_update (mtsac.py:607-613) on caller-owned flat buffers, as one
+// stand-alone operator: the two kernels the fused update runs (sumsq_kernel, adam_kernel).
+extern "C" int mtrl_adam_polyak_step(float* params, const float* grads, float* m, float* v, float* target, long long n, int* step,
+                                     float lr, float b1, float b2, float eps, float max_grad_norm, float tau, double* scratch,
+                                     void* stream) {
+  MTRL_REQUIRE(params && grads && m && v && step && scratch, "mtrl_adam_polyak_step: null argument");
+  MTRL_REQUIRE(n >= 4 && n % 4 == 0, "mtrl_adam_polyak_step: n %lld must be a positive multiple of 4", n);
+  for (const void* p : {static_cast<const void*>(params), static_cast<const void*>(grads), static_cast<const void*>(m),
+                        static_cast<const void*>(v), static_cast<const void*>(target)})
+    MTRL_REQUIRE((reinterpret_cast<uintptr_t>(p) & 15u) == 0, "mtrl_adam_polyak_step: buffers must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // scratch: [0] squared gradient norm, [1] |params_new|^2, [2] unused (head part), [3] |params_old|^2, [4] = 0.0f slot
+  MTRL_CUDA_CHECK(cudaMemsetAsync(scratch, 0, 5 * sizeof(double), st));
+  sumsq_kernel<<<sms * 2, 256, 0, st>>>(grads, n, scratch);
+  AdamArgs a;
+  memset(&a, 0, sizeof(a));
+  a.p = params; a.m = m; a.v = v; a.g = grads; a.target = target;
+  a.n = n; a.trunk_n = n;   // no reduction slots in a caller-owned buffer
+  a.g2_trunk = scratch; a.g2_heads = reinterpret_cast<const float*>(scratch + 4);
+  a.step = step;
+  a.p2_trunk = scratch + 1; a.p2_head = scratch + 2; a.p2_old = scratch + 3;
+  a.lr = lr; a.b1 = b1; a.b2 = b2; a.eps = eps; a.max_norm = max_grad_norm; a.tau = tau;
+  adam_kernel<<<sms * 4, 256, 0, st>>>(a);
+  step_inc_kernel<<<1, 1, 0, st>>>(step);
+  MTRL_CUDA_CHECK(cudaGetLastError());
+  return MTRL_OK;
+}
+
+// The fused SAC loss pass alone (mtsac.py:547-566, 659-666): from the last trunk activations of the target / online
+// critics (and the heads' parameters) to the loss sums and dL/dQ, for rows already packed in 128-row tiles of one task.
+extern "C" int mtrl_sac_losses_fwd_bwd(const mtrl_sac_losses_args_t* a, void* stream) {
+  MTRL_REQUIRE(a, "mtrl_sac_losses_fwd_bwd: null argument");
+  MTRL_REQUIRE(a->num_critics >= 1 && a->num_critics <= kMaxE, "mtrl_sac_losses_fwd_bwd: num_critics %d outside [1, %d]",
+               a->num_critics, kMaxE);
+  MTRL_REQUIRE(a->rows >= kTileRows && a->rows % kTileRows == 0 && a->width >= 4 && a->width % 4 == 0,
+               "mtrl_sac_losses_fwd_bwd: rows %d must be a multiple of %d and width %d of 4", a->rows, kTileRows, a->width);
+  MTRL_REQUIRE(a->tile_task && a->row_valid && a->alpha && a->task_weights && a->dq && a->acc && a->global_batch >= 1,
+               "mtrl_sac_losses_fwd_bwd: null pointer or empty batch");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int M = a->rows, E = a->num_critics;
+  MTRL_CUDA_CHECK(cudaMemsetAsync(a->acc, 0, 4 * sizeof(double), st));
+  // the kernels index their accumulators by ACC_*: give them a base such that ACC_QLOSS / ACC_QSUM / ACC_ACTOR_LOSS land
+  // in acc[0], acc[1], acc[2]
+  static_assert(ACC_QLOSS == 0 && ACC_QSUM == 1, "accumulator layout");
+  if (a->mode == 0) {
+    MTRL_REQUIRE(a->rewards && a->dones && a->logp_next, "mtrl_sac_losses_fwd_bwd: the critic loss needs rewards, dones, logp_next");
+    CriticLossArgs p;
+    memset(&p, 0, sizeof(p));
+    for (int e = 0; e < E; ++e) {
+      MTRL_REQUIRE(a->H_target[e] && a->H_online[e] && a->w_target[e] && a->w_online[e] && a->b_target[e] && a->b_online[e],
+                   "mtrl_sac_losses_fwd_bwd: null member pointer");
+      p.target.H[e] = a->H_target[e]; p.target.w[e] = a->w_target[e]; p.target.b[e] = a->b_target[e];
+      p.online.H[e] = a->H_online[e]; p.online.w[e] = a->w_online[e]; p.online.b[e] = a->b_online[e];
+    }
+    p.tile_task = a->tile_task; p.slot_src = a->row_valid; p.rew = a->rewards; p.done = a->dones; p.logp_next = a->logp_next;
+    p.alpha_val = a->alpha; p.task_w = a->task_weights; p.dq = a->dq; p.acc = a->acc; p.M = M; p.W = a->width; p.E = E;
+    p.gamma = a->gamma; p.dq_scale = 2.f / (static_cast<float>(E) * static_cast<float>(a->global_batch)); p.clip = a->clip_q;
+    critic_loss_kernel<<<(M + 7) / 8, 256, 0, st>>>(p);
+  } else {
+    MTRL_REQUIRE(a->logp, "mtrl_sac_losses_fwd_bwd: the actor loss needs logp");
+    ActorLossArgs p;
+    memset(&p, 0, sizeof(p));
+    for (int e = 0; e < E; ++e) {
+      MTRL_REQUIRE(a->H_online[e] && a->w_online[e] && a->b_online[e], "mtrl_sac_losses_fwd_bwd: null member pointer");
+      p.online.H[e] = a->H_online[e]; p.online.w[e] = a->w_online[e]; p.online.b[e] = a->b_online[e];
+    }
+    p.tile_task = a->tile_task; p.slot_src = a->row_valid; p.logp = a->logp; p.alpha_val = a->alpha; p.task_w = a->task_weights;
+    p.dq = a->dq; p.acc = a->acc - ACC_ACTOR_LOSS + 2; p.M = M; p.W = a->width; p.E = E;
+    p.inv_b = 1.f / static_cast<float>(a->global_batch);
+    actor_loss_kernel<<<(M + 7) / 8, 256, 0, st>>>(p);
+  }
   MTRL_CUDA_CHECK(cudaGetLastError());
   return MTRL_OK;
 }

@@ -275,6 +275,76 @@ static __global__ void act_pack_kernel(const float* __restrict__ obs, int n, int
   }
 }
 
+// Stand-alone network forward (mtrl_mlp_forward): rows of any owned tasks, in the caller's order.  Writes the padded GEMM
+// input row [actions | obs] (actions == nullptr: [obs], the actor's input) and the row's task.  One block per row.
+static __global__ void mlp_pack_kernel(const float* __restrict__ obs, const float* __restrict__ actions, int obs_dim, int act_dim,
+                                       int K, int T, int task_begin, int T_local, float* __restrict__ X, int* __restrict__ row_task,
+                                       int* __restrict__ status, long long lo_delta) {
+  const int row = blockIdx.x;
+  const float* o = obs + static_cast<long long>(row) * obs_dim;
+  const int A = actions ? act_dim : 0;
+  float* x = X + static_cast<long long>(row) * K;
+  for (int j = threadIdx.x; j < K; j += blockDim.x) {
+    float v = 0.f;
+    if (j < A) v = actions[static_cast<long long>(row) * act_dim + j];
+    else if (j < A + obs_dim) v = o[j - A];
+    store_operand(x + j, lo_delta, v);
+  }
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    const float* oh = o + (obs_dim - T);
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int t = lane; t < T; t += 32) {
+      const float v = oh[t];
+      if (v > best) { best = v; bi = t; }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) {
+      int task = bi - task_begin;
+      if (task < 0 || task >= T_local) { atomicExch(status, 1); task = -1; }
+      row_task[row] = task;
+    }
+  }
+}
+
+// out[e][row][j] = H_e[row] . Wh_e[task(row)][:, j] + bh_e[task(row)][j]: the own-task head of MultiHeadNetwork
+// (multi_head.py:50-66) for rows in arbitrary order.  One warp per (row, member); rows of foreign tasks give zeros.
+struct HeadFwdArgs {
+  const float* H[kMaxE];    // [n][W]
+  const float* Wh[kMaxE];   // (T_local, W, HD)
+  const float* bh[kMaxE];   // (T_local, HD)
+  const int* row_task;
+  float* out;               // [E][n][HD]
+  long long h_lo_delta;
+  int n, W, HD, E;
+};
+static __global__ void head_fwd_kernel(const HeadFwdArgs p) {
+  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (gw >= p.n * p.E) return;
+  const int e = gw / p.n, row = gw % p.n;
+  const int t = p.row_task[row];
+  float* o = p.out + (static_cast<long long>(e) * p.n + row) * p.HD;
+  const float* h = p.H[e] + static_cast<long long>(row) * p.W;
+  for (int j = 0; j < p.HD; ++j) {
+    float s = 0.f;
+    if (t >= 0) {
+      const float* w = p.Wh[e] + static_cast<long long>(t) * p.W * p.HD + j;
+      for (int k = lane; k < p.W; k += 32) {
+        const float hv = p.h_lo_delta ? h[k] + h[k + p.h_lo_delta] : h[k];
+        s = fmaf(hv, __ldg(w + static_cast<long long>(k) * p.HD), s);
+      }
+    }
+    s = warp_sum(s);
+    if (lane == 0) o[j] = t >= 0 ? s + p.bh[e][t * p.HD + j] : 0.f;
+  }
+}
+
 // alpha_t = exp(log_alpha_t) (MultiTaskTemperature, mtsac.py:60-63); w_t = T * softmax(-log_alpha)_t
 // (extract_task_weights, mtsac.py:103-113) or 1.
 static __global__ void alpha_prep_kernel(const float* __restrict__ log_alpha, int T_local, int use_w, float* __restrict__ alpha_val,
@@ -1513,11 +1583,11 @@ static __global__ void adam_kernel(const AdamArgs a) {
     reinterpret_cast<float4*>(a.m)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
     reinterpret_cast<float4*>(a.v)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
     reinterpret_cast<float4*>(a.p)[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
-    reinterpret_cast<float4*>(a.shadow)[i] = make_float4(sh[0], sh[1], sh[2], sh[3]);
+    if (a.shadow) reinterpret_cast<float4*>(a.shadow)[i] = make_float4(sh[0], sh[1], sh[2], sh[3]);
     if (a.shadow_lo) reinterpret_cast<float4*>(a.shadow_lo)[i] = make_float4(shl[0], shl[1], shl[2], shl[3]);
     if (a.target) {
       reinterpret_cast<float4*>(a.target)[i] = make_float4(tt[0], tt[1], tt[2], tt[3]);
-      reinterpret_cast<float4*>(a.target_shadow)[i] = make_float4(tsh[0], tsh[1], tsh[2], tsh[3]);
+      if (a.target_shadow) reinterpret_cast<float4*>(a.target_shadow)[i] = make_float4(tsh[0], tsh[1], tsh[2], tsh[3]);
       if (a.target_shadow_lo) reinterpret_cast<float4*>(a.target_shadow_lo)[i] = make_float4(tshl[0], tshl[1], tshl[2], tshl[3]);
     }
     if (i < slot4) s_trunk += static_cast<double>(sq);
@@ -1541,6 +1611,8 @@ static __global__ void shadow_kernel(const float* __restrict__ p, float* __restr
     if (s_lo) s_lo[i] = tf32_lo(p[i], hi);
   }
 }
+
+static __global__ void step_inc_kernel(int* step) { *step += 1; }
 
 // Single thread: turn accumulators into the reference's log scalars and advance the Adam count.
 static __global__ void finalize_critic_kernel(const double* acc, const float* g2_heads, int* steps, float* logs, float inv_eb,

@@ -268,7 +268,9 @@ extern "C" int mtrl_sampler_create(mtrl_sampler_t** out, int capacity, int num_t
   s->store[2] = next_obs;
   s->store[3] = dones;
   s->store[4] = rewards;
-  s->idx_cap = 4096;
+  // an index draw never exceeds the ring capacity (sampling more rows than that is refused like numpy's IndexError), so
+  // the scratch is sized from it: sample(ndarray) may legitimately ask one task for up to 128 * T rows (buffers.py:498)
+  s->idx_cap = capacity > 4096 ? capacity : 4096;
   if (cudaMalloc(&s->state, sizeof(PcgState)) != cudaSuccess ||
       cudaMalloc(&s->idx, sizeof(long long) * s->idx_cap) != cudaSuccess) {
     mtrl_set_error("mtrl_sampler_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));

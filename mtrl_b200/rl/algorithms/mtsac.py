@@ -104,6 +104,7 @@ L._EXTRA_DECLS.update({
     "mtrl_sac_launches_per_update": ([_vp],),
     "mtrl_sac_read_status_async": ([_vp, _vp, _vp],),
     "mtrl_sac_act": ([_vp, _vp, _i, _vp, _i, _vp, _vp],),
+    "mtrl_mlp_forward": ([_vp, _i, _vp, _vp, _i, _vp, _vp],),
     "mtrl_sac_task_grads": ([_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp],),
     "mtrl_sac_enable_pcgrad": ([_vp, _i, _i, _vp, _vp, _vp, _vp, _vp],),
     "mtrl_sac_enable_cagrad": ([_vp, _i, _i, _vp, _vp, _vp],),
@@ -916,6 +917,32 @@ class MTSAC:
         self._status_event.record()
         self._pending_status = True
         return out
+
+    def network_forward(self, net: str, observations, actions=None) -> torch.Tensor:
+        """`MultiHeadNetwork.__call__` (mtrl/nn/multi_head.py:21-68) of one of the agent's networks on arbitrary rows, as a
+        CUDA tensor: net="actor" -> (n, 2 * action_dim) head outputs (mean | log_std before the clip, networks.py:36-40);
+        net="critic" / "target" -> (num_critics, n, 1) Q-values of `QValueFunction` on (actions, observations)
+        (networks.py:55-67, 208-222).  C entry `mtrl_mlp_forward`."""
+        code = {"actor": 0, "critic": 1, "target": 2}[net]
+        obs = self._dev(observations)
+        if obs.dim() == 1:
+            obs = obs[None]
+        n, c = obs.shape[0], self._cfg
+        assert obs.shape[1] == c.obs_dim
+        act = None
+        if code:
+            if actions is None:
+                raise ValueError("the critic takes (observations, actions)")
+            act = self._dev(actions).reshape(n, c.action_dim)
+        E, hd = (1, 2 * c.action_dim) if code == 0 else (c.num_critics, 1)
+        out = torch.empty(E, n, hd, dtype=torch.float32, device=self.device)
+        stream = _vp(L.current_stream_ptr())
+        L.check(L.lib().mtrl_mlp_forward(self._h, code, _vp(obs.data_ptr()), _vp(act.data_ptr() if act is not None else None), n,
+                                         _vp(out.data_ptr()), stream))
+        L.check(L.lib().mtrl_sac_read_status_async(self._h, _vp(self._status_host.data_ptr()), stream))
+        self._status_event.record()
+        self._pending_status = True
+        return out[0] if code == 0 else out
 
     def sample_action(self, observation, task_ids=None, eps=None):
         """mtsac.py:299-304: `(self, action)` with the action on the host as a NumPy array (the reference returns

@@ -165,3 +165,27 @@ def test_raw_draws_match_live_numpy_including_rejections(cuda, high):
     assert st["state"] == ref_st["state"] and st["has_uint32"] == ref_st["has_uint32"]
     if ref_st["has_uint32"]:
         assert st["uinteger"] == ref_st["uinteger"]
+
+
+def test_per_task_counts_beyond_4096_rows(cuda):
+    """sample(ndarray) only requires sum == 128 T (buffers.py:498), so with MT50 a single task may receive thousands of
+    rows; the index scratch is sized from the ring capacity (it used to be a fixed 4096)."""
+    from oracle.sampler_oracle import MultiTaskReplayBufferOracle
+
+    T, od, ad, cap = 50, 6, 2, 6000
+    buf = make(T, od, ad, cap, seed=4)
+    orc = MultiTaskReplayBufferOracle(cap * T, T, od, ad, seed=4)
+    rng = np.random.default_rng(1)
+    obs = rng.standard_normal((cap, T, od)).astype(np.float32)
+    for name in ("obs", "next_obs"):
+        getattr(buf, name).copy_(torch.from_numpy(obs))
+        getattr(orc, name)[:] = obs
+    buf.full = orc.full = True
+    counts = np.zeros(T, dtype=np.int64)
+    counts[3], counts[17] = 5000, 128 * T - 5000
+    a, b = buf.sample(counts), orc.sample(counts)
+    for x, y in zip(a, b):
+        assert np.array_equal(x.cpu().numpy(), y)
+    big = buf.sample(5000 * T)          # sample(int) with more than 4096 rows per task
+    ref = orc.sample(5000 * T)
+    assert np.array_equal(big.observations.cpu().numpy(), ref.observations)
