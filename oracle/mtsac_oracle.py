@@ -57,6 +57,10 @@ class OracleConfig:
     #         sm_100a kernels do, which is also what XLA's default f32 dot precision does on NVIDIA GPUs.
     #         Used by tests to separate kernel correctness from the tf32 ReLU-gate effect.
     matmul_operands: str = "exact"
+    # VanillaNetworkConfig.use_layer_norm / use_skip_connections (mtrl/config/nn.py:33-39): only read by the MLP of the
+    # single-task SAC / MT-PPO oracles (mtrl/nn/base.py:32-63); MultiHeadNetwork has neither.
+    use_layer_norm: bool = False
+    use_skip_connections: bool = False
 
     @property
     def target_entropy(self) -> float:  # mtsac.py:258

@@ -1,7 +1,8 @@
 """Oracle for the single-task SAC update: PyTorch-CPU restatement of `SAC._update_inner`
 (/root/reference/mtrl/rl/algorithms/sac.py:262-383) on `VanillaNetwork` / `MLP`
-(/root/reference/mtrl/nn/base.py:11-89, no layer norm, no skip connections -- the settings of every
-SAC experiment in the reference, e.g. experiments/baselines/mt10_sac_v2.py:36-50).
+(/root/reference/mtrl/nn/base.py:11-89), including its optional pre-layer LayerNorm and residual connections
+(`VanillaNetworkConfig.use_layer_norm / use_skip_connections`, off in every SAC experiment of the reference, e.g.
+experiments/baselines/mt10_sac_v2.py:36-50, but part of the MLP).
 
 TEST INFRASTRUCTURE (see oracle/__init__.py).  Parity status: PARITY UNPINNED, for the same reasons as
 oracle/mtsac_oracle.py (no reference test or golden vector for the update; JAX stack absent).
@@ -36,6 +37,9 @@ def init_mlp(gen: torch.Generator, in_dim: int, cfg: OracleConfig, head_dim: int
         p[f"layer_{i}"] = {"kernel": u(lead + (d, cfg.width), math.sqrt(6.0 / d)), "bias": torch.zeros(lead + (cfg.width,), dtype=dtype)}
         d = cfg.width
     p[f"layer_{cfg.depth}"] = {"kernel": u(lead + (cfg.width, head_dim), head_bound), "bias": u(lead + (head_dim,), head_bound)}
+    if cfg.use_layer_norm:   # nn.LayerNorm() before layers 1..depth-1 and before the output Dense (base.py:35-37, 52-53):
+        for k in range(cfg.depth):   # Flax names them LayerNorm_0.. in creation order; scale = ones, bias = zeros
+            p[f"LayerNorm_{k}"] = {"scale": torch.ones(lead + (cfg.width,), dtype=dtype), "bias": torch.zeros(lead + (cfg.width,), dtype=dtype)}
     return p
 
 
@@ -52,21 +56,41 @@ def init_state(cfg: OracleConfig, seed: int = 1, dtype=torch.float32) -> OracleS
     return OracleState(actor, critic, tree_map(lambda x: x.clone(), critic), log_alpha, opt)
 
 
-def mlp_forward(p: dict, x: torch.Tensor, depth: int, operands: str = "exact") -> torch.Tensor:
-    h = _rt(x, operands)
+def layer_norm(x: torch.Tensor, scale: torch.Tensor, bias: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
+    """flax.linen.LayerNorm defaults (flax 0.10.4): over the last axis, epsilon 1e-6, use_fast_variance=True, i.e.
+    var = max(E[x^2] - E[x]^2, 0); y = (x - mean) * rsqrt(var + eps) * scale + bias."""
+    mean = x.mean(dim=-1, keepdim=True)
+    var = torch.clamp((x * x).mean(dim=-1, keepdim=True) - mean * mean, min=0.0)
+    return (x - mean) * torch.rsqrt(var + eps) * scale + bias
+
+
+def mlp_forward(p: dict, x: torch.Tensor, depth: int, operands: str = "exact", use_layer_norm: bool = False,
+                use_skip_connections: bool = False) -> torch.Tensor:
+    """MLP.__call__ (mtrl/nn/base.py:32-63).  With use_layer_norm a LayerNorm precedes every Dense except the first
+    (:35-37, 52-53); with use_skip_connections a layer whose input already has the hidden width adds that (normalised)
+    input to its activation (:45-48)."""
+    width = p["layer_0"]["kernel"].shape[-1]
+    h = x
     for i in range(depth):
-        h = _rt(torch.relu(h @ _rt(p[f"layer_{i}"]["kernel"], operands) + p[f"layer_{i}"]["bias"]), operands)
+        if use_layer_norm and i != 0:
+            h = layer_norm(h, p[f"LayerNorm_{i - 1}"]["scale"], p[f"LayerNorm_{i - 1}"]["bias"])
+        h = _rt(h, operands)
+        d = _rt(torch.relu(h @ _rt(p[f"layer_{i}"]["kernel"], operands) + p[f"layer_{i}"]["bias"]), operands)
+        h = h + d if (use_skip_connections and h.shape[-1] == width) else d
+    if use_layer_norm and depth != 0:
+        h = layer_norm(h, p[f"LayerNorm_{depth - 1}"]["scale"], p[f"LayerNorm_{depth - 1}"]["bias"])
     return h @ p[f"layer_{depth}"]["kernel"] + p[f"layer_{depth}"]["bias"]
 
 
 def critic_forward(p: dict, obs, act, cfg: OracleConfig) -> torch.Tensor:
     x = torch.cat((act, obs), dim=-1)  # networks.py:61
     E = p["layer_0"]["kernel"].shape[0]
-    return torch.stack([mlp_forward(tree_map(lambda t: t[e], p), x, cfg.depth, cfg.matmul_operands) for e in range(E)], 0)
+    return torch.stack([mlp_forward(tree_map(lambda t: t[e], p), x, cfg.depth, cfg.matmul_operands, cfg.use_layer_norm,
+                                    cfg.use_skip_connections) for e in range(E)], 0)
 
 
 def actor_sample_and_log_prob(p: dict, obs, eps, cfg: OracleConfig):
-    out = mlp_forward(p, obs, cfg.depth, cfg.matmul_operands)
+    out = mlp_forward(p, obs, cfg.depth, cfg.matmul_operands, cfg.use_layer_norm, cfg.use_skip_connections)
     mean, log_std = out[..., : cfg.action_dim], out[..., cfg.action_dim:]
     log_std = torch.clamp(log_std, cfg.log_std_min, cfg.log_std_max)
     std = torch.exp(log_std)

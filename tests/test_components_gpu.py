@@ -55,7 +55,8 @@ def test_adam_polyak_step_matches_optax_restatement(cuda, with_target, clip):
     out = adam_polyak_step(dp, dg, dm, dv, step, max_grad_norm=clip, target=dt if with_target else None)
     assert int(step) == 7
     assert SU.rel(dp, ref_p) < 1e-6 and SU.rel(dm, ref_opt["m"]) < 1e-6 and SU.rel(dv, ref_opt["v"]) < 1e-6
-    assert SU.rel(dp - p.cuda(), ref_p - p.double()) < 1e-4          # the step itself
+    # the step itself: |p| ~ 1 stored in fp32 carries 6e-8 absolute, i.e. ~2e-4 of a 3e-4 step
+    assert SU.rel(dp - p.cuda(), ref_p - p.double()) < 2e-3
     assert abs(float(out["grad_norm"]) - float(gr.double().norm())) < 1e-6 * float(gr.double().norm())
     assert abs(float(out["params_norm"]) - float(ref_p.norm())) < 1e-6 * float(ref_p.norm())
     if with_target:
