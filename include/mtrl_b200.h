@@ -167,11 +167,16 @@ typedef struct mtrl_sac_config {
                            is a plain MLP, mtrl/nn/base.py:11-63, its last Dense is the one "head"), alpha updated first,
                            critic loss 0.5 * sum_e mean_b, parameter-norm logs of the pre-update parameters        */
   int precision;        /* MTRL_PRECISION_*                                                                        */
+  int use_layer_norm;        /* MTRL_VARIANT_SAC only: VanillaNetworkConfig.use_layer_norm (mtrl/config/nn.py:33-39): a
+                                flax LayerNorm (eps 1e-6, scale + bias) before every Dense of the MLP except the first
+                                (mtrl/nn/base.py:35-37, 52-53)                                                        */
+  int use_skip_connections;  /* MTRL_VARIANT_SAC only: VanillaNetworkConfig.use_skip_connections: hidden layers whose
+                                input has the hidden width add it to their activation (mtrl/nn/base.py:46-49)         */
 } mtrl_sac_config_t;
 
 /* Flat fp32 layout of one network (all ensemble members).  [member trunks | 32 reduction slots |
  * member heads]; the trunk prefix (plus the slots) is what ranks all-reduce.  Flax names:
- * layer_i/kernel (in, W) at trunk(e) + kernel_off[i], layer_i/bias (W) at trunk(e) + bias_off[i],
+ * layer_i/kernel (in, W) at trunk(e) + kernel_off[i], layer_i/bias (W) at trunk(e) + bias_off[i], (LayerNorm_i below,)
  * VmapDense_0/kernel (T_local, W, head) at heads(e) + head_kernel_off, bias (T_local, head). */
 typedef struct mtrl_net_layout {
   long long total;
@@ -185,6 +190,12 @@ typedef struct mtrl_net_layout {
   long long head_kernel_off;
   long long head_bias_off;
   int in_dim, head_dim, members, num_local_tasks, width, depth;
+  /* MLP with use_layer_norm: LayerNorm_k/scale (W) and /bias (W), k = 0 .. depth-1, inside the member's trunk at
+   * trunk(e) + ln_scale_off[k] / ln_bias_off[k]; LayerNorm_k normalises the input of layer_{k+1} (the output Dense for
+   * k = depth-1).  use_layer_norm = 0: the arrays are unused. */
+  long long ln_scale_off[MTRL_MAX_DEPTH];
+  long long ln_bias_off[MTRL_MAX_DEPTH];
+  int use_layer_norm, reserved;
 } mtrl_net_layout_t;
 
 typedef struct mtrl_sac_layout {

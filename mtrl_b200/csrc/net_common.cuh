@@ -15,7 +15,8 @@ using namespace sac;
 inline long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
 
 
-inline void fill_net_layout(mtrl_net_layout_t* L, int in_dim, int head_dim, int members, int t_local, int width, int depth) {
+inline void fill_net_layout(mtrl_net_layout_t* L, int in_dim, int head_dim, int members, int t_local, int width, int depth,
+                            bool use_layer_norm = false) {
   memset(L, 0, sizeof(*L));
   L->in_dim = in_dim;
   L->head_dim = head_dim;
@@ -30,8 +31,15 @@ inline void fill_net_layout(mtrl_net_layout_t* L, int in_dim, int head_dim, int 
     off = round_up(off + static_cast<long long>(d) * width, 32);
     L->bias_off[i] = off;
     off = round_up(off + width, 32);
+    if (use_layer_norm) {
+      L->ln_scale_off[i] = off;
+      off = round_up(off + width, 32);
+      L->ln_bias_off[i] = off;
+      off = round_up(off + width, 32);
+    }
     d = width;
   }
+  L->use_layer_norm = use_layer_norm ? 1 : 0;
   L->member_trunk_stride = off;
   L->trunk_total = off * members;
   L->slots_off = L->trunk_total;
@@ -55,6 +63,8 @@ inline int block_n_for(int n) {
 
 inline float* tk(float* base, const mtrl_net_layout_t& L, int e, int l) { return base + e * L.member_trunk_stride + L.kernel_off[l]; }
 inline float* tb(float* base, const mtrl_net_layout_t& L, int e, int l) { return base + e * L.member_trunk_stride + L.bias_off[l]; }
+inline float* lns(float* base, const mtrl_net_layout_t& L, int e, int k) { return base + e * L.member_trunk_stride + L.ln_scale_off[k]; }
+inline float* lnb(float* base, const mtrl_net_layout_t& L, int e, int k) { return base + e * L.member_trunk_stride + L.ln_bias_off[k]; }
 inline float* hk(float* base, const mtrl_net_layout_t& L, int e) { return base + L.heads_base + e * L.member_head_stride + L.head_kernel_off; }
 inline float* hb(float* base, const mtrl_net_layout_t& L, int e) { return base + L.heads_base + e * L.member_head_stride + L.head_bias_off; }
 

@@ -12,6 +12,7 @@
 
 #include "comm.cuh"
 #include "common.cuh"
+#include "ln_kernels.cuh"
 #include "mtrl_b200.h"
 #include "net_common.cuh"
 #include "sac_kernels.cuh"
@@ -37,6 +38,13 @@ struct Workspace {
   // parameter operand copies (shadows) follow.
   long long lo_delta;
   float *ash_lo, *csh_lo, *tsh_lo;
+  // MLP with LayerNorm / skip connections (ln_kernels.cuh): n_j = the input of Dense_j, j = 1 .. depth, stored at index
+  // j - 1 (index depth - 1 = the head's input), per chain like the activations above, and the rows' (mean, rstd);
+  // backward: GN = gradient of n_j (dX GEMM / head VJP output, fp32), GS = g(x_j) travelling through a skip connection
+  // (ping-pong), rowc = per-row coefficients, part_dg / part_dbeta = column partials of the LayerNorm gradients.
+  float *An_n[MTRL_MAX_DEPTH], *Ao_n[MTRL_MAX_DEPTH], *C_n[kMaxE][MTRL_MAX_DEPTH], *Tg_n[kMaxE][MTRL_MAX_DEPTH];
+  float *An_st[MTRL_MAX_DEPTH], *Ao_st[MTRL_MAX_DEPTH], *C_st[kMaxE][MTRL_MAX_DEPTH], *Tg_st[kMaxE][MTRL_MAX_DEPTH];
+  float *GN[kMaxE], *GS[kMaxE][2], *rowc[kMaxE], *part_dg[kMaxE], *part_dbeta[kMaxE];
 };
 
 // Bump allocation; with base == nullptr only the size is computed.
@@ -68,7 +76,36 @@ long long carve(const mtrl_sac_config_t& c, int Ka, int Kc, long long actor_tota
     w.G[e][0] = f(M * W);
     w.G[e][1] = f(M * W);
   }
+  const bool ln_mode = c.use_layer_norm || c.use_skip_connections;
+  if (ln_mode) {
+    for (int l = 0; l < c.depth; ++l) {
+      w.An_n[l] = f(M * W);
+      w.Ao_n[l] = f(M * W);
+      for (int e = 0; e < E; ++e) {
+        w.C_n[e][l] = f(M * W);
+        w.Tg_n[e][l] = f(M * W);
+      }
+    }
+  }
   const long long mirror_bytes = off;   // everything above is a GEMM operand
+  if (ln_mode) {
+    for (int l = 0; l < c.depth; ++l) {
+      w.An_st[l] = f(M * 2);
+      w.Ao_st[l] = f(M * 2);
+      for (int e = 0; e < E; ++e) {
+        w.C_st[e][l] = f(M * 2);
+        w.Tg_st[e][l] = f(M * 2);
+      }
+    }
+    for (int e = 0; e < E; ++e) {
+      w.GN[e] = f(M * W);
+      w.GS[e][0] = f(M * W);
+      w.GS[e][1] = f(M * W);
+      w.rowc[e] = f(M * 2);
+      w.part_dg[e] = f((M / kTileRows) * W);
+      w.part_dbeta[e] = f((M / kTileRows) * W);
+    }
+  }
   w.dXin = f(E * M * 16);
   w.rew = f(M);
   w.done = f(M);
@@ -129,6 +166,10 @@ int validate(const mtrl_sac_config_t& c) {
                "sac config: use_task_weights needs all tasks on one handle (softmax over every log_alpha)");
   MTRL_REQUIRE(c.precision == MTRL_PRECISION_TF32 || c.precision == MTRL_PRECISION_FP32X3, "sac config: unknown precision %d",
                c.precision);
+  MTRL_REQUIRE(!(c.use_layer_norm || c.use_skip_connections) || c.variant == MTRL_VARIANT_SAC,
+               "sac config: LayerNorm / skip connections belong to the MLP of the single-task variant (MultiHeadNetwork has neither)");
+  MTRL_REQUIRE(!c.use_skip_connections || (c.obs_dim != c.width && c.obs_dim + c.action_dim != c.width),
+               "sac config: skip connections with an input as wide as the hidden layers are not supported");
   return MTRL_OK;
 }
 
@@ -181,6 +222,7 @@ struct mtrl_sac {
   //                 (mtsac.py:515-523, 995-1003), while the target critics still see next_observations;
   //   split_actor:  the vmapped actor loss runs with `_explore` at its default True (mtsac.py:631-637, 676-682).
   bool split_critic = false, split_actor = false;
+  bool ln_mode = false;   // MLP with LayerNorm and / or skip connections: junction kernels between the Dense GEMMs
   comm::Segment *d_segs_critic = nullptr, *d_segs_actor = nullptr;   // ownership tables (device)
   int nsegs_critic = 0, nsegs_actor = 0;
 };
@@ -196,6 +238,24 @@ template <typename Ptr>
 Ptr lo(const mtrl_sac* h, Ptr p) { return h->ws.lo_delta ? p + h->ws.lo_delta : nullptr; }
 // ... and of a trunk kernel inside one of the three parameter operand copies
 float* tk_lo(float* base_lo, const mtrl_net_layout_t& L, int e, int l) { return base_lo ? tk(base_lo, L, e, l) : nullptr; }
+
+// The four activation chains of an update: actor on next_obs / obs, critic members (online params) and target members.
+enum Chain { CH_AN = 0, CH_AO = 1, CH_C = 2, CH_TG = 3 };
+float* chain_d(const mtrl_sac* h, int ch, int e, int l) {   // relu output of Dense_l
+  const Workspace& w = h->ws;
+  return ch == CH_AN ? w.An[l] : (ch == CH_AO ? w.Ao[l] : (ch == CH_C ? w.C[e][l] : w.Tg[e][l]));
+}
+float* chain_n(const mtrl_sac* h, int ch, int e, int l) {   // n_{l+1} = LN_l(x_{l+1}): the input of Dense_{l+1} / of the head
+  const Workspace& w = h->ws;
+  return ch == CH_AN ? w.An_n[l] : (ch == CH_AO ? w.Ao_n[l] : (ch == CH_C ? w.C_n[e][l] : w.Tg_n[e][l]));
+}
+float* chain_st(const mtrl_sac* h, int ch, int e, int l) {
+  const Workspace& w = h->ws;
+  return ch == CH_AN ? w.An_st[l] : (ch == CH_AO ? w.Ao_st[l] : (ch == CH_C ? w.C_st[e][l] : w.Tg_st[e][l]));
+}
+// input of Dense_l for l >= 1, and of the head
+float* dense_in(const mtrl_sac* h, int ch, int e, int l) { return h->ln_mode ? chain_n(h, ch, e, l - 1) : chain_d(h, ch, e, l - 1); }
+float* head_in(const mtrl_sac* h, int ch, int e) { return dense_in(h, ch, e, h->cfg.depth); }
 
 // Rows [r0, r1) of a hidden-layer kernel (in = W rows) that rank r owns when the trunk is sharded over G ranks.
 void row_block(int W, int G, int r, int* r0, int* r1) {
@@ -274,19 +334,29 @@ int build_backward_plans(mtrl_sac* h) {
     v->clear();
   }
   // Backward: dZ_{D-1} (masked head VJP) sits in G[e][0]; layer l reads G[e][(D-1-l)&1], writes G[e][(D-l)&1].
+  // MLP with LayerNorm / skip (ln_mode): the junction kernels produce dZ_l in G[e][0] for every layer; the dX problem
+  // stores the plain gradient of the layer's input n_l in GN[e] (fp32, no ReLU gate: the junction below applies it).
+  const bool ln = h->ln_mode;
+  auto dx_any = [&](int e, int src, int dst, float* sh, float* sh_lo, const mtrl_net_layout_t& L, int l, unsigned* bits, float* csum) {
+    if (!ln)
+      return dx_problem(w.G[e][src], tk(sh, L, e, l), W, bits, w.G[e][dst], M, W, csum, lo(h, w.G[e][src]), tk_lo(sh_lo, L, e, l),
+                        lo(h, w.G[e][dst]));
+    mtrl_gemm_problem_t p = dx_problem(w.G[e][0], tk(sh, L, e, l), W, nullptr, w.GN[e], M, W, nullptr, lo(h, w.G[e][0]),
+                                       tk_lo(sh_lo, L, e, l), nullptr);
+    p.epilogue = MTRL_EPI_STORE;
+    return p;
+  };
   for (int l = D - 1; l >= 0; --l) {
-    const int src = (D - 1 - l) & 1, dst = src ^ 1;
+    const int src = ln ? 0 : (D - 1 - l) & 1, dst = src ^ 1;
     std::vector<mtrl_gemm_problem_t> pc, ppi, pa;
     for (int e = 0; e < E; ++e) {
-      const float* X = l == 0 ? w.Xc : w.C[e][l - 1];
+      const float* X = l == 0 ? w.Xc : dense_in(h, CH_C, e, l);
       push_dw(h, pc, X, l == 0 ? Kc : W, l == 0 ? LC.in_dim : W, w.G[e][src], h->buf.critic_grads, h->off_critic_grads, LC, e, l);
     }
     for (int e = 0; e < E; ++e) {
       if (l > 0) {
-        pc.push_back(dx_problem(w.G[e][src], tk(csh, LC, e, l), W, w.bits_C[e][l - 1], w.G[e][dst], M, W, colsum_part(h, e),
-                                lo(h, w.G[e][src]), tk_lo(csh_lo, LC, e, l), lo(h, w.G[e][dst])));
-        ppi.push_back(dx_problem(w.G[e][src], tk(csh, LC, e, l), W, w.bits_C[e][l - 1], w.G[e][dst], M, W, nullptr,
-                                 lo(h, w.G[e][src]), tk_lo(csh_lo, LC, e, l), lo(h, w.G[e][dst])));
+        pc.push_back(dx_any(e, src, dst, csh, csh_lo, LC, l, ln ? nullptr : w.bits_C[e][l - 1], colsum_part(h, e)));
+        ppi.push_back(dx_any(e, src, dst, csh, csh_lo, LC, l, ln ? nullptr : w.bits_C[e][l - 1], nullptr));
       } else {
         // actor step: only dL/da = first action_dim input columns of dZ_0 W_0^T (N = 16 rows of W_0)
         mtrl_gemm_problem_t p;
@@ -303,11 +373,9 @@ int build_backward_plans(mtrl_sac* h) {
         ppi.push_back(p);
       }
     }
-    push_dw(h, pa, l == 0 ? w.Xa : w.Ao[l - 1], l == 0 ? Ka : W, l == 0 ? LA.in_dim : W, w.G[0][src], h->buf.actor_grads,
+    push_dw(h, pa, l == 0 ? w.Xa : dense_in(h, CH_AO, 0, l), l == 0 ? Ka : W, l == 0 ? LA.in_dim : W, w.G[0][src], h->buf.actor_grads,
             h->off_actor_grads, LA, 0, l);
-    if (l > 0)
-      pa.push_back(dx_problem(w.G[0][src], tk(ash, LA, 0, l), W, w.bits_Ao[l - 1], w.G[0][dst], M, W, colsum_part(h, 0),
-                              lo(h, w.G[0][src]), tk_lo(ash_lo, LA, 0, l), lo(h, w.G[0][dst])));
+    if (l > 0) pa.push_back(dx_any(0, src, dst, ash, ash_lo, LA, l, ln ? nullptr : w.bits_Ao[l - 1], colsum_part(h, 0)));
     MTRL_PROPAGATE(make_plan(h->bwd_critic, pc));
     MTRL_PROPAGATE(make_plan(h->bwd_pi, ppi));
     MTRL_PROPAGATE(make_plan(h->bwd_actor, pa));
@@ -325,30 +393,29 @@ int build_plans(mtrl_sac* h) {
   float* ash = h->buf.actor_shadow;
   float* csh = h->buf.critic_shadow;
   float* tsh = h->buf.critic_target_shadow;
-  // forward problem of one trunk layer: input / kernel / output with their fp32x3 remainders (null in tf32 mode)
-  auto fwd = [&](float* X0, float* Hprev, int K0, int in_dim, float* sh, float* sh_lo, float* params, const mtrl_net_layout_t& L,
-                 int e, int l, float* out, unsigned* bits) {
-    float* X = l == 0 ? X0 : Hprev;
-    return fwd_problem(X, l == 0 ? K0 : W, l == 0 ? in_dim : W, tk(sh, L, e, l), tb(params, L, e, l), out, M, W, bits, lo(h, X),
-                       tk_lo(sh_lo, L, e, l), lo(h, out));
+  // forward problem of one trunk layer of one chain: input / kernel / output with their fp32x3 remainders (null in tf32
+  // mode).  With LayerNorm / skip the layer's input is the junction's output n_l and the ReLU gate bits are not needed
+  // (the junction reads the activation itself).
+  auto fwd = [&](int ch, float* X0, int K0, int in_dim, float* sh, float* sh_lo, float* params, const mtrl_net_layout_t& L, int e, int l,
+                 unsigned* bits) {
+    float* X = l == 0 ? X0 : dense_in(h, ch, e, l);
+    float* out = chain_d(h, ch, e, l);
+    return fwd_problem(X, l == 0 ? K0 : W, l == 0 ? in_dim : W, tk(sh, L, e, l), tb(params, L, e, l), out, M, W, h->ln_mode ? nullptr : bits,
+                       lo(h, X), tk_lo(sh_lo, L, e, l), lo(h, out));
   };
   for (int l = 0; l < D; ++l) {
     std::vector<mtrl_gemm_problem_t> p;
-    p.push_back(fwd(w.Xa_next, l ? w.An[l - 1] : nullptr, Ka, LA.in_dim, ash, w.ash_lo, h->buf.actor_params, LA, 0, l, w.An[l], nullptr));
-    p.push_back(fwd(w.Xa, l ? w.Ao[l - 1] : nullptr, Ka, LA.in_dim, ash, w.ash_lo, h->buf.actor_params, LA, 0, l, w.Ao[l],
-                    l + 1 < D ? w.bits_Ao[l] : nullptr));
+    p.push_back(fwd(CH_AN, w.Xa_next, Ka, LA.in_dim, ash, w.ash_lo, h->buf.actor_params, LA, 0, l, nullptr));
+    p.push_back(fwd(CH_AO, w.Xa, Ka, LA.in_dim, ash, w.ash_lo, h->buf.actor_params, LA, 0, l, l + 1 < D ? w.bits_Ao[l] : nullptr));
     for (int e = 0; e < E; ++e)
-      p.push_back(fwd(w.Xc, l ? w.C[e][l - 1] : nullptr, Kc, LC.in_dim, csh, w.csh_lo, h->buf.critic_params, LC, e, l, w.C[e][l],
-                      l + 1 < D ? w.bits_C[e][l] : nullptr));
+      p.push_back(fwd(CH_C, w.Xc, Kc, LC.in_dim, csh, w.csh_lo, h->buf.critic_params, LC, e, l, l + 1 < D ? w.bits_C[e][l] : nullptr));
     MTRL_PROPAGATE(make_plan(h->fwd, p));
   }
   for (int l = 0; l < D; ++l) {
     std::vector<mtrl_gemm_problem_t> p, q;
     for (int e = 0; e < E; ++e) {
-      p.push_back(fwd(w.Xc_next, l ? w.Tg[e][l - 1] : nullptr, Kc, LC.in_dim, tsh, w.tsh_lo, h->buf.critic_target, LC, e, l, w.Tg[e][l],
-                      nullptr));
-      q.push_back(fwd(w.Xc, l ? w.C[e][l - 1] : nullptr, Kc, LC.in_dim, csh, w.csh_lo, h->buf.critic_params, LC, e, l, w.C[e][l],
-                      l + 1 < D ? w.bits_C[e][l] : nullptr));
+      p.push_back(fwd(CH_TG, w.Xc_next, Kc, LC.in_dim, tsh, w.tsh_lo, h->buf.critic_target, LC, e, l, nullptr));
+      q.push_back(fwd(CH_C, w.Xc, Kc, LC.in_dim, csh, w.csh_lo, h->buf.critic_params, LC, e, l, l + 1 < D ? w.bits_C[e][l] : nullptr));
     }
     MTRL_PROPAGATE(make_plan(h->fwd_target, p));
     MTRL_PROPAGATE(make_plan(h->fwd_pi, q));
@@ -465,11 +532,105 @@ int launch_colsum(mtrl_sac* h, const ColsumJobs& jobs, int groups, cudaStream_t 
   return MTRL_OK;
 }
 
+// One chain of an MLP pass through a junction: which activation buffers, and which parameter buffer holds its LayerNorms.
+struct ChainRef {
+  int ch, e;
+  float* params;
+  const mtrl_net_layout_t* L;
+};
+
+// Junction l + 1 of the given chains, right after their Dense_l: n_{l+1} = LayerNorm_l(d_l [+ n_l]) (ln_kernels.cuh).
+int run_junctions_fwd(mtrl_sac* h, const ChainRef* chains, int n, int l, int rows, cudaStream_t st) {
+  const mtrl_sac_config_t& c = h->cfg;
+  LnFwdArgs a;
+  memset(&a, 0, sizeof(a));
+  MTRL_REQUIRE(n <= kMaxLnPasses, "run_junctions_fwd: %d chains in one launch", n);
+  for (int i = 0; i < n; ++i) {
+    const ChainRef& r = chains[i];
+    LnFwdPass& p = a.p[i];
+    p.D = chain_d(h, r.ch, r.e, l);
+    p.Nprev = (c.use_skip_connections && l >= 1) ? chain_n(h, r.ch, r.e, l - 1) : nullptr;
+    p.scale = c.use_layer_norm ? lns(r.params, *r.L, r.e, l) : nullptr;
+    p.bias = c.use_layer_norm ? lnb(r.params, *r.L, r.e, l) : nullptr;
+    p.N = chain_n(h, r.ch, r.e, l);
+    p.stats = chain_st(h, r.ch, r.e, l);
+  }
+  a.npass = n; a.M = rows; a.W = c.width; a.lo_delta = h->ws.lo_delta; a.eps = 1e-6f;
+  mtrl_launch(ln_fwd_kernel, dim3((rows + 7) / 8, n), dim3(256), 0, st, a);
+  MTRL_CUDA_CHECK(cudaGetLastError());
+  LAUNCHED(h);
+  return MTRL_OK;
+}
+
+int launch_colsum(mtrl_sac* h, const ColsumJobs& jobs, int groups, cudaStream_t st);
+
+// Trunk backward of an MLP with LayerNorm / skip connections: per layer l (from the top), junction l + 1 turns the
+// gradient of n_{l+1} (GN: head VJP for l = depth - 1, the dX GEMM of layer l + 1 below that, plus what arrives through
+// the skip connection) into dZ_l, the bias / LayerNorm gradient partials and the gradient that skips on; then the
+// layer's dW / dX plan.
+int run_trunk_backward_ln(mtrl_sac* h, std::vector<mtrl_gemm_plan_t*>& plans, float* grads, float* params, const mtrl_net_layout_t& L,
+                          int ch, int E, bool want_wgrad, cudaStream_t st) {
+  const mtrl_sac_config_t& c = h->cfg;
+  Workspace& w = h->ws;
+  const int D = c.depth, M = c.max_rows, W = c.width;
+  const bool ln = c.use_layer_norm != 0, skip = c.use_skip_connections != 0;
+  for (int l = D - 1, i = 0; l >= 0; --l, ++i) {
+    const int j = l + 1;
+    LnBwdArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int e = 0; e < E; ++e) {
+      LnBwdPass& p = a.p[e];
+      p.dN = w.GN[e];
+      p.dSkip = (skip && j >= 1 && j <= D - 1) ? w.GS[e][(j + 1) & 1] : nullptr;
+      p.D = chain_d(h, ch, e, l);
+      p.Nprev = (skip && l >= 1) ? chain_n(h, ch, e, l - 1) : nullptr;
+      p.scale = ln ? lns(params, L, e, l) : nullptr;
+      p.stats = chain_st(h, ch, e, l);
+      p.rowc = w.rowc[e];
+      p.dZ = w.G[e][0];
+      p.dX = (skip && l >= 1) ? w.GS[e][j & 1] : nullptr;
+      p.part_db = want_wgrad ? colsum_part(h, e) : nullptr;
+      p.part_dg = (want_wgrad && ln) ? w.part_dg[e] : nullptr;
+      p.part_dbeta = (want_wgrad && ln) ? w.part_dbeta[e] : nullptr;
+    }
+    a.npass = E; a.M = M; a.W = W; a.lo_delta = w.lo_delta;
+    if (ln) {
+      mtrl_launch(ln_bwd_rows_kernel, dim3((M + 7) / 8, E), dim3(256), 0, st, a);
+      LAUNCHED(h);
+    }
+    mtrl_launch(ln_bwd_tile_kernel, dim3((W + 127) / 128, M / kTileRows, E), dim3(256), 0, st, a);
+    MTRL_CUDA_CHECK(cudaGetLastError());
+    LAUNCHED(h);
+    if (want_wgrad) {
+      ColsumJobs jobs;
+      jobs.njobs = 0;
+      for (int e = 0; e < E; ++e) {
+        jobs.part[jobs.njobs] = colsum_part(h, e);
+        jobs.dst[jobs.njobs++] = tb(grads, L, e, l);
+        if (ln) {
+          jobs.part[jobs.njobs] = w.part_dg[e];
+          jobs.dst[jobs.njobs++] = lns(grads, L, e, l);
+          jobs.part[jobs.njobs] = w.part_dbeta[e];
+          jobs.dst[jobs.njobs++] = lnb(grads, L, e, l);
+        }
+      }
+      MTRL_PROPAGATE(launch_colsum(h, jobs, M / kTileRows, st));
+    }
+    MTRL_PROPAGATE(run_plan(h, plans[i], st));
+  }
+  return MTRL_OK;
+}
+
 // Trunk backward of one network: per layer, finish the bias gradient from the partial column sums its dZ producer
 // left behind (head VJP: per 128-row tile; previous layer's dX GEMM epilogue: per 32 rows), then the dW / dX plan.
 int run_trunk_backward(mtrl_sac* h, std::vector<mtrl_gemm_plan_t*>& plans, float* grads, const mtrl_net_layout_t& L, int E,
                        bool want_wgrad, cudaStream_t st) {
   const int D = h->cfg.depth;
+  if (h->ln_mode) {
+    const bool actor = grads == h->buf.actor_grads;
+    return run_trunk_backward_ln(h, plans, grads, actor ? h->buf.actor_params : h->buf.critic_params, L, actor ? CH_AO : CH_C, E,
+                                 want_wgrad, st);
+  }
   for (int l = D - 1, i = 0; l >= 0; --l, ++i) {
     const int src = (D - 1 - l) & 1;
     (void)src;
@@ -545,9 +706,10 @@ extern "C" int mtrl_sac_query_layout(const mtrl_sac_config_t* cfg, mtrl_sac_layo
   MTRL_REQUIRE(cfg && out, "mtrl_sac_query_layout: null argument");
   MTRL_PROPAGATE(validate(*cfg));
   memset(out, 0, sizeof(*out));
-  fill_net_layout(&out->actor, cfg->obs_dim, 2 * cfg->action_dim, 1, cfg->num_local_tasks, cfg->width, cfg->depth);
+  fill_net_layout(&out->actor, cfg->obs_dim, 2 * cfg->action_dim, 1, cfg->num_local_tasks, cfg->width, cfg->depth,
+                  cfg->use_layer_norm != 0);
   fill_net_layout(&out->critic, cfg->action_dim + cfg->obs_dim, 1, cfg->num_critics, cfg->num_local_tasks, cfg->width,
-                  cfg->depth);
+                  cfg->depth, cfg->use_layer_norm != 0);
   out->k_actor = static_cast<int>(round_up(cfg->obs_dim, 32));
   out->k_critic = static_cast<int>(round_up(cfg->action_dim + cfg->obs_dim, 32));
   out->workspace_bytes = carve(*cfg, out->k_actor, out->k_critic, out->actor.total, out->critic.total, nullptr, nullptr);
@@ -559,6 +721,7 @@ extern "C" int mtrl_sac_create(mtrl_sac_t** out, const mtrl_sac_config_t* cfg, c
   mtrl_sac* h = new mtrl_sac();
   h->cfg = *cfg;
   h->buf = *b;
+  h->ln_mode = cfg->use_layer_norm || cfg->use_skip_connections;
   int rc = mtrl_sac_query_layout(cfg, &h->lay);
   if (rc != MTRL_OK) { delete h; return rc; }
   const void* need[] = {b->actor_params, b->actor_grads, b->actor_m, b->actor_v, b->actor_shadow, b->critic_params,
@@ -678,7 +841,14 @@ int step_begin(mtrl_sac* h, const float* obs, const float* actions, const float*
   mtrl_launch(pack_rows_kernel, M, dim3(128), 0, st, a);
   LAUNCHED(h);
   MTRL_CUDA_CHECK(cudaGetLastError());
-  for (int l = 0; l < D; ++l) MTRL_PROPAGATE(run_plan(h, h->fwd[l], st));
+  for (int l = 0; l < D; ++l) {
+    MTRL_PROPAGATE(run_plan(h, h->fwd[l], st));
+    if (h->ln_mode) {
+      ChainRef ch[2 + kMaxE] = {{CH_AN, 0, h->buf.actor_params, &h->lay.actor}, {CH_AO, 0, h->buf.actor_params, &h->lay.actor}};
+      for (int e = 0; e < c.num_critics; ++e) ch[2 + e] = {CH_C, e, h->buf.critic_params, &h->lay.critic};
+      MTRL_PROPAGATE(run_junctions_fwd(h, ch, 2 + c.num_critics, l, M, st));
+    }
+  }
   return MTRL_OK;
 }
 
@@ -689,16 +859,23 @@ int step_critic_grads(mtrl_sac* h, cudaStream_t st) {
   Workspace& w = h->ws;
   const mtrl_net_layout_t& LC = h->lay.critic;
   const int M = c.max_rows, W = c.width, D = c.depth, E = c.num_critics;
-  MTRL_PROPAGATE(launch_actor_head(h, h->split_critic ? w.Ao[D - 1] : w.An[D - 1], w.eps_c, w.Xc_next, w.logp_next, false, st));
-  for (int l = 0; l < D; ++l) MTRL_PROPAGATE(run_plan(h, h->fwd_target[l], st));
+  MTRL_PROPAGATE(launch_actor_head(h, head_in(h, h->split_critic ? CH_AO : CH_AN, 0), w.eps_c, w.Xc_next, w.logp_next, false, st));
+  for (int l = 0; l < D; ++l) {
+    MTRL_PROPAGATE(run_plan(h, h->fwd_target[l], st));
+    if (h->ln_mode) {
+      ChainRef ch[kMaxE];
+      for (int e = 0; e < E; ++e) ch[e] = {CH_TG, e, h->buf.critic_target, &h->lay.critic};
+      MTRL_PROPAGATE(run_junctions_fwd(h, ch, E, l, M, st));
+    }
+  }
   {
     CriticLossArgs a;
     memset(&a, 0, sizeof(a));
     for (int e = 0; e < E; ++e) {
-      a.target.H[e] = w.Tg[e][D - 1];
+      a.target.H[e] = head_in(h, CH_TG, e);
       a.target.w[e] = hk(h->buf.critic_target, LC, e);
       a.target.b[e] = hb(h->buf.critic_target, LC, e);
-      a.online.H[e] = w.C[e][D - 1];
+      a.online.H[e] = head_in(h, CH_C, e);
       a.online.w[e] = hk(h->buf.critic_params, LC, e);
       a.online.b[e] = hb(h->buf.critic_params, LC, e);
     }
@@ -720,15 +897,15 @@ int step_critic_grads(mtrl_sac* h, cudaStream_t st) {
     HeadBwdArgs a;
     memset(&a, 0, sizeof(a));
     for (int e = 0; e < E; ++e) {
-      a.H[e] = w.C[e][D - 1];
+      a.H[e] = head_in(h, CH_C, e);
       a.dout[e] = w.dq + static_cast<long long>(e) * M;
       a.Wh[e] = hk(h->buf.critic_params, LC, e);
-      a.dZ[e] = w.G[e][0];
+      a.dZ[e] = h->ln_mode ? w.GN[e] : w.G[e][0];
       a.dWh[e] = hk(h->buf.critic_grads, LC, e);
       a.dbh[e] = hb(h->buf.critic_grads, LC, e);
-      a.colsum[e] = colsum_part(h, e);
+      a.colsum[e] = h->ln_mode ? nullptr : colsum_part(h, e);
     }
-    a.seg_start = w.seg_start; a.M = M; a.W = W; a.dz_lo_delta = w.lo_delta;
+    a.seg_start = w.seg_start; a.M = M; a.W = W; a.dz_lo_delta = w.lo_delta; a.no_mask = h->ln_mode;
     MTRL_PROPAGATE(launch_head_bwd(h, a, 1, E, st));
   }
   if (h->comm) {
@@ -796,7 +973,7 @@ int step_critic_apply(mtrl_sac* h, cudaStream_t st) {
 // action also becomes the action columns of the critic input (only valid once the critic backward has consumed them).
 int step_actor_sample(mtrl_sac* h, bool write_x, cudaStream_t st) {
   Workspace& w = h->ws;
-  return launch_actor_head(h, w.Ao[h->cfg.depth - 1], w.eps_a, write_x ? w.Xc : nullptr, w.logp, true, st);
+  return launch_actor_head(h, head_in(h, CH_AO, 0), w.eps_a, write_x ? w.Xc : nullptr, w.logp, true, st);
 }
 
 int step_write_actions(mtrl_sac* h, cudaStream_t st) {
@@ -820,12 +997,19 @@ int step_actor_grads(mtrl_sac* h, cudaStream_t st) {
   // dL/da accumulates over K splits (see build_plans)
   MTRL_CUDA_CHECK(cudaMemsetAsync(w.dXin, 0, static_cast<size_t>(E) * M * 16 * sizeof(float), st));
   h->launches += 1;
-  for (int l = 0; l < D; ++l) MTRL_PROPAGATE(run_plan(h, h->fwd_pi[l], st));
+  for (int l = 0; l < D; ++l) {
+    MTRL_PROPAGATE(run_plan(h, h->fwd_pi[l], st));
+    if (h->ln_mode) {
+      ChainRef ch[kMaxE];
+      for (int e = 0; e < E; ++e) ch[e] = {CH_C, e, h->buf.critic_params, &h->lay.critic};
+      MTRL_PROPAGATE(run_junctions_fwd(h, ch, E, l, M, st));
+    }
+  }
   {
     ActorLossArgs a;
     memset(&a, 0, sizeof(a));
     for (int e = 0; e < E; ++e) {
-      a.online.H[e] = w.C[e][D - 1];
+      a.online.H[e] = head_in(h, CH_C, e);
       a.online.w[e] = hk(h->buf.critic_params, LC, e);
       a.online.b[e] = hb(h->buf.critic_params, LC, e);
     }
@@ -839,12 +1023,12 @@ int step_actor_grads(mtrl_sac* h, cudaStream_t st) {
     HeadBwdArgs a;  // critic heads, input gradients only
     memset(&a, 0, sizeof(a));
     for (int e = 0; e < E; ++e) {
-      a.H[e] = w.C[e][D - 1];
+      a.H[e] = head_in(h, CH_C, e);
       a.dout[e] = w.dq + static_cast<long long>(e) * M;
       a.Wh[e] = hk(h->buf.critic_params, LC, e);
-      a.dZ[e] = w.G[e][0];
+      a.dZ[e] = h->ln_mode ? w.GN[e] : w.G[e][0];
     }
-    a.seg_start = w.seg_start; a.M = M; a.W = W; a.dz_lo_delta = w.lo_delta;
+    a.seg_start = w.seg_start; a.M = M; a.W = W; a.dz_lo_delta = w.lo_delta; a.no_mask = h->ln_mode;
     MTRL_PROPAGATE(launch_head_bwd(h, a, 1, E, st));
   }
   MTRL_PROPAGATE(run_trunk_backward(h, h->bwd_pi, nullptr, LC, E, false, st));
@@ -861,14 +1045,14 @@ int step_actor_grads(mtrl_sac* h, cudaStream_t st) {
   {
     HeadBwdArgs a;
     memset(&a, 0, sizeof(a));
-    a.H[0] = w.Ao[D - 1];
+    a.H[0] = head_in(h, CH_AO, 0);
     a.dout[0] = w.dout;
     a.Wh[0] = hk(h->buf.actor_params, LA, 0);
-    a.dZ[0] = w.G[0][0];
+    a.dZ[0] = h->ln_mode ? w.GN[0] : w.G[0][0];
     a.dWh[0] = hk(h->buf.actor_grads, LA, 0);
     a.dbh[0] = hb(h->buf.actor_grads, LA, 0);
-    a.colsum[0] = colsum_part(h, 0);
-    a.seg_start = w.seg_start; a.M = M; a.W = W; a.dz_lo_delta = w.lo_delta;
+    a.colsum[0] = h->ln_mode ? nullptr : colsum_part(h, 0);
+    a.seg_start = w.seg_start; a.M = M; a.W = W; a.dz_lo_delta = w.lo_delta; a.no_mask = h->ln_mode;
     MTRL_PROPAGATE(launch_head_bwd(h, a, 2 * c.action_dim, 1, st));
   }
   MTRL_PROPAGATE(run_trunk_backward(h, h->bwd_actor, h->buf.actor_grads, LA, 1, true, st));
@@ -1038,7 +1222,7 @@ extern "C" int mtrl_sac_act(mtrl_sac_t* h, const float* obs, int n, const float*
     std::vector<mtrl_gemm_plan_t*> plans;
     for (int l = 0; l < D; ++l) {
       std::vector<mtrl_gemm_problem_t> p;
-      float* X = l == 0 ? w.Xa : w.Ao[l - 1];
+      float* X = l == 0 ? w.Xa : dense_in(h, CH_AO, 0, l);
       p.push_back(fwd_problem(X, l == 0 ? Ka : W, l == 0 ? LA.in_dim : W, tk(h->buf.actor_shadow, LA, 0, l),
                               tb(h->buf.actor_params, LA, 0, l), w.Ao[l], n, W, nullptr, lo(h, X), tk_lo(w.ash_lo, LA, 0, l),
                               lo(h, w.Ao[l])));
@@ -1050,10 +1234,16 @@ extern "C" int mtrl_sac_act(mtrl_sac_t* h, const float* obs, int n, const float*
   act_pack_kernel<<<n, 128, 0, st>>>(obs, n, c.obs_dim, Ka, c.num_tasks, c.task_begin, c.num_local_tasks, eps, deterministic,
                                      c.action_dim, c.noise_seed, h->act_calls++, w.Xa, w.slot_src, w.eps_a, w.status, w.lo_delta);
   MTRL_CUDA_CHECK(cudaGetLastError());
-  for (auto* plan : it->second) MTRL_PROPAGATE(mtrl_gemm_plan_run(plan, st));
+  for (int l = 0; l < D; ++l) {
+    MTRL_PROPAGATE(mtrl_gemm_plan_run(it->second[l], st));
+    if (h->ln_mode) {
+      ChainRef ch = {CH_AO, 0, h->buf.actor_params, &h->lay.actor};
+      MTRL_PROPAGATE(run_junctions_fwd(h, &ch, 1, l, n, st));
+    }
+  }
   ActorHeadArgs a;
   memset(&a, 0, sizeof(a));
-  a.H = w.Ao[D - 1];
+  a.H = head_in(h, CH_AO, 0);
   a.h_lo_delta = w.lo_delta;
   a.Wh = hk(h->buf.actor_params, LA, 0);
   a.bh = hb(h->buf.actor_params, LA, 0);
@@ -1094,7 +1284,8 @@ extern "C" int mtrl_mlp_forward(mtrl_sac_t* h, int net, const float* obs, const 
   float* params = actor ? h->buf.actor_params : (net == 1 ? h->buf.critic_params : h->buf.critic_target);
   float* sh = actor ? h->buf.actor_shadow : (net == 1 ? h->buf.critic_shadow : h->buf.critic_target_shadow);
   float* sh_lo = actor ? w.ash_lo : (net == 1 ? w.csh_lo : w.tsh_lo);
-  auto act_buf = [&](int e, int l) { return actor ? w.Ao[l] : (net == 1 ? w.C[e][l] : w.Tg[e][l]); };
+  const int chn = actor ? CH_AO : (net == 1 ? CH_C : CH_TG);
+  auto act_buf = [&](int e, int l) { return chain_d(h, chn, e, l); };
   auto key = std::make_pair(net, n);
   auto it = h->mlp_plans.find(key);
   if (it == h->mlp_plans.end()) {
@@ -1102,7 +1293,7 @@ extern "C" int mtrl_mlp_forward(mtrl_sac_t* h, int net, const float* obs, const 
     for (int l = 0; l < D; ++l) {
       std::vector<mtrl_gemm_problem_t> p;
       for (int e = 0; e < E; ++e) {
-        float* in = l == 0 ? X : act_buf(e, l - 1);
+        float* in = l == 0 ? X : dense_in(h, chn, e, l);
         p.push_back(fwd_problem(in, l == 0 ? K : W, l == 0 ? L.in_dim : W, tk(sh, L, e, l), tb(params, L, e, l), act_buf(e, l), n, W,
                                 nullptr, lo(h, in), tk_lo(sh_lo, L, e, l), lo(h, act_buf(e, l))));
       }
@@ -1114,11 +1305,18 @@ extern "C" int mtrl_mlp_forward(mtrl_sac_t* h, int net, const float* obs, const 
   mlp_pack_kernel<<<n, 128, 0, st>>>(obs, actor ? nullptr : actions, c.obs_dim, c.action_dim, K, c.num_tasks, c.task_begin,
                                      c.num_local_tasks, X, w.slot_src, w.status, w.lo_delta);
   MTRL_CUDA_CHECK(cudaGetLastError());
-  for (auto* plan : it->second) MTRL_PROPAGATE(mtrl_gemm_plan_run(plan, st));
+  for (int l = 0; l < D; ++l) {
+    MTRL_PROPAGATE(mtrl_gemm_plan_run(it->second[l], st));
+    if (h->ln_mode) {
+      ChainRef ch[kMaxE];
+      for (int e = 0; e < E; ++e) ch[e] = {chn, e, params, &L};
+      MTRL_PROPAGATE(run_junctions_fwd(h, ch, E, l, n, st));
+    }
+  }
   HeadFwdArgs a;
   memset(&a, 0, sizeof(a));
   for (int e = 0; e < E; ++e) {
-    a.H[e] = act_buf(e, D - 1);
+    a.H[e] = head_in(h, chn, e);
     a.Wh[e] = hk(params, L, e);
     a.bh[e] = hb(params, L, e);
   }

@@ -880,6 +880,8 @@ struct HeadBwdArgs {
   float* colsum[kMaxE];       // may be null: [M/128][W] column sums of dZ per 128-row tile (trunk bias gradient partials)
   const int* seg_start;
   long long dz_lo_delta;      // fp32x3: remainder of dZ at dZ[... + dz_lo_delta]; column sums then use the unrounded values
+  int no_mask;                // the head's input is not a ReLU output (MLP with LayerNorm / skip, ln_kernels.cuh): dZ is the plain
+                              // input gradient dout Wh^T in fp32 (no ReLU gate, no rounding, no remainder), consumed by the junction
   int M, W;
 };
 
@@ -940,6 +942,11 @@ static __global__ void __launch_bounds__(RG * 32, ((RG == 8 && HD <= 8) || HD <=
             }
           }
           float dlo[4];
+          float* dzp = dZ + static_cast<long long>(base + rr + r) * p.W + k;
+          if (p.no_mask) {
+            *reinterpret_cast<float4*>(dzp) = make_float4(dz[0], dz[1], dz[2], dz[3]);
+            continue;
+          }
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const float full = hv[c] > 0.f ? dz[c] : 0.f;
@@ -947,7 +954,6 @@ static __global__ void __launch_bounds__(RG * 32, ((RG == 8 && HD <= 8) || HD <=
             dlo[c] = tf32_lo(full, dz[c]);
             csum[c] += p.dz_lo_delta ? full : dz[c];
           }
-          float* dzp = dZ + static_cast<long long>(base + rr + r) * p.W + k;
           *reinterpret_cast<float4*>(dzp) = make_float4(dz[0], dz[1], dz[2], dz[3]);
           if (p.dz_lo_delta) *reinterpret_cast<float4*>(dzp + p.dz_lo_delta) = make_float4(dlo[0], dlo[1], dlo[2], dlo[3]);
         }
@@ -975,7 +981,7 @@ static __global__ void __launch_bounds__(RG * 32, ((RG == 8 && HD <= 8) || HD <=
       for (int r = warp; r < kTileRows; r += RG) {
         float* dzp = dZ + static_cast<long long>(base + r) * p.W + k;
         *reinterpret_cast<float4*>(dzp) = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.dz_lo_delta) *reinterpret_cast<float4*>(dzp + p.dz_lo_delta) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.dz_lo_delta && !p.no_mask) *reinterpret_cast<float4*>(dzp + p.dz_lo_delta) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       if (p.colsum[e] && warp == 0)
         *reinterpret_cast<float4*>(p.colsum[e] + static_cast<long long>(base / kTileRows) * p.W + k) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1004,9 +1010,10 @@ static __global__ void __launch_bounds__(RG * 32, ((RG == 8 && HD <= 8) || HD <=
 // emit (head_bwd_kernel: one row of partials per 128-row tile; the dX GEMM epilogue: one per 32 rows).
 // Fixed summation order, no float atomics.
 // ---------------------------------------------------------------------------------------------
+constexpr int kMaxColsumJobs = 3 * kMaxE;   // bias, LayerNorm scale and LayerNorm bias gradients of every member
 struct ColsumJobs {
-  const float* part[kMaxE];   // [groups][W]
-  float* dst[kMaxE];
+  const float* part[kMaxColsumJobs];   // [groups][W]
+  float* dst[kMaxColsumJobs];
   int njobs;
 };
 

@@ -51,7 +51,7 @@ class SacConfigC(C.Structure):
         ("actor_max_grad_norm", C.c_float), ("critic_max_grad_norm", C.c_float), ("alpha_max_grad_norm", C.c_float),
         ("log_std_min", C.c_float), ("log_std_max", C.c_float), ("target_entropy", C.c_float),
         ("clip_q", C.c_int), ("use_task_weights", C.c_int), ("noise_seed", C.c_ulonglong), ("variant", C.c_int),
-        ("precision", C.c_int),
+        ("precision", C.c_int), ("use_layer_norm", C.c_int), ("use_skip_connections", C.c_int),
     ]
 
 
@@ -76,6 +76,8 @@ class NetLayoutC(C.Structure):
         ("head_kernel_off", C.c_longlong), ("head_bias_off", C.c_longlong),
         ("in_dim", C.c_int), ("head_dim", C.c_int), ("members", C.c_int), ("num_local_tasks", C.c_int),
         ("width", C.c_int), ("depth", C.c_int),
+        ("ln_scale_off", C.c_longlong * MAX_DEPTH), ("ln_bias_off", C.c_longlong * MAX_DEPTH),
+        ("use_layer_norm", C.c_int), ("reserved", C.c_int),
     ]
 
 

@@ -1,6 +1,7 @@
 """Mirror of `mtrl.rl.algorithms.sac.SAC` (/root/reference/mtrl/rl/algorithms/sac.py:96-386): the single-task SAC the
-reference uses as its parameter-matched baseline (experiments/baselines/mt10_sac_v2.py:36-50), on a plain MLP
-(`VanillaNetwork`, mtrl/nn/base.py:11-89, no layer norm / skip connections -- no experiment enables them).
+reference uses as its parameter-matched baseline (experiments/baselines/mt10_sac_v2.py:36-50), on the MLP of
+`VanillaNetwork` (mtrl/nn/base.py:11-89) including its optional pre-layer LayerNorm and skip connections
+(`VanillaNetworkConfig.use_layer_norm / use_skip_connections`; csrc/ln_kernels.cuh).
 
 It runs on the same fused CUDA update as MTSAC with `variant = MTRL_VARIANT_SAC`: one "task", the MLP's last Dense is
 the single head, the temperature is a scalar, alpha is updated first, the critic loss is 0.5 * sum_e mean_b and the
@@ -53,6 +54,11 @@ def _mlp_views(flat: torch.Tensor, lay, in_dim: int, ensemble: bool) -> dict:
     hk = flat.as_strided((E, W, hd), (lay.member_head_stride, hd, 1), o0 + lay.heads_base + lay.head_kernel_off)
     hb = flat.as_strided((E, hd), (lay.member_head_stride, 1), o0 + lay.heads_base + lay.head_bias_off)
     tree[f"layer_{D}"] = {"kernel": hk if ensemble else hk[0], "bias": hb if ensemble else hb[0]}
+    if lay.use_layer_norm:   # nn.LayerNorm() modules in creation order (base.py:35-37, 52-53): LayerNorm_k feeds layer_{k+1}
+        for k in range(D):
+            sc = flat.as_strided((E, W), (lay.member_trunk_stride, 1), o0 + lay.ln_scale_off[k])
+            bi = flat.as_strided((E, W), (lay.member_trunk_stride, 1), o0 + lay.ln_bias_off[k])
+            tree[f"LayerNorm_{k}"] = {"scale": sc if ensemble else sc[0], "bias": bi if ensemble else bi[0]}
     return tree
 
 
@@ -82,12 +88,11 @@ class SAC(MTSAC):
         for nc in (anc, cnc):
             if type(nc) is not VanillaNetworkConfig:
                 raise NotImplementedError(f"{type(nc).__name__}: the accelerated SAC path covers VanillaNetworkConfig")
-            if nc.use_layer_norm or nc.use_skip_connections:
-                raise NotImplementedError("MLP layer norm / skip connections are off in every reference SAC experiment")
             if nc.activation != Activation.ReLU or not nc.use_bias:
                 raise NotImplementedError("the fused path implements Dense(use_bias=True) + ReLU")
-        if (anc.width, anc.depth) != (cnc.width, cnc.depth):
-            raise NotImplementedError("actor and critic must share width and depth")
+        if (anc.width, anc.depth, anc.use_layer_norm, anc.use_skip_connections) != \
+                (cnc.width, cnc.depth, cnc.use_layer_norm, cnc.use_skip_connections):
+            raise NotImplementedError("actor and critic must share width, depth, use_layer_norm and use_skip_connections")
         a_opt, c_opt, t_opt = anc.optimizer.spawn(), cnc.optimizer.spawn(), config.temperature_optimizer_config.spawn()
         self.gamma, self.tau, self.num_critics = config.gamma, config.tau, config.num_critics
         self.target_entropy = -float(act_dim)
@@ -101,7 +106,8 @@ class SAC(MTSAC):
             adam_eps=a_opt.eps, actor_max_grad_norm=nm(a_opt.max_grad_norm), critic_max_grad_norm=nm(c_opt.max_grad_norm),
             alpha_max_grad_norm=nm(t_opt.max_grad_norm), log_std_min=config.actor_config.log_std_min,
             log_std_max=config.actor_config.log_std_max, target_entropy=self.target_entropy, clip_q=0, use_task_weights=0,
-            noise_seed=int(seed) & (2**63 - 1), variant=1, precision=precision_code(precision))
+            noise_seed=int(seed) & (2**63 - 1), variant=1, precision=precision_code(precision),
+            use_layer_norm=int(anc.use_layer_norm), use_skip_connections=int(anc.use_skip_connections))
         self.precision = "fp32x3" if self._cfg.precision else "tf32"
         self._allocate(dev, 1)
         lay = self._lay
@@ -129,6 +135,9 @@ class SAC(MTSAC):
                 d = nc.width
             p[f"layer_{nc.depth}"] = {"kernel": uniform(bound)(gen, lead + (nc.width, head_dim)),
                                       "bias": uniform(bound)(gen, lead + (head_dim,))}
+            if nc.use_layer_norm:   # flax LayerNorm: scale = ones, bias = zeros
+                for k in range(nc.depth):
+                    p[f"LayerNorm_{k}"] = {"scale": torch.ones(lead + (nc.width,)), "bias": torch.zeros(lead + (nc.width,))}
             return p
         _tree_copy_(self.actor.params["params"]["VanillaNetwork_0"]["MLP_0"], init(anc, obs_dim, 2 * act_dim, 1e-3, None))
         _tree_copy_(self.critic.params["params"]["VmapQValueFunction_0"]["VanillaNetwork_0"]["MLP_0"],
@@ -149,6 +158,8 @@ class SAC(MTSAC):
             for _ in range(c.depth):
                 n += d * c.width + c.width
                 d = c.width
+            if c.use_layer_norm:
+                n += c.depth * 2 * c.width
             return n + c.width * head + head
         return {"actor_num_params": count(c.obs_dim, 2 * c.action_dim),
                 "critic_num_params": c.num_critics * count(c.action_dim + c.obs_dim, 1)}

@@ -13,24 +13,25 @@ from oracle import sac_oracle as S
 pytestmark = pytest.mark.gpu
 
 
-def make_sac(cfg, max_batch, seed=1):
+def make_sac(cfg, max_batch, seed=1, **kw):
     from mtrl_b200.config.networks import ContinuousActionPolicyConfig, QValueFunctionConfig
     from mtrl_b200.config.nn import VanillaNetworkConfig
     from mtrl_b200.config.optim import OptimizerConfig
     from mtrl_b200.rl.algorithms import SAC, SACConfig
 
     opt = OptimizerConfig(lr=cfg.lr, max_grad_norm=cfg.max_grad_norm, eps=cfg.adam_eps)
-    net = VanillaNetworkConfig(width=cfg.width, depth=cfg.depth, optimizer=opt)
+    net = VanillaNetworkConfig(width=cfg.width, depth=cfg.depth, optimizer=opt, use_layer_norm=cfg.use_layer_norm,
+                               use_skip_connections=cfg.use_skip_connections)
     sc = SACConfig(num_tasks=10, gamma=cfg.gamma, actor_config=ContinuousActionPolicyConfig(network_config=net),
                    critic_config=QValueFunctionConfig(network_config=net), num_critics=cfg.num_critics, tau=cfg.tau,
                    initial_temperature=cfg.initial_temperature)
-    return SAC.initialize(sc, SU.EnvSpec(cfg.obs_dim, cfg.action_dim), seed=seed, max_batch=max_batch)
+    return SAC.initialize(sc, SU.EnvSpec(cfg.obs_dim, cfg.action_dim), seed=seed, max_batch=max_batch, **kw)
 
 
 def mlp_pairs(otree, atree, ens):
     p = atree["params"]
     p = (p["VmapQValueFunction_0"] if ens else p)["VanillaNetwork_0"]["MLP_0"]
-    return [(f"{k}/{leaf}", otree[k][leaf], p[k][leaf]) for k in otree for leaf in ("kernel", "bias")]
+    return [(f"{k}/{leaf}", otree[k][leaf], p[k][leaf]) for k in otree for leaf in otree[k]]
 
 
 def load(agent, st):
@@ -78,6 +79,70 @@ def test_sac_update_matches_oracle(cuda, width, batch):
         la = agent.alpha.params["params"]["log_alpha"]
         assert SU.rel(la - old.log_alpha.cuda().float(), st64.log_alpha - old.log_alpha) <= 1e-2
     assert agent.get_num_params()["actor_num_params"] == O.num_params(st.actor)
+
+
+@pytest.mark.parametrize("ln,skip", [(True, False), (False, True), (True, True)])
+@pytest.mark.parametrize("width,batch,depth", [(64, 96, 3), (256, 640, 4)])
+def test_sac_update_with_layer_norm_and_skip_connections(cuda, ln, skip, width, batch, depth):
+    """MLP(use_layer_norm, use_skip_connections) (mtrl/nn/base.py:32-63; flax LayerNorm eps 1e-6, scale + bias): the
+    junction kernels (csrc/ln_kernels.cuh) between the Dense GEMMs, in the parity precision: three updates, every leaf --
+    LayerNorm scales and biases included -- and every log scalar to 1e-3 of the fp64 oracle."""
+    cfg = O.OracleConfig(num_tasks=1, obs_dim=49, action_dim=4, width=width, depth=depth, initial_temperature=0.8, use_layer_norm=ln,
+                         use_skip_connections=skip)
+    st = S.init_state(cfg, seed=3)
+    if ln:   # non-trivial scales / biases, different per member
+        g = torch.Generator().manual_seed(5)
+        for net in (st.actor, st.critic):
+            for k in range(depth):
+                net[f"LayerNorm_{k}"]["scale"] = 1.0 + 0.3 * torch.randn(net[f"LayerNorm_{k}"]["scale"].shape, generator=g)
+                net[f"LayerNorm_{k}"]["bias"] = 0.2 * torch.randn(net[f"LayerNorm_{k}"]["bias"].shape, generator=g)
+        st.critic_target = O.tree_map(lambda x: x.clone(), st.critic)
+    agent = make_sac(cfg, batch, seed=3, precision="fp32x3")
+    load(agent, st)
+    assert agent.get_num_params()["actor_num_params"] == O.num_params(st.actor)
+    assert agent.get_num_params()["critic_num_params"] == O.num_params(st.critic)
+    st64 = st.to(torch.float64)
+    for step in range(3):
+        b, ec, ea = S.synthetic_batch(cfg, batch, seed=20 + step)
+        st64, logs64, gr = S.sac_update(st64, tuple(x.double() for x in b), ec.double(), ea.double(), cfg, return_grads=True)
+        _, logs = agent.update(tuple(x.cuda() for x in b), eps_c=ec.cuda(), eps_a=ea.cuda(), check=True)
+        for k in S.SAC_LOG_KEYS:
+            ref, got = float(logs64[k]), float(logs[k])
+            assert abs(got - ref) <= 1e-3 * abs(ref) + 1e-7, f"step {step} {k}: {got} vs {ref}"
+        if step == 0:
+            for name, tree, ens in (("actor", agent.actor.grads, False), ("critic", agent.critic.grads, True)):
+                for leaf, o, a in mlp_pairs(gr[name], tree, ens):
+                    assert SU.rel(a, o) <= 1e-3, f"grad {name}/{leaf}: {SU.rel(a, o)}"
+        for name, new_t, tree, ens in (("actor", st64.actor, agent.actor.params, False), ("critic", st64.critic, agent.critic.params, True),
+                                       ("target", st64.critic_target, agent.critic.target_params, True)):
+            for leaf, o, a in mlp_pairs(new_t, tree, ens):
+                assert SU.rel(a, o) <= 1e-3, f"step {step} param {name}/{leaf}: {SU.rel(a, o)}"
+    # the policy (action sampling) goes through the same junctions
+    obs = S.synthetic_batch(cfg, 8, seed=99)[0][0]
+    got = agent.eval_action(obs.numpy())
+    ref = torch.tanh(S.mlp_forward(st64.actor, obs.double(), depth, "exact", ln, skip)[:, :4])
+    assert SU.rel(torch.from_numpy(got), ref) <= 1e-4
+
+
+def test_sac_layer_norm_tf32_precision(cuda):
+    """The same path with tf32 operands: log scalars to 1e-3, networks to 1e-3 (relative l2)."""
+    cfg = O.OracleConfig(num_tasks=1, obs_dim=49, action_dim=4, width=256, initial_temperature=0.8, use_layer_norm=True,
+                         use_skip_connections=True)
+    st = S.init_state(cfg, seed=4)
+    agent = make_sac(cfg, 640, seed=4)
+    load(agent, st)
+    st64 = st.to(torch.float64)
+    b, ec, ea = S.synthetic_batch(cfg, 640, seed=30)
+    st64, logs64 = S.sac_update(st64, tuple(x.double() for x in b), ec.double(), ea.double(), cfg)
+    _, logs = agent.update(tuple(x.cuda() for x in b), eps_c=ec.cuda(), eps_a=ea.cuda(), check=True)
+    for k in S.SAC_LOG_KEYS:
+        ref, got = float(logs64[k]), float(logs[k])
+        assert abs(got - ref) <= 1e-3 * abs(ref) + 1e-5, f"{k}: {got} vs {ref}"
+    for name, new_t, tree, ens in (("actor", st64.actor, agent.actor.params, False), ("critic", st64.critic, agent.critic.params, True)):
+        pairs = mlp_pairs(new_t, tree, ens)
+        fa = torch.cat([a.detach().double().flatten().cpu() for _, _, a in pairs])
+        fo = torch.cat([o.flatten() for _, o, _ in pairs])
+        assert float((fa - fo).norm() / fo.norm()) <= 1e-3, name
 
 
 def _buffer(capacity):
