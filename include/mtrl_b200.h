@@ -453,6 +453,8 @@ typedef struct mtrl_ppo_config {
   float policy_max_grad_norm, vf_max_grad_norm;   /* <= 0: no clipping                                       */
   float log_std_min, log_std_max;
   unsigned long long noise_seed;
+  int use_layer_norm;        /* num_tasks == 1 (plain MLP) only: VanillaNetworkConfig.use_layer_norm, as in mtrl_sac_config_t */
+  int use_skip_connections;  /* num_tasks == 1 only: VanillaNetworkConfig.use_skip_connections                               */
 } mtrl_ppo_config_t;
 
 typedef struct mtrl_ppo_layout {

@@ -35,6 +35,7 @@ class PpoConfigC(C.Structure):
         ("policy_lr", C.c_float), ("vf_lr", C.c_float), ("adam_b1", C.c_float), ("adam_b2", C.c_float), ("adam_eps", C.c_float),
         ("policy_max_grad_norm", C.c_float), ("vf_max_grad_norm", C.c_float), ("log_std_min", C.c_float),
         ("log_std_max", C.c_float), ("noise_seed", C.c_ulonglong),
+        ("use_layer_norm", C.c_int), ("use_skip_connections", C.c_int),
     ]
 
 
@@ -100,9 +101,11 @@ class MTPPO:
         for nc in (pnc, vnc):
             if nc.activation != Activation.ReLU or not nc.use_bias:
                 raise NotImplementedError("the fused path implements Dense(use_bias=True) + ReLU")
-            if isinstance(nc, VanillaNetworkConfig) and (nc.use_layer_norm or nc.use_skip_connections):
-                raise NotImplementedError("MLP layer norm / skip connections are not on the accelerated path")
         self._multihead = type(pnc) is MultiHeadConfig
+        use_ln = (not self._multihead) and bool(pnc.use_layer_norm)
+        use_skip = (not self._multihead) and bool(pnc.use_skip_connections)
+        if not self._multihead and (pnc.use_layer_norm, pnc.use_skip_connections) != (vnc.use_layer_norm, vnc.use_skip_connections):
+            raise NotImplementedError("policy and value function must share use_layer_norm / use_skip_connections")
         heads = config.num_tasks if self._multihead else 1
         p_opt, v_opt = pnc.optimizer.spawn(), vnc.optimizer.spawn()
         nm = lambda v: -1.0 if v is None else float(v)  # noqa: E731
@@ -115,7 +118,8 @@ class MTPPO:
             normalize_advantages=int(config.normalize_advantages), policy_lr=p_opt.lr, vf_lr=v_opt.lr, adam_b1=p_opt.b1,
             adam_b2=p_opt.b2, adam_eps=p_opt.eps, policy_max_grad_norm=nm(p_opt.max_grad_norm),
             vf_max_grad_norm=nm(v_opt.max_grad_norm), log_std_min=config.policy_config.log_std_min,
-            log_std_max=config.policy_config.log_std_max, noise_seed=int(seed) & (2**63 - 1))
+            log_std_max=config.policy_config.log_std_max, noise_seed=int(seed) & (2**63 - 1),
+            use_layer_norm=int(use_ln), use_skip_connections=int(use_skip))
         lay = PpoLayoutC()
         L.check(L.lib().mtrl_ppo_query_layout(C.byref(self._cfg), C.byref(lay)))
         self._lay = lay
@@ -149,6 +153,9 @@ class MTPPO:
                 p["VmapDense_0"] = {"kernel": uniform(bound)(gen, (heads, nc.width, head_dim)), "bias": uniform(bound)(gen, (heads, head_dim))}
             else:
                 p[f"layer_{nc.depth}"] = {"kernel": uniform(bound)(gen, (nc.width, head_dim)), "bias": uniform(bound)(gen, (head_dim,))}
+                if nc.use_layer_norm:   # flax LayerNorm: scale = ones, bias = zeros (mtrl/nn/base.py:35-37, 52-53)
+                    for k in range(nc.depth):
+                        p[f"LayerNorm_{k}"] = {"scale": torch.ones(nc.width), "bias": torch.zeros(nc.width)}
             return p
         self._inner = (lambda t: t["params"][net_name]) if self._multihead else (lambda t: t["params"][net_name]["MLP_0"])
         _tree_copy_(self._inner(self.policy.params), init(pnc, 2 * act_dim, 1e-3))      # networks.py:33-34

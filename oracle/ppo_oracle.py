@@ -54,9 +54,26 @@ def init_state(cfg: PPOConfig, seed: int = 1, dtype=torch.float32) -> PPOState:
     n = cfg.net
     policy = init_multihead(gen, n.obs_dim, n, 2 * n.action_dim, 1e-3, None, dtype)
     vf = init_multihead(gen, n.obs_dim, n, 1, 3e-3, None, dtype)
+    if n.use_layer_norm:   # plain MLP (VanillaNetworkConfig): flax LayerNorm params, scale = ones, bias = zeros
+        for net in (policy, vf):
+            for k in range(n.depth):
+                net[f"LayerNorm_{k}"] = {"scale": torch.ones(n.width, dtype=dtype), "bias": torch.zeros(n.width, dtype=dtype)}
     zeros = lambda t: tree_map(torch.zeros_like, t)  # noqa: E731
     return PPOState(policy, vf, {"policy": {"m": zeros(policy), "v": zeros(policy), "count": 0},
                                  "vf": {"m": zeros(vf), "v": zeros(vf), "count": 0}})
+
+
+def net_forward(p: dict, obs: torch.Tensor, n: OracleConfig) -> torch.Tensor:
+    """MultiHeadNetwork (num_tasks > 1), or the plain MLP of VanillaNetwork for num_tasks == 1 -- then with its optional
+    LayerNorm / skip connections (mtrl/nn/base.py:32-63); the MLP's output Dense is the single 'head'."""
+    if not (n.use_layer_norm or n.use_skip_connections):
+        return multihead_forward(p, obs, n.num_tasks, n.depth, False, n.matmul_operands)
+    assert n.num_tasks == 1, "LayerNorm / skip connections belong to the plain MLP"
+    from .sac_oracle import mlp_forward
+
+    q = {k: v for k, v in p.items() if k != "heads"}
+    q[f"layer_{n.depth}"] = {"kernel": p["heads"]["kernel"][0], "bias": p["heads"]["bias"][0]}
+    return mlp_forward(q, obs, n.depth, n.matmul_operands, n.use_layer_norm, n.use_skip_connections)
 
 
 def ppo_update(state: PPOState, rollout, eps: torch.Tensor, cfg: PPOConfig, return_grads: bool = False):
@@ -66,7 +83,7 @@ def ppo_update(state: PPOState, rollout, eps: torch.Tensor, cfg: PPOConfig, retu
     logs, opt = {}, dict(state.opt)
     # ---- policy (mtppo.py:196-254) ----
     pp = _with_grad(state.policy)
-    out = multihead_forward(pp, obs, n.num_tasks, n.depth, False, n.matmul_operands)
+    out = net_forward(pp, obs, n)
     log_std = torch.clamp(out[..., n.action_dim:], n.log_std_min, n.log_std_max)          # networks.py:37-41
     new_logp = (-0.5 * eps**2 - 0.5 * math.log(2 * math.pi) - log_std).sum(-1)               # fresh sample, :205-207
     log_ratio = new_logp.reshape(-1, 1) - old_logp                                          # :208
@@ -83,7 +100,7 @@ def ppo_update(state: PPOState, rollout, eps: torch.Tensor, cfg: PPOConfig, retu
                  "losses/approx_kl": approx_kl, "losses/clip_fracs": clip_fracs})
     # ---- value function (mtppo.py:256-290) ----
     vp = _with_grad(state.vf)
-    v = multihead_forward(vp, obs, n.num_tasks, n.depth, False, n.matmul_operands)
+    v = net_forward(vp, obs, n)
     if cfg.clip_vf_loss:
         unclipped = (v - returns) ** 2
         v_clipped = old_values + torch.clamp(v - old_values, -cfg.clip_eps, cfg.clip_eps)

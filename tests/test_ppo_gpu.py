@@ -20,7 +20,8 @@ def make_ppo(cfg: P.PPOConfig, steps: int, multihead: bool, seed=1):
     n = cfg.net
     opt = OptimizerConfig(lr=n.lr, max_grad_norm=n.max_grad_norm, eps=n.adam_eps)
     net = (MultiHeadConfig(width=n.width, depth=n.depth, num_tasks=n.num_tasks, optimizer=opt) if multihead
-           else VanillaNetworkConfig(width=n.width, depth=n.depth, optimizer=opt))
+           else VanillaNetworkConfig(width=n.width, depth=n.depth, optimizer=opt, use_layer_norm=n.use_layer_norm,
+                                     use_skip_connections=n.use_skip_connections))
     pc = MTPPOConfig(num_tasks=n.num_tasks if multihead else 5,
                      policy_config=ContinuousActionPolicyConfig(network_config=net, squash_tanh=False),
                      vf_config=ValueFunctionConfig(network_config=net), clip_eps=cfg.clip_eps, clip_vf_loss=cfg.clip_vf_loss,
@@ -34,7 +35,7 @@ def pairs(otree, agent, ts):
     out = []
     for k, v in otree.items():
         ak = ("VmapDense_0" if agent._multihead else f"layer_{agent._cfg.depth}") if k == "heads" else k
-        for leaf in ("kernel", "bias"):
+        for leaf in v:
             o = v[leaf]
             if k == "heads" and not agent._multihead:
                 o = o[0]
@@ -42,8 +43,14 @@ def pairs(otree, agent, ts):
     return out
 
 
-def run(cfg, steps, multihead):
+def run(cfg, steps, multihead, perturb_ln=False):
     st = P.init_state(cfg, seed=3)
+    if perturb_ln:   # non-trivial LayerNorm scales / biases
+        g = torch.Generator().manual_seed(11)
+        for net in (st.policy, st.vf):
+            for k in range(cfg.net.depth):
+                net[f"LayerNorm_{k}"]["scale"] = 1.0 + 0.3 * torch.randn(cfg.net.width, generator=g)
+                net[f"LayerNorm_{k}"]["bias"] = 0.2 * torch.randn(cfg.net.width, generator=g)
     agent = make_ppo(cfg, steps if multihead else steps // 5, multihead, seed=3)
     for o, ts in ((st.policy, agent.policy.params), (st.vf, agent.value_function.params)):
         for _, src, dst in pairs(o, agent, ts):
@@ -94,6 +101,15 @@ def test_ppo_multihead_mt10_w256_no_clip_vf_no_norm(cuda):
 def test_ppo_vanilla_mlp(cuda):
     cfg = P.PPOConfig(net=O.OracleConfig(num_tasks=1, obs_dim=49, action_dim=4, width=128, depth=2))
     run(cfg, steps=640, multihead=False)
+
+
+@pytest.mark.parametrize("ln,skip", [(True, False), (False, True), (True, True)])
+def test_ppo_vanilla_mlp_layer_norm_and_skip_connections(cuda, ln, skip):
+    """MT-PPO on VanillaNetworkConfig(use_layer_norm / use_skip_connections) (mtrl/nn/base.py:32-63): the junction kernels of
+    csrc/ln_kernels.cuh in the PPO update, LayerNorm scale / bias gradients included."""
+    cfg = P.PPOConfig(net=O.OracleConfig(num_tasks=1, obs_dim=49, action_dim=4, width=128, depth=3, use_layer_norm=ln,
+                                         use_skip_connections=skip))
+    run(cfg, steps=640, multihead=False, perturb_ln=ln)
 
 
 def test_ppo_requires_unsquashed_policy(cuda):
