@@ -469,7 +469,17 @@ def main() -> None:
     ms_stream = p0.elapsed_time(p1)
     gemm_ms, gemm_launches = agent.profile_read()
     xchg_ms, xchg_launches = agent.profile_exchange()
+    classes = agent.profile_classes()
     agent.profile_gemms(False)
+    # the replay sampler's two kernels (index draw + slab gather), event-bracketed the same way
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    s0.record()
+    for _ in range(args.steps):
+        buf.sample(B_local)
+    s1.record()
+    barrier()
+    sampler_ms = s0.elapsed_time(s1) / args.steps
 
     # ---------------- timed region 2: end to end through the public API with host buffers ----------------
     n_host = min(args.steps, 8)
@@ -583,6 +593,25 @@ def main() -> None:
         }
         if parity is not None:
             line["parity_check"] = parity
+        # HBM-bound kernels of the step: algorithmic bytes (M = this rank's rows) / event-bracketed duration
+        Pa, Pc, E = agent._lay.actor.total, agent._lay.critic.total, 2
+        Mrows, od = B_local if (world > 1 or emulate) else B, 39 + T
+        alg = {"adam_polyak": 32.0 * (Pa + Pc) + 8.0 * Pc, "head_vjp": (4 * E + 2) * Mrows * W * 4.0, "critic_loss": 2 * E * Mrows * W * 4.0,
+               "actor_loss": E * Mrows * W * 4.0, "actor_head": 2 * Mrows * W * 4.0, "grad_norms": 4.0 * (Pa + Pc)}
+        hbm = []
+        for name, (cms, cn) in classes.items():
+            if name in alg and cn:
+                per_step_ms = cms / args.steps
+                gbs = alg[name] / (per_step_ms * 1e-3) / 1e9
+                hbm.append({"kernel": name, "launches_per_step": cn / args.steps, "ms_per_step": per_step_ms,
+                            "algorithmic_bytes_per_step": alg[name], "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peaks["hbm_gbs"]})
+        samp_bytes = 2.0 * Mrows * (8 * od + 24)
+        hbm.append({"kernel": "replay_sampler (draw_indices + gather_slabs)", "launches_per_step": 2, "ms_per_step": sampler_ms,
+                    "algorithmic_bytes_per_step": samp_bytes, "achieved_gbs": samp_bytes / (sampler_ms * 1e-3) / 1e9,
+                    "frac_of_hbm_peak": samp_bytes / (sampler_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                    "note": "latency-bound: 9.4 MB per step; includes the Python call overhead of sample()"})
+        line["hbm_kernels"] = {"peak_gbs": peaks["hbm_gbs"], "peak_source": peaks["_source"] + " copy bandwidth", "kernels": hbm,
+                               "other_classes_ms_per_step": {k: v[0] / args.steps for k, v in classes.items() if k not in alg and k != "gemm"}}
         if emulate:
             line["config"]["emulated_shard_of"] = emulate
             line["config"]["note"] = "PROFILING AID: rank 0's shard alone, no exchange; not a benchmark result"

@@ -384,6 +384,11 @@ int mtrl_sac_profile_read(mtrl_sac_t* h, double* total_ms, int* launches);
 /* The exchange kernels (csrc/comm.cuh) bracketed in the same pass: their summed duration and count as of the last
  * mtrl_sac_profile_read. */
 int mtrl_sac_profile_exchange(mtrl_sac_t* h, double* total_ms, int* launches);
+/* The other kernel classes bracketed in the same pass, as of the last mtrl_sac_profile_read: ms12[c] / n12[c] = summed
+ * duration / number of launches of class c: 0 GEMM, 1 exchange, 2 Adam + Polyak, 3 head VJP, 4 critic loss, 5 actor head
+ * (policy sample + log-prob), 6 actor loss, 7 batch packing (3 kernels per bracket), 8 gradient norms, 9 bias-gradient
+ * column sums, 10 LayerNorm junctions; 11 unused. */
+int mtrl_sac_profile_classes(mtrl_sac_t* h, double* ms12, int* n12);
 /* Asynchronous copy of the status words of the last update into 4 pinned host ints:
  * [0] == 0 ok, 1: a row's task is outside this handle's task range, 2: rows do not fit max_rows, 3: unbalanced split;
  * [1] != 0: the peer exchange is dead -- an in-kernel wait for another rank timed out (code = 1 + barrier, 10 + barrier

@@ -197,6 +197,8 @@ struct mtrl_sac {
   size_t ev_used = 0;
   double exchange_ms = 0.0;
   int exchange_launches = 0;
+  double class_ms[12] = {};
+  int class_n[12] = {};
   // fused peer-memory exchange (comm.cuh); null = single GPU, or the caller all-reduces between the phases
   mtrl_comm* comm = nullptr;
   long long off_critic_grads = 0, off_actor_grads = 0, off_critic_params = 0, off_actor_params = 0;
@@ -425,6 +427,10 @@ int build_plans(mtrl_sac* h) {
 
 #define LAUNCHED(h) ((h)->launches++)
 
+// Kernel classes of the event-bracketed profiling pass (mtrl_sac_profile_gemms / _read / _classes).
+enum ProfTag { PT_GEMM = 0, PT_EXCHANGE = 1, PT_ADAM = 2, PT_HEAD_BWD = 3, PT_CRITIC_LOSS = 4, PT_ACTOR_HEAD = 5, PT_ACTOR_LOSS = 6,
+               PT_PACK = 7, PT_SUMSQ = 8, PT_COLSUM = 9, PT_JUNCTION = 10, PT_COUNT = 12 };
+
 int prof_begin(mtrl_sac* h, int tag, cudaStream_t st) {
   if (!h->prof) return MTRL_OK;
   while (h->ev.size() < h->ev_used + 2) {
@@ -490,6 +496,7 @@ int launch_actor_head(mtrl_sac* h, const float* H, const float* eps, float* Xdst
   a.ls_min = c.log_std_min;
   a.ls_max = c.log_std_max;
   const size_t wbytes = static_cast<size_t>(c.width + 4) * 2 * c.action_dim * sizeof(float);
+  MTRL_PROPAGATE(prof_begin(h, PT_ACTOR_HEAD, st));
   if (wbytes <= 200 * 1024) {
     // few rows (a task shard of a multi-GPU job): smaller blocks so the launch still covers the SMs
     const int rpb = c.max_rows <= 4096 ? 16 : 32;
@@ -502,6 +509,7 @@ int launch_actor_head(mtrl_sac* h, const float* H, const float* eps, float* Xdst
     }
 #undef MTRL_AH_TILE
     MTRL_CUDA_CHECK(cudaGetLastError());
+    MTRL_PROPAGATE(prof_end(h, st));
     LAUNCHED(h);
     return MTRL_OK;
   }
@@ -509,16 +517,19 @@ int launch_actor_head(mtrl_sac* h, const float* H, const float* eps, float* Xdst
   dim3 grid((c.max_rows + wpb - 1) / wpb), block(wpb * 32);
   launch_actor_head_rows(a, c.action_dim, grid, block, st);
   MTRL_CUDA_CHECK(cudaGetLastError());
+  MTRL_PROPAGATE(prof_end(h, st));
   LAUNCHED(h);
   return MTRL_OK;
 }
 
 int launch_head_bwd(mtrl_sac* h, const HeadBwdArgs& a, int hd, int E, cudaStream_t st) {
+  MTRL_PROPAGATE(prof_begin(h, PT_HEAD_BWD, st));
   if (!launch_head_bwd_any(a, hd, h->cfg.num_local_tasks, E, st)) {
     mtrl_set_error("head_bwd: unsupported head_dim %d", hd);
     return MTRL_ERR_UNSUPPORTED;
   }
   MTRL_CUDA_CHECK(cudaGetLastError());
+  MTRL_PROPAGATE(prof_end(h, st));
   LAUNCHED(h);
   return MTRL_OK;
 }
@@ -526,8 +537,10 @@ int launch_head_bwd(mtrl_sac* h, const HeadBwdArgs& a, int hd, int E, cudaStream
 int launch_colsum(mtrl_sac* h, const ColsumJobs& jobs, int groups, cudaStream_t st) {
   const int W = h->cfg.width;
   dim3 g((W + 31) / 32, jobs.njobs);
+  MTRL_PROPAGATE(prof_begin(h, PT_COLSUM, st));
   mtrl_launch(colsum_final_kernel, g, dim3(256), 0, st, jobs, groups, W);
   MTRL_CUDA_CHECK(cudaGetLastError());
+  MTRL_PROPAGATE(prof_end(h, st));
   LAUNCHED(h);
   return MTRL_OK;
 }
@@ -664,9 +677,11 @@ int run_trunk_backward(mtrl_sac* h, std::vector<mtrl_gemm_plan_t*>& plans, float
 
 int head_sumsq_to_slot(mtrl_sac* h, float* grads, const mtrl_net_layout_t& L, int acc_idx, cudaStream_t st) {
   const long long n = L.total - L.heads_base;
+  MTRL_PROPAGATE(prof_begin(h, PT_SUMSQ, st));
   mtrl_launch(sumsq_kernel, dim3(64), dim3(256), 0, st, grads + L.heads_base, n, h->ws.acc + acc_idx);
   mtrl_launch(write_slot_kernel, dim3(1), dim3(1), 0, st, grads + L.slots_off, h->ws.acc + acc_idx);
   MTRL_CUDA_CHECK(cudaGetLastError());
+  MTRL_PROPAGATE(prof_end(h, st));
   h->launches += 2;
   return MTRL_OK;
 }
@@ -824,6 +839,7 @@ int step_begin(mtrl_sac* h, const float* obs, const float* actions, const float*
   const int nchunks = (batch + 31) / 32;
   const size_t smem = (static_cast<size_t>(nchunks) * T + T + 1) * sizeof(int);
   MTRL_REQUIRE(smem <= 200 * 1024, "mtrl_sac_update: batch %d x %d tasks exceeds the packing kernel's shared memory", batch, T);
+  MTRL_PROPAGATE(prof_begin(h, PT_PACK, st));
   mtrl_launch(row_task_kernel, dim3((batch + 7) / 8), dim3(256), 0, st, obs, batch, c.obs_dim, c.num_tasks, c.task_begin, T, w.row_slot, w.status);
   mtrl_launch(pack_plan_kernel, dim3(1), dim3(1024), smem, st, batch, T, M, w.row_slot, w.slot_src, w.tile_task, w.seg_start, w.status);
   h->launches += 2;
@@ -841,6 +857,7 @@ int step_begin(mtrl_sac* h, const float* obs, const float* actions, const float*
   mtrl_launch(pack_rows_kernel, M, dim3(128), 0, st, a);
   LAUNCHED(h);
   MTRL_CUDA_CHECK(cudaGetLastError());
+  MTRL_PROPAGATE(prof_end(h, st));
   for (int l = 0; l < D; ++l) {
     MTRL_PROPAGATE(run_plan(h, h->fwd[l], st));
     if (h->ln_mode) {
@@ -889,8 +906,10 @@ int step_critic_grads(mtrl_sac* h, cudaStream_t st) {
     // MT-SAC: L = mean over (E, B) of (q-y)^2 (mtsac.py:565); SAC: L = 0.5 * sum_e mean_b (q-y)^2 (sac.py:292)
     a.dq_scale = c.variant == MTRL_VARIANT_SAC ? 1.f / B : 2.f / (static_cast<float>(E) * B);
     a.clip = c.clip_q;
+    MTRL_PROPAGATE(prof_begin(h, PT_CRITIC_LOSS, st));
     mtrl_launch(critic_loss_kernel, dim3((M + 7) / 8), dim3(256), 0, st, a);
     MTRL_CUDA_CHECK(cudaGetLastError());
+    MTRL_PROPAGATE(prof_end(h, st));
     LAUNCHED(h);
   }
   {
@@ -947,7 +966,9 @@ int step_critic_apply(mtrl_sac* h, cudaStream_t st) {
     MTRL_CUDA_CHECK(cudaGetLastError());
     return MTRL_OK;
   }
+  MTRL_PROPAGATE(prof_begin(h, PT_SUMSQ, st));
   mtrl_launch(sumsq_kernel, dim3(h->sms * 2), dim3(256), 0, st, h->buf.critic_grads, LC.trunk_total, w.acc + ACC_CRITIC_G2);
+  MTRL_PROPAGATE(prof_end(h, st));
   LAUNCHED(h);
   AdamArgs a;
   memset(&a, 0, sizeof(a));
@@ -960,7 +981,9 @@ int step_critic_apply(mtrl_sac* h, cudaStream_t st) {
   a.p2_trunk = w.acc + ACC_CRITIC_P2_TRUNK; a.p2_head = w.acc + ACC_CRITIC_P2_HEAD; a.p2_old = w.acc + ACC_CRITIC_P2_OLD;
   a.lr = c.critic_lr; a.b1 = c.adam_b1; a.b2 = c.adam_b2; a.eps = c.adam_eps; a.max_norm = c.critic_max_grad_norm;
   a.tau = c.tau;
+  MTRL_PROPAGATE(prof_begin(h, PT_ADAM, st));
   mtrl_launch(adam_kernel, dim3(h->sms * 4), dim3(256), 0, st, a);
+  MTRL_PROPAGATE(prof_end(h, st));
   LAUNCHED(h);
   mtrl_launch(finalize_critic_kernel, dim3(1), dim3(1), 0, st, w.acc, h->buf.critic_grads + LC.slots_off, h->buf.steps, h->buf.logs, 1.f / EB,
                                           loss_scale, c.variant == MTRL_VARIANT_SAC);
@@ -1015,8 +1038,10 @@ int step_actor_grads(mtrl_sac* h, cudaStream_t st) {
     }
     a.tile_task = w.tile_task; a.slot_src = w.slot_src; a.logp = w.logp; a.alpha_val = w.alpha_val; a.task_w = w.task_w;
     a.dq = w.dq; a.acc = w.acc; a.M = M; a.W = W; a.E = E; a.inv_b = inv_b; a.h_lo_delta = w.lo_delta;
+    MTRL_PROPAGATE(prof_begin(h, PT_ACTOR_LOSS, st));
     mtrl_launch(actor_loss_kernel, dim3((M + 7) / 8), dim3(256), 0, st, a);
     MTRL_CUDA_CHECK(cudaGetLastError());
+    MTRL_PROPAGATE(prof_end(h, st));
     LAUNCHED(h);
   }
   {
@@ -1081,7 +1106,9 @@ int step_actor_apply(mtrl_sac* h, cudaStream_t st) {
     MTRL_CUDA_CHECK(cudaGetLastError());
     return MTRL_OK;
   }
+  MTRL_PROPAGATE(prof_begin(h, PT_SUMSQ, st));
   mtrl_launch(sumsq_kernel, dim3(h->sms * 2), dim3(256), 0, st, h->buf.actor_grads, LA.trunk_total, w.acc + ACC_ACTOR_G2);
+  MTRL_PROPAGATE(prof_end(h, st));
   LAUNCHED(h);
   AdamArgs a;
   memset(&a, 0, sizeof(a));
@@ -1093,7 +1120,9 @@ int step_actor_apply(mtrl_sac* h, cudaStream_t st) {
   a.step = h->buf.steps + 0;
   a.p2_trunk = w.acc + ACC_ACTOR_P2_TRUNK; a.p2_head = w.acc + ACC_ACTOR_P2_HEAD; a.p2_old = w.acc + ACC_ACTOR_P2_OLD;
   a.lr = c.actor_lr; a.b1 = c.adam_b1; a.b2 = c.adam_b2; a.eps = c.adam_eps; a.max_norm = c.actor_max_grad_norm; a.tau = 0.f;
+  MTRL_PROPAGATE(prof_begin(h, PT_ADAM, st));
   mtrl_launch(adam_kernel, dim3(h->sms * 4), dim3(256), 0, st, a);
+  MTRL_PROPAGATE(prof_end(h, st));
   LAUNCHED(h);
   mtrl_launch(finalize_actor_kernel, dim3(1), dim3(1), 0, st, w.acc, h->buf.actor_grads + LA.slots_off, h->buf.steps, h->buf.logs,
                                          1.f / static_cast<float>(h->global_batch), c.variant == MTRL_VARIANT_SAC,
@@ -1791,18 +1820,21 @@ extern "C" int mtrl_sac_profile_gemms(mtrl_sac_t* h, int enable) {
 // Sum of the event-bracketed GEMM launch durations since profiling was enabled (synchronises on the events).
 extern "C" int mtrl_sac_profile_read(mtrl_sac_t* h, double* total_ms, int* launches) {
   MTRL_REQUIRE(h && total_ms && launches, "mtrl_sac_profile_read: null argument");
-  double sum = 0.0, xsum = 0.0;
-  int n = 0, xn = 0;
+  double sum = 0.0, xsum = 0.0, class_ms[PT_COUNT] = {};
+  int n = 0, xn = 0, class_n[PT_COUNT] = {};
   for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
     MTRL_CUDA_CHECK(cudaEventSynchronize(h->ev[i + 1]));
     float ms = 0.f;
     MTRL_CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]));
-    if (h->ev_tag[i / 2] == 0) { sum += ms; ++n; } else { xsum += ms; ++xn; }
+    const int tag = h->ev_tag[i / 2];
+    if (tag >= 0 && tag < PT_COUNT) { class_ms[tag] += ms; ++class_n[tag]; }
+    if (tag == PT_GEMM) { sum += ms; ++n; } else if (tag == PT_EXCHANGE) { xsum += ms; ++xn; }
   }
   *total_ms = sum;
   *launches = n;
   h->exchange_ms = xsum;
   h->exchange_launches = xn;
+  for (int i = 0; i < PT_COUNT; ++i) { h->class_ms[i] = class_ms[i]; h->class_n[i] = class_n[i]; }
   h->ev_used = 0;
   return MTRL_OK;
 }
@@ -1813,6 +1845,13 @@ extern "C" int mtrl_sac_profile_exchange(mtrl_sac_t* h, double* total_ms, int* l
   MTRL_REQUIRE(h && total_ms && launches, "mtrl_sac_profile_exchange: null argument");
   *total_ms = h->exchange_ms;
   *launches = h->exchange_launches;
+  return MTRL_OK;
+}
+// Per kernel class (see include/mtrl_b200.h MTRL_PROF_*): summed event-bracketed duration and launch count as of the last
+// mtrl_sac_profile_read.
+extern "C" int mtrl_sac_profile_classes(mtrl_sac_t* h, double* ms12, int* n12) {
+  MTRL_REQUIRE(h && ms12 && n12, "mtrl_sac_profile_classes: null argument");
+  for (int i = 0; i < PT_COUNT; ++i) { ms12[i] = h->class_ms[i]; n12[i] = h->class_n[i]; }
   return MTRL_OK;
 }
 // Device int[4] written by the packing kernel: [0] != 0 means the last batch was rejected

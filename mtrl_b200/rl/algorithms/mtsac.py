@@ -120,6 +120,7 @@ L._EXTRA_DECLS.update({
     "mtrl_sac_profile_gemms": ([_vp, _i],),
     "mtrl_sac_profile_read": ([_vp, C.POINTER(C.c_double), C.POINTER(_i)],),
     "mtrl_sac_profile_exchange": ([_vp, C.POINTER(C.c_double), C.POINTER(_i)],),
+    "mtrl_sac_profile_classes": ([_vp, C.POINTER(C.c_double), C.POINTER(_i)],),
     "mtrl_comm_create": ([C.POINTER(_vp), _i, _i, C.c_longlong, _vp],),
     "mtrl_comm_arena": ([_vp], _vp),
     "mtrl_comm_open_peers": ([_vp, _vp],),
@@ -660,6 +661,15 @@ class MTSAC:
         L.check(L.lib().mtrl_comm_phase_times(self._comm, buf))
         names = ("wait_grads", "norms", "norm_exchange", "adam_allgather", "wait_stores", "derived", "total")
         return {"critic": dict(zip(names, list(buf)[:7])), "actor": dict(zip(names, list(buf)[7:]))}
+
+    PROFILE_CLASSES = ("gemm", "exchange", "adam_polyak", "head_vjp", "critic_loss", "actor_head", "actor_loss", "pack",
+                       "grad_norms", "bias_colsum", "layernorm_junction", "unused")
+
+    def profile_classes(self) -> dict:
+        """{kernel class: (summed ms, launches)} of the event-bracketed pass, as of the last profile_read()."""
+        ms, n = (C.c_double * 12)(), (_i * 12)()
+        L.check(L.lib().mtrl_sac_profile_classes(self._h, ms, n))
+        return {k: (ms[i], n[i]) for i, k in enumerate(self.PROFILE_CLASSES) if n[i]}
 
     def profile_exchange(self) -> tuple[float, int]:
         """(sum of exchange-kernel durations in ms, their count) as of the last profile_read()."""
