@@ -61,7 +61,10 @@ typedef struct mtrl_gemm_problem {
                             every 32-row group of D (bias gradients are their sum over groups); NULL to skip  */
   int schedule_first;    /* != 0: this problem's tiles are dealt to the workers before all others (outputs that travel
                             over NVLink: their stores then overlap the remaining tiles instead of the launch's tail)  */
-  int reserved;
+  int phase;             /* 0 .. 7.  Problems of phase p start only after EVERY problem of the launch with a smaller phase
+                            has completed and its outputs are visible (a grid-wide barrier inside the persistent kernel):
+                            the consecutive Dense layers of one network pass, or of its backward, run as ONE launch
+                            instead of one launch per layer.  All zero = a plain grouped launch.                      */
   /* fp32x3 mode ("3xTF32", the precision the reference's fp32 CPU dots have).  A_lo / B_lo: the tf32 remainders of the
    * operands (x = hi + lo, both tf32; same shape, pitch and layout as A / B).  Both set: the contraction accumulates
    * A B + A B_lo + A_lo B in the same fp32 TMEM accumulator (three tcgen05.mma passes per k-block).  D_lo (needs an

@@ -26,7 +26,7 @@ class GemmProblem(C.Structure):
         ("block_n", C.c_int), ("k_splits", C.c_int), ("epilogue", C.c_int),
         ("bias", C.c_void_p), ("mask", C.c_void_p), ("ldmask", C.c_longlong),
         ("mask_bits", C.c_void_p), ("relu_bits_out", C.c_void_p), ("ldbits", C.c_longlong), ("colsum_partial", C.c_void_p),
-        ("schedule_first", C.c_int), ("reserved", C.c_int),
+        ("schedule_first", C.c_int), ("phase", C.c_int),
         ("A_lo", C.c_void_p), ("B_lo", C.c_void_p), ("D_lo", C.c_void_p),
     ]
 

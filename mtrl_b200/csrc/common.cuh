@@ -129,6 +129,8 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+// Orders generic-proxy and async-proxy (TMA) accesses to any state space against each other.
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(tmap), "r"(src), "r"(c0), "r"(c1)

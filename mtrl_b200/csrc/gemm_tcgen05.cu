@@ -107,6 +107,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 
 constexpr int kMaxProblems = 24;
 constexpr int kMapsPer = 6;
+constexpr int kMaxPhases = 8;
 
 // Passed by value as a __grid_constant__ kernel parameter (the usual home of TMA descriptors).
 struct GemmParams {
@@ -115,9 +116,13 @@ struct GemmParams {
   int nprob;
   int total_units;
   long long* dbg;  // optional: 8 cycle counters summed over CTAs (see mtrl_gemm_plan_set_debug)
-  // Static schedule built by the host (longest-processing-time-first over the workers): worker w runs units
-  // sched[nworkers + 1 + i] for i in [sched[w], sched[w + 1]).
+  // Static schedule built by the host (longest-processing-time-first over the workers, phase by phase): worker w runs,
+  // in phase p, units sched[nworkers * nphases + 1 + i] for i in [sched[w * nphases + p], sched[w * nphases + p + 1]).
   const int* sched;
+  // Phases: between two phases every CTA meets at a grid-wide barrier (phase_cnt[p], one ticket counter per boundary,
+  // monotonic over launches: a launch adds exactly gridDim.x tickets to each) after its TMA stores have completed.
+  int nphases;
+  unsigned long long* phase_cnt;
 };
 
 struct UnitCoord {
@@ -187,6 +192,7 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  const uint32_t phase_bar = bar_base + 8u * (2 * kStages + 5);   // epilogue leader -> producer: the grid passed the phase barrier
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -195,8 +201,9 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
   const uint32_t rank = kCtas == 2 ? cluster_ctarank() : 0u;   // 0 = leader of the pair
   const int worker = blockIdx.x / kCtas;                       // CTA (or pair) index
   const int nworkers = gridDim.x / kCtas;
-  const int* __restrict__ sched_units = params.sched + nworkers + 1;
-  const int sched_begin = params.sched[worker], sched_end = params.sched[worker + 1];
+  const int nphases = params.nphases;
+  const int* __restrict__ sched_units = params.sched + nworkers * nphases + 1;
+  const int* __restrict__ sched_off = params.sched + worker * nphases;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -207,6 +214,7 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), kEpilogueWarps * kCtas);  // one arrive per epilogue warp of every CTA of the pair
     }
+    mbar_init(phase_bar, 1);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -233,7 +241,14 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
       int stage = 0;
       uint32_t phase = 0;
       long long t_wait = 0, t_issue = 0;
-      for (int si = sched_begin; si < sched_end; ++si) {
+      for (int ph = 0; ph < nphases; ++ph) {
+      if (ph > 0) {
+        // the operands of this phase are outputs of the previous one, written by other CTAs' TMA stores: wait until the
+        // whole grid has passed the phase barrier, then order this (async-proxy) reader behind it
+        mbar_wait(phase_bar, static_cast<uint32_t>(ph - 1) & 1u);
+        fence_proxy_async_all();
+      }
+      for (int si = sched_off[ph]; si < sched_off[ph + 1]; ++si) {
         const int unit = sched_units[si];
         const UnitCoord c = decode_unit(probs, nprob, unit);
         const DevProblem& P = probs[c.p];
@@ -294,6 +309,7 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
         }
         }  // sub-units
       }
+      }  // phases
       if (params.dbg && lane == 0) {
         atomicAdd(reinterpret_cast<unsigned long long*>(params.dbg + 0), static_cast<unsigned long long>(t_wait));
         atomicAdd(reinterpret_cast<unsigned long long*>(params.dbg + 1), static_cast<unsigned long long>(t_issue));
@@ -307,7 +323,7 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
       int acc = 0;
       uint32_t acc_phase = 0;
       long long t_wfull = 0, t_wtempty = 0, t_issue = 0, t_total0 = params.dbg ? clock64() : 0;
-      for (int si = sched_begin; si < sched_end; ++si) {
+      for (int si = sched_off[0]; si < sched_off[nphases]; ++si) {   // the issuer is paced by the producer: no phase logic here
         const int unit = sched_units[si];
         const UnitCoord c = decode_unit(probs, nprob, unit);
         const DevProblem& P = probs[c.p];
@@ -392,7 +408,8 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
     uint32_t acc_phase = 0;
     uint32_t nbox = 0;  // running count of TMA boxes this warp has issued (selects the staging buffer)
     long long t_wait = 0, t_work = 0;
-    for (int si = sched_begin; si < sched_end; ++si) {
+    for (int ph = 0; ph < nphases; ++ph) {
+    for (int si = sched_off[ph]; si < sched_off[ph + 1]; ++si) {
         const int unit = sched_units[si];
       const UnitCoord c = decode_unit(probs, nprob, unit);
       const DevProblem& P = probs[c.p];
@@ -630,6 +647,30 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
         acc_phase ^= 1u;
       }
     }
+    if (ph + 1 < nphases) {
+      // Phase barrier.  Writer side: this warp's bulk stores have completed, its plain stores (ReLU bits, column-sum
+      // partials, atomics) are fenced, all eight epilogue warps of the CTA have done so; then one thread takes a ticket
+      // and waits until every CTA of the grid has (tickets are monotonic over launches: generation = ticket / gridDim.x).
+      if (lane == 0) tma_store_wait<0>();
+      __threadfence();
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpilogueWarps) : "memory");
+      if (warp == 2 && lane == 0) {
+        fence_proxy_async_all();
+        unsigned long long* cnt = params.phase_cnt + ph;
+        const unsigned long long ticket = atomicAdd(cnt, 1ull);
+        const unsigned long long target = (ticket / gridDim.x + 1ull) * gridDim.x;
+        unsigned long long seen;
+        const long long t_spin = clock64();
+        do {
+          asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(cnt) : "memory");
+          // every CTA of the grid is resident (grid <= SM count, one CTA per SM), so this cannot wait long; a bound keeps a
+          // logic error from hanging the GPU (the results are then wrong and the parity tests say so)
+        } while (seen < target && clock64() - t_spin < (1ll << 32));
+        fence_proxy_async_all();
+        mbar_arrive(phase_bar);   // release the producer warp of this CTA into the next phase
+      }
+    }
+    }  // phases
     if (lane == 0) tma_store_wait<0>();   // all bulk stores of this warp have landed before the CTA retires
     if (params.dbg && lane == 0 && warp == 2) {
       atomicAdd(reinterpret_cast<unsigned long long*>(params.dbg + 6), static_cast<unsigned long long>(t_wait));
@@ -713,8 +754,10 @@ struct mtrl_gemm_plan {
   int grid = 0;
   int ctas = 1;  // 1: one CTA per tile; 2: CTA pairs (cta_group::2)
   int* d_sched = nullptr;
+  unsigned long long* d_phase_cnt = nullptr;
   ~mtrl_gemm_plan() {
     if (d_sched) cudaFree(d_sched);
+    if (d_phase_cnt) cudaFree(d_phase_cnt);
   }
 };
 
@@ -854,54 +897,67 @@ extern "C" int mtrl_gemm_plan_create_ex(mtrl_gemm_plan_t** out, const mtrl_gemm_
   }
   P.nprob = n;
   P.total_units = units;
+  int nphases = 1;
+  for (int i = 0; i < n; ++i) {
+    MTRL_REQUIRE(problems[i].phase >= 0 && problems[i].phase < kMaxPhases, "problem %d: phase %d outside [0, %d)", i,
+                 problems[i].phase, kMaxPhases);
+    nphases = std::max(nphases, problems[i].phase + 1);
+  }
+  P.nphases = nphases;
   const int workers = sms / ctas;
+  // with phases every CTA must be resident at once (they meet at in-kernel barriers): never more workers than CTA slots
   const int nworkers = units < workers ? units : workers;
   plan->grid = nworkers * ctas;
   {
-    // Longest-processing-time-first assignment.  Unit cost ~ k-blocks x tile width (narrow tiles are bounded by the
-    // per-k-block TMA / issue latency, not by the MMA) + a constant for prologue and epilogue drain.  Units of equal
-    // cost keep their index order, so a launch of uniform units degenerates to the round-robin it replaces
-    // (neighbouring workers share operand tiles in L2).
+    // Longest-processing-time-first assignment, phase by phase.  Unit cost ~ k-blocks x tile width (narrow tiles are
+    // bounded by the per-k-block TMA / issue latency, not by the MMA) + a constant for prologue and epilogue drain.
+    // Units of equal cost keep their index order, so a launch of uniform units degenerates to the round-robin it
+    // replaces (neighbouring workers share operand tiles in L2).
     struct U { int unit; long long cost; int first; };
-    std::vector<U> us;
-    us.reserve(units);
-    for (int i = 0; i < n; ++i) {
-      const DevProblem& d = P.probs[i];
-      for (int u = 0; u < d.unit_count; ++u) {
-        const int split = u / (d.n_tiles * d.m_tiles);
-        const int kb0 = split * d.kb_per_split;
-        const int kb1 = kb0 + d.kb_per_split < d.kb_total ? kb0 + d.kb_per_split : d.kb_total;
-        const long long per_kb = d.block_n > 160 ? d.block_n : 160;
-        us.push_back({d.unit_begin + u, static_cast<long long>(kb1 - kb0) * per_kb * (d.x3 ? 3 : 1) + 4 * 256,
-                      problems[i].schedule_first ? 1 : 0});
-      }
-    }
     const bool lpt = !(getenv("MTRL_GEMM_NO_LPT") && getenv("MTRL_GEMM_NO_LPT")[0] == '1');
-    // schedule_first problems (outputs reduce-added into a peer GPU) lead every worker's list; cost order within a class
-    if (lpt)
-      std::stable_sort(us.begin(), us.end(), [](const U& a, const U& b) { return a.first != b.first ? a.first > b.first : a.cost > b.cost; });
-    std::vector<std::vector<int>> lists(nworkers);
-    std::vector<long long> load(nworkers, 0);
-    for (size_t i = 0; i < us.size(); ++i) {
-      int best = static_cast<int>(i % nworkers);
-      if (lpt) {
-        best = 0;
-        for (int w = 1; w < nworkers; ++w)
-          if (load[w] < load[best]) best = w;
+    std::vector<std::vector<int>> lists(static_cast<size_t>(nworkers) * nphases);
+    for (int ph = 0; ph < nphases; ++ph) {
+      std::vector<U> us;
+      for (int i = 0; i < n; ++i) {
+        if (problems[i].phase != ph) continue;
+        const DevProblem& d = P.probs[i];
+        for (int u = 0; u < d.unit_count; ++u) {
+          const int split = u / (d.n_tiles * d.m_tiles);
+          const int kb0 = split * d.kb_per_split;
+          const int kb1 = kb0 + d.kb_per_split < d.kb_total ? kb0 + d.kb_per_split : d.kb_total;
+          const long long per_kb = d.block_n > 160 ? d.block_n : 160;
+          us.push_back({d.unit_begin + u, static_cast<long long>(kb1 - kb0) * per_kb * (d.x3 ? 3 : 1) + 4 * 256,
+                        problems[i].schedule_first ? 1 : 0});
+        }
       }
-      lists[best].push_back(us[i].unit);
-      load[best] += us[i].cost;
+      // schedule_first problems (outputs reduce-added into a peer GPU) lead every worker's list; cost order within a class
+      if (lpt)
+        std::stable_sort(us.begin(), us.end(), [](const U& a, const U& b) { return a.first != b.first ? a.first > b.first : a.cost > b.cost; });
+      std::vector<long long> load(nworkers, 0);
+      for (size_t i = 0; i < us.size(); ++i) {
+        int best = static_cast<int>(i % nworkers);
+        if (lpt) {
+          best = 0;
+          for (int w = 1; w < nworkers; ++w)
+            if (load[w] < load[best]) best = w;
+        }
+        lists[static_cast<size_t>(best) * nphases + ph].push_back(us[i].unit);
+        load[best] += us[i].cost;
+      }
     }
-    std::vector<int> table(nworkers + 1 + units);
+    std::vector<int> table(static_cast<size_t>(nworkers) * nphases + 1 + units);
     int off = 0;
-    for (int w = 0; w < nworkers; ++w) {
-      table[w] = off;
-      for (int u : lists[w]) table[nworkers + 1 + off++] = u;
+    for (size_t k = 0; k < lists.size(); ++k) {
+      table[k] = off;
+      for (int u : lists[k]) table[static_cast<size_t>(nworkers) * nphases + 1 + off++] = u;
     }
-    table[nworkers] = off;
+    table[static_cast<size_t>(nworkers) * nphases] = off;
     MTRL_CUDA_CHECK(cudaMalloc(&plan->d_sched, table.size() * sizeof(int)));
     MTRL_CUDA_CHECK(cudaMemcpy(plan->d_sched, table.data(), table.size() * sizeof(int), cudaMemcpyHostToDevice));
     P.sched = plan->d_sched;
+    MTRL_CUDA_CHECK(cudaMalloc(&plan->d_phase_cnt, kMaxPhases * sizeof(unsigned long long)));
+    MTRL_CUDA_CHECK(cudaMemset(plan->d_phase_cnt, 0, kMaxPhases * sizeof(unsigned long long)));
+    P.phase_cnt = plan->d_phase_cnt;
   }
   static bool attr_set = false;
   if (!attr_set) {

@@ -498,8 +498,8 @@ int launch_actor_head(mtrl_sac* h, const float* H, const float* eps, float* Xdst
   const size_t wbytes = static_cast<size_t>(c.width + 4) * 2 * c.action_dim * sizeof(float);
   MTRL_PROPAGATE(prof_begin(h, PT_ACTOR_HEAD, st));
   if (wbytes <= 200 * 1024) {
-    // few rows (a task shard of a multi-GPU job): smaller blocks so the launch still covers the SMs
-    const int rpb = c.max_rows <= 4096 ? 16 : 32;
+    // 16-row blocks, three resident per SM: 6400 rows = 400 blocks = one wave
+    const int rpb = c.max_rows <= 16 * 3 * h->sms ? 16 : 32;
     dim3 grid(c.max_rows / rpb), block(256);
 #define MTRL_AH_TILE(A_) \
   case A_: mtrl_launch(actor_head_tile_kernel<A_>, grid, block, wbytes, st, a, rpb); break;

@@ -459,8 +459,10 @@ static __global__ void actor_head_kernel(const ActorHeadArgs p) {
 // multiple of 16): the task's (W, 2A) head matrix is staged once per block in shared memory, transposed to
 // [2A][W + 4] so that a lane reads 4 consecutive hidden units of one output as a conflict-free float4.  A warp works
 // on two rows at a time (the weight reads are shared) with all of a row's float4 activation loads in flight.
+constexpr int kAhBatch = 4;
+
 template <int A>
-static __global__ void __launch_bounds__(256) actor_head_tile_kernel(const ActorHeadArgs p, int rows_per_block) {
+static __global__ void __launch_bounds__(256, 3) actor_head_tile_kernel(const ActorHeadArgs p, int rows_per_block) {
   MTRL_PDL_PROLOGUE();
   extern __shared__ __align__(16) float sw[];  // [2A][W + 4]
   const int ldw = p.W + 4;
@@ -520,10 +522,12 @@ static __global__ void __launch_bounds__(256) actor_head_tile_kernel(const Actor
     if (valid[0] || valid[1]) {
       const float4* h0 = reinterpret_cast<const float4*>(p.H + static_cast<long long>(rp) * p.W);
       const float4* h1 = reinterpret_cast<const float4*>(p.H + static_cast<long long>(rp + (rp + 1 < p.M ? 1 : 0)) * p.W);
-      for (int kb = lane; kb < W4; kb += 32 * 8) {
-        float4 a[8], b[8];
+      // kAhBatch float4 loads per row in flight per lane: small enough for three resident blocks per SM (85 registers),
+      // which with 16-row blocks puts a 6400-row batch in ONE wave (400 blocks <= 3 x 148 slots)
+      for (int kb = lane; kb < W4; kb += 32 * kAhBatch) {
+        float4 a[kAhBatch], b[kAhBatch];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < kAhBatch; ++u) {
           const int k4 = kb + 32 * u;
           a[u] = k4 < W4 ? h0[k4] : make_float4(0.f, 0.f, 0.f, 0.f);
           b[u] = k4 < W4 ? h1[k4] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -532,7 +536,7 @@ static __global__ void __launch_bounds__(256) actor_head_tile_kernel(const Actor
           const float4* l0 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(h0) + p.h_lo_delta);
           const float4* l1 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(h1) + p.h_lo_delta);
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
+          for (int u = 0; u < kAhBatch; ++u) {
             const int k4 = kb + 32 * u;
             if (k4 < W4) {
               const float4 x = l0[k4], y = l1[k4];
@@ -542,7 +546,7 @@ static __global__ void __launch_bounds__(256) actor_head_tile_kernel(const Actor
           }
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < kAhBatch; ++u) {
           const int k4 = kb + 32 * u;
           if (k4 < W4) {
 #pragma unroll

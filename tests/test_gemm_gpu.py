@@ -129,3 +129,85 @@ def test_relu_bits_roundtrip(cuda):
     L.GemmPlan([pm]).run()
     torch.cuda.synchronize()
     assert torch.equal(D1, D2)
+
+
+@pytest.mark.parametrize("ctas", [2, 1])
+def test_phased_launch_matches_layer_by_layer(cuda, ctas):
+    """Three dependent Dense layers (each reads what the previous one wrote) as ONE launch with grid-wide phase barriers
+    (`problem.phase`) vs one launch per layer: bit-identical outputs, repeatedly (a race on the barrier / the TMA-store
+    visibility would show up as a stale operand in some repetition)."""
+    import torch
+
+    import gemm_cases as G
+    from mtrl_b200 import _lib as L
+
+    M, W, K0 = 2304, 1024, 96
+    g = torch.Generator().manual_seed(7)
+    X = G.tf32_round(torch.randn(M, K0, generator=g)).cuda()
+    Ws = [G.tf32_round(torch.randn(K0 if i == 0 else W, W, generator=g) * (2.0 / (K0 if i == 0 else W)) ** 0.5).cuda() for i in range(3)]
+    bs = [(torch.randn(W, generator=g) * 0.1).cuda() for _ in range(3)]
+
+    def problems(outs, phased):
+        ps, x = [], X
+        for i in range(3):
+            ps.append(L.GemmProblem(A=x.data_ptr(), lda=x.stride(0), a_major=0, B=Ws[i].data_ptr(), ldb=W, b_major=1,
+                                    D=outs[i].data_ptr(), ldd=W, M=M, N=W, K=x.shape[1], block_n=256, k_splits=1,
+                                    epilogue=L.EPI_BIAS_RELU, bias=bs[i].data_ptr(), phase=i if phased else 0))
+            x = outs[i]
+        return ps
+
+    ref = [torch.zeros(M, W, device="cuda") for _ in range(3)]
+    for p in problems(ref, False):
+        L.GemmPlan([p], ctas=ctas).run()
+    torch.cuda.synchronize()
+    assert float(ref[2].abs().sum()) > 0
+    out = [torch.zeros(M, W, device="cuda") for _ in range(3)]
+    plan = L.GemmPlan(problems(out, True), ctas=ctas)
+    for rep in range(40):
+        for o in out:
+            o.fill_(float("nan"))
+        plan.run()
+        torch.cuda.synchronize()
+        for i in range(3):
+            assert torch.equal(out[i], ref[i]), f"repetition {rep}: layer {i} differs"
+
+
+def test_phased_backward_chain(cuda):
+    """dX of layer l feeds dW and dX of layer l - 1 inside one launch (MN-major 3-D maps read what a TMA store of the
+    previous phase wrote)."""
+    import torch
+
+    import gemm_cases as G
+    from mtrl_b200 import _lib as L
+
+    M, W = 1536, 768
+    g = torch.Generator().manual_seed(9)
+    dZ2 = G.tf32_round(torch.randn(M, W, generator=g)).cuda()
+    Hs = [G.tf32_round(torch.relu(torch.randn(M, W, generator=g))).cuda() for _ in range(2)]   # H0, H1 (forward activations)
+    Wk = [G.tf32_round(torch.randn(W, W, generator=g) * (2.0 / W) ** 0.5).cuda() for _ in range(3)]  # kernels (in, out) of layers 1, 2
+
+    def build(dZ1, dZ0, dW2, dW1, phased):
+        def dx(src, Wl, mask, dst, ph):
+            return L.GemmProblem(A=src.data_ptr(), lda=W, a_major=0, B=Wl.data_ptr(), ldb=W, b_major=0, D=dst.data_ptr(), ldd=W,
+                                 M=M, N=W, K=W, block_n=256, k_splits=1, epilogue=L.EPI_RELU_MASK, mask=mask.data_ptr(), ldmask=W,
+                                 phase=ph if phased else 0)
+
+        def dw(Xl, dZl, dst, ph):
+            return L.GemmProblem(A=Xl.data_ptr(), lda=W, a_major=1, B=dZl.data_ptr(), ldb=W, b_major=1, D=dst.data_ptr(), ldd=W,
+                                 M=W, N=W, K=M, block_n=256, k_splits=1, epilogue=L.EPI_STORE, phase=ph if phased else 0)
+        return [[dw(Hs[1], dZ2, dW2, 0), dx(dZ2, Wk[2], Hs[1], dZ1, 0)], [dw(Hs[0], dZ1, dW1, 1), dx(dZ1, Wk[1], Hs[0], dZ0, 1)]]
+
+    z = lambda *s: torch.zeros(*s, device="cuda")  # noqa: E731
+    r = [z(M, W), z(M, W), z(W, W), z(W, W)]
+    for layer in build(*r, False):
+        L.GemmPlan(layer).run()
+    torch.cuda.synchronize()
+    o = [z(M, W), z(M, W), z(W, W), z(W, W)]
+    plan = L.GemmPlan(sum(build(*o, True), []))
+    for rep in range(20):
+        for t in o:
+            t.fill_(float("nan"))
+        plan.run()
+        torch.cuda.synchronize()
+        for a, b in zip(o, r):
+            assert torch.equal(a, b), f"repetition {rep}"
