@@ -78,6 +78,9 @@ typedef struct mtrl_gemm_problem {
 
 typedef struct mtrl_gemm_plan mtrl_gemm_plan_t;
 
+#define MTRL_GEMM_MAX_PROBLEMS 24   /* problems per launch */
+#define MTRL_GEMM_MAX_PHASES 8      /* dependent phases per launch */
+
 /* Encodes the TMA descriptors for up to 24 problems that will run as one persistent launch. */
 int mtrl_gemm_plan_create(mtrl_gemm_plan_t** out, const mtrl_gemm_problem_t* problems, int n);
 /* Same with the tile shape chosen by the caller: ctas = 2 -> 256-row tiles over CTA pairs (cta_group::2; fewest operand

@@ -105,9 +105,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   return d;
 }
 
-constexpr int kMaxProblems = 24;
+constexpr int kMaxProblems = MTRL_GEMM_MAX_PROBLEMS;
 constexpr int kMapsPer = 6;
-constexpr int kMaxPhases = 8;
+constexpr int kMaxPhases = MTRL_GEMM_MAX_PHASES;
 
 // Passed by value as a __grid_constant__ kernel parameter (the usual home of TMA descriptors).
 struct GemmParams {

@@ -316,7 +316,7 @@ extern "C" int mtrl_ppo_update(mtrl_ppo_t* h, const float* obs, const float* log
     sac::LnBwdArgs ja;
     memset(&ja, 0, sizeof(ja));
     sac::ColsumJobs jobs;
-    jobs.njobs = 0;
+    memset(&jobs, 0, sizeof(jobs));
     for (int n = 0; n < 2; ++n) {
       sac::LnBwdPass& p = ja.p[n];
       p.dN = w.GN[n];
@@ -349,6 +349,7 @@ extern "C" int mtrl_ppo_update(mtrl_ppo_t* h, const float* obs, const float* log
   }
   for (int l = D - 1, i = 0; l >= 0 && !h->ln_mode; --l, ++i) {
     sac::ColsumJobs jobs;
+    memset(&jobs, 0, sizeof(jobs));
     jobs.njobs = 2;
     jobs.part[0] = cpart(0); jobs.dst[0] = tb(h->buf.policy_grads, LP, 0, l);
     jobs.part[1] = cpart(1); jobs.dst[1] = tb(h->buf.vf_grads, LV, 0, l);

@@ -118,7 +118,9 @@ long long carve(const mtrl_sac_config_t& c, int Ka, int Kc, long long actor_tota
   w.logstd = f(M * A);
   w.dq = f(E * M);
   w.dout = f(M * 2 * A);
-  w.colsum_part = f(static_cast<long long>(kMaxE) * (M / 32) * W);  // per member: [M/32 row groups][W]
+  // bias-gradient column partials, one slot per (layer, member): [M/32 row groups][W] (a fused backward launch fills the
+  // slots of all layers before one finishing kernel sums them)
+  w.colsum_part = f(static_cast<long long>(c.depth) * kMaxE * (M / 32) * W);
   w.alpha_val = f(c.num_local_tasks);
   w.task_w = f(c.num_local_tasks);
   w.inrange = reinterpret_cast<unsigned*>(take(M * 4));
@@ -188,6 +190,11 @@ struct mtrl_sac {
   std::vector<mtrl_gemm_plan_t*> fwd_pi;       // [depth] critic (new params) on (pi(s), s)
   std::vector<mtrl_gemm_plan_t*> bwd_pi;       // [depth] dX only
   std::vector<mtrl_gemm_plan_t*> bwd_actor;    // [depth]
+  // Launch-bound widths: the layers of each list above as ONE phased launch (grid-wide barriers between dependent layers
+  // inside the persistent GEMM kernel, mtrl_gemm_problem_t::phase); null = layer by layer.
+  enum Fused { F_FWD = 0, F_FWD_TARGET, F_FWD_PI, F_BWD_CRITIC, F_BWD_PI, F_BWD_ACTOR, F_COUNT };
+  mtrl_gemm_plan_t* fused[F_COUNT] = {};
+  bool fuse_layers = false;
   int launches = 0;
   int batch = 0, global_batch = 0;
   // optional CUDA-event bracketing of every GEMM launch (bench.py's live roofline measurement)
@@ -231,8 +238,9 @@ struct mtrl_sac {
 
 namespace {
 
-float* colsum_part(const mtrl_sac* h, int e) {
-  return h->ws.colsum_part + static_cast<long long>(e) * (h->cfg.max_rows / 32) * h->cfg.width;
+// column partials of dZ_l of member e (bias gradient of layer l)
+float* colsum_part(const mtrl_sac* h, int e, int l) {
+  return h->ws.colsum_part + (static_cast<long long>(l) * kMaxE + e) * (h->cfg.max_rows / 32) * h->cfg.width;
 }
 
 // fp32x3: the tf32 remainder of a workspace operand buffer (nullptr in tf32 mode); works for interior pointers.
@@ -320,6 +328,27 @@ void push_dw(mtrl_sac* h, std::vector<mtrl_gemm_problem_t>& dst, const float* X,
   }
 }
 
+// One phased plan out of per-layer problem lists (launch order = phase order).  Too many problems for one launch (the
+// per-owner dW problems of a sharded trunk) leaves the slot empty and the caller runs layer by layer.
+int make_fused_plan(mtrl_sac* h, int slot, const std::vector<std::vector<mtrl_gemm_problem_t>>& layers) {
+  if (h->fused[slot]) {
+    mtrl_gemm_plan_destroy(h->fused[slot]);
+    h->fused[slot] = nullptr;
+  }
+  if (!h->fuse_layers) return MTRL_OK;
+  std::vector<mtrl_gemm_problem_t> all;
+  for (size_t i = 0; i < layers.size(); ++i)
+    for (mtrl_gemm_problem_t p : layers[i]) {
+      p.phase = static_cast<int>(i);
+      all.push_back(p);
+    }
+  if (static_cast<int>(all.size()) > MTRL_GEMM_MAX_PROBLEMS || static_cast<int>(layers.size()) > MTRL_GEMM_MAX_PHASES) return MTRL_OK;
+  std::vector<mtrl_gemm_plan_t*> out;
+  MTRL_PROPAGATE(make_plan(out, all));
+  h->fused[slot] = out[0];
+  return MTRL_OK;
+}
+
 int build_backward_plans(mtrl_sac* h) {
   const mtrl_sac_config_t& c = h->cfg;
   const mtrl_net_layout_t& LA = h->lay.actor;
@@ -348,6 +377,7 @@ int build_backward_plans(mtrl_sac* h) {
     p.epilogue = MTRL_EPI_STORE;
     return p;
   };
+  std::vector<std::vector<mtrl_gemm_problem_t>> all_c, all_pi, all_a;
   for (int l = D - 1; l >= 0; --l) {
     const int src = ln ? 0 : (D - 1 - l) & 1, dst = src ^ 1;
     std::vector<mtrl_gemm_problem_t> pc, ppi, pa;
@@ -357,7 +387,7 @@ int build_backward_plans(mtrl_sac* h) {
     }
     for (int e = 0; e < E; ++e) {
       if (l > 0) {
-        pc.push_back(dx_any(e, src, dst, csh, csh_lo, LC, l, ln ? nullptr : w.bits_C[e][l - 1], colsum_part(h, e)));
+        pc.push_back(dx_any(e, src, dst, csh, csh_lo, LC, l, ln ? nullptr : w.bits_C[e][l - 1], colsum_part(h, e, l - 1)));
         ppi.push_back(dx_any(e, src, dst, csh, csh_lo, LC, l, ln ? nullptr : w.bits_C[e][l - 1], nullptr));
       } else {
         // actor step: only dL/da = first action_dim input columns of dZ_0 W_0^T (N = 16 rows of W_0)
@@ -377,11 +407,17 @@ int build_backward_plans(mtrl_sac* h) {
     }
     push_dw(h, pa, l == 0 ? w.Xa : dense_in(h, CH_AO, 0, l), l == 0 ? Ka : W, l == 0 ? LA.in_dim : W, w.G[0][src], h->buf.actor_grads,
             h->off_actor_grads, LA, 0, l);
-    if (l > 0) pa.push_back(dx_any(0, src, dst, ash, ash_lo, LA, l, ln ? nullptr : w.bits_Ao[l - 1], colsum_part(h, 0)));
+    if (l > 0) pa.push_back(dx_any(0, src, dst, ash, ash_lo, LA, l, ln ? nullptr : w.bits_Ao[l - 1], colsum_part(h, 0, l - 1)));
     MTRL_PROPAGATE(make_plan(h->bwd_critic, pc));
     MTRL_PROPAGATE(make_plan(h->bwd_pi, ppi));
     MTRL_PROPAGATE(make_plan(h->bwd_actor, pa));
+    all_c.push_back(pc);
+    all_pi.push_back(ppi);
+    all_a.push_back(pa);
   }
+  MTRL_PROPAGATE(make_fused_plan(h, mtrl_sac::F_BWD_CRITIC, all_c));
+  MTRL_PROPAGATE(make_fused_plan(h, mtrl_sac::F_BWD_PI, all_pi));
+  MTRL_PROPAGATE(make_fused_plan(h, mtrl_sac::F_BWD_ACTOR, all_a));
   return MTRL_OK;
 }
 
@@ -405,6 +441,7 @@ int build_plans(mtrl_sac* h) {
     return fwd_problem(X, l == 0 ? K0 : W, l == 0 ? in_dim : W, tk(sh, L, e, l), tb(params, L, e, l), out, M, W, h->ln_mode ? nullptr : bits,
                        lo(h, X), tk_lo(sh_lo, L, e, l), lo(h, out));
   };
+  std::vector<std::vector<mtrl_gemm_problem_t>> all_f, all_t, all_pi;
   for (int l = 0; l < D; ++l) {
     std::vector<mtrl_gemm_problem_t> p;
     p.push_back(fwd(CH_AN, w.Xa_next, Ka, LA.in_dim, ash, w.ash_lo, h->buf.actor_params, LA, 0, l, nullptr));
@@ -412,6 +449,7 @@ int build_plans(mtrl_sac* h) {
     for (int e = 0; e < E; ++e)
       p.push_back(fwd(CH_C, w.Xc, Kc, LC.in_dim, csh, w.csh_lo, h->buf.critic_params, LC, e, l, l + 1 < D ? w.bits_C[e][l] : nullptr));
     MTRL_PROPAGATE(make_plan(h->fwd, p));
+    all_f.push_back(p);
   }
   for (int l = 0; l < D; ++l) {
     std::vector<mtrl_gemm_problem_t> p, q;
@@ -421,7 +459,12 @@ int build_plans(mtrl_sac* h) {
     }
     MTRL_PROPAGATE(make_plan(h->fwd_target, p));
     MTRL_PROPAGATE(make_plan(h->fwd_pi, q));
+    all_t.push_back(p);
+    all_pi.push_back(q);
   }
+  MTRL_PROPAGATE(make_fused_plan(h, mtrl_sac::F_FWD, all_f));
+  MTRL_PROPAGATE(make_fused_plan(h, mtrl_sac::F_FWD_TARGET, all_t));
+  MTRL_PROPAGATE(make_fused_plan(h, mtrl_sac::F_FWD_PI, all_pi));
   return build_backward_plans(h);
 }
 
@@ -602,7 +645,7 @@ int run_trunk_backward_ln(mtrl_sac* h, std::vector<mtrl_gemm_plan_t*>& plans, fl
       p.rowc = w.rowc[e];
       p.dZ = w.G[e][0];
       p.dX = (skip && l >= 1) ? w.GS[e][j & 1] : nullptr;
-      p.part_db = want_wgrad ? colsum_part(h, e) : nullptr;
+      p.part_db = want_wgrad ? colsum_part(h, e, l) : nullptr;
       p.part_dg = (want_wgrad && ln) ? w.part_dg[e] : nullptr;
       p.part_dbeta = (want_wgrad && ln) ? w.part_dbeta[e] : nullptr;
     }
@@ -616,9 +659,9 @@ int run_trunk_backward_ln(mtrl_sac* h, std::vector<mtrl_gemm_plan_t*>& plans, fl
     LAUNCHED(h);
     if (want_wgrad) {
       ColsumJobs jobs;
-      jobs.njobs = 0;
+      memset(&jobs, 0, sizeof(jobs));
       for (int e = 0; e < E; ++e) {
-        jobs.part[jobs.njobs] = colsum_part(h, e);
+        jobs.part[jobs.njobs] = colsum_part(h, e, l);
         jobs.dst[jobs.njobs++] = tb(grads, L, e, l);
         if (ln) {
           jobs.part[jobs.njobs] = w.part_dg[e];
@@ -636,34 +679,51 @@ int run_trunk_backward_ln(mtrl_sac* h, std::vector<mtrl_gemm_plan_t*>& plans, fl
 
 // Trunk backward of one network: per layer, finish the bias gradient from the partial column sums its dZ producer
 // left behind (head VJP: per 128-row tile; previous layer's dX GEMM epilogue: per 32 rows), then the dW / dX plan.
-int run_trunk_backward(mtrl_sac* h, std::vector<mtrl_gemm_plan_t*>& plans, float* grads, const mtrl_net_layout_t& L, int E,
-                       bool want_wgrad, cudaStream_t st) {
+int run_trunk_backward(mtrl_sac* h, std::vector<mtrl_gemm_plan_t*>& plans, mtrl_gemm_plan_t* fused, float* grads,
+                       const mtrl_net_layout_t& L, int E, bool want_wgrad, cudaStream_t st) {
   const int D = h->cfg.depth;
   if (h->ln_mode) {
     const bool actor = grads == h->buf.actor_grads;
     return run_trunk_backward_ln(h, plans, grads, actor ? h->buf.actor_params : h->buf.critic_params, L, actor ? CH_AO : CH_C, E,
                                  want_wgrad, st);
   }
-  for (int l = D - 1, i = 0; l >= 0; --l, ++i) {
-    const int src = (D - 1 - l) & 1;
-    (void)src;
+  const bool tg = h->tg_active && (grads == h->buf.critic_grads ? h->tg_active->fill_critic : h->tg_active->fill_actor);
+  if (fused && !tg) {
+    // every layer's dW / dX in ONE phased launch, then the bias gradients of all layers in one finishing kernel
+    // (per-task gradients read each layer's dZ before the next layer overwrites it: layer by layer below)
+    MTRL_PROPAGATE(run_plan(h, fused, st));
     if (want_wgrad) {
       ColsumJobs jobs;
+      memset(&jobs, 0, sizeof(jobs));
+      for (int l = D - 1; l >= 0; --l)
+        for (int e = 0; e < E; ++e) {
+          jobs.part[jobs.njobs] = colsum_part(h, e, l);
+          jobs.dst[jobs.njobs] = tb(grads, L, e, l);
+          jobs.groups[jobs.njobs++] = l == D - 1 ? h->cfg.max_rows / kTileRows : h->cfg.max_rows / 32;
+        }
+      MTRL_PROPAGATE(launch_colsum(h, jobs, 1, st));
+    }
+    return MTRL_OK;
+  }
+  for (int l = D - 1, i = 0; l >= 0; --l, ++i) {
+    if (want_wgrad) {
+      ColsumJobs jobs;
+      memset(&jobs, 0, sizeof(jobs));
       jobs.njobs = E;
       for (int e = 0; e < E; ++e) {
-        jobs.part[e] = colsum_part(h, e);
+        jobs.part[e] = colsum_part(h, e, l);
         jobs.dst[e] = tb(grads, L, e, l);
       }
       const int groups = l == D - 1 ? h->cfg.max_rows / kTileRows : h->cfg.max_rows / 32;
       MTRL_PROPAGATE(launch_colsum(h, jobs, groups, st));
-      if (h->tg_active && (grads == h->buf.critic_grads ? h->tg_active->fill_critic : h->tg_active->fill_actor)) {
+      if (tg) {
         // row t of the (T, P) matrix: bias slice from the task's partial column sums, kernel slice from the per-task
         // dW GEMMs (dZ of this layer is still in place; the plan below consumes it)
         const bool critic = grads == h->buf.critic_grads;
-        float* tg = critic ? h->tg_active->critic_tg : h->tg_active->actor_tg;
+        float* tgm = critic ? h->tg_active->critic_tg : h->tg_active->actor_tg;
         const int R = h->tg_active->rows_per_task;
         dim3 g((h->cfg.width + 255) / 256, h->cfg.num_local_tasks, E);
-        task_bias_kernel<<<g, 256, 0, st>>>(jobs, tg, L.total, L.member_trunk_stride, L.bias_off[l],
+        task_bias_kernel<<<g, 256, 0, st>>>(jobs, tgm, L.total, L.member_trunk_stride, L.bias_off[l],
                                             l == D - 1 ? R / kTileRows : R / 32, h->cfg.width);
         MTRL_CUDA_CHECK(cudaGetLastError());
         LAUNCHED(h);
@@ -737,6 +797,11 @@ extern "C" int mtrl_sac_create(mtrl_sac_t** out, const mtrl_sac_config_t* cfg, c
   h->cfg = *cfg;
   h->buf = *b;
   h->ln_mode = cfg->use_layer_norm || cfg->use_skip_connections;
+  {
+    // MTRL_FUSE_LAYERS=0|1 overrides; default: where the update is launch-latency bound
+    const char* env = getenv("MTRL_FUSE_LAYERS");
+    h->fuse_layers = !h->ln_mode && cfg->depth > 1 && (env ? env[0] == '1' : cfg->width <= 1024);
+  }
   int rc = mtrl_sac_query_layout(cfg, &h->lay);
   if (rc != MTRL_OK) { delete h; return rc; }
   const void* need[] = {b->actor_params, b->actor_grads, b->actor_m, b->actor_v, b->actor_shadow, b->critic_params,
@@ -776,6 +841,8 @@ extern "C" void mtrl_sac_destroy(mtrl_sac_t* h) {
   if (!h) return;
   for (auto* v : {&h->fwd, &h->fwd_target, &h->bwd_critic, &h->fwd_pi, &h->bwd_pi, &h->bwd_actor})
     for (auto* p : *v) mtrl_gemm_plan_destroy(p);
+  for (auto* p : h->fused)
+    if (p) mtrl_gemm_plan_destroy(p);
   for (auto& kv : h->act_plans)
     for (auto* p : kv.second) mtrl_gemm_plan_destroy(p);
   for (auto& kv : h->mlp_plans)
@@ -858,7 +925,8 @@ int step_begin(mtrl_sac* h, const float* obs, const float* actions, const float*
   LAUNCHED(h);
   MTRL_CUDA_CHECK(cudaGetLastError());
   MTRL_PROPAGATE(prof_end(h, st));
-  for (int l = 0; l < D; ++l) {
+  if (h->fused[mtrl_sac::F_FWD]) MTRL_PROPAGATE(run_plan(h, h->fused[mtrl_sac::F_FWD], st));
+  for (int l = 0; l < D && !h->fused[mtrl_sac::F_FWD]; ++l) {
     MTRL_PROPAGATE(run_plan(h, h->fwd[l], st));
     if (h->ln_mode) {
       ChainRef ch[2 + kMaxE] = {{CH_AN, 0, h->buf.actor_params, &h->lay.actor}, {CH_AO, 0, h->buf.actor_params, &h->lay.actor}};
@@ -877,7 +945,8 @@ int step_critic_grads(mtrl_sac* h, cudaStream_t st) {
   const mtrl_net_layout_t& LC = h->lay.critic;
   const int M = c.max_rows, W = c.width, D = c.depth, E = c.num_critics;
   MTRL_PROPAGATE(launch_actor_head(h, head_in(h, h->split_critic ? CH_AO : CH_AN, 0), w.eps_c, w.Xc_next, w.logp_next, false, st));
-  for (int l = 0; l < D; ++l) {
+  if (h->fused[mtrl_sac::F_FWD_TARGET]) MTRL_PROPAGATE(run_plan(h, h->fused[mtrl_sac::F_FWD_TARGET], st));
+  for (int l = 0; l < D && !h->fused[mtrl_sac::F_FWD_TARGET]; ++l) {
     MTRL_PROPAGATE(run_plan(h, h->fwd_target[l], st));
     if (h->ln_mode) {
       ChainRef ch[kMaxE];
@@ -922,7 +991,7 @@ int step_critic_grads(mtrl_sac* h, cudaStream_t st) {
       a.dZ[e] = h->ln_mode ? w.GN[e] : w.G[e][0];
       a.dWh[e] = hk(h->buf.critic_grads, LC, e);
       a.dbh[e] = hb(h->buf.critic_grads, LC, e);
-      a.colsum[e] = h->ln_mode ? nullptr : colsum_part(h, e);
+      a.colsum[e] = h->ln_mode ? nullptr : colsum_part(h, e, D - 1);
     }
     a.seg_start = w.seg_start; a.M = M; a.W = W; a.dz_lo_delta = w.lo_delta; a.no_mask = h->ln_mode;
     MTRL_PROPAGATE(launch_head_bwd(h, a, 1, E, st));
@@ -936,7 +1005,7 @@ int step_critic_grads(mtrl_sac* h, cudaStream_t st) {
     MTRL_PROPAGATE(prof_end(h, st));
     LAUNCHED(h);
   }
-  MTRL_PROPAGATE(run_trunk_backward(h, h->bwd_critic, h->buf.critic_grads, LC, E, true, st));
+  MTRL_PROPAGATE(run_trunk_backward(h, h->bwd_critic, h->fused[mtrl_sac::F_BWD_CRITIC], h->buf.critic_grads, LC, E, true, st));
   MTRL_PROPAGATE(head_sumsq_to_slot(h, h->buf.critic_grads, LC, ACC_CRITIC_HEAD_G2, st));
   return MTRL_OK;
 }
@@ -1020,7 +1089,8 @@ int step_actor_grads(mtrl_sac* h, cudaStream_t st) {
   // dL/da accumulates over K splits (see build_plans)
   MTRL_CUDA_CHECK(cudaMemsetAsync(w.dXin, 0, static_cast<size_t>(E) * M * 16 * sizeof(float), st));
   h->launches += 1;
-  for (int l = 0; l < D; ++l) {
+  if (h->fused[mtrl_sac::F_FWD_PI]) MTRL_PROPAGATE(run_plan(h, h->fused[mtrl_sac::F_FWD_PI], st));
+  for (int l = 0; l < D && !h->fused[mtrl_sac::F_FWD_PI]; ++l) {
     MTRL_PROPAGATE(run_plan(h, h->fwd_pi[l], st));
     if (h->ln_mode) {
       ChainRef ch[kMaxE];
@@ -1056,7 +1126,7 @@ int step_actor_grads(mtrl_sac* h, cudaStream_t st) {
     a.seg_start = w.seg_start; a.M = M; a.W = W; a.dz_lo_delta = w.lo_delta; a.no_mask = h->ln_mode;
     MTRL_PROPAGATE(launch_head_bwd(h, a, 1, E, st));
   }
-  MTRL_PROPAGATE(run_trunk_backward(h, h->bwd_pi, nullptr, LC, E, false, st));
+  MTRL_PROPAGATE(run_trunk_backward(h, h->bwd_pi, h->fused[mtrl_sac::F_BWD_PI], nullptr, LC, E, false, st));
   {
     ActorDoutArgs a;
     a.dXin = w.dXin; a.act = w.act; a.logstd = w.logstd; a.eps = w.eps_a; a.alpha_val = w.alpha_val; a.task_w = w.task_w;
@@ -1076,11 +1146,11 @@ int step_actor_grads(mtrl_sac* h, cudaStream_t st) {
     a.dZ[0] = h->ln_mode ? w.GN[0] : w.G[0][0];
     a.dWh[0] = hk(h->buf.actor_grads, LA, 0);
     a.dbh[0] = hb(h->buf.actor_grads, LA, 0);
-    a.colsum[0] = h->ln_mode ? nullptr : colsum_part(h, 0);
+    a.colsum[0] = h->ln_mode ? nullptr : colsum_part(h, 0, D - 1);
     a.seg_start = w.seg_start; a.M = M; a.W = W; a.dz_lo_delta = w.lo_delta; a.no_mask = h->ln_mode;
     MTRL_PROPAGATE(launch_head_bwd(h, a, 2 * c.action_dim, 1, st));
   }
-  MTRL_PROPAGATE(run_trunk_backward(h, h->bwd_actor, h->buf.actor_grads, LA, 1, true, st));
+  MTRL_PROPAGATE(run_trunk_backward(h, h->bwd_actor, h->fused[mtrl_sac::F_BWD_ACTOR], h->buf.actor_grads, LA, 1, true, st));
   MTRL_PROPAGATE(head_sumsq_to_slot(h, h->buf.actor_grads, LA, ACC_ACTOR_HEAD_G2, st));
   return MTRL_OK;
 }

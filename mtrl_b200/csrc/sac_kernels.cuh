@@ -1014,10 +1014,12 @@ static __global__ void __launch_bounds__(RG * 32, ((RG == 8 && HD <= 8) || HD <=
 // emit (head_bwd_kernel: one row of partials per 128-row tile; the dX GEMM epilogue: one per 32 rows).
 // Fixed summation order, no float atomics.
 // ---------------------------------------------------------------------------------------------
-constexpr int kMaxColsumJobs = 3 * kMaxE;   // bias, LayerNorm scale and LayerNorm bias gradients of every member
+constexpr int kMaxColsumJobs = 4 * kMaxE;   // bias gradients of every member and layer of a fused backward launch, or bias /
+                                            // LayerNorm scale / LayerNorm bias gradients of every member of one layer
 struct ColsumJobs {
   const float* part[kMaxColsumJobs];   // [groups][W]
   float* dst[kMaxColsumJobs];
+  int groups[kMaxColsumJobs];          // 0: the launch's common group count
   int njobs;
 };
 
@@ -1029,6 +1031,7 @@ static __global__ void colsum_final_kernel(const ColsumJobs jobs, int groups, in
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int k = blockIdx.x * 32 + tx;
   const float* p = jobs.part[job];
+  if (jobs.groups[job] > 0) groups = jobs.groups[job];
   float a = 0.f;
   if (k < W)
     for (int g = ty; g < groups; g += 8) a += p[static_cast<long long>(g) * W + k];

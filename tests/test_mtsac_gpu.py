@@ -282,6 +282,34 @@ def test_three_consecutive_updates(cuda):
     run_case(cfg, per_task=32, steps=3, check_grads=False)
 
 
+@pytest.mark.parametrize("precision", ["tf32", "fp32x3"])
+def test_fused_layer_launches_equal_layerwise(cuda, monkeypatch, precision):
+    """Width <= 1024 runs the layers of each trunk pass as ONE phased GEMM launch (mtrl_gemm_problem_t::phase); same update
+    as one launch per layer: fewer kernels, identical forward values (logs), parameters equal up to the split-K atomic
+    order of the dW reductions."""
+    cfg = O.OracleConfig(num_tasks=10, obs_dim=49, action_dim=4, width=400)
+    agents = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("MTRL_FUSE_LAYERS", mode)
+        st = O.init_state(cfg, seed=3, dtype=torch.float32)
+        agents[mode] = SU.make_agent(cfg, 64, seed=3, precision=precision)
+        SU.load_oracle_state(agents[mode], st)
+    logs = {}
+    for step in range(3):
+        batch, ec, ea = O.synthetic_batch(cfg, 64, seed=200 + step, dtype=torch.float32)
+        for mode, agent in agents.items():
+            _, logs[mode] = agent.update(tuple(b.cuda() for b in batch), eps_c=ec.cuda(), eps_a=ea.cuda(), check=True)
+        for k in O.LOG_KEYS:
+            a, b = float(logs["0"][k]), float(logs["1"][k])
+            assert abs(a - b) <= 2e-5 * max(abs(a), 1e-6) * (1 + step), (step, k, a, b)
+    # 3 layers x 6 passes -> 6 launches, and the 6 bias-gradient finishing kernels -> 2
+    assert agents["0"].launches_per_update() - agents["1"].launches_per_update() == 12 + 4
+    for name in ("actor", "critic"):
+        p0 = torch.cat([x.flatten() for x in O.tree_leaves(getattr(agents["0"], name).params)])
+        p1 = torch.cat([x.flatten() for x in O.tree_leaves(getattr(agents["1"], name).params)])
+        assert float((p0 - p1).norm() / p0.norm()) < 1e-5
+
+
 def test_mt50_w2048_full_size_vs_oracle_on_gpu(cuda):
     """BASELINE headline config (MT50, width 2048, B = 6400): the oracle itself is run in fp64 with
     torch on the same GPU (it is device agnostic); the fused path must match it to the north-star
