@@ -688,25 +688,28 @@ int run_trunk_backward(mtrl_sac* h, std::vector<mtrl_gemm_plan_t*>& plans, mtrl_
                                  want_wgrad, st);
   }
   const bool tg = h->tg_active && (grads == h->buf.critic_grads ? h->tg_active->fill_critic : h->tg_active->fill_actor);
-  if (fused && !tg) {
-    // every layer's dW / dX in ONE phased launch, then the bias gradients of all layers in one finishing kernel
-    // (per-task gradients read each layer's dZ before the next layer overwrites it: layer by layer below)
+  // bias gradients of all layers in one finishing kernel once every layer's column partials are in their slots
+  auto finish_biases = [&]() {
+    ColsumJobs jobs;
+    memset(&jobs, 0, sizeof(jobs));
+    for (int l = D - 1; l >= 0; --l)
+      for (int e = 0; e < E; ++e) {
+        jobs.part[jobs.njobs] = colsum_part(h, e, l);
+        jobs.dst[jobs.njobs] = tb(grads, L, e, l);
+        jobs.groups[jobs.njobs++] = l == D - 1 ? h->cfg.max_rows / kTileRows : h->cfg.max_rows / 32;
+      }
+    return launch_colsum(h, jobs, 1, st);
+  };
+  const bool one_finisher = D * E <= kMaxColsumJobs;
+  if (fused && !tg && (!want_wgrad || one_finisher)) {
+    // every layer's dW / dX in ONE phased launch (per-task gradients read each layer's dZ before the next layer
+    // overwrites it: layer by layer below)
     MTRL_PROPAGATE(run_plan(h, fused, st));
-    if (want_wgrad) {
-      ColsumJobs jobs;
-      memset(&jobs, 0, sizeof(jobs));
-      for (int l = D - 1; l >= 0; --l)
-        for (int e = 0; e < E; ++e) {
-          jobs.part[jobs.njobs] = colsum_part(h, e, l);
-          jobs.dst[jobs.njobs] = tb(grads, L, e, l);
-          jobs.groups[jobs.njobs++] = l == D - 1 ? h->cfg.max_rows / kTileRows : h->cfg.max_rows / 32;
-        }
-      MTRL_PROPAGATE(launch_colsum(h, jobs, 1, st));
-    }
+    if (want_wgrad) MTRL_PROPAGATE(finish_biases());
     return MTRL_OK;
   }
   for (int l = D - 1, i = 0; l >= 0; --l, ++i) {
-    if (want_wgrad) {
+    if (want_wgrad && (tg || !one_finisher)) {
       ColsumJobs jobs;
       memset(&jobs, 0, sizeof(jobs));
       jobs.njobs = E;
@@ -732,6 +735,7 @@ int run_trunk_backward(mtrl_sac* h, std::vector<mtrl_gemm_plan_t*>& plans, mtrl_
     }
     MTRL_PROPAGATE(run_plan(h, plans[i], st));
   }
+  if (want_wgrad && !tg && one_finisher) MTRL_PROPAGATE(finish_biases());
   return MTRL_OK;
 }
 
@@ -798,9 +802,12 @@ extern "C" int mtrl_sac_create(mtrl_sac_t** out, const mtrl_sac_config_t* cfg, c
   h->buf = *b;
   h->ln_mode = cfg->use_layer_norm || cfg->use_skip_connections;
   {
-    // MTRL_FUSE_LAYERS=0|1 overrides; default: where the update is launch-latency bound
+    // MTRL_FUSE_LAYERS=1: the layers of every trunk pass as one phased launch.  Off by default: with graph replay and
+    // programmatic dependent launch the kernel boundaries it removes are already hidden, and the in-kernel grid barrier
+    // costs as much (same-box A/B, fused vs layer by layer: MT10/W400 0.322 vs 0.319 ms, 1/8 shard of MT50/W2048 0.978 vs
+    // 0.977, MT50/W2048 unchanged) -- kept as a switch for launch-bound hosts without graph replay.
     const char* env = getenv("MTRL_FUSE_LAYERS");
-    h->fuse_layers = !h->ln_mode && cfg->depth > 1 && (env ? env[0] == '1' : cfg->width <= 1024);
+    h->fuse_layers = !h->ln_mode && cfg->depth > 1 && env && env[0] == '1';
   }
   int rc = mtrl_sac_query_layout(cfg, &h->lay);
   if (rc != MTRL_OK) { delete h; return rc; }
