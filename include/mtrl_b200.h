@@ -74,6 +74,17 @@ typedef struct mtrl_gemm_problem {
   const float* A_lo;
   const float* B_lo;
   float* D_lo;
+  /* Fused output head (MTRL_EPI_BIAS_RELU only; all four set, or head_w NULL): the own-task head of a multi-head network
+   * (nn.vmap(Dense) heads, mtrl/nn/multi_head.py:50-66) evaluated on the tile while it is still in registers, so the
+   * last trunk activation is not read back for it:
+   *   head_out[m][j] += sum_n D[m][n] * head_w[task(m)][n][j],   task(m) = head_tile_task[m / 128]
+   * (float atomics, one per row, output and column slice of the tile; the caller zeroes head_out and adds the head bias).
+   * D is the value the epilogue stores (tf32-rounded; the unrounded hi + lo value with D_lo).  head_w is the Flax head
+   * kernel (tasks, N, head_dim) row-major; head_dim in {1, 2, 4, 8}. */
+  const float* head_w;
+  float* head_out;
+  const int* head_tile_task;
+  int head_dim;
 } mtrl_gemm_problem_t;
 
 typedef struct mtrl_gemm_plan mtrl_gemm_plan_t;

@@ -28,13 +28,14 @@ class GemmProblem(C.Structure):
         ("mask_bits", C.c_void_p), ("relu_bits_out", C.c_void_p), ("ldbits", C.c_longlong), ("colsum_partial", C.c_void_p),
         ("schedule_first", C.c_int), ("phase", C.c_int),
         ("A_lo", C.c_void_p), ("B_lo", C.c_void_p), ("D_lo", C.c_void_p),
+        ("head_w", C.c_void_p), ("head_out", C.c_void_p), ("head_tile_task", C.c_void_p), ("head_dim", C.c_int),
     ]
 
 
 EPI_STORE, EPI_BIAS_RELU, EPI_RELU_MASK, EPI_ATOMIC_ADD, EPI_STORE_TF32 = range(5)
 
 
-ABI_VERSION = 5   # mtrl_abi_version() of the library these ctypes structures were written for
+ABI_VERSION = 6   # mtrl_abi_version() of the library these ctypes structures were written for
 
 
 def lib() -> C.CDLL:

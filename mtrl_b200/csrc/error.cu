@@ -14,4 +14,4 @@ void mtrl_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* mtrl_last_error(void) { return g_err; }
-extern "C" int mtrl_abi_version(void) { return 5; }
+extern "C" int mtrl_abi_version(void) { return 6; }

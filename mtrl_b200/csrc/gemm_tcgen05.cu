@@ -30,6 +30,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -55,6 +56,8 @@ constexpr int kThreads = 64 + 32 * kEpilogueWarps;
 constexpr int kEpiBoxBytes = 32 * 32 * 4;
 constexpr int kEpiStageBytes = kEpilogueWarps * 2 * kEpiBoxBytes;   // 64 KB
 constexpr int kEpiBiasBytes = kEpilogueWarps * 512;                 // 4 KB
+constexpr int kMaxHeadDim = 8;
+constexpr int kEpiHeadBytes = kEpilogueWarps * 32 * kMaxHeadDim * 4;   // 8 KB: one box's (32 columns x head_dim) head weights per warp
 
 template <int kCtas>
 struct Cfg {
@@ -62,7 +65,7 @@ struct Cfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = kCtas == 1 ? 3 : 4;
   static constexpr int kSmemBytes =
-      kStages * kStageBytes + kEpiStageBytes + kEpiBiasBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+      kStages * kStageBytes + kEpiStageBytes + kEpiBiasBytes + kEpiHeadBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct __align__(16) DevProblem {
@@ -88,7 +91,10 @@ struct __align__(16) DevProblem {
   int tma_out;   // output goes through smem staging + TMA store / reduce-add (needs block_n % 32 == 0)
   int x3;        // fp32x3: > 0 = k-blocks per chunk (maps 3 / 4 = A_lo / B_lo); every chunk is a MAIN and a SMALL sub-unit
   int d_lo;      // the epilogue also stores the tf32 remainder of the unrounded output through map 5
-  int pad2;
+  int head_dim;  // fused output head (bias+ReLU epilogue): 0 = none
+  const float* head_w;      // (tasks, N, head_dim)
+  float* head_out;          // [M][head_dim], accumulated with atomics
+  const int* head_tile;     // task of every 128-row tile
 };
 
 // smem matrix descriptor (cute::UMMA::SmemDescriptor layout): start>>4 [0,14), LBO>>4 [16,30),
@@ -185,7 +191,7 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t epi_base = smem_base + kStages * C::kStageBytes;   // 1024-aligned staging boxes, then bias
-  const uint32_t bar_base = epi_base + kEpiStageBytes + kEpiBiasBytes;
+  const uint32_t bar_base = epi_base + kEpiStageBytes + kEpiBiasBytes + kEpiHeadBytes;
   // barrier layout (8 bytes each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
@@ -404,6 +410,7 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
     const int col_half = ew >> 2;
     const uint32_t stg0 = epi_base + static_cast<uint32_t>(ew) * 2u * kEpiBoxBytes;
     const uint32_t sbias = epi_base + kEpiStageBytes + static_cast<uint32_t>(ew) * 512u;
+    const uint32_t shead = epi_base + kEpiStageBytes + kEpiBiasBytes + static_cast<uint32_t>(ew) * (32u * kMaxHeadDim * 4u);
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t nbox = 0;  // running count of TMA boxes this warp has issued (selects the staging buffer)
@@ -427,6 +434,25 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
       const int cbeg = col_half ? c0 * 16 : 0;
       const int cend = col_half ? P.block_n : c0 * 16;
       const int epi = P.epilogue;
+      // fused output head: the (32 columns x hd) weights of a box are fetched one box ahead (the first box's before the wait
+      // for the accumulator), so their latency never sits between two TMEM loads
+      const int hd = row0 < P.M ? P.head_dim : 0;   // (a pair's second half may lie past the last row tile)
+      const float* head_wt = nullptr;
+      float4 hw_next[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+      auto head_fetch = [&](int cc) {
+        const int col0 = n0 + cc;
+        const int nval = (cc < cend ? min(32, P.N - col0) : 0) * hd;   // valid floats (columns past N contribute nothing)
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int q = lane + 32 * u;
+          hw_next[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (q < 8 * hd && 4 * q < nval) hw_next[u] = __ldg(reinterpret_cast<const float4*>(head_wt + static_cast<long long>(col0) * hd) + q);
+        }
+      };
+      if (hd) {
+        head_wt = P.head_w + static_cast<long long>(__ldg(P.head_tile + (row0 >> 7))) * P.N * hd;
+        head_fetch(cbeg);
+      }
       // fp32x3: all sub-units but the last are added (fp32, round to nearest) into the running sum this warp keeps for
       // its lanes x columns in the third TMEM region, columns [128, 256) (block_n <= 128 in that mode)
       const int nsub = num_subunits(P, c);
@@ -484,6 +510,10 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
           if (cbeg + 32 * b < cend && col < P.N) mbits[b] = __ldg(P.mask_bits + static_cast<long long>(row) * P.ldbits + (col >> 5));
         }
       }
+      // fused output head: this thread's row x this warp's columns, summed over the boxes of the tile
+      float hs[kMaxHeadDim];
+#pragma unroll
+      for (int j = 0; j < kMaxHeadDim; ++j) hs[j] = 0.f;
       int bi = 0;
       for (int cc = cbeg; cc < cend; cc += 32, ++bi) {
         const int ncols = min(32, cend - cc);
@@ -529,6 +559,39 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) bits |= (o[i] > 0.f ? 1u : 0u) << i;
             if (row_ok && col0 < P.N) P.bits_out[static_cast<long long>(row) * P.ldbits + (col0 >> 5)] = bits;
+          }
+          if (hd) {
+            // the box's 32 x hd head weights: staged by the warp (coalesced), read back as broadcast float4s
+            __syncwarp();   // the previous box's reads are done
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int q = lane + 32 * u;
+              if (q < 8 * hd)
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(shead + 16u * q), "f"(hw_next[u].x), "f"(hw_next[u].y),
+                             "f"(hw_next[u].z), "f"(hw_next[u].w)
+                             : "memory");
+            }
+            __syncwarp();
+            head_fetch(cc + 32);
+            auto head_box = [&](auto hdc) {
+              constexpr int HD = decltype(hdc)::value;
+#pragma unroll
+              for (int q = 0; q < 8 * HD; ++q) {
+                float4 w4;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w4.x), "=f"(w4.y), "=f"(w4.z), "=f"(w4.w)
+                             : "r"(shead + 16u * q));
+                const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                  const int idx = 4 * q + r;   // flat (column, output) index of the box
+                  hs[idx % HD] = fmaf(o[idx / HD], wv[r], hs[idx % HD]);
+                }
+              }
+            };
+            if (hd == 1) head_box(std::integral_constant<int, 1>());
+            else if (hd == 2) head_box(std::integral_constant<int, 2>());
+            else if (hd == 4) head_box(std::integral_constant<int, 4>());
+            else head_box(std::integral_constant<int, 8>());
           }
         } else if (epi == MTRL_EPI_RELU_MASK) {
           if (P.mask_bits) {
@@ -640,6 +703,11 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
       __syncwarp();
       if (lane == 0) {
         if (kCtas == 2) mbar_arrive_cluster(tempty_bar(acc), 0); else mbar_arrive(tempty_bar(acc));
+      }
+      if (hd && row_ok && cbeg < cend) {
+#pragma unroll
+        for (int j = 0; j < kMaxHeadDim; ++j)
+          if (j < hd) atomicAdd(P.head_out + static_cast<long long>(row) * hd + j, hs[j]);
       }
       if (params.dbg) t_work += clock64() - t1;
       if (++acc == 2) {
@@ -861,6 +929,22 @@ extern "C" int mtrl_gemm_plan_create_ex(mtrl_gemm_plan_t** out, const mtrl_gemm_
     if (allow_tma_out && block_n % 32 == 0 &&
         encode_map(&P.maps[kMapsPer * i + 2], p.D, p.N, p.M, p.ldd, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B) == MTRL_OK)
       d.tma_out = 1;
+    d.head_dim = 0;
+    d.head_w = nullptr;
+    d.head_out = nullptr;
+    d.head_tile = nullptr;
+    if (p.head_w) {
+      MTRL_REQUIRE(p.epilogue == MTRL_EPI_BIAS_RELU, "problem %d: the fused head needs the bias + ReLU epilogue", i);
+      MTRL_REQUIRE(p.head_out && p.head_tile_task, "problem %d: head_w without head_out / head_tile_task", i);
+      MTRL_REQUIRE(p.head_dim == 1 || p.head_dim == 2 || p.head_dim == 4 || p.head_dim == 8,
+                   "problem %d: fused head_dim %d not in {1, 2, 4, 8}", i, p.head_dim);
+      MTRL_REQUIRE(block_n % 32 == 0 && (reinterpret_cast<uintptr_t>(p.head_w) & 15u) == 0,
+                   "problem %d: the fused head needs block_n %% 32 == 0 and a 16-byte aligned head_w", i);
+      d.head_dim = p.head_dim;
+      d.head_w = p.head_w;
+      d.head_out = p.head_out;
+      d.head_tile = p.head_tile_task;
+    }
     d.d_lo = 0;
     if (p.D_lo) {
       MTRL_REQUIRE(p.epilogue == MTRL_EPI_BIAS_RELU || p.epilogue == MTRL_EPI_RELU_MASK || p.epilogue == MTRL_EPI_STORE_TF32,

@@ -29,6 +29,10 @@ struct Workspace {
   float* G[kMaxE][2];
   float* dXin;
   float *rew, *done, *eps_c, *eps_a, *logp_next, *logp, *act, *act_data, *logstd, *dq, *dout, *colsum_part, *alpha_val, *task_w;
+  // head outputs accumulated by the last trunk layer's GEMM epilogue (fused heads, without the head bias): actor on
+  // next_obs / obs [M][2A], critic members on (a, s) / target members on (a', s') / critic members on (pi(s), s) [M]
+  float *pre_an, *pre_ao, *pre_c[kMaxE], *pre_tg[kMaxE], *pre_pi[kMaxE];
+  long long pre_floats;   // the region [pre_an, pre_an + pre_floats) is zeroed at the start of every update
   unsigned* inrange;
   unsigned *bits_Ao[MTRL_MAX_DEPTH], *bits_C[kMaxE][MTRL_MAX_DEPTH];  // ReLU sign bits of Ao[l] / C[e][l], [M][W/32]
   int *row_slot, *slot_src, *tile_task, *seg_start, *status;
@@ -123,6 +127,17 @@ long long carve(const mtrl_sac_config_t& c, int Ka, int Kc, long long actor_tota
   w.colsum_part = f(static_cast<long long>(c.depth) * kMaxE * (M / 32) * W);
   w.alpha_val = f(c.num_local_tasks);
   w.task_w = f(c.num_local_tasks);
+  {
+    const long long o0 = off;
+    w.pre_an = f(M * 2 * A);
+    w.pre_ao = f(M * 2 * A);
+    for (int e = 0; e < E; ++e) {
+      w.pre_c[e] = f(M);
+      w.pre_tg[e] = f(M);
+      w.pre_pi[e] = f(M);
+    }
+    w.pre_floats = (off - o0) / 4;
+  }
   w.inrange = reinterpret_cast<unsigned*>(take(M * 4));
   const long long bit_words = M * ((W + 31) / 32);
   for (int l = 0; l + 1 < c.depth; ++l) {
@@ -195,6 +210,9 @@ struct mtrl_sac {
   enum Fused { F_FWD = 0, F_FWD_TARGET, F_FWD_PI, F_BWD_CRITIC, F_BWD_PI, F_BWD_ACTOR, F_COUNT };
   mtrl_gemm_plan_t* fused[F_COUNT] = {};
   bool fuse_layers = false;
+  // the output heads ride in the epilogue of the last trunk layer's GEMM (mtrl_gemm_problem_t::head_w): the loss / sampling
+  // kernels then read M x head_dim numbers instead of the M x W activation
+  bool fused_heads = false;
   int launches = 0;
   int batch = 0, global_batch = 0;
   // optional CUDA-event bracketing of every GEMM launch (bench.py's live roofline measurement)
@@ -435,27 +453,36 @@ int build_plans(mtrl_sac* h) {
   // mode).  With LayerNorm / skip the layer's input is the junction's output n_l and the ReLU gate bits are not needed
   // (the junction reads the activation itself).
   auto fwd = [&](int ch, float* X0, int K0, int in_dim, float* sh, float* sh_lo, float* params, const mtrl_net_layout_t& L, int e, int l,
-                 unsigned* bits) {
+                 unsigned* bits, float* head_pre) {
     float* X = l == 0 ? X0 : dense_in(h, ch, e, l);
     float* out = chain_d(h, ch, e, l);
-    return fwd_problem(X, l == 0 ? K0 : W, l == 0 ? in_dim : W, tk(sh, L, e, l), tb(params, L, e, l), out, M, W, h->ln_mode ? nullptr : bits,
-                       lo(h, X), tk_lo(sh_lo, L, e, l), lo(h, out));
+    mtrl_gemm_problem_t p = fwd_problem(X, l == 0 ? K0 : W, l == 0 ? in_dim : W, tk(sh, L, e, l), tb(params, L, e, l), out, M, W,
+                                        h->ln_mode ? nullptr : bits, lo(h, X), tk_lo(sh_lo, L, e, l), lo(h, out));
+    if (h->fused_heads && l == D - 1) {
+      p.head_w = hk(params, L, e);
+      p.head_out = head_pre;
+      p.head_tile_task = w.tile_task;
+      p.head_dim = L.head_dim;
+    }
+    return p;
   };
   std::vector<std::vector<mtrl_gemm_problem_t>> all_f, all_t, all_pi;
   for (int l = 0; l < D; ++l) {
     std::vector<mtrl_gemm_problem_t> p;
-    p.push_back(fwd(CH_AN, w.Xa_next, Ka, LA.in_dim, ash, w.ash_lo, h->buf.actor_params, LA, 0, l, nullptr));
-    p.push_back(fwd(CH_AO, w.Xa, Ka, LA.in_dim, ash, w.ash_lo, h->buf.actor_params, LA, 0, l, l + 1 < D ? w.bits_Ao[l] : nullptr));
+    p.push_back(fwd(CH_AN, w.Xa_next, Ka, LA.in_dim, ash, w.ash_lo, h->buf.actor_params, LA, 0, l, nullptr, w.pre_an));
+    p.push_back(fwd(CH_AO, w.Xa, Ka, LA.in_dim, ash, w.ash_lo, h->buf.actor_params, LA, 0, l, l + 1 < D ? w.bits_Ao[l] : nullptr, w.pre_ao));
     for (int e = 0; e < E; ++e)
-      p.push_back(fwd(CH_C, w.Xc, Kc, LC.in_dim, csh, w.csh_lo, h->buf.critic_params, LC, e, l, l + 1 < D ? w.bits_C[e][l] : nullptr));
+      p.push_back(fwd(CH_C, w.Xc, Kc, LC.in_dim, csh, w.csh_lo, h->buf.critic_params, LC, e, l, l + 1 < D ? w.bits_C[e][l] : nullptr,
+                      w.pre_c[e]));
     MTRL_PROPAGATE(make_plan(h->fwd, p));
     all_f.push_back(p);
   }
   for (int l = 0; l < D; ++l) {
     std::vector<mtrl_gemm_problem_t> p, q;
     for (int e = 0; e < E; ++e) {
-      p.push_back(fwd(CH_TG, w.Xc_next, Kc, LC.in_dim, tsh, w.tsh_lo, h->buf.critic_target, LC, e, l, nullptr));
-      q.push_back(fwd(CH_C, w.Xc, Kc, LC.in_dim, csh, w.csh_lo, h->buf.critic_params, LC, e, l, l + 1 < D ? w.bits_C[e][l] : nullptr));
+      p.push_back(fwd(CH_TG, w.Xc_next, Kc, LC.in_dim, tsh, w.tsh_lo, h->buf.critic_target, LC, e, l, nullptr, w.pre_tg[e]));
+      q.push_back(fwd(CH_C, w.Xc, Kc, LC.in_dim, csh, w.csh_lo, h->buf.critic_params, LC, e, l, l + 1 < D ? w.bits_C[e][l] : nullptr,
+                      w.pre_pi[e]));
     }
     MTRL_PROPAGATE(make_plan(h->fwd_target, p));
     MTRL_PROPAGATE(make_plan(h->fwd_pi, q));
@@ -516,11 +543,13 @@ void launch_actor_head_rows(const ActorHeadArgs& a, int action_dim, dim3 grid, d
   }
 }
 
-int launch_actor_head(mtrl_sac* h, const float* H, const float* eps, float* Xdst, float* logp, bool save, cudaStream_t st) {
+int launch_actor_head(mtrl_sac* h, const float* H, const float* pre, const float* eps, float* Xdst, float* logp, bool save,
+                      cudaStream_t st) {
   const mtrl_sac_config_t& c = h->cfg;
   ActorHeadArgs a;
   a.h_lo_delta = h->ws.lo_delta;
   a.H = H;
+  a.pre = pre;
   a.Wh = hk(h->buf.actor_params, h->lay.actor, 0);
   a.bh = hb(h->buf.actor_params, h->lay.actor, 0);
   a.tile_task = h->ws.tile_task;
@@ -540,6 +569,15 @@ int launch_actor_head(mtrl_sac* h, const float* H, const float* eps, float* Xdst
   a.ls_max = c.log_std_max;
   const size_t wbytes = static_cast<size_t>(c.width + 4) * 2 * c.action_dim * sizeof(float);
   MTRL_PROPAGATE(prof_begin(h, PT_ACTOR_HEAD, st));
+  if (pre) {
+    // the head's outputs came out of the GEMM epilogue: one thread per (row, action dimension) worth of work
+    const int wpb = 8;
+    launch_actor_head_rows(a, c.action_dim, dim3((c.max_rows + wpb - 1) / wpb), dim3(wpb * 32), st);
+    MTRL_CUDA_CHECK(cudaGetLastError());
+    MTRL_PROPAGATE(prof_end(h, st));
+    LAUNCHED(h);
+    return MTRL_OK;
+  }
   if (wbytes <= 200 * 1024) {
     // 16-row blocks, three resident per SM: 6400 rows = 400 blocks = one wave
     const int rpb = c.max_rows <= 16 * 3 * h->sms ? 16 : 32;
@@ -809,6 +847,13 @@ extern "C" int mtrl_sac_create(mtrl_sac_t** out, const mtrl_sac_config_t* cfg, c
     const char* env = getenv("MTRL_FUSE_LAYERS");
     h->fuse_layers = !h->ln_mode && cfg->depth > 1 && env && env[0] == '1';
   }
+  {
+    // MTRL_FUSED_HEADS=0 keeps the stand-alone head kernels (which LayerNorm / skip networks and head widths the GEMM
+    // epilogue does not take always use)
+    const char* env = getenv("MTRL_FUSED_HEADS");
+    const int hd = 2 * cfg->action_dim;
+    h->fused_heads = !h->ln_mode && (hd == 2 || hd == 4 || hd == 8) && cfg->width % 32 == 0 && !(env && env[0] == '0');
+  }
   int rc = mtrl_sac_query_layout(cfg, &h->lay);
   if (rc != MTRL_OK) { delete h; return rc; }
   const void* need[] = {b->actor_params, b->actor_grads, b->actor_m, b->actor_v, b->actor_shadow, b->critic_params,
@@ -909,6 +954,10 @@ int step_begin(mtrl_sac* h, const float* obs, const float* actions, const float*
   MTRL_CUDA_CHECK(cudaMemsetAsync(h->buf.critic_grads, 0, h->lay.critic.total * sizeof(float), st));
   MTRL_CUDA_CHECK(cudaMemsetAsync(h->buf.actor_grads, 0, h->lay.actor.total * sizeof(float), st));
   h->launches += 4;
+  if (h->fused_heads) {
+    MTRL_CUDA_CHECK(cudaMemsetAsync(w.pre_an, 0, w.pre_floats * sizeof(float), st));
+    h->launches += 1;
+  }
   MTRL_PROPAGATE(step_alpha_prep(h, st));
   const int nchunks = (batch + 31) / 32;
   const size_t smem = (static_cast<size_t>(nchunks) * T + T + 1) * sizeof(int);
@@ -951,7 +1000,9 @@ int step_critic_grads(mtrl_sac* h, cudaStream_t st) {
   Workspace& w = h->ws;
   const mtrl_net_layout_t& LC = h->lay.critic;
   const int M = c.max_rows, W = c.width, D = c.depth, E = c.num_critics;
-  MTRL_PROPAGATE(launch_actor_head(h, head_in(h, h->split_critic ? CH_AO : CH_AN, 0), w.eps_c, w.Xc_next, w.logp_next, false, st));
+  MTRL_PROPAGATE(launch_actor_head(h, head_in(h, h->split_critic ? CH_AO : CH_AN, 0),
+                                   h->fused_heads ? (h->split_critic ? w.pre_ao : w.pre_an) : nullptr, w.eps_c, w.Xc_next, w.logp_next,
+                                   false, st));
   if (h->fused[mtrl_sac::F_FWD_TARGET]) MTRL_PROPAGATE(run_plan(h, h->fused[mtrl_sac::F_FWD_TARGET], st));
   for (int l = 0; l < D && !h->fused[mtrl_sac::F_FWD_TARGET]; ++l) {
     MTRL_PROPAGATE(run_plan(h, h->fwd_target[l], st));
@@ -971,6 +1022,8 @@ int step_critic_grads(mtrl_sac* h, cudaStream_t st) {
       a.online.H[e] = head_in(h, CH_C, e);
       a.online.w[e] = hk(h->buf.critic_params, LC, e);
       a.online.b[e] = hb(h->buf.critic_params, LC, e);
+      a.target.pre[e] = h->fused_heads ? w.pre_tg[e] : nullptr;
+      a.online.pre[e] = h->fused_heads ? w.pre_c[e] : nullptr;
     }
     a.tile_task = w.tile_task; a.slot_src = w.slot_src;
     a.rew = w.rew; a.done = w.done; a.logp_next = w.logp_next; a.alpha_val = w.alpha_val; a.task_w = w.task_w;
@@ -1043,7 +1096,7 @@ int step_critic_apply(mtrl_sac* h, cudaStream_t st) {
     return MTRL_OK;
   }
   MTRL_PROPAGATE(prof_begin(h, PT_SUMSQ, st));
-  mtrl_launch(sumsq_kernel, dim3(h->sms * 2), dim3(256), 0, st, h->buf.critic_grads, LC.trunk_total, w.acc + ACC_CRITIC_G2);
+  mtrl_launch(sumsq_kernel, dim3(h->sms * 4), dim3(256), 0, st, h->buf.critic_grads, LC.trunk_total, w.acc + ACC_CRITIC_G2);
   MTRL_PROPAGATE(prof_end(h, st));
   LAUNCHED(h);
   AdamArgs a;
@@ -1072,7 +1125,8 @@ int step_critic_apply(mtrl_sac* h, cudaStream_t st) {
 // action also becomes the action columns of the critic input (only valid once the critic backward has consumed them).
 int step_actor_sample(mtrl_sac* h, bool write_x, cudaStream_t st) {
   Workspace& w = h->ws;
-  return launch_actor_head(h, head_in(h, CH_AO, 0), w.eps_a, write_x ? w.Xc : nullptr, w.logp, true, st);
+  return launch_actor_head(h, head_in(h, CH_AO, 0), h->fused_heads ? w.pre_ao : nullptr, w.eps_a, write_x ? w.Xc : nullptr, w.logp, true,
+                           st);
 }
 
 int step_write_actions(mtrl_sac* h, cudaStream_t st) {
@@ -1112,6 +1166,7 @@ int step_actor_grads(mtrl_sac* h, cudaStream_t st) {
       a.online.H[e] = head_in(h, CH_C, e);
       a.online.w[e] = hk(h->buf.critic_params, LC, e);
       a.online.b[e] = hb(h->buf.critic_params, LC, e);
+      a.online.pre[e] = h->fused_heads ? w.pre_pi[e] : nullptr;
     }
     a.tile_task = w.tile_task; a.slot_src = w.slot_src; a.logp = w.logp; a.alpha_val = w.alpha_val; a.task_w = w.task_w;
     a.dq = w.dq; a.acc = w.acc; a.M = M; a.W = W; a.E = E; a.inv_b = inv_b; a.h_lo_delta = w.lo_delta;
@@ -1184,7 +1239,7 @@ int step_actor_apply(mtrl_sac* h, cudaStream_t st) {
     return MTRL_OK;
   }
   MTRL_PROPAGATE(prof_begin(h, PT_SUMSQ, st));
-  mtrl_launch(sumsq_kernel, dim3(h->sms * 2), dim3(256), 0, st, h->buf.actor_grads, LA.trunk_total, w.acc + ACC_ACTOR_G2);
+  mtrl_launch(sumsq_kernel, dim3(h->sms * 4), dim3(256), 0, st, h->buf.actor_grads, LA.trunk_total, w.acc + ACC_ACTOR_G2);
   MTRL_PROPAGATE(prof_end(h, st));
   LAUNCHED(h);
   AdamArgs a;

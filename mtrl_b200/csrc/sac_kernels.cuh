@@ -379,6 +379,7 @@ static __global__ void alpha_prep_kernel(const float* __restrict__ log_alpha, in
 struct ActorHeadArgs {
   long long h_lo_delta;  // fp32x3: H[i + h_lo_delta] is the tf32 remainder of H[i]; the heads then see hi + lo (0 = tf32 mode)
   const float* H;        // [M][W] last trunk activation
+  const float* pre;      // optional [M][2A]: H . Wh already computed by the GEMM epilogue (fused heads); H is then not read
   const float* Wh;       // (T_local, W, 2A)
   const float* bh;       // (T_local, 2A)
   const int* tile_task;
@@ -407,7 +408,10 @@ static __global__ void actor_head_kernel(const ActorHeadArgs p) {
   float acc[2 * A];
 #pragma unroll
   for (int j = 0; j < 2 * A; ++j) acc[j] = 0.f;
-  if (valid) {
+  if (valid && p.pre) {
+#pragma unroll
+    for (int j = 0; j < 2 * A; ++j) acc[j] = p.pre[static_cast<long long>(row) * (2 * A) + j];
+  } else if (valid) {
     const float* h = p.H + static_cast<long long>(row) * p.W;
     const float* w = p.Wh + static_cast<long long>(t) * p.W * (2 * A);
     for (int k = lane; k < p.W; k += 32) {
@@ -417,8 +421,10 @@ static __global__ void actor_head_kernel(const ActorHeadArgs p) {
       for (int j = 0; j < 2 * A; ++j) acc[j] = fmaf(hv, __ldg(wk + j), acc[j]);
     }
   }
+  if (!p.pre) {
 #pragma unroll
-  for (int j = 0; j < 2 * A; ++j) acc[j] = warp_sum(acc[j]);
+    for (int j = 0; j < 2 * A; ++j) acc[j] = warp_sum(acc[j]);
+  }
   float lp = 0.f;
   unsigned mask = 0;
   if (lane < A) {
@@ -618,6 +624,7 @@ struct QHeads {
   const float* H[kMaxE];   // [M][W] last trunk activation of member e
   const float* w[kMaxE];   // (T_local, W, 1)
   const float* b[kMaxE];   // (T_local, 1)
+  const float* pre[kMaxE]; // optional [M]: H_e . w_e already computed by the GEMM epilogue (fused heads); H is then not read
 };
 
 // N row-by-vector dot products at once (one warp, lanes stride the float4 columns): every pass issues the 2N loads of
@@ -709,7 +716,12 @@ static __global__ void critic_loss_kernel(const CriticLossArgs p) {
         const float* const hh[2] = {p.target.H[e] + ro, p.online.H[e] + ro};
         const float* const ww[2] = {p.target.w[e] + wo, p.online.w[e] + wo};
         float o[2];
-        row_dots<2>(hh, ww, p.W, lane, o, p.h_lo_delta);
+        if (p.online.pre[e]) {
+          o[0] = p.target.pre[e][row];
+          o[1] = p.online.pre[e][row];
+        } else {
+          row_dots<2>(hh, ww, p.W, lane, o, p.h_lo_delta);
+        }
         qt_min = fminf(qt_min, o[0] + p.target.b[e][t]);
         q[e] = o[1] + p.online.b[e][t];
       }
@@ -774,7 +786,15 @@ static __global__ void actor_loss_kernel(const ActorLossArgs p) {
 #pragma unroll
     for (int e = 0; e < kMaxE; ++e) q[e] = INFINITY;
     const long long ro = static_cast<long long>(row) * p.W, wo = static_cast<long long>(t) * p.W;
-    if (valid && p.E == 2) {   // the reference's ensemble size: both members' loads in flight together
+    if (valid && p.online.pre[0]) {
+#pragma unroll
+      for (int e = 0; e < kMaxE; ++e) {
+        if (e < p.E) {
+          q[e] = p.online.pre[e][row] + p.online.b[e][t];
+          qmin = fminf(qmin, q[e]);
+        }
+      }
+    } else if (valid && p.E == 2) {   // the reference's ensemble size: both members' loads in flight together
       const float* const hh[2] = {p.online.H[0] + ro, p.online.H[1] + ro};
       const float* const ww[2] = {p.online.w[0] + wo, p.online.w[1] + wo};
       float o[2];
@@ -1521,12 +1541,22 @@ static __global__ void sumsq_kernel(const float* __restrict__ x, long long n, do
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   const long long n4 = n / 4;
   const float4* x4 = reinterpret_cast<const float4*>(x);
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  // four independent 16-byte loads in flight per thread (one per iteration leaves the kernel latency-bound)
+  for (; i + 3 * stride < n4; i += 4 * stride) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = x4[i + u * stride];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      s += static_cast<double>(v[u].x * v[u].x + v[u].y * v[u].y) + static_cast<double>(v[u].z * v[u].z + v[u].w * v[u].w);
+  }
+  for (; i < n4; i += stride) {
     const float4 v = x4[i];
     s += static_cast<double>(v.x * v.x + v.y * v.y) + static_cast<double>(v.z * v.z + v.w * v.w);
   }
-  for (long long i = n4 * 4 + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
-    s += static_cast<double>(x[i] * x[i]);
+  for (long long j = n4 * 4 + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; j < n; j += stride)
+    s += static_cast<double>(x[j] * x[j]);
   s = block_sum(s, red);
   if (threadIdx.x == 0) atomicAdd(acc, s);
 }
@@ -1554,7 +1584,7 @@ struct AdamArgs {
   float lr, b1, b2, eps, max_norm, tau;
 };
 
-static __global__ void adam_kernel(const AdamArgs a) {
+static __global__ void __launch_bounds__(256, 4) adam_kernel(const AdamArgs a) {
   MTRL_PDL_PROLOGUE();
   __shared__ double red[32];
   const double g2 = *a.g2_trunk + static_cast<double>(*a.g2_heads);

@@ -211,3 +211,52 @@ def test_phased_backward_chain(cuda):
         torch.cuda.synchronize()
         for a, b in zip(o, r):
             assert torch.equal(a, b), f"repetition {rep}"
+
+
+@pytest.mark.parametrize("ctas", [2, 1])
+@pytest.mark.parametrize("hd", [1, 2, 4, 8])
+@pytest.mark.parametrize("shape", [(384, 512, 320, 256), (256, 400, 96, 224), (384, 256, 64, 128)])
+def test_fused_output_head(cuda, ctas, hd, shape):
+    """mtrl_gemm_problem_t::head_w: the own-task head (nn.vmap(Dense), multi_head.py:50-66) accumulated by the bias + ReLU
+    epilogue, head_out[m][j] = sum_n D[m][n] head_w[task(m)][n][j], against a matmul of the D the launch stored."""
+    import torch
+
+    import gemm_cases as G
+    from mtrl_b200 import _lib as L
+
+    M, N, K, bn = shape
+    p, D, ref, keep = G.make_problem(M, N, K, 0, 1, L.EPI_BIAS_RELU, bn, 1, seed=3)
+    T = 3
+    g = torch.Generator(device="cpu").manual_seed(7)
+    head_w = torch.randn(T, N, hd, generator=g).cuda()
+    tile_task = torch.tensor([(2 * i + 1) % T for i in range(M // 128)], dtype=torch.int32, device="cuda")
+    out = torch.zeros(M, hd, device="cuda")
+    p.head_w, p.head_out, p.head_tile_task, p.head_dim = head_w.data_ptr(), out.data_ptr(), tile_task.data_ptr(), hd
+    L.GemmPlan([p], ctas=ctas).run()
+    torch.cuda.synchronize()
+    rel, _ = G.rel_err(D, ref, L.EPI_BIAS_RELU)
+    assert rel < 5e-4
+    want = torch.cat([D[128 * i:128 * (i + 1)].double() @ head_w[int(tile_task[i])].double() for i in range(M // 128)])
+    err = float((out.double() - want).norm() / want.norm())
+    assert err < 2e-6, f"fused head rel err {err}"
+
+
+def test_fused_output_head_fp32x3(cuda):
+    """With D_lo the head sees the unrounded result (hi + lo), as the stand-alone head kernels do in that mode."""
+    import torch
+
+    import gemm_cases as G
+    from mtrl_b200 import _lib as L
+
+    M, N, K, hd = 256, 512, 320, 8
+    p, D, D_lo, ref, keep = G.make_problem_x3(M, N, K, 0, 1, L.EPI_BIAS_RELU, 128, 1, seed=5)
+    head_w = torch.randn(2, N, hd, generator=torch.Generator().manual_seed(9)).cuda()
+    tile_task = torch.tensor([1, 0], dtype=torch.int32, device="cuda")
+    out = torch.zeros(M, hd, device="cuda")
+    p.head_w, p.head_out, p.head_tile_task, p.head_dim = head_w.data_ptr(), out.data_ptr(), tile_task.data_ptr(), hd
+    L.GemmPlan([p]).run()
+    torch.cuda.synchronize()
+    full = D.double() + D_lo.double()
+    want = torch.cat([full[128 * i:128 * (i + 1)] @ head_w[int(tile_task[i])].double() for i in range(2)])
+    err = float((out.double() - want).norm() / want.norm())
+    assert err < 2e-6, f"fused head (fp32x3) rel err {err}"
