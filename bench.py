@@ -560,7 +560,8 @@ def main() -> None:
             "dtype": args.precision, "data": "synthetic",
             "config": dict(workload_config(args), **{
                        "parallelism": (f"tasks sharded over {world} GPU(s); trunk gradients: " +
-                                       ("fused peer-memory reduce-scatter + sharded Adam + all-gather kernel (NVLink P2P, no NCCL)"
+                                       ("fused peer-memory reduce-scatter + sharded Adam + all-gather kernel (NVLink P2P, no NCCL; all-gather by "
+                                        + ("NVSwitch multicast stores, multimem.st)" if getattr(agent, "multicast", False) else "one store per peer)")
                                         if exchange == "p2p" else "NCCL all-reduce between the phases")) if world > 1 else "single GPU",
                        "l2": "per-step working set (activations + parameters, ~%.1f GB) exceeds the 126 MB L2; no explicit flush"
                              % ((22 * B_local * W * 4 + 12 * 3 * W * W * 4) / 1e9),

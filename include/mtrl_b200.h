@@ -431,6 +431,21 @@ int mtrl_comm_create(mtrl_comm_t** out, int rank, int world, long long arena_byt
 void* mtrl_comm_arena(mtrl_comm_t* c);
 /* handles: world x 64 bytes, rank-major (the caller all-gathers what mtrl_comm_create returned). */
 int mtrl_comm_open_peers(mtrl_comm_t* c, const unsigned char* handles);
+/* NVSwitch multicast ("NVLS") region for the parameter all-gather (optional; needs CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED
+ * on every GPU).  Protocol, each step on every rank unless noted, with a host barrier after add_device and after bind:
+ *   rank 0: mtrl_comm_mc_create(bytes) -> POSIX fd, passed to the other ranks by the host (SCM_RIGHTS);
+ *   others: mtrl_comm_mc_import(bytes, fd);   all: mtrl_comm_mc_add_device;   all: mtrl_comm_mc_bind.
+ * mtrl_comm_mc_local = this rank's copy of the region (ordinary device memory: the parameter buffers of the handle
+ * live here), mtrl_comm_mc_ptr = the multicast alias (multimem.st only).  mtrl_sac_attach_comm on a comm with a bound
+ * region takes the two parameter offsets relative to that region. */
+int mtrl_comm_mc_supported(int* out);
+int mtrl_comm_mc_create(mtrl_comm_t* c, long long bytes, int* fd_out);
+int mtrl_comm_mc_import(mtrl_comm_t* c, long long bytes, int fd);
+int mtrl_comm_mc_add_device(mtrl_comm_t* c);
+int mtrl_comm_mc_bind(mtrl_comm_t* c);
+void* mtrl_comm_mc_local(mtrl_comm_t* c);
+void* mtrl_comm_mc_ptr(mtrl_comm_t* c);
+long long mtrl_comm_mc_bytes(mtrl_comm_t* c);
 /* Synchronous read of the arena's error word: 0 ok, otherwise the in-kernel wait that timed out (a peer never came). */
 int mtrl_comm_error(mtrl_comm_t* c, int* code);
 /* Synchronous read of the phase durations (microseconds, CTA 0 of this rank) of the last two fused trunk steps:

@@ -1,7 +1,9 @@
 // Exchange arena: one cudaMalloc block per rank, exported to the other ranks of the box through CUDA IPC so that
 // kernels can load / store peer memory over NVLink (comm.cuh).  Replaces nothing in the reference (it is single
 // device); it is the multi-GPU plumbing of SURVEY 8(e).
+#include <cuda.h>
 #include <stdlib.h>
+#include <unistd.h>
 
 #include "comm.cuh"
 
@@ -73,6 +75,172 @@ extern "C" int mtrl_comm_open_peers(mtrl_comm_t* c, const unsigned char* handles
   c->opened = true;
   return MTRL_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// NVSwitch multicast ("NVLS") region for the parameter all-gather.  One multicast object spans the box; every rank binds
+// a physical allocation of its own to it and maps (a) that allocation for ordinary local access and (b) the multicast
+// address, where ONE multimem.st lands in all ranks' copies -- the switch replicates the store, so the owner of a trunk
+// segment sends its new parameters over NVLink once instead of once per peer.  Driver entry points are looked up at run
+// time (the library links no libcuda, so it still loads on a box without a driver).
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+template <typename Fn>
+int driver_fn(const char* name, Fn* out) {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess) {
+    cudaGetLastError();
+    mtrl_set_error("driver entry point %s is not available", name);
+    return MTRL_ERR_UNSUPPORTED;
+  }
+  *out = reinterpret_cast<Fn>(fn);
+  return MTRL_OK;
+}
+
+#define MTRL_DRV(name, ...)                                             \
+  typedef CUresult (*name##_t)(__VA_ARGS__);                            \
+  name##_t name##_p = nullptr;                                          \
+  MTRL_PROPAGATE(driver_fn(#name, &name##_p))
+
+#define MTRL_CU_CHECK(call)                                                       \
+  do {                                                                            \
+    const CUresult r_ = (call);                                                   \
+    if (r_ != CUDA_SUCCESS) {                                                     \
+      mtrl_set_error("%s failed with CUresult %d", #call, static_cast<int>(r_));  \
+      return MTRL_ERR_CUDA;                                                       \
+    }                                                                             \
+  } while (0)
+
+int current_device(CUdevice* dev, int* ordinal) {
+  MTRL_DRV(cuDeviceGet, CUdevice*, int);
+  MTRL_CUDA_CHECK(cudaGetDevice(ordinal));
+  MTRL_CUDA_CHECK(cudaFree(nullptr));   // make sure the primary context exists
+  MTRL_CU_CHECK(cuDeviceGet_p(dev, *ordinal));
+  return MTRL_OK;
+}
+
+long long round_up_ll(long long x, long long m) { return (x + m - 1) / m * m; }
+
+int mc_prop(const mtrl_comm* c, long long bytes, CUmulticastObjectProp* prop, size_t* gran) {
+  MTRL_DRV(cuMulticastGetGranularity, size_t*, const CUmulticastObjectProp*, CUmulticastGranularity_flags);
+  memset(prop, 0, sizeof(*prop));
+  prop->numDevices = static_cast<unsigned>(c->world);
+  prop->handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+  prop->size = static_cast<size_t>(bytes);
+  MTRL_CU_CHECK(cuMulticastGetGranularity_p(gran, prop, CU_MULTICAST_GRANULARITY_RECOMMENDED));
+  prop->size = static_cast<size_t>(round_up_ll(bytes, static_cast<long long>(*gran)));
+  return MTRL_OK;
+}
+
+}  // namespace
+
+extern "C" int mtrl_comm_mc_supported(int* out) {
+  MTRL_REQUIRE(out, "mtrl_comm_mc_supported: null argument");
+  *out = 0;
+  MTRL_DRV(cuDeviceGetAttribute, int*, CUdevice_attribute, CUdevice);
+  CUdevice dev;
+  int ordinal = 0;
+  MTRL_PROPAGATE(current_device(&dev, &ordinal));
+  int v = 0;
+  MTRL_CU_CHECK(cuDeviceGetAttribute_p(&v, CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, dev));
+  *out = v;
+  return MTRL_OK;
+}
+
+extern "C" int mtrl_comm_mc_create(mtrl_comm_t* c, long long bytes, int* fd_out) {
+  MTRL_REQUIRE(c && fd_out && bytes > 0, "mtrl_comm_mc_create: bad argument");
+  MTRL_REQUIRE(!c->mc_handle, "mtrl_comm_mc_create: the multicast object exists already");
+  MTRL_DRV(cuMulticastCreate, CUmemGenericAllocationHandle*, const CUmulticastObjectProp*);
+  MTRL_DRV(cuMemExportToShareableHandle, void*, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long);
+  CUmulticastObjectProp prop;
+  size_t gran = 0;
+  MTRL_PROPAGATE(mc_prop(c, bytes, &prop, &gran));
+  CUmemGenericAllocationHandle mc = 0;
+  MTRL_CU_CHECK(cuMulticastCreate_p(&mc, &prop));
+  int fd = -1;
+  MTRL_CU_CHECK(cuMemExportToShareableHandle_p(&fd, mc, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0));
+  c->mc_handle = mc;
+  c->mc_bytes = static_cast<long long>(prop.size);
+  *fd_out = fd;
+  return MTRL_OK;
+}
+
+extern "C" int mtrl_comm_mc_import(mtrl_comm_t* c, long long bytes, int fd) {
+  MTRL_REQUIRE(c && bytes > 0 && fd >= 0, "mtrl_comm_mc_import: bad argument");
+  MTRL_REQUIRE(!c->mc_handle, "mtrl_comm_mc_import: the multicast object exists already");
+  MTRL_DRV(cuMemImportFromShareableHandle, CUmemGenericAllocationHandle*, void*, CUmemAllocationHandleType);
+  CUmulticastObjectProp prop;
+  size_t gran = 0;
+  MTRL_PROPAGATE(mc_prop(c, bytes, &prop, &gran));
+  CUmemGenericAllocationHandle mc = 0;
+  MTRL_CU_CHECK(cuMemImportFromShareableHandle_p(&mc, reinterpret_cast<void*>(static_cast<uintptr_t>(fd)),
+                                                 CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
+  c->mc_handle = mc;
+  c->mc_bytes = static_cast<long long>(prop.size);
+  return MTRL_OK;
+}
+
+extern "C" int mtrl_comm_mc_add_device(mtrl_comm_t* c) {
+  MTRL_REQUIRE(c && c->mc_handle, "mtrl_comm_mc_add_device: no multicast object");
+  MTRL_DRV(cuMulticastAddDevice, CUmemGenericAllocationHandle, CUdevice);
+  CUdevice dev;
+  int ordinal = 0;
+  MTRL_PROPAGATE(current_device(&dev, &ordinal));
+  MTRL_CU_CHECK(cuMulticastAddDevice_p(static_cast<CUmemGenericAllocationHandle>(c->mc_handle), dev));
+  return MTRL_OK;
+}
+
+extern "C" int mtrl_comm_mc_bind(mtrl_comm_t* c) {
+  MTRL_REQUIRE(c && c->mc_handle && !c->mc_local, "mtrl_comm_mc_bind: no multicast object, or bound already");
+  MTRL_DRV(cuMemCreate, CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long);
+  MTRL_DRV(cuMemGetAllocationGranularity, size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags);
+  MTRL_DRV(cuMemAddressReserve, CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long);
+  MTRL_DRV(cuMemMap, CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long);
+  MTRL_DRV(cuMemSetAccess, CUdeviceptr, size_t, const CUmemAccessDesc*, size_t);
+  MTRL_DRV(cuMulticastBindMem, CUmemGenericAllocationHandle, size_t, CUmemGenericAllocationHandle, size_t, size_t, unsigned long long);
+  CUdevice dev;
+  int ordinal = 0;
+  MTRL_PROPAGATE(current_device(&dev, &ordinal));
+  const size_t size = static_cast<size_t>(c->mc_bytes);
+  CUmemAllocationProp ap;
+  memset(&ap, 0, sizeof(ap));
+  ap.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+  ap.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  ap.location.id = ordinal;
+  ap.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+  size_t agran = 0;
+  MTRL_CU_CHECK(cuMemGetAllocationGranularity_p(&agran, &ap, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED));
+  MTRL_REQUIRE(size % agran == 0, "mtrl_comm_mc_bind: multicast size %zu is not a multiple of the allocation granularity %zu", size,
+               agran);
+  CUmemGenericAllocationHandle mem = 0;
+  MTRL_CU_CHECK(cuMemCreate_p(&mem, size, &ap, 0));
+  const CUmemGenericAllocationHandle mc = static_cast<CUmemGenericAllocationHandle>(c->mc_handle);
+  MTRL_CU_CHECK(cuMulticastBindMem_p(mc, 0, mem, 0, size, 0));
+  CUmemAccessDesc ad;
+  memset(&ad, 0, sizeof(ad));
+  ad.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  ad.location.id = ordinal;
+  ad.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  CUdeviceptr local = 0, mcva = 0;
+  MTRL_CU_CHECK(cuMemAddressReserve_p(&local, size, agran, 0, 0));
+  MTRL_CU_CHECK(cuMemMap_p(local, size, 0, mem, 0));
+  MTRL_CU_CHECK(cuMemSetAccess_p(local, size, &ad, 1));
+  MTRL_CU_CHECK(cuMemAddressReserve_p(&mcva, size, agran, 0, 0));
+  MTRL_CU_CHECK(cuMemMap_p(mcva, size, 0, mc, 0));
+  MTRL_CU_CHECK(cuMemSetAccess_p(mcva, size, &ad, 1));
+  c->mc_mem = mem;
+  c->mc_local = reinterpret_cast<uint8_t*>(local);
+  c->mc_ptr = reinterpret_cast<uint8_t*>(mcva);
+  MTRL_CUDA_CHECK(cudaMemset(c->mc_local, 0, size));
+  MTRL_CUDA_CHECK(cudaDeviceSynchronize());
+  return MTRL_OK;
+}
+
+extern "C" void* mtrl_comm_mc_local(mtrl_comm_t* c) { return c ? c->mc_local : nullptr; }
+extern "C" void* mtrl_comm_mc_ptr(mtrl_comm_t* c) { return c ? c->mc_ptr : nullptr; }
+extern "C" long long mtrl_comm_mc_bytes(mtrl_comm_t* c) { return c ? c->mc_bytes : 0; }
 
 extern "C" int mtrl_comm_error(mtrl_comm_t* c, int* code) {
   MTRL_REQUIRE(c && code, "mtrl_comm_error: null argument");

@@ -93,6 +93,8 @@ struct TrunkStepArgs {
   long long n, trunk_n;                                    // as AdamArgs
   float* peer_g[MTRL_COMM_MAX_RANKS];                      // every rank's gradient buffer ([rank] == g)
   float* peer_p[MTRL_COMM_MAX_RANKS];                      // every rank's parameter buffer ([rank] == p)
+  float* mc_p;                                             // multicast alias of the parameter buffers (one multimem.st reaches
+                                                           // every rank's copy, this rank's included), or null
   Header* peer_hdr[MTRL_COMM_MAX_RANKS];
   const Segment* segs;                                     // device table covering [0, trunk_n)
   int nsegs;
@@ -338,9 +340,16 @@ static __global__ void __launch_bounds__(512, 1) trunk_step_kernel(const TrunkSt
       adam4(a, scale, bc1, bc2, g4, m4, v4, p4);
       reinterpret_cast<float4*>(a.m)[i] = m4;
       reinterpret_cast<float4*>(a.v)[i] = v4;
+      if (a.mc_p) {
+        // NVLS: the switch replicates the store into every rank's copy
+        asm volatile("multimem.st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.mc_p + i * 4), "f"(p4.x), "f"(p4.y), "f"(p4.z),
+                     "f"(p4.w)
+                     : "memory");
+      } else {
 #pragma unroll
-      for (int q = 0; q < (WORLD ? WORLD : MTRL_COMM_MAX_RANKS); ++q)
-        if (q < world) reinterpret_cast<float4*>(a.peer_p[q])[i] = p4;
+        for (int q = 0; q < (WORLD ? WORLD : MTRL_COMM_MAX_RANKS); ++q)
+          if (q < world) reinterpret_cast<float4*>(a.peer_p[q])[i] = p4;
+      }
       p2_trunk += static_cast<double>(derived4(a, i, p4));
     }
   }
@@ -408,4 +417,9 @@ struct mtrl_comm {
   uint8_t* peer[MTRL_COMM_MAX_RANKS] = {};
   bool opened = false;
   comm::Header** d_peer_hdr = nullptr;   // device copy of the header pointers (rank_barrier_kernel)
+  // NVSwitch multicast region (comm.cu): the parameters live in mc_local (this rank's own physical copy); a multimem.st
+  // to mc_ptr + offset lands at mc_local + offset of EVERY rank.  All zero: peers' parameter copies are written one by one.
+  unsigned long long mc_handle = 0, mc_mem = 0;
+  long long mc_bytes = 0;
+  uint8_t *mc_local = nullptr, *mc_ptr = nullptr;
 };

@@ -800,9 +800,11 @@ int launch_trunk_step(mtrl_sac* h, comm::TrunkStepArgs& a, long long off_grads, 
   a.world = c->world;
   for (int q = 0; q < c->world; ++q) {
     a.peer_g[q] = reinterpret_cast<float*>(c->peer[q] + off_grads);
-    a.peer_p[q] = reinterpret_cast<float*>(c->peer[q] + off_params);
+    // with a multicast region the peers' parameter copies are not mapped here: one multimem.st reaches them all
+    a.peer_p[q] = c->mc_ptr ? (q == c->rank ? a.p : nullptr) : reinterpret_cast<float*>(c->peer[q] + off_params);
     a.peer_hdr[q] = reinterpret_cast<comm::Header*>(c->peer[q]);
   }
+  a.mc_p = c->mc_ptr ? reinterpret_cast<float*>(c->mc_ptr + off_params) : nullptr;
   const dim3 grid(h->sms), block(512);
   MTRL_PROPAGATE(prof_begin(h, 1, st));
   switch (c->world) {
@@ -1342,7 +1344,15 @@ extern "C" int mtrl_sac_attach_comm(mtrl_sac_t* h, mtrl_comm_t* c, long long off
   const struct { const char* name; long long off; long long bytes; const float* ptr; } r[4] = {
       {"critic_grads", off_critic_grads, need_c, h->buf.critic_grads}, {"actor_grads", off_actor_grads, need_a, h->buf.actor_grads},
       {"critic_params", off_critic_params, need_c, h->buf.critic_params}, {"actor_params", off_actor_params, need_a, h->buf.actor_params}};
-  for (const auto& x : r) {
+  for (int i = 0; i < 4; ++i) {
+    const auto& x = r[i];
+    if (i >= 2 && c->mc_local) {   // parameters in the multicast region
+      MTRL_REQUIRE(x.off >= 0 && x.off % 128 == 0 && x.off + x.bytes <= c->mc_bytes,
+                   "mtrl_sac_attach_comm: %s region [%lld, +%lld) outside the multicast region or misaligned", x.name, x.off, x.bytes);
+      MTRL_REQUIRE(reinterpret_cast<const uint8_t*>(x.ptr) == c->mc_local + x.off,
+                   "mtrl_sac_attach_comm: the handle's %s buffer is not mc_local + %lld", x.name, x.off);
+      continue;
+    }
     MTRL_REQUIRE(x.off >= MTRL_COMM_HEADER_BYTES && x.off % 128 == 0 && x.off + x.bytes <= c->arena_bytes,
                  "mtrl_sac_attach_comm: %s region [%lld, +%lld) outside the arena or misaligned", x.name, x.off, x.bytes);
     MTRL_REQUIRE(reinterpret_cast<const uint8_t*>(x.ptr) == c->arena + x.off,

@@ -127,6 +127,14 @@ L._EXTRA_DECLS.update({
     "mtrl_comm_error": ([_vp, C.POINTER(_i)],),
     "mtrl_comm_destroy": ([_vp], None),
     "mtrl_comm_phase_times": ([_vp, C.POINTER(C.c_double)],),
+    "mtrl_comm_mc_supported": ([C.POINTER(_i)],),
+    "mtrl_comm_mc_create": ([_vp, C.c_longlong, C.POINTER(_i)],),
+    "mtrl_comm_mc_import": ([_vp, C.c_longlong, _i],),
+    "mtrl_comm_mc_add_device": ([_vp],),
+    "mtrl_comm_mc_bind": ([_vp],),
+    "mtrl_comm_mc_local": ([_vp], _vp),
+    "mtrl_comm_mc_ptr": ([_vp], _vp),
+    "mtrl_comm_mc_bytes": ([_vp], C.c_longlong),
     "mtrl_sac_attach_comm": ([_vp, _vp, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong],),
 })
 
@@ -451,14 +459,99 @@ class MTSAC:
         blob = bytes(torch.stack(allh).cpu().flatten().tolist())
         L.check(L.lib().mtrl_comm_open_peers(comm, C.cast(C.c_char_p(blob), _vp)))
         base = L.lib().mtrl_comm_arena(comm)
-        self._arena_plan = plan
+        self._arena_plan = dict(plan)
         lay = self._lay
         out = {}
         for name, n in (("critic_grads", lay.critic.total), ("actor_grads", lay.actor.total),
                         ("critic_params", lay.critic.total), ("actor_params", lay.actor.total)):
             out[name] = torch.as_tensor(_DeviceSpan(base + plan[name], n, self), device=dev)
+        # parameter all-gather through the NVSwitch multicast engine where the box has one: the parameters then live in
+        # the multicast-bound region instead of the arena
+        mc_actor_off = -(-(4 * lay_max.critic.total) // 4096) * 4096
+        mc_local = self._open_multicast(dev, mc_actor_off + 4 * lay_max.actor.total)
+        self.multicast = mc_local is not None
+        if mc_local is not None:
+            self._arena_plan["critic_params"], self._arena_plan["actor_params"] = 0, mc_actor_off
+            out["critic_params"] = torch.as_tensor(_DeviceSpan(mc_local, lay.critic.total, self), device=dev)
+            out["actor_params"] = torch.as_tensor(_DeviceSpan(mc_local + mc_actor_off, lay.actor.total, self), device=dev)
         dist.barrier(group=self.process_group)
         return out
+
+    def _open_multicast(self, dev, nbytes: int):
+        """Set up the multicast region of csrc/comm.cu on every rank, or return None on ALL ranks (every stage ends with
+        an agreement, so no rank is left on a different exchange path): the device attribute, the multicast object on
+        rank 0, its file descriptor handed to the other ranks over an abstract unix socket (SCM_RIGHTS), add-device,
+        bind + map.  On by default from 8 ranks up (MTRL_MULTICAST=1|0 forces it): measured on 2, 4 and 8 B200s it barely
+        shortens the update -- the all-gather is bound by what every GPU RECEIVES (7/8 of the trunk = 60 MB per critic
+        step at 8 GPUs, ~0.75 TB/s of NVLink ingress), which a multicast store does not reduce; it only cuts the sender's
+        egress (Adam + stores 76 -> 29 us, wait for everyone's stores 36 -> 78 us; +0.5 % at 8 GPUs, -1...2 % at 2 and 4
+        where the sender's own copy loops through the switch: profiles/r02_multicast.md)."""
+        import os
+        import socket
+
+        import torch.distributed as dist
+
+        lib, comm, group = L.lib(), self._comm, self.process_group
+
+        def agree(ok: bool) -> bool:
+            if not ok and want:
+                import sys
+
+                print(f"rank {self.rank}: no multicast region ({(lib.mtrl_last_error() or b'').decode()}); "
+                      "parameters are all-gathered with one store per peer", file=sys.stderr, flush=True)
+            t = torch.tensor([1 if ok else 0], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+            return bool(int(t.item()))
+
+        sup = _i(0)
+        env = os.environ.get("MTRL_MULTICAST")
+        want = env == "1" or (env is None and self.world_size >= 8)
+        ok = want and lib.mtrl_comm_mc_supported(C.byref(sup)) == 0 and sup.value != 0
+        if not agree(ok):
+            return None
+        fd, srv, name = _i(-1), None, [None]
+        if self.rank == 0:
+            ok = lib.mtrl_comm_mc_create(comm, nbytes, C.byref(fd)) == 0
+            if ok:
+                try:
+                    srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+                    name[0] = "\0mtrl_b200_mc_%d_%d" % (os.getpid(), id(self) & 0xFFFFFF)
+                    srv.bind(name[0])
+                    srv.listen(self.world_size)
+                    srv.settimeout(60.0)
+                except OSError:
+                    ok = False
+        if not agree(ok):
+            return None
+        dist.broadcast_object_list(name, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        ok = True
+        try:
+            if self.rank == 0:
+                for _ in range(self.world_size - 1):
+                    conn, _ = srv.accept()
+                    socket.send_fds(conn, [b"m"], [fd.value])
+                    conn.close()
+                srv.close()
+            else:
+                s_ = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+                s_.settimeout(60.0)
+                s_.connect(name[0])
+                _, fds, _, _ = socket.recv_fds(s_, 16, 1)
+                s_.close()
+                ok = len(fds) == 1 and lib.mtrl_comm_mc_import(comm, nbytes, fds[0]) == 0
+                for f in fds:
+                    os.close(f)
+        except OSError:
+            ok = False
+        if not agree(ok):
+            return None
+        if self.rank == 0:
+            os.close(fd.value)
+        if not agree(lib.mtrl_comm_mc_add_device(comm) == 0):   # every device is in before anyone binds
+            return None
+        if not agree(lib.mtrl_comm_mc_bind(comm) == 0):         # every rank is bound before anyone stores
+            return None
+        return lib.mtrl_comm_mc_local(comm)
 
     def _create_handle(self) -> None:
         bufs = SacBuffersC(**{k: v.data_ptr() for k, v in self._flat.items()}, steps=self._steps.data_ptr(),

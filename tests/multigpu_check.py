@@ -61,7 +61,7 @@ def main():
     assert agent.exchange_error() == 0, f"rank {rank}: peer exchange timed out (code {agent.exchange_error()})"
     dist.barrier()
     if rank == 0:
-        print(f"multigpu_check ok: world={world} T={T} W={W} exchange={exchange}", flush=True)
+        print(f"multigpu_check ok: world={world} T={T} W={W} exchange={exchange} multicast={getattr(agent, 'multicast', False)}", flush=True)
     dist.destroy_process_group()
 
 
