@@ -122,6 +122,11 @@ inline mtrl_gemm_problem_t dw_problem(const float* X, int ldx, int n_in, const f
   const int max_splits = kb / 4 > 0 ? kb / 4 : 1;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
+  // enough output tiles to occupy every SM without cutting K (W >= 2048): one unit per tile, plain stores -- no reduce-adds, and
+  // the gradient is bit-reproducible run to run; the longest-first schedule absorbs the longer units (same-box A/B at
+  // MT50/W2048: GEMM launches 1.5 % shorter).  MTRL_DW_SPLITS=n forces n.
+  if (n_in >= 128 && tiles * 2 >= sms) splits = 1;
+  if (n_in >= 128 && getenv("MTRL_DW_SPLITS")) splits = atoi(getenv("MTRL_DW_SPLITS")) > 0 ? atoi(getenv("MTRL_DW_SPLITS")) : splits;
   (void)units_hint;
   p.k_splits = splits;
   p.epilogue = splits > 1 ? MTRL_EPI_ATOMIC_ADD : MTRL_EPI_STORE;

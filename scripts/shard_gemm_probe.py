@@ -69,6 +69,9 @@ GROUPS = {
                                            4 * 2 * rows * W * W),
     "bwd pi: 2 dX": lambda bn: ([dx(rows, W, W, bn) for _ in range(2)], 2 * 2 * rows * W * W),
     "bwd actor: dW + dX": lambda bn: ([dw(W, W, rows, bn, 1), dx(rows, W, W, bn)], 2 * 2 * rows * W * W),
+    # first layer (K = 96 after padding): output-store bound, not tensor bound
+    "fwd L0 x4 (K = 96)": lambda bn: ([fwd(rows, W, 96, bn) for _ in range(4)], 4 * 2 * rows * W * 96),
+    "fwd L0 x2 (K = 96)": lambda bn: ([fwd(rows, W, 96, bn) for _ in range(2)], 2 * 2 * rows * W * 96),
 }
 only = os.environ.get("PROBE_ONLY")
 for name, make in GROUPS.items():
