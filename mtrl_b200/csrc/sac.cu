@@ -213,6 +213,10 @@ struct mtrl_sac {
   // the output heads ride in the epilogue of the last trunk layer's GEMM (mtrl_gemm_problem_t::head_w): the loss / sampling
   // kernels then read M x head_dim numbers instead of the M x W activation
   bool fused_heads = false;
+  // Polyak target update on a side stream, forked after the critic's Adam step and joined at the end of the update
+  bool defer_polyak = false, polyak_pending = false;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int launches = 0;
   int batch = 0, global_batch = 0;
   // optional CUDA-event bracketing of every GEMM launch (bench.py's live roofline measurement)
@@ -496,6 +500,27 @@ int build_plans(mtrl_sac* h) {
 }
 
 #define LAUNCHED(h) ((h)->launches++)
+
+// The deferred Polyak update (polyak_kernel): fork from `st` behind everything enqueued so far, run on the side stream.
+int fork_polyak(mtrl_sac* h, cudaStream_t st) {
+  const mtrl_net_layout_t& LC = h->lay.critic;
+  MTRL_CUDA_CHECK(cudaEventRecord(h->ev_fork, st));
+  MTRL_CUDA_CHECK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+  polyak_kernel<<<h->sms * 2, 256, 0, h->side>>>(h->buf.critic_params, h->buf.critic_target, h->buf.critic_target_shadow, h->ws.tsh_lo,
+                                                 LC.total, LC.trunk_total, h->cfg.tau);
+  MTRL_CUDA_CHECK(cudaGetLastError());
+  MTRL_CUDA_CHECK(cudaEventRecord(h->ev_join, h->side));
+  h->polyak_pending = true;
+  LAUNCHED(h);
+  return MTRL_OK;
+}
+// ... and `st` continues only after it (end of the update; also before anything else that touches the target).
+int join_polyak(mtrl_sac* h, cudaStream_t st) {
+  if (!h->polyak_pending) return MTRL_OK;
+  MTRL_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_join, 0));
+  h->polyak_pending = false;
+  return MTRL_OK;
+}
 
 // Kernel classes of the event-bracketed profiling pass (mtrl_sac_profile_gemms / _read / _classes).
 enum ProfTag { PT_GEMM = 0, PT_EXCHANGE = 1, PT_ADAM = 2, PT_HEAD_BWD = 3, PT_CRITIC_LOSS = 4, PT_ACTOR_HEAD = 5, PT_ACTOR_LOSS = 6,
@@ -882,6 +907,19 @@ extern "C" int mtrl_sac_create(mtrl_sac_t** out, const mtrl_sac_config_t* cfg, c
   cudaFuncSetAttribute(actor_head_tile_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(actor_head_tile_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(actor_head_tile_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  {
+    // MTRL_DEFER_POLYAK=0: the target update stays inside the critic's Adam kernel / trunk step
+    const char* env = getenv("MTRL_DEFER_POLYAK");
+    h->defer_polyak = !(env && env[0] == '0');
+    if (h->defer_polyak) {
+      if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        h->defer_polyak = false;
+      }
+    }
+  }
   rc = build_plans(h);
   if (rc != MTRL_OK) { mtrl_sac_destroy(h); return rc; }
   rc = mtrl_sac_refresh_shadows(h, nullptr);
@@ -905,6 +943,10 @@ extern "C" void mtrl_sac_destroy(mtrl_sac_t* h) {
     for (auto& launches : *v)
       for (auto* p : launches) mtrl_gemm_plan_destroy(p);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+  if (h->side) cudaStreamSynchronize(h->side);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->side) cudaStreamDestroy(h->side);
   if (h->d_segs_critic) cudaFree(h->d_segs_critic);
   if (h->d_segs_actor) cudaFree(h->d_segs_actor);
   delete h;
@@ -948,6 +990,7 @@ int step_begin(mtrl_sac* h, const float* obs, const float* actions, const float*
   Workspace& w = h->ws;
   const int M = c.max_rows, D = c.depth, T = c.num_local_tasks;
   mtrl_pdl_auto(c.width <= 1024);   // programmatic dependent launch only where the update is launch-latency bound
+  MTRL_PROPAGATE(join_polyak(h, st));   // (an update abandoned between its phases)
   h->launches = 0;
   h->batch = batch;
   h->global_batch = global_batch;
@@ -1090,7 +1133,9 @@ int step_critic_apply(mtrl_sac* h, cudaStream_t st) {
     t.g2_trunk_out = w.acc + ACC_CRITIC_G2; t.p2_trunk = w.acc + ACC_CRITIC_P2_TRUNK; t.p2_head = w.acc + ACC_CRITIC_P2_HEAD;
     t.lr = c.critic_lr; t.b1 = c.adam_b1; t.b2 = c.adam_b2; t.eps = c.adam_eps; t.max_norm = c.critic_max_grad_norm;
     t.tau = c.tau;
+    if (h->defer_polyak) t.target = t.target_shadow = t.target_shadow_lo = nullptr;
     MTRL_PROPAGATE(launch_trunk_step(h, t, h->off_critic_grads, h->off_critic_params, h->d_segs_critic, h->nsegs_critic, st));
+    if (h->defer_polyak) MTRL_PROPAGATE(fork_polyak(h, st));
     mtrl_launch(finalize_critic_kernel, dim3(1), dim3(1), 0, st, w.acc, h->buf.critic_grads + LC.slots_off + 1, h->buf.steps, h->buf.logs, 1.f / EB,
                                             loss_scale, 0);
     LAUNCHED(h);
@@ -1112,10 +1157,12 @@ int step_critic_apply(mtrl_sac* h, cudaStream_t st) {
   a.p2_trunk = w.acc + ACC_CRITIC_P2_TRUNK; a.p2_head = w.acc + ACC_CRITIC_P2_HEAD; a.p2_old = w.acc + ACC_CRITIC_P2_OLD;
   a.lr = c.critic_lr; a.b1 = c.adam_b1; a.b2 = c.adam_b2; a.eps = c.adam_eps; a.max_norm = c.critic_max_grad_norm;
   a.tau = c.tau;
+  if (h->defer_polyak) a.target = a.target_shadow = a.target_shadow_lo = nullptr;
   MTRL_PROPAGATE(prof_begin(h, PT_ADAM, st));
   mtrl_launch(adam_kernel, dim3(h->sms * 4), dim3(256), 0, st, a);
   MTRL_PROPAGATE(prof_end(h, st));
   LAUNCHED(h);
+  if (h->defer_polyak) MTRL_PROPAGATE(fork_polyak(h, st));
   mtrl_launch(finalize_critic_kernel, dim3(1), dim3(1), 0, st, w.acc, h->buf.critic_grads + LC.slots_off, h->buf.steps, h->buf.logs, 1.f / EB,
                                           loss_scale, c.variant == MTRL_VARIANT_SAC);
   LAUNCHED(h);
@@ -1219,7 +1266,14 @@ int step_actor_grads(mtrl_sac* h, cudaStream_t st) {
   return MTRL_OK;
 }
 
+int step_actor_apply_inner(mtrl_sac* h, cudaStream_t st);
+// Last optimiser step of every update variant: the deferred Polyak update rejoins the caller's stream here.
 int step_actor_apply(mtrl_sac* h, cudaStream_t st) {
+  MTRL_PROPAGATE(step_actor_apply_inner(h, st));
+  return join_polyak(h, st);
+}
+
+int step_actor_apply_inner(mtrl_sac* h, cudaStream_t st) {
   const mtrl_sac_config_t& c = h->cfg;
   Workspace& w = h->ws;
   const mtrl_net_layout_t& LA = h->lay.actor;

@@ -1647,6 +1647,33 @@ static __global__ void __launch_bounds__(256, 4) adam_kernel(const AdamArgs a) {
   }
 }
 
+// Polyak target update alone (mtsac.py:607-613): target = tau p + (1 - tau) target and its tf32 operand copies, for the whole
+// flat network except the reduction slots.  Launched on a side stream right after the critic's Adam step, so that it runs
+// under the actor-phase GEMMs instead of on the critical path (nothing reads the target before the next update): few
+// registers and no shared memory, so a block fits on an SM beside a resident GEMM CTA; streaming loads / stores keep the 4 x
+// P bytes it moves from evicting the GEMMs' operand tiles from L2.
+static __global__ void __launch_bounds__(256) polyak_kernel(const float* __restrict__ p, float* __restrict__ target,
+                                                            float* __restrict__ tsh, float* __restrict__ tsh_lo, long long n,
+                                                            long long trunk_n, float tau) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long n4 = n / 4, slot4 = trunk_n / 4;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    if (i >= slot4 && i < slot4 + 8) continue;
+    const float4 p4 = __ldcs(reinterpret_cast<const float4*>(p) + i);
+    float4 t4 = __ldcs(reinterpret_cast<const float4*>(target) + i);
+    t4.x = tau * p4.x + (1.f - tau) * t4.x;
+    t4.y = tau * p4.y + (1.f - tau) * t4.y;
+    t4.z = tau * p4.z + (1.f - tau) * t4.z;
+    t4.w = tau * p4.w + (1.f - tau) * t4.w;
+    __stcs(reinterpret_cast<float4*>(target) + i, t4);
+    const float4 h4 = make_float4(tf32_rna(t4.x), tf32_rna(t4.y), tf32_rna(t4.z), tf32_rna(t4.w));
+    reinterpret_cast<float4*>(tsh)[i] = h4;   // read by the next update's first target GEMM: may stay in L2
+    if (tsh_lo)
+      __stcs(reinterpret_cast<float4*>(tsh_lo) + i,
+             make_float4(tf32_lo(t4.x, h4.x), tf32_lo(t4.y, h4.y), tf32_lo(t4.z, h4.z), tf32_lo(t4.w, h4.w)));
+  }
+}
+
 static __global__ void shadow_kernel(const float* __restrict__ p, float* __restrict__ s, float* __restrict__ s_lo, long long n) {
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
