@@ -98,6 +98,11 @@ int mtrl_gemm_plan_create(mtrl_gemm_plan_t** out, const mtrl_gemm_problem_t* pro
  * bytes per flop, the default), 1 -> 128-row tiles on single CTAs (twice as many, half-size units: better when a launch
  * has too few 256-row units to fill the 74 pairs evenly, e.g. one rank's rows of a task-sharded batch), 0 -> default. */
 int mtrl_gemm_plan_create_ex(mtrl_gemm_plan_t** out, const mtrl_gemm_problem_t* problems, int n, int ctas);
+/* OR-ed into `ctas`: stream-K schedule.  The launch's k-blocks, not its tiles, are dealt evenly to the SMs (every SM gets a
+ * contiguous run of k-blocks that may start and end inside a tile); a tile cut into several units is finished by the unit
+ * that completes last, which adds the others' parked accumulators to its own before the fused epilogue.  For launches of
+ * only a few tiles per SM (one rank's rows of a task-sharded batch, MT10), where whole-tile rounds leave SMs idle. */
+#define MTRL_GEMM_STREAMK 16
 int mtrl_gemm_plan_run(mtrl_gemm_plan_t* plan, void* stream);
 int mtrl_gemm_plan_units(const mtrl_gemm_plan_t* plan);
 /* 2 when the plan runs as CTA pairs (tcgen05 cta_group::2, 256-row tiles), 1 for single-CTA tiles. */

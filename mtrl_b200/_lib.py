@@ -33,6 +33,7 @@ class GemmProblem(C.Structure):
 
 
 EPI_STORE, EPI_BIAS_RELU, EPI_RELU_MASK, EPI_ATOMIC_ADD, EPI_STORE_TF32 = range(5)
+GEMM_STREAMK = 16   # OR-ed into GemmPlan(ctas=...): stream-K schedule (MTRL_GEMM_STREAMK)
 
 
 ABI_VERSION = 6   # mtrl_abi_version() of the library these ctypes structures were written for

@@ -56,6 +56,7 @@ constexpr int kThreads = 64 + 32 * kEpilogueWarps;
 constexpr int kEpiBoxBytes = 32 * 32 * 4;
 constexpr int kEpiStageBytes = kEpilogueWarps * 2 * kEpiBoxBytes;   // 64 KB
 constexpr int kEpiBiasBytes = kEpilogueWarps * 512;                 // 4 KB
+constexpr int kFixSlabFloats = kEpilogueWarps * 4 * 8 * 32 * 4;   // one CTA's parked accumulator (stream-K): 128 x 256 floats
 constexpr int kMaxHeadDim = 8;
 constexpr int kEpiHeadBytes = kEpilogueWarps * 32 * kMaxHeadDim * 4;   // 8 KB: one box's (32 columns x head_dim) head weights per warp
 
@@ -129,14 +130,33 @@ struct GemmParams {
   // monotonic over launches: a launch adds exactly gridDim.x tickets to each) after its TMA stores have completed.
   int nphases;
   unsigned long long* phase_cnt;
+  // Stream-K plans (MTRL_GEMM_STREAMK): the schedule's entries index unit_tab, explicit {problem, tile, kb0 | kb1 << 16, fix} units
+  // whose k-ranges cut the launch's k-blocks evenly over the workers instead of whole tiles.  A tile cut into `pieces` units whose
+  // epilogue is not a plain accumulation (fix >= 0) is finished by whichever unit completes LAST: the others park their raw
+  // accumulators in fix_ws and count themselves in fix_cnt; the last one adds them to its own before the fused epilogue.
+  const int4* unit_tab;
+  const int4* fix_tab;      // [fix] = {pieces, slab offset in floats (lo, hi), 0}
+  float* fix_ws;
+  unsigned* fix_cnt;        // [fix][cta of the pair][4] = {arrived, parked (x epilogue warps), consumed, -}
 };
 
 struct UnitCoord {
-  int p, m_tile, n_tile, kb0, kb1;
+  int p, m_tile, n_tile, kb0, kb1, fix;
 };
 
 __device__ __forceinline__ UnitCoord decode_unit(const DevProblem* __restrict__ probs, int nprob,
-                                                 int unit) {
+                                                 int unit, const int4* __restrict__ unit_tab = nullptr) {
+  if (unit_tab) {
+    const int4 e = __ldg(unit_tab + unit);
+    UnitCoord c;
+    c.p = e.x;
+    c.n_tile = e.y % probs[e.x].n_tiles;
+    c.m_tile = e.y / probs[e.x].n_tiles;
+    c.kb0 = e.z & 0xFFFF;
+    c.kb1 = static_cast<int>(static_cast<unsigned>(e.z) >> 16);
+    c.fix = e.w;
+    return c;
+  }
   int p = 0;
   while (p + 1 < nprob && unit >= probs[p + 1].unit_begin) ++p;
   const DevProblem& P = probs[p];
@@ -149,6 +169,7 @@ __device__ __forceinline__ UnitCoord decode_unit(const DevProblem* __restrict__ 
   int split = u / P.m_tiles;
   c.kb0 = split * P.kb_per_split;
   c.kb1 = min(P.kb_total, c.kb0 + P.kb_per_split);
+  c.fix = -1;
   return c;
 }
 
@@ -199,6 +220,7 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
   const uint32_t phase_bar = bar_base + 8u * (2 * kStages + 5);   // epilogue leader -> producer: the grid passed the phase barrier
+  const uint32_t fix_slot = bar_base + 8u * (2 * kStages + 6);    // two 4-byte ticket slots (stream-K fix-up), alternating per unit
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -256,7 +278,7 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
       }
       for (int si = sched_off[ph]; si < sched_off[ph + 1]; ++si) {
         const int unit = sched_units[si];
-        const UnitCoord c = decode_unit(probs, nprob, unit);
+        const UnitCoord c = decode_unit(probs, nprob, unit, params.unit_tab);
         const DevProblem& P = probs[c.p];
         const CUtensorMap* mapA0 = maps + kMapsPer * c.p;
         const int n_cta = P.block_n / kCtas;                       // B columns staged by this CTA
@@ -331,7 +353,7 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
       long long t_wfull = 0, t_wtempty = 0, t_issue = 0, t_total0 = params.dbg ? clock64() : 0;
       for (int si = sched_off[0]; si < sched_off[nphases]; ++si) {   // the issuer is paced by the producer: no phase logic here
         const int unit = sched_units[si];
-        const UnitCoord c = decode_unit(probs, nprob, unit);
+        const UnitCoord c = decode_unit(probs, nprob, unit, params.unit_tab);
         const DevProblem& P = probs[c.p];
         const uint32_t idesc = P.idesc;
         // K-major (SWIZZLE_128B): rows are 128 B, 8-row swizzle atoms 1024 B apart (SBO);
@@ -414,11 +436,12 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t nbox = 0;  // running count of TMA boxes this warp has issued (selects the staging buffer)
+    uint32_t nfix = 0;  // stream-K fix-up units seen so far (selects the ticket slot)
     long long t_wait = 0, t_work = 0;
     for (int ph = 0; ph < nphases; ++ph) {
     for (int si = sched_off[ph]; si < sched_off[ph + 1]; ++si) {
         const int unit = sched_units[si];
-      const UnitCoord c = decode_unit(probs, nprob, unit);
+      const UnitCoord c = decode_unit(probs, nprob, unit, params.unit_tab);
       const DevProblem& P = probs[c.p];
       const CUtensorMap* mapD = maps + kMapsPer * c.p + 2;
       const CUtensorMap* mapDlo = maps + kMapsPer * c.p + 5;
@@ -492,6 +515,45 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                              static_cast<uint32_t>(acc) * kMaxBlockN;
+      // Stream-K fix-up (this unit is one of `fix_pieces` k-ranges of its tile and the epilogue is not a plain accumulation):
+      // one ticket per CTA once the accumulator is complete; the LAST unit to arrive finishes the tile (fix_role 2), the others
+      // park their raw accumulators (fix_role 1).  Nobody waits for a unit that has not arrived yet, so the static schedule
+      // cannot deadlock; the finisher only waits for units already in their epilogue.
+      int fix_role = 0, fix_pieces = 0;
+      float* fix_slab = nullptr;
+      unsigned* fix_cnt = nullptr;
+      if (c.fix >= 0) {
+        const int4 fi = __ldg(params.fix_tab + c.fix);
+        fix_pieces = fi.x;
+        fix_cnt = params.fix_cnt + (static_cast<long long>(c.fix) * kCtas + rank) * 4;
+        const uint32_t slot = fix_slot + 4u * (nfix & 1u);
+        if (warp == 2 && lane == 0) {
+          const unsigned t = atomicAdd(fix_cnt, 1u);
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(slot), "r"(t) : "memory");
+        }
+        asm volatile("bar.sync 2, %0;" ::"n"(32 * kEpilogueWarps) : "memory");
+        unsigned ticket;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ticket) : "r"(slot) : "memory");
+        ++nfix;
+        fix_role = static_cast<int>(ticket) == fix_pieces - 1 ? 2 : 1;
+        const long long slab_off = (static_cast<long long>(static_cast<unsigned>(fi.z)) << 32) | static_cast<unsigned>(fi.y);
+        // slabs: [piece][cta of the pair][kFixSlabFloats]
+        fix_slab = params.fix_ws + slab_off + static_cast<long long>(rank) * kFixSlabFloats;
+        if (fix_role == 1) {
+          fix_slab += static_cast<long long>(ticket) * kCtas * kFixSlabFloats;
+        } else {
+          // every earlier arrival has parked all of its eight warps' boxes
+          if (lane == 0) {
+            const unsigned want = static_cast<unsigned>(fix_pieces - 1) * kEpilogueWarps;
+            const long long t_spin = clock64();
+            unsigned seen;
+            do {
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(fix_cnt + 1) : "memory");
+            } while (seen < want && clock64() - t_spin < (1ll << 31));   // bounded: a logic error must not hang the GPU
+          }
+          __syncwarp();
+        }
+      }
       if (epi == MTRL_EPI_BIAS_RELU) {
         // this warp's (<= 128) bias values, staged once per tile
         const int col = n0 + cbeg + 4 * lane;
@@ -535,6 +597,26 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
           for (int i = 0; i < 16; ++i) {
             o[i] += __uint_as_float(v0[i]);
             if (ncols == 32) o[16 + i] += __uint_as_float(v1[i]);
+          }
+        }
+        if (fix_role) {
+          // slab layout [epilogue warp][box][16-byte piece j][lane]: every load / store instruction moves 512 contiguous bytes
+          float4* fp = reinterpret_cast<float4*>(fix_slab) + ((ew * 4 + bi) * 8) * 32 + lane;
+          if (fix_role == 1) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (4 * j < ncols) __stcg(fp + j * 32, make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]));
+            continue;   // nothing else for a parked unit: no fused op, no output, no staging box
+          }
+          for (int piece = 0; piece + 1 < fix_pieces; ++piece) {
+            const float4* sp = fp + static_cast<long long>(piece) * kCtas * (kFixSlabFloats / 4);
+            float4 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = 4 * j < ncols ? __ldcg(sp + j * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              o[4 * j] += v[j].x; o[4 * j + 1] += v[j].y; o[4 * j + 2] += v[j].z; o[4 * j + 3] += v[j].w;
+            }
           }
         }
         const int col0 = n0 + cc;
@@ -704,10 +786,23 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
       if (lane == 0) {
         if (kCtas == 2) mbar_arrive_cluster(tempty_bar(acc), 0); else mbar_arrive(tempty_bar(acc));
       }
-      if (hd && row_ok && cbeg < cend) {
+      if (hd && row_ok && cbeg < cend && fix_role != 1) {
 #pragma unroll
         for (int j = 0; j < kMaxHeadDim; ++j)
           if (j < hd) atomicAdd(P.head_out + static_cast<long long>(row) * hd + j, hs[j]);
+      }
+      if (fix_role == 1) {
+        __threadfence();   // this warp's parked boxes are visible before it counts itself in
+        __syncwarp();
+        if (lane == 0) atomicAdd(fix_cnt + 1, 1u);
+      } else if (fix_role == 2) {
+        __syncwarp();
+        if (lane == 0 && atomicAdd(fix_cnt + 2, 1u) == kEpilogueWarps - 1) {
+          // the last warp of the finisher re-arms the counters for the next launch of this plan
+          fix_cnt[0] = 0u;
+          fix_cnt[1] = 0u;
+          fix_cnt[2] = 0u;
+        }
       }
       if (params.dbg) t_work += clock64() - t1;
       if (++acc == 2) {
@@ -823,9 +918,17 @@ struct mtrl_gemm_plan {
   int ctas = 1;  // 1: one CTA per tile; 2: CTA pairs (cta_group::2)
   int* d_sched = nullptr;
   unsigned long long* d_phase_cnt = nullptr;
+  int4 *d_unit_tab = nullptr, *d_fix_tab = nullptr;   // stream-K plans only
+  float* d_fix_ws = nullptr;
+  unsigned* d_fix_cnt = nullptr;
+  bool streamk = false;
   ~mtrl_gemm_plan() {
     if (d_sched) cudaFree(d_sched);
     if (d_phase_cnt) cudaFree(d_phase_cnt);
+    if (d_unit_tab) cudaFree(d_unit_tab);
+    if (d_fix_tab) cudaFree(d_fix_tab);
+    if (d_fix_ws) cudaFree(d_fix_ws);
+    if (d_fix_cnt) cudaFree(d_fix_cnt);
   }
 };
 
@@ -845,6 +948,8 @@ extern "C" int mtrl_gemm_plan_create(mtrl_gemm_plan_t** out, const mtrl_gemm_pro
 extern "C" int mtrl_gemm_plan_create_ex(mtrl_gemm_plan_t** out, const mtrl_gemm_problem_t* problems, int n, int ctas_req) {
   MTRL_REQUIRE(out && problems && n >= 1 && n <= kMaxProblems,
                "mtrl_gemm_plan_create: need 1..%d problems per launch, got %d", kMaxProblems, n);
+  const bool streamk = (ctas_req & MTRL_GEMM_STREAMK) != 0;
+  ctas_req &= ~MTRL_GEMM_STREAMK;
   MTRL_REQUIRE(ctas_req >= 0 && ctas_req <= 2, "mtrl_gemm_plan_create_ex: ctas %d outside {0, 1, 2}", ctas_req);
   int dev_id = 0, sms = 148;
   cudaGetDevice(&dev_id);
@@ -990,9 +1095,122 @@ extern "C" int mtrl_gemm_plan_create_ex(mtrl_gemm_plan_t** out, const mtrl_gemm_
   P.nphases = nphases;
   const int workers = sms / ctas;
   // with phases every CTA must be resident at once (they meet at in-kernel barriers): never more workers than CTA slots
-  const int nworkers = units < workers ? units : workers;
+  const int nworkers = (units < workers && !streamk) ? units : workers;
   plan->grid = nworkers * ctas;
-  {
+  plan->streamk = streamk;
+  if (streamk) {
+    // Stream-K: per phase, the k-blocks of all tiles (weighted by tile width) are laid end to end and cut into `nworkers` equal
+    // shares; a worker's share is a run of whole tiles with at most one partial tile at either end.  Pieces shorter than
+    // kMinPiece k-blocks are not cut off (the neighbour keeps them), so shares differ by a few k-blocks at most.
+    constexpr int kMinPiece = 4;
+    struct Piece { int p, tile, kb0, kb1; };
+    std::vector<int4> unit_tab, fix_tab;
+    std::vector<std::vector<int>> lists(static_cast<size_t>(nworkers) * nphases);
+    long long ws_floats = 0;
+    for (int ph = 0; ph < nphases; ++ph) {
+      struct Tile { int p, tile, kb0, kb1; long long w; };
+      std::vector<Tile> tiles;
+      long long total = 0;
+      for (int i = 0; i < n; ++i) {
+        if (problems[i].phase != ph) continue;
+        const DevProblem& d = P.probs[i];
+        MTRL_REQUIRE(d.kb_total < 65536, "problem %d: K too long for a stream-K plan", i);
+        const long long w = (d.block_n > 160 ? d.block_n : 160) * (d.x3 ? 3 : 1);
+        for (int t = 0; t < d.m_tiles * d.n_tiles; ++t)
+          for (int sp = 0; sp < d.k_splits; ++sp) {   // existing split-K units (accumulating epilogue) stay separate runs
+            const int kb0 = sp * d.kb_per_split, kb1 = std::min(d.kb_total, kb0 + d.kb_per_split);
+            tiles.push_back({i, t, kb0, kb1, w});
+            total += (kb1 - kb0) * w;
+          }
+      }
+      if (tiles.empty()) continue;
+      // (no per-unit constant here, unlike the LPT cost model: every worker ends up with about the same number of units, and
+      // a constant that the running sum counts per UNIT but the total per TILE would starve the last worker's predecessors)
+      const long long overhead = 0;
+      size_t ti = 0;
+      int kb = tiles[0].kb0;
+      long long done = 0;
+      for (int wk = 0; wk < nworkers && ti < tiles.size(); ++wk) {
+        const long long target = total * (wk + 1) / nworkers;   // cumulative boundary: rounding never accumulates
+        while (ti < tiles.size() && (done < target || wk == nworkers - 1)) {
+          const Tile& t = tiles[ti];
+          const long long room = target - done;
+          int take = t.kb1 - kb;
+          if (wk != nworkers - 1 && (take * t.w + overhead) > room) {
+            take = static_cast<int>((room - overhead) / t.w);
+            if (take < kMinPiece) break;                              // not worth a unit: the next worker starts here
+            if (t.kb1 - (kb + take) < kMinPiece) take = t.kb1 - kb;   // do not leave a sliver behind
+          }
+          const bool whole = kb == t.kb0 && kb + take == t.kb1;
+          unit_tab.push_back(make_int4(t.p, t.tile, kb | ((kb + take) << 16), whole ? -1 : -2 - static_cast<int>(ti)));
+          lists[static_cast<size_t>(wk) * nphases + ph].push_back(static_cast<int>(unit_tab.size()) - 1);
+          done += take * t.w + overhead;
+          kb += take;
+          if (kb == t.kb1) {
+            ++ti;
+            if (ti < tiles.size()) kb = tiles[ti].kb0;
+          }
+        }
+      }
+      MTRL_REQUIRE(ti == tiles.size(), "stream-K schedule left %zu tiles unassigned", tiles.size() - ti);
+      // pieces of one tile: accumulate-only epilogues need no fix-up (fix = -1); the others share a fix entry
+      std::vector<int> npieces(tiles.size(), 0), fix_of(tiles.size(), -1);
+      for (const int4& u : unit_tab)
+        if (u.w <= -2) npieces[-2 - u.w]++;
+      for (int4& u : unit_tab) {
+        if (u.w > -2) continue;
+        const int t = -2 - u.w;
+        const DevProblem& d = P.probs[tiles[t].p];
+        if (d.epilogue == MTRL_EPI_ATOMIC_ADD) { u.w = -1; continue; }
+        if (fix_of[t] < 0) {
+          fix_of[t] = static_cast<int>(fix_tab.size());
+          fix_tab.push_back(make_int4(npieces[t], static_cast<int>(ws_floats & 0xFFFFFFFFll), static_cast<int>(ws_floats >> 32), 0));
+          ws_floats += static_cast<long long>(npieces[t] - 1) * ctas * kFixSlabFloats;
+        }
+        u.w = fix_of[t];
+      }
+      for (int4& u : unit_tab)
+        if (u.w <= -2) u.w = -1;   // (units of earlier phases are already resolved; nothing left at <= -2 here)
+    }
+    P.total_units = static_cast<int>(unit_tab.size());
+    if (getenv("MTRL_GEMM_STREAMK_DUMP")) {
+      for (int wk = 0; wk < nworkers; ++wk)
+        for (int ph = 0; ph < nphases; ++ph) {
+          fprintf(stderr, "[stream-K] worker %d phase %d:", wk, ph);
+          for (int u : lists[static_cast<size_t>(wk) * nphases + ph]) {
+            const int4 e = unit_tab[u];
+            fprintf(stderr, " (p%d t%d kb %d-%d fix %d)", e.x, e.y, e.z & 0xFFFF, static_cast<unsigned>(e.z) >> 16, e.w);
+          }
+          fprintf(stderr, "\n");
+        }
+      for (size_t f = 0; f < fix_tab.size(); ++f) fprintf(stderr, "[stream-K] fix %zu: pieces %d\n", f, fix_tab[f].x);
+    }
+    std::vector<int> table(static_cast<size_t>(nworkers) * nphases + 1 + unit_tab.size());
+    int off = 0;
+    for (size_t k = 0; k < lists.size(); ++k) {
+      table[k] = off;
+      for (int u : lists[k]) table[static_cast<size_t>(nworkers) * nphases + 1 + off++] = u;
+    }
+    table[static_cast<size_t>(nworkers) * nphases] = off;
+    MTRL_CUDA_CHECK(cudaMalloc(&plan->d_sched, table.size() * sizeof(int)));
+    MTRL_CUDA_CHECK(cudaMemcpy(plan->d_sched, table.data(), table.size() * sizeof(int), cudaMemcpyHostToDevice));
+    P.sched = plan->d_sched;
+    MTRL_CUDA_CHECK(cudaMalloc(&plan->d_phase_cnt, kMaxPhases * sizeof(unsigned long long)));
+    MTRL_CUDA_CHECK(cudaMemset(plan->d_phase_cnt, 0, kMaxPhases * sizeof(unsigned long long)));
+    P.phase_cnt = plan->d_phase_cnt;
+    MTRL_CUDA_CHECK(cudaMalloc(&plan->d_unit_tab, std::max<size_t>(unit_tab.size(), 1) * sizeof(int4)));
+    MTRL_CUDA_CHECK(cudaMemcpy(plan->d_unit_tab, unit_tab.data(), unit_tab.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    P.unit_tab = plan->d_unit_tab;
+    MTRL_CUDA_CHECK(cudaMalloc(&plan->d_fix_tab, std::max<size_t>(fix_tab.size(), 1) * sizeof(int4)));
+    MTRL_CUDA_CHECK(cudaMemcpy(plan->d_fix_tab, fix_tab.data(), fix_tab.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    P.fix_tab = plan->d_fix_tab;
+    MTRL_CUDA_CHECK(cudaMalloc(&plan->d_fix_ws, std::max<long long>(ws_floats, 4) * sizeof(float)));
+    P.fix_ws = plan->d_fix_ws;
+    const size_t cnt_bytes = std::max<size_t>(fix_tab.size(), 1) * ctas * 4 * sizeof(unsigned);
+    MTRL_CUDA_CHECK(cudaMalloc(&plan->d_fix_cnt, cnt_bytes));
+    MTRL_CUDA_CHECK(cudaMemset(plan->d_fix_cnt, 0, cnt_bytes));
+    P.fix_cnt = plan->d_fix_cnt;
+  } else {
     // Longest-processing-time-first assignment, phase by phase.  Unit cost ~ k-blocks x tile width (narrow tiles are
     // bounded by the per-k-block TMA / issue latency, not by the MMA) + a constant for prologue and epilogue drain.
     // Units of equal cost keep their index order, so a launch of uniform units degenerates to the round-robin it

@@ -171,18 +171,25 @@ inline int make_plan(std::vector<mtrl_gemm_plan_t*>& dst, const std::vector<mtrl
   float best_ms = 0.f;
   int rc = MTRL_OK;
   const char* force = getenv("MTRL_GEMM_CTAS");
-  const int kinds[2] = {2, 1};
+  // MTRL_GEMM_STREAMK=1 adds the stream-K schedule (default tile width) of either kind to the candidates.  Off by default:
+  // at every shape probed (profiles/r02_streamk_probe_*.txt) its fix-up -- the last unit of a cut tile reads the parked
+  // partial accumulators before the fused epilogue, on the launch's critical path -- costs more than the idle SMs it fills.
+  const bool try_streamk = getenv("MTRL_GEMM_STREAMK") && getenv("MTRL_GEMM_STREAMK")[0] == '1';
+  const int kinds[4] = {2, 1, 2 | MTRL_GEMM_STREAMK, 1 | MTRL_GEMM_STREAMK};
   const int cands[4] = {0, 192, 128, 64};   // 0 = the caller's default
-  for (int kind : kinds) {
+  for (int kind_flags : kinds) {
+    const int kind = kind_flags & ~MTRL_GEMM_STREAMK;
+    if ((kind_flags & MTRL_GEMM_STREAMK) && !try_streamk) continue;
     if (force && (force[0] == '1' || force[0] == '2') && force[0] - '0' != kind) continue;
     for (int cand : cands) {
+      if ((kind_flags & MTRL_GEMM_STREAMK) && cand != 0) continue;
       std::vector<mtrl_gemm_problem_t> q = probs;
       bool changed = cand == 0;
       for (auto& p : q)
         if (cand && p.N >= 256 && p.block_n > cand) { p.block_n = cand; changed = true; }
       if (!changed) continue;
       mtrl_gemm_plan_t* plan = nullptr;
-      rc = mtrl_gemm_plan_create_ex(&plan, q.data(), static_cast<int>(q.size()), kind);
+      rc = mtrl_gemm_plan_create_ex(&plan, q.data(), static_cast<int>(q.size()), kind_flags);
       if (rc != MTRL_OK) break;
       if (mtrl_gemm_plan_ctas(plan) != kind) {   // an odd SM count turns pairs into single CTAs: already covered
         mtrl_gemm_plan_destroy(plan);

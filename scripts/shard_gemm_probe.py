@@ -78,19 +78,21 @@ for name, make in GROUPS.items():
     if only and only not in name:
         continue
     print(f"== {name}: rows {rows}, width {W}")
-    for ctas in (2, 1):
-        for bn in (256, 224, 192, 160, 128, 96, 64):
-            if bn > W:
-                continue
-            keep.clear()
-            probs, flops = make(bn)
-            try:
-                plan = L.GemmPlan(probs, ctas=ctas)
-            except Exception as e:  # noqa: BLE001
-                print(f"   ctas {ctas} block_n {bn}: {e}")
-                continue
-            us = timeit(plan)
-            workers = 148 // plan.ctas
-            print(f"   ctas {plan.ctas} block_n {bn:3d}: {us:7.1f} us  {flops / us / 1e6:6.0f} TFLOP/s  units {plan.units:4d} "
-                  f"({plan.units / workers:5.2f} rounds)  ideal {flops / PEAK / 1e6:5.1f} us")
-            del plan
+    widths = [int(x) for x in os.environ.get("PROBE_WIDTHS", "256,224,192,160,128,96,64").split(",")]
+    for sk in (0, L.GEMM_STREAMK):
+        for ctas in (2, 1):
+            for bn in widths:
+                if bn > W:
+                    continue
+                keep.clear()
+                probs, flops = make(bn)
+                try:
+                    plan = L.GemmPlan(probs, ctas=ctas | sk)
+                except Exception as e:  # noqa: BLE001
+                    print(f"   ctas {ctas} block_n {bn}: {e}")
+                    continue
+                us = timeit(plan)
+                workers = 148 // plan.ctas
+                print(f"   {'stream-K' if sk else 'tiles   '} ctas {plan.ctas} block_n {bn:3d}: {us:7.1f} us  {flops / us / 1e6:6.0f} TFLOP/s  units "
+                      f"{plan.units:4d} ({plan.units / workers:5.2f} per worker)  ideal {flops / PEAK / 1e6:5.1f} us")
+                del plan

@@ -260,3 +260,73 @@ def test_fused_output_head_fp32x3(cuda):
     want = torch.cat([full[128 * i:128 * (i + 1)] @ head_w[int(tile_task[i])].double() for i in range(2)])
     err = float((out.double() - want).norm() / want.norm())
     assert err < 2e-6, f"fused head (fp32x3) rel err {err}"
+
+
+# ---------------------------------------------------------------------------------------------
+# Stream-K plans (MTRL_GEMM_STREAMK): k-ranges instead of whole tiles; cut tiles are finished by the last unit to arrive.
+# ---------------------------------------------------------------------------------------------
+STREAMK_EXTRA = [
+    # few tiles, long K: every tile is cut into many pieces (store, bias + ReLU, ReLU mask, rounding store)
+    ("sk_kk_store_longk", 256, 256, 4096, 0, 0, 0, 256, 1),
+    ("sk_fwd_longk", 384, 512, 2048, 0, 1, 1, 256, 1),
+    ("sk_dx_mask_longk", 384, 512, 2048, 0, 0, 2, 256, 1),
+    ("sk_store_tf32", 256, 384, 1024, 0, 0, 4, 128, 1),
+    # a shard-like launch: 7 row tiles x 8 column tiles, K = 2048
+    ("sk_shard_fwd", 896, 2048, 2048, 0, 1, 1, 256, 1),
+    ("sk_dw_splitk", 512, 512, 1280, 1, 1, 3, 256, 3),
+]
+
+
+@pytest.mark.parametrize("ctas", [2, 1])
+@pytest.mark.parametrize("idx", range(16 + len(STREAMK_EXTRA)))
+def test_gemm_case_streamk(cuda, idx, ctas):
+    import gemm_cases as G
+    from mtrl_b200 import _lib as L
+
+    case = (G.CASES + STREAMK_EXTRA)[idx]
+    for rep in range(2):   # the second launch runs on the counters the first one re-armed
+        rel, _ = G.run_case(case, ctas=ctas | L.GEMM_STREAMK)
+        assert rel < 5e-4, f"{case[0]} (stream-K, ctas {ctas}, launch {rep}): rel err {rel}"
+
+
+@pytest.mark.parametrize("ctas", [2, 1])
+def test_streamk_repeated_launches_and_fused_extras(cuda, ctas):
+    """One stream-K plan launched repeatedly (counters re-armed by the finishers), with everything the fused epilogues emit:
+    ReLU bits, the fused output head (accumulated once per tile, by the finisher only), column-sum partials."""
+    import torch
+
+    import gemm_cases as G
+    from mtrl_b200 import _lib as L
+
+    M, N, K, hd = 640, 512, 1536, 8
+    p, D, ref, keep = G.make_problem(M, N, K, 0, 1, L.EPI_BIAS_RELU, 256, 1, seed=11)
+    head_w = torch.randn(3, N, hd, generator=torch.Generator().manual_seed(2)).cuda()
+    tile_task = torch.tensor([i % 3 for i in range(M // 128)], dtype=torch.int32, device="cuda")
+    out = torch.zeros(M, hd, device="cuda")
+    bits = torch.zeros(M, N // 32, dtype=torch.int32, device="cuda")
+    p.head_w, p.head_out, p.head_tile_task, p.head_dim = head_w.data_ptr(), out.data_ptr(), tile_task.data_ptr(), hd
+    p.relu_bits_out, p.ldbits = bits.data_ptr(), N // 32
+    q, Dq, refq, keepq = G.make_problem(M, N, K, 0, 0, L.EPI_RELU_MASK, 256, 1, seed=12)
+    cs = torch.zeros((M + 31) // 32, N, device="cuda")
+    q.colsum_partial = cs.data_ptr()
+    plan = L.GemmPlan([p, q], ctas=ctas | L.GEMM_STREAMK)
+    for _ in range(3):   # (which unit finishes a tile depends on arrival order, so launches agree to rounding, not bit for bit)
+        out.zero_()
+        plan.run()
+        torch.cuda.synchronize()
+        assert G.rel_err(D, ref, L.EPI_BIAS_RELU)[0] < 5e-4 and G.rel_err(Dq, refq, L.EPI_RELU_MASK)[0] < 5e-4
+        want = torch.cat([D[128 * i:128 * (i + 1)].double() @ head_w[int(tile_task[i])].double() for i in range(M // 128)])
+        assert float((out.double() - want).norm() / want.norm()) < 2e-6
+        want_bits = (D > 0).view(M, N // 32, 32).to(torch.int64).mul(2 ** torch.arange(32, device="cuda")).sum(-1)
+        assert torch.equal(bits.to(torch.int64) & 0xFFFFFFFF, want_bits)
+        want_cs = Dq.view((M + 31) // 32, 32, N).double().sum(1)
+        assert float((cs.double() - want_cs).norm() / want_cs.norm()) < 1e-5
+
+
+def test_streamk_fp32x3(cuda):
+    import gemm_cases as G
+    from mtrl_b200 import _lib as L
+
+    for case in (G.CASES[3], G.CASES[8], ("sk_x3_longk", 256, 384, 2048, 0, 1, 1, 128, 1)):
+        rel, _, _ = G.run_case_x3(case, ctas=2 | L.GEMM_STREAMK)
+        assert rel < 3e-6, f"{case[0]} fp32x3 stream-K: rel err {rel}"
