@@ -599,7 +599,8 @@ def main() -> None:
         Mrows, od = B_local if (world > 1 or emulate) else B, 39 + T
         alg = {"adam_polyak": 32.0 * (Pa + Pc) + 8.0 * Pc, "head_vjp": (4 * E + 2) * Mrows * W * 4.0, "critic_loss": 2 * E * Mrows * W * 4.0,
                "actor_loss": E * Mrows * W * 4.0, "actor_head": 2 * Mrows * W * 4.0, "grad_norms": 4.0 * (Pa + Pc)}
-        if os.environ.get("MTRL_DEFER_POLYAK", "1") != "0":
+        polyak_side = os.environ.get("MTRL_DEFER_POLYAK", "1" if (world == 1 and not emulate) else "0") != "0"
+        if polyak_side:
             # the Polyak update (8 P_critic of SURVEY's bytes) runs on a side stream under the actor-phase GEMMs
             alg["adam_polyak"] = 32.0 * (Pa + Pc)
         fused_heads = os.environ.get("MTRL_FUSED_HEADS", "1") != "0"
@@ -621,7 +622,7 @@ def main() -> None:
                     "frac_of_hbm_peak": samp_bytes / (sampler_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                     "note": "latency-bound: 9.4 MB per step; includes the Python call overhead of sample()"})
         line["hbm_kernels"] = {"peak_gbs": peaks["hbm_gbs"], "peak_source": peaks["_source"] + " copy bandwidth", "kernels": hbm,
-                               "fused_heads": fused_heads, "polyak_on_side_stream": os.environ.get("MTRL_DEFER_POLYAK", "1") != "0",
+                               "fused_heads": fused_heads, "polyak_on_side_stream": polyak_side,
                                "other_classes_ms_per_step": {k: v[0] / args.steps for k, v in classes.items() if k not in alg and k != "gemm"}}
         if emulate:
             line["config"]["emulated_shard_of"] = emulate

@@ -908,9 +908,12 @@ extern "C" int mtrl_sac_create(mtrl_sac_t** out, const mtrl_sac_config_t* cfg, c
   cudaFuncSetAttribute(actor_head_tile_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(actor_head_tile_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   {
-    // MTRL_DEFER_POLYAK=0: the target update stays inside the critic's Adam kernel / trunk step
+    // Default: on an unsharded handle (same-box A/B: -1 % step time at MT50/W2048, -1...4 % at MT10/W1024).  On a task shard the
+    // kernel still walks the WHOLE replicated critic while the rank's GEMM launches are 1/N as long: it shortens the exchange
+    // kernels (8 GPUs: 0.337 -> 0.305 ms) but slows the GEMMs it runs under by more (862.7 -> 849.1 updates/s), so there the
+    // target update stays inside the trunk step.  MTRL_DEFER_POLYAK=0|1 forces either.
     const char* env = getenv("MTRL_DEFER_POLYAK");
-    h->defer_polyak = !(env && env[0] == '0');
+    h->defer_polyak = env ? env[0] != '0' : cfg->num_local_tasks == cfg->num_tasks;
     if (h->defer_polyak) {
       if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
           cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
