@@ -103,6 +103,12 @@ int mtrl_gemm_plan_create_ex(mtrl_gemm_plan_t** out, const mtrl_gemm_problem_t* 
  * that completes last, which adds the others' parked accumulators to its own before the fused epilogue.  For launches of
  * only a few tiles per SM (one rank's rows of a task-sharded batch, MT10), where whole-tile rounds leave SMs idle. */
 #define MTRL_GEMM_STREAMK 16
+/* OR-ed into `ctas`: the phases of the launch are ordered by per-row-tile dependencies instead of grid-wide barriers.  Every
+ * problem of phase p > 0 must take as its (K-major) A operand the D of one problem of phase p - 1 with the same rows (the next
+ * Dense layer of the same network pass); a tile of it starts as soon as the producing problem has stored every column tile of
+ * those rows, so SMs that run out of tiles of one layer continue with the next instead of idling at a barrier -- for chains of
+ * short layers (few rows: MT10, one rank's share of a sharded batch) whose tile count does not fill whole rounds of SMs. */
+#define MTRL_GEMM_ROWDEPS 32
 int mtrl_gemm_plan_run(mtrl_gemm_plan_t* plan, void* stream);
 int mtrl_gemm_plan_units(const mtrl_gemm_plan_t* plan);
 /* 2 when the plan runs as CTA pairs (tcgen05 cta_group::2, 256-row tiles), 1 for single-CTA tiles. */

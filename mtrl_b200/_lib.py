@@ -34,6 +34,7 @@ class GemmProblem(C.Structure):
 
 EPI_STORE, EPI_BIAS_RELU, EPI_RELU_MASK, EPI_ATOMIC_ADD, EPI_STORE_TF32 = range(5)
 GEMM_STREAMK = 16   # OR-ed into GemmPlan(ctas=...): stream-K schedule (MTRL_GEMM_STREAMK)
+GEMM_ROWDEPS = 32   # ... phases ordered by per-row-tile dependencies instead of grid barriers (MTRL_GEMM_ROWDEPS)
 
 
 ABI_VERSION = 6   # mtrl_abi_version() of the library these ctypes structures were written for

@@ -92,6 +92,8 @@ struct __align__(16) DevProblem {
   int tma_out;   // output goes through smem staging + TMA store / reduce-add (needs block_n % 32 == 0)
   int x3;        // fp32x3: > 0 = k-blocks per chunk (maps 3 / 4 = A_lo / B_lo); every chunk is a MAIN and a SMALL sub-unit
   int d_lo;      // the epilogue also stores the tf32 remainder of the unrounded output through map 5
+  int dep_prob;  // row-dependency plans: the problem whose D is this problem's A operand (-1: none)
+  int sig_base;  // ... and, when other problems read this problem's D: first of its per-row-tile completion counters (-1: none)
   int head_dim;  // fused output head (bias+ReLU epilogue): 0 = none
   const float* head_w;      // (tasks, N, head_dim)
   float* head_out;          // [M][head_dim], accumulated with atomics
@@ -134,6 +136,13 @@ struct GemmParams {
   // whose k-ranges cut the launch's k-blocks evenly over the workers instead of whole tiles.  A tile cut into `pieces` units whose
   // epilogue is not a plain accumulation (fix >= 0) is finished by whichever unit completes LAST: the others park their raw
   // accumulators in fix_ws and count themselves in fix_cnt; the last one adds them to its own before the fused epilogue.
+  // Row-dependency plans (MTRL_GEMM_ROWDEPS): no grid barrier between phases.  A unit of a later phase starts as soon as the
+  // row tile of its A operand is complete: every epilogue warp of a producing unit adds one to row_cnt[sig_base + m_tile] once its
+  // bulk stores have landed; the TMA producer of a consuming unit waits for (launches so far + 1) x arrivals per launch.  Counters
+  // are monotonic over launches (launch_cnt gives the generation), so nothing is reset between launches.
+  int rowdeps;
+  unsigned long long* row_cnt;
+  unsigned long long* launch_cnt;
   const int4* unit_tab;
   const int4* fix_tab;      // [fix] = {pieces, slab offset in floats (lo, hi), 0}
   float* fix_ws;
@@ -269,8 +278,13 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
       int stage = 0;
       uint32_t phase = 0;
       long long t_wait = 0, t_issue = 0;
+      unsigned long long gen = 0;   // row-dependency plans: launches of this plan before this one
+      if (params.rowdeps) {
+        if (lane == 0) gen = atomicAdd(params.launch_cnt, 1ull) / gridDim.x;
+        gen = __shfl_sync(0xffffffffu, gen, 0);
+      }
       for (int ph = 0; ph < nphases; ++ph) {
-      if (ph > 0) {
+      if (ph > 0 && !params.rowdeps) {
         // the operands of this phase are outputs of the previous one, written by other CTAs' TMA stores: wait until the
         // whole grid has passed the phase barrier, then order this (async-proxy) reader behind it
         mbar_wait(phase_bar, static_cast<uint32_t>(ph - 1) & 1u);
@@ -287,6 +301,22 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
         const uint32_t b_bytes = P.b_major ? static_cast<uint32_t>(P.b_chunks) * kChunkBytes
                                            : static_cast<uint32_t>(n_cta) * kBlockK * 4u;
         const int nsub = num_subunits(P, c);
+        if (params.rowdeps && P.dep_prob >= 0) {
+          // the A rows of this tile are the D rows of tile row m_tile of the producing problem: all of its column tiles (every
+          // epilogue warp of every CTA that stored a piece of them) must have counted themselves in for THIS launch
+          const DevProblem& Q = probs[P.dep_prob];
+          const unsigned long long want = (gen + 1ull) * static_cast<unsigned long long>(Q.n_tiles * kEpilogueWarps * kCtas);
+          const unsigned long long* cnt = params.row_cnt + Q.sig_base + c.m_tile;
+          if (lane == 0) {
+            unsigned long long seen;
+            const long long t_spin = clock64();
+            do {
+              asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(cnt) : "memory");
+            } while (seen < want && clock64() - t_spin < (1ll << 32));   // bounded: a logic error must not hang the GPU
+          }
+          __syncwarp();
+          fence_proxy_async_all();   // order the TMA (async-proxy) reads below behind the acquire
+        }
         for (int sub = 0; sub < nsub; ++sub) {
         const SubUnit su = get_subunit(P, c, sub);
         for (int sst = 0; sst < su.nst; ++sst) {
@@ -804,13 +834,23 @@ gemm_tf32_grouped_kernel(const __grid_constant__ GemmParams params) {
           fix_cnt[2] = 0u;
         }
       }
+      if (params.rowdeps && P.sig_base >= 0) {
+        // this warp's part of the tile (rows of this CTA x its columns) is in global memory: count it in for the consumers
+        if (lane == 0) {
+          tma_store_wait<0>();
+          __threadfence();
+          fence_proxy_async_all();
+          atomicAdd(params.row_cnt + P.sig_base + c.m_tile, 1ull);
+        }
+        __syncwarp();
+      }
       if (params.dbg) t_work += clock64() - t1;
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1u;
       }
     }
-    if (ph + 1 < nphases) {
+    if (ph + 1 < nphases && !params.rowdeps) {
       // Phase barrier.  Writer side: this warp's bulk stores have completed, its plain stores (ReLU bits, column-sum
       // partials, atomics) are fenced, all eight epilogue warps of the CTA have done so; then one thread takes a ticket
       // and waits until every CTA of the grid has (tickets are monotonic over launches: generation = ticket / gridDim.x).
@@ -921,6 +961,7 @@ struct mtrl_gemm_plan {
   int4 *d_unit_tab = nullptr, *d_fix_tab = nullptr;   // stream-K plans only
   float* d_fix_ws = nullptr;
   unsigned* d_fix_cnt = nullptr;
+  unsigned long long* d_row_cnt = nullptr;   // row-dependency plans: [0] launches x grid, [1 ..] per row tile arrivals
   bool streamk = false;
   ~mtrl_gemm_plan() {
     if (d_sched) cudaFree(d_sched);
@@ -929,6 +970,7 @@ struct mtrl_gemm_plan {
     if (d_fix_tab) cudaFree(d_fix_tab);
     if (d_fix_ws) cudaFree(d_fix_ws);
     if (d_fix_cnt) cudaFree(d_fix_cnt);
+    if (d_row_cnt) cudaFree(d_row_cnt);
   }
 };
 
@@ -949,7 +991,9 @@ extern "C" int mtrl_gemm_plan_create_ex(mtrl_gemm_plan_t** out, const mtrl_gemm_
   MTRL_REQUIRE(out && problems && n >= 1 && n <= kMaxProblems,
                "mtrl_gemm_plan_create: need 1..%d problems per launch, got %d", kMaxProblems, n);
   const bool streamk = (ctas_req & MTRL_GEMM_STREAMK) != 0;
-  ctas_req &= ~MTRL_GEMM_STREAMK;
+  const bool rowdeps = (ctas_req & MTRL_GEMM_ROWDEPS) != 0;
+  ctas_req &= ~(MTRL_GEMM_STREAMK | MTRL_GEMM_ROWDEPS);
+  MTRL_REQUIRE(!(streamk && rowdeps), "mtrl_gemm_plan_create_ex: stream-K and row dependencies cannot be combined");
   MTRL_REQUIRE(ctas_req >= 0 && ctas_req <= 2, "mtrl_gemm_plan_create_ex: ctas %d outside {0, 1, 2}", ctas_req);
   int dev_id = 0, sms = 148;
   cudaGetDevice(&dev_id);
@@ -1034,6 +1078,8 @@ extern "C" int mtrl_gemm_plan_create_ex(mtrl_gemm_plan_t** out, const mtrl_gemm_
     if (allow_tma_out && block_n % 32 == 0 &&
         encode_map(&P.maps[kMapsPer * i + 2], p.D, p.N, p.M, p.ldd, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B) == MTRL_OK)
       d.tma_out = 1;
+    d.dep_prob = -1;
+    d.sig_base = -1;
     d.head_dim = 0;
     d.head_w = nullptr;
     d.head_out = nullptr;
@@ -1093,6 +1139,31 @@ extern "C" int mtrl_gemm_plan_create_ex(mtrl_gemm_plan_t** out, const mtrl_gemm_
     nphases = std::max(nphases, problems[i].phase + 1);
   }
   P.nphases = nphases;
+  int row_counters = 0;
+  if (rowdeps) {
+    // who reads whose output: a problem of a later phase whose A operand is the D of an earlier problem waits per row tile
+    for (int i = 0; i < n; ++i) {
+      const mtrl_gemm_problem_t& p = problems[i];
+      for (int j = 0; j < n; ++j) {
+        const mtrl_gemm_problem_t& q = problems[j];
+        if (j == i || q.phase >= p.phase) continue;
+        MTRL_REQUIRE(p.B != q.D && (!p.B_lo || p.B_lo != q.D_lo),
+                     "row-dependency plan: problem %d reads the output of problem %d as its B operand (needs a grid barrier)", i, j);
+        if (p.A != q.D) continue;
+        MTRL_REQUIRE(q.phase == p.phase - 1 && !p.a_major && p.lda == q.ldd && p.M == q.M && p.K == q.N && P.probs[j].tma_out &&
+                         P.probs[j].k_splits == 1 && q.epilogue != MTRL_EPI_ATOMIC_ADD && (p.A_lo == nullptr || p.A_lo == q.D_lo),
+                     "row-dependency plan: problem %d cannot chain on problem %d (phase, layout, shape or epilogue)", i, j);
+        MTRL_REQUIRE(P.probs[i].dep_prob < 0, "row-dependency plan: problem %d has two producers", i);
+        P.probs[i].dep_prob = j;
+        if (P.probs[j].sig_base < 0) {
+          P.probs[j].sig_base = row_counters;
+          row_counters += P.probs[j].m_tiles;
+        }
+      }
+      MTRL_REQUIRE(p.phase == 0 || P.probs[i].dep_prob >= 0,
+                   "row-dependency plan: problem %d of phase %d reads no output of the previous phase", i, p.phase);
+    }
+  }
   const int workers = sms / ctas;
   // with phases every CTA must be resident at once (they meet at in-kernel barriers): never more workers than CTA slots
   const int nworkers = (units < workers && !streamk) ? units : workers;
@@ -1260,6 +1331,14 @@ extern "C" int mtrl_gemm_plan_create_ex(mtrl_gemm_plan_t** out, const mtrl_gemm_
     MTRL_CUDA_CHECK(cudaMalloc(&plan->d_phase_cnt, kMaxPhases * sizeof(unsigned long long)));
     MTRL_CUDA_CHECK(cudaMemset(plan->d_phase_cnt, 0, kMaxPhases * sizeof(unsigned long long)));
     P.phase_cnt = plan->d_phase_cnt;
+  }
+  if (rowdeps) {
+    const size_t bytes = (static_cast<size_t>(row_counters) + 1) * sizeof(unsigned long long);
+    MTRL_CUDA_CHECK(cudaMalloc(&plan->d_row_cnt, bytes));
+    MTRL_CUDA_CHECK(cudaMemset(plan->d_row_cnt, 0, bytes));
+    P.rowdeps = 1;
+    P.row_cnt = plan->d_row_cnt + 1;
+    P.launch_cnt = plan->d_row_cnt;
   }
   static bool attr_set = false;
   if (!attr_set) {

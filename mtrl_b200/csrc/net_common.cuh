@@ -134,11 +134,35 @@ inline mtrl_gemm_problem_t dw_problem(const float* X, int ldx, int n_in, const f
   return p;
 }
 
-inline int make_plan_plain(std::vector<mtrl_gemm_plan_t*>& dst, const std::vector<mtrl_gemm_problem_t>& probs) {
+inline int make_plan_plain(std::vector<mtrl_gemm_plan_t*>& dst, const std::vector<mtrl_gemm_problem_t>& probs, int flags = 0) {
   mtrl_gemm_plan_t* plan = nullptr;
-  MTRL_PROPAGATE(mtrl_gemm_plan_create(&plan, probs.data(), static_cast<int>(probs.size())));
+  MTRL_PROPAGATE(mtrl_gemm_plan_create_ex(&plan, probs.data(), static_cast<int>(probs.size()), flags));
   dst.push_back(plan);
   return MTRL_OK;
+}
+
+// Average duration (ms) of running the plans one after the other on the default stream: min over `reps` timed rounds after
+// one warm-up round.  Used at handle creation to choose between equivalent launch structures.
+inline int time_plans(const std::vector<mtrl_gemm_plan_t*>& plans, float* ms_out, int reps = 4) {
+  cudaEvent_t e0, e1;
+  MTRL_CUDA_CHECK(cudaEventCreate(&e0));
+  MTRL_CUDA_CHECK(cudaEventCreate(&e1));
+  float best = 1e30f;
+  int rc = MTRL_OK;
+  for (int rep = 0; rep <= reps && rc == MTRL_OK; ++rep) {
+    cudaEventRecord(e0, nullptr);
+    for (mtrl_gemm_plan_t* p : plans)
+      if (rc == MTRL_OK) rc = mtrl_gemm_plan_run(p, nullptr);
+    cudaEventRecord(e1, nullptr);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { mtrl_set_error("GEMM timing launch failed"); rc = MTRL_ERR_CUDA; }
+    float t = 0.f;
+    cudaEventElapsedTime(&t, e0, e1);
+    if (rep > 0 && t < best) best = t;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_out = best;
+  return rc;
 }
 
 // Tile-shape selection by measurement.  A launch is a static schedule of units over the SMs, so its duration is (rounds of
@@ -149,15 +173,16 @@ inline int make_plan_plain(std::vector<mtrl_gemm_plan_t*>& dst, const std::vecto
 // every candidate (CTA pairs or single CTAs) x (tile width) is built and timed once at plan creation (a few launches on the
 // real buffers: forward outputs are overwritten and gradient accumulators re-zeroed by every update) and the fastest plan
 // is kept.  MTRL_GEMM_AUTOTUNE=0 keeps the default shape; MTRL_GEMM_CTAS=1|2 restricts the candidates to one kind.
-inline int make_plan(std::vector<mtrl_gemm_plan_t*>& dst, const std::vector<mtrl_gemm_problem_t>& probs) {
+// `flags`: MTRL_GEMM_ROWDEPS for a chain of dependent layers in one launch (every candidate is built with it).
+inline int make_plan(std::vector<mtrl_gemm_plan_t*>& dst, const std::vector<mtrl_gemm_problem_t>& probs, int flags = 0) {
   const char* env = getenv("MTRL_GEMM_AUTOTUNE");
   bool wide = false;
   for (const auto& p : probs) wide = wide || p.N >= 256;
-  if ((env && env[0] == '0') || !wide) return make_plan_plain(dst, probs);
+  if ((env && env[0] == '0') || !wide) return make_plan_plain(dst, probs, flags);
   {
     // many rounds of units: the last partial round costs little and every candidate launch would take milliseconds
     mtrl_gemm_plan_t* probe = nullptr;
-    MTRL_PROPAGATE(mtrl_gemm_plan_create(&probe, probs.data(), static_cast<int>(probs.size())));
+    MTRL_PROPAGATE(mtrl_gemm_plan_create_ex(&probe, probs.data(), static_cast<int>(probs.size()), flags));
     if (mtrl_gemm_plan_units(probe) >= 6 * 74) {
       dst.push_back(probe);
       return MTRL_OK;
@@ -179,7 +204,7 @@ inline int make_plan(std::vector<mtrl_gemm_plan_t*>& dst, const std::vector<mtrl
   const int cands[4] = {0, 192, 128, 64};   // 0 = the caller's default
   for (int kind_flags : kinds) {
     const int kind = kind_flags & ~MTRL_GEMM_STREAMK;
-    if ((kind_flags & MTRL_GEMM_STREAMK) && !try_streamk) continue;
+    if ((kind_flags & MTRL_GEMM_STREAMK) && (!try_streamk || flags)) continue;
     if (force && (force[0] == '1' || force[0] == '2') && force[0] - '0' != kind) continue;
     for (int cand : cands) {
       if ((kind_flags & MTRL_GEMM_STREAMK) && cand != 0) continue;
@@ -189,7 +214,7 @@ inline int make_plan(std::vector<mtrl_gemm_plan_t*>& dst, const std::vector<mtrl
         if (cand && p.N >= 256 && p.block_n > cand) { p.block_n = cand; changed = true; }
       if (!changed) continue;
       mtrl_gemm_plan_t* plan = nullptr;
-      rc = mtrl_gemm_plan_create_ex(&plan, q.data(), static_cast<int>(q.size()), kind_flags);
+      rc = mtrl_gemm_plan_create_ex(&plan, q.data(), static_cast<int>(q.size()), kind_flags | flags);
       if (rc != MTRL_OK) break;
       if (mtrl_gemm_plan_ctas(plan) != kind) {   // an odd SM count turns pairs into single CTAs: already covered
         mtrl_gemm_plan_destroy(plan);

@@ -205,11 +205,10 @@ struct mtrl_sac {
   std::vector<mtrl_gemm_plan_t*> fwd_pi;       // [depth] critic (new params) on (pi(s), s)
   std::vector<mtrl_gemm_plan_t*> bwd_pi;       // [depth] dX only
   std::vector<mtrl_gemm_plan_t*> bwd_actor;    // [depth]
-  // Launch-bound widths: the layers of each list above as ONE phased launch (grid-wide barriers between dependent layers
-  // inside the persistent GEMM kernel, mtrl_gemm_problem_t::phase); null = layer by layer.
+  // The layers of each list above as ONE launch (make_fused_plan: row-tile dependencies for the chains, grid barriers for the
+  // backward passes with weight gradients); null = layer by layer.
   enum Fused { F_FWD = 0, F_FWD_TARGET, F_FWD_PI, F_BWD_CRITIC, F_BWD_PI, F_BWD_ACTOR, F_COUNT };
   mtrl_gemm_plan_t* fused[F_COUNT] = {};
-  bool fuse_layers = false;
   // the output heads ride in the epilogue of the last trunk layer's GEMM (mtrl_gemm_problem_t::head_w): the loss / sampling
   // kernels then read M x head_dim numbers instead of the M x W activation
   bool fused_heads = false;
@@ -350,14 +349,26 @@ void push_dw(mtrl_sac* h, std::vector<mtrl_gemm_problem_t>& dst, const float* X,
   }
 }
 
-// One phased plan out of per-layer problem lists (launch order = phase order).  Too many problems for one launch (the
-// per-owner dW problems of a sharded trunk) leaves the slot empty and the caller runs layer by layer.
-int make_fused_plan(mtrl_sac* h, int slot, const std::vector<std::vector<mtrl_gemm_problem_t>>& layers) {
+// One launch for all layers of a trunk pass, out of the per-layer problem lists (launch order = phase order).
+//   chain = true  (forward passes, the input-gradient-only backward): every layer's A operand is the previous layer's output,
+//                 so the launch is ordered by per-row-tile dependencies (MTRL_GEMM_ROWDEPS): SMs that run out of tiles of one
+//                 layer continue with the next.  Default where that pays under graph replay (same-box A/B): few row tiles and
+//                 wide layers -- one rank's share of a sharded batch (1/8 of MT50/W2048: 0.924 -> 0.899 ms per update), MT10 at
+//                 W1024 (0.526 -> 0.514) -- and not at MT10/W400 (+4 %: launches that short are cheaper than the counters) nor
+//                 at MT50 on one GPU (11 rounds of tiles per layer: nothing to fill).
+//   chain = false (backward passes with weight gradients): grid barriers between the layers, only on request.
+// MTRL_FUSE_LAYERS=0: never; =1: always, both kinds.  Too many problems for one launch (the per-owner dW problems of a sharded
+// trunk) leaves the slot empty and the caller runs layer by layer.
+int make_fused_plan(mtrl_sac* h, int slot, const std::vector<std::vector<mtrl_gemm_problem_t>>& layers, bool chain) {
   if (h->fused[slot]) {
     mtrl_gemm_plan_destroy(h->fused[slot]);
     h->fused[slot] = nullptr;
   }
-  if (!h->fuse_layers) return MTRL_OK;
+  const char* env = getenv("MTRL_FUSE_LAYERS");
+  const bool never = h->ln_mode || layers.size() < 2 || (env && env[0] == '0');
+  const bool always = env && env[0] == '1';
+  const bool by_shape = chain && h->cfg.width >= 1024 && h->cfg.max_rows <= 2048;
+  if (never || !(always || by_shape)) return MTRL_OK;
   std::vector<mtrl_gemm_problem_t> all;
   for (size_t i = 0; i < layers.size(); ++i)
     for (mtrl_gemm_problem_t p : layers[i]) {
@@ -366,7 +377,7 @@ int make_fused_plan(mtrl_sac* h, int slot, const std::vector<std::vector<mtrl_ge
     }
   if (static_cast<int>(all.size()) > MTRL_GEMM_MAX_PROBLEMS || static_cast<int>(layers.size()) > MTRL_GEMM_MAX_PHASES) return MTRL_OK;
   std::vector<mtrl_gemm_plan_t*> out;
-  MTRL_PROPAGATE(make_plan(out, all));
+  MTRL_PROPAGATE(make_plan(out, all, chain ? MTRL_GEMM_ROWDEPS : 0));
   h->fused[slot] = out[0];
   return MTRL_OK;
 }
@@ -437,9 +448,9 @@ int build_backward_plans(mtrl_sac* h) {
     all_pi.push_back(ppi);
     all_a.push_back(pa);
   }
-  MTRL_PROPAGATE(make_fused_plan(h, mtrl_sac::F_BWD_CRITIC, all_c));
-  MTRL_PROPAGATE(make_fused_plan(h, mtrl_sac::F_BWD_PI, all_pi));
-  MTRL_PROPAGATE(make_fused_plan(h, mtrl_sac::F_BWD_ACTOR, all_a));
+  MTRL_PROPAGATE(make_fused_plan(h, mtrl_sac::F_BWD_CRITIC, all_c, false));
+  MTRL_PROPAGATE(make_fused_plan(h, mtrl_sac::F_BWD_PI, all_pi, true));
+  MTRL_PROPAGATE(make_fused_plan(h, mtrl_sac::F_BWD_ACTOR, all_a, false));
   return MTRL_OK;
 }
 
@@ -493,9 +504,9 @@ int build_plans(mtrl_sac* h) {
     all_t.push_back(p);
     all_pi.push_back(q);
   }
-  MTRL_PROPAGATE(make_fused_plan(h, mtrl_sac::F_FWD, all_f));
-  MTRL_PROPAGATE(make_fused_plan(h, mtrl_sac::F_FWD_TARGET, all_t));
-  MTRL_PROPAGATE(make_fused_plan(h, mtrl_sac::F_FWD_PI, all_pi));
+  MTRL_PROPAGATE(make_fused_plan(h, mtrl_sac::F_FWD, all_f, true));
+  MTRL_PROPAGATE(make_fused_plan(h, mtrl_sac::F_FWD_TARGET, all_t, true));
+  MTRL_PROPAGATE(make_fused_plan(h, mtrl_sac::F_FWD_PI, all_pi, true));
   return build_backward_plans(h);
 }
 
@@ -867,14 +878,6 @@ extern "C" int mtrl_sac_create(mtrl_sac_t** out, const mtrl_sac_config_t* cfg, c
   h->buf = *b;
   h->ln_mode = cfg->use_layer_norm || cfg->use_skip_connections;
   {
-    // MTRL_FUSE_LAYERS=1: the layers of every trunk pass as one phased launch.  Off by default: with graph replay and
-    // programmatic dependent launch the kernel boundaries it removes are already hidden, and the in-kernel grid barrier
-    // costs as much (same-box A/B, fused vs layer by layer: MT10/W400 0.322 vs 0.319 ms, 1/8 shard of MT50/W2048 0.978 vs
-    // 0.977, MT50/W2048 unchanged) -- kept as a switch for launch-bound hosts without graph replay.
-    const char* env = getenv("MTRL_FUSE_LAYERS");
-    h->fuse_layers = !h->ln_mode && cfg->depth > 1 && env && env[0] == '1';
-  }
-  {
     // MTRL_FUSED_HEADS=0 keeps the stand-alone head kernels (which LayerNorm / skip networks and head widths the GEMM
     // epilogue does not take always use)
     const char* env = getenv("MTRL_FUSED_HEADS");
@@ -923,6 +926,7 @@ extern "C" int mtrl_sac_create(mtrl_sac_t** out, const mtrl_sac_config_t* cfg, c
       }
     }
   }
+  mtrl_pdl_auto(cfg->width <= 1024);   // the plan timings below see the launch mode the updates will use
   rc = build_plans(h);
   if (rc != MTRL_OK) { mtrl_sac_destroy(h); return rc; }
   rc = mtrl_sac_refresh_shadows(h, nullptr);

@@ -131,17 +131,21 @@ def test_relu_bits_roundtrip(cuda):
     assert torch.equal(D1, D2)
 
 
+@pytest.mark.parametrize("rows", [2304, 640])
+@pytest.mark.parametrize("flags", [0, 32])
 @pytest.mark.parametrize("ctas", [2, 1])
-def test_phased_launch_matches_layer_by_layer(cuda, ctas):
-    """Three dependent Dense layers (each reads what the previous one wrote) as ONE launch with grid-wide phase barriers
-    (`problem.phase`) vs one launch per layer: bit-identical outputs, repeatedly (a race on the barrier / the TMA-store
-    visibility would show up as a stale operand in some repetition)."""
+def test_phased_launch_matches_layer_by_layer(cuda, ctas, flags, rows):
+    """Three dependent Dense layers (each reads what the previous one wrote) as ONE launch -- with grid-wide phase barriers
+    (`problem.phase`), or with per-row-tile dependencies (MTRL_GEMM_ROWDEPS = 32: a tile of layer l + 1 starts once its rows of
+    layer l are stored, no barrier) -- vs one launch per layer: bit-identical outputs, repeatedly (a race on the barrier / the
+    counters / the TMA-store visibility would show up as a stale operand in some repetition).  640 rows: fewer tiles than SMs,
+    so most workers run ahead into the next layer and really wait on the counters."""
     import torch
 
     import gemm_cases as G
     from mtrl_b200 import _lib as L
 
-    M, W, K0 = 2304, 1024, 96
+    M, W, K0 = rows, 1024, 96
     g = torch.Generator().manual_seed(7)
     X = G.tf32_round(torch.randn(M, K0, generator=g)).cuda()
     Ws = [G.tf32_round(torch.randn(K0 if i == 0 else W, W, generator=g) * (2.0 / (K0 if i == 0 else W)) ** 0.5).cuda() for i in range(3)]
@@ -162,7 +166,7 @@ def test_phased_launch_matches_layer_by_layer(cuda, ctas):
     torch.cuda.synchronize()
     assert float(ref[2].abs().sum()) > 0
     out = [torch.zeros(M, W, device="cuda") for _ in range(3)]
-    plan = L.GemmPlan(problems(out, True), ctas=ctas)
+    plan = L.GemmPlan(problems(out, True), ctas=ctas | flags)
     for rep in range(40):
         for o in out:
             o.fill_(float("nan"))
@@ -330,3 +334,20 @@ def test_streamk_fp32x3(cuda):
     for case in (G.CASES[3], G.CASES[8], ("sk_x3_longk", 256, 384, 2048, 0, 1, 1, 128, 1)):
         rel, _, _ = G.run_case_x3(case, ctas=2 | L.GEMM_STREAMK)
         assert rel < 3e-6, f"{case[0]} fp32x3 stream-K: rel err {rel}"
+
+
+def test_rowdeps_rejects_what_needs_a_barrier(cuda):
+    """A row-dependency plan takes chains of Dense layers only: reading an earlier output as the B operand (dW of a backward
+    chain) needs the whole previous problem and is refused at plan creation."""
+    import torch
+
+    from mtrl_b200 import _lib as L
+
+    M, W = 256, 256
+    a, w, d0, d1 = (torch.zeros(M, W, device="cuda") for _ in range(4))
+    p0 = L.GemmProblem(A=a.data_ptr(), lda=W, a_major=0, B=w.data_ptr(), ldb=W, b_major=0, D=d0.data_ptr(), ldd=W, M=M, N=W, K=W,
+                       block_n=256, k_splits=1, epilogue=L.EPI_STORE, phase=0)
+    p1 = L.GemmProblem(A=a.data_ptr(), lda=W, a_major=1, B=d0.data_ptr(), ldb=W, b_major=1, D=d1.data_ptr(), ldd=W, M=W, N=W, K=M,
+                       block_n=256, k_splits=1, epilogue=L.EPI_STORE, phase=1)
+    with pytest.raises(L.MtrlError):
+        L.GemmPlan([p0, p1], ctas=2 | L.GEMM_ROWDEPS)
