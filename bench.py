@@ -221,10 +221,15 @@ def cpu_update_rate(T: int, W: int, per_task: int, budget_s: float, threads: int
 
 
 def workload_config(args) -> dict:
-    """The `config` object both arms print (same keys, so the driver can tell they measured the same workload)."""
+    """The `config` object BOTH arms print, identical key for key and value for value (it depends on the command line only), so
+    the driver can tell they measured the same workload.  What is specific to an arm goes into its `implementation` object."""
     T, W, per_task = WORKLOADS[args.workload]
+    n = max(int(args.gpus), 1)
     return {"workload": args.workload, "num_tasks": T, "width": W, "depth": 3, "num_critics": 2, "global_batch": per_task * T,
-            "per_task_batch": per_task, "obs_dim": 39 + T, "action_dim": 4, "ring_capacity_per_task": args.capacity}
+            "per_task_batch": per_task, "obs_dim": 39 + T, "action_dim": 4, "ring_capacity_per_task": args.capacity,
+            "parallelism": f"tasks sharded over {n} GPU(s), fixed global batch" if n > 1 else "single GPU",
+            "l2": "per-step working set (activations + parameters, ~%.1f GB per GPU) exceeds the 126 MB L2; no explicit flush"
+                  % ((22 * (per_task * T / n) * W * 4 + 12 * 3 * W * W * 4) / 1e9)}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -242,12 +247,12 @@ def run_reference_arm(args, out) -> None:
     dt = r.pop("_sec_per_update")
     r.pop("_n_timed")
     cfg = workload_config(args)
-    cfg["note"] = "CPU restatement of MTSAC.update + NumPy sampler (the reference itself needs jax, absent here): " + r["sample"]
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": cfg,
+        "implementation": {"note": "CPU restatement of MTSAC.update + NumPy sampler (the reference itself needs jax, absent here): " + r["sample"]},
         "cpu_baseline": r,
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -558,17 +563,15 @@ def main() -> None:
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic",
-            "config": dict(workload_config(args), **{
-                       "parallelism": (f"tasks sharded over {world} GPU(s); trunk gradients: " +
-                                       ("fused peer-memory reduce-scatter + sharded Adam + all-gather kernel (NVLink P2P, no NCCL; all-gather by "
-                                        + ("NVSwitch multicast stores, multimem.st)" if getattr(agent, "multicast", False) else "one store per peer)")
-                                        if exchange == "p2p" else "NCCL all-reduce between the phases")) if world > 1 else "single GPU",
-                       "l2": "per-step working set (activations + parameters, ~%.1f GB) exceeds the 126 MB L2; no explicit flush"
-                             % ((22 * B_local * W * 4 + 12 * 3 * W * W * 4) / 1e9),
-                       "precision": ("fp32 storage, tf32 tensor-core operands (round-to-nearest), fp32 accumulate" if args.precision == "tf32"
-                                     else "fp32 storage, every operand a (hi, lo) pair of tf32 values, three tensor-core passes per "
-                                          "k-block (3xTF32), fp32 accumulate; roofline.achieved still counts the algorithmic FLOPs once"),
-                       "launch": "one CUDA graph replay per step" if graph is not None else "stream launches"}),
+            "config": workload_config(args),
+            "implementation": {
+                "exchange": (("trunk gradients: fused peer-memory reduce-scatter + sharded Adam + all-gather kernel (NVLink P2P, no NCCL; all-gather by "
+                              + ("NVSwitch multicast stores, multimem.st)" if getattr(agent, "multicast", False) else "one store per peer)"))
+                             if exchange == "p2p" else "trunk gradients: NCCL all-reduce between the phases") if world > 1 else None,
+                "precision": ("fp32 storage, tf32 tensor-core operands (round-to-nearest), fp32 accumulate" if args.precision == "tf32"
+                              else "fp32 storage, every operand a (hi, lo) pair of tf32 values, three tensor-core passes per "
+                                   "k-block (3xTF32), fp32 accumulate; roofline.achieved still counts the algorithmic FLOPs once"),
+                "launch": "one CUDA graph replay per step" if graph is not None else "stream launches"},
             "gpu_launches": launches_per_step * args.steps,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps,
@@ -625,8 +628,8 @@ def main() -> None:
                                "fused_heads": fused_heads, "polyak_on_side_stream": polyak_side,
                                "other_classes_ms_per_step": {k: v[0] / args.steps for k, v in classes.items() if k not in alg and k != "gemm"}}
         if emulate:
-            line["config"]["emulated_shard_of"] = emulate
-            line["config"]["note"] = "PROFILING AID: rank 0's shard alone, no exchange; not a benchmark result"
+            line["implementation"]["emulated_shard_of"] = emulate
+            line["implementation"]["note"] = "PROFILING AID: rank 0's shard alone, no exchange; not a benchmark result"
         if not args.no_cpu_baseline and world == 1 and not emulate:
             r = cpu_update_rate(T, W, per_task, budget_s=float(os.environ.get("MTRL_CPU_BUDGET_S", "20")))
             r.pop("_sec_per_update", None)

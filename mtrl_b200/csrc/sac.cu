@@ -367,7 +367,9 @@ int make_fused_plan(mtrl_sac* h, int slot, const std::vector<std::vector<mtrl_ge
   const char* env = getenv("MTRL_FUSE_LAYERS");
   const bool never = h->ln_mode || layers.size() < 2 || (env && env[0] == '0');
   const bool always = env && env[0] == '1';
-  const bool by_shape = chain && h->cfg.width >= 1024 && h->cfg.max_rows <= 2048;
+  // (the two-network passes keep paying up to one rank's share of a 2-GPU split; the four-network forward pass stops at 2048 rows)
+  const int rows2 = getenv("MTRL_CHAIN_ROWS2") ? atoi(getenv("MTRL_CHAIN_ROWS2")) : 3200;
+  const bool by_shape = chain && h->cfg.width >= 1024 && h->cfg.max_rows <= (slot == mtrl_sac::F_FWD ? 2048 : rows2);
   if (never || !(always || by_shape)) return MTRL_OK;
   std::vector<mtrl_gemm_problem_t> all;
   for (size_t i = 0; i < layers.size(); ++i)

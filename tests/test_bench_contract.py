@@ -20,6 +20,14 @@ def test_reference_arm_json_line():
     assert d["higher_is_better"] is True and d["value"] > 0 and d["config"]["workload"] == "mt10_w400"
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
     assert d["e2e"] == {"value": d["value"], "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # both arms print the SAME config object: it is a function of the command line only
+    import argparse
+
+    sys.path.insert(0, ROOT)
+    import bench
+
+    assert d["config"] == bench.workload_config(argparse.Namespace(workload="mt10_w400", gpus=1, capacity=100000))
+    assert d["steps"] == 2 and d["warmup"] == 3   # (warm-up is raised to the timing rules' minimum of 3 on both arms)
 
 
 def test_non_zero_rank_of_reference_arm_prints_nothing():
