@@ -22,6 +22,10 @@ extern "C" {
 const char* mtrl_last_error(void);
 /* Library ABI version; bumped whenever a struct below changes layout. */
 int mtrl_abi_version(void);
+/* n host -> device copies on `stream` in one call (the five arrays of a batch handed to `update`, mtrl/types.py:30-35,
+ * mtrl/rl/algorithms/base.py:221): cudaMemcpyAsync semantics per entry (pinned sources must stay untouched until the stream
+ * has passed the copies; pageable sources are staged before the call returns). */
+int mtrl_memcpy_h2d_batch(int n, void* const* dst, const void* const* src, const long long* bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Grouped TF32 GEMM (tcgen05 / TMEM / TMA).  Replaces the dot_generals XLA emits for

@@ -127,6 +127,7 @@ L._EXTRA_DECLS.update({
     "mtrl_comm_error": ([_vp, C.POINTER(_i)],),
     "mtrl_comm_destroy": ([_vp], None),
     "mtrl_comm_phase_times": ([_vp, C.POINTER(C.c_double)],),
+    "mtrl_memcpy_h2d_batch": ([_i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_longlong), _vp],),
     "mtrl_comm_mc_supported": ([C.POINTER(_i)],),
     "mtrl_comm_mc_create": ([_vp, C.c_longlong, C.POINTER(_i)],),
     "mtrl_comm_mc_import": ([_vp, C.c_longlong, _i],),
@@ -663,9 +664,7 @@ class MTSAC:
             self._graph_seen.add(key)
         if entry is not None:
             src = list(data) + ([eps_c, eps_a] if eps_c is not None else [])
-            for dst, x in zip(entry["inputs"], src):
-                t = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(x, dtype=np.float32))
-                dst.copy_(t.reshape(dst.shape), non_blocking=True)
+            self._stage_inputs(entry["inputs"], src)
             entry["graph"].replay()
             logs = entry["logs"] if entry["logs"] is not None else self.logs()
         else:
@@ -684,6 +683,33 @@ class MTSAC:
             if check:
                 self._check_status()
         return self, logs
+
+    def _stage_inputs(self, staging, src) -> None:
+        """Copy one batch into the captured graph's input buffers.  Device tensors: device-to-device copies.  Host arrays (CPU
+        tensors, NumPy arrays -- what the reference's loop passes, base.py:220-221): ONE library call that enqueues all the
+        host-to-device copies (mtrl_memcpy_h2d_batch); five framework-level copies cost more CPU time than the transfer takes."""
+        dsts, srcs, sizes, keep = [], [], [], []
+        for dst, x in zip(staging, src):
+            if isinstance(x, torch.Tensor) and x.is_cuda:
+                dst.copy_(x.reshape(dst.shape), non_blocking=True)
+                continue
+            if isinstance(x, torch.Tensor):
+                t = x if (x.dtype == torch.float32 and x.is_contiguous()) else x.to(torch.float32).contiguous()
+                ptr, n = t.data_ptr(), t.numel()
+            else:
+                t = np.ascontiguousarray(x, dtype=np.float32)
+                ptr, n = t.ctypes.data, t.size
+            if n != dst.numel():
+                raise ValueError(f"batch array of {n} elements where {dst.numel()} are expected")
+            keep.append(t)
+            dsts.append(dst.data_ptr())
+            srcs.append(ptr)
+            sizes.append(4 * n)
+        if dsts:
+            k = len(dsts)
+            L.check(L.lib().mtrl_memcpy_h2d_batch(k, (_vp * k)(*dsts), (_vp * k)(*srcs), (C.c_longlong * k)(*sizes),
+                                                  _vp(L.current_stream_ptr())))
+            self._staged_src = keep   # pinned sources are read asynchronously: keep them alive until the next batch replaces them
 
     def _launch_update(self, tensors, ec, ea, B: int, global_batch: int | None) -> None:
         obs, act, nxt, done, rew = tensors
