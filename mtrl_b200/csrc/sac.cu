@@ -367,7 +367,9 @@ int make_fused_plan(mtrl_sac* h, int slot, const std::vector<std::vector<mtrl_ge
   const char* env = getenv("MTRL_FUSE_LAYERS");
   const bool never = h->ln_mode || layers.size() < 2 || (env && env[0] == '0');
   const bool always = env && env[0] == '1';
-  // (the two-network passes keep paying up to one rank's share of a 2-GPU split; the four-network forward pass stops at 2048 rows)
+  // (the two-network passes keep paying up to one rank's share of a 2-GPU split: -2.2 % per update at 3200 rows; at the full 6400
+  // rows the event-bracketed GEMM time still drops 1.7 % but the replayed step does not, 3.211 vs 3.195 ms, so the bound stays
+  // at 3200; the four-network forward pass stops at 2048 rows.  MTRL_CHAIN_ROWS2 moves the bound.)
   const int rows2 = getenv("MTRL_CHAIN_ROWS2") ? atoi(getenv("MTRL_CHAIN_ROWS2")) : 3200;
   const bool by_shape = chain && h->cfg.width >= 1024 && h->cfg.max_rows <= (slot == mtrl_sac::F_FWD ? 2048 : rows2);
   if (never || !(always || by_shape)) return MTRL_OK;
